@@ -1,0 +1,146 @@
+"""Thin object wrapper over the C ABI (one `Context` = one gpar_ctx = one device + stream)."""
+import ctypes
+import numpy as np
+from . import _ffi
+from ._ffi import as_f64, dptr
+
+
+class Context:
+    """Owns a `gpar_ctx`.  Data set through the `set_*` methods stays resident on the device across
+    evaluations, as the optimiser closures of the reference re-evaluate the objective hundreds of
+    times on fixed data (src/gp/dtc.jl:29-61)."""
+
+    def __init__(self, device=0):
+        self._lib = _ffi.load_library()
+        h = ctypes.c_void_p()
+        st = self._lib.gpar_ctx_create(int(device), ctypes.byref(h))
+        if st != _ffi.GPAR_OK:
+            raise _ffi.GparError(st, "gpar_ctx_create(device=%d) failed (no usable CUDA device?)" % device)
+        self._h = h
+        self.device = int(device)
+        self.N = self.M = self.D = 0
+        self.batch = 0
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _check(self, st):
+        if st == _ffi.GPAR_OK:
+            return
+        msg = self._lib.gpar_last_error(self._h).decode("utf-8", "replace")
+        if st == _ffi.GPAR_ERR_NOT_POSDEF:
+            raise _ffi.PosDefException(st, msg)
+        raise _ffi.GparError(st, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.gpar_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def last_timing(self):
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        self._check(self._lib.gpar_last_timing(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    # -- resident data ------------------------------------------------------------------------
+    def set_inputs(self, X):
+        """X: (N, D) records (memory image of the reference's D x N ColVecs, util.jl:16-31)."""
+        X = as_f64(np.atleast_2d(X) if np.ndim(X) > 1 else np.asarray(X, dtype=np.float64).reshape(-1, 1))
+        self._check(self._lib.gpar_set_inputs(self._h, dptr(X), X.shape[1], X.shape[0]))
+        self.N, self.D = X.shape
+
+    def set_pseudo(self, Z):
+        Z = as_f64(np.atleast_2d(Z) if np.ndim(Z) > 1 else np.asarray(Z, dtype=np.float64).reshape(-1, 1))
+        self._check(self._lib.gpar_set_pseudo(self._h, dptr(Z), Z.shape[1], Z.shape[0]))
+        self.M = Z.shape[0]
+
+    def set_times(self, t):
+        t = as_f64(np.asarray(t).ravel())
+        self._check(self._lib.gpar_set_times(self._h, dptr(t), t.shape[0]))
+        self.Nt = t.shape[0]
+
+    def set_outputs(self, y):
+        """y: (N,) or (batch, N) — sequence b contiguous."""
+        y = as_f64(y)
+        if y.ndim == 1:
+            y = y[None, :]
+        self._check(self._lib.gpar_set_outputs(self._h, dptr(y), y.shape[1], y.shape[0]))
+        self.batch, self.Ny = y.shape
+
+    def set_noise_vector(self, r):
+        if r is None:
+            self._check(self._lib.gpar_set_noise_vector(self._h, None, 0))
+            return
+        r = as_f64(np.asarray(r).ravel())
+        self._check(self._lib.gpar_set_noise_vector(self._h, dptr(r), r.shape[0]))
+
+    # -- compute --------------------------------------------------------------------------------
+    def dtc_logpdf(self, kernel, theta, vfe=False, jitter=-1.0, grad=False):
+        th = as_f64(np.asarray(theta).ravel())
+        val = ctypes.c_double()
+        g = np.zeros(3) if grad else None
+        self._check(self._lib.gpar_dtc_logpdf(self._h, int(kernel), dptr(th), int(bool(vfe)), float(jitter),
+                                              ctypes.byref(val), dptr(g)))
+        return (val.value, g) if grad else val.value
+
+    def scaled_dtc(self, k_time, k_out, theta, return_A=False):
+        th = as_f64(np.asarray(theta).ravel())
+        val = ctypes.c_double()
+        A = np.zeros((self.M, self.N), order="F") if return_A else None
+        self._check(self._lib.gpar_scaled_dtc(self._h, int(k_time), int(k_out), dptr(th), ctypes.byref(val), dptr(A)))
+        return (val.value, A) if return_A else val.value
+
+    def compute_q_u(self, k_time, k_out, params):
+        p = as_f64(np.asarray(params).ravel())
+        m_e = np.zeros(self.M)
+        Dinv = np.zeros((self.M, self.M), order="F")
+        U_u = np.zeros((self.M, self.M), order="F")
+        self._check(self._lib.gpar_compute_q_u(self._h, int(k_time), int(k_out), dptr(p), dptr(m_e), dptr(Dinv), dptr(U_u)))
+        return m_e, Dinv, U_u
+
+    def lgssm_logpdf(self, kernel, theta):
+        th = as_f64(np.atleast_2d(theta))
+        out = np.zeros(self.batch)
+        self._check(self._lib.gpar_lgssm_logpdf(self._h, int(kernel), dptr(th), th.shape[0], dptr(out)))
+        return out
+
+    def lgssm_decorrelate(self, kernel, theta):
+        th = as_f64(np.asarray(theta).ravel())
+        alpha = np.zeros((self.batch, self.Ny))
+        lml = np.zeros(self.batch)
+        self._check(self._lib.gpar_lgssm_decorrelate(self._h, int(kernel), dptr(th), dptr(alpha), dptr(lml)))
+        return lml, alpha
+
+    def lgssm_smooth(self, kernel, theta):
+        th = as_f64(np.asarray(theta).ravel())
+        mean = np.zeros((self.batch, self.Ny))
+        var = np.zeros((self.batch, self.Ny))
+        lml = np.zeros(self.batch)
+        self._check(self._lib.gpar_lgssm_smooth(self._h, int(kernel), dptr(th), dptr(mean), dptr(var), dptr(lml)))
+        return lml, mean, var
+
+    def exact_logpdf(self, k_time, k_out, theta):
+        th = as_f64(np.asarray(theta).ravel())
+        out = np.zeros(self.batch)
+        self._check(self._lib.gpar_exact_logpdf(self._h, int(k_time), int(k_out), dptr(th), th.shape[0], dptr(out)))
+        return out
+
+    def exact_posterior(self, k_time, k_out, theta, Xs):
+        th = as_f64(np.asarray(theta).ravel())
+        Xs = as_f64(np.atleast_2d(Xs) if np.ndim(Xs) > 1 else np.asarray(Xs, dtype=np.float64).reshape(-1, 1))
+        mean = np.zeros((self.batch, Xs.shape[0]))
+        var = np.zeros(Xs.shape[0])
+        self._check(self._lib.gpar_exact_posterior(self._h, int(k_time), int(k_out), dptr(th), th.shape[0],
+                                                   dptr(Xs), Xs.shape[0], dptr(mean), dptr(var)))
+        return mean, var

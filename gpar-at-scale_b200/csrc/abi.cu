@@ -1,0 +1,178 @@
+// abi.cu — extern "C" entry points of libgpar_b200.so (include/gpar_b200.h): context, resident
+// data, and the host-side orchestration of each hot-path call.  No torch types, no CPU fallback:
+// every compute entry point runs the CUDA kernels of this library or returns an error status.
+#include "common.cuh"
+#include <algorithm>
+
+int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+namespace {
+struct CallTimer {   // brackets the kernels of one compute call with events on the ctx stream
+  gpar_ctx* c;
+  explicit CallTimer(gpar_ctx* ctx) : c(ctx) { c->launches = 0; cudaEventRecord(c->ev0, c->stream); }
+  ~CallTimer() {
+    cudaEventRecord(c->ev1, c->stream);
+    if (cudaEventSynchronize(c->ev1) == cudaSuccess) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; }
+    c->last_launches = c->launches;
+  }
+};
+
+int upload(gpar_ctx* ctx, DevBuf& buf, const double* src, size_t count) {
+  CU(cudaSetDevice(ctx->device));
+  CU(buf.reserve(std::max<size_t>(count, 1) * sizeof(double)));
+  if (count) CU(cudaMemcpyAsync(buf.p, src, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+__global__ void sumsq_kernel(const double* __restrict__ y, int64_t n, double* __restrict__ part) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  // fixed chunking: block b sums a contiguous range in fixed order (deterministic)
+  int64_t per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = i0 + per < n ? i0 + per : n;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) acc = fma(y[i], y[i], acc);
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+__global__ void sum_final_kernel(const double* part, int n, double* out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = r;
+}
+}  // namespace
+
+extern "C" {
+
+int gpar_abi_version(void) { return GPAR_ABI_VERSION; }
+
+int gpar_ctx_create(int device, gpar_ctx** out) {
+  if (!out) return GPAR_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GPAR_ERR_CUDA;   // no GPU: fail loudly, no CPU fallback
+  if (device < 0 || device >= ndev) return GPAR_ERR_INVALID;
+  gpar_ctx* ctx = new gpar_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) {
+    delete ctx;
+    return GPAR_ERR_CUDA;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  *out = ctx;
+  return GPAR_OK;
+}
+
+int gpar_ctx_destroy(gpar_ctx* ctx) {
+  if (!ctx) return GPAR_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->partial, &ctx->segs,
+                    &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
+                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->blas) cublasDestroy(ctx->blas);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GPAR_OK;
+}
+
+const char* gpar_last_error(const gpar_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gpar_last_timing(const gpar_ctx* ctx, double* device_ms, int64_t* kernel_launches) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (device_ms) *device_ms = ctx->last_ms;
+  if (kernel_launches) *kernel_launches = ctx->last_launches;
+  return GPAR_OK;
+}
+
+int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!X || D < 1 || N < 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_inputs: need X != NULL, D >= 1, N >= 0");
+  CHK(upload(ctx, ctx->X, X, (size_t)N * D));
+  ctx->D = D; ctx->N = N;
+  return GPAR_OK;
+}
+int gpar_set_pseudo(gpar_ctx* ctx, const double* Z, int32_t D, int64_t M) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!Z || D < 1 || M < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_pseudo: need Z != NULL, D >= 1, M >= 1");
+  CHK(upload(ctx, ctx->Z, Z, (size_t)M * D));
+  ctx->Dz = D; ctx->M = M;
+  return GPAR_OK;
+}
+int gpar_set_times(gpar_ctx* ctx, const double* t, int64_t N) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!t || N < 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_times: need t != NULL, N >= 0");
+  CHK(upload(ctx, ctx->t, t, (size_t)N));
+  ctx->Nt = N;
+  return GPAR_OK;
+}
+int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!y || N < 0 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_outputs: need y != NULL, N >= 0, batch >= 1");
+  CHK(upload(ctx, ctx->y, y, (size_t)N * batch));
+  ctx->Ny = N; ctx->ybatch = batch;
+  return GPAR_OK;
+}
+int gpar_set_noise_vector(gpar_ctx* ctx, const double* r, int64_t N) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!r) { ctx->has_rvec = false; ctx->Nr = 0; return GPAR_OK; }
+  CHK(upload(ctx, ctx->rvec, r, (size_t)N));
+  ctx->Nr = N; ctx->has_rvec = true;
+  return GPAR_OK;
+}
+
+int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !val) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc_logpdf: theta and val must not be NULL");
+  if (kernel < GPAR_EQ || kernel > GPAR_MATERN52) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc_logpdf: unknown kernel code %d", kernel);
+  if (ctx->N < 1 || ctx->M < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc_logpdf: inputs (set_inputs) and pseudo-inputs (set_pseudo) must be set");
+  if (ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc_logpdf: X has D=%d but Z has D=%d", ctx->D, ctx->Dz);
+  if (ctx->Ny != ctx->N || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc_logpdf: outputs length %lld != N %lld", (long long)ctx->Ny, (long long)ctx->N);
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  const GpParams p = unpack_gp3(theta);
+  const bool want_grad = grad != nullptr;
+  const int64_t N = ctx->N; const int M = (int)ctx->M;
+  const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
+  const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT;
+  const size_t panel_bytes = (size_t)Npad * Mpad * sizeof(double);
+  CU(ctx->panelK.reserve(panel_bytes));
+  if (want_grad) CU(ctx->panelD.reserve(panel_bytes));
+  const int T = Mpad / GPAR_TILE;
+  int nsplit = std::max(1, (ctx->num_sms * 8) / T);
+  nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, Npad / 4));
+  CU(ctx->gpart.reserve((size_t)nsplit * 2 * Mpad * sizeof(double) + 1024 * sizeof(double)));
+  const size_t MM = (size_t)M * M;
+  CU(ctx->scal.reserve(64));
+  // G, H, g/h, yy live in kal_a (not used by this entry point otherwise)
+  CU(ctx->kal_a.reserve((2 * MM + 2 * (size_t)Mpad + 8) * sizeof(double)));
+  double* G = ctx->kal_a.as<double>(); double* H = G + MM; double* gh = H + MM; double* dyy = gh + 2 * Mpad;
+  CHK(launch_kuf_panels(ctx, kernel, want_grad, p.l, p.s, ctx->panelK.as<double>(), ctx->panelD.as<double>(),
+                        ctx->gpart.as<double>(), nsplit, Npad, Mpad));
+  CHK(launch_reduce_gh(ctx, ctx->gpart.as<double>(), nsplit, Mpad, 2, gh));
+  double* ypart = ctx->gpart.as<double>() + (size_t)nsplit * 2 * Mpad;
+  LAUNCH(ctx, sumsq_kernel, 1024, 256, 0, ctx->y.as<double>(), N, ypart);
+  LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
+  CHK(panel_syrk_run(ctx, ctx->panelK.as<double>(), ctx->panelD.as<double>(), Npad, Mpad, M, want_grad, G, H));
+  double yy = 0.0;
+  CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad);
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// common.cuh — context, device buffers and error plumbing shared by the kernels of libgpar_b200.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include "../../include/gpar_b200.h"
+
+#define GPAR_TILE 128          // M-tile of the panel layout and of the DMMA kernel
+#define GPAR_KT 32             // n-steps per pipeline stage of the DMMA kernel
+
+// Growable device buffer (never shrinks; freed with the context).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct gpar_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 148;
+  std::string err;
+  double last_ms = 0.0;
+  int64_t last_launches = 0;
+  int64_t launches = 0;      // running counter, reset at the start of every compute call
+
+  // resident data
+  DevBuf X, Z, t, y, rvec;
+  int32_t D = 0, Dz = 0, ybatch = 0;
+  int64_t N = 0, M = 0, Nt = 0, Ny = 0, Nr = 0;
+  bool has_rvec = false;
+
+  // scratch (grown on demand)
+  DevBuf panelK, panelD, partial, segs, jobs, gpart, scal, dense, tailws, info;
+  DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
+  void* pinned = nullptr; size_t pinned_cap = 0;
+};
+
+int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...);
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return gpar_fail(ctx, e_ == cudaErrorMemoryAllocation ? GPAR_ERR_NOMEM : GPAR_ERR_CUDA, \
+                       "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CB(call)                                                                          \
+  do {                                                                                    \
+    cublasStatus_t s_ = (call);                                                           \
+    if (s_ != CUBLAS_STATUS_SUCCESS)                                                      \
+      return gpar_fail(ctx, GPAR_ERR_CUDA, "%s failed: cublas status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+  } while (0)
+#define CS(call)                                                                          \
+  do {                                                                                    \
+    cusolverStatus_t s_ = (call);                                                         \
+    if (s_ != CUSOLVER_STATUS_SUCCESS)                                                    \
+      return gpar_fail(ctx, GPAR_ERR_CUDA, "%s failed: cusolver status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+  } while (0)
+#define CHK(call) do { int r_ = (call); if (r_ != GPAR_OK) return r_; } while (0)
+
+// Every kernel of this library is launched through this macro so that launches are counted.
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                                          \
+  do {                                                                                    \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+    (ctx)->launches++;                                                                    \
+    CU(cudaGetLastError());                                                               \
+  } while (0)
+
+struct GpParams { double l, var, s, sigma, noise; double dl, ds_dv, dn; };
+// exp(theta)+1e-3 (src/util.jl:36-43), s = var^2, noise = sigma^2; d*/dtheta chain factors.
+static inline GpParams unpack_gp3(const double* th) {
+  GpParams p;
+  p.l = exp(th[0]) + 1e-3; p.var = exp(th[1]) + 1e-3; p.sigma = exp(th[2]) + 1e-3;
+  p.s = p.var * p.var; p.noise = p.sigma * p.sigma;
+  p.dl = exp(th[0]); p.ds_dv = 2.0 * p.var * exp(th[1]); p.dn = 2.0 * p.sigma * exp(th[2]);
+  return p;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+// Stheno base kernels as a function of d2 = ||x - z||^2 / l^2 (src: oracle/kernels.py).
+// Returns kappa(r); *dkdl_l receives  l * d kappa / d l  (= -r kappa'(r)), used for gradients.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double base_kernel_dev(double d2, double& l_dkdl) {
+  if (KIND == GPAR_EQ) {
+    double k = exp(-0.5 * d2);
+    if (GRAD) l_dkdl = d2 * k;                      // d/dl exp(-r0^2/(2 l^2)) = r0^2/l^3 k
+    return k;
+  } else if (KIND == GPAR_MATERN12) {
+    double r = sqrt(d2), k = exp(-r);
+    if (GRAD) l_dkdl = r * k;
+    return k;
+  } else if (KIND == GPAR_MATERN32) {
+    double a = sqrt(3.0 * d2), e = exp(-a);
+    if (GRAD) l_dkdl = a * a * e;                   // -a d/da[(1+a)e^-a] = a^2 e^-a
+    return (1.0 + a) * e;
+  } else {
+    double a = sqrt(5.0 * d2), e = exp(-a);
+    if (GRAD) l_dkdl = a * a * (1.0 + a) * e * (1.0 / 3.0);  // -a d/da[(1+a+a^2/3)e^-a] = a^2(1+a)e^-a/3
+    return (1.0 + a + a * a * (1.0 / 3.0)) * e;
+  }
+}
+
+// deterministic block reduction of one double (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < nw ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in warp 0
+}
+
+// ---- module entry points (host) -----------------------------------------------------------
+// kuf_panel.cu
+int launch_kuf_panels(gpar_ctx* ctx, int kind, bool grad, double l, double s,
+                      double* panelK, double* panelD, double* gpart, int nsplit, int64_t Npad, int Mpad);
+int launch_reduce_gh(gpar_ctx* ctx, const double* gpart, int nsplit, int Mpad, int nvec, double* out);
+// panel_syrk.cu
+struct SyrkPlan { int njobs_g, njobs_h, nseg, nctas; };
+int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, int64_t Npad, int Mpad,
+                   int M, bool with_h, double* G, double* H);
+// dense_tail.cu
+int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
+             const double* G, const double* H, const double* g, const double* h, double yy,
+             double* val, double* grad);

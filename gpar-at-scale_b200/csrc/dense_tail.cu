@@ -1,0 +1,219 @@
+// dense_tail.cu — the M x M tail of the pseudo-point objectives.
+//
+// Replaces, for Sigma_y = sigma^2 I (Stheno dtc/elbo as restated at examples/dtc_example.jl:10-23)
+//   A = chol(cov(u)).U' \ (Cfu / sigma)',  Lambda = chol(A A' + I),
+//   dtc = -1/2 [N log 2pi + N log sigma^2 + logdet Lambda + y'y/sigma^2 - ||Lambda.U' \ (A y/sigma)||^2]
+// evaluated from the collapsed statistics G = Kuf Kfu, g = Kuf y, y'y, so no
+// N x M array is touched here:  B = L_u^{-1} G L_u^{-T}/sigma^2, Lambda = I + B,
+// c = L_Lambda^{-1} L_u^{-1} g / sigma^2.
+// The analytic gradient (NEW: the reference has none) uses Q = cov(u) + G/sigma^2 = L_u Lambda L_u',
+// P = Q^{-1}, w = P g, T = P + w w'/sigma^4:
+//   dF = -1/(2 sigma^2) tr(T dG) + w'dg/sigma^4 - 1/2 tr((T - cov(u)^{-1}) dcov(u)) + direct sigma^2 term
+// with dG/dlog l = H + H' from the forward-mode panel (panel_syrk.cu).  DESIGN.md has the derivation;
+// tests pin it on torch autograd of the oracle.
+// M^3-class pieces (potrf / trsm / gemm on M x M) are plain library calls (cuSOLVER / cuBLAS);
+// the element-wise and reduction pieces are kernels of this file.
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+// Kj = s kappa(Z,Z) + jitter I  (cov(u), dtc.jl:35,119);  dKu = s * l dkappa/dl
+template <int KIND>
+__global__ void kuu_kernel(const double* __restrict__ Z, int M, int D, double inv_l2, double s, double jitter,
+                           double* __restrict__ Kj, double* __restrict__ dKu) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (a >= M) return;
+  double d2 = 0.0;
+  for (int d = 0; d < D; d++) { double df = Z[(int64_t)a * D + d] - Z[(int64_t)b * D + d]; d2 = fma(df, df, d2); }
+  double ld; double k = base_kernel_dev<KIND, true>(d2 * inv_l2, ld);
+  Kj[(int64_t)a + (int64_t)b * M] = s * k + (a == b ? jitter : 0.0);
+  if (dKu) dKu[(int64_t)a + (int64_t)b * M] = s * ld;
+}
+
+__global__ void set_identity_kernel(double* A, int M) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * M) return;
+  A[i] = (i % M == i / M) ? 1.0 : 0.0;
+}
+
+// out[0] = tr(B); then B += I.   single block.
+__global__ void trace_add_identity_kernel(double* B, int M, double* out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { double v = B[(int64_t)i * M + i]; acc += v; B[(int64_t)i * M + i] = v + 1.0; }
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// out[0] = 2 sum log diag(L)
+__global__ void logdet_kernel(const double* L, int M, double* out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) acc += log(L[(int64_t)i * M + i]);
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = 2.0 * r;
+}
+
+__global__ void scale_kernel(double* v, int n, double a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= a;
+}
+
+constexpr int NTR = 20;
+// Element-wise trace sums over the M x M matrices (column-major; all symmetric except H).
+// part[block][NTR]; reduced in fixed order by trace_final_kernel.
+__global__ void __launch_bounds__(256)
+trace_kernel(int M, const double* __restrict__ P, const double* __restrict__ Kinv, const double* __restrict__ G,
+             const double* __restrict__ H, const double* __restrict__ Kj, const double* __restrict__ dKu,
+             const double* __restrict__ Cm, const double* __restrict__ w, const double* __restrict__ g,
+             const double* __restrict__ h, double* __restrict__ part) {
+  __shared__ double sh[32];
+  double acc[NTR];
+#pragma unroll
+  for (int i = 0; i < NTR; i++) acc[i] = 0.0;
+  const int64_t total = (int64_t)M * M;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int a = (int)(e % M), b = (int)(e / M);
+    double p = P[e], ki = Kinv[e], gg = G[e], hh = H[e], kj = Kj[e], dk = dKu[e];
+    double ww = w[a] * w[b];
+    acc[0] += p * hh;  acc[1] += ww * hh;
+    acc[2] += p * gg;  acc[3] += ww * gg;
+    acc[4] += p * dk;  acc[5] += ww * dk;  acc[6] += ki * dk;
+    acc[7] += p * kj;  acc[8] += ww * kj;  acc[9] += ki * kj;
+    acc[13] += ki * hh;
+    if (Cm) { double c = Cm[e]; acc[14] += c * dk; if (a == b) acc[15] += c; }
+    if (a == b) { acc[10] += p; acc[11] += ki; acc[12] += ww; }
+    if (b == 0) { acc[16] += g[a] * w[a]; acc[17] += h[a] * w[a]; }
+  }
+#pragma unroll
+  for (int i = 0; i < NTR; i++) {
+    double r = block_sum(acc[i], sh);
+    if (threadIdx.x == 0) part[(int64_t)blockIdx.x * NTR + i] = r;
+  }
+}
+__global__ void trace_final_kernel(const double* part, int nblocks, double* out) {
+  int i = threadIdx.x;
+  if (i >= NTR) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; b++) acc += part[(int64_t)b * NTR + i];
+  out[i] = acc;
+}
+
+}  // namespace
+
+static const double LOG2PI = 1.8378770664093454835606594728112;
+
+int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_in, int64_t N,
+             const double* G, const double* H, const double* g, const double* h, double yy,
+             double* val, double* grad) {
+  const int M = (int)ctx->M, D = ctx->Dz;
+  const size_t MM = (size_t)M * M;
+  const bool want_grad = grad != nullptr;
+  const bool jit_is_noise = jitter_in < 0.0;
+  const double jitter = jit_is_noise ? p.noise : jitter_in;
+  const double ip = 1.0 / p.noise;
+  cublasSetStream(ctx->blas, ctx->stream);
+  cusolverDnSetStream(ctx->solver, ctx->stream);
+
+  const int nmat = want_grad ? (vfe ? 10 : 8) : 3;
+  CU(ctx->dense.reserve(nmat * MM * sizeof(double) + 8 * (size_t)M * sizeof(double) + 64 * sizeof(double)));
+  double* base = ctx->dense.as<double>();
+  double* Kj = base;           double* Lu = base + MM;       double* Bm = base + 2 * MM;
+  double* dKu = want_grad ? base + 3 * MM : nullptr;
+  double* V = base + 4 * MM;   double* Kinv = base + 5 * MM; double* R = base + 6 * MM; double* Pm = base + 7 * MM;
+  double* Tm = base + 8 * MM;  double* Cm = base + 9 * MM;
+  double* vecs = base + nmat * MM;
+  double* cvec = vecs;         double* wvec = vecs + M;
+  double* sc = vecs + 8 * (size_t)M;   // device scalars: [0]=trB [1]=logdetLam [2]=cc [8..8+NTR) traces
+  int lwork = 0;
+  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, &lwork));
+  CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
+  CU(ctx->info.reserve(4 * sizeof(int)));
+  int* dinfo = ctx->info.as<int>();
+
+  const double inv_l2 = 1.0 / (p.l * p.l);
+  dim3 kgrid((M + 127) / 128, M);
+  const double* Zd = ctx->Z.as<double>();
+  switch (kind) {
+    case GPAR_EQ: LAUNCH(ctx, kuu_kernel<GPAR_EQ>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
+    case GPAR_MATERN12: LAUNCH(ctx, kuu_kernel<GPAR_MATERN12>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
+    case GPAR_MATERN32: LAUNCH(ctx, kuu_kernel<GPAR_MATERN32>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
+    default: LAUNCH(ctx, kuu_kernel<GPAR_MATERN52>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
+  }
+  CU(cudaMemcpyAsync(Lu, Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+  // B = L_u^{-1} G L_u^{-T} / sigma^2
+  CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  const double one = 1.0, zero = 0.0;
+  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
+  LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
+  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
+  LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
+  // c = L_Lambda^{-1} L_u^{-1} g / sigma^2
+  CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
+  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
+  LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
+  CB(cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_DEVICE));
+  cublasStatus_t st = cublasDdot(ctx->blas, M, cvec, 1, cvec, 1, sc + 2);
+  cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_HOST);
+  CB(st);
+  int trace_blocks = 0;
+  if (want_grad) {
+    // V = L_u^{-1};  Kinv = V'V;  R = L_Lambda^{-1} V;  P = R'R;  w = sigma^2 L_u^{-T} L_Lambda^{-T} c
+    LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, V, M);
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, V, M));
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, V, M, V, M, &zero, Kinv, M));
+    CU(cudaMemcpyAsync(R, V, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Bm, M, R, M));
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, R, M, R, M, &zero, Pm, M));
+    CU(cudaMemcpyAsync(wvec, cvec, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Bm, M, wvec, 1));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Lu, M, wvec, 1));
+    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, wvec, M, p.noise);
+    if (vfe) {
+      CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Kinv, M, G, M, &zero, Tm, M));
+      CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Tm, M, Kinv, M, &zero, Cm, M));
+    }
+    trace_blocks = (int)std::min<size_t>((MM + 255) / 256, (size_t)ctx->num_sms * 4);
+    CU(ctx->scal.reserve((size_t)trace_blocks * NTR * sizeof(double)));
+    LAUNCH(ctx, trace_kernel, trace_blocks, 256, 0, M, Pm, Kinv, G, H, Kj, dKu, vfe ? Cm : nullptr, wvec, g, h, ctx->scal.as<double>());
+    LAUNCH(ctx, trace_final_kernel, 1, 32, 0, ctx->scal.as<double>(), trace_blocks, sc + 8);
+  }
+  double hs[8 + NTR]; int hinfo[2];
+  CU(cudaMemcpyAsync(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hinfo, dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
+  const double trB = hs[0], logdetL = hs[1], cc = hs[2];
+  double v = -0.5 * ((double)N * LOG2PI + (double)N * log(p.noise) + logdetL + yy * ip - cc);
+  if (vfe) v += -0.5 * ((double)N * p.s * ip - trB);
+  *val = v;
+  if (want_grad) {
+    const double* t = hs + 8;
+    const double ip2 = ip * ip;
+    const double trTH = t[0] + t[1] * ip2, trTG = t[2] + t[3] * ip2;
+    const double trTKdK = t[4] + t[5] * ip2 - t[6];
+    const double trTKK = t[7] + t[8] * ip2 - t[9];
+    const double trTK = t[10] + t[12] * ip2 - t[11];
+    const double gw = t[16], hw = t[17];
+    double dlogl = -ip * trTH + ip2 * hw - 0.5 * trTKdK;
+    double ds = (-ip * trTG + ip2 * gw - 0.5 * (trTKK - jitter * trTK)) / p.s;
+    double dn = -0.5 * ((double)N * ip - yy * ip2 + 2.0 * gw * ip2 * ip - trTG * ip2);
+    if (jit_is_noise) dn += -0.5 * trTK;
+    if (vfe) {
+      const double SKinvH = t[13], SCdK = t[14], trC = t[15];
+      dlogl += -0.5 * ip * (-2.0 * SKinvH + SCdK);
+      ds += -0.5 * ((double)N * ip - (trB + jitter * ip * trC) / p.s);
+      dn += -0.5 * (-(double)N * p.s * ip2 + trB * ip);
+      if (jit_is_noise) dn += -0.5 * ip * trC;
+    }
+    grad[0] = dlogl * p.dl / p.l;
+    grad[1] = ds * p.ds_dv;
+    grad[2] = dn * p.dn;
+  }
+  return GPAR_OK;
+}

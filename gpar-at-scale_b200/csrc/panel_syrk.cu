@@ -1,0 +1,222 @@
+// panel_syrk.cu — FP64 tensor-core (DMMA) symmetric rank-N update over operand panels.
+//
+// Replaces `A * A'` (src/gp/dtc.jl:120), `B_ef * B_ef'` (gpar_scaled_inference.jl:187) — the one
+// genuine dense contraction of the path:  G = P_K^T P_K  (M x M, contraction over N; only tiles
+// i >= j are computed, N M (M+1) flops) and, for the forward-mode length-scale gradient,
+// H = P_K^T P_D (full, 2 N M^2 flops).
+//
+// sm_100a has no tcgen05 .kind::f64: FP64 tensor math is mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4,
+// and it shares the FP64 pipe with DFMA (profiles/peaks_r01.json: 37.0 TF each, 36.9 TF mixed), so
+// the design goal is a main loop that issues nothing but DMMA and fragment loads:
+//  * operands come pre-evaluated in the fragment-native panel layout (kuf_panel.cu) and are
+//    staged with ONE cp.async.bulk (TMA engine, SASS UBLKCP) of 32 KB per operand per stage into
+//    a 3-stage, mbarrier-synchronised shared-memory ring by a dedicated producer warp;
+//  * 8 consumer warps each own a 32 x 64 accumulator tile (32 DMMA per k4-step, 12 LDS.64);
+//  * persistent stream-K schedule: the (tile-job x k-block) space is cut into one contiguous
+//    range per CTA (grid = #SMs), so all 148 SMs are busy for any M; a CTA's partial tile goes to a
+//    workspace slot and a second kernel sums the slots of each job in fixed order (deterministic,
+//    no atomics) and writes G (mirrored) / H column-major.
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int STAGES = 3;
+constexpr int STAGE_DOUBLES = GPAR_KT * GPAR_TILE;        // 4096 doubles = 32 KB per operand
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+constexpr int NCONSUMER_WARPS = 8;
+constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
+constexpr size_t SMEM_BYTES = (size_t)2 * STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+
+struct Seg {      // one contiguous k-block range of one tile-job, processed by one CTA
+  int a_tile, b_tile;   // M-tile index of the A (rows) and B (cols) operand
+  int b_panel;          // 0: B from panel K (G job), 1: B from panel D (H job)
+  int kb0, kb1;         // k-block range [kb0, kb1)
+  int slot;             // partial-tile slot in the workspace
+  int job, pad;
+};
+struct Job { int a_tile, b_tile, b_panel, slot0, nslots, pad0, pad1, pad2; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok, addr = smem_u32(b);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+panel_syrk_kernel(const double* __restrict__ pK, const double* __restrict__ pD, int64_t tile_stride /*doubles per M-tile panel*/,
+                  const Seg* __restrict__ segs, const int* __restrict__ cta_seg, double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sA = reinterpret_cast<double*>(smem_raw);
+  double* sB = sA + STAGES * STAGE_DOUBLES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * STAGE_DOUBLES);
+  uint64_t* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCONSUMER_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int s0 = cta_seg[blockIdx.x], s1 = cta_seg[blockIdx.x + 1];
+  int stage = 0; uint32_t phase = 0;
+  if (warp == NCONSUMER_WARPS) {
+    if (lane == 0) {
+      for (int si = s0; si < s1; si++) {
+        const Seg sg = segs[si];
+        const double* a = pK + (int64_t)sg.a_tile * tile_stride;
+        const double* b = (sg.b_panel ? pD : pK) + (int64_t)sg.b_tile * tile_stride;
+        const bool same = (a == b);
+        for (int kb = sg.kb0; kb < sg.kb1; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_expect_tx(&full[stage], same ? STAGE_BYTES : 2 * STAGE_BYTES);
+          bulk_g2s(sA + stage * STAGE_DOUBLES, a + (int64_t)kb * STAGE_DOUBLES, STAGE_BYTES, &full[stage]);
+          if (!same) bulk_g2s(sB + stage * STAGE_DOUBLES, b + (int64_t)kb * STAGE_DOUBLES, STAGE_BYTES, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+  const int wr = warp >> 1, wc = warp & 1;     // 4 x 2 warps over the 128 x 128 tile
+  for (int si = s0; si < s1; si++) {
+    const Seg sg = segs[si];
+    const bool same = (sg.b_panel == 0 && sg.a_tile == sg.b_tile);
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kb = sg.kb0; kb < sg.kb1; kb++) {
+      mbar_wait(&full[stage], phase);
+      const double* A = sA + stage * STAGE_DOUBLES + wr * 32 * 4 + lane;
+      const double* B = (same ? sA : sB) + stage * STAGE_DOUBLES + wc * 64 * 4 + lane;
+#pragma unroll
+      for (int k4 = 0; k4 < GPAR_KT / 4; k4++) {
+        double af[4], bf[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = A[k4 * (GPAR_TILE * 4) + i * 32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) bf[j] = B[k4 * (GPAR_TILE * 4) + j * 32];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    double* out = partial + (int64_t)sg.slot * (GPAR_TILE * GPAR_TILE);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        int r = wr * 32 + i * 8 + (lane >> 2), c = wc * 64 + j * 8 + (lane & 3) * 2;
+        *reinterpret_cast<double2*>(out + r * GPAR_TILE + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+  }
+}
+
+// One block per (job, 8-row strip): fixed-order sum of the job's partial tiles, then the
+// column-major M x M write (G: lower tile + mirror; H: plain).
+__global__ void __launch_bounds__(256)
+syrk_reduce_kernel(const Job* __restrict__ jobs, const double* __restrict__ partial, int M, double* __restrict__ G, double* __restrict__ H) {
+  const Job jb = jobs[blockIdx.x];
+  const int r0 = blockIdx.y * 16;
+  for (int e = threadIdx.x; e < 16 * GPAR_TILE; e += blockDim.x) {
+    int r = r0 + e / GPAR_TILE, c = e % GPAR_TILE;
+    double v = 0.0;
+    for (int s = 0; s < jb.nslots; s++) v += partial[(int64_t)(jb.slot0 + s) * (GPAR_TILE * GPAR_TILE) + r * GPAR_TILE + c];
+    int gr = jb.a_tile * GPAR_TILE + r, gc = jb.b_tile * GPAR_TILE + c;
+    if (gr >= M || gc >= M) continue;
+    if (jb.b_panel == 0) {
+      if (jb.a_tile == jb.b_tile && c > r) continue;          // diagonal tile: keep lower, mirror
+      G[(int64_t)gr + (int64_t)gc * M] = v;
+      G[(int64_t)gc + (int64_t)gr * M] = v;
+    } else {
+      H[(int64_t)gr + (int64_t)gc * M] = v;
+    }
+  }
+}
+
+}  // namespace
+
+int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, int64_t Npad, int Mpad, int M,
+                   bool with_h, double* G, double* H) {
+  const int T = Mpad / GPAR_TILE;
+  const int64_t NBK = Npad / GPAR_KT;
+  std::vector<Job> jobs;
+  for (int i = 0; i < T; i++)
+    for (int j = 0; j <= i; j++) jobs.push_back(Job{i, j, 0, 0, 0, 0, 0, 0});
+  if (with_h)
+    for (int i = 0; i < T; i++)
+      for (int j = 0; j < T; j++) jobs.push_back(Job{i, j, 1, 0, 0, 0, 0, 0});
+  const int J = (int)jobs.size();
+  const int64_t W = (int64_t)J * NBK;
+  int C = ctx->num_sms;
+  if (W < C) C = (int)W;
+  if (C < 1) C = 1;
+  std::vector<Seg> segs;
+  std::vector<int> cta_seg(C + 1, 0);
+  for (int c = 0; c < C; c++) {
+    int64_t w0 = W * c / C, w1 = W * (c + 1) / C;
+    cta_seg[c] = (int)segs.size();
+    while (w0 < w1) {
+      int j = (int)(w0 / NBK);
+      int64_t kb0 = w0 % NBK, kb1 = std::min<int64_t>(NBK, kb0 + (w1 - w0));
+      segs.push_back(Seg{jobs[j].a_tile, jobs[j].b_tile, jobs[j].b_panel, (int)kb0, (int)kb1, 0, j, 0});
+      w0 += kb1 - kb0;
+    }
+  }
+  cta_seg[C] = (int)segs.size();
+  // slots: segments of a job are consecutive in w-order, so number them in that order
+  {
+    int slot = 0;
+    std::vector<int> order(segs.size());
+    for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (segs[a].job != segs[b].job) return segs[a].job < segs[b].job;
+      return segs[a].kb0 < segs[b].kb0; });
+    for (int idx : order) {
+      Job& jb = jobs[segs[idx].job];
+      if (jb.nslots == 0) jb.slot0 = slot;
+      jb.nslots++;
+      segs[idx].slot = slot++;
+    }
+  }
+  const size_t nseg = segs.size();
+  CU(ctx->partial.reserve(nseg * GPAR_TILE * GPAR_TILE * sizeof(double)));
+  CU(ctx->segs.reserve(nseg * sizeof(Seg) + (C + 1) * sizeof(int) + 64));
+  CU(ctx->jobs.reserve(J * sizeof(Job)));
+  Seg* dsegs = ctx->segs.as<Seg>();
+  int* dcta = reinterpret_cast<int*>(reinterpret_cast<char*>(dsegs) + nseg * sizeof(Seg));
+  CU(cudaMemcpyAsync(dsegs, segs.data(), nseg * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dcta, cta_seg.data(), (C + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), J * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope below
+  CU(cudaFuncSetAttribute(panel_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int64_t tile_stride = (Npad / 4) * (GPAR_TILE * 4);
+  LAUNCH(ctx, panel_syrk_kernel, C, NTHREADS, SMEM_BYTES, panelK, panelD, tile_stride, dsegs, dcta, ctx->partial.as<double>());
+  LAUNCH(ctx, syrk_reduce_kernel, dim3(J, GPAR_TILE / 16), 256, 0, ctx->jobs.as<Job>(), ctx->partial.as<double>(), M, G, H);
+  return GPAR_OK;
+}

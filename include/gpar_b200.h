@@ -1,0 +1,116 @@
+/* gpar_b200.h — C ABI of libgpar_b200.so: the B200 (sm_100a) GP linear-algebra hot path of
+ * GPAR-at-scale.  This is the drop-in boundary: the reference's Julia functions keep their names
+ * and signatures and `ccall` these entry points instead of calling Stheno.jl / TemporalGPs.jl /
+ * LinearAlgebra (INTEGRATION.md shows the Julia stubs; the Python ctypes binding in
+ * gpar-at-scale_b200/_ffi.py binds the same symbols with the same layouts).
+ *
+ * Conventions
+ *  - every function returns an int status (GPAR_OK = 0); no exception or abort crosses the ABI;
+ *    gpar_last_error(ctx) returns the message of the last failing call on that context.
+ *  - all pointers in the signatures are HOST pointers owned by the caller; inputs are copied to
+ *    the device by the gpar_set_* calls and stay resident across optimiser evaluations; outputs
+ *    are written synchronously (the call blocks until its stream has drained).
+ *  - matrices are column-major Float64, exactly the memory of a Julia Array{Float64}.  A Stheno
+ *    `ColVecs` (src/util.jl:16-31) is a D x N column-major matrix = N records of D contiguous
+ *    doubles; X and Z are passed in that layout.
+ *  - `theta` are the RAW optimiser parameters; the library applies exp(theta)+1e-3 and the
+ *    squaring of variances / noise itself (src/util.jl:36-55; dtc.jl:31-37).
+ *  - kernel codes: GPAR_EQ, GPAR_MATERN12, GPAR_MATERN32, GPAR_MATERN52 (Stheno EQ / Matern12 /
+ *    Matern32 / Matern52).  State-space entry points accept the three Matern kinds only.
+ *  - a context is bound to one device and is not thread-safe; distinct contexts may be used
+ *    concurrently from distinct host threads.
+ */
+#ifndef GPAR_B200_H
+#define GPAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPAR_ABI_VERSION 1
+
+enum gpar_status {
+  GPAR_OK = 0,
+  GPAR_ERR_INVALID = 1,      /* bad argument / missing data (message says which) */
+  GPAR_ERR_CUDA = 2,         /* CUDA runtime / cuBLAS / cuSOLVER failure */
+  GPAR_ERR_NOT_POSDEF = 3,   /* a Cholesky factorisation failed (Julia: PosDefException) */
+  GPAR_ERR_NOMEM = 4
+};
+
+enum gpar_kernel { GPAR_EQ = 0, GPAR_MATERN12 = 1, GPAR_MATERN32 = 2, GPAR_MATERN52 = 3 };
+
+typedef struct gpar_ctx gpar_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int gpar_abi_version(void);
+int gpar_ctx_create(int device, gpar_ctx** out);
+int gpar_ctx_destroy(gpar_ctx* ctx);
+const char* gpar_last_error(const gpar_ctx* ctx);
+/* Device time (ms, CUDA events on the context's stream) of the kernels of the last compute call,
+ * and how many of the library's own kernels it launched. */
+int gpar_last_timing(const gpar_ctx* ctx, double* device_ms, int64_t* kernel_launches);
+
+/* ---- resident data (host -> device copies) ------------------------------------------------ */
+/* ColVecs inputs, src/gp/dtc.jl:26-27, gpar_scaled_inference.jl:38-40 (to_ColVecs, util.jl:16-31) */
+int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N);
+int gpar_set_pseudo(gpar_ctx* ctx, const double* Z, int32_t D, int64_t M);
+/* time locations, ascending (callers sort: temporal_gp_inference.jl:61-66) */
+int gpar_set_times(gpar_ctx* ctx, const double* t, int64_t N);
+/* outputs: `batch` sequences of N values, sequence b at y + b*N */
+int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch);
+/* per-step observation noise R_k (the 1e10 trick, temporal_gp_inference.jl:93-97); NULL clears it */
+int gpar_set_noise_vector(gpar_ctx* ctx, const double* r, int64_t N);
+
+/* ---- pseudo-point approximation, diagonal noise: Stheno dtc / elbo --------------------------
+ * Replaces Stheno's `dtc(f(X, sigma^2), y, u)` / `elbo(...)` (restated at
+ * examples/dtc_example.jl:10-23) for f = GP(kernel(k; l, s = var^2)), theta = (log l, log var,
+ * log sigma) as unpack_gp (util.jl:36-43).  cov(u) = Kuu + jitter*I; jitter < 0 means "use
+ * sigma^2", the reference's own convention (u = gp_prior(Z, noise_sigma^2), dtc.jl:35,
+ * dtc_example.jl:46-47) and then the gradient flows through it.
+ * vfe = 0: DTC; vfe = 1: Titsias bound (DTC - 1/2 (tr(Kff)/sigma^2 - ||A||_F^2)).
+ * grad (nullable): d val / d theta[0..2].  Needs set_inputs, set_pseudo, set_outputs(batch=1). */
+int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, double jitter,
+                    double* val, double* grad);
+
+/* ---- scaled GPAR objective: compute_gpar_dtc_objective, src/gp/dtc.jl:83-128 ---------------
+ * theta = unpack_gpar parameters (util.jl:45-55).  Returns dtc (the nlml closure dtc.jl:29-47
+ * returns -dtc).  A_or_null: optional M x N column-major output of the `A` the reference also
+ * returns (dtc.jl:119,127).  Needs set_inputs, set_pseudo, set_times, set_outputs(batch=1). */
+int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc,
+                    double* A_or_null);
+
+/* compute_q_u, src/gp/gpar_scaled_inference.jl:141-196: m_e (M), inv(D) (M x M), U_u (M x M upper).
+ * params are the POSITIVE (already unpacked) values (time_l, time_var, out_l, out_var, noise_sigma),
+ * as the reference passes kernels built from opt_params (gpar_scaled_inference.jl:57-73). */
+int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], double* m_e,
+                     double* Dinv, double* U_u);
+
+/* ---- state-space approximation: TemporalGPs logpdf / decorrelate / smooth ------------------
+ * Model of create_lgssm (temporal_gp_inference.jl:15-39): GP(kernel(k; l, s = var^2)) -> SDE ->
+ * LGSSM on the resident times with noise sigma^2, or the resident noise vector if one is set.
+ * theta = unpack_gp parameters (log l, log var, log sigma).
+ * gpar_lgssm_logpdf: `batch_theta` parameter sets (theta + 3*b); with batch_theta == outputs batch,
+ *   sequence b uses theta b (independent models); with batch_theta == 1 all sequences share it.
+ *   lml: one value per sequence (temporal_gp_inference.jl:78). */
+int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml);
+/* decorrelate (dtc.jl:106,115): alpha (N x batch) and lml (batch) for every resident sequence. */
+int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], double* alpha, double* lml);
+/* smooth (temporal_gp_inference.jl:109; gpar_scaled_inference.jl:117): mean = m_s[1], var = P_s[1,1]
+ * per step and sequence (N x batch each), lml (batch, nullable). */
+int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* mean, double* var, double* lml);
+
+/* ---- exact GP / GPAR (dense), src/gp/optimized.jl ------------------------------------------
+ * ntheta = 3: GP on the resident inputs (any D) with kernel k_time (optimized.jl:28-36);
+ * ntheta = 5: GPAR kernel time_var^2 k_time(|dx_1|/time_l) + out_var^2 k_out(||dx_2:D||/out_l)
+ * (optimized.jl:132-154).  logpdf per resident output sequence. */
+int gpar_exact_logpdf(gpar_ctx* ctx, int k_time, int k_out, const double* theta, int32_t ntheta, double* lml);
+/* posterior marginals at Xs (D x Ns ColVecs): mean and variance (optimized.jl:94,236; eeg.jl:185-208) */
+int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* theta, int32_t ntheta,
+                         const double* Xs, int64_t Ns, double* mean, double* var);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPAR_B200_H */

@@ -1,0 +1,69 @@
+"""Gradient oracle (test infrastructure only): the oracle objectives restated in torch float64 so
+that autograd supplies d/d theta.  The reference has NO gradients (Zygote is imported at
+src/gp/optimized.jl:3 and temporal_gp_inference.jl:4 but never called; every optimiser is
+NelderMead), so gradient parity is pinned on autograd of these functions, cross-checked by central
+differences of the NumPy oracle in tests/."""
+import math
+import torch
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+def _unpack(theta):
+    return torch.exp(theta) + 1e-3
+
+
+def _kern(kind, d2):
+    d2 = torch.clamp(d2, min=0.0)
+    if kind == 0:
+        return torch.exp(-0.5 * d2)
+    # sqrt has an infinite derivative at 0: guard it (the kernels themselves are C^1 there)
+    r = torch.sqrt(d2 + 1e-300)
+    if kind == 1:
+        return torch.exp(-r)
+    if kind == 2:
+        a = math.sqrt(3.0) * r
+        return (1.0 + a) * torch.exp(-a)
+    a = math.sqrt(5.0) * r
+    return (1.0 + a + a * a / 3.0) * torch.exp(-a)
+
+
+def pairwise_t(kind, X, Z, l, s):
+    d2 = ((X[:, None, :] - Z[None, :, :]) ** 2).sum(-1) / (l * l)
+    return s * _kern(kind, d2)
+
+
+def dtc_diag_t(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
+    """torch twin of oracle.dtc.dtc_diag / elbo_diag with theta = (log l, log var, log sigma)
+    (unpack_gp, src/util.jl:36-43); jitter < 0 -> sigma^2 (dtc.jl:35)."""
+    l, var, sig = _unpack(theta)
+    s = var * var
+    nv = sig * sig
+    j = nv if jitter < 0 else torch.as_tensor(jitter, dtype=torch.float64)
+    Cfu = pairwise_t(kind, X, Z, l, s)
+    Kuu = pairwise_t(kind, Z, Z, l, s) + j * torch.eye(Z.shape[0], dtype=torch.float64)
+    Lu = torch.linalg.cholesky(Kuu)
+    A = torch.linalg.solve_triangular(Lu, Cfu.T, upper=False) / sig
+    m = A.shape[0]
+    Ll = torch.linalg.cholesky(A @ A.T + torch.eye(m, dtype=torch.float64))
+    delta = y / sig
+    c = torch.linalg.solve_triangular(Ll, (A @ delta)[:, None], upper=False)[:, 0]
+    n = y.shape[0]
+    tmp = n * torch.log(nv) + 2.0 * torch.log(torch.diagonal(Ll)).sum() + delta @ delta - c @ c
+    val = -(n * LOG2PI + tmp) / 2.0
+    if vfe:
+        val = val - 0.5 * (n * s / nv - (A * A).sum())
+    return val
+
+
+def dtc_diag_value_and_grad(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
+    th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    X = torch.as_tensor(X, dtype=torch.float64)
+    Z = torch.as_tensor(Z, dtype=torch.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    if Z.ndim == 1:
+        Z = Z[:, None]
+    v = dtc_diag_t(th, X, Z, torch.as_tensor(y, dtype=torch.float64), kind, vfe, jitter)
+    v.backward()
+    return float(v), th.grad.numpy().copy()
