@@ -12,16 +12,6 @@ int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...) {
 }
 
 namespace {
-struct CallTimer {   // brackets the kernels of one compute call with events on the ctx stream
-  gpar_ctx* c;
-  explicit CallTimer(gpar_ctx* ctx) : c(ctx) { c->launches = 0; cudaEventRecord(c->ev0, c->stream); }
-  ~CallTimer() {
-    cudaEventRecord(c->ev1, c->stream);
-    if (cudaEventSynchronize(c->ev1) == cudaSuccess) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; }
-    c->last_launches = c->launches;
-  }
-};
-
 int upload(gpar_ctx* ctx, DevBuf& buf, const double* src, size_t count) {
   CU(cudaSetDevice(ctx->device));
   CU(buf.reserve(std::max<size_t>(count, 1) * sizeof(double)));

@@ -57,6 +57,19 @@ struct gpar_ctx {
 
 int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...);
 
+// Brackets the KERNELS of one compute call with CUDA events on the context's stream; call stop()
+// before the device->host copies of the results so that gpar_last_timing reports device work only.
+struct CallTimer {
+  gpar_ctx* c; bool stopped = false;
+  explicit CallTimer(gpar_ctx* ctx) : c(ctx) { c->launches = 0; cudaEventRecord(c->ev0, c->stream); }
+  void stop() { if (!stopped) { cudaEventRecord(c->ev1, c->stream); stopped = true; } }
+  ~CallTimer() {
+    stop();
+    if (cudaEventSynchronize(c->ev1) == cudaSuccess) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; }
+    c->last_launches = c->launches;
+  }
+};
+
 #define CU(call)                                                                          \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
@@ -144,6 +157,12 @@ int launch_reduce_gh(gpar_ctx* ctx, const double* gpart, int nsplit, int Mpad, i
 struct SyrkPlan { int njobs_g, njobs_h, nseg, nctas; };
 int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, int64_t Npad, int Mpad,
                    int M, bool with_h, double* G, double* H);
+// kalman.cu: filter / smoother on device buffers.  hl/hs/hn: host arrays (nparam = 1 or batch) of
+// positive (l, s, noise).  table (nullable, batch == 1): per-step [Phi (D*D), K (D), HA (D), 1/sqrt(S)].
+// sums (nullable): per sequence (sum log S, sum alpha^2).
+int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
+              const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
+              double* d_table, double* d_sums);
 // dense_tail.cu
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,

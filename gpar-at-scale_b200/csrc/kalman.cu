@@ -1,0 +1,527 @@
+// kalman.cu — Matern LGSSM Kalman filter / RTS smoother as a temporally-parallel associative scan.
+//
+// Replaces TemporalGPs' sequential `logpdf(lgssm, y)` (src/gp/temporal_gp_inference.jl:78),
+// `decorrelate` (src/gp/dtc.jl:106,115; gpar_scaled_inference.jl:175,183) and `smooth`
+// (temporal_gp_inference.jl:109; gpar_scaled_inference.jl:117) for batches of sequences on one
+// time grid, each with its own (l, s, sigma^2) or all sharing one.
+//
+// Chunked three-phase scan (Sarkka & Garcia-Fernandez 2021 elements):
+//  P1 kf_chunk_summary : one thread per chunk of L steps builds the chunk's filtering element
+//     (A, b, C, eta, J) in registers with a *sequential* pass (a Kalman filter whose mean is affine in
+//     the unknown chunk-start state: Phi x0 + b) — ~2x a plain filter step instead of one full
+//     element combine per step.
+//  P2 scan_up / scan_down : warp-shuffle Kogge-Stone scan of the chunk elements with the full
+//     associative combine, 32 elements per warp, recursive over levels (32^k chunks), identity-
+//     padded per sequence so no segmentation logic is needed.
+//  P3 kf_chunk_filter : one thread per chunk restarts the ordinary filter from the scanned prefix
+//     state and emits alpha_k, sum log S_k, sum alpha_k^2 (and, for smoothing, the filtered states
+//     and the chunk's smoothing element (E, g, L), composed forward).
+//  P4 the same scan machinery over the smoothing elements in reversed time; P5 ks_backward walks
+//     each chunk backwards from the scanned smoothed state of the next chunk.
+// All state lives in registers; FP64 ALU bound: ~16-24 B of HBM traffic per step.
+#include "lgssm_math.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 4;
+__device__ constexpr double kSmoothJitter = 1e-12;   // TemporalGPs smooth: cholesky(P_pred + 1e-12 I)
+
+struct Level { double* base; int n; int P; };   // n valid elements per sequence, padded to P (multiple of 32)
+
+template <class Elem>
+__device__ __forceinline__ void load_elem(Elem& e, const double* base, int64_t fstride, int64_t off) {
+#pragma unroll
+  for (int f = 0; f < Elem::NF; f++) e.v[f] = base[f * fstride + off];
+}
+template <class Elem>
+__device__ __forceinline__ void store_elem(const Elem& e, double* base, int64_t fstride, int64_t off) {
+#pragma unroll
+  for (int f = 0; f < Elem::NF; f++) base[f * fstride + off] = e.v[f];
+}
+
+// inclusive prefix (scan order) of element idx of sequence b, from level 0 (local prefixes) and the
+// finalised level 1 (if any)
+template <class Elem>
+__device__ __forceinline__ Elem inclusive_prefix(const Level l0, const Level l1, int batch, int b, int idx) {
+  Elem loc; load_elem(loc, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + idx);
+  int T = idx >> 5;
+  if (T > 0 && l1.base) {
+    Elem up; load_elem(up, l1.base, (int64_t)batch * l1.P, (int64_t)b * l1.P + (T - 1));
+    return Elem::scan_combine(up, loc);
+  }
+  return loc;
+}
+
+// Up-sweep: one warp per 32-element tile; stores the within-tile inclusive prefixes in place and
+// the tile total to the upper level (identity beyond the valid tiles).
+template <class Elem>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+scan_up_kernel(Level cur, Level up, int batch) {
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  const int ntiles = cur.P >> 5;
+  const int tile_lim = up.base ? up.P : ntiles;
+  if (tile >= tile_lim) return;
+  if (tile >= ntiles) {   // padding slot of the upper level
+    if (lane == 0) { Elem id; id.set_identity(); store_elem(id, up.base, (int64_t)batch * up.P, (int64_t)b * up.P + tile); }
+    return;
+  }
+  Elem e; load_elem(e, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + tile * 32 + lane);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Elem o;
+#pragma unroll
+    for (int f = 0; f < Elem::NF; f++) o.v[f] = __shfl_up_sync(0xffffffffu, e.v[f], d);
+    if (lane >= d) e = Elem::scan_combine(o, e);
+  }
+  store_elem(e, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + tile * 32 + lane);
+  if (up.base && lane == 31) store_elem(e, up.base, (int64_t)batch * up.P, (int64_t)b * up.P + tile);
+}
+
+// Down-sweep for levels >= 1: element i of tile T > 0 becomes carry(T-1) o local(i).
+template <class Elem>
+__global__ void scan_down_kernel(Level cur, Level up, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= cur.P || i < 32) return;
+  Elem loc; load_elem(loc, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + i);
+  Elem c; load_elem(c, up.base, (int64_t)batch * up.P, (int64_t)b * up.P + ((i >> 5) - 1));
+  Elem r = Elem::scan_combine(c, loc);
+  store_elem(r, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + i);
+}
+
+struct SeqParams { const double *l, *s, *noise; int nparam; };
+
+// P1: chunk filtering element.
+template <int D>
+__global__ void __launch_bounds__(128)
+kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
+                        SeqParams sp, int64_t N, int L, int nC, Level l0, int batch) {
+  typedef FiltElem<D> E;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= l0.P) return;
+  E e;
+  if (c >= nC) { e.set_identity(); store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c); return; }
+  const int pb = sp.nparam == 1 ? 0 : b;
+  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
+  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
+  double* Phi = e.v; double* bv = e.v + E::OB; double* C = e.v + E::OC; double* eta = e.v + E::OE; double* J = e.v + E::OJ;
+  e.set_identity();
+  if (c == 0) {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Phi[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) C[i] = P0[i];
+  }
+  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
+  double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
+  const double* yb = y + (int64_t)b * N;
+  for (int64_t k = k0; k < k1; k++) {
+    const double tk = __ldg(t + k);
+    double A[D * D], Q[NSYM<D>], T[D * D], u[D], Cn[NSYM<D>];
+    lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
+    lgssm_q<D>(A, P0, Q);
+    matmul<D>(A, Phi, T);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Phi[i] = T[i];
+    matvec<D>(A, bv, u);
+#pragma unroll
+    for (int i = 0; i < D; i++) bv[i] = u[i];
+    asat<D>(A, C, Cn);
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) C[i] = Cn[i] + Q[i];
+    const double R = rvec ? __ldg(rvec + k) : noise;
+    const double S = C[0] + R, iS = 1.0 / S;
+    const double r = __ldg(yb + k) - bv[0];
+    double h[D], Kg[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { h[i] = Phi[i]; Kg[i] = SYM(C, i, 0) * iS; }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      eta[i] = fma(iS * r, h[i], eta[i]);
+#pragma unroll
+      for (int j = i; j < D; j++) SYM(J, i, j) = fma(iS * h[i], h[j], SYM(J, i, j));
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+      for (int j = 0; j < D; j++) Phi[i * D + j] = fma(-Kg[i], h[j], Phi[i * D + j]);
+      bv[i] = fma(Kg[i], r, bv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = i; j < D; j++) SYM(C, i, j) = fma(-S * Kg[i], Kg[j], SYM(C, i, j));
+  }
+  store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c);
+}
+
+// P3: restart the ordinary filter from the scanned prefix state.
+// part: [b][c][2] = (sum log S, sum alpha^2).  SMOOTH additionally stores the filtered states
+// fs[(f*batch + b)*N + k] (f < D + NSYM) and the chunk smoothing element at reversed index.
+template <int D, bool SMOOTH>
+__global__ void __launch_bounds__(128)
+kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
+                       SeqParams sp, int64_t N, int L, int nC, Level l0, Level l1, int batch,
+                       double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ fs, Level s0,
+                       double* __restrict__ table) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= nC) return;
+  const int pb = sp.nparam == 1 ? 0 : b;
+  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
+  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
+  double m[D], P[NSYM<D>];
+  if (c == 0) {
+#pragma unroll
+    for (int i = 0; i < D; i++) m[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) P[i] = P0[i];
+  } else {
+    FiltElem<D> pre = inclusive_prefix<FiltElem<D>>(l0, l1, batch, b, c - 1);
+#pragma unroll
+    for (int i = 0; i < D; i++) m[i] = pre.v[FiltElem<D>::OB + i];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) P[i] = pre.v[FiltElem<D>::OC + i];
+  }
+  SmoothElem<D> comp; if (SMOOTH) comp.set_identity();
+  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
+  double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
+  const double* yb = y + (int64_t)b * N;
+  double sum_logS = 0.0, sum_a2 = 0.0;
+  const int64_t kend = SMOOTH ? k1 + 1 : k1;    // one extra predict closes the chunk's last smoothing element
+  for (int64_t k = k0; k < kend; k++) {
+    double A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>];
+    if (k < N) {
+      const double tk = __ldg(t + k);
+      lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
+      lgssm_q<D>(A, P0, Q);
+      matvec<D>(A, m, mp);
+      asat<D>(A, P, Pp);
+#pragma unroll
+      for (int i = 0; i < NSYM<D>; i++) Pp[i] += Q[i];
+    }
+    if (SMOOTH && k > k0) {
+      // smoothing element of step k-1: G = P A^T (Pp + eps I)^{-1}, g = m - G mp, Ls = P - G Pp G^T
+      SmoothElem<D> el;
+      double* G = el.v; double* g = el.v + SmoothElem<D>::OG; double* Ls = el.v + SmoothElem<D>::OL;
+      if (k < N) {
+        double W[D * D];
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+          for (int j = 0; j < D; j++) { double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < D; q++) v = fma(SYM(P, i, q), A[j * D + q], v);
+            W[i * D + j] = v; }
+        solve_spd_right<D>(W, Pp, kSmoothJitter, G);
+        double u[D], R[NSYM<D>];
+        matvec<D>(G, mp, u);
+#pragma unroll
+        for (int i = 0; i < D; i++) g[i] = m[i] - u[i];
+        asat<D>(G, Pp, R);
+#pragma unroll
+        for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i] - R[i];
+      } else {   // last step of the sequence: (0, m_N, P_N)
+#pragma unroll
+        for (int i = 0; i < D * D; i++) G[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) g[i] = m[i];
+#pragma unroll
+        for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i];
+      }
+      comp = SmoothElem<D>::combine(comp, el);
+    }
+    if (k >= k1) break;
+    const double R = rvec ? __ldg(rvec + k) : noise;
+    const double S = Pp[0] + R, sq = sqrt(S);
+    const double a = (__ldg(yb + k) - mp[0]) / sq;
+    double Bv[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { Bv[i] = SYM(Pp, 0, i) / sq; m[i] = fma(Bv[i], a, mp[i]); }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = i; j < D; j++) SYM(P, i, j) = fma(-Bv[i], Bv[j], SYM(Pp, i, j));
+    sum_logS += log(S); sum_a2 = fma(a, a, sum_a2);
+    if (alpha) alpha[(int64_t)b * N + k] = a;
+    if (!SMOOTH && table) {   // shared-model step table for the affine mean scans (scaled.cu)
+      double* row = table + k * (D * D + 2 * D + 1);
+      const double iS = 1.0 / S;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        const double Kg = SYM(Pp, i, 0) * iS;
+#pragma unroll
+        for (int j = 0; j < D; j++) row[i * D + j] = fma(-Kg, A[j], A[i * D + j]);
+        row[D * D + i] = Kg;
+        row[D * D + D + i] = A[i];
+      }
+      row[D * D + 2 * D] = 1.0 / sq;
+    }
+    if (SMOOTH) {
+#pragma unroll
+      for (int i = 0; i < D; i++) fs[((int64_t)i * batch + b) * N + k] = m[i];
+#pragma unroll
+      for (int i = 0; i < NSYM<D>; i++) fs[((int64_t)(D + i) * batch + b) * N + k] = P[i];
+    }
+  }
+  part[((int64_t)b * nC + c) * 2 + 0] = sum_logS;
+  part[((int64_t)b * nC + c) * 2 + 1] = sum_a2;
+  if (SMOOTH) store_elem(comp, s0.base, (int64_t)batch * s0.P, (int64_t)b * s0.P + (nC - 1 - c));
+}
+
+// pads the reversed smoothing level 0 beyond nC with identities
+template <int D>
+__global__ void smooth_pad_kernel(Level s0, int nC, int batch) {
+  const int i = nC + blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= s0.P) return;
+  SmoothElem<D> id; id.set_identity();
+  store_elem(id, s0.base, (int64_t)batch * s0.P, (int64_t)b * s0.P + i);
+}
+
+// P5: backward walk inside each chunk from the smoothed state at the start of the next chunk.
+template <int D>
+__global__ void __launch_bounds__(128)
+ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L, int nC, Level s0, Level s1, int batch,
+                   const double* __restrict__ fs, double* __restrict__ mean, double* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= nC) return;
+  const int pb = sp.nparam == 1 ? 0 : b;
+  const double il = 1.0 / sp.l[pb], s = sp.s[pb];
+  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
+  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
+  double ms[D], Ps[NSYM<D>];
+  int64_t k = k1 - 1;
+  if (c == nC - 1) {
+#pragma unroll
+    for (int i = 0; i < D; i++) ms[i] = fs[((int64_t)i * batch + b) * N + k];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) Ps[i] = fs[((int64_t)(D + i) * batch + b) * N + k];
+    mean[(int64_t)b * N + k] = ms[0]; var[(int64_t)b * N + k] = Ps[0];
+    k--;
+  } else {
+    SmoothElem<D> suf = inclusive_prefix<SmoothElem<D>>(s0, s1, batch, b, nC - 2 - c);
+#pragma unroll
+    for (int i = 0; i < D; i++) ms[i] = suf.v[SmoothElem<D>::OG + i];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) Ps[i] = suf.v[SmoothElem<D>::OL + i];
+  }
+  for (; k >= k0; k--) {
+    double m[D], P[NSYM<D>], A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>], W[D * D], G[D * D];
+#pragma unroll
+    for (int i = 0; i < D; i++) m[i] = fs[((int64_t)i * batch + b) * N + k];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) P[i] = fs[((int64_t)(D + i) * batch + b) * N + k];
+    lgssm_transition<D>((__ldg(t + k + 1) - __ldg(t + k)) * il, A);
+    lgssm_q<D>(A, P0, Q);
+    matvec<D>(A, m, mp);
+    asat<D>(A, P, Pp);
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) Pp[i] += Q[i];
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = 0; j < D; j++) { double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) v = fma(SYM(P, i, q), A[j * D + q], v);
+        W[i * D + j] = v; }
+    solve_spd_right<D>(W, Pp, kSmoothJitter, G);
+    double dm[D], dP[NSYM<D>], u[D], R[NSYM<D>];
+#pragma unroll
+    for (int i = 0; i < D; i++) dm[i] = ms[i] - mp[i];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) dP[i] = Ps[i] - Pp[i];
+    matvec<D>(G, dm, u);
+    asat<D>(G, dP, R);
+#pragma unroll
+    for (int i = 0; i < D; i++) ms[i] = m[i] + u[i];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) Ps[i] = P[i] + R[i];
+    mean[(int64_t)b * N + k] = ms[0]; var[(int64_t)b * N + k] = Ps[0];
+  }
+}
+
+// lml[b] = -1/2 (N log 2pi + sum log S + sum alpha^2); one block per sequence, fixed order.
+__global__ void __launch_bounds__(256)
+lml_reduce_kernel(const double* __restrict__ part, int nC, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  double a0 = 0.0, a1 = 0.0;
+  for (int c = threadIdx.x; c < nC; c += blockDim.x) { a0 += part[((int64_t)b * nC + c) * 2]; a1 += part[((int64_t)b * nC + c) * 2 + 1]; }
+  double r0 = block_sum(a0, sh);
+  double r1 = block_sum(a1, sh);
+  if (threadIdx.x == 0) {
+    lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + r0 + r1);
+    if (sums) { sums[2 * b] = r0; sums[2 * b + 1] = r1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct LevelPlan { std::vector<Level> lv; size_t doubles = 0; };
+LevelPlan plan_levels(int n0, int NF, int batch) {
+  LevelPlan p;
+  int n = n0;
+  for (;;) {
+    int P = (n + 31) / 32 * 32;
+    p.lv.push_back(Level{nullptr, n, P});
+    p.doubles += (size_t)NF * batch * P;
+    if (P <= 32) break;
+    n = P / 32;
+  }
+  return p;
+}
+void bind_levels(LevelPlan& p, double* base, int NF, int batch) {
+  for (auto& l : p.lv) { l.base = base; base += (size_t)NF * batch * l.P; }
+}
+
+template <class Elem>
+int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
+  const int nl = (int)p.lv.size();
+  for (int l = 0; l < nl; l++) {
+    Level up = (l + 1 < nl) ? p.lv[l + 1] : Level{nullptr, 0, 0};
+    int tiles = up.base ? up.P : p.lv[l].P / 32;
+    dim3 grid((tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, batch);
+    LAUNCH(ctx, scan_up_kernel<Elem>, grid, WARPS_PER_BLOCK * 32, 0, p.lv[l], up, batch);
+  }
+  for (int l = nl - 2; l >= 1; l--) {
+    dim3 grid((p.lv[l].P + 127) / 128, batch);
+    LAUNCH(ctx, scan_down_kernel<Elem>, grid, 128, 0, p.lv[l], p.lv[l + 1], batch);
+  }
+  return GPAR_OK;
+}
+
+template <int D>
+int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec,
+                double* d_alpha, double* d_lml, double* d_mean, double* d_var, double* d_table, double* d_sums) {
+  const bool smooth = d_mean != nullptr;
+  const int L = 32;
+  const int nC = (int)((N + L - 1) / L);
+  LevelPlan fp = plan_levels(nC, FiltElem<D>::NF, batch);
+  LevelPlan spn = smooth ? plan_levels(nC, SmoothElem<D>::NF, batch) : LevelPlan{};
+  const size_t part_doubles = (size_t)batch * nC * 2;
+  const size_t fs_doubles = smooth ? (size_t)(D + NSYM<D>) * batch * N : 0;
+  CU(ctx->kal_a.reserve((fp.doubles + spn.doubles + part_doubles) * sizeof(double)));
+  if (smooth) CU(ctx->kal_b.reserve(fs_doubles * sizeof(double)));
+  double* base = ctx->kal_a.as<double>();
+  bind_levels(fp, base, FiltElem<D>::NF, batch);
+  if (smooth) bind_levels(spn, base + fp.doubles, SmoothElem<D>::NF, batch);
+  double* part = base + fp.doubles + spn.doubles;
+  double* fs = smooth ? ctx->kal_b.as<double>() : nullptr;
+  const Level none{nullptr, 0, 0};
+  const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
+  dim3 g1((f0.P + 127) / 128, batch);
+  LAUNCH(ctx, kf_chunk_summary_kernel<D>, g1, 128, 0, t, y, rvec, sp, N, L, nC, f0, batch);
+  CHK(run_scan<FiltElem<D>>(ctx, fp, batch));
+  dim3 g3((nC + 127) / 128, batch);
+  if (smooth) {
+    const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
+    LAUNCH(ctx, (kf_chunk_filter_kernel<D, true>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, d_alpha, part, fs, s0, (double*)nullptr);
+    if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
+    CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
+    LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, d_mean, d_var);
+  } else {
+    LAUNCH(ctx, (kf_chunk_filter_kernel<D, false>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, d_alpha, part, fs, none, d_table);
+  }
+  LAUNCH(ctx, lml_reduce_kernel, batch, 256, 0, part, nC, N, d_lml, d_sums);
+  return GPAR_OK;
+}
+
+}  // namespace
+
+// Device-level entry used by the ABI functions below and by the scaled-GPAR path.
+// params: host arrays (nparam = 1 or batch) of positive (l, s, noise).
+int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
+              const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
+              double* d_table, double* d_sums) {
+  if (N < 1 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: need at least one time step and one sequence");
+  if (d_table && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
+  CU(ctx->kal_c.reserve((size_t)3 * nparam * sizeof(double)));
+  double* dp = ctx->kal_c.as<double>();
+  CU(cudaMemcpyAsync(dp, hl, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp + nparam, hs, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp + 2 * nparam, hn, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SeqParams sp{dp, dp + nparam, dp + 2 * nparam, nparam};
+  switch (kind) {
+    case GPAR_MATERN12: return lgssm_run_d<1>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
+    case GPAR_MATERN32: return lgssm_run_d<2>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
+    case GPAR_MATERN52: return lgssm_run_d<3>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "kernel code %d has no state-space form (use Matern12/32/52)", kind);
+  }
+}
+
+namespace {
+int check_seq(gpar_ctx* ctx, const char* who) {
+  if (ctx->Nt < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: times not set (gpar_set_times)", who);
+  if (ctx->ybatch < 1 || ctx->Ny != ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: outputs length %lld != number of times %lld", who, (long long)ctx->Ny, (long long)ctx->Nt);
+  if (ctx->has_rvec && ctx->Nr != ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: noise vector length %lld != number of times %lld", who, (long long)ctx->Nr, (long long)ctx->Nt);
+  return GPAR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !lml) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: theta and lml must not be NULL");
+  CHK(check_seq(ctx, "lgssm_logpdf"));
+  const int batch = ctx->ybatch;
+  if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: batch_theta=%d must be 1 or the outputs batch %d", batch_theta, batch);
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
+  for (int b = 0; b < batch_theta; b++) { GpParams p = unpack_gp3(theta + 3 * b); hl[b] = p.l; hs[b] = p.s; hn[b] = p.noise; }
+  CU(ctx->kal_d.reserve((size_t)batch * sizeof(double)));
+  CHK(lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
+                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr));
+  timer.stop();
+  CU(cudaMemcpyAsync(lml, ctx->kal_d.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], double* alpha, double* lml) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !alpha) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_decorrelate: theta and alpha must not be NULL");
+  CHK(check_seq(ctx, "lgssm_decorrelate"));
+  const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  GpParams p = unpack_gp3(theta);
+  CU(ctx->kal_d.reserve(((size_t)batch * N + batch) * sizeof(double)));
+  double* d_alpha = ctx->kal_d.as<double>(); double* d_lml = d_alpha + (size_t)batch * N;
+  CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml, nullptr, nullptr, nullptr, nullptr));
+  timer.stop();
+  CU(cudaMemcpyAsync(alpha, d_alpha, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (lml) CU(cudaMemcpyAsync(lml, d_lml, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* mean, double* var, double* lml) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !mean || !var) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_smooth: theta, mean and var must not be NULL");
+  CHK(check_seq(ctx, "lgssm_smooth"));
+  const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  GpParams p = unpack_gp3(theta);
+  CU(ctx->kal_d.reserve((2 * (size_t)batch * N + batch) * sizeof(double)));
+  double* d_mean = ctx->kal_d.as<double>(); double* d_var = d_mean + (size_t)batch * N; double* d_lml = d_var + (size_t)batch * N;
+  CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, d_lml, d_mean, d_var, nullptr, nullptr));
+  timer.stop();
+  CU(cudaMemcpyAsync(mean, d_mean, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(var, d_var, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (lml) CU(cudaMemcpyAsync(lml, d_lml, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+}  // extern "C"

@@ -4,9 +4,6 @@
 extern "C" {
 int gpar_scaled_dtc(gpar_ctx* ctx, int, int, const double*, double*, double*) { NOTYET("gpar_scaled_dtc"); }
 int gpar_compute_q_u(gpar_ctx* ctx, int, int, const double*, double*, double*, double*) { NOTYET("gpar_compute_q_u"); }
-int gpar_lgssm_logpdf(gpar_ctx* ctx, int, const double*, int32_t, double*) { NOTYET("gpar_lgssm_logpdf"); }
-int gpar_lgssm_decorrelate(gpar_ctx* ctx, int, const double*, double*, double*) { NOTYET("gpar_lgssm_decorrelate"); }
-int gpar_lgssm_smooth(gpar_ctx* ctx, int, const double*, double*, double*, double*) { NOTYET("gpar_lgssm_smooth"); }
 int gpar_exact_logpdf(gpar_ctx* ctx, int, int, const double*, int32_t, double*) { NOTYET("gpar_exact_logpdf"); }
 int gpar_exact_posterior(gpar_ctx* ctx, int, int, const double*, int32_t, const double*, int64_t, double*, double*) { NOTYET("gpar_exact_posterior"); }
 }

@@ -66,4 +66,4 @@ def dtc_diag_value_and_grad(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
         Z = Z[:, None]
     v = dtc_diag_t(th, X, Z, torch.as_tensor(y, dtype=torch.float64), kind, vfe, jitter)
     v.backward()
-    return float(v), th.grad.numpy().copy()
+    return float(v.detach()), th.grad.numpy().copy()
