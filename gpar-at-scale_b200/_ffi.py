@@ -24,6 +24,7 @@ SIGNATURES = {
     "gpar_ctx_destroy": (ctypes.c_int, [_c_void_p]),
     "gpar_last_error": (ctypes.c_char_p, [_c_void_p]),
     "gpar_last_timing": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
+    "gpar_last_profile": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32]),
     "gpar_set_inputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_pseudo": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_times": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),

@@ -53,6 +53,12 @@ class Context:
         self._check(self._lib.gpar_last_timing(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def last_profile(self):
+        """(producer_ms, dmma_syrk_kernel_ms, tail_ms) of the last pseudo-point call."""
+        out = np.zeros(3)
+        self._check(self._lib.gpar_last_profile(self._h, dptr(out), 3))
+        return tuple(out.tolist())
+
     # -- resident data ------------------------------------------------------------------------
     def set_inputs(self, X):
         """X: (N, D) records (memory image of the reference's D x N ColVecs, util.jl:16-31)."""

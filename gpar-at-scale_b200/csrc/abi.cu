@@ -54,6 +54,8 @@ int gpar_ctx_create(int device, gpar_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[0]) != cudaSuccess || cudaEventCreate(&ctx->pev[1]) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess ||
       cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) {
     delete ctx;
     return GPAR_ERR_CUDA;
@@ -76,6 +78,7 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (ctx->blas) cublasDestroy(ctx->blas);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GPAR_OK;
@@ -87,6 +90,17 @@ int gpar_last_timing(const gpar_ctx* ctx, double* device_ms, int64_t* kernel_lau
   if (!ctx) return GPAR_ERR_INVALID;
   if (device_ms) *device_ms = ctx->last_ms;
   if (kernel_launches) *kernel_launches = ctx->last_launches;
+  return GPAR_OK;
+}
+
+int gpar_last_profile(const gpar_ctx* ctx, double* phase_ms, int32_t n) {
+  if (!ctx || !phase_ms || n < 3) return GPAR_ERR_INVALID;
+  for (int i = 0; i < n; i++) phase_ms[i] = 0.0;
+  if (!ctx->phase_valid) return GPAR_OK;
+  float a = 0, b = 0;
+  if (cudaEventElapsedTime(&a, ctx->ev0, ctx->pev[0]) != cudaSuccess) return GPAR_OK;
+  if (cudaEventElapsedTime(&b, ctx->pev[1], ctx->pev[2]) != cudaSuccess) return GPAR_OK;
+  phase_ms[0] = a; phase_ms[1] = b; phase_ms[2] = ctx->last_ms - a - b;
   return GPAR_OK;
 }
 
@@ -158,7 +172,9 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   double* ypart = ctx->gpart.as<double>() + (size_t)nsplit * 2 * Mpad;
   LAUNCH(ctx, sumsq_kernel, 1024, 256, 0, ctx->y.as<double>(), N, ypart);
   LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
+  cudaEventRecord(ctx->pev[0], ctx->stream);
   CHK(panel_syrk_run(ctx, ctx->panelK.as<double>(), ctx->panelD.as<double>(), Npad, Mpad, M, want_grad, G, H));
+  ctx->phase_valid = true;
   double yy = 0.0;
   CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

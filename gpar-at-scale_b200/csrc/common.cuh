@@ -37,6 +37,8 @@ struct gpar_ctx {
   cublasHandle_t blas = nullptr;
   cusolverDnHandle_t solver = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};   // phase marks: producers done, main kernel start/end
+  bool phase_valid = false;
   int num_sms = 148;
   std::string err;
   double last_ms = 0.0;

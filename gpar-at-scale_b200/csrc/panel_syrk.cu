@@ -216,7 +216,9 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope below
   CU(cudaFuncSetAttribute(panel_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int64_t tile_stride = (Npad / 4) * (GPAR_TILE * 4);
+  cudaEventRecord(ctx->pev[1], ctx->stream);
   LAUNCH(ctx, panel_syrk_kernel, C, NTHREADS, SMEM_BYTES, panelK, panelD, tile_stride, dsegs, dcta, ctx->partial.as<double>());
+  cudaEventRecord(ctx->pev[2], ctx->stream);
   LAUNCH(ctx, syrk_reduce_kernel, dim3(J, GPAR_TILE / 16), 256, 0, ctx->jobs.as<Job>(), ctx->partial.as<double>(), M, G, H);
   return GPAR_OK;
 }

@@ -52,6 +52,11 @@ const char* gpar_last_error(const gpar_ctx* ctx);
  * and how many of the library's own kernels it launched. */
 int gpar_last_timing(const gpar_ctx* ctx, double* device_ms, int64_t* kernel_launches);
 
+/* Device time of the phases of the last pseudo-point call (gpar_dtc_logpdf / gpar_scaled_dtc /
+ * gpar_compute_q_u): phase_ms[0] = panel producers (Kuf evaluation, whitening), [1] = the DMMA
+ * panel-SYRK kernel alone, [2] = everything after it (partial-tile reduction, M x M tail). n >= 3. */
+int gpar_last_profile(const gpar_ctx* ctx, double* phase_ms, int32_t n);
+
 /* ---- resident data (host -> device copies) ------------------------------------------------ */
 /* ColVecs inputs, src/gp/dtc.jl:26-27, gpar_scaled_inference.jl:38-40 (to_ColVecs, util.jl:16-31) */
 int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N);
