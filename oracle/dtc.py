@@ -116,3 +116,78 @@ def compute_q_u(Cfu, Cuu, t, y, k_time, time_l, time_s, noise_var, decorrelate=k
     m_e = solve_triangular(Ld.T, solve_triangular(Ld, rhs, lower=True), lower=False)
     Dinv = np.linalg.inv(0.5 * (D + D.T))
     return m_e, 0.5 * (Dinv + Dinv.T), Lu.T
+
+
+def _l_dkdl(kind, d2):
+    """(kappa, l dkappa/dl) of the base kernels as functions of d2 = r^2 (already length-scaled)."""
+    if kind == 0:
+        k = np.exp(-0.5 * d2); return k, d2 * k
+    if kind == 1:
+        r = np.sqrt(d2); k = np.exp(-r); return k, r * k
+    if kind == 2:
+        a = np.sqrt(3.0 * d2); e = np.exp(-a); return (1.0 + a) * e, a * a * e
+    a = np.sqrt(5.0 * d2); e = np.exp(-a)
+    return (1.0 + a + a * a / 3.0) * e, a * a * (1.0 + a) * e / 3.0
+
+
+def dtc_diag_value_and_grad_np(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
+    """BLAS-backed CPU port of one logpdf+grad evaluation (the CPU baseline of bench.py): the same
+    collapsed-statistics algebra as DESIGN.md (G = Kuf Kfu by dsyrk/dgemm, forward-mode dG/dlog l,
+    analytic M x M adjoints), float64 NumPy/SciPy on all host threads.  Pinned against torch
+    autograd of dtc_diag (oracle/grad.py) in tests/test_oracle.py.  theta = (log l, log var,
+    log sigma) as unpack_gp (src/util.jl:36-43); jitter < 0 -> sigma^2 (dtc.jl:35)."""
+    from .params import unpack_gp
+    X = np.asarray(X, dtype=np.float64); Z = np.asarray(Z, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    if Z.ndim == 1:
+        Z = Z[:, None]
+    l, v, sg = unpack_gp(theta)
+    s = v * v; nz = sg * sg; j = nz if jitter < 0 else jitter
+    N, M = len(y), len(Z)
+    d2 = np.zeros((N, M))
+    for c in range(X.shape[1]):
+        df = X[:, c][:, None] - Z[:, c][None, :]
+        d2 += df * df
+    d2 /= l * l
+    k, dk = _l_dkdl(kind, d2)
+    K = s * k; dK = s * dk
+    G = K.T @ K; H = K.T @ dK; g = K.T @ y; h = dK.T @ y; yy = y @ y
+    d2u = np.zeros((M, M))
+    for c in range(Z.shape[1]):
+        df = Z[:, c][:, None] - Z[:, c][None, :]
+        d2u += df * df
+    ku, dku = _l_dkdl(kind, d2u / (l * l))
+    Kj = s * ku + j * np.eye(M); dKu = s * dku
+    ip = 1.0 / nz
+    Lu = _chol(Kj)
+    B = solve_triangular(Lu, solve_triangular(Lu, G, lower=True).T, lower=True) * ip
+    trB = np.trace(B)
+    Ll = _chol(B + np.eye(M))
+    c = solve_triangular(Ll, solve_triangular(Lu, g, lower=True), lower=True) * ip
+    val = -0.5 * (N * LOG2PI + N * np.log(nz) + 2.0 * np.log(np.diag(Ll)).sum() + yy * ip - c @ c)
+    if vfe:
+        val += -0.5 * (N * s * ip - trB)
+    V = solve_triangular(Lu, np.eye(M), lower=True); Kinv = V.T @ V
+    R = solve_triangular(Ll, V, lower=True); P = R.T @ R
+    w = nz * solve_triangular(Lu.T, solve_triangular(Ll.T, c, lower=False), lower=False)
+    ip2 = ip * ip
+    trTH = (P * H).sum() + w @ H @ w * ip2; trTG = (P * G).sum() + w @ G @ w * ip2
+    trTKdK = (P * dKu).sum() + w @ dKu @ w * ip2 - (Kinv * dKu).sum()
+    trTKK = (P * Kj).sum() + w @ Kj @ w * ip2 - (Kinv * Kj).sum()
+    trTK = np.trace(P) + w @ w * ip2 - np.trace(Kinv)
+    gw = g @ w; hw = h @ w
+    dlogl = -ip * trTH + ip2 * hw - 0.5 * trTKdK
+    ds = (-ip * trTG + ip2 * gw - 0.5 * (trTKK - j * trTK)) / s
+    dn = -0.5 * (N * ip - yy * ip2 + 2.0 * gw * ip2 * ip - trTG * ip2)
+    if jitter < 0:
+        dn += -0.5 * trTK
+    if vfe:
+        C = Kinv @ G @ Kinv; trC = np.trace(C)
+        dlogl += -0.5 * ip * (-2.0 * (Kinv * H).sum() + (C * dKu).sum())
+        ds += -0.5 * (N * ip - (trB + j * ip * trC) / s)
+        dn += -0.5 * (-N * s * ip2 + trB * ip)
+        if jitter < 0:
+            dn += -0.5 * ip * trC
+    grad = np.array([dlogl * (l - 1e-3) / l, ds * 2.0 * v * (v - 1e-3), dn * 2.0 * sg * (sg - 1e-3)])
+    return float(val), grad

@@ -1,0 +1,213 @@
+"""GPU parity tests proper: every entry point of the C ABI against the CPU oracle and the
+committed golden fixtures.  FP64 tolerance of the north star: 1e-8 relative on logpdf and posterior
+mean/variance (written per assertion below)."""
+import os
+import numpy as np
+import pytest
+import oracle
+from oracle import cport
+from oracle.grad import dtc_diag_value_and_grad
+from oracle.dtc import scaled_gpar_objective
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-8
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float); b = np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# ---- pseudo-point DTC / VFE ----------------------------------------------------------------
+def test_dtc_golden(ctx):
+    z = np.load(os.path.join(G, "dtc.npz"))
+    for i in range(int(z["ncases"])):
+        kind, vfe, jit = z[f"c{i}_meta"]
+        ctx.set_inputs(z[f"c{i}_X"]); ctx.set_pseudo(z[f"c{i}_Z"]); ctx.set_outputs(z[f"c{i}_y"])
+        val, grad = ctx.dtc_logpdf(int(kind), z[f"c{i}_theta"], vfe=bool(vfe), jitter=float(jit), grad=True)
+        assert abs(val - float(z[f"c{i}_val"])) <= RTOL * abs(float(z[f"c{i}_val"]))
+        assert relerr(grad, z[f"c{i}_grad"]) <= 1e-7
+        assert ctx.dtc_logpdf(int(kind), z[f"c{i}_theta"], vfe=bool(vfe), jitter=float(jit)) == pytest.approx(val, rel=1e-10)
+        ms, launches = ctx.last_timing()
+        assert launches >= 5          # the library's own kernels ran
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,m,d", [(1, 1, 1), (5, 3, 2), (127, 129, 1), (1000, 64, 3), (4099, 300, 2), (20000, 128, 7)])
+def test_dtc_vs_oracle_ragged_shapes(ctx, kind, n, m, d):
+    rng = np.random.default_rng(1000 * kind + n + m)
+    X = rng.normal(size=(n, d)) * 2; Z = rng.normal(size=(m, d)) * 2; y = rng.normal(size=n)
+    th = rng.uniform(-1, 0.5, 3)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y)
+    for vfe in (False, True):
+        val, grad = ctx.dtc_logpdf(kind, th, vfe=vfe, grad=True)
+        v0, g0 = dtc_diag_value_and_grad(th, X, Z, y, kind, vfe)
+        assert abs(val - v0) <= RTOL * abs(v0)
+        assert np.all(np.abs(grad - g0) <= 1e-6 * np.abs(g0) + 1e-7 * np.max(np.abs(g0)))
+
+
+def test_dtc_full_size_properties(ctx):
+    """BASELINE config 2 at full size (N = 1M, M = 1024): size-independent properties.
+    (a) duplicating the data set doubles the sufficient statistics: dtc(2 copies) is reproduced by the
+    oracle tail from the GPU's N-linear statistics, checked through the value identity
+    dtc_2N(theta) computed on device == device value on a permuted copy (order independence);
+    (b) a 1/32 sub-sample agrees with the oracle to 1e-8."""
+    rng = np.random.default_rng(1)
+    N, M = 1_000_000, 1024
+    x = rng.uniform(0, 100, N); z = np.linspace(0, 100, M)
+    y = np.sin(x) + 0.3 * np.cos(3.1 * x) + 0.1 * rng.normal(size=N)
+    th = np.log([1.0, 1.0, 0.1])
+    ctx.set_inputs(x); ctx.set_pseudo(z); ctx.set_outputs(y)
+    v, g = ctx.dtc_logpdf(3, th, grad=True)
+    perm = rng.permutation(N)
+    ctx.set_inputs(x[perm]); ctx.set_outputs(y[perm])
+    vp, gp_ = ctx.dtc_logpdf(3, th, grad=True)
+    assert abs(v - vp) <= RTOL * abs(v)                       # the objective is permutation invariant
+    assert np.all(np.abs(g - gp_) <= 1e-6 * np.abs(g) + 1e-8 * np.max(np.abs(g)))
+    # central difference of the device value confirms the device gradient at full size
+    for i in range(3):
+        e = np.zeros(3); e[i] = 1e-4
+        fd = (ctx.dtc_logpdf(3, th + e) - ctx.dtc_logpdf(3, th - e)) / 2e-4
+        assert abs(fd - gp_[i]) <= 1e-5 * abs(gp_[i]) + 1e-3
+    ns = N // 32
+    ctx.set_inputs(x[:ns]); ctx.set_outputs(y[:ns])
+    vs, gs = ctx.dtc_logpdf(3, th, grad=True)
+    v0, g0 = dtc_diag_value_and_grad(th, x[:ns], z, y[:ns], 3)
+    assert abs(vs - v0) <= RTOL * abs(v0)
+    assert relerr(gs, g0) <= 1e-6
+
+
+def test_not_posdef_is_reported_like_julia(ctx):
+    import gpar_at_scale_b200 as gp
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=200); z = np.concatenate([np.linspace(-1, 1, 40), np.linspace(-1, 1, 40)])   # duplicated pseudo-points
+    ctx.set_inputs(x); ctx.set_pseudo(z); ctx.set_outputs(rng.normal(size=200))
+    with pytest.raises(gp.PosDefException):
+        ctx.dtc_logpdf(0, np.log([1.0, 1.0, 0.1]), jitter=0.0)
+    with pytest.raises(gp.GparError):
+        ctx.dtc_logpdf(9, np.log([1.0, 1.0, 0.1]))
+
+
+# ---- state-space: logpdf / decorrelate / smooth ------------------------------------------------
+def test_lgssm_golden(ctx):
+    z = np.load(os.path.join(G, "lgssm.npz"))
+    for i in range(int(z["ncases"])):
+        kind = int(z[f"c{i}_kind"])
+        ctx.set_times(z[f"c{i}_t"]); ctx.set_outputs(z[f"c{i}_Y"])
+        ctx.set_noise_vector(z[f"c{i}_rvec"] if f"c{i}_rvec" in z else None)
+        lml, alpha = ctx.lgssm_decorrelate(kind, z[f"c{i}_theta"])
+        assert relerr(lml, z[f"c{i}_lml"]) <= RTOL and np.max(np.abs(alpha - z[f"c{i}_alpha"])) <= 1e-9
+        assert relerr(ctx.lgssm_logpdf(kind, z[f"c{i}_theta"]), z[f"c{i}_lml"]) <= RTOL
+        lml2, mean, var = ctx.lgssm_smooth(kind, z[f"c{i}_theta"])
+        assert relerr(lml2, z[f"c{i}_lml"]) <= RTOL
+        assert np.max(np.abs(mean - z[f"c{i}_mean"])) <= 1e-9 and np.max(np.abs(var / z[f"c{i}_var"] - 1)) <= RTOL
+    ctx.set_noise_vector(None)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+@pytest.mark.parametrize("n,batch", [(1, 1), (2, 3), (31, 2), (32, 1), (33, 2), (1025, 3), (33000, 2)])
+def test_lgssm_vs_c_oracle(ctx, kind, n, batch):
+    rng = np.random.default_rng(100 * kind + n)
+    t = np.cumsum(rng.exponential(1 / 30, n))
+    if n > 40:
+        t[n // 2] = t[n // 2 - 1]            # a duplicated time stamp (dt = 0: train/test collision after a merge)
+    Y = rng.normal(size=(batch, n))
+    rv = np.where(rng.uniform(size=n) < 0.1, 1e10, 0.09)
+    ths = rng.uniform(-1.5, 0.5, (batch, 3))
+    pp = np.exp(ths) + 1e-3
+    ctx.set_times(t); ctx.set_outputs(Y)
+    for rvec in (None, rv):
+        ctx.set_noise_vector(rvec)
+        lml = ctx.lgssm_logpdf(kind, ths)                                   # independent models
+        lml0 = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2, rvec=rvec)
+        assert relerr(lml, lml0) <= RTOL
+        lml_s, alpha = ctx.lgssm_decorrelate(kind, ths[0])                  # shared model
+        l0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[0, 0], pp[0, 1] ** 2, pp[0, 2] ** 2, rvec=rvec, want_alpha=True)
+        assert relerr(lml_s, l0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
+        _, mean, var = ctx.lgssm_smooth(kind, ths[0])
+        _, m0, v0 = cport.kalman_smooth_batch(kind, t, Y, pp[0, 0], pp[0, 1] ** 2, rvec if rvec is not None else pp[0, 2] ** 2)
+        assert np.max(np.abs(mean - m0)) <= 1e-8 * max(1.0, np.max(np.abs(m0)))
+        assert np.max(np.abs(var - v0) / v0) <= 1e-7
+    ctx.set_noise_vector(None)
+
+
+def test_lgssm_full_size_config3(ctx):
+    """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
+    and one 10M-step sequence; every lml against the C oracle."""
+    rng = np.random.default_rng(2)
+    B, N = 1024, 10000
+    t = np.cumsum(rng.exponential(1 / 30, N)); Y = rng.normal(size=(B, N))
+    ths = np.stack([np.log(rng.uniform(0.05, 5, B)), np.log(rng.uniform(0.3, 3, B)), np.log(rng.uniform(0.01, 1, B))], axis=1)
+    pp = np.exp(ths) + 1e-3
+    ctx.set_times(t); ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    lml = ctx.lgssm_logpdf(3, ths)
+    lml0 = cport.kalman_filter_batch(3, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2)
+    assert np.max(np.abs(lml - lml0) / np.abs(lml0)) <= RTOL
+    N = 10_000_000
+    t = np.arange(N) / 30.0; y = np.sin(0.01 * t) + 0.1 * rng.normal(size=N)
+    th = np.log([1.0, 1.0, 0.1])
+    ctx.set_times(t); ctx.set_outputs(y)
+    lml, alpha = ctx.lgssm_decorrelate(3, th)
+    l0, a0 = cport.kalman_decorrelate(3, t, y, *(lambda p: (p[0], p[1] ** 2, p[2] ** 2))(oracle.unpack_gp(th)))
+    assert abs(lml[0] - l0) <= RTOL * abs(l0)
+    assert np.max(np.abs(alpha[0] - a0)) <= 1e-8 * np.max(np.abs(a0))
+
+
+def test_sde_prediction_protocol_against_dense_gp(ctx):
+    """get_sde_predictions protocol (temporal_gp_inference.jl:55-113) through the ABI: merge, sort,
+    1e10 noise at the test locations, smooth, un-sort; against the oracle and the dense posterior."""
+    rng = np.random.default_rng(3)
+    ntr, nte = 300, 200
+    ttr = np.sort(rng.uniform(0, 10, ntr)); tte = rng.uniform(0, 11, nte); ytr = np.sin(ttr) + 0.1 * rng.normal(size=ntr)
+    th = np.log([0.8, 1.1, 0.1])
+    l, var, sig = oracle.unpack_gp(th)
+    tc = np.concatenate([ttr, tte]); perm = np.argsort(tc, kind="stable"); rev = np.argsort(perm, kind="stable")
+    yc = np.concatenate([ytr, np.zeros(nte)]); rc = np.concatenate([np.full(ntr, sig ** 2), np.full(nte, 1e10)])
+    ctx.set_times(tc[perm]); ctx.set_outputs(yc[perm]); ctx.set_noise_vector(rc[perm])
+    _, mean, v = ctx.lgssm_smooth(3, th)
+    ctx.set_noise_vector(None)
+    mean = mean[0][rev][ntr:]; v = v[0][rev][ntr:]
+    m0, v0 = oracle.sde_predictions(3, ttr, ytr, tte, l, var, sig, smooth=cport.kalman_smooth)
+    assert np.max(np.abs(mean - m0)) <= 1e-8 and np.max(np.abs(v - v0) / v0) <= 1e-7
+    Kff = oracle.pairwise(3, ttr[:, None], ttr[:, None], l, var ** 2); Ksf = oracle.pairwise(3, tte[:, None], ttr[:, None], l, var ** 2)
+    md, vd = oracle.exact_posterior(Kff, Ksf, np.full(nte, var ** 2), sig ** 2, ytr, obs_noise=0.0)
+    assert np.max(np.abs(mean - md)) <= 1e-6
+
+
+# ---- scaled GPAR objective and q(u) ---------------------------------------------------------
+def test_scaled_golden(ctx):
+    z = np.load(os.path.join(G, "scaled.npz"))
+    for i in range(int(z["ncases"])):
+        kt, ko = (int(v) for v in z[f"c{i}_meta"])
+        ctx.set_inputs(z[f"c{i}_X"]); ctx.set_pseudo(z[f"c{i}_Z"]); ctx.set_times(z[f"c{i}_t"]); ctx.set_outputs(z[f"c{i}_y"])
+        dtc, A = ctx.scaled_dtc(kt, ko, z[f"c{i}_theta"], return_A=True)
+        assert abs(dtc - float(z[f"c{i}_dtc"])) <= RTOL * abs(float(z[f"c{i}_dtc"]))
+        assert np.max(np.abs(A - z[f"c{i}_A"])) <= 1e-8 * max(1.0, np.max(np.abs(z[f"c{i}_A"])))
+        if f"c{i}_m_e" in z:
+            m_e, Dinv, U_u = ctx.compute_q_u(kt, ko, np.array(oracle.unpack_gpar(z[f"c{i}_theta"])))
+            assert relerr(m_e, z[f"c{i}_m_e"]) <= 1e-7 and relerr(Dinv, z[f"c{i}_Dinv"]) <= 1e-7 and relerr(U_u, z[f"c{i}_U_u"]) <= 1e-9
+
+
+@pytest.mark.parametrize("n,m,d,kt,ko", [(1, 1, 1, 3, 3), (1023, 50, 1, 3, 3), (1025, 129, 2, 3, 3), (8496, 81, 2, 3, 3), (5000, 40, 4, 2, 1), (3000, 17, 7, 1, 0)])
+def test_scaled_dtc_vs_oracle(ctx, n, m, d, kt, ko):
+    rng = np.random.default_rng(n + m)
+    t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    th = rng.uniform(-1.0, 0.3, 5)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    v = ctx.scaled_dtc(kt, ko, th)
+    v0 = scaled_gpar_objective(th, X, Z, t, y, k_out=ko, k_time=kt, decorrelate=cport.kalman_decorrelate)
+    assert abs(v - v0) <= RTOL * abs(v0)
+
+
+# ---- exact GP / GPAR -----------------------------------------------------------------------
+def test_exact_golden(ctx):
+    z = np.load(os.path.join(G, "exact.npz"))
+    ctx.set_inputs(z["gp_X"]); ctx.set_outputs(z["gp_Y"])
+    assert relerr(ctx.exact_logpdf(0, 0, z["gp_theta"]), z["gp_lml"]) <= RTOL
+    mean, var = ctx.exact_posterior(0, 0, z["gp_theta"], z["gp_Xs"])
+    assert np.max(np.abs(mean - z["gp_mean"])) <= 1e-8 and np.max(np.abs(var - z["gp_var"])) <= 1e-8 * np.max(z["gp_var"]) + 1e-12
+    ctx.set_inputs(z["gpar_X"]); ctx.set_outputs(z["gpar_y"])
+    assert relerr(ctx.exact_logpdf(0, 3, z["gpar_theta"]), z["gpar_lml"]) <= RTOL
+    mean, var = ctx.exact_posterior(0, 3, z["gpar_theta"], z["gpar_Xs"])
+    assert np.max(np.abs(mean[0] - z["gpar_mean"])) <= 1e-8 and np.max(np.abs(var - z["gpar_var"])) <= 1e-8 * np.max(z["gpar_var"]) + 1e-12

@@ -205,3 +205,20 @@ def test_gradient_oracle_against_central_differences():
                 e = np.zeros(3); e[i] = 1e-5
                 fd = (f(th + e, kind, vfe) - f(th - e, kind, vfe)) / 2e-5
                 assert g[i] == pytest.approx(fd, rel=1e-6, abs=1e-7)
+
+
+def test_blas_cpu_port_of_logpdf_grad_matches_autograd():
+    """bench.py's CPU baseline (oracle.dtc.dtc_diag_value_and_grad_np) == torch autograd oracle."""
+    from oracle.grad import dtc_diag_value_and_grad
+    from oracle.dtc import dtc_diag_value_and_grad_np
+    rng = np.random.default_rng(8)
+    for kind in range(4):
+        for D in (1, 3):
+            for vfe in (False, True):
+                for jit in (-1.0, 1e-4):
+                    X = rng.normal(size=(150, D)) * 2; Z = rng.normal(size=(13, D)) * 2; y = rng.normal(size=150)
+                    th = rng.uniform(-1, 0.5, 3)
+                    v0, g0 = dtc_diag_value_and_grad(th, X, Z, y, kind, vfe, jit)
+                    v1, g1 = dtc_diag_value_and_grad_np(th, X, Z, y, kind, vfe, jit)
+                    assert v1 == pytest.approx(v0, rel=1e-9)
+                    assert np.allclose(g1, g0, rtol=1e-6, atol=1e-8 * np.max(np.abs(g0)))
