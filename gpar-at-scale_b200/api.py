@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference's Julia interface for the hot path.
+
+Julia is not installed in this image, so the reference-facing host layer is restated in Python with
+the SAME function names, argument meaning, defaults and error behaviour as the Julia functions it
+mirrors (cited per function); INTEGRATION.md shows the Julia `ccall` shim that binds the same C
+ABI.  Everything numeric goes through `Context` -> libgpar_b200.so; nothing here computes a kernel
+matrix, a Cholesky or a filter on the CPU.
+"""
+import numpy as np
+from . import _ffi
+from .context import Context
+from . import neldermead
+
+# ---- kernel structures (Stheno's EQ(), Matern12(), Matern32(), Matern52()) ---------------------
+
+
+class Kernel:
+    code = None
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class EQ(Kernel):
+    code = _ffi.EQ
+
+
+class Matern12(Kernel):
+    code = _ffi.MATERN12
+
+
+class Matern32(Kernel):
+    code = _ffi.MATERN32
+
+
+class Matern52(Kernel):
+    code = _ffi.MATERN52
+
+
+class ScaledKernel(Kernel):
+    """`kernel(k; l, s)` = s * stretch(k, 1/l) (Stheno; cf. optimized.jl:30-31)."""
+
+    def __init__(self, base, l, s):
+        self.base, self.l, self.s = base, float(l), float(s)
+        self.code = base.code
+
+
+def kernel(k, l=1.0, s=1.0):
+    return ScaledKernel(k, l, s)
+
+
+class GP:
+    """`GP(kernel, GPC())`: zero-mean prior; calling it on inputs gives a FiniteGP."""
+
+    def __init__(self, k):
+        self.kernel = k if isinstance(k, ScaledKernel) else ScaledKernel(k, 1.0, 1.0)
+
+    def __call__(self, x, noise=1e-18):
+        return FiniteGP(self, to_ColVecs(x), float(noise))
+
+
+class FiniteGP:
+    def __init__(self, gp, x, noise):
+        self.gp, self.x, self.noise = gp, x, noise
+
+    def __len__(self):
+        return self.x.shape[0]
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """One lazily-created Context per device for the functional API."""
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---- src/util.jl ------------------------------------------------------------------------------
+def to_ColVecs(inputs):
+    """util.jl:16-31.  A list of per-feature vectors (or an (N, D) array of records, or a 1-D vector)
+    -> (N, D) C-contiguous records = memory of the reference's D x N column-major ColVecs."""
+    if isinstance(inputs, np.ndarray):
+        a = np.asarray(inputs, dtype=np.float64)
+        return np.ascontiguousarray(a.reshape(-1, 1) if a.ndim == 1 else a)
+    if len(inputs) and np.ndim(inputs[0]) == 0:
+        return np.ascontiguousarray(np.asarray(inputs, dtype=np.float64).reshape(-1, 1))
+    return np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.float64).ravel() for c in inputs], axis=1))
+
+
+def unpack_gp(params):
+    """util.jl:36-43."""
+    return tuple(float(np.exp(params[i]) + 1e-3) for i in range(3))
+
+
+def unpack_gpar(params):
+    """util.jl:45-55."""
+    return tuple(float(np.exp(params[i]) + 1e-3) for i in range(5))
+
+
+def get_time_mask(input_length):
+    """util.jl:102-106."""
+    m = np.zeros(input_length); m[0] = 1.0
+    return m
+
+
+def get_output_mask(input_length):
+    """util.jl:111-123 (DomainError for input_length <= 1)."""
+    if input_length <= 1:
+        raise ValueError("DomainError: Input length must be integer greater than 1")
+    m = np.zeros((input_length - 1, input_length))
+    for r in range(input_length - 1):
+        m[r, r + 1] = 1.0
+    return m
+
+
+def _parse_param(p, rng=None):
+    """util.jl:128-134: a missing parameter is drawn with rand() — uniform [0, 1)."""
+    if p is None:
+        return float((rng or np.random).random())
+    return float(p)
+
+
+def parse_initial_gp_params(i_log_l, i_log_process_var, i_log_noise_sigma, rng=None):
+    """util.jl:141-147."""
+    return np.array([_parse_param(i_log_l, rng), _parse_param(i_log_process_var, rng), _parse_param(i_log_noise_sigma, rng)])
+
+
+def parse_initial_gpar_params(i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma, rng=None):
+    """util.jl:154-169."""
+    return np.array([_parse_param(p, rng) for p in (i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma)])
+
+
+def _log_pos(v):
+    """inverse of exp(p) + 1e-3 for passing positive values through theta-taking entry points"""
+    return np.log(np.asarray(v, dtype=np.float64) - 1e-3)
+
+
+# ---- src/gp/optimized.jl ------------------------------------------------------------------------
+class Posterior:
+    """`gp | (gp(x, sigma^2) <- y)` (optimized.jl:94,236): callable data holder with the two
+    operations the reference's callers use, `marginals` and `mean` (eeg.jl:185-208)."""
+
+    def __init__(self, ctx, X, y, theta, k_time, k_out):
+        self.ctx, self.X, self.y, self.theta, self.k_time, self.k_out = ctx, X, np.asarray(y, dtype=np.float64), np.asarray(theta), k_time, k_out
+
+    def _post(self, Xs):
+        self.ctx.set_inputs(self.X); self.ctx.set_outputs(self.y)
+        mean, var = self.ctx.exact_posterior(self.k_time.code, self.k_out.code, self.theta, to_ColVecs(Xs))
+        return mean[0], var
+
+    def marginals(self, Xs):
+        """-> (mean, std): Stheno's marginals are Normal(mu, sqrt(var))."""
+        mean, var = self._post(Xs)
+        return mean, np.sqrt(np.maximum(var, 0.0))
+
+    def mean(self, Xs):
+        return self._post(Xs)[0]
+
+
+def create_optim_gp(input_locations, outputs, kernel_structure=None, i_log_l=None, i_log_process_var=None,
+                    i_log_noise_sigma=None, debug=False, ctx=None, rng=None):
+    """optimized.jl:19-59 -> (gp, opt_params)."""
+    kernel_structure = kernel_structure or EQ()
+    ctx = ctx or default_context()
+    X = to_ColVecs(input_locations)
+    ctx.set_inputs(X); ctx.set_outputs(outputs)
+
+    def nlml(params):   # optimized.jl:28-36
+        return -ctx.exact_logpdf(kernel_structure.code, kernel_structure.code, params)[0]
+
+    params = parse_initial_gp_params(i_log_l, i_log_process_var, i_log_noise_sigma, rng)
+    if debug:
+        print("Generating GP with initial parameters:\n\tl=%s; var=%s; noise=%s" % unpack_gp(params))
+    results = neldermead.optimize(nlml, params)
+    opt_params = unpack_gp(results.minimizer)
+    if debug:
+        print("Finished optimizing parameters:\n\tOptimum L: %s \n\tOptimum Process Variance: %s\n\tOptimum noise: %s\n" % opt_params)
+    gp = GP(kernel(kernel_structure, l=opt_params[0], s=opt_params[1] ** 2))
+    gp._theta = results.minimizer
+    return gp, opt_params
+
+
+def create_optim_gp_post(input_locations, outputs, kernel_structure=None, i_log_l=None, i_log_process_var=None,
+                         i_log_noise_sigma=None, debug=False, ctx=None, rng=None):
+    """optimized.jl:76-97."""
+    kernel_structure = kernel_structure or EQ()
+    ctx = ctx or default_context()
+    gp, opt_params = create_optim_gp(input_locations, outputs, kernel_structure, i_log_l, i_log_process_var, i_log_noise_sigma, debug, ctx, rng)
+    return Posterior(ctx, to_ColVecs(input_locations), outputs, _log_pos(opt_params), kernel_structure, kernel_structure)
+
+
+def create_optim_gpar(input_locations, outputs, time_kernel=None, out_kernel=None, i_log_time_l=None, i_log_time_var=None,
+                      i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None, multi_input=True, debug=False, ctx=None, rng=None):
+    """optimized.jl:106-183 -> (gpar, opt_params)."""
+    time_kernel = time_kernel or EQ(); out_kernel = out_kernel or EQ()
+    if not multi_input:
+        return create_optim_gp(input_locations, outputs, time_kernel, i_log_time_l, i_log_time_var, i_log_noise_sigma, debug, ctx, rng)
+    ctx = ctx or default_context()
+    X = to_ColVecs(input_locations)
+    if X.shape[1] <= 1:
+        get_output_mask(X.shape[1])     # raises like util.jl:112-117
+    ctx.set_inputs(X); ctx.set_outputs(outputs)
+
+    def nlml(params):   # optimized.jl:147-154
+        return -ctx.exact_logpdf(time_kernel.code, out_kernel.code, params)[0]
+
+    params = parse_initial_gpar_params(i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma, rng)
+    results = neldermead.optimize(nlml, params)
+    opt_params = unpack_gpar(results.minimizer)
+    if debug:
+        print("Finished optimizing parameters:\n\tOptimum time L: %s \n\tOptimum time var: %s\n\tOptimum outputs l: %s\n"
+              "\tOptimum outputs var: %s\n\tOptimum Noise std: %s\n" % opt_params)
+    return ("gpar", time_kernel, out_kernel, opt_params), opt_params
+
+
+def create_optim_gpar_post(input_locations, outputs, time_kernel=None, out_kernel=None, i_log_time_l=None, i_log_time_var=None,
+                           i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None, multi_input=True, debug=False, ctx=None, rng=None):
+    """optimized.jl:201-239."""
+    time_kernel = time_kernel or EQ(); out_kernel = out_kernel or EQ()
+    if not multi_input:
+        return create_optim_gp_post(input_locations, outputs, time_kernel, i_log_time_l, i_log_time_var, i_log_noise_sigma, debug, ctx, rng)
+    ctx = ctx or default_context()
+    _, opt_params = create_optim_gpar(input_locations, outputs, time_kernel, out_kernel, i_log_time_l, i_log_time_var, i_log_out_l,
+                                      i_log_out_var, i_log_noise_sigma, multi_input, debug, ctx, rng)
+    return Posterior(ctx, to_ColVecs(input_locations), outputs, _log_pos(opt_params), time_kernel, out_kernel)
+
+
+# ---- src/gp/temporal_gp_inference.jl ---------------------------------------------------------
+class LGSSM:
+    """Handle returned by create_lgssm: the model is rebuilt on the device from these values."""
+
+    def __init__(self, locations, l, process_var, noise_sigma, kernel_structure, noise_vector=None):
+        self.t = np.asarray(locations, dtype=np.float64)
+        self.l, self.process_var, self.noise_sigma = float(l), float(process_var), float(noise_sigma)
+        self.kernel_structure, self.noise_vector = kernel_structure, noise_vector
+
+    @property
+    def theta(self):
+        return _log_pos([self.l, self.process_var, self.noise_sigma])
+
+
+def create_lgssm(latent_locations, l, process_var, noise_sigma, kernel_structure, noise_vector=None, debug=False):
+    """temporal_gp_inference.jl:15-39."""
+    if kernel_structure.code == _ffi.EQ:
+        raise ValueError("EQ has no finite-dimensional SDE form (TemporalGPs.to_sde has no method for EQ)")
+    return LGSSM(latent_locations, l, process_var, noise_sigma, kernel_structure, noise_vector)
+
+
+def logpdf(lgssm, y, ctx=None):
+    """`logpdf(lgssm, y)` (temporal_gp_inference.jl:78)."""
+    ctx = ctx or default_context()
+    ctx.set_times(lgssm.t); ctx.set_outputs(y); ctx.set_noise_vector(lgssm.noise_vector)
+    out = ctx.lgssm_logpdf(lgssm.kernel_structure.code, lgssm.theta)
+    ctx.set_noise_vector(None)
+    return out[0] if np.ndim(y) == 1 else out
+
+
+def decorrelate(lgssm, y, ctx=None):
+    """`decorrelate(lgssm, y)` -> (lml, alpha) (dtc.jl:106)."""
+    ctx = ctx or default_context()
+    ctx.set_times(lgssm.t); ctx.set_outputs(y); ctx.set_noise_vector(lgssm.noise_vector)
+    lml, alpha = ctx.lgssm_decorrelate(lgssm.kernel_structure.code, lgssm.theta)
+    ctx.set_noise_vector(None)
+    return (lml[0], alpha[0]) if np.ndim(y) == 1 else (lml, alpha)
+
+
+class Gaussian:
+    """Element of `smooth`'s output as the reference's callers read it: `.m[1]`, `.P[1]`
+    (GPAR_scaled_examples.jl:111,128-129) -> here `.m[0]`, `.P[0]`."""
+    __slots__ = ("m", "P")
+
+    def __init__(self, m, P):
+        self.m, self.P = (m,), (P,)
+
+
+def smooth(lgssm, y, ctx=None):
+    """`smooth(lgssm, y)` -> (None, y_smooth, lml): the reference only reads the 2nd return."""
+    ctx = ctx or default_context()
+    ctx.set_times(lgssm.t); ctx.set_outputs(y); ctx.set_noise_vector(lgssm.noise_vector)
+    lml, mean, var = ctx.lgssm_smooth(lgssm.kernel_structure.code, lgssm.theta)
+    ctx.set_noise_vector(None)
+    return None, [Gaussian(m, v) for m, v in zip(mean[0], var[0])], lml[0]
+
+
+def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_structure=None, i_log_time_l=None, i_log_time_var=None,
+                        i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False):
+    """temporal_gp_inference.jl:45-114 -> (opt_lgssm, output_observations)."""
+    kernel_structure = kernel_structure or Matern52()
+    ctx = ctx or default_context()
+    data_locations = np.asarray(data_locations, dtype=np.float64); output_locations = np.asarray(output_locations, dtype=np.float64)
+    data_outputs = np.asarray(data_outputs, dtype=np.float64)
+    latent_locations = np.concatenate([data_locations, output_locations])                      # :56
+    outputs = np.concatenate([data_outputs, np.zeros(len(output_locations))])                  # :58
+    sorting_perm = np.argsort(latent_locations, kind="stable")                                 # :61 (Julia's sortperm is stable)
+    reverse_perm = np.argsort(sorting_perm, kind="stable")                                     # :62
+    s_latent_locations = latent_locations[sorting_perm]; s_outputs = outputs[sorting_perm]
+
+    ctx.set_times(data_locations); ctx.set_outputs(data_outputs); ctx.set_noise_vector(None)
+
+    def nlml(params):    # :69-79 (the LGSSM is built on data_locations as given)
+        return -ctx.lgssm_logpdf(kernel_structure.code, params)[0]
+
+    params = parse_initial_gp_params(i_log_time_l, i_log_time_var, i_log_noise_sigma, rng)
+    results = neldermead.optimize(nlml, params)                                                # :82
+    opt_l, opt_process_var, opt_noise_sigma = unpack_gp(results.minimizer)
+    if debug:
+        print("Finished optimizing parameters:\n\tOptimum L: %s \n\tOptimum Process Variance: %s\n\tOptimum noise: %s\n"
+              % (opt_l, opt_process_var, opt_noise_sigma))
+    noise_vector = np.concatenate([np.full(len(data_locations), opt_noise_sigma ** 2), np.full(len(output_locations), 1e10)])   # :93-96
+    s_noise_vector = noise_vector[sorting_perm]
+    opt_lgssm = create_lgssm(s_latent_locations, opt_l, opt_process_var, opt_noise_sigma, kernel_structure, noise_vector=s_noise_vector)
+    ctx.set_times(s_latent_locations); ctx.set_outputs(s_outputs); ctx.set_noise_vector(s_noise_vector)
+    _, mean, var = ctx.lgssm_smooth(kernel_structure.code, results.minimizer)                  # :109
+    ctx.set_noise_vector(None)
+    nd = len(data_outputs)
+    mean = mean[0][reverse_perm][nd:]; var = var[0][reverse_perm][nd:]                         # :111-112
+    if return_arrays:
+        return opt_lgssm, (mean, var)
+    return opt_lgssm, [Gaussian(m, v) for m, v in zip(mean, var)]
+
+
+# ---- src/gp/dtc.jl ---------------------------------------------------------------------------
+def compute_gpar_dtc_objective(f, u, time_loc, outputs, time_kernel=None, temporal_noise_sigma=0.04, ctx=None, return_A=True):
+    """dtc.jl:83-128 -> (dtc, A).  f, u: FiniteGPs of one prior at the inputs / pseudo-inputs;
+    cov(u) includes u's noise as jitter (dtc.jl:35,119); time_kernel a (scaled) Matern kernel."""
+    ctx = ctx or default_context()
+    tk = time_kernel if isinstance(time_kernel, ScaledKernel) else ScaledKernel(time_kernel or Matern52(), 1.0, 1.0)
+    ok = f.gp.kernel
+    if abs(u.noise - temporal_noise_sigma ** 2) > 1e-15 * max(u.noise, 1e-300):
+        raise ValueError("the device path implements the reference's call pattern cov(u) = Kuu + temporal_noise_sigma^2 I "
+                         "(dtc.jl:34-35,44): u's noise must equal temporal_noise_sigma^2")
+    ctx.set_inputs(f.x); ctx.set_pseudo(u.x); ctx.set_times(time_loc); ctx.set_outputs(outputs)
+    theta = _log_pos([tk.l, np.sqrt(tk.s), ok.l, np.sqrt(ok.s), temporal_noise_sigma])
+    if return_A:
+        return ctx.scaled_dtc(tk.code, ok.code, theta, return_A=True)
+    return ctx.scaled_dtc(tk.code, ok.code, theta), None
+
+
+def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_loc, outputs, out_kernel=None, time_kernel=None,
+                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
+                                 optimization_time_limit=1000.0, show_optimization_trace=False, debug=False, ctx=None, rng=None,
+                                 iterations=1000, return_result=False):
+    """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma)."""
+    out_kernel = out_kernel or Matern52(); time_kernel = time_kernel or Matern52()
+    ctx = ctx or default_context()
+    ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
+    ctx.set_times(time_loc); ctx.set_outputs(outputs)
+
+    def nlml(params):    # dtc.jl:29-48; data stays resident on the device across evaluations
+        return -ctx.scaled_dtc(time_kernel.code, out_kernel.code, params)
+
+    params = parse_initial_gpar_params(i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma, rng)
+    if debug:
+        print("Generating scaled GPAR with initial parameters:\n\ti_time_l=%s; i_time_var=%s; i_out_l=%s; i_out_var=%s; i_noise_sigma=%s" % unpack_gpar(params))
+    results = neldermead.optimize(nlml, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
+    opt_params = unpack_gpar(results.minimizer)
+    if debug:
+        print("Finished optimizing parameters:\n\tOptimum time L: %s \n\tOptimum time var: %s\n\tOptimum outputs l: %s\n"
+              "\tOptimum outputs var: %s\n\tOptimum Noise std: %s\n" % opt_params)
+    return (opt_params, results) if return_result else opt_params
+
+
+# ---- src/gp/gpar_scaled_inference.jl ---------------------------------------------------------
+def compute_q_u(input_locations, pseudo_input_locations, time_loc, outputs, out_kernel=None, time_kernel=None,
+                temporal_noise_sigma=0.05, debug=False, ctx=None):
+    """gpar_scaled_inference.jl:141-196 -> ((m_e, inv(D)), U_u): q_u = MvNormal(m_e, inv(D))."""
+    ctx = ctx or default_context()
+    ok = out_kernel if isinstance(out_kernel, ScaledKernel) else ScaledKernel(out_kernel or Matern52(), 1.0, 1.0)
+    tk = time_kernel if isinstance(time_kernel, ScaledKernel) else ScaledKernel(time_kernel or Matern52(), 1.0, 1.0)
+    ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
+    ctx.set_times(time_loc); ctx.set_outputs(outputs)
+    m_e, Dinv, U_u = ctx.compute_q_u(tk.code, ok.code, [tk.l, np.sqrt(tk.s), ok.l, np.sqrt(ok.s), temporal_noise_sigma])
+    return (m_e, Dinv), U_u
