@@ -1,0 +1,102 @@
+"""Multi-GPU sharding of the GPAR fit: one process per GPU, tasks = (output i, restart r).
+
+Training of output i conditions on the OBSERVED earlier outputs (examples/eeg.jl:53-92,212-281;
+examples/GPAR_scaled_examples.jl:132-175 pass `[y1]`, `[y1, y2]`), so the per-output / per-restart
+fits are mutually independent: they are partitioned over the ranks with NO data-path collective,
+and torch.distributed (NCCL on GPUs, gloo in the CPU tests) only all-gathers the scalars
+`(task id, minimum, minimizer)` at the end.  Only prediction is sequential over outputs:
+the owner of output i broadcasts its posterior means to the later outputs
+(GPAR_scaled_examples.jl:172 `[test_y1, y2_out]`).
+"""
+import numpy as np
+
+
+def dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def shard_tasks(costs, world, rank=None):
+    """Greedy longest-processing-time partition of tasks with the given relative costs (output 1 is
+    a time-only LGSSM and much cheaper than the pseudo-point outputs; cost grows mildly with D).
+    Deterministic: every rank computes the same assignment.  -> list of task indices per rank (or the
+    list of `rank` when given)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(world)
+    assign = [[] for _ in range(world)]
+    for t in order:
+        r = int(np.argmin(load))          # ties -> lowest rank
+        assign[r].append(int(t))
+        load[r] += costs[t]
+    for a in assign:
+        a.sort()
+    return assign if rank is None else assign[rank]
+
+
+def gather_results(local, ntasks, nparam, device=None):
+    """local: {task: (minimum, minimizer[nparam])} -> (minimum[ntasks], minimizer[ntasks, nparam]) on
+    every rank.  One all_gather of a (max tasks per rank) x (2 + nparam) float64 tensor."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info()
+    if world == 1:
+        vals = np.full(ntasks, np.nan); thetas = np.full((ntasks, nparam), np.nan)
+        for t, (v, th) in local.items():
+            vals[t] = v; thetas[t] = th
+        return vals, thetas
+    cap = (ntasks + world - 1) // world + ntasks % world + 1
+    cap = ntasks          # LPT can be uneven; ntasks rows is tiny (48 B each)
+    buf = torch.full((cap, 2 + nparam), float("nan"), dtype=torch.float64)
+    for i, (t, (v, th)) in enumerate(sorted(local.items())):
+        buf[i, 0] = t; buf[i, 1] = v; buf[i, 2:] = torch.as_tensor(np.asarray(th, dtype=np.float64))
+    if device is not None:
+        buf = buf.to(device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    vals = np.full(ntasks, np.nan); thetas = np.full((ntasks, nparam), np.nan)
+    for o in out:
+        o = o.cpu().numpy()
+        for row in o:
+            if row[0] == row[0]:
+                vals[int(row[0])] = row[1]; thetas[int(row[0])] = row[2:]
+    return vals, thetas
+
+
+def broadcast_means(means, src, device=None):
+    """Posterior means of one output passed down the GPAR chain (8 N* bytes)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info()
+    if world == 1:
+        return means
+    t = torch.as_tensor(np.ascontiguousarray(means, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
+def fit_tasks(tasks, costs, run_task, nparam, device=None):
+    """Runs `run_task(task) -> (minimum, minimizer)` for this rank's share of `tasks` and gathers
+    everything.  -> (minimum[len(tasks)], minimizer[len(tasks), nparam])."""
+    rank, world = dist_info()
+    mine = shard_tasks(costs, world, rank)
+    local = {}
+    for ti in mine:
+        local[ti] = run_task(tasks[ti])
+    return gather_results(local, len(tasks), nparam, device)
+
+
+def best_per_output(tasks, minimum, minimizer):
+    """tasks: list of (output, restart).  -> {output: (best minimum, its minimizer, restart)}"""
+    best = {}
+    for (o, r), v, th in zip(tasks, minimum, minimizer):
+        if v == v and (o not in best or v < best[o][0]):
+            best[o] = (float(v), np.array(th), r)
+    return best

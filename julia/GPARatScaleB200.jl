@@ -1,0 +1,123 @@
+# GPARatScaleB200.jl — Julia-side binding of libgpar_b200.so (include/gpar_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The same symbols, argument
+# order and memory layouts are exercised through Python ctypes (gpar-at-scale_b200/_ffi.py) by the
+# test-suite; this file is what a maintainer of GPAR-at-scale adds so that the package's exported
+# functions keep their names and signatures while their numeric cores run on the B200.
+#
+# Usage inside the reference package (src/GPARatScale.jl):
+#     include("GPARatScaleB200.jl"); using .GPARatScaleB200
+# and replace the bodies shown in INTEGRATION.md.
+module GPARatScaleB200
+
+using LinearAlgebra: PosDefException
+
+const LIB = get(ENV, "GPAR_B200_LIB", "libgpar_b200.so")
+const GPAR_OK, GPAR_ERR_INVALID, GPAR_ERR_CUDA, GPAR_ERR_NOT_POSDEF, GPAR_ERR_NOMEM = 0, 1, 2, 3, 4
+@enum KernelCode EQ_K = 0 MATERN12_K = 1 MATERN32_K = 2 MATERN52_K = 3
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:gpar_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
+        st == GPAR_OK || error("gpar_ctx_create failed with status $st (no CUDA device?)")
+        c = new(r[])
+        finalizer(x -> ccall((:gpar_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+function check(c::Ctx, st::Integer)
+    st == GPAR_OK && return nothing
+    msg = unsafe_string(ccall((:gpar_last_error, LIB), Cstring, (Ptr{Cvoid},), c.h))
+    # what `cholesky` throws in the reference (src/gp/dtc.jl:119-120) and Optim propagates
+    st == GPAR_ERR_NOT_POSDEF && throw(PosDefException(1))
+    error("libgpar_b200 status $st: $msg")
+end
+
+# Stheno kernel structure -> code.  (Stheno.EQ, Matern12, Matern32, Matern52)
+kernel_code(k) = let n = string(nameof(typeof(k)))
+    n == "EQ" ? 0 : n == "Matern12" ? 1 : n == "Matern32" ? 2 : n == "Matern52" ? 3 :
+        throw(ArgumentError("kernel $n has no libgpar_b200 code"))
+end
+
+# ---- resident data.  ColVecs.X is a D x N column-major Matrix{Float64} (src/util.jl:16-31):
+#      exactly the N-records-of-D-doubles layout the ABI expects, so the pointer is passed as is.
+set_inputs!(c::Ctx, X::Matrix{Float64}) =
+    check(c, ccall((:gpar_set_inputs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int64), c.h, X, size(X, 1), size(X, 2)))
+set_pseudo!(c::Ctx, Z::Matrix{Float64}) =
+    check(c, ccall((:gpar_set_pseudo, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int64), c.h, Z, size(Z, 1), size(Z, 2)))
+set_times!(c::Ctx, t::Vector{Float64}) =
+    check(c, ccall((:gpar_set_times, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), c.h, t, length(t)))
+set_outputs!(c::Ctx, y::VecOrMat{Float64}) =      # N or N x batch (column-major: sequence b contiguous)
+    check(c, ccall((:gpar_set_outputs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32), c.h, y, size(y, 1), size(y, 2)))
+set_noise_vector!(c::Ctx, r::Union{Nothing, Vector{Float64}}) = r === nothing ?
+    check(c, ccall((:gpar_set_noise_vector, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), c.h, C_NULL, 0)) :
+    check(c, ccall((:gpar_set_noise_vector, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), c.h, r, length(r)))
+
+# ---- compute ------------------------------------------------------------------------------
+"DTC / VFE log-pdf (and gradient) for Sigma_y = sigma^2 I; theta = raw (log l, log var, log sigma)."
+function dtc_logpdf(c::Ctx, k, theta::Vector{Float64}; vfe::Bool = false, jitter::Float64 = -1.0, grad::Bool = false)
+    val = Ref{Float64}(0.0)
+    g = grad ? zeros(3) : Float64[]
+    check(c, ccall((:gpar_dtc_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Float64, Ref{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, vfe, jitter, val, grad ? pointer(g) : C_NULL))
+    return grad ? (val[], g) : val[]
+end
+
+"compute_gpar_dtc_objective (src/gp/dtc.jl:83-128): returns (dtc, A) like the reference."
+function scaled_dtc(c::Ctx, k_time, k_out, theta::Vector{Float64}, N::Integer, M::Integer; return_A::Bool = false)
+    val = Ref{Float64}(0.0)
+    A = return_A ? zeros(M, N) : zeros(0, 0)
+    check(c, ccall((:gpar_scaled_dtc, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), theta, val, return_A ? pointer(A) : C_NULL))
+    return val[], A
+end
+
+"compute_q_u (src/gp/gpar_scaled_inference.jl:141-196): (m_e, inv(D), U_u); params are positive values."
+function compute_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, M::Integer)
+    m_e = zeros(M); Dinv = zeros(M, M); U_u = zeros(M, M)
+    check(c, ccall((:gpar_compute_q_u, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), params, m_e, Dinv, U_u))
+    return m_e, Dinv, U_u
+end
+
+"logpdf(lgssm, y) for every resident sequence; theta is 3 x batch_theta (column per model)."
+function lgssm_logpdf(c::Ctx, k, theta::VecOrMat{Float64}, batch::Integer)
+    lml = zeros(batch)
+    check(c, ccall((:gpar_lgssm_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int32, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, size(theta, 2), lml))
+    return lml
+end
+
+function lgssm_decorrelate(c::Ctx, k, theta::Vector{Float64}, N::Integer, batch::Integer = 1)
+    alpha = zeros(N, batch); lml = zeros(batch)
+    check(c, ccall((:gpar_lgssm_decorrelate, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, alpha, lml))
+    return lml, alpha
+end
+
+function lgssm_smooth(c::Ctx, k, theta::Vector{Float64}, N::Integer, batch::Integer = 1)
+    m = zeros(N, batch); v = zeros(N, batch); lml = zeros(batch)
+    check(c, ccall((:gpar_lgssm_smooth, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, m, v, lml))
+    return lml, m, v
+end
+
+function exact_logpdf(c::Ctx, k_time, k_out, theta::Vector{Float64}, batch::Integer = 1)
+    lml = zeros(batch)
+    check(c, ccall((:gpar_exact_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int32, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), theta, length(theta), lml))
+    return lml
+end
+
+function exact_posterior(c::Ctx, k_time, k_out, theta::Vector{Float64}, Xs::Matrix{Float64}, batch::Integer = 1)
+    Ns = size(Xs, 2); mean = zeros(Ns, batch); var = zeros(Ns)
+    check(c, ccall((:gpar_exact_posterior, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), theta, length(theta), Xs, Ns, mean, var))
+    return mean, var
+end
+
+end # module
