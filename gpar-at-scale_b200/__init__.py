@@ -8,7 +8,7 @@ directory to that module name).
 """
 from ._ffi import (EQ, MATERN12, MATERN32, MATERN52, GparError, PosDefException, load_library, LIB_PATH)
 from .context import Context
-from . import api, neldermead, parallel
+from . import api, neldermead, parallel, data, chain
 
 __all__ = ["EQ", "MATERN12", "MATERN32", "MATERN52", "GparError", "PosDefException", "load_library",
            "LIB_PATH", "Context"]

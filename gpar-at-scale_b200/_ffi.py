@@ -35,6 +35,8 @@ SIGNATURES = {
     "gpar_scaled_dtc": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_compute_q_u": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p,
                                         _c_double_p, _c_double_p]),
+    "gpar_scaled_predict": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int32,
+                                           _c_double_p, _c_double_p]),
     "gpar_lgssm_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),
     "gpar_lgssm_decorrelate": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_lgssm_smooth": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),

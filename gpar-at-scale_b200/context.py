@@ -115,6 +115,15 @@ class Context:
         self._check(self._lib.gpar_compute_q_u(self._h, int(k_time), int(k_out), dptr(p), dptr(m_e), dptr(Dinv), dptr(U_u)))
         return m_e, Dinv, U_u
 
+    def scaled_predict(self, k_time, k_out, params, W):
+        """W: (M, S) — column j = U_u \\ eps_j.  -> (mean, std) over the merged, sorted locations."""
+        p = as_f64(np.asarray(params).ravel())
+        W = np.asfortranarray(W, dtype=np.float64)
+        mean = np.zeros(self.N); sd = np.zeros(self.N)
+        self._check(self._lib.gpar_scaled_predict(self._h, int(k_time), int(k_out), dptr(p), W.ctypes.data_as(_ffi._c_double_p),
+                                                  W.shape[1], dptr(mean), dptr(sd)))
+        return mean, sd
+
     def lgssm_logpdf(self, kernel, theta):
         th = as_f64(np.atleast_2d(theta))
         out = np.zeros(self.batch)

@@ -158,7 +158,7 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   CU(ctx->panelK.reserve(panel_bytes));
   if (want_grad) CU(ctx->panelD.reserve(panel_bytes));
   const int T = Mpad / GPAR_TILE;
-  int nsplit = std::max(1, (ctx->num_sms * 8) / T);
+  int nsplit = std::max(1, (ctx->num_sms * 16) / T);   // 16 CTAs of 128 threads per SM: full occupancy at 48 registers
   nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, Npad / 4));
   CU(ctx->gpart.reserve((size_t)nsplit * 2 * Mpad * sizeof(double) + 1024 * sizeof(double)));
   const size_t MM = (size_t)M * M;

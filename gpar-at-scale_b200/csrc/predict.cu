@@ -1,0 +1,107 @@
+// predict.cu — the Monte-Carlo prediction of one scaled-GPAR output, batched on the device.
+//
+// Replaces the loop of get_gpar_scaled_predictions (src/gp/gpar_scaled_inference.jl:89-135):
+//   Cfu_star = pairwise(out_kernel, X*_sorted, Z)                       (:89)
+//   100 x { fx = Cfu_star * (U_u \ rand(q_u));  _, y_smooth, _ = smooth(time_lgssm_star, y* - fx);
+//           f* = fx + [g.m[1] for g in y_smooth] }                      (:110-123)
+//   mean(acc), std(acc)                                                 (:125)
+// The draws stay with the caller (Julia's global RNG, :94): it passes W[:, j] = U_u \ eps_j (M x S).
+// Device: (1) fx = K(X*, Z) W evaluated tile-wise without materialising Cfu_star, fused with
+// y* - fx; (2) ONE batched, temporally-parallel smoother over the S residual sequences sharing the
+// LGSSM (kalman.cu); (3) sample mean / corrected std over the S draws per location.
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+constexpr int SCHUNK = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+fx_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int DX, double inv_l2, double s_out,
+          const double* __restrict__ W, int S, const double* __restrict__ y, double* __restrict__ fx, double* __restrict__ ys) {
+  extern __shared__ double sm[];
+  double* zs = sm;                    // 128 x DX
+  double* ws = sm + 128 * DX;         // 128 x SCHUNK
+  const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int s0 = blockIdx.y * SCHUNK;
+  double acc[SCHUNK];
+#pragma unroll
+  for (int j = 0; j < SCHUNK; j++) acc[j] = 0.0;
+  double x[8];
+  for (int d = 0; d < DX; d++) x[d] = n < N ? X[n * DX + d] : 0.0;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    const int mc = min(128, M - m0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < mc * DX; e += 128) zs[e] = Z[(int64_t)m0 * DX + e];
+    for (int e = threadIdx.x; e < mc * SCHUNK; e += 128) {
+      int mm = e / SCHUNK, j = e % SCHUNK;
+      ws[e] = (s0 + j < S) ? W[(int64_t)(s0 + j) * M + m0 + mm] : 0.0;
+    }
+    __syncthreads();
+    for (int mm = 0; mm < mc; mm++) {
+      double d2 = 0.0;
+      for (int d = 0; d < DX; d++) { double df = x[d] - zs[mm * DX + d]; d2 = fma(df, df, d2); }
+      double dummy; const double k = s_out * base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
+#pragma unroll
+      for (int j = 0; j < SCHUNK; j++) acc[j] = fma(k, ws[mm * SCHUNK + j], acc[j]);
+    }
+  }
+  if (n >= N) return;
+  const double yn = y[n];
+#pragma unroll
+  for (int j = 0; j < SCHUNK; j++)
+    if (s0 + j < S) { fx[(int64_t)(s0 + j) * N + n] = acc[j]; ys[(int64_t)(s0 + j) * N + n] = yn - acc[j]; }
+}
+
+// mean_n = mean_s(fx + sm), std_n = corrected sample std (Julia `std`), 0 for S == 1
+__global__ void mc_reduce_kernel(const double* __restrict__ fx, const double* __restrict__ smean, int64_t N, int S,
+                                 double* __restrict__ mean, double* __restrict__ sd) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double m = 0.0;
+  for (int s = 0; s < S; s++) m += fx[(int64_t)s * N + n] + smean[(int64_t)s * N + n];
+  m /= S;
+  double v = 0.0;
+  for (int s = 0; s < S; s++) { double d = fx[(int64_t)s * N + n] + smean[(int64_t)s * N + n] - m; v = fma(d, d, v); }
+  mean[n] = m;
+  sd[n] = S > 1 ? sqrt(v / (S - 1)) : 0.0;
+}
+}  // namespace
+
+extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W, int32_t S,
+                                   double* mean, double* sd) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!params || !W || !mean || !sd || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: NULL argument or S < 1");
+  if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: merged inputs and pseudo-inputs must be set with equal D");
+  if (ctx->Nt != ctx->N || ctx->Ny != ctx->N) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: times/outputs must have the merged length N+N* = %lld", (long long)ctx->N);
+  if (ctx->has_rvec && ctx->Nr != ctx->N) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: noise vector length mismatch");
+  if (ctx->D > 8) return gpar_fail(ctx, GPAR_ERR_INVALID, "input dimension D=%d not supported (1..8)", ctx->D);
+  CU(cudaSetDevice(ctx->device));
+  const int64_t N = ctx->N; const int M = (int)ctx->M, DX = ctx->D;
+  const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
+  // fx | ys | smoothed mean | smoothed var | lml | mean | sd | W
+  CU(ctx->kal_e.reserve(((size_t)4 * S * N + S + 2 * (size_t)N + (size_t)M * S) * sizeof(double)));
+  double* fx = ctx->kal_e.as<double>(); double* ys = fx + (size_t)S * N; double* smean = ys + (size_t)S * N;
+  double* svar = smean + (size_t)S * N; double* lml = svar + (size_t)S * N; double* dmean = lml + S; double* dsd = dmean + N; double* dW = dsd + N;
+  CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CallTimer timer(ctx); ctx->phase_valid = false;
+  dim3 grid((unsigned)((N + 127) / 128), (S + SCHUNK - 1) / SCHUNK);
+  const size_t smem = (size_t)128 * (DX + SCHUNK) * sizeof(double);
+  const double inv_l2 = 1.0 / (out_l * out_l);
+  const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>(); const double* y = ctx->y.as<double>();
+  switch (k_out) {
+    case GPAR_EQ: LAUNCH(ctx, fx_kernel<GPAR_EQ>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
+    case GPAR_MATERN12: LAUNCH(ctx, fx_kernel<GPAR_MATERN12>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
+    case GPAR_MATERN32: LAUNCH(ctx, fx_kernel<GPAR_MATERN32>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
+    case GPAR_MATERN52: LAUNCH(ctx, fx_kernel<GPAR_MATERN52>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
+  }
+  CHK(lgssm_run(ctx, k_time, &time_l, &time_s, &noise, 1, S, N, ctx->t.as<double>(), ys, ctx->has_rvec ? ctx->rvec.as<double>() : nullptr,
+                nullptr, lml, smean, svar, nullptr, nullptr));
+  LAUNCH(ctx, mc_reduce_kernel, (unsigned)((N + 255) / 256), 256, 0, fx, smean, N, S, dmean, dsd);
+  timer.stop();
+  CU(cudaMemcpyAsync(mean, dmean, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(sd, dsd, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}

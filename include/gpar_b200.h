@@ -92,6 +92,16 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
 int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], double* m_e,
                      double* Dinv, double* U_u);
 
+/* Monte-Carlo prediction of one scaled-GPAR output, get_gpar_scaled_predictions
+ * (gpar_scaled_inference.jl:89-135), batched: resident data are the MERGED, time-SORTED train+test
+ * inputs X* (set_inputs), times (set_times), outputs with 0 at test points (set_outputs, batch 1),
+ * noise vector sigma^2 / 1e10 (set_noise_vector) and Z.  W (M x S column-major): column j =
+ * U_u \ eps_j for the caller's draws eps_j ~ q_u (:91-97; the RNG stays with the caller).
+ * Outputs (length N+N*, still in sorted order): sample mean and corrected std over the S draws of
+ * f*_j = fx_j + smooth(y* - fx_j).m[1] (:113-125).  params: positive values as gpar_compute_q_u. */
+int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W,
+                        int32_t S, double* mean, double* std);
+
 /* ---- state-space approximation: TemporalGPs logpdf / decorrelate / smooth ------------------
  * Model of create_lgssm (temporal_gp_inference.jl:15-39): GP(kernel(k; l, s = var^2)) -> SDE ->
  * LGSSM on the resident times with noise sigma^2, or the resident noise vector if one is set.

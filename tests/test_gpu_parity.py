@@ -187,7 +187,10 @@ def test_scaled_golden(ctx):
         assert np.max(np.abs(A - z[f"c{i}_A"])) <= 1e-8 * max(1.0, np.max(np.abs(z[f"c{i}_A"])))
         if f"c{i}_m_e" in z:
             m_e, Dinv, U_u = ctx.compute_q_u(kt, ko, np.array(oracle.unpack_gpar(z[f"c{i}_theta"])))
-            assert relerr(m_e, z[f"c{i}_m_e"]) <= 1e-7 and relerr(Dinv, z[f"c{i}_Dinv"]) <= 1e-7 and relerr(U_u, z[f"c{i}_U_u"]) <= 1e-9
+            # bare Cuu (no jitter, gpar_scaled_inference.jl:157-159) is ill-conditioned: both sides are
+            # float64 with different summation orders, so agreement is bounded by eps * cond(Cuu)
+            tol = max(1e-8, 100 * np.finfo(float).eps * np.linalg.cond(z[f"c{i}_U_u"]) ** 2)
+            assert relerr(m_e, z[f"c{i}_m_e"]) <= tol and relerr(Dinv, z[f"c{i}_Dinv"]) <= tol and relerr(U_u, z[f"c{i}_U_u"]) <= 1e-9
 
 
 @pytest.mark.parametrize("n,m,d,kt,ko", [(1, 1, 1, 3, 3), (1023, 50, 1, 3, 3), (1025, 129, 2, 3, 3), (8496, 81, 2, 3, 3), (5000, 40, 4, 2, 1), (3000, 17, 7, 1, 0)])
@@ -212,3 +215,56 @@ def test_exact_golden(ctx):
     assert relerr(ctx.exact_logpdf(0, 3, z["gpar_theta"]), z["gpar_lml"]) <= RTOL
     mean, var = ctx.exact_posterior(0, 3, z["gpar_theta"], z["gpar_Xs"])
     assert np.max(np.abs(mean[0] - z["gpar_mean"])) <= 1e-8 and np.max(np.abs(var - z["gpar_var"])) <= 1e-8 * np.max(z["gpar_var"]) + 1e-12
+
+
+def test_scaled_predict_against_oracle(ctx):
+    """Deterministic core of get_gpar_scaled_predictions (gpar_scaled_inference.jl:74-135) for given
+    draws eps_j ~ q_u: merged/sorted timeline, 1e10 noise at test points, fx_j = Cf*u (U_u \\ eps_j),
+    f*_j = fx_j + smooth(y* - fx_j).m[1], sample mean and corrected std."""
+    from scipy.linalg import solve_triangular
+    from oracle.predict import gpar_scaled_predict_given_eps, merge_sort
+    rng = np.random.default_rng(11)
+    n, ns, m, d, S = 400, 700, 12, 2, 9
+    t = np.sort(rng.uniform(0, 12, n)); ts = np.sort(rng.uniform(0, 13, ns))
+    X = rng.normal(size=(n, d)); Xs = rng.normal(size=(ns, d)); Z = rng.normal(size=(m, d)) * 1.5
+    y = np.sin(t) + 0.3 * X[:, 0] + 0.1 * rng.normal(size=n)
+    params = (0.9, 1.2, 1.4, 0.8, 0.12)                    # time_l, time_var, out_l, out_var, noise_sigma
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+    m_e, Dinv, U_u = ctx.compute_q_u(3, 3, np.array(params))
+    eps = m_e[None, :] + rng.normal(size=(S, m)) @ np.linalg.cholesky(Dinv).T
+    mean0, std0 = gpar_scaled_predict_given_eps(3, 3, X, Z, t, y, ts, Xs, params, m_e, U_u, eps, smooth=cport.kalman_smooth)
+    tc, perm, rev = merge_sort(t, ts)
+    ctx.set_inputs(np.concatenate([X, Xs])[perm]); ctx.set_times(tc[perm])
+    ctx.set_outputs(np.concatenate([y, np.zeros(ns)])[perm])
+    ctx.set_noise_vector(np.concatenate([np.full(n, params[4] ** 2), np.full(ns, 1e10)])[perm])
+    W = solve_triangular(U_u, eps.T, lower=False)           # (m, S): column j = U_u \ eps_j
+    mean, std = ctx.scaled_predict(3, 3, np.array(params), W)
+    ctx.set_noise_vector(None)
+    mean = mean[rev][n:]; std = std[rev][n:]
+    assert np.max(np.abs(mean - mean0)) <= 1e-8 * max(1.0, np.max(np.abs(mean0)))
+    assert np.max(np.abs(std - std0)) <= 1e-7 * max(1.0, np.max(np.abs(std0)))
+
+
+def test_reference_example_chain_end_to_end(ctx):
+    """examples/GPAR_scaled_examples.jl:86-175 through the host mirror (fit + predict, 3 outputs,
+    N = 8 496, 20 000 prediction points): the predictions track the noise-free functions."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gpar_scaled_example", os.path.join(root, "examples", "gpar_scaled_example.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    rmse, dt = mod.main(iterations=120, seed=0, true_samples=20000, quiet=True)
+    # observation noise std is 0.8^2 = 0.64 (toy_data.jl:29 quirk); a fitted model must do far better than that
+    assert rmse[0] < 0.15 and rmse[1] < 0.25 and rmse[2] < 0.8, rmse
+
+
+def test_chain_fit_and_predict_small(ctx):
+    from gpar_at_scale_b200 import chain, data
+    rng = np.random.default_rng(5)
+    x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
+    Y = np.stack(y_obs)
+    best, info = chain.fit_chain(x, Y, M=40, n_restarts=2, iterations=60, seed=1, ctx=ctx)
+    assert set(best) == {0, 1, 2} and info["tasks"] == 6
+    means, spreads = chain.predict_chain(x, Y, x_true, 40, best, nsamples=20, seed=1, ctx=ctx)
+    inside = x_true <= x.max()
+    assert np.sqrt(np.mean((means[0][inside] - y_true[0][inside]) ** 2)) < 0.3
+    assert np.all(np.isfinite(means)) and np.all(spreads >= 0)
