@@ -34,10 +34,13 @@ def main(iterations=150, seed=0, true_samples=100000, quiet=False):
                                                      debug=not quiet, rng=rng)                                        # :165-175
     dt = time.perf_counter() - t0
     inside = x_true <= x.max()
-    rmse = [float(np.sqrt(np.mean((o[inside] - tr[inside]) ** 2))) for o, tr in ((y1_out, test_y1), (y2_out, test_y2), (y3_out, test_y3))]
+    pairs = ((y1_out, test_y1), (y2_out, test_y2), (y3_out, test_y3))
+    rmse = [float(np.sqrt(np.mean((o[inside] - tr[inside]) ** 2))) for o, tr in pairs]
+    nrmse = [r / float(np.std(tr[inside])) for r, (o, tr) in zip(rmse, pairs)]      # relative to the spread of the true function
     if not quiet:
-        print("fit + predict: %.1f s; RMSE vs true functions on the training span: y1 %.3f  y2 %.3f  y3 %.3f" % (dt, *rmse))
-    return rmse, dt
+        print("fit + predict: %.1f s; RMSE vs true functions on the training span: y1 %.3f  y2 %.3f  y3 %.3f (normalised %.3f %.3f %.3f)"
+              % (dt, *rmse, *nrmse))
+    return nrmse, dt
 
 
 if __name__ == "__main__":

@@ -192,7 +192,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
   const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
   const double* yb = y + (int64_t)b * N;
-  double sum_logS = 0.0, sum_a2 = 0.0;
+  double sum_logS = 0.0, sum_a2 = 0.0, prodS = 1.0;
   const int64_t kend = SMOOTH ? k1 + 1 : k1;    // one extra predict closes the chunk's last smoothing element
   for (int64_t k = k0; k < kend; k++) {
     double A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>];
@@ -238,16 +238,19 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
     }
     if (k >= k1) break;
     const double R = rvec ? __ldg(rvec + k) : noise;
-    const double S = Pp[0] + R, sq = sqrt(S);
-    const double a = (__ldg(yb + k) - mp[0]) / sq;
+    const double S = Pp[0] + R, rs = rsqrt(S);          // one reciprocal square root instead of sqrt + D+1 divisions
+    const double a = (__ldg(yb + k) - mp[0]) * rs;
     double Bv[D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { Bv[i] = SYM(Pp, 0, i) / sq; m[i] = fma(Bv[i], a, mp[i]); }
+    for (int i = 0; i < D; i++) { Bv[i] = SYM(Pp, 0, i) * rs; m[i] = fma(Bv[i], a, mp[i]); }
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
       for (int j = i; j < D; j++) SYM(P, i, j) = fma(-Bv[i], Bv[j], SYM(Pp, i, j));
-    sum_logS += log(S); sum_a2 = fma(a, a, sum_a2);
+    // sum log S_k as the log of a running product, flushed every 8 steps (S in [1e-12, 1e10]: no over/underflow)
+    prodS *= S;
+    if (((k - k0) & 7) == 7) { sum_logS += log(prodS); prodS = 1.0; }
+    sum_a2 = fma(a, a, sum_a2);
     if (alpha) alpha[(int64_t)b * N + k] = a;
     if (!SMOOTH && table) {   // shared-model step table for the affine mean scans (scaled.cu)
       double* row = table + k * (D * D + 2 * D + 1);
@@ -260,7 +263,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
         row[D * D + i] = Kg;
         row[D * D + D + i] = A[i];
       }
-      row[D * D + 2 * D] = 1.0 / sq;
+      row[D * D + 2 * D] = rs;
     }
     if (SMOOTH) {
 #pragma unroll
@@ -269,7 +272,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
       for (int i = 0; i < NSYM<D>; i++) fs[((int64_t)(D + i) * batch + b) * N + k] = P[i];
     }
   }
-  part[((int64_t)b * nC + c) * 2 + 0] = sum_logS;
+  part[((int64_t)b * nC + c) * 2 + 0] = sum_logS + log(prodS);
   part[((int64_t)b * nC + c) * 2 + 1] = sum_a2;
   if (SMOOTH) store_elem(comp, s0.base, (int64_t)batch * s0.P, (int64_t)b * s0.P + (nC - 1 - c));
 }

@@ -11,7 +11,8 @@
 //  * operands come pre-evaluated in the fragment-native panel layout (kuf_panel.cu) and are
 //    staged with ONE cp.async.bulk (TMA engine, SASS UBLKCP) of 32 KB per operand per stage into
 //    a 3-stage, mbarrier-synchronised shared-memory ring by a dedicated producer warp;
-//  * 8 consumer warps each own a 32 x 64 accumulator tile (32 DMMA per k4-step, 12 LDS.64);
+//  * 8 consumer warps each own a 32 x 64 accumulator tile (32 DMMA per k4-step, 12 LDS.64); the
+//    diagonal tiles of G use a triangular 16x16-block mapping (20 DMMA per warp and k4-step);
 //  * persistent stream-K schedule: the (tile-job x k-block) space is cut into one contiguous
 //    range per CTA (grid = #SMs), so all 148 SMs are busy for any M; a CTA's partial tile goes to a
 //    workspace slot and a second kernel sums the slots of each job in fixed order (deterministic,
@@ -63,6 +64,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// lower-triangular 16x16 blocks (row, col, valid) of a 128 x 128 diagonal tile, 5 per consumer warp
+__constant__ unsigned char c_diag_blocks[8][5][4] = {
+  {{7, 0, 1, 0}, {7, 1, 1, 0}, {7, 2, 1, 0}, {7, 3, 1, 0}, {7, 4, 1, 0}},
+  {{7, 5, 1, 0}, {7, 6, 1, 0}, {7, 7, 1, 0}, {1, 0, 1, 0}, {1, 1, 1, 0}},
+  {{6, 0, 1, 0}, {6, 1, 1, 0}, {6, 2, 1, 0}, {6, 3, 1, 0}, {6, 4, 1, 0}},
+  {{6, 5, 1, 0}, {6, 6, 1, 0}, {2, 0, 1, 0}, {2, 1, 1, 0}, {2, 2, 1, 0}},
+  {{5, 0, 1, 0}, {5, 1, 1, 0}, {5, 2, 1, 0}, {5, 3, 1, 0}, {5, 4, 1, 0}},
+  {{5, 5, 1, 0}, {3, 0, 1, 0}, {3, 1, 1, 0}, {3, 2, 1, 0}, {3, 3, 1, 0}},
+  {{4, 0, 1, 0}, {4, 1, 1, 0}, {4, 2, 1, 0}, {4, 3, 1, 0}, {4, 4, 1, 0}},
+  {{0, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}};
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 panel_syrk_kernel(const double* __restrict__ pK, const double* __restrict__ pD, int64_t tile_stride /*doubles per M-tile panel*/,
                   const Seg* __restrict__ segs, const int* __restrict__ cta_seg, double* __restrict__ partial) {
@@ -100,40 +112,82 @@ panel_syrk_kernel(const double* __restrict__ pK, const double* __restrict__ pD, 
   const int wr = warp >> 1, wc = warp & 1;     // 4 x 2 warps over the 128 x 128 tile
   for (int si = s0; si < s1; si++) {
     const Seg sg = segs[si];
-    const bool same = (sg.b_panel == 0 && sg.a_tile == sg.b_tile);
-    double acc[4][8][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int kb = sg.kb0; kb < sg.kb1; kb++) {
-      mbar_wait(&full[stage], phase);
-      const double* A = sA + stage * STAGE_DOUBLES + wr * 32 * 4 + lane;
-      const double* B = (same ? sA : sB) + stage * STAGE_DOUBLES + wc * 64 * 4 + lane;
-#pragma unroll
-      for (int k4 = 0; k4 < GPAR_KT / 4; k4++) {
-        double af[4], bf[8];
-#pragma unroll
-        for (int i = 0; i < 4; i++) af[i] = A[k4 * (GPAR_TILE * 4) + i * 32];
-#pragma unroll
-        for (int j = 0; j < 8; j++) bf[j] = B[k4 * (GPAR_TILE * 4) + j * 32];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-    }
+    const bool diag = (sg.b_panel == 0 && sg.a_tile == sg.b_tile);
     double* out = partial + (int64_t)sg.slot * (GPAR_TILE * GPAR_TILE);
+    if (!diag) {
+      double acc[4][8][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        int r = wr * 32 + i * 8 + (lane >> 2), c = wc * 64 + j * 8 + (lane & 3) * 2;
-        *reinterpret_cast<double2*>(out + r * GPAR_TILE + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int kb = sg.kb0; kb < sg.kb1; kb++) {
+        mbar_wait(&full[stage], phase);
+        const double* A = sA + stage * STAGE_DOUBLES + wr * 32 * 4 + lane;
+        const double* B = sB + stage * STAGE_DOUBLES + wc * 64 * 4 + lane;
+#pragma unroll
+        for (int k4 = 0; k4 < GPAR_KT / 4; k4++) {
+          double af[4], bf[8];
+#pragma unroll
+          for (int i = 0; i < 4; i++) af[i] = A[k4 * (GPAR_TILE * 4) + i * 32];
+#pragma unroll
+          for (int j = 0; j < 8; j++) bf[j] = B[k4 * (GPAR_TILE * 4) + j * 32];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          int r = wr * 32 + i * 8 + (lane >> 2), c = wc * 64 + j * 8 + (lane & 3) * 2;
+          *reinterpret_cast<double2*>(out + r * GPAR_TILE + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    } else {
+      // Diagonal tile of G: only the lower triangle is needed.  In 16x16 blocks that is 36 of 64;
+      // a static table gives every warp 5 blocks (4 padding blocks on warp 7), i.e. 20 DMMA per warp
+      // and k4-step instead of 32.  Offsets are loop-invariant registers, accumulators are static.
+      double acc[5][2][2][2];
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[i][q >> 1][q & 1][0] = acc[i][q >> 1][q & 1][1] = 0.0;
+      int offA[5], offB[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) { offA[i] = c_diag_blocks[warp][i][0] * 64; offB[i] = c_diag_blocks[warp][i][1] * 64; }
+      for (int kb = sg.kb0; kb < sg.kb1; kb++) {
+        mbar_wait(&full[stage], phase);
+        const double* P = sA + stage * STAGE_DOUBLES + lane;
+#pragma unroll
+        for (int k4 = 0; k4 < GPAR_KT / 4; k4++) {
+          const double* Pk = P + k4 * (GPAR_TILE * 4);
+          double a[5][2], b[5][2];
+#pragma unroll
+          for (int i = 0; i < 5; i++) { a[i][0] = Pk[offA[i]]; a[i][1] = Pk[offA[i] + 32]; b[i][0] = Pk[offB[i]]; b[i][1] = Pk[offB[i] + 32]; }
+#pragma unroll
+          for (int i = 0; i < 5; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) dmma884(acc[i][q >> 1][q & 1][0], acc[i][q >> 1][q & 1][1], a[i][q >> 1], b[i][q & 1]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        if (c_diag_blocks[warp][i][2]) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            int r = (offA[i] >> 2) + (q >> 1) * 8 + (lane >> 2), c = (offB[i] >> 2) + (q & 1) * 8 + (lane & 3) * 2;
+            *reinterpret_cast<double2*>(out + r * GPAR_TILE + c) = make_double2(acc[i][q >> 1][q & 1][0], acc[i][q >> 1][q & 1][1]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -172,20 +226,36 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
     for (int i = 0; i < T; i++)
       for (int j = 0; j < T; j++) jobs.push_back(Job{i, j, 1, 0, 0, 0, 0, 0});
   const int J = (int)jobs.size();
-  const int64_t W = (int64_t)J * NBK;
+  // cost-weighted stream-K: a k-block of a regular job issues 32 DMMA per warp and k4-step, of a
+  // diagonal G job 20; cut the cumulative cost into one equal range per CTA.
+  std::vector<int64_t> base(J + 1, 0);
+  std::vector<int> cost(J);
+  for (int j = 0; j < J; j++) {
+    cost[j] = (jobs[j].b_panel == 0 && jobs[j].a_tile == jobs[j].b_tile) ? 20 : 32;
+    base[j + 1] = base[j] + (int64_t)cost[j] * NBK;
+  }
+  const int64_t W = base[J];
   int C = ctx->num_sms;
-  if (W < C) C = (int)W;
+  if ((int64_t)J * NBK < C) C = (int)((int64_t)J * NBK);
   if (C < 1) C = 1;
+  // boundary c -> (job, k-block), rounded to whole k-blocks
+  auto locate = [&](int64_t w, int& job, int64_t& kb) {
+    int j = (int)(std::upper_bound(base.begin(), base.end(), w) - base.begin()) - 1;
+    if (j >= J) { job = J; kb = 0; return; }
+    kb = (w - base[j] + cost[j] / 2) / cost[j];
+    if (kb >= NBK) { job = j + 1; kb = 0; } else job = j;
+  };
   std::vector<Seg> segs;
   std::vector<int> cta_seg(C + 1, 0);
+  int pj = 0; int64_t pk = 0;
   for (int c = 0; c < C; c++) {
-    int64_t w0 = W * c / C, w1 = W * (c + 1) / C;
+    int ej; int64_t ek;
+    if (c == C - 1) { ej = J; ek = 0; } else locate(W * (c + 1) / C, ej, ek);
     cta_seg[c] = (int)segs.size();
-    while (w0 < w1) {
-      int j = (int)(w0 / NBK);
-      int64_t kb0 = w0 % NBK, kb1 = std::min<int64_t>(NBK, kb0 + (w1 - w0));
-      segs.push_back(Seg{jobs[j].a_tile, jobs[j].b_tile, jobs[j].b_panel, (int)kb0, (int)kb1, 0, j, 0});
-      w0 += kb1 - kb0;
+    while (pj < ej || (pj == ej && pk < ek)) {
+      int64_t kend = (pj < ej) ? NBK : ek;
+      if (kend > pk) segs.push_back(Seg{jobs[pj].a_tile, jobs[pj].b_tile, jobs[pj].b_panel, (int)pk, (int)kend, 0, pj, 0});
+      if (pj < ej) { pj++; pk = 0; } else pk = kend;
     }
   }
   cta_seg[C] = (int)segs.size();

@@ -252,9 +252,10 @@ def test_reference_example_chain_end_to_end(ctx):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("gpar_scaled_example", os.path.join(root, "examples", "gpar_scaled_example.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
-    rmse, dt = mod.main(iterations=120, seed=0, true_samples=20000, quiet=True)
-    # observation noise std is 0.8^2 = 0.64 (toy_data.jl:29 quirk); a fitted model must do far better than that
-    assert rmse[0] < 0.15 and rmse[1] < 0.25 and rmse[2] < 0.8, rmse
+    nrmse, dt = mod.main(iterations=120, seed=0, true_samples=20000, quiet=True)
+    # RMSE against the noise-free functions, relative to their spread (observation noise std is 0.64,
+    # toy_data.jl:29 quirk; y3 = y2 y1^2 + 0.1 x has a spread of several units)
+    assert nrmse[0] < 0.25 and nrmse[1] < 0.35 and nrmse[2] < 0.6, nrmse
 
 
 def test_chain_fit_and_predict_small(ctx):
