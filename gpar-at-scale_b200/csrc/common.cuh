@@ -156,7 +156,6 @@ int launch_kuf_panels(gpar_ctx* ctx, int kind, bool grad, double l, double s,
                       double* panelK, double* panelD, double* gpart, int nsplit, int64_t Npad, int Mpad);
 int launch_reduce_gh(gpar_ctx* ctx, const double* gpart, int nsplit, int Mpad, int nvec, double* out);
 // panel_syrk.cu
-struct SyrkPlan { int njobs_g, njobs_h, nseg, nctas; };
 int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, int64_t Npad, int Mpad,
                    int M, bool with_h, double* G, double* H);
 // kalman.cu: filter / smoother on device buffers.  hl/hs/hn: host arrays (nparam = 1 or batch) of

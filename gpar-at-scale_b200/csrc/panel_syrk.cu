@@ -18,7 +18,7 @@
 //    workspace slot and a second kernel sums the slots of each job in fixed order (deterministic,
 //    no atomics) and writes G (mirrored) / H column-major.
 #include "common.cuh"
-#include <algorithm>
+#include "syrk_plan.h"
 
 namespace {
 
@@ -29,14 +29,8 @@ constexpr int NCONSUMER_WARPS = 8;
 constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;
 constexpr size_t SMEM_BYTES = (size_t)2 * STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
 
-struct Seg {      // one contiguous k-block range of one tile-job, processed by one CTA
-  int a_tile, b_tile;   // M-tile index of the A (rows) and B (cols) operand
-  int b_panel;          // 0: B from panel K (G job), 1: B from panel D (H job)
-  int kb0, kb1;         // k-block range [kb0, kb1)
-  int slot;             // partial-tile slot in the workspace
-  int job, pad;
-};
-struct Job { int a_tile, b_tile, b_panel, slot0, nslots, pad0, pad1, pad2; };
+typedef SyrkSeg Seg;
+typedef SyrkJob Job;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -219,61 +213,12 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
                    bool with_h, double* G, double* H) {
   const int T = Mpad / GPAR_TILE;
   const int64_t NBK = Npad / GPAR_KT;
-  std::vector<Job> jobs;
-  for (int i = 0; i < T; i++)
-    for (int j = 0; j <= i; j++) jobs.push_back(Job{i, j, 0, 0, 0, 0, 0, 0});
-  if (with_h)
-    for (int i = 0; i < T; i++)
-      for (int j = 0; j < T; j++) jobs.push_back(Job{i, j, 1, 0, 0, 0, 0, 0});
+  SyrkPlan pl = plan_syrk(T, NBK, with_h, ctx->num_sms);
+  std::vector<Job>& jobs = pl.jobs;
+  std::vector<Seg>& segs = pl.segs;
+  std::vector<int>& cta_seg = pl.cta_seg;
   const int J = (int)jobs.size();
-  // cost-weighted stream-K: a k-block of a regular job issues 32 DMMA per warp and k4-step, of a
-  // diagonal G job 20; cut the cumulative cost into one equal range per CTA.
-  std::vector<int64_t> base(J + 1, 0);
-  std::vector<int> cost(J);
-  for (int j = 0; j < J; j++) {
-    cost[j] = (jobs[j].b_panel == 0 && jobs[j].a_tile == jobs[j].b_tile) ? 20 : 32;
-    base[j + 1] = base[j] + (int64_t)cost[j] * NBK;
-  }
-  const int64_t W = base[J];
-  int C = ctx->num_sms;
-  if ((int64_t)J * NBK < C) C = (int)((int64_t)J * NBK);
-  if (C < 1) C = 1;
-  // boundary c -> (job, k-block), rounded to whole k-blocks
-  auto locate = [&](int64_t w, int& job, int64_t& kb) {
-    int j = (int)(std::upper_bound(base.begin(), base.end(), w) - base.begin()) - 1;
-    if (j >= J) { job = J; kb = 0; return; }
-    kb = (w - base[j] + cost[j] / 2) / cost[j];
-    if (kb >= NBK) { job = j + 1; kb = 0; } else job = j;
-  };
-  std::vector<Seg> segs;
-  std::vector<int> cta_seg(C + 1, 0);
-  int pj = 0; int64_t pk = 0;
-  for (int c = 0; c < C; c++) {
-    int ej; int64_t ek;
-    if (c == C - 1) { ej = J; ek = 0; } else locate(W * (c + 1) / C, ej, ek);
-    cta_seg[c] = (int)segs.size();
-    while (pj < ej || (pj == ej && pk < ek)) {
-      int64_t kend = (pj < ej) ? NBK : ek;
-      if (kend > pk) segs.push_back(Seg{jobs[pj].a_tile, jobs[pj].b_tile, jobs[pj].b_panel, (int)pk, (int)kend, 0, pj, 0});
-      if (pj < ej) { pj++; pk = 0; } else pk = kend;
-    }
-  }
-  cta_seg[C] = (int)segs.size();
-  // slots: segments of a job are consecutive in w-order, so number them in that order
-  {
-    int slot = 0;
-    std::vector<int> order(segs.size());
-    for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      if (segs[a].job != segs[b].job) return segs[a].job < segs[b].job;
-      return segs[a].kb0 < segs[b].kb0; });
-    for (int idx : order) {
-      Job& jb = jobs[segs[idx].job];
-      if (jb.nslots == 0) jb.slot0 = slot;
-      jb.nslots++;
-      segs[idx].slot = slot++;
-    }
-  }
+  const int C = pl.C;
   const size_t nseg = segs.size();
   CU(ctx->partial.reserve(nseg * GPAR_TILE * GPAR_TILE * sizeof(double)));
   CU(ctx->segs.reserve(nseg * sizeof(Seg) + (C + 1) * sizeof(int) + 64));
