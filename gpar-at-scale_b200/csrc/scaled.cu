@@ -16,152 +16,278 @@
 //  3. G = beta^T beta by the DMMA panel SYRK (panel_syrk.cu); the M x M tail follows dtc.jl:119-125.
 #include "lgssm_math.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
 constexpr int WH_GROUPS = 256;   // 4-step groups per whitening chunk (1024 steps)
 
-// pass 1: K panel + zero-state chunk response b_c[m] (D doubles) -> resp[(c*D + i)*Mpad + m]
-template <int KIND, int DX, int D>
+
+// ---- shared-memory staging of the per-step table (Phi_k, K_k, HA_k, S_k^-1/2) -------------------
+// Every thread of a whitening block walks the same steps, and the loads of a step's row sit on the
+// critical path of the recurrence; rows are therefore streamed with cp.async into a double-buffered
+// shared-memory window WH_SUB steps ahead of their use.
+constexpr int WH_SUB = 64;      // steps per staged window (16 groups of 4)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
+template <int TS>
+__device__ __forceinline__ void stage_table(double* buf, const double* __restrict__ table, int64_t step0, int64_t N) {
+  int64_t nrows = N - step0; if (nrows > WH_SUB) nrows = WH_SUB; if (nrows < 0) nrows = 0;
+  const int total = (int)nrows * TS;
+  const double* src = table + step0 * TS;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) cp_async8(buf + e, src + e);
+  cp_async_commit();
+}
+
+// pass 1: K panel + zero-state chunk response b_c[m] (D doubles) -> resp[(c*D + i)*Mpad + m].
+// Each thread carries CT columns (one per M-tile mt0..mt0+CT-1) so that a step's table row
+// (Phi_k, K_k — shared by every column) is loaded once per CT kernel evaluations.
+template <int KIND, int DX, int D, int CT>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
                     const double* __restrict__ table, double* __restrict__ panel, double* __restrict__ resp, int Mpad) {
   constexpr int TS = D * D + 2 * D + 1;
-  const int mt = blockIdx.x, mi = threadIdx.x, m = mt * GPAR_TILE + mi;
-  const bool mvalid = m < M;
-  double z[DX];
-#pragma unroll
-  for (int d = 0; d < DX; d++) z[d] = mvalid ? Z[(int64_t)m * DX + d] : 0.0;
+  const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
+  double z[CT][DX], ms[CT][D];
+  bool mvalid[CT];
+  double* out[CT];
   const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
   const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
-  double* out = panel + (((int64_t)mt * NB4 + g0) * GPAR_TILE + mi) * 4;
-  double ms[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) ms[i] = 0.0;
-  for (int64_t g = g0; g < g1; g++) {
-    double kv[4];
+  for (int c = 0; c < CT; c++) {
+    const int m = (mt0 + c) * GPAR_TILE + mi;
+    mvalid[c] = m < M;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int64_t n = g * 4 + j;
-      const bool valid = n < N;
-      const int64_t nn = valid ? n : N - 1;
-      double d2 = 0.0;
+    for (int d = 0; d < DX; d++) z[c][d] = mvalid[c] ? Z[(int64_t)m * DX + d] : 0.0;
 #pragma unroll
-      for (int d = 0; d < DX; d++) { double df = __ldg(X + nn * DX + d) - z[d]; d2 = fma(df, df, d2); }
-      double dummy; double k = base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
-      k = (valid && mvalid) ? s * k : 0.0;
-      kv[j] = k;
-      if (valid) {   // m <- Phi m + K v
-        const double* row = table + nn * TS;
-        double nm[D];
+    for (int i = 0; i < D; i++) ms[c][i] = 0.0;
+    out[c] = panel + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
+  }
+  __shared__ double tbl[2][WH_SUB * TS];
+  stage_table<TS>(tbl[0], table, g0 * 4, N);
+  int cur = 0;
+  for (int64_t gs = g0; gs < g1; gs += WH_SUB / 4) {
+    if (gs + WH_SUB / 4 < g1) { stage_table<TS>(tbl[cur ^ 1], table, (gs + WH_SUB / 4) * 4, N); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int64_t ge = (gs + WH_SUB / 4 < g1) ? gs + WH_SUB / 4 : g1;
+    for (int64_t g = gs; g < ge; g++) {
+      double kv[CT][4];
 #pragma unroll
-        for (int i = 0; i < D; i++) { double v = __ldg(row + D * D + i) * k;
+      for (int j = 0; j < 4; j++) {
+        const int64_t n = g * 4 + j;
+        const bool valid = n < N;
+        const int64_t nn = valid ? n : N - 1;
+        double x[DX], F[D * D], Kg[D];
 #pragma unroll
-          for (int q = 0; q < D; q++) v = fma(__ldg(row + i * D + q), ms[q], v);
-          nm[i] = v; }
+        for (int d = 0; d < DX; d++) x[d] = __ldg(X + nn * DX + d);
+        const double* row = tbl[cur] + (int)(n - gs * 4) * TS;
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < D; i++) ms[i] = nm[i];
+          for (int i = 0; i < D * D; i++) F[i] = row[i];
+#pragma unroll
+          for (int i = 0; i < D; i++) Kg[i] = row[D * D + i];
+        }
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+          double d2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < DX; d++) { double df = x[d] - z[c][d]; d2 = fma(df, df, d2); }
+          double dummy; double k = base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
+          k = (valid && mvalid[c]) ? s * k : 0.0;
+          kv[c][j] = k;
+          if (valid) {   // m <- Phi m + K v
+            double nm[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) { double v = Kg[i] * k;
+#pragma unroll
+              for (int q = 0; q < D; q++) v = fma(F[i * D + q], ms[c][q], v);
+              nm[i] = v; }
+#pragma unroll
+            for (int i = 0; i < D; i++) ms[c][i] = nm[i];
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CT; c++) {
+        reinterpret_cast<double2*>(out[c])[0] = make_double2(kv[c][0], kv[c][1]);
+        reinterpret_cast<double2*>(out[c])[1] = make_double2(kv[c][2], kv[c][3]);
+        out[c] += GPAR_TILE * 4;
       }
     }
-    reinterpret_cast<double2*>(out)[0] = make_double2(kv[0], kv[1]);
-    reinterpret_cast<double2*>(out)[1] = make_double2(kv[2], kv[3]);
-    out += GPAR_TILE * 4;
+    __syncthreads();
+    cur ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < D; i++) resp[((int64_t)blockIdx.y * D + i) * Mpad + m] = ms[i];
+  for (int c = 0; c < CT; c++)
+#pragma unroll
+    for (int i = 0; i < D; i++) resp[((int64_t)blockIdx.y * D + i) * Mpad + (mt0 + c) * GPAR_TILE + mi] = ms[c][i];
 }
 
-// chunk transition Psi_c = Phi_{k1-1} ... Phi_{k0}: lane j < D propagates e_j through the chunk.
+// chunk transition Psi_c = Phi_{k1-1} ... Phi_{k0}: one warp per chunk; lane l multiplies its own
+// contiguous run of steps (independent loads, pipelined), then an ordered shuffle tree multiplies
+// the 32 partial products (later steps on the left).
 template <int D>
-__global__ void chunk_transition_kernel(const double* __restrict__ table, int64_t N, double* __restrict__ psi) {
+__global__ void __launch_bounds__(32)
+chunk_transition_kernel(const double* __restrict__ table, int64_t N, double* __restrict__ psi) {
   constexpr int TS = D * D + 2 * D + 1;
-  const int c = blockIdx.x, j = threadIdx.x;
-  if (j >= D) return;
+  const int c = blockIdx.x, lane = threadIdx.x;
   const int64_t k0 = (int64_t)c * WH_GROUPS * 4, k1 = (k0 + (int64_t)WH_GROUPS * 4 < N) ? k0 + (int64_t)WH_GROUPS * 4 : N;
-  double v[D];
+  constexpr int PER = WH_GROUPS * 4 / 32;
+  double Pm[D * D];
 #pragma unroll
-  for (int i = 0; i < D; i++) v[i] = (i == j) ? 1.0 : 0.0;
-  for (int64_t k = k0; k < k1; k++) {
-    const double* row = table + k * TS;
-    double nv[D];
+  for (int i = 0; i < D * D; i++) Pm[i] = (i / D == i % D) ? 1.0 : 0.0;
+  const int64_t a0 = k0 + (int64_t)lane * PER;
+#pragma unroll 4
+  for (int q = 0; q < PER; q++) {
+    const int64_t k = a0 + q;
+    if (k < k1) {
+      const double* row = table + k * TS;
+      double F[D * D], R[D * D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { double a = 0.0;
+      for (int i = 0; i < D * D; i++) F[i] = __ldg(row + i);
+      matmul<D>(F, Pm, R);
 #pragma unroll
-      for (int q = 0; q < D; q++) a = fma(row[i * D + q], v[q], a);
-      nv[i] = a; }
-#pragma unroll
-    for (int i = 0; i < D; i++) v[i] = nv[i];
+      for (int i = 0; i < D * D; i++) Pm[i] = R[i];
+    }
   }
+  // ordered reduction: after round d, lane l (l % 2d == 0) holds the product of lanes l .. l+2d-1
 #pragma unroll
-  for (int i = 0; i < D; i++) psi[(int64_t)c * D * D + i * D + j] = v[i];
+  for (int d = 1; d < 32; d <<= 1) {
+    double O[D * D], R[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) O[i] = __shfl_down_sync(0xffffffffu, Pm[i], d);
+    matmul<D>(O, Pm, R);     // the partner covers LATER steps: it multiplies from the left
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Pm[i] = R[i];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) psi[(int64_t)c * D * D + i] = Pm[i];
+  }
 }
 
-// carry scan over chunks, one thread per column: start[c] = state entering chunk c (in place over resp)
+// carry scan over chunks, one thread per column: start[c] = state entering chunk c (in place over
+// resp).  The chain is latency-bound (one dependent 3x3 mat-vec per chunk), so the loads of the next
+// 8 chunks are issued ahead of the dependent arithmetic.
 template <int D>
-__global__ void carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Mpad) {
+__global__ void __launch_bounds__(32)
+carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Mpad) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mpad) return;
+  constexpr int PF = 8;
   double st[D];
 #pragma unroll
   for (int i = 0; i < D; i++) st[i] = 0.0;
-  for (int c = 0; c < nch; c++) {
-    double b[D], nx[D];
+  for (int c0 = 0; c0 < nch; c0 += PF) {
+    double b[PF][D], ps[PF][D * D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { b[i] = resp[((int64_t)c * D + i) * Mpad + m]; resp[((int64_t)c * D + i) * Mpad + m] = st[i]; }
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
 #pragma unroll
-    for (int i = 0; i < D; i++) { double a = b[i];
+        for (int i = 0; i < D; i++) b[u][i] = resp[((int64_t)c * D + i) * Mpad + m];
 #pragma unroll
-      for (int q = 0; q < D; q++) a = fma(psi[(int64_t)c * D * D + i * D + q], st[q], a);
-      nx[i] = a; }
+        for (int i = 0; i < D * D; i++) ps[u][i] = __ldg(psi + (int64_t)c * D * D + i);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < D; i++) st[i] = nx[i];
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) { resp[((int64_t)c * D + i) * Mpad + m] = st[i]; double a = b[u][i];
+#pragma unroll
+          for (int q = 0; q < D; q++) a = fma(ps[u][i * D + q], st[q], a);
+          nx[i] = a; }
+#pragma unroll
+        for (int i = 0; i < D; i++) st[i] = nx[i];
+      }
+    }
   }
 }
 
-// pass 2: in-place whitening of the panel: beta = (K - HA m) / sqrt(S); m <- Phi m + K_k K; g partials
-template <int D>
+// pass 2: in-place whitening of the panel: beta = (K - HA m) / sqrt(S); m <- Phi m + K_k K; g partials.
+// CT columns per thread share each step's table row, as in pass 1.
+template <int D, int CT>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass2_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ alpha,
                     double* __restrict__ panel, const double* __restrict__ start, double* __restrict__ gpart, int Mpad) {
   constexpr int TS = D * D + 2 * D + 1;
-  const int mt = blockIdx.x, mi = threadIdx.x, m = mt * GPAR_TILE + mi;
+  const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
   const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
-  double* io = panel + (((int64_t)mt * NB4 + g0) * GPAR_TILE + mi) * 4;
-  double ms[D];
+  double* io[CT];
+  double ms[CT][D], gacc[CT];
 #pragma unroll
-  for (int i = 0; i < D; i++) ms[i] = start[((int64_t)blockIdx.y * D + i) * Mpad + m];
-  double gacc = 0.0;
-  for (int64_t g = g0; g < g1; g++) {
-    double2 a01 = reinterpret_cast<double2*>(io)[0], a23 = reinterpret_cast<double2*>(io)[1];
-    double kv[4] = {a01.x, a01.y, a23.x, a23.y};
+  for (int c = 0; c < CT; c++) {
+    io[c] = panel + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int64_t n = g * 4 + j;
-      if (n < N) {
-        const double* row = table + n * TS;
-        double pred = 0.0;
+    for (int i = 0; i < D; i++) ms[c][i] = start[((int64_t)blockIdx.y * D + i) * Mpad + (mt0 + c) * GPAR_TILE + mi];
+    gacc[c] = 0.0;
+  }
+  __shared__ double tbl[2][WH_SUB * TS];
+  stage_table<TS>(tbl[0], table, g0 * 4, N);
+  int cur = 0;
+  for (int64_t gs = g0; gs < g1; gs += WH_SUB / 4) {
+    if (gs + WH_SUB / 4 < g1) { stage_table<TS>(tbl[cur ^ 1], table, (gs + WH_SUB / 4) * 4, N); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int64_t ge = (gs + WH_SUB / 4 < g1) ? gs + WH_SUB / 4 : g1;
+    for (int64_t g = gs; g < ge; g++) {
+      double kv[CT][4];
 #pragma unroll
-        for (int q = 0; q < D; q++) pred = fma(__ldg(row + D * D + D + q), ms[q], pred);
-        const double k = kv[j];
-        const double beta = (k - pred) * __ldg(row + D * D + 2 * D);
-        double nm[D];
+      for (int c = 0; c < CT; c++) {
+        double2 a01 = reinterpret_cast<double2*>(io[c])[0], a23 = reinterpret_cast<double2*>(io[c])[1];
+        kv[c][0] = a01.x; kv[c][1] = a01.y; kv[c][2] = a23.x; kv[c][3] = a23.y;
+      }
 #pragma unroll
-        for (int i = 0; i < D; i++) { double v = __ldg(row + D * D + i) * k;
+      for (int j = 0; j < 4; j++) {
+        const int64_t n = g * 4 + j;
+        if (n < N) {
+          const double* row = tbl[cur] + (int)(n - gs * 4) * TS;
+          double F[D * D], Kg[D], ha[D];
 #pragma unroll
-          for (int q = 0; q < D; q++) v = fma(__ldg(row + i * D + q), ms[q], v);
-          nm[i] = v; }
+          for (int i = 0; i < D * D; i++) F[i] = row[i];
 #pragma unroll
-        for (int i = 0; i < D; i++) ms[i] = nm[i];
-        kv[j] = beta;
-        gacc = fma(beta, __ldg(alpha + n), gacc);
+          for (int i = 0; i < D; i++) { Kg[i] = row[D * D + i]; ha[i] = row[D * D + D + i]; }
+          const double rs = row[D * D + 2 * D], an = __ldg(alpha + n);
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            double pred = 0.0;
+#pragma unroll
+            for (int q = 0; q < D; q++) pred = fma(ha[q], ms[c][q], pred);
+            const double k = kv[c][j];
+            const double beta = (k - pred) * rs;
+            double nm[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) { double v = Kg[i] * k;
+#pragma unroll
+              for (int q = 0; q < D; q++) v = fma(F[i * D + q], ms[c][q], v);
+              nm[i] = v; }
+#pragma unroll
+            for (int i = 0; i < D; i++) ms[c][i] = nm[i];
+            kv[c][j] = beta;
+            gacc[c] = fma(beta, an, gacc[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CT; c++) {
+        reinterpret_cast<double2*>(io[c])[0] = make_double2(kv[c][0], kv[c][1]);
+        reinterpret_cast<double2*>(io[c])[1] = make_double2(kv[c][2], kv[c][3]);
+        io[c] += GPAR_TILE * 4;
       }
     }
-    reinterpret_cast<double2*>(io)[0] = make_double2(kv[0], kv[1]);
-    reinterpret_cast<double2*>(io)[1] = make_double2(kv[2], kv[3]);
-    io += GPAR_TILE * 4;
+    __syncthreads();
+    cur ^= 1;
   }
-  gpart[(int64_t)blockIdx.y * Mpad + m] = gacc;
+#pragma unroll
+  for (int c = 0; c < CT; c++) gpart[(int64_t)blockIdx.y * Mpad + (mt0 + c) * GPAR_TILE + mi] = gacc[c];
 }
 
 // bare Kuu + jitter I
@@ -205,16 +331,27 @@ __global__ void panel_to_dense_t_kernel(const double* __restrict__ panel, int64_
   Bt[e] = panel[((((int64_t)(m / GPAR_TILE)) * NB4 + n / 4) * GPAR_TILE + (m % GPAR_TILE)) * 4 + (n % 4)];
 }
 
-template <int KIND, int D>
+template <int KIND, int D, int CT>
 int launch_pass1_dx(gpar_ctx* ctx, int DX, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
                     const double* table, double* panel, double* resp, int Mpad) {
-#define CASE_DX(DD) case DD: LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad); break;
+#define CASE_DX(DD) case DD: LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad); break;
   switch (DX) {
     CASE_DX(1) CASE_DX(2) CASE_DX(3) CASE_DX(4) CASE_DX(5) CASE_DX(6) CASE_DX(7) CASE_DX(8)
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "input dimension D=%d not supported (1..8)", DX);
   }
 #undef CASE_DX
   return GPAR_OK;
+}
+template <int D, int CT>
+int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
+                 const double* table, double* panel, double* resp, int Mpad) {
+  switch (k_out) {
+    case GPAR_EQ: return launch_pass1_dx<GPAR_EQ, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
+    case GPAR_MATERN12: return launch_pass1_dx<GPAR_MATERN12, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
+    case GPAR_MATERN32: return launch_pass1_dx<GPAR_MATERN32, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
+    case GPAR_MATERN52: return launch_pass1_dx<GPAR_MATERN52, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
+  }
 }
 
 struct ScaledStats { double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad; };
@@ -240,20 +377,21 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   const int kind_time = D == 1 ? GPAR_MATERN12 : (D == 2 ? GPAR_MATERN32 : GPAR_MATERN52);
   CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, N, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
                 alpha, lml, nullptr, nullptr, table, sums));
-  dim3 grid(T, nch);
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
   double* panel = ctx->panelK.as<double>();
-  switch (k_out) {
-    case GPAR_EQ: CHK((launch_pass1_dx<GPAR_EQ, D>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad))); break;
-    case GPAR_MATERN12: CHK((launch_pass1_dx<GPAR_MATERN12, D>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad))); break;
-    case GPAR_MATERN32: CHK((launch_pass1_dx<GPAR_MATERN32, D>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad))); break;
-    case GPAR_MATERN52: CHK((launch_pass1_dx<GPAR_MATERN52, D>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad))); break;
-    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
-  }
+  // column tiles per thread: amortises the shared per-step table loads (registers limit it for large D)
+  int CT = (T % 2 == 0) ? 2 : 1;   // measured best on B200 (CT = 1 / 2 / 4: 8.5 / 7.6 / 7.9 ms at N = 1M, M = 1024)
+  if (const char* e = getenv("GPAR_WH_CT")) { int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && T % v == 0) CT = v; }   // tuning knob
+  dim3 grid(T / CT, nch);
+  if (CT == 4) CHK((launch_pass1<D, 4>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
+  else if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
+  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
   LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi);
-  LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 127) / 128, 128, 0, psi, resp, nch, Mpad);
-  LAUNCH(ctx, whiten_pass2_kernel<D>, grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
+  LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad);
+  if (CT == 4) LAUNCH(ctx, (whiten_pass2_kernel<D, 4>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
+  else if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
+  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
   cudaEventRecord(ctx->pev[0], ctx->stream);
   CHK(panel_syrk_run(ctx, panel, nullptr, Npad, Mpad, M, false, G, nullptr));
