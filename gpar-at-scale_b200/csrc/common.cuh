@@ -55,6 +55,8 @@ struct gpar_ctx {
   DevBuf panelK, panelD, partial, segs, jobs, gpart, scal, dense, tailws, info;
   DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
   void* pinned = nullptr; size_t pinned_cap = 0;
+  // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
+  int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;
 };
 
 int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...);

@@ -143,36 +143,52 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
   }
   CU(cudaMemcpyAsync(Lu, Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
-  // B = L_u^{-1} G L_u^{-T} / sigma^2
-  CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   const double one = 1.0, zero = 0.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
-  LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
-  LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
-  // c = L_Lambda^{-1} L_u^{-1} g / sigma^2
-  CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
-  LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
-  CB(cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_DEVICE));
-  cublasStatus_t st = cublasDdot(ctx->blas, M, cvec, 1, cvec, 1, sc + 2);
-  cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_HOST);
-  CB(st);
   int trace_blocks = 0;
-  if (want_grad) {
-    // V = L_u^{-1};  Kinv = V'V;  R = L_Lambda^{-1} V;  P = R'R;  w = sigma^2 L_u^{-T} L_Lambda^{-T} c
+  if (!want_grad) {
+    // value only — the reference's own sequence of triangular solves (dtc_example.jl:14-21)
+    CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
+    LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
+    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
+    LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
+    CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
+    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
+  } else {
+    // with gradient: the explicit triangular inverses are needed anyway (P, cov(u)^-1), so B is formed
+    // from them with two GEMMs instead of two more triangular solves:
+    //   V = L_u^-1;  B = V G V'/sigma^2;  R = L_Lambda^-1 V;  Kinv = V'V;  P = R'R
     LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, V, M);
     CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, V, M));
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, V, M, V, M, &zero, Kinv, M));
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, V, M, G, M, &zero, Pm, M));        // Pm = V G (scratch)
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_T, M, M, M, &ip, Pm, M, V, M, &zero, Bm, M));         // B
+    LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
+    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
+    LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
     CU(cudaMemcpyAsync(R, V, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Bm, M, R, M));
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, V, M, V, M, &zero, Kinv, M));
     CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, R, M, R, M, &zero, Pm, M));
+    // c and w through backward-stable triangular solves, NOT through the explicit inverses: the gradient
+    // sums cancel terms of size g'w / sigma^4 and need w to satisfy Q w = g to working accuracy
+    // (with w = P g the s-derivative at N = 1M, M = 1024 was off by 1 %).
+    CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
+    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
+    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
     CU(cudaMemcpyAsync(wvec, cvec, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Bm, M, wvec, 1));
     CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Lu, M, wvec, 1));
     LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, wvec, M, p.noise);
+  }
+  CB(cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_DEVICE));
+  cublasStatus_t st = cublasDdot(ctx->blas, M, cvec, 1, cvec, 1, sc + 2);
+  cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_HOST);
+  CB(st);
+  if (want_grad) {
     if (vfe) {
       CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Kinv, M, G, M, &zero, Tm, M));
       CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Tm, M, Kinv, M, &zero, Cm, M));

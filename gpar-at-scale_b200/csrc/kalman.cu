@@ -25,6 +25,9 @@
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
+#ifndef KF_MIN_BLOCKS
+#define KF_MIN_BLOCKS 4
+#endif
 __device__ constexpr double kSmoothJitter = 1e-12;   // TemporalGPs smooth: cholesky(P_pred + 1e-12 I)
 
 struct Level { double* base; int n; int P; };   // n valid elements per sequence, padded to P (multiple of 32)
@@ -95,7 +98,7 @@ struct SeqParams { const double *l, *s, *noise; int nparam; };
 
 // P1: chunk filtering element.
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KF_MIN_BLOCKS)
 kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch) {
   typedef FiltElem<D> E;
@@ -163,7 +166,7 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
 // part: [b][c][2] = (sum log S, sum alpha^2).  SMOOTH additionally stores the filtered states
 // fs[(f*batch + b)*N + k] (f < D + NSYM) and the chunk smoothing element at reversed index.
 template <int D, bool SMOOTH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SMOOTH ? 2 : KF_MIN_BLOCKS)
 kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                        SeqParams sp, int64_t N, int L, int nC, Level l0, Level l1, int batch,
                        double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ fs, Level s0,
@@ -265,11 +268,12 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
       }
       row[D * D + 2 * D] = rs;
     }
-    if (SMOOTH) {
+    if (SMOOTH) {   // warp-coalesced layout: [sequence][group of 32 chunks][field][step in chunk][chunk % 32]
+      double* fsw = fs + (((int64_t)b * ((nC + 31) >> 5) + (c >> 5)) * (D + NSYM<D>) * L + (k - k0)) * 32 + (c & 31);
 #pragma unroll
-      for (int i = 0; i < D; i++) fs[((int64_t)i * batch + b) * N + k] = m[i];
+      for (int i = 0; i < D; i++) fsw[(int64_t)i * L * 32] = m[i];
 #pragma unroll
-      for (int i = 0; i < NSYM<D>; i++) fs[((int64_t)(D + i) * batch + b) * N + k] = P[i];
+      for (int i = 0; i < NSYM<D>; i++) fsw[(int64_t)(D + i) * L * 32] = P[i];
     }
   }
   part[((int64_t)b * nC + c) * 2 + 0] = sum_logS + log(prodS);
@@ -301,11 +305,12 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
   const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   double ms[D], Ps[NSYM<D>];
   int64_t k = k1 - 1;
+  const double* fsb = fs + (((int64_t)b * ((nC + 31) >> 5) + (c >> 5)) * (D + NSYM<D>) * L) * 32 + (c & 31);
   if (c == nC - 1) {
 #pragma unroll
-    for (int i = 0; i < D; i++) ms[i] = fs[((int64_t)i * batch + b) * N + k];
+    for (int i = 0; i < D; i++) ms[i] = fsb[((int64_t)i * L + (k - k0)) * 32];
 #pragma unroll
-    for (int i = 0; i < NSYM<D>; i++) Ps[i] = fs[((int64_t)(D + i) * batch + b) * N + k];
+    for (int i = 0; i < NSYM<D>; i++) Ps[i] = fsb[((int64_t)(D + i) * L + (k - k0)) * 32];
     mean[(int64_t)b * N + k] = ms[0]; var[(int64_t)b * N + k] = Ps[0];
     k--;
   } else {
@@ -318,9 +323,9 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
   for (; k >= k0; k--) {
     double m[D], P[NSYM<D>], A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>], W[D * D], G[D * D];
 #pragma unroll
-    for (int i = 0; i < D; i++) m[i] = fs[((int64_t)i * batch + b) * N + k];
+    for (int i = 0; i < D; i++) m[i] = fsb[((int64_t)i * L + (k - k0)) * 32];
 #pragma unroll
-    for (int i = 0; i < NSYM<D>; i++) P[i] = fs[((int64_t)(D + i) * batch + b) * N + k];
+    for (int i = 0; i < NSYM<D>; i++) P[i] = fsb[((int64_t)(D + i) * L + (k - k0)) * 32];
     lgssm_transition<D>((__ldg(t + k + 1) - __ldg(t + k)) * il, A);
     lgssm_q<D>(A, P0, Q);
     matvec<D>(A, m, mp);
@@ -408,7 +413,7 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   LevelPlan fp = plan_levels(nC, FiltElem<D>::NF, batch);
   LevelPlan spn = smooth ? plan_levels(nC, SmoothElem<D>::NF, batch) : LevelPlan{};
   const size_t part_doubles = (size_t)batch * nC * 2;
-  const size_t fs_doubles = smooth ? (size_t)(D + NSYM<D>) * batch * N : 0;
+  const size_t fs_doubles = smooth ? (size_t)(D + NSYM<D>) * batch * ((size_t)((nC + 31) / 32) * 32) * L : 0;
   CU(ctx->kal_a.reserve((fp.doubles + spn.doubles + part_doubles) * sizeof(double)));
   if (smooth) CU(ctx->kal_b.reserve(fs_doubles * sizeof(double)));
   double* base = ctx->kal_a.as<double>();

@@ -213,22 +213,25 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
                    bool with_h, double* G, double* H) {
   const int T = Mpad / GPAR_TILE;
   const int64_t NBK = Npad / GPAR_KT;
-  SyrkPlan pl = plan_syrk(T, NBK, with_h, ctx->num_sms);
-  std::vector<Job>& jobs = pl.jobs;
-  std::vector<Seg>& segs = pl.segs;
-  std::vector<int>& cta_seg = pl.cta_seg;
-  const int J = (int)jobs.size();
-  const int C = pl.C;
-  const size_t nseg = segs.size();
-  CU(ctx->partial.reserve(nseg * GPAR_TILE * GPAR_TILE * sizeof(double)));
-  CU(ctx->segs.reserve(nseg * sizeof(Seg) + (C + 1) * sizeof(int) + 64));
-  CU(ctx->jobs.reserve(J * sizeof(Job)));
+  // the optimiser re-evaluates on fixed shapes: plan once, keep the segment tables on the device
+  if (ctx->plan_T != T || ctx->plan_NBK != NBK || ctx->plan_h != (int)with_h) {
+    SyrkPlan pl = plan_syrk(T, NBK, with_h, ctx->num_sms);
+    const size_t nseg = pl.segs.size();
+    const int Jn = (int)pl.jobs.size();
+    CU(ctx->partial.reserve(nseg * GPAR_TILE * GPAR_TILE * sizeof(double)));
+    CU(ctx->segs.reserve(nseg * sizeof(Seg) + (pl.C + 1) * sizeof(int) + 64));
+    CU(ctx->jobs.reserve(Jn * sizeof(Job)));
+    Seg* ds = ctx->segs.as<Seg>();
+    int* dc = reinterpret_cast<int*>(reinterpret_cast<char*>(ds) + nseg * sizeof(Seg));
+    CU(cudaMemcpyAsync(ds, pl.segs.data(), nseg * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc, pl.cta_seg.data(), (pl.C + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->jobs.p, pl.jobs.data(), Jn * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope below
+    ctx->plan_T = T; ctx->plan_NBK = NBK; ctx->plan_h = (int)with_h; ctx->plan_C = pl.C; ctx->plan_J = Jn; ctx->plan_nseg = nseg;
+  }
+  const int J = ctx->plan_J, C = ctx->plan_C;
   Seg* dsegs = ctx->segs.as<Seg>();
-  int* dcta = reinterpret_cast<int*>(reinterpret_cast<char*>(dsegs) + nseg * sizeof(Seg));
-  CU(cudaMemcpyAsync(dsegs, segs.data(), nseg * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(dcta, cta_seg.data(), (C + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), J * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope below
+  int* dcta = reinterpret_cast<int*>(reinterpret_cast<char*>(dsegs) + ctx->plan_nseg * sizeof(Seg));
   CU(cudaFuncSetAttribute(panel_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int64_t tile_stride = (Npad / 4) * (GPAR_TILE * 4);
   cudaEventRecord(ctx->pev[1], ctx->stream);

@@ -68,7 +68,47 @@ inline SyrkPlan plan_syrk(int ntiles, int64_t NBK, bool with_h, int num_sms) {
     if (prev < NBK) tails.push_back(Tail{j, prev});
   }
   {
-    // pool: pack the tails into the remaining CTAs, equal cost each
+    // level 2: the tails of the regular jobs all cover the same k range [K1, NBK); a CTA takes q whole
+    // tails plus one partial [K1, K1 + rho), so these CTAs are phase-aligned as well.  What is left
+    // (partial remainders, diagonal-job tails) goes to the unaligned pool below.
+    std::vector<Tail> reg, rest;
+    for (const Tail& t : tails) (cost[t.job] == SYRK_COST_REGULAR ? reg : rest).push_back(t);
+    bool same = !reg.empty();
+    for (const Tail& t : reg) same = same && t.kb0 == reg[0].kb0;
+    if (same && reg.size() >= 2) {
+      const int64_t K1 = reg[0].kb0, tau = NBK - K1;
+      const double Lk = T / SYRK_COST_REGULAR;
+      const int64_t q = (int64_t)std::floor(Lk / (double)tau + 1e-9);
+      const int64_t rho = (int64_t)std::floor(Lk - (double)(q * tau) + 1e-9);
+      const int64_t per = q + (rho > 0 ? 1 : 0);
+      if (q >= 1 && per >= 1) {
+        size_t ti = 0;
+        while (ti + (size_t)per <= reg.size() && used < C - 1) {
+          cta_seg.push_back((int)segs.size());
+          for (int64_t i = 0; i < q; i++, ti++) {
+            const int j = reg[ti].job;
+            segs.push_back(Seg{jobs[j].a_tile, jobs[j].b_tile, jobs[j].b_panel, (int)K1, (int)NBK, 0, j, 0});
+          }
+          if (rho > 0) {
+            const int j = reg[ti].job;
+            segs.push_back(Seg{jobs[j].a_tile, jobs[j].b_tile, jobs[j].b_panel, (int)K1, (int)(K1 + rho), 0, j, 0});
+            rest.push_back(Tail{j, K1 + rho});
+            ti++;
+          }
+          used++;
+        }
+        for (; ti < reg.size(); ti++) rest.push_back(reg[ti]);
+      } else {
+        rest.insert(rest.end(), reg.begin(), reg.end());
+      }
+    } else {
+      rest.insert(rest.end(), reg.begin(), reg.end());
+    }
+    tails.swap(rest);
+    std::sort(tails.begin(), tails.end(), [](const Tail& a, const Tail& b) { return a.job < b.job; });
+  }
+  {
+    // pool: pack the remaining tails into the remaining CTAs, equal cost each
     double pool = 0.0;
     for (const Tail& t : tails) pool += (double)cost[t.job] * (NBK - t.kb0);
     int npool = std::max(1, C - used);

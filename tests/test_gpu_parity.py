@@ -269,3 +269,69 @@ def test_chain_fit_and_predict_small(ctx):
     inside = x_true <= x.max()
     assert np.sqrt(np.mean((means[0][inside] - y_true[0][inside]) ** 2)) < 0.3
     assert np.all(np.isfinite(means)) and np.all(spreads >= 0)
+
+
+def test_config1_toy_exact_gpar_chain(ctx):
+    """BASELINE config 1 — GPAR_examples/toy_example.jl: 3-output GPAR with FIXED hyper-parameters
+    (EQ on time, stretch(EQ, 10)-style on outputs), exact posteriors on N = 30, prediction chain
+    through posterior MEANS on 1000 points (:118-134).  Device vs oracle at every link of the chain."""
+    rng = np.random.default_rng(21)
+    n, ns = 30, 1000
+    x = np.linspace(0, 1, n); xs = np.linspace(0, 1, ns)
+    y1 = -np.sin(10 * np.pi * (x + 1)) / (2 * x + 1) - x ** 4 + 0.05 ** 2 * rng.normal(size=n)
+    y2 = np.cos(y1) ** 2 + np.sin(3 * x) + 0.05 ** 2 * rng.normal(size=n)
+    y3 = y2 * y1 ** 2 + 3 * x + 0.05 ** 2 * rng.normal(size=n)
+    th3 = np.log(np.array([0.1, 1.0, 0.05]) - 1e-3)
+    th5 = np.log(np.array([0.1, 1.0, 1.0, 1.0, 0.05]) - 1e-3)
+    # y1 | x
+    ctx.set_inputs(x); ctx.set_outputs(y1)
+    m1, v1 = ctx.exact_posterior(0, 0, th3, xs)
+    l, var, sig = oracle.unpack_gp(th3)
+    K = oracle.pairwise(0, x[:, None], x[:, None], l, var ** 2); Ks = oracle.pairwise(0, xs[:, None], x[:, None], l, var ** 2)
+    m1o, v1o = oracle.exact_posterior(K, Ks, np.full(ns, var ** 2), sig ** 2, y1)
+    assert np.max(np.abs(m1[0] - m1o)) <= 1e-8 * max(1, np.max(np.abs(m1o))) and np.max(np.abs(v1 - v1o)) <= 1e-8
+    # y2 | (x, y1), y3 | (x, y1, y2): predicted means feed the next link
+    prev_tr = [y1]; prev_te = [m1[0]]
+    for ytr in (y2, y3):
+        X = np.stack([x] + prev_tr, axis=1); Xs = np.stack([xs] + prev_te, axis=1)
+        ctx.set_inputs(X); ctx.set_outputs(ytr)
+        lml = ctx.exact_logpdf(0, 0, th5)[0]
+        m, v = ctx.exact_posterior(0, 0, th5, Xs)
+        tl, tv, ol, ov, ns_ = oracle.unpack_gpar(th5)
+        K = oracle.gpar_kernel_matrix(0, 0, X, X, tl, tv, ol, ov); Ks = oracle.gpar_kernel_matrix(0, 0, Xs, X, tl, tv, ol, ov)
+        mo, vo = oracle.exact_posterior(K, Ks, np.full(ns, tv ** 2 + ov ** 2), ns_ ** 2, ytr)
+        assert abs(lml - oracle.exact_logpdf(K, ns_ ** 2, ytr)) <= RTOL * abs(lml)
+        assert np.max(np.abs(m[0] - mo)) <= 1e-7 * max(1, np.max(np.abs(mo))) and np.max(np.abs(v - vo)) <= 1e-7
+        prev_tr.append(ytr); prev_te.append(m[0])
+
+
+def test_config4_eeg_shaped(ctx):
+    """BASELINE config 4 — examples/eeg.jl shapes: 7 channels x 256 time steps, train rows 1:156;
+    exact GPAR with D = 5, 6, 7 inputs (time + previous channels, eeg.jl:53-92) and scaled GPAR with
+    pseudo-inputs = training inputs (M = N = 156, D = 4, 5, 6; eeg.jl:212-232); outputs rounded
+    through Float32 as eeg.jl:32.  Batched over replicated trials."""
+    rng = np.random.default_rng(22)
+    T, ntr, R = 256, 156, 16
+    t = np.arange(T) / 256.0
+    ch = [np.sin(2 * np.pi * (3 + i) * t + i) for i in range(7)]
+    for i in range(1, 7):
+        ch[i] = ch[i] + 0.5 * np.tanh(ch[i - 1])
+    chans = np.stack(ch)
+    obs = (chans[None] + 0.1 * rng.normal(size=(R, 7, T))).astype(np.float32).astype(np.float64)     # trials x channels x time
+    th5 = np.log(np.array([0.2, 1.0, 2.0, 1.0, 0.1]) - 1e-3)
+    tl, tv, ol, ov, ns_ = oracle.unpack_gpar(th5)
+    for dprev in (4, 5, 6):
+        # exact GPAR: inputs (time, previous channels of trial 0), outputs = channel dprev of every trial
+        X = np.concatenate([t[:ntr, None], obs[0, :dprev, :ntr].T], axis=1)
+        Y = obs[:, dprev, :ntr]
+        ctx.set_inputs(X); ctx.set_outputs(Y)
+        lml = ctx.exact_logpdf(3, 3, th5)
+        K = oracle.gpar_kernel_matrix(3, 3, X, X, tl, tv, ol, ov)
+        lml0 = np.array([oracle.exact_logpdf(K, ns_ ** 2, Y[r]) for r in range(R)])
+        assert relerr(lml, lml0) <= RTOL
+        # scaled GPAR, pseudo-inputs = training inputs (M = N = 156)
+        Xo = np.ascontiguousarray(obs[0, :dprev, :ntr].T)
+        ctx.set_inputs(Xo); ctx.set_pseudo(Xo); ctx.set_times(t[:ntr]); ctx.set_outputs(Y[0])
+        v = ctx.scaled_dtc(3, 3, th5)
+        v0 = scaled_gpar_objective(th5, Xo, Xo, t[:ntr], Y[0], decorrelate=cport.kalman_decorrelate)
+        assert abs(v - v0) <= RTOL * abs(v0)

@@ -3,7 +3,7 @@ output, R hyper-parameter restarts, a FIXED Nelder-Mead iteration budget instead
 wall-clock limits (GPAR_scaled_examples.jl:140,173).  Tasks (output, restart) are sharded over the
 ranks (one process per GPU, torchrun); NCCL only gathers (minimum, minimizer) per task.
 
-    python -m torch.distributed.run --nproc-per-node G tools/bench_gpar_fit.py --n 2097152 --m 2048 --outputs 8 --restarts 2 --iterations 10
+    python -m torch.distributed.run --nproc-per-node G tools/bench_gpar_fit.py --npoints 2097152 --pseudo 2048 --outputs 8 --restarts 2 --iterations 10
 Prints one JSON line on rank 0: {"metric": "GPAR fit s", ...}.
 """
 import argparse
@@ -29,7 +29,7 @@ def synth(P, N, seed=4):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2097152); ap.add_argument("--m", type=int, default=2048)
+    ap.add_argument("--npoints", type=int, default=2097152); ap.add_argument("--pseudo", type=int, default=2048)
     ap.add_argument("--outputs", type=int, default=8); ap.add_argument("--restarts", type=int, default=2)
     ap.add_argument("--iterations", type=int, default=10)
     a = ap.parse_args()
@@ -42,16 +42,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gp.Context(local)
-    t, Y = synth(a.outputs, a.n)
+    t, Y = synth(a.outputs, a.npoints)
     # warm-up: one objective evaluation allocates the panels
     X = np.ascontiguousarray(Y[:1].T)
-    ctx.set_inputs(X); ctx.set_pseudo(chain.strided_pseudo_inputs(X, a.m)); ctx.set_times(t); ctx.set_outputs(Y[1])
+    ctx.set_inputs(X); ctx.set_pseudo(chain.strided_pseudo_inputs(X, a.pseudo)); ctx.set_times(t); ctx.set_outputs(Y[1])
     ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, np.zeros(5))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    best, info = chain.fit_chain(t, Y, a.m, n_restarts=a.restarts, iterations=a.iterations, seed=4, ctx=ctx)
+    best, info = chain.fit_chain(t, Y, a.pseudo, n_restarts=a.restarts, iterations=a.iterations, seed=4, ctx=ctx)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -65,7 +65,7 @@ def main():
         evals = [int(ev[0].item())]
     if rank == 0:
         print(json.dumps({"metric": "GPAR fit s", "value": dt, "unit": "s", "n_gpus": world, "higher_is_better": False, "scaling": "strong",
-                          "config": {"workload": "gpar_fit outputs=%d N=%d M=%d restarts=%d nelder_mead_iterations=%d" % (a.outputs, a.n, a.m, a.restarts, a.iterations)},
+                          "config": {"workload": "gpar_fit outputs=%d N=%d M=%d restarts=%d nelder_mead_iterations=%d" % (a.outputs, a.npoints, a.pseudo, a.restarts, a.iterations)},
                           "objective_evals_per_rank": evals, "tasks": info["tasks"],
                           "best_nlml": {str(o): best[o][0] for o in sorted(best)}}))
     if world > 1:
