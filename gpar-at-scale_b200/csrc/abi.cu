@@ -53,6 +53,8 @@ int gpar_ctx_create(int device, gpar_ctx** out) {
   cudaDeviceProp prop;
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[0]) != cudaSuccess || cudaEventCreate(&ctx->pev[1]) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess ||
@@ -69,6 +71,7 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (!ctx) return GPAR_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->partial, &ctx->segs,
                     &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
                     &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e};
@@ -79,6 +82,9 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GPAR_OK;
@@ -166,6 +172,9 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   // G, H, g/h, yy live in kal_a (not used by this entry point otherwise)
   CU(ctx->kal_a.reserve((2 * MM + 2 * (size_t)Mpad + 8) * sizeof(double)));
   double* G = ctx->kal_a.as<double>(); double* H = G + MM; double* gh = H + MM; double* dyy = gh + 2 * Mpad;
+  // fork: cov(u), its Cholesky factor and (for gradients) its explicit inverse do not depend on the data
+  // statistics — they run on the side stream underneath the producer and the SYRK
+  CHK(dtc_tail_prepare(ctx, kernel, p, vfe, jitter, want_grad));
   CHK(launch_kuf_panels(ctx, kernel, want_grad, p.l, p.s, ctx->panelK.as<double>(), ctx->panelD.as<double>(),
                         ctx->gpart.as<double>(), nsplit, Npad, Mpad));
   CHK(launch_reduce_gh(ctx, ctx->gpart.as<double>(), nsplit, Mpad, 2, gh));

@@ -34,6 +34,8 @@ struct DevBuf {
 struct gpar_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;     // side stream: the G-independent part of the M x M tail overlaps the SYRK
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
   cublasHandle_t blas = nullptr;
   cusolverDnHandle_t solver = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -167,6 +169,7 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
               const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
               double* d_table, double* d_sums);
 // dense_tail.cu
+int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, bool want_grad);
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
              double* val, double* grad);

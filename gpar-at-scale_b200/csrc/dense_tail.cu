@@ -104,10 +104,76 @@ __global__ void trace_final_kernel(const double* part, int nblocks, double* out)
 
 static const double LOG2PI = 1.8378770664093454835606594728112;
 
+// Buffer layout of the tail, shared by dtc_tail_prepare and dtc_tail.
+struct TailBufs {
+  double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;
+  int* dinfo; int lwork;
+};
+static int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b) {
+  const int M = (int)ctx->M;
+  const size_t MM = (size_t)M * M;
+  const int nmat = want_grad ? (vfe ? 10 : 8) : 3;
+  CU(ctx->dense.reserve(nmat * MM * sizeof(double) + 8 * (size_t)M * sizeof(double) + 64 * sizeof(double)));
+  double* base = ctx->dense.as<double>();
+  b->Kj = base; b->Lu = base + MM; b->Bm = base + 2 * MM;
+  b->dKu = want_grad ? base + 3 * MM : nullptr;
+  b->V = base + 4 * MM; b->Kinv = base + 5 * MM; b->R = base + 6 * MM; b->Pm = base + 7 * MM;
+  b->Tm = base + 8 * MM; b->Cm = base + 9 * MM;
+  double* vecs = base + nmat * MM;
+  b->cvec = vecs; b->wvec = vecs + M;
+  b->sc = vecs + 8 * (size_t)M;   // device scalars: [0]=trB [1]=logdetLam [2]=cc [8..8+NTR) traces
+  b->lwork = 0;
+  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, b->Lu, M, &b->lwork));
+  CU(ctx->tailws.reserve((size_t)2 * b->lwork * sizeof(double)));      // two potrf workspaces (side + main stream)
+  CU(ctx->info.reserve(4 * sizeof(int)));
+  b->dinfo = ctx->info.as<int>();
+  return GPAR_OK;
+}
+
+// G-independent part of the tail, enqueued on the SIDE stream (overlaps the producer and the SYRK):
+// cov(u) = Kuu + jitter I (and l dKuu/dl), its Cholesky factor L_u and, for gradients, V = L_u^-1 and
+// cov(u)^-1 = V'V.  Records ctx->ev_side.
+int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_in, bool want_grad) {
+  const int M = (int)ctx->M, D = ctx->Dz;
+  const size_t MM = (size_t)M * M;
+  const double jitter = jitter_in < 0.0 ? p.noise : jitter_in;
+  TailBufs b;
+  CHK(tail_layout(ctx, want_grad, vfe, &b));
+  cudaStream_t main_stream = ctx->stream;
+  CU(cudaEventRecord(ctx->ev_fork, main_stream));
+  CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  ctx->stream = ctx->stream2;                 // LAUNCH() and the library handles follow ctx->stream
+  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
+  int rc = [&]() -> int {
+    const double inv_l2 = 1.0 / (p.l * p.l);
+    dim3 kgrid((M + 127) / 128, M);
+    const double* Zd = ctx->Z.as<double>();
+    switch (kind) {
+      case GPAR_EQ: LAUNCH(ctx, kuu_kernel<GPAR_EQ>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, b.Kj, b.dKu); break;
+      case GPAR_MATERN12: LAUNCH(ctx, kuu_kernel<GPAR_MATERN12>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, b.Kj, b.dKu); break;
+      case GPAR_MATERN32: LAUNCH(ctx, kuu_kernel<GPAR_MATERN32>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, b.Kj, b.dKu); break;
+      default: LAUNCH(ctx, kuu_kernel<GPAR_MATERN52>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, b.Kj, b.dKu); break;
+    }
+    CU(cudaMemcpyAsync(b.Lu, b.Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, b.Lu, M, ctx->tailws.as<double>() + b.lwork, b.lwork, b.dinfo));
+    if (want_grad) {
+      const double one = 1.0, zero = 0.0;
+      LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, b.V, M);
+      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, b.Lu, M, b.V, M));
+      CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, b.V, M, b.V, M, &zero, b.Kinv, M));
+    }
+    return GPAR_OK;
+  }();
+  cudaEventRecord(ctx->ev_side, ctx->stream2);
+  ctx->stream = main_stream;
+  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
+  return rc;
+}
+
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_in, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
              double* val, double* grad) {
-  const int M = (int)ctx->M, D = ctx->Dz;
+  const int M = (int)ctx->M;
   const size_t MM = (size_t)M * M;
   const bool want_grad = grad != nullptr;
   const bool jit_is_noise = jitter_in < 0.0;
@@ -115,34 +181,13 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
   const double ip = 1.0 / p.noise;
   cublasSetStream(ctx->blas, ctx->stream);
   cusolverDnSetStream(ctx->solver, ctx->stream);
-
-  const int nmat = want_grad ? (vfe ? 10 : 8) : 3;
-  CU(ctx->dense.reserve(nmat * MM * sizeof(double) + 8 * (size_t)M * sizeof(double) + 64 * sizeof(double)));
-  double* base = ctx->dense.as<double>();
-  double* Kj = base;           double* Lu = base + MM;       double* Bm = base + 2 * MM;
-  double* dKu = want_grad ? base + 3 * MM : nullptr;
-  double* V = base + 4 * MM;   double* Kinv = base + 5 * MM; double* R = base + 6 * MM; double* Pm = base + 7 * MM;
-  double* Tm = base + 8 * MM;  double* Cm = base + 9 * MM;
-  double* vecs = base + nmat * MM;
-  double* cvec = vecs;         double* wvec = vecs + M;
-  double* sc = vecs + 8 * (size_t)M;   // device scalars: [0]=trB [1]=logdetLam [2]=cc [8..8+NTR) traces
-  int lwork = 0;
-  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, &lwork));
-  CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
-  CU(ctx->info.reserve(4 * sizeof(int)));
-  int* dinfo = ctx->info.as<int>();
-
-  const double inv_l2 = 1.0 / (p.l * p.l);
-  dim3 kgrid((M + 127) / 128, M);
-  const double* Zd = ctx->Z.as<double>();
-  switch (kind) {
-    case GPAR_EQ: LAUNCH(ctx, kuu_kernel<GPAR_EQ>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
-    case GPAR_MATERN12: LAUNCH(ctx, kuu_kernel<GPAR_MATERN12>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
-    case GPAR_MATERN32: LAUNCH(ctx, kuu_kernel<GPAR_MATERN32>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
-    default: LAUNCH(ctx, kuu_kernel<GPAR_MATERN52>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, Kj, dKu); break;
-  }
-  CU(cudaMemcpyAsync(Lu, Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+  TailBufs tb;
+  CHK(tail_layout(ctx, want_grad, vfe, &tb));
+  double *Kj = tb.Kj, *Lu = tb.Lu, *Bm = tb.Bm, *dKu = tb.dKu, *V = tb.V, *Kinv = tb.Kinv, *R = tb.R, *Pm = tb.Pm, *Tm = tb.Tm, *Cm = tb.Cm;
+  double *cvec = tb.cvec, *wvec = tb.wvec, *sc = tb.sc;
+  int* dinfo = tb.dinfo; const int lwork = tb.lwork;
+  (void)kind;
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));     // join: L_u (and V, cov(u)^-1) are ready
   const double one = 1.0, zero = 0.0;
   int trace_blocks = 0;
   if (!want_grad) {
@@ -161,8 +206,6 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
     // with gradient: the explicit triangular inverses are needed anyway (P, cov(u)^-1), so B is formed
     // from them with two GEMMs instead of two more triangular solves:
     //   V = L_u^-1;  B = V G V'/sigma^2;  R = L_Lambda^-1 V;  Kinv = V'V;  P = R'R
-    LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, V, M);
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, V, M));
     CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, V, M, G, M, &zero, Pm, M));        // Pm = V G (scratch)
     CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_T, M, M, M, &ip, Pm, M, V, M, &zero, Bm, M));         // B
     LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
@@ -170,7 +213,6 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
     LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
     CU(cudaMemcpyAsync(R, V, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Bm, M, R, M));
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, V, M, V, M, &zero, Kinv, M));
     CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, R, M, R, M, &zero, Pm, M));
     // c and w through backward-stable triangular solves, NOT through the explicit inverses: the gradient
     // sums cancel terms of size g'w / sigma^4 and need w to satisfy Q w = g to working accuracy
