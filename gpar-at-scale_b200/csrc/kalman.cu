@@ -21,6 +21,7 @@
 // All state lives in registers; FP64 ALU bound: ~16-24 B of HBM traffic per step.
 #include "lgssm_math.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -355,13 +356,26 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
   }
 }
 
-// lml[b] = -1/2 (N log 2pi + sum log S + sum alpha^2); one block per sequence, fixed order.
+// lml[b] = -1/2 (N log 2pi + sum log S + sum alpha^2), fixed-order two-stage reduction:
+// stage 1: block (s, b) sums a contiguous slice of sequence b's chunk partials; stage 2: one block per
+// sequence sums the slices (a single long sequence would otherwise be reduced by one block).
 __global__ void __launch_bounds__(256)
-lml_reduce_kernel(const double* __restrict__ part, int nC, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
+lml_partial_kernel(const double* __restrict__ part, int nC, int nslice, double* __restrict__ part2) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int per = (nC + nslice - 1) / nslice, c0 = s * per, c1 = min(nC, c0 + per);
+  double a0 = 0.0, a1 = 0.0;
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) { a0 += part[((int64_t)b * nC + c) * 2]; a1 += part[((int64_t)b * nC + c) * 2 + 1]; }
+  double r0 = block_sum(a0, sh);
+  double r1 = block_sum(a1, sh);
+  if (threadIdx.x == 0) { part2[((int64_t)b * nslice + s) * 2] = r0; part2[((int64_t)b * nslice + s) * 2 + 1] = r1; }
+}
+__global__ void __launch_bounds__(64)
+lml_reduce_kernel(const double* __restrict__ part2, int nslice, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
   __shared__ double sh[32];
   const int b = blockIdx.x;
   double a0 = 0.0, a1 = 0.0;
-  for (int c = threadIdx.x; c < nC; c += blockDim.x) { a0 += part[((int64_t)b * nC + c) * 2]; a1 += part[((int64_t)b * nC + c) * 2 + 1]; }
+  for (int s = threadIdx.x; s < nslice; s += blockDim.x) { a0 += part2[((int64_t)b * nslice + s) * 2]; a1 += part2[((int64_t)b * nslice + s) * 2 + 1]; }
   double r0 = block_sum(a0, sh);
   double r1 = block_sum(a1, sh);
   if (threadIdx.x == 0) {
@@ -408,11 +422,16 @@ template <int D>
 int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec,
                 double* d_alpha, double* d_lml, double* d_mean, double* d_var, double* d_table, double* d_sums) {
   const bool smooth = d_mean != nullptr;
-  const int L = 32;
+  // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel
+  const int64_t total_steps = N * (int64_t)batch;
+  int L = total_steps <= (1 << 19) ? 8 : (total_steps <= (1 << 21) ? 16 : 32);
+  if (N / 32 > 100000) L = 128; else if (N / 32 > 30000) L = 64;      // very long sequences: fewer scan levels
+  if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 256) L = v; }   // tuning knob
   const int nC = (int)((N + L - 1) / L);
   LevelPlan fp = plan_levels(nC, FiltElem<D>::NF, batch);
   LevelPlan spn = smooth ? plan_levels(nC, SmoothElem<D>::NF, batch) : LevelPlan{};
-  const size_t part_doubles = (size_t)batch * nC * 2;
+  const int nslice = std::max(1, std::min(64, (nC + 2047) / 2048));
+  const size_t part_doubles = (size_t)batch * nC * 2 + (size_t)batch * nslice * 2;
   const size_t fs_doubles = smooth ? (size_t)(D + NSYM<D>) * batch * ((size_t)((nC + 31) / 32) * 32) * L : 0;
   CU(ctx->kal_a.reserve((fp.doubles + spn.doubles + part_doubles) * sizeof(double)));
   if (smooth) CU(ctx->kal_b.reserve(fs_doubles * sizeof(double)));
@@ -436,7 +455,9 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   } else {
     LAUNCH(ctx, (kf_chunk_filter_kernel<D, false>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, d_alpha, part, fs, none, d_table);
   }
-  LAUNCH(ctx, lml_reduce_kernel, batch, 256, 0, part, nC, N, d_lml, d_sums);
+  double* part2 = part + (size_t)batch * nC * 2;
+  LAUNCH(ctx, lml_partial_kernel, dim3(nslice, batch), 256, 0, part, nC, nslice, part2);
+  LAUNCH(ctx, lml_reduce_kernel, batch, 64, 0, part2, nslice, N, d_lml, d_sums);
   return GPAR_OK;
 }
 
