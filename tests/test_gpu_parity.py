@@ -335,3 +335,38 @@ def test_config4_eeg_shaped(ctx):
         v = ctx.scaled_dtc(3, 3, th5)
         v0 = scaled_gpar_objective(th5, Xo, Xo, t[:ntr], Y[0], decorrelate=cport.kalman_decorrelate)
         assert abs(v - v0) <= RTOL * abs(v0)
+
+
+def test_abi_error_behaviour():
+    """Status codes instead of exceptions/aborts across the ABI: missing data, shape mismatches,
+    kernels without a state-space form, bad batch sizes — each with a message."""
+    import gpar_at_scale_b200 as gp
+    c = gp.Context(0)
+    th3 = np.zeros(3); th5 = np.zeros(5)
+    with pytest.raises(gp.GparError, match="must be set"):
+        c.dtc_logpdf(3, th3)
+    c.set_inputs(np.zeros((10, 2))); c.set_pseudo(np.zeros((3, 1)) + np.arange(3)[:, None]); c.set_outputs(np.zeros(10))
+    with pytest.raises(gp.GparError, match="D="):
+        c.dtc_logpdf(3, th3)
+    c.set_pseudo(np.random.default_rng(0).normal(size=(3, 2))); c.set_outputs(np.zeros(7))
+    with pytest.raises(gp.GparError, match="outputs length"):
+        c.dtc_logpdf(3, th3)
+    c.set_outputs(np.zeros(10))
+    with pytest.raises(gp.GparError, match="time"):
+        c.scaled_dtc(3, 3, th5)
+    c.set_times(np.arange(10.0))
+    with pytest.raises(gp.GparError, match="state-space"):
+        c.scaled_dtc(0, 3, th5)                       # EQ has no SDE form
+    with pytest.raises(gp.GparError, match="state-space"):
+        c.lgssm_logpdf(0, th3)
+    c.set_outputs(np.zeros((4, 10)))
+    with pytest.raises(gp.GparError, match="batch_theta"):
+        c.lgssm_logpdf(3, np.zeros((3, 3)))
+    c.set_noise_vector(np.ones(5))
+    with pytest.raises(gp.GparError, match="noise vector"):
+        c.lgssm_logpdf(3, th3)
+    c.set_noise_vector(None)
+    assert np.all(np.isfinite(c.lgssm_logpdf(3, th3)))
+    with pytest.raises(gp.GparError, match="ntheta"):
+        c.exact_logpdf(3, 3, np.zeros(4))
+    c.close()

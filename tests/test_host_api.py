@@ -1,0 +1,76 @@
+"""CPU: host-side logic of the mirror of the reference's Julia interface (no GPU, no library calls)."""
+import numpy as np
+import pytest
+import gpar_at_scale_b200 as gp
+from gpar_at_scale_b200 import api, data, neldermead, chain, parallel
+
+
+def test_to_colvecs_layout_matches_reference():
+    # util.jl:16-31: a list of per-feature vectors -> D x N column-major == N records of D doubles
+    X = api.to_ColVecs([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    assert X.shape == (3, 2) and X.flags["C_CONTIGUOUS"] and X.tolist() == [[1, 4], [2, 5], [3, 6]]
+    assert api.to_ColVecs(np.arange(4.0)).shape == (4, 1)
+    assert api.to_ColVecs([1.0, 2.0]).shape == (2, 1)
+    Y = np.asfortranarray(np.arange(6.0).reshape(3, 2))
+    assert api.to_ColVecs(Y).flags["C_CONTIGUOUS"]
+
+
+def test_unpack_and_parse_params():
+    assert api.unpack_gp([0.0, 0.0, 0.0]) == pytest.approx((1.001,) * 3)
+    assert api.unpack_gpar(np.log(np.array([2.0, 3.0, 4.0, 5.0, 6.0]) - 1e-3)) == pytest.approx((2, 3, 4, 5, 6))
+    rng = np.random.default_rng(0)
+    p = api.parse_initial_gpar_params(None, 1.5, None, None, -3.0, rng=rng)      # util.jl:128-134: missing -> rand() in [0, 1)
+    assert p[1] == 1.5 and p[4] == -3.0 and all(0 <= p[i] < 1 for i in (0, 2, 3))
+    assert api.parse_initial_gp_params(0.1, 0.2, 0.3).tolist() == [0.1, 0.2, 0.3]
+
+
+def test_masks():
+    assert api.get_time_mask(3).tolist() == [1, 0, 0]
+    assert api.get_output_mask(3).tolist() == [[0, 1, 0], [0, 0, 1]]
+    with pytest.raises(ValueError):
+        api.get_output_mask(1)
+
+
+def test_kernel_objects_and_finite_gp():
+    k = api.kernel(api.Matern52(), l=2.0, s=3.0)
+    assert k.code == gp.MATERN52 and k.l == 2.0 and k.s == 3.0
+    f = api.GP(k)(np.arange(5.0), 0.04)
+    assert len(f) == 5 and f.noise == 0.04 and f.x.shape == (5, 1)
+    with pytest.raises(ValueError):
+        api.create_lgssm(np.arange(3.0), 1.0, 1.0, 0.1, api.EQ())      # EQ has no SDE form
+
+
+def test_toy_data_shapes_follow_the_reference():
+    # toy_data.jl:76-98: 10 000 samples minus 5 x 300 nuked minus the 4-point remainder -> 8 496; 100 000 true points
+    x, y_obs, x_true, y_true = data.generate_big_dataset(np.random.default_rng(0))
+    assert len(x) == 8496 and len(x_true) == 100000 and len(y_obs) == 3 and all(len(y) == 8496 for y in y_obs)
+    assert x_true[-1] == pytest.approx(10000 / 30 + 50) and np.all(np.diff(x) > 0)
+    gaps = np.diff(x)
+    assert np.sum(gaps > 5) == 5                                    # five removed intervals
+    x, y_obs, x_true, y_true = data.generate_small_dataset(np.random.default_rng(0))
+    assert len(x) == 30 and len(x_true) == 1000
+    # noise std is observation_noise^2 (toy_data.jl:29 quirk): 0.05^2 on the small set
+    resid = y_obs[0] - data.f1_small(x)
+    assert 0.3 * 0.0025 < np.std(resid) < 3 * 0.0025
+
+
+def test_nelder_mead_matches_optim_defaults_on_rosenbrock():
+    f = lambda v: (1 - v[0]) ** 2 + 100 * (v[1] - v[0] ** 2) ** 2
+    res = neldermead.optimize(f, np.array([-1.2, 1.0]), iterations=2000)
+    assert res.converged and res.minimum < 1e-8 and np.allclose(res.minimizer, [1, 1], atol=1e-3)   # g_tol = 1e-8 on the simplex spread
+    # time limit and iteration budget are honoured
+    res = neldermead.optimize(f, np.array([-1.2, 1.0]), iterations=5)
+    assert res.iterations == 5 and not res.converged
+    res = neldermead.optimize(lambda v: f(v), np.array([-1.2, 1.0]), time_limit=0.0)
+    assert res.stopped_by_time
+
+
+def test_chain_tasks_and_pseudo_inputs():
+    tasks, costs = chain.make_tasks(8, 8)
+    assert len(tasks) == 64 and tasks[0] == (0, 0) and costs[0] < costs[8] < costs[-1]
+    X = np.arange(20.0).reshape(10, 2)
+    Z = chain.strided_pseudo_inputs(X, 4)
+    assert Z.shape == (4, 2) and Z[0].tolist() == X[0].tolist() and Z[-1].tolist() == X[-1].tolist()
+    assert chain.strided_pseudo_inputs(X, 50).shape == (10, 2)
+    best = parallel.best_per_output([(0, 0), (0, 1), (1, 0)], np.array([3.0, 2.0, 5.0]), np.zeros((3, 5)))
+    assert best[0][0] == 2.0 and best[0][2] == 1 and best[1][0] == 5.0
