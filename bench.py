@@ -37,7 +37,7 @@ N_FULL, M_FULL = 1_000_000, 1024
 THETA = np.log(np.array([1.0, 1.0, 0.1]))
 METRIC = "pseudo-point logpdf+grad evals/s (N=1M,M=1024)"
 FP64_PEAK_TFLOPS_FALLBACK = 36.96     # profiles/peaks_r01.json: DMMA m8n8k4 microbenchmark on this pool's B200
-NCU_SYRK_DRAM_BYTES = 83.71e9          # dram__bytes_read.sum + dram__bytes_write.sum of panel_syrk_kernel, one `ncu --set full` launch (profiles/ncu_dtc_r01b.csv)
+NCU_SYRK_DRAM_BYTES = 30.93e9          # dram__bytes_read.sum + dram__bytes_write.sum of panel_syrk_kernel, one ncu launch (profiles/ncu_syrk_traffic_r01c.csv)
 
 
 def make_data(seed, n=N_FULL, m=M_FULL):
@@ -226,7 +226,7 @@ def run_ours(args):
             "e2e": {"value": world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(16 * N_FULL), "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_SYRK_DRAM_BYTES,
-                         "kernel": "panel_syrk_kernel (FP64 DMMA.8x8x4)", "traffic_note": "operand panels: 16.8 GB unique; L2 hit 45% after phase-aligned stream-K (was 181.9 GB)", "kernel_ms": syrk, "algorithmic_flops_per_launch": flops,
+                         "kernel": "panel_syrk_kernel (FP64 DMMA.8x8x4)", "traffic_note": "operand panels: 16.8 GB unique; L2 hit 74% with the two-level phase-aligned stream-K (plain stream-K: 181.9 GB)", "kernel_ms": syrk, "algorithmic_flops_per_launch": flops,
                          "peak_source": "FP64 DMMA peak measured on this pool (profiles/peaks_r01.json; cuBLAS DGEMM 8192^3 = 35.9); MEASURED_PEAKS.json has no FP64 entry",
                          "step_breakdown_ms": {"panel_producer": float(np.mean(prod_ms)), "dmma_syrk": syrk, "reduce_and_tail": float(np.mean(tail_ms)),
                                                "device_total": float(np.mean(dev_ms))}},
