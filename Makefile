@@ -9,7 +9,7 @@ OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 
 all: $(LIBDIR)/libgpar_b200.so oracle
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/gpar_b200.h
+build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/gpar_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -54,7 +54,7 @@ struct gpar_ctx {
   bool has_rvec = false;
 
   // scratch (grown on demand)
-  DevBuf panelK, panelD, partial, segs, jobs, gpart, scal, dense, tailws, info;
+  DevBuf panelK, panelD, panelB, kal_f, partial, segs, jobs, gpart, scal, dense, tailws, info;
   DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
   void* pinned = nullptr; size_t pinned_cap = 0;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
@@ -169,7 +169,14 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
               const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
               double* d_table, double* d_sums);
 // dense_tail.cu
+struct TailBufs {   // M x M scratch of the tail inside ctx->dense
+  double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;
+  int* dinfo; int lwork;
+};
+constexpr int GPAR_NTR = 20;      // number of trace scalars produced by the tail (after 8 header scalars)
+int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b);
 int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, bool want_grad);
+// raw_out (nullable): host array of 8 + GPAR_NTR doubles receiving [trB, logdetLambda, c'c, -, ..., traces]
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
-             double* val, double* grad);
+             double* val, double* grad, double* raw_out = nullptr);

@@ -60,7 +60,7 @@ __global__ void scale_kernel(double* v, int n, double a) {
   if (i < n) v[i] *= a;
 }
 
-constexpr int NTR = 20;
+constexpr int NTR = GPAR_NTR;
 // Element-wise trace sums over the M x M matrices (column-major; all symmetric except H).
 // part[block][NTR]; reduced in fixed order by trace_final_kernel.
 __global__ void __launch_bounds__(256)
@@ -104,12 +104,9 @@ __global__ void trace_final_kernel(const double* part, int nblocks, double* out)
 
 static const double LOG2PI = 1.8378770664093454835606594728112;
 
-// Buffer layout of the tail, shared by dtc_tail_prepare and dtc_tail.
-struct TailBufs {
-  double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;
-  int* dinfo; int lwork;
-};
-static int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b) {
+// Buffer layout of the tail (struct TailBufs, common.cuh), shared by dtc_tail_prepare, dtc_tail and
+// the scaled-GPAR gradient (scaled.cu), which reads P, w, ... back from it.
+int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b) {
   const int M = (int)ctx->M;
   const size_t MM = (size_t)M * M;
   const int nmat = want_grad ? (vfe ? 10 : 8) : 3;
@@ -172,7 +169,7 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
 
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_in, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
-             double* val, double* grad) {
+             double* val, double* grad, double* raw_out) {
   const int M = (int)ctx->M;
   const size_t MM = (size_t)M * M;
   const bool want_grad = grad != nullptr;
@@ -237,7 +234,8 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
     }
     trace_blocks = (int)std::min<size_t>((MM + 255) / 256, (size_t)ctx->num_sms * 4);
     CU(ctx->scal.reserve((size_t)trace_blocks * NTR * sizeof(double)));
-    LAUNCH(ctx, trace_kernel, trace_blocks, 256, 0, M, Pm, Kinv, G, H, Kj, dKu, vfe ? Cm : nullptr, wvec, g, h, ctx->scal.as<double>());
+    // reverse-mode callers (scaled.cu) have no forward-mode H / h: G / g stand in and those sums are ignored
+    LAUNCH(ctx, trace_kernel, trace_blocks, 256, 0, M, Pm, Kinv, G, H ? H : G, Kj, dKu, vfe ? Cm : nullptr, wvec, g, h ? h : g, ctx->scal.as<double>());
     LAUNCH(ctx, trace_final_kernel, 1, 32, 0, ctx->scal.as<double>(), trace_blocks, sc + 8);
   }
   double hs[8 + NTR]; int hinfo[2];
@@ -246,6 +244,7 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
   CU(cudaStreamSynchronize(ctx->stream));
   if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) failed: leading minor %d is not positive definite", hinfo[0]);
   if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
+  if (raw_out) memcpy(raw_out, hs, sizeof(hs));
   const double trB = hs[0], logdetL = hs[1], cc = hs[2];
   double v = -0.5 * ((double)N * LOG2PI + (double)N * log(p.noise) + logdetL + yy * ip - cc);
   if (vfe) v += -0.5 * ((double)N * p.s * ip - trB);

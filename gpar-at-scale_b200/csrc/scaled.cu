@@ -216,16 +216,18 @@ carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int
 template <int D, int CT>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass2_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ alpha,
-                    double* __restrict__ panel, const double* __restrict__ start, double* __restrict__ gpart, int Mpad) {
+                    const double* pin, double* pout, const double* __restrict__ start, double* __restrict__ gpart, int Mpad) {
   constexpr int TS = D * D + 2 * D + 1;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
   const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const double* in[CT];
   double* io[CT];
   double ms[CT][D], gacc[CT];
 #pragma unroll
   for (int c = 0; c < CT; c++) {
-    io[c] = panel + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
+    in[c] = pin + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
+    io[c] = pout + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
 #pragma unroll
     for (int i = 0; i < D; i++) ms[c][i] = start[((int64_t)blockIdx.y * D + i) * Mpad + (mt0 + c) * GPAR_TILE + mi];
     gacc[c] = 0.0;
@@ -242,8 +244,9 @@ whiten_pass2_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, co
       double kv[CT][4];
 #pragma unroll
       for (int c = 0; c < CT; c++) {
-        double2 a01 = reinterpret_cast<double2*>(io[c])[0], a23 = reinterpret_cast<double2*>(io[c])[1];
+        double2 a01 = reinterpret_cast<const double2*>(in[c])[0], a23 = reinterpret_cast<const double2*>(in[c])[1];
         kv[c][0] = a01.x; kv[c][1] = a01.y; kv[c][2] = a23.x; kv[c][3] = a23.y;
+        in[c] += GPAR_TILE * 4;
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -354,19 +357,21 @@ int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const dou
   }
 }
 
-struct ScaledStats { double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad; };
+struct ScaledStats { double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad; double *table, *alpha, *beta; int nch; };
 
 // Steps 1-3 of the header comment.  Leaves G (M x M) and g (M) on the device.
 template <int D>
-int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st) {
+int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st, bool keep_k) {
   constexpr int TS = D * D + 2 * D + 1;
   const int64_t N = ctx->N; const int M = (int)ctx->M;
   const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
-  const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT;
+  const int64_t npad_to = keep_k ? 128 : GPAR_KT;        // the gradient's panel GEMM works on 128-step blocks
+  const int64_t Npad = (N + npad_to - 1) / npad_to * npad_to;
   const int64_t NB4 = Npad / 4;
   const int nch = (int)((NB4 + WH_GROUPS - 1) / WH_GROUPS);
   const int T = Mpad / GPAR_TILE;
   CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
+  if (keep_k) CU(ctx->panelB.reserve((size_t)Npad * Mpad * sizeof(double)));
   CU(ctx->kal_e.reserve(((size_t)N * TS + (size_t)N + 16) * sizeof(double)));                 // table, alpha, sums
   CU(ctx->gpart.reserve(((size_t)nch * D * Mpad + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad) * sizeof(double)));
   const size_t MM = (size_t)M * M;
@@ -380,6 +385,7 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
   double* panel = ctx->panelK.as<double>();
+  double* beta = keep_k ? ctx->panelB.as<double>() : panel;     // in place unless K is needed again (gradient)
   // column tiles per thread: amortises the shared per-step table loads (registers limit it for large D)
   int CT = (T % 2 == 0) ? 2 : 1;   // measured best on B200 (CT = 1 / 2 / 4: 8.5 / 7.6 / 7.9 ms at N = 1M, M = 1024)
   if (const char* e = getenv("GPAR_WH_CT")) { int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && T % v == 0) CT = v; }   // tuning knob
@@ -389,25 +395,27 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
   LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi);
   LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad);
-  if (CT == 4) LAUNCH(ctx, (whiten_pass2_kernel<D, 4>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
-  else if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
-  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, resp, gp, Mpad);
+  if (CT == 4) LAUNCH(ctx, (whiten_pass2_kernel<D, 4>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
+  else if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
+  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
   cudaEventRecord(ctx->pev[0], ctx->stream);
-  CHK(panel_syrk_run(ctx, panel, nullptr, Npad, Mpad, M, false, G, nullptr));
+  CHK(panel_syrk_run(ctx, beta, nullptr, Npad, Mpad, M, false, G, nullptr));
   ctx->phase_valid = true;
   double hs[2];
   CU(cudaMemcpyAsync(hs, sums, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   st->G = G; st->g = g; st->sum_logS = hs[0]; st->sum_a2 = hs[1]; st->Mpad = Mpad; st->Npad = Npad;
+  st->table = table; st->alpha = alpha; st->beta = beta; st->nch = nch;
   return GPAR_OK;
 }
 
-int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st) {
+int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st,
+                 bool keep_k = false) {
   switch (k_time) {
-    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st);
-    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st);
-    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st);
+    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
+    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
+    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
   }
 }

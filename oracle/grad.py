@@ -67,3 +67,82 @@ def dtc_diag_value_and_grad(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
     v = dtc_diag_t(th, X, Z, torch.as_tensor(y, dtype=torch.float64), kind, vfe, jitter)
     v.backward()
     return float(v.detach()), th.grad.numpy().copy()
+
+
+# ---- scaled-GPAR objective (src/gp/dtc.jl:83-128) in torch, for autograd gradients -------------------
+def _sde_torch(kind):
+    import numpy as np
+    from .lgssm import sde_matrices
+    F, Pinf, H = sde_matrices(kind)
+    lam = {1: 1.0, 2: math.sqrt(3.0), 3: math.sqrt(5.0)}[F.shape[0]]
+    return (torch.as_tensor(F), torch.as_tensor(Pinf), lam)
+
+
+def _transition_t(F, lam, a):
+    d = F.shape[0]
+    Nm = F + lam * torch.eye(d, dtype=torch.float64)
+    A = torch.eye(d, dtype=torch.float64)
+    term = torch.eye(d, dtype=torch.float64)
+    for j in range(1, d):
+        term = term @ Nm * (a / j)
+        A = A + term
+    return torch.exp(-lam * a) * A
+
+
+def kalman_decorrelate_t(kind, t, V, l, s, noise):
+    """Differentiable sequential Kalman `decorrelate` of the columns of V (n x c) sharing one model
+    (torch twin of oracle.lgssm._filter; small n only).  -> (sum log S, alpha (n x c))."""
+    F, Pinf, lam = _sde_torch(kind)
+    d = F.shape[0]
+    n = V.shape[0]
+    P0 = s * Pinf
+    P = P0
+    M = torch.zeros(d, V.shape[1], dtype=torch.float64)
+    alphas = []
+    logS = torch.zeros((), dtype=torch.float64)
+    tprev = t[0] - 1.0
+    for k in range(n):
+        A = _transition_t(F, lam, (t[k] - tprev) / l)
+        tprev = t[k]
+        Q = P0 - A @ P0 @ A.T
+        Mp = A @ M
+        Pp = A @ P @ A.T + Q
+        S = Pp[0, 0] + noise
+        sq = torch.sqrt(S)
+        B = Pp[0, :] / sq
+        a = (V[k] - Mp[0]) / sq
+        M = Mp + B[:, None] * a[None, :]
+        P = Pp - torch.outer(B, B)
+        alphas.append(a)
+        logS = logS + torch.log(S)
+    return logS, torch.stack(alphas)
+
+
+def scaled_dtc_t(theta, X, Z, t, y, k_time, k_out):
+    """torch twin of oracle.dtc.scaled_gpar_objective (dtc.jl:29-47 + :83-128, O(N) log-determinant)."""
+    p = _unpack(theta)
+    time_l, time_var, out_l, out_var, sig = p[0], p[1], p[2], p[3], p[4]
+    nv = sig * sig
+    Cfu = pairwise_t(k_out, X, Z, out_l, out_var * out_var)
+    cov_u = pairwise_t(k_out, Z, Z, out_l, out_var * out_var) + nv * torch.eye(Z.shape[0], dtype=torch.float64)
+    logS, W = kalman_decorrelate_t(k_time, t, torch.cat([y[:, None], Cfu], dim=1), time_l, time_var * time_var, nv)
+    alpha, beta = W[:, 0], W[:, 1:]
+    Lu = torch.linalg.cholesky(cov_u)
+    A = torch.linalg.solve_triangular(Lu, beta.T, upper=False)
+    m = A.shape[0]
+    Ll = torch.linalg.cholesky(A @ A.T + torch.eye(m, dtype=torch.float64))
+    c = torch.linalg.solve_triangular(Ll, (A @ alpha)[:, None], upper=False)[:, 0]
+    n = y.shape[0]
+    return -(n * LOG2PI + logS + 2.0 * torch.log(torch.diagonal(Ll)).sum() + alpha @ alpha - c @ c) / 2.0
+
+
+def scaled_dtc_value_and_grad(theta, X, Z, t, y, k_time=3, k_out=3):
+    th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    X = torch.as_tensor(X, dtype=torch.float64); Z = torch.as_tensor(Z, dtype=torch.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    if Z.ndim == 1:
+        Z = Z[:, None]
+    v = scaled_dtc_t(th, X, Z, torch.as_tensor(t, dtype=torch.float64), torch.as_tensor(y, dtype=torch.float64), k_time, k_out)
+    v.backward()
+    return float(v.detach()), th.grad.numpy().copy()
