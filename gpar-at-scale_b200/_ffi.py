@@ -38,6 +38,7 @@ SIGNATURES = {
     "gpar_scaled_predict": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int32,
                                            _c_double_p, _c_double_p]),
     "gpar_lgssm_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),
+    "gpar_lgssm_logpdf_grad": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p, _c_double_p]),
     "gpar_lgssm_decorrelate": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_lgssm_smooth": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_exact_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),

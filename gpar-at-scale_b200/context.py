@@ -130,6 +130,14 @@ class Context:
         self._check(self._lib.gpar_lgssm_logpdf(self._h, int(kernel), dptr(th), th.shape[0], dptr(out)))
         return out
 
+    def lgssm_logpdf_grad(self, kernel, theta):
+        """-> (lml (batch,), grad (batch, 3)): d lml[b] / d theta of the parameter set sequence b uses."""
+        th = as_f64(np.atleast_2d(theta))
+        out = np.zeros(self.batch)
+        grad = np.zeros((self.batch, 3))
+        self._check(self._lib.gpar_lgssm_logpdf_grad(self._h, int(kernel), dptr(th), th.shape[0], dptr(out), dptr(grad)))
+        return out, grad
+
     def lgssm_decorrelate(self, kernel, theta):
         th = as_f64(np.asarray(theta).ravel())
         alpha = np.zeros((self.batch, self.Ny))

@@ -168,6 +168,10 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
 int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
               const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
               double* d_table, double* d_sums);
+// forward-mode variant: values and two tangents (dirs = tangent slot 0/1/-1 of l, s, noise) in one pass
+int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
+                      const double* t, const double* y, const double* rvec, const int dirs[3],
+                      double* d_alpha, double* d_lml, double* d_dlml, double* d_sums, double* d_dalpha, double* d_table, double* d_dtable);
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;

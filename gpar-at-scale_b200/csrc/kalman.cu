@@ -33,16 +33,41 @@ __device__ constexpr double kSmoothJitter = 1e-12;   // TemporalGPs smooth: chol
 
 struct Level { double* base; int n; int P; };   // n valid elements per sequence, padded to P (multiple of 32)
 
+// An element is stored as Elem::NFD double fields (value and tangent components of each entry).
 template <class Elem>
 __device__ __forceinline__ void load_elem(Elem& e, const double* base, int64_t fstride, int64_t off) {
+  typedef Scalar<typename Elem::scalar_t> SC;
 #pragma unroll
-  for (int f = 0; f < Elem::NF; f++) e.v[f] = base[f * fstride + off];
+  for (int f = 0; f < Elem::NF; f++)
+#pragma unroll
+    for (int c = 0; c < SC::NC; c++) SC::comp(e.v[f], c) = base[(f * SC::NC + c) * fstride + off];
 }
 template <class Elem>
 __device__ __forceinline__ void store_elem(const Elem& e, double* base, int64_t fstride, int64_t off) {
+  typedef Scalar<typename Elem::scalar_t> SC;
 #pragma unroll
-  for (int f = 0; f < Elem::NF; f++) base[f * fstride + off] = e.v[f];
+  for (int f = 0; f < Elem::NF; f++)
+#pragma unroll
+    for (int c = 0; c < SC::NC; c++) base[(f * SC::NC + c) * fstride + off] = SC::comp(e.v[f], c);
 }
+template <class Elem>
+__device__ __forceinline__ void shfl_up_elem(Elem& o, const Elem& e, int d) {
+  typedef Scalar<typename Elem::scalar_t> SC;
+#pragma unroll
+  for (int f = 0; f < Elem::NF; f++)
+#pragma unroll
+    for (int c = 0; c < SC::NC; c++) SC::comp(o.v[f], c) = __shfl_up_sync(0xffffffffu, SC::comp(e.v[f], c), d);
+}
+// parameter with a unit tangent in direction `dir` (none if dir < 0)
+template <class F> struct Seed { __device__ __forceinline__ static double make(double x, int) { return x; } };
+template <int NT> struct Seed<Dual<NT>> {
+  __device__ __forceinline__ static Dual<NT> make(double x, int dir) {
+    Dual<NT> r(x);
+#pragma unroll
+    for (int i = 0; i < NT; i++) r.d[i] = (i == dir) ? 1.0 : 0.0;
+    return r;
+  }
+};
 
 // inclusive prefix (scan order) of element idx of sequence b, from level 0 (local prefixes) and the
 // finalised level 1 (if any)
@@ -76,8 +101,7 @@ scan_up_kernel(Level cur, Level up, int batch) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     Elem o;
-#pragma unroll
-    for (int f = 0; f < Elem::NF; f++) o.v[f] = __shfl_up_sync(0xffffffffu, e.v[f], d);
+    shfl_up_elem(o, e, d);
     if (lane >= d) e = Elem::scan_combine(o, e);
   }
   store_elem(e, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + tile * 32 + lane);
@@ -95,24 +119,25 @@ __global__ void scan_down_kernel(Level cur, Level up, int batch) {
   store_elem(r, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + i);
 }
 
-struct SeqParams { const double *l, *s, *noise; int nparam; };
+// dir_*: tangent slot of each parameter in the Dual instantiations (-1: not differentiated)
+struct SeqParams { const double *l, *s, *noise; int nparam; int dir_l, dir_s, dir_n; };
 
 // P1: chunk filtering element.
-template <int D>
-__global__ void __launch_bounds__(128, KF_MIN_BLOCKS)
+template <int D, class F>
+__global__ void __launch_bounds__(128, Scalar<F>::NC == 1 ? KF_MIN_BLOCKS : 1)
 kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch) {
-  typedef FiltElem<D> E;
+  typedef FiltElem<D, F> E;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= l0.P) return;
   E e;
   if (c >= nC) { e.set_identity(); store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c); return; }
   const int pb = sp.nparam == 1 ? 0 : b;
-  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
-  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+  const F il = 1.0 / Seed<F>::make(sp.l[pb], sp.dir_l), s = Seed<F>::make(sp.s[pb], sp.dir_s), noise = Seed<F>::make(sp.noise[pb], sp.dir_n);
+  F P0[NSYM<D>]; lgssm_pinf<D>(P0);
 #pragma unroll
-  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
-  double* Phi = e.v; double* bv = e.v + E::OB; double* C = e.v + E::OC; double* eta = e.v + E::OE; double* J = e.v + E::OJ;
+  for (int i = 0; i < NSYM<D>; i++) P0[i] = P0[i] * s;
+  F* Phi = e.v; F* bv = e.v + E::OB; F* C = e.v + E::OC; F* eta = e.v + E::OE; F* J = e.v + E::OJ;
   e.set_identity();
   if (c == 0) {
 #pragma unroll
@@ -125,7 +150,7 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
   const double* yb = y + (int64_t)b * N;
   for (int64_t k = k0; k < k1; k++) {
     const double tk = __ldg(t + k);
-    double A[D * D], Q[NSYM<D>], T[D * D], u[D], Cn[NSYM<D>];
+    F A[D * D], Q[NSYM<D>], T[D * D], u[D], Cn[NSYM<D>];
     lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
     lgssm_q<D>(A, P0, Q);
     matmul<D>(A, Phi, T);
@@ -137,10 +162,10 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
     asat<D>(A, C, Cn);
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) C[i] = Cn[i] + Q[i];
-    const double R = rvec ? __ldg(rvec + k) : noise;
-    const double S = C[0] + R, iS = 1.0 / S;
-    const double r = __ldg(yb + k) - bv[0];
-    double h[D], Kg[D];
+    const F S = rvec ? C[0] + __ldg(rvec + k) : C[0] + noise;
+    const F iS = 1.0 / S;
+    const F r = __ldg(yb + k) - bv[0];
+    F h[D], Kg[D];
 #pragma unroll
     for (int i = 0; i < D; i++) { h[i] = Phi[i]; Kg[i] = SYM(C, i, 0) * iS; }
 #pragma unroll
@@ -164,42 +189,46 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
 }
 
 // P3: restart the ordinary filter from the scanned prefix state.
-// part: [b][c][2] = (sum log S, sum alpha^2).  SMOOTH additionally stores the filtered states
-// fs[(f*batch + b)*N + k] (f < D + NSYM) and the chunk smoothing element at reversed index.
-template <int D, bool SMOOTH>
-__global__ void __launch_bounds__(128, SMOOTH ? 2 : KF_MIN_BLOCKS)
+// part: [b][c][2 NC] = (sum log S, sum alpha^2), each with its tangents.  SMOOTH additionally stores
+// the filtered states fs (f < D + NSYM, warp-coalesced) and the chunk smoothing element at reversed
+// index.  Dual instantiations also emit d alpha (dalpha[(j*batch + b)*N + k]) and the tangent rows of
+// the step table (dtable, layout in scaled.cu).
+template <int D, bool SMOOTH, class F>
+__global__ void __launch_bounds__(128, Scalar<F>::NC == 1 ? (SMOOTH ? 2 : KF_MIN_BLOCKS) : 1)
 kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                        SeqParams sp, int64_t N, int L, int nC, Level l0, Level l1, int batch,
                        double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ fs, Level s0,
-                       double* __restrict__ table) {
+                       double* __restrict__ table, double* __restrict__ dalpha, double* __restrict__ dtable) {
+  typedef Scalar<F> SC;
+  constexpr int NC = SC::NC;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= nC) return;
   const int pb = sp.nparam == 1 ? 0 : b;
-  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
-  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+  const F il = 1.0 / Seed<F>::make(sp.l[pb], sp.dir_l), s = Seed<F>::make(sp.s[pb], sp.dir_s), noise = Seed<F>::make(sp.noise[pb], sp.dir_n);
+  F P0[NSYM<D>]; lgssm_pinf<D>(P0);
 #pragma unroll
-  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
-  double m[D], P[NSYM<D>];
+  for (int i = 0; i < NSYM<D>; i++) P0[i] = P0[i] * s;
+  F m[D], P[NSYM<D>];
   if (c == 0) {
 #pragma unroll
     for (int i = 0; i < D; i++) m[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) P[i] = P0[i];
   } else {
-    FiltElem<D> pre = inclusive_prefix<FiltElem<D>>(l0, l1, batch, b, c - 1);
+    FiltElem<D, F> pre = inclusive_prefix<FiltElem<D, F>>(l0, l1, batch, b, c - 1);
 #pragma unroll
-    for (int i = 0; i < D; i++) m[i] = pre.v[FiltElem<D>::OB + i];
+    for (int i = 0; i < D; i++) m[i] = pre.v[FiltElem<D, F>::OB + i];
 #pragma unroll
-    for (int i = 0; i < NSYM<D>; i++) P[i] = pre.v[FiltElem<D>::OC + i];
+    for (int i = 0; i < NSYM<D>; i++) P[i] = pre.v[FiltElem<D, F>::OC + i];
   }
-  SmoothElem<D> comp; if (SMOOTH) comp.set_identity();
+  SmoothElem<D, F> comp; if (SMOOTH) comp.set_identity();
   const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
   const double* yb = y + (int64_t)b * N;
-  double sum_logS = 0.0, sum_a2 = 0.0, prodS = 1.0;
+  F sum_logS = 0.0, sum_a2 = 0.0, prodS = 1.0;
   const int64_t kend = SMOOTH ? k1 + 1 : k1;    // one extra predict closes the chunk's last smoothing element
   for (int64_t k = k0; k < kend; k++) {
-    double A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>];
+    F A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>];
     if (k < N) {
       const double tk = __ldg(t + k);
       lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
@@ -209,42 +238,44 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NSYM<D>; i++) Pp[i] += Q[i];
     }
-    if (SMOOTH && k > k0) {
-      // smoothing element of step k-1: G = P A^T (Pp + eps I)^{-1}, g = m - G mp, Ls = P - G Pp G^T
-      SmoothElem<D> el;
-      double* G = el.v; double* g = el.v + SmoothElem<D>::OG; double* Ls = el.v + SmoothElem<D>::OL;
-      if (k < N) {
-        double W[D * D];
+    if constexpr (SMOOTH) {
+      if (k > k0) {
+        // smoothing element of step k-1: G = P A^T (Pp + eps I)^{-1}, g = m - G mp, Ls = P - G Pp G^T
+        SmoothElem<D, F> el;
+        F* G = el.v; F* g = el.v + SmoothElem<D, F>::OG; F* Ls = el.v + SmoothElem<D, F>::OL;
+        if (k < N) {
+          F W[D * D];
 #pragma unroll
-        for (int i = 0; i < D; i++)
+          for (int i = 0; i < D; i++)
 #pragma unroll
-          for (int j = 0; j < D; j++) { double v = 0.0;
+            for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
-            for (int q = 0; q < D; q++) v = fma(SYM(P, i, q), A[j * D + q], v);
-            W[i * D + j] = v; }
-        solve_spd_right<D>(W, Pp, kSmoothJitter, G);
-        double u[D], R[NSYM<D>];
-        matvec<D>(G, mp, u);
+              for (int q = 0; q < D; q++) v = fma(SYM(P, i, q), A[j * D + q], v);
+              W[i * D + j] = v; }
+          solve_spd_right<D>(W, Pp, kSmoothJitter, G);
+          F u[D], R[NSYM<D>];
+          matvec<D>(G, mp, u);
 #pragma unroll
-        for (int i = 0; i < D; i++) g[i] = m[i] - u[i];
-        asat<D>(G, Pp, R);
+          for (int i = 0; i < D; i++) g[i] = m[i] - u[i];
+          asat<D>(G, Pp, R);
 #pragma unroll
-        for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i] - R[i];
-      } else {   // last step of the sequence: (0, m_N, P_N)
+          for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i] - R[i];
+        } else {   // last step of the sequence: (0, m_N, P_N)
 #pragma unroll
-        for (int i = 0; i < D * D; i++) G[i] = 0.0;
+          for (int i = 0; i < D * D; i++) G[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < D; i++) g[i] = m[i];
+          for (int i = 0; i < D; i++) g[i] = m[i];
 #pragma unroll
-        for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i];
+          for (int i = 0; i < NSYM<D>; i++) Ls[i] = P[i];
+        }
+        comp = SmoothElem<D, F>::combine(comp, el);
       }
-      comp = SmoothElem<D>::combine(comp, el);
     }
     if (k >= k1) break;
-    const double R = rvec ? __ldg(rvec + k) : noise;
-    const double S = Pp[0] + R, rs = rsqrt(S);          // one reciprocal square root instead of sqrt + D+1 divisions
-    const double a = (__ldg(yb + k) - mp[0]) * rs;
-    double Bv[D];
+    const F S = rvec ? Pp[0] + __ldg(rvec + k) : Pp[0] + noise;
+    const F rs = rsqrt(S);          // one reciprocal square root instead of sqrt + D+1 divisions
+    const F a = (__ldg(yb + k) - mp[0]) * rs;
+    F Bv[D];
 #pragma unroll
     for (int i = 0; i < D; i++) { Bv[i] = SYM(Pp, 0, i) * rs; m[i] = fma(Bv[i], a, mp[i]); }
 #pragma unroll
@@ -252,34 +283,64 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
 #pragma unroll
       for (int j = i; j < D; j++) SYM(P, i, j) = fma(-Bv[i], Bv[j], SYM(Pp, i, j));
     // sum log S_k as the log of a running product, flushed every 8 steps (S in [1e-12, 1e10]: no over/underflow)
-    prodS *= S;
+    prodS = prodS * S;
     if (((k - k0) & 7) == 7) { sum_logS += log(prodS); prodS = 1.0; }
     sum_a2 = fma(a, a, sum_a2);
-    if (alpha) alpha[(int64_t)b * N + k] = a;
-    if (!SMOOTH && table) {   // shared-model step table for the affine mean scans (scaled.cu)
-      double* row = table + k * (D * D + 2 * D + 1);
-      const double iS = 1.0 / S;
+    if (alpha) alpha[(int64_t)b * N + k] = value_of(a);
+    if constexpr (NC > 1) {
+      if (dalpha) {
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        const double Kg = SYM(Pp, i, 0) * iS;
-#pragma unroll
-        for (int j = 0; j < D; j++) row[i * D + j] = fma(-Kg, A[j], A[i * D + j]);
-        row[D * D + i] = Kg;
-        row[D * D + D + i] = A[i];
+        for (int j = 1; j < NC; j++) dalpha[((int64_t)(j - 1) * batch + b) * N + k] = SC::comp(a, j);
       }
-      row[D * D + 2 * D] = rs;
     }
-    if (SMOOTH) {   // warp-coalesced layout: [sequence][group of 32 chunks][field][step in chunk][chunk % 32]
+    if constexpr (!SMOOTH) {
+      if (table) {   // shared-model step table for the affine mean scans (scaled.cu)
+        constexpr int TS = D * D + 2 * D + 1;
+        double* row = table + k * TS;
+        double* drow = nullptr;
+        if constexpr (NC > 1) { if (dtable) drow = dtable + k * (1 + (NC - 1) * TS); }
+        const F iS = 1.0 / S;
+        F ent[TS];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          const F Kg = SYM(Pp, i, 0) * iS;
+#pragma unroll
+          for (int j = 0; j < D; j++) ent[i * D + j] = fma(-Kg, A[j], A[i * D + j]);
+          ent[D * D + i] = Kg;
+          ent[D * D + D + i] = A[i];
+        }
+        ent[D * D + 2 * D] = rs;
+#pragma unroll
+        for (int i = 0; i < TS; i++) row[i] = value_of(ent[i]);
+        if constexpr (NC > 1) {
+          if (drow) {
+            drow[0] = value_of(S) * value_of(rs);       // sqrt(S): turns beta back into the innovation
+            const double irs = 1.0 / value_of(rs);
+#pragma unroll
+            for (int j = 1; j < NC; j++) {
+#pragma unroll
+              for (int i = 0; i < TS - 1; i++) drow[1 + (j - 1) * TS + i] = SC::comp(ent[i], j);
+              drow[1 + (j - 1) * TS + TS - 1] = SC::comp(rs, j) * irs;   // d log rs
+            }
+          }
+        }
+      }
+    }
+    if constexpr (SMOOTH) {   // warp-coalesced layout: [sequence][group of 32 chunks][field][step in chunk][chunk % 32]
       double* fsw = fs + (((int64_t)b * ((nC + 31) >> 5) + (c >> 5)) * (D + NSYM<D>) * L + (k - k0)) * 32 + (c & 31);
 #pragma unroll
-      for (int i = 0; i < D; i++) fsw[(int64_t)i * L * 32] = m[i];
+      for (int i = 0; i < D; i++) fsw[(int64_t)i * L * 32] = value_of(m[i]);
 #pragma unroll
-      for (int i = 0; i < NSYM<D>; i++) fsw[(int64_t)(D + i) * L * 32] = P[i];
+      for (int i = 0; i < NSYM<D>; i++) fsw[(int64_t)(D + i) * L * 32] = value_of(P[i]);
     }
   }
-  part[((int64_t)b * nC + c) * 2 + 0] = sum_logS + log(prodS);
-  part[((int64_t)b * nC + c) * 2 + 1] = sum_a2;
-  if (SMOOTH) store_elem(comp, s0.base, (int64_t)batch * s0.P, (int64_t)b * s0.P + (nC - 1 - c));
+  sum_logS += log(prodS);
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    part[((int64_t)b * nC + c) * 2 * NC + j] = SC::comp(sum_logS, j);
+    part[((int64_t)b * nC + c) * 2 * NC + NC + j] = SC::comp(sum_a2, j);
+  }
+  if constexpr (SMOOTH) store_elem(comp, s0.base, (int64_t)batch * s0.P, (int64_t)b * s0.P + (nC - 1 - c));
 }
 
 // pads the reversed smoothing level 0 beyond nC with identities
@@ -359,28 +420,55 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
 // lml[b] = -1/2 (N log 2pi + sum log S + sum alpha^2), fixed-order two-stage reduction:
 // stage 1: block (s, b) sums a contiguous slice of sequence b's chunk partials; stage 2: one block per
 // sequence sums the slices (a single long sequence would otherwise be reduced by one block).
+// NC = 1 + number of tangents; per chunk the partials are [sum log S (NC), sum alpha^2 (NC)].
+template <int NC>
 __global__ void __launch_bounds__(256)
 lml_partial_kernel(const double* __restrict__ part, int nC, int nslice, double* __restrict__ part2) {
   __shared__ double sh[32];
+  constexpr int NP = 2 * NC;
   const int b = blockIdx.y, s = blockIdx.x;
   const int per = (nC + nslice - 1) / nslice, c0 = s * per, c1 = min(nC, c0 + per);
-  double a0 = 0.0, a1 = 0.0;
-  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) { a0 += part[((int64_t)b * nC + c) * 2]; a1 += part[((int64_t)b * nC + c) * 2 + 1]; }
-  double r0 = block_sum(a0, sh);
-  double r1 = block_sum(a1, sh);
-  if (threadIdx.x == 0) { part2[((int64_t)b * nslice + s) * 2] = r0; part2[((int64_t)b * nslice + s) * 2 + 1] = r1; }
+  double a[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) a[i] = 0.0;
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < NP; i++) a[i] += part[((int64_t)b * nC + c) * NP + i];
+  }
+#pragma unroll
+  for (int i = 0; i < NP; i++) {
+    double r = block_sum(a[i], sh);
+    if (threadIdx.x == 0) part2[((int64_t)b * nslice + s) * NP + i] = r;
+  }
 }
+// lml[b]; dlml[b*(NC-1) + j] = d lml / d tangent j; sums[b*2NC + ...] = the raw sums.
+template <int NC>
 __global__ void __launch_bounds__(64)
-lml_reduce_kernel(const double* __restrict__ part2, int nslice, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
+lml_reduce_kernel(const double* __restrict__ part2, int nslice, int64_t N, double* __restrict__ lml, double* __restrict__ dlml,
+                  double* __restrict__ sums) {
   __shared__ double sh[32];
+  constexpr int NP = 2 * NC;
   const int b = blockIdx.x;
-  double a0 = 0.0, a1 = 0.0;
-  for (int s = threadIdx.x; s < nslice; s += blockDim.x) { a0 += part2[((int64_t)b * nslice + s) * 2]; a1 += part2[((int64_t)b * nslice + s) * 2 + 1]; }
-  double r0 = block_sum(a0, sh);
-  double r1 = block_sum(a1, sh);
+  double a[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) a[i] = 0.0;
+  for (int s = threadIdx.x; s < nslice; s += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < NP; i++) a[i] += part2[((int64_t)b * nslice + s) * NP + i];
+  }
+  double r[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) r[i] = block_sum(a[i], sh);
   if (threadIdx.x == 0) {
-    lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + r0 + r1);
-    if (sums) { sums[2 * b] = r0; sums[2 * b + 1] = r1; }
+    if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + r[0] + r[NC]);
+    if (dlml) {
+#pragma unroll
+      for (int j = 1; j < NC; j++) dlml[b * (NC - 1) + (j - 1)] = -0.5 * (r[j] + r[NC + j]);
+    }
+    if (sums) {
+#pragma unroll
+      for (int i = 0; i < NP; i++) sums[b * NP + i] = r[i];
+    }
   }
 }
 
@@ -418,46 +506,72 @@ int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
   return GPAR_OK;
 }
 
-template <int D>
-int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec,
-                double* d_alpha, double* d_lml, double* d_mean, double* d_var, double* d_table, double* d_sums) {
-  const bool smooth = d_mean != nullptr;
+// Outputs of one filter / smoother run (device pointers, all nullable except lml or sums).
+struct LgssmOut {
+  double* alpha = nullptr; double* lml = nullptr; double* mean = nullptr; double* var = nullptr;
+  double* table = nullptr; double* sums = nullptr;
+  double* dlml = nullptr; double* dalpha = nullptr; double* dtable = nullptr;    // tangent outputs (Dual runs)
+};
+
+template <int D, class F>
+int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec, const LgssmOut& o) {
+  constexpr int NC = Scalar<F>::NC;
+  typedef FiltElem<D, F> FE;
+  const bool smooth = o.mean != nullptr;
   // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel
   const int64_t total_steps = N * (int64_t)batch;
   int L = total_steps <= (1 << 19) ? 8 : (total_steps <= (1 << 21) ? 16 : 32);
   if (N / 32 > 100000) L = 128; else if (N / 32 > 30000) L = 64;      // very long sequences: fewer scan levels
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 256) L = v; }   // tuning knob
   const int nC = (int)((N + L - 1) / L);
-  LevelPlan fp = plan_levels(nC, FiltElem<D>::NF, batch);
-  LevelPlan spn = smooth ? plan_levels(nC, SmoothElem<D>::NF, batch) : LevelPlan{};
+  LevelPlan fp = plan_levels(nC, FE::NFD, batch);
+  LevelPlan spn = smooth ? plan_levels(nC, SmoothElem<D>::NFD, batch) : LevelPlan{};
   const int nslice = std::max(1, std::min(64, (nC + 2047) / 2048));
-  const size_t part_doubles = (size_t)batch * nC * 2 + (size_t)batch * nslice * 2;
+  const size_t part_doubles = ((size_t)batch * nC + (size_t)batch * nslice) * 2 * NC;
   const size_t fs_doubles = smooth ? (size_t)(D + NSYM<D>) * batch * ((size_t)((nC + 31) / 32) * 32) * L : 0;
   CU(ctx->kal_a.reserve((fp.doubles + spn.doubles + part_doubles) * sizeof(double)));
   if (smooth) CU(ctx->kal_b.reserve(fs_doubles * sizeof(double)));
   double* base = ctx->kal_a.as<double>();
-  bind_levels(fp, base, FiltElem<D>::NF, batch);
-  if (smooth) bind_levels(spn, base + fp.doubles, SmoothElem<D>::NF, batch);
+  bind_levels(fp, base, FE::NFD, batch);
+  if (smooth) bind_levels(spn, base + fp.doubles, SmoothElem<D>::NFD, batch);
   double* part = base + fp.doubles + spn.doubles;
   double* fs = smooth ? ctx->kal_b.as<double>() : nullptr;
   const Level none{nullptr, 0, 0};
   const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
   dim3 g1((f0.P + 127) / 128, batch);
-  LAUNCH(ctx, kf_chunk_summary_kernel<D>, g1, 128, 0, t, y, rvec, sp, N, L, nC, f0, batch);
-  CHK(run_scan<FiltElem<D>>(ctx, fp, batch));
+  LAUNCH(ctx, (kf_chunk_summary_kernel<D, F>), g1, 128, 0, t, y, rvec, sp, N, L, nC, f0, batch);
+  CHK(run_scan<FE>(ctx, fp, batch));
   dim3 g3((nC + 127) / 128, batch);
-  if (smooth) {
-    const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
-    LAUNCH(ctx, (kf_chunk_filter_kernel<D, true>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, d_alpha, part, fs, s0, (double*)nullptr);
-    if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
-    CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
-    LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, d_mean, d_var);
+  if constexpr (NC == 1) {
+    if (smooth) {
+      const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
+      LAUNCH(ctx, (kf_chunk_filter_kernel<D, true, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, s0,
+             (double*)nullptr, (double*)nullptr, (double*)nullptr);
+      if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
+      CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
+      LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var);
+    } else {
+      LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
+             o.table, (double*)nullptr, (double*)nullptr);
+    }
   } else {
-    LAUNCH(ctx, (kf_chunk_filter_kernel<D, false>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, d_alpha, part, fs, none, d_table);
+    if (smooth) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: the smoother has no tangent mode");
+    LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, F>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
+           o.table, o.dalpha, o.dtable);
   }
-  double* part2 = part + (size_t)batch * nC * 2;
-  LAUNCH(ctx, lml_partial_kernel, dim3(nslice, batch), 256, 0, part, nC, nslice, part2);
-  LAUNCH(ctx, lml_reduce_kernel, batch, 64, 0, part2, nslice, N, d_lml, d_sums);
+  double* part2 = part + (size_t)batch * nC * 2 * NC;
+  LAUNCH(ctx, lml_partial_kernel<NC>, dim3(nslice, batch), 256, 0, part, nC, nslice, part2);
+  LAUNCH(ctx, lml_reduce_kernel<NC>, batch, 64, 0, part2, nslice, N, o.lml, o.dlml, o.sums);
+  return GPAR_OK;
+}
+
+int upload_params(gpar_ctx* ctx, const double* hl, const double* hs, const double* hn, int nparam, SeqParams* sp) {
+  CU(ctx->kal_c.reserve((size_t)3 * nparam * sizeof(double)));
+  double* dp = ctx->kal_c.as<double>();
+  CU(cudaMemcpyAsync(dp, hl, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp + nparam, hs, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp + 2 * nparam, hn, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *sp = SeqParams{dp, dp + nparam, dp + 2 * nparam, nparam, -1, -1, -1};
   return GPAR_OK;
 }
 
@@ -470,16 +584,34 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
               double* d_table, double* d_sums) {
   if (N < 1 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: need at least one time step and one sequence");
   if (d_table && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
-  CU(ctx->kal_c.reserve((size_t)3 * nparam * sizeof(double)));
-  double* dp = ctx->kal_c.as<double>();
-  CU(cudaMemcpyAsync(dp, hl, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(dp + nparam, hs, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(dp + 2 * nparam, hn, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  SeqParams sp{dp, dp + nparam, dp + 2 * nparam, nparam};
+  SeqParams sp;
+  CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
+  LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums;
   switch (kind) {
-    case GPAR_MATERN12: return lgssm_run_d<1>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
-    case GPAR_MATERN32: return lgssm_run_d<2>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
-    case GPAR_MATERN52: return lgssm_run_d<3>(ctx, sp, batch, N, t, y, rvec, d_alpha, d_lml, d_mean, d_var, d_table, d_sums);
+    case GPAR_MATERN12: return lgssm_run_d<1, double>(ctx, sp, batch, N, t, y, rvec, o);
+    case GPAR_MATERN32: return lgssm_run_d<2, double>(ctx, sp, batch, N, t, y, rvec, o);
+    case GPAR_MATERN52: return lgssm_run_d<3, double>(ctx, sp, batch, N, t, y, rvec, o);
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "kernel code %d has no state-space form (use Matern12/32/52)", kind);
+  }
+}
+
+// Forward-mode run: values plus two tangents in ONE pass.  dirs = tangent slot (0, 1 or -1) of
+// (l, s, noise).  Outputs: d_lml (batch), d_dlml (batch x 2), d_sums (batch x 6: sum log S, its two
+// tangents, sum alpha^2, its two tangents), optionally alpha, d alpha (2 x batch x N) and, for
+// batch == 1, the step table and its tangent rows (layout: kf_chunk_filter_kernel).
+int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
+                      const double* t, const double* y, const double* rvec, const int dirs[3],
+                      double* d_alpha, double* d_lml, double* d_dlml, double* d_sums, double* d_dalpha, double* d_table, double* d_dtable) {
+  if (N < 1 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: need at least one time step and one sequence");
+  if ((d_table || d_dtable) && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
+  SeqParams sp;
+  CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
+  sp.dir_l = dirs[0]; sp.dir_s = dirs[1]; sp.dir_n = dirs[2];
+  LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.dlml = d_dlml; o.sums = d_sums; o.dalpha = d_dalpha; o.table = d_table; o.dtable = d_dtable;
+  switch (kind) {
+    case GPAR_MATERN12: return lgssm_run_d<1, Dual<2>>(ctx, sp, batch, N, t, y, rvec, o);
+    case GPAR_MATERN32: return lgssm_run_d<2, Dual<2>>(ctx, sp, batch, N, t, y, rvec, o);
+    case GPAR_MATERN52: return lgssm_run_d<3, Dual<2>>(ctx, sp, batch, N, t, y, rvec, o);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "kernel code %d has no state-space form (use Matern12/32/52)", kind);
   }
 }
@@ -511,6 +643,44 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   timer.stop();
   CU(cudaMemcpyAsync(lml, ctx->kal_d.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+// logpdf and its gradient with respect to the raw parameters theta (NEW: the reference's optimisers
+// are derivative-free).  One forward-mode pass carries two tangents through the whole scan; the third
+// derivative follows from the scale identity  s dF/ds + sigma^2 dF/dsigma^2 = -1/2 (N - sum alpha^2)
+// (Sigma(c s, c sigma^2) = c Sigma).  With a resident noise vector the tangents are (l, s) and the
+// theta noise parameter has no effect (gradient 0).
+int gpar_lgssm_logpdf_grad(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml, double* grad) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !lml || !grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf_grad: theta, lml and grad must not be NULL");
+  CHK(check_seq(ctx, "lgssm_logpdf_grad"));
+  const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
+  if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf_grad: batch_theta=%d must be 1 or the outputs batch %d", batch_theta, batch);
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx); ctx->phase_valid = false;
+  std::vector<GpParams> ps(batch_theta);
+  std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
+  for (int b = 0; b < batch_theta; b++) { ps[b] = unpack_gp3(theta + 3 * b); hl[b] = ps[b].l; hs[b] = ps[b].s; hn[b] = ps[b].noise; }
+  const bool rv = ctx->has_rvec;
+  const int dirs[3] = {0, rv ? 1 : -1, rv ? -1 : 1};
+  CU(ctx->kal_d.reserve((size_t)batch * 9 * sizeof(double)));
+  double* d_lml = ctx->kal_d.as<double>(); double* d_dlml = d_lml + batch; double* d_sums = d_dlml + 2 * (size_t)batch;
+  CHK(lgssm_run_tangent(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                        rv ? ctx->rvec.as<double>() : nullptr, dirs, nullptr, d_lml, d_dlml, d_sums, nullptr, nullptr, nullptr));
+  timer.stop();
+  std::vector<double> h((size_t)batch * 9);
+  CU(cudaMemcpyAsync(h.data(), d_lml, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < batch; b++) {
+    const GpParams& p = ps[batch_theta == 1 ? 0 : b];
+    lml[b] = h[b];
+    const double d0 = h[batch + 2 * b], d1 = h[batch + 2 * b + 1], a2 = h[3 * (size_t)batch + 6 * b + 3];
+    double dl = d0, ds, dn;
+    if (rv) { ds = d1; dn = 0.0; }
+    else { dn = d1; ds = (-0.5 * ((double)N - a2) - p.noise * dn) / p.s; }
+    grad[3 * b + 0] = dl * p.dl; grad[3 * b + 1] = ds * p.ds_dv; grad[3 * b + 2] = dn * p.dn;
+  }
   return GPAR_OK;
 }
 

@@ -3,6 +3,7 @@
 // row-major): D=3 -> [00 01 02 11 12 22].
 #pragma once
 #include "common.cuh"
+#include "dual.cuh"
 
 template <int D> struct SymIdx;
 template <> struct SymIdx<1> { __host__ __device__ static constexpr int at(int i, int j) { return 0; } };
@@ -18,16 +19,16 @@ template <int D> constexpr int NSYM = D * (D + 1) / 2;
 template <int D> __device__ __forceinline__ double lgssm_lambda() { return D == 1 ? 1.0 : (D == 2 ? 1.7320508075688772 : 2.23606797749979); }
 
 // Stationary unit-variance covariance P_inf (packed) — TemporalGPs stationary_distribution.
-template <int D> __device__ __forceinline__ void lgssm_pinf(double* P) {
+template <int D, class F> __device__ __forceinline__ void lgssm_pinf(F* P) {
   if (D == 1) { P[0] = 1.0; }
   else if (D == 2) { P[0] = 1.0; P[1] = 0.0; P[2] = 3.0; }
   else { P[0] = 1.0; P[1] = 0.0; P[2] = -5.0 / 3.0; P[3] = 5.0 / 3.0; P[4] = 0.0; P[5] = 25.0; }
 }
 
 // A = exp(F a) = e^{-lam a} (I + N a + N^2 a^2/2),  N = F + lam I  (row-major D x D)
-template <int D> __device__ __forceinline__ void lgssm_transition(double a, double* A) {
+template <int D, class F> __device__ __forceinline__ void lgssm_transition(F a, F* A) {
   const double lam = lgssm_lambda<D>();
-  const double e = exp(-lam * a);
+  const F e = exp(-lam * a);
   if (D == 1) { A[0] = e; }
   else if (D == 2) {
     // N = [lam 1; -lam^2 -lam]
@@ -35,7 +36,7 @@ template <int D> __device__ __forceinline__ void lgssm_transition(double a, doub
     A[2] = e * (-lam * lam * a); A[3] = e * (1.0 - lam * a);
   } else {
     // N = [lam 1 0; 0 lam 1; -lam^3 -3lam^2 -2lam],  N^2 = [lam^2 2lam 1; -lam^3 -2lam^2 -lam; lam^4 2lam^3 lam^2]
-    const double l2 = lam * lam, l3 = l2 * lam, l4 = l2 * l2, h = 0.5 * a * a;
+    const double l2 = lam * lam, l3 = l2 * lam, l4 = l2 * l2; const F h = 0.5 * a * a;
     A[0] = e * (1.0 + lam * a + l2 * h);  A[1] = e * (a + 2.0 * lam * h);            A[2] = e * h;
     A[3] = e * (-l3 * h);                 A[4] = e * (1.0 + lam * a - 2.0 * l2 * h);  A[5] = e * (a - lam * h);
     A[6] = e * (-l3 * a + l4 * h);        A[7] = e * (-3.0 * l2 * a + 2.0 * l3 * h);  A[8] = e * (1.0 - 2.0 * lam * a + l2 * h);
@@ -43,29 +44,29 @@ template <int D> __device__ __forceinline__ void lgssm_transition(double a, doub
 }
 
 // R = A S A^T  (S symmetric packed; result packed)
-template <int D> __device__ __forceinline__ void asat(const double* A, const double* S, double* R) {
-  double T[D * D];
+template <int D, class F> __device__ __forceinline__ void asat(const F* A, const F* S, F* R) {
+  F T[D * D];
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = 0; j < D; j++) { double v = 0.0;
+    for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(A[i * D + k], SYM(S, k, j), v);
       T[i * D + j] = v; }
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = i; j < D; j++) { double v = 0.0;
+    for (int j = i; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(T[i * D + k], A[j * D + k], v);
       SYM(R, i, j) = v; }
 }
 
 // Q = P0 - A P0 A^T   (P0 = s P_inf; for D = 3 the zeros of P_inf are skipped: 33 instead of 45 FMA)
-template <int D> __device__ __forceinline__ void lgssm_q(const double* A, const double* P0, double* Q) {
-  double R[NSYM<D>];
+template <int D, class F> __device__ __forceinline__ void lgssm_q(const F* A, const F* P0, F* Q) {
+  F R[NSYM<D>];
   if (D == 3) {
-    double T[9];
+    F T[9];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       T[i * 3 + 0] = fma(A[i * 3 + 2], P0[2], A[i * 3 + 0] * P0[0]);
@@ -75,7 +76,7 @@ template <int D> __device__ __forceinline__ void lgssm_q(const double* A, const 
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int j = i; j < 3; j++) { double v = 0.0;
+      for (int j = i; j < 3; j++) { F v = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; k++) v = fma(T[i * 3 + k], A[j * 3 + k], v);
         SYM(R, i, j) = v; }
@@ -86,59 +87,59 @@ template <int D> __device__ __forceinline__ void lgssm_q(const double* A, const 
   for (int i = 0; i < NSYM<D>; i++) Q[i] = P0[i] - R[i];
 }
 
-template <int D> __device__ __forceinline__ void matvec(const double* A, const double* x, double* y) {
+template <int D, class F> __device__ __forceinline__ void matvec(const F* A, const F* x, F* y) {
 #pragma unroll
-  for (int i = 0; i < D; i++) { double v = 0.0;
+  for (int i = 0; i < D; i++) { F v = 0.0;
 #pragma unroll
     for (int k = 0; k < D; k++) v = fma(A[i * D + k], x[k], v);
     y[i] = v; }
 }
-template <int D> __device__ __forceinline__ void matmul(const double* A, const double* B, double* C) {
+template <int D, class F> __device__ __forceinline__ void matmul(const F* A, const F* B, F* C) {
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = 0; j < D; j++) { double v = 0.0;
+    for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(A[i * D + k], B[k * D + j], v);
       C[i * D + j] = v; }
 }
 // C = A * S (S symmetric packed) -> full
-template <int D> __device__ __forceinline__ void matsym(const double* A, const double* S, double* C) {
+template <int D, class F> __device__ __forceinline__ void matsym(const F* A, const F* S, F* C) {
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = 0; j < D; j++) { double v = 0.0;
+    for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(A[i * D + k], SYM(S, k, j), v);
       C[i * D + j] = v; }
 }
 // C = S * A (S symmetric packed) -> full
-template <int D> __device__ __forceinline__ void symmat(const double* S, const double* A, double* C) {
+template <int D, class F> __device__ __forceinline__ void symmat(const F* S, const F* A, F* C) {
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = 0; j < D; j++) { double v = 0.0;
+    for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(SYM(S, i, k), A[k * D + j], v);
       C[i * D + j] = v; }
 }
-template <int D> __device__ __forceinline__ void symvec(const double* S, const double* x, double* y) {
+template <int D, class F> __device__ __forceinline__ void symvec(const F* S, const F* x, F* y) {
 #pragma unroll
-  for (int i = 0; i < D; i++) { double v = 0.0;
+  for (int i = 0; i < D; i++) { F v = 0.0;
 #pragma unroll
     for (int k = 0; k < D; k++) v = fma(SYM(S, i, k), x[k], v);
     y[i] = v; }
 }
 
 // general inverse (adjugate); returns via Minv
-template <int D> __device__ __forceinline__ void inv_general(const double* M, double* Minv) {
+template <int D, class F> __device__ __forceinline__ void inv_general(const F* M, F* Minv) {
   if (D == 1) { Minv[0] = 1.0 / M[0]; }
   else if (D == 2) {
-    double id = 1.0 / (M[0] * M[3] - M[1] * M[2]);
+    F id = 1.0 / (M[0] * M[3] - M[1] * M[2]);
     Minv[0] = M[3] * id; Minv[1] = -M[1] * id; Minv[2] = -M[2] * id; Minv[3] = M[0] * id;
   } else {
-    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
-    double id = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+    F c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    F id = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
     Minv[0] = c00 * id; Minv[3] = c01 * id; Minv[6] = c02 * id;
     Minv[1] = (M[2] * M[7] - M[1] * M[8]) * id; Minv[4] = (M[0] * M[8] - M[2] * M[6]) * id; Minv[7] = (M[1] * M[6] - M[0] * M[7]) * id;
     Minv[2] = (M[1] * M[5] - M[2] * M[4]) * id; Minv[5] = (M[2] * M[3] - M[0] * M[5]) * id; Minv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
@@ -147,13 +148,13 @@ template <int D> __device__ __forceinline__ void inv_general(const double* M, do
 
 // X = W * (S + eps I)^{-1} for symmetric positive definite S (packed), through the Cholesky
 // factor as TemporalGPs' smooth does (U = cholesky(P + eps I).U; Gt = U \ (U' \ (A P))).
-template <int D> __device__ __forceinline__ void solve_spd_right(const double* W, const double* S, double eps, double* X) {
-  double L[D * D];
+template <int D, class F> __device__ __forceinline__ void solve_spd_right(const F* W, const F* S, double eps, F* X) {
+  F L[D * D];
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
     for (int j = 0; j <= i; j++) {
-      double v = SYM(S, i, j) + (i == j ? eps : 0.0);
+      F v = SYM(S, i, j) + (i == j ? eps : 0.0);
 #pragma unroll
       for (int q = 0; q < j; q++) v -= L[i * D + q] * L[j * D + q];
       L[i * D + j] = (i == j) ? sqrt(v) : v / L[j * D + j];
@@ -161,14 +162,14 @@ template <int D> __device__ __forceinline__ void solve_spd_right(const double* W
   // row r of X solves (L L^T) x = W[r,:]^T
 #pragma unroll
   for (int r = 0; r < D; r++) {
-    double z[D];
+    F z[D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { double v = W[r * D + i];
+    for (int i = 0; i < D; i++) { F v = W[r * D + i];
 #pragma unroll
       for (int q = 0; q < i; q++) v -= L[i * D + q] * z[q];
       z[i] = v / L[i * D + i]; }
 #pragma unroll
-    for (int i = D - 1; i >= 0; i--) { double v = z[i];
+    for (int i = D - 1; i >= 0; i--) { F v = z[i];
 #pragma unroll
       for (int q = i + 1; q < D; q++) v -= L[q * D + i] * X[r * D + q];
       X[r * D + i] = v / L[i * D + i]; }
@@ -176,11 +177,11 @@ template <int D> __device__ __forceinline__ void solve_spd_right(const double* W
 }
 
 // C = S1 * S2 (both symmetric packed) -> full
-template <int D> __device__ __forceinline__ void symsym(const double* S1, const double* S2, double* C) {
+template <int D, class F> __device__ __forceinline__ void symsym(const F* S1, const F* S2, F* C) {
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int j = 0; j < D; j++) { double v = 0.0;
+    for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) v = fma(SYM(S1, i, k), SYM(S2, k, j), v);
       C[i * D + j] = v; }
@@ -188,12 +189,14 @@ template <int D> __device__ __forceinline__ void symsym(const double* S1, const 
 
 // ---- filtering element (Sarkka & Garcia-Fernandez 2021, temporal parallelisation of Bayesian
 //      smoothers): p(x_k | x_{k-1}, y) = N(A x + b, C),  p(y | x_{k-1}) ~ N_info(eta, J) ----------
-template <int D> struct FiltElem {
+template <int D, class F = double> struct FiltElem {
   static constexpr int NF = D * D + 2 * D + 2 * NSYM<D>;
   static constexpr int OB = D * D, OC = OB + D, OE = OC + NSYM<D>, OJ = OE + D;
-  double v[NF];
+  typedef F scalar_t;
+  static constexpr int NFD = NF * Scalar<F>::NC;     // doubles per element (value + tangents)
+  F v[NF];
   __device__ __forceinline__ void set_identity() {
-    double *A = v, *b = v + OB, *C = v + OC, *eta = v + OE, *J = v + OJ;
+    F *A = v, *b = v + OB, *C = v + OC, *eta = v + OE, *J = v + OJ;
 #pragma unroll
     for (int i = 0; i < D * D; i++) A[i] = (i / D == i % D) ? 1.0 : 0.0;
 #pragma unroll
@@ -204,11 +207,11 @@ template <int D> struct FiltElem {
   // result = e1 (earlier in time) then e2 (later in time)
   __device__ __forceinline__ static FiltElem combine(const FiltElem& x1, const FiltElem& x2) {
     FiltElem rr;
-    struct V { const double *A, *b, *C, *eta, *J; };
-    struct W { double *A, *b, *C, *eta, *J; };
+    struct V { const F *A, *b, *C, *eta, *J; };
+    struct W { F *A, *b, *C, *eta, *J; };
     const V e1{x1.v, x1.v + OB, x1.v + OC, x1.v + OE, x1.v + OJ}, e2{x2.v, x2.v + OB, x2.v + OC, x2.v + OE, x2.v + OJ};
     const W r{rr.v, rr.v + OB, rr.v + OC, rr.v + OE, rr.v + OJ};
-    double Mx[D * D], Mi[D * D], X[D * D], T[D * D], v[D], u[D];
+    F Mx[D * D], Mi[D * D], X[D * D], T[D * D], v[D], u[D];
     symsym<D>(e1.C, e2.J, Mx);
 #pragma unroll
     for (int i = 0; i < D; i++) Mx[i * D + i] += 1.0;
@@ -225,7 +228,7 @@ template <int D> struct FiltElem {
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
-      for (int j = i; j < D; j++) { double a = SYM(e2.C, i, j);
+      for (int j = i; j < D; j++) { F a = SYM(e2.C, i, j);
 #pragma unroll
         for (int k = 0; k < D; k++) a = fma(T[i * D + k], e2.A[j * D + k], a);
         SYM(r.C, i, j) = a; }
@@ -233,7 +236,7 @@ template <int D> struct FiltElem {
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
-      for (int j = 0; j < D; j++) { double a = 0.0;
+      for (int j = 0; j < D; j++) { F a = 0.0;
 #pragma unroll
         for (int k = 0; k < D; k++) a = fma(e1.A[k * D + i], Mi[j * D + k], a);
         X[i * D + j] = a; }
@@ -247,7 +250,7 @@ template <int D> struct FiltElem {
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
-      for (int j = i; j < D; j++) { double a = SYM(e1.J, i, j);
+      for (int j = i; j < D; j++) { F a = SYM(e1.J, i, j);
 #pragma unroll
         for (int k = 0; k < D; k++) a = fma(T[i * D + k], e1.A[k * D + j], a);
         SYM(r.J, i, j) = a; }
@@ -258,12 +261,14 @@ template <int D> struct FiltElem {
 };
 
 // ---- smoothing element: m^s_k = E m^s_{k+1} + g,  P^s_k = E P^s_{k+1} E^T + L ---------------
-template <int D> struct SmoothElem {
+template <int D, class F = double> struct SmoothElem {
   static constexpr int NF = D * D + D + NSYM<D>;
   static constexpr int OG = D * D, OL = OG + D;
-  double v[NF];
+  typedef F scalar_t;
+  static constexpr int NFD = NF * Scalar<F>::NC;
+  F v[NF];
   __device__ __forceinline__ void set_identity() {
-    double *E = v, *g = v + OG, *L = v + OL;
+    F *E = v, *g = v + OG, *L = v + OL;
 #pragma unroll
     for (int i = 0; i < D * D; i++) E[i] = (i / D == i % D) ? 1.0 : 0.0;
 #pragma unroll
@@ -274,11 +279,11 @@ template <int D> struct SmoothElem {
   // e1 earlier in time, e2 later in time: (E1 E2, E1 g2 + g1, E1 L2 E1^T + L1)
   __device__ __forceinline__ static SmoothElem combine(const SmoothElem& x1, const SmoothElem& x2) {
     SmoothElem rr;
-    struct V { const double *E, *g, *L; };
-    struct W { double *E, *g, *L; };
+    struct V { const F *E, *g, *L; };
+    struct W { F *E, *g, *L; };
     const V e1{x1.v, x1.v + OG, x1.v + OL}, e2{x2.v, x2.v + OG, x2.v + OL};
     const W r{rr.v, rr.v + OG, rr.v + OL};
-    double u[D], R[NSYM<D>];
+    F u[D], R[NSYM<D>];
     matmul<D>(e1.E, e2.E, r.E);
     matvec<D>(e1.E, e2.g, u);
 #pragma unroll

@@ -110,6 +110,10 @@ int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double param
  *   sequence b uses theta b (independent models); with batch_theta == 1 all sequences share it.
  *   lml: one value per sequence (temporal_gp_inference.jl:78). */
 int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml);
+/* The same log-pdf with its gradient (NEW — the reference's optimisers are derivative-free,
+ * temporal_gp_inference.jl:82): grad + 3*b = d lml[b] / d theta of the parameter set sequence b uses
+ * (its own, or the shared one).  With a resident noise vector d/d theta[2] = 0 (sigma is unused). */
+int gpar_lgssm_logpdf_grad(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml, double* grad);
 /* decorrelate (dtc.jl:106,115): alpha (N x batch) and lml (batch) for every resident sequence. */
 int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], double* alpha, double* lml);
 /* smooth (temporal_gp_inference.jl:109; gpar_scaled_inference.jl:117): mean = m_s[1], var = P_s[1,1]

@@ -91,6 +91,14 @@ function lgssm_logpdf(c::Ctx, k, theta::VecOrMat{Float64}, batch::Integer)
     return lml
 end
 
+"logpdf and d logpdf / d theta (3 x batch) — for gradient-based optimisers (Optim.LBFGS) in place of NelderMead."
+function lgssm_logpdf_grad(c::Ctx, k, theta::VecOrMat{Float64}, batch::Integer)
+    lml = zeros(batch); grad = zeros(3, batch)
+    check(c, ccall((:gpar_lgssm_logpdf_grad, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, size(theta, 2), lml, grad))
+    return lml, grad
+end
+
 function lgssm_decorrelate(c::Ctx, k, theta::Vector{Float64}, N::Integer, batch::Integer = 1)
     alpha = zeros(N, batch); lml = zeros(batch)
     check(c, ccall((:gpar_lgssm_decorrelate, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),

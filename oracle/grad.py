@@ -107,7 +107,7 @@ def kalman_decorrelate_t(kind, t, V, l, s, noise):
         Q = P0 - A @ P0 @ A.T
         Mp = A @ M
         Pp = A @ P @ A.T + Q
-        S = Pp[0, 0] + noise
+        S = Pp[0, 0] + (noise[k] if getattr(noise, 'ndim', 0) == 1 else noise)
         sq = torch.sqrt(S)
         B = Pp[0, :] / sq
         a = (V[k] - Mp[0]) / sq
@@ -116,6 +116,23 @@ def kalman_decorrelate_t(kind, t, V, l, s, noise):
         alphas.append(a)
         logS = logS + torch.log(S)
     return logS, torch.stack(alphas)
+
+
+def lgssm_logpdf_value_and_grad(theta, t, y, kind=3, rvec=None):
+    """logpdf(lgssm, y) (temporal_gp_inference.jl:78) and its autograd gradient w.r.t. the raw theta;
+    sequential torch filter — small n only.  rvec: optional per-step noise (then sigma is unused)."""
+    th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    p = _unpack(th)
+    t = torch.as_tensor(t, dtype=torch.float64)
+    y = torch.as_tensor(y, dtype=torch.float64)
+    if rvec is None:
+        logS, a = kalman_decorrelate_t(kind, t, y[:, None], p[0], p[1] * p[1], p[2] * p[2])
+    else:
+        logS, a = kalman_decorrelate_t(kind, t, y[:, None], p[0], p[1] * p[1], torch.as_tensor(rvec, dtype=torch.float64))
+    v = -(y.shape[0] * LOG2PI + logS + (a * a).sum()) / 2.0
+    v.backward()
+    g = th.grad.numpy().copy() if th.grad is not None else None
+    return float(v.detach()), g
 
 
 def scaled_dtc_t(theta, X, Z, t, y, k_time, k_out):

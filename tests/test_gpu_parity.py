@@ -133,6 +133,60 @@ def test_lgssm_vs_c_oracle(ctx, kind, n, batch):
     ctx.set_noise_vector(None)
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+@pytest.mark.parametrize("n,batch", [(1, 1), (7, 2), (33, 1), (300, 3), (1100, 2)])
+def test_lgssm_logpdf_grad_vs_autograd(ctx, kind, n, batch):
+    """gpar_lgssm_logpdf_grad (forward-mode tangents through the whole scan + the scale identity)
+    against torch autograd of the sequential oracle filter; independent and shared models, with and
+    without a noise vector.  Gradient tolerance 1e-6 relative (observed ~1e-11)."""
+    from oracle.grad import lgssm_logpdf_value_and_grad
+    rng = np.random.default_rng(7 * kind + n)
+    t = np.cumsum(rng.exponential(1 / 30, n))
+    if n > 40:
+        t[n // 2] = t[n // 2 - 1]
+    Y = rng.normal(size=(batch, n))
+    rv = np.where(rng.uniform(size=n) < 0.1, 1e10, 0.09)
+    ths = rng.uniform(-1.5, 0.5, (batch, 3))
+    ctx.set_times(t); ctx.set_outputs(Y)
+    for rvec in (None, rv):
+        ctx.set_noise_vector(rvec)
+        for shared in (False, True):
+            th_in = ths[:1] if shared else ths
+            lml, grad = ctx.lgssm_logpdf_grad(kind, th_in)
+            assert relerr(lml, ctx.lgssm_logpdf(kind, th_in)) <= 1e-12
+            for b in range(batch):
+                v0, g0 = lgssm_logpdf_value_and_grad(th_in[0 if shared else b], t, Y[b], kind, rvec=rvec)
+                assert abs(lml[b] - v0) <= RTOL * abs(v0)
+                assert np.all(np.abs(grad[b] - g0) <= 1e-6 * np.abs(g0) + 1e-8 * np.max(np.abs(g0))), (grad[b], g0)
+    ctx.set_noise_vector(None)
+
+
+def test_lgssm_logpdf_grad_full_size(ctx):
+    """1024 x 10k independent models and one 10M-step sequence: the gradient against central
+    differences of the DEVICE log-pdf (itself pinned on the C oracle above); h = 1e-5 in theta."""
+    rng = np.random.default_rng(12)
+    B, N = 1024, 10000
+    t = np.cumsum(rng.exponential(1 / 30, N)); Y = rng.normal(size=(B, N))
+    ths = np.stack([np.log(rng.uniform(0.05, 5, B)), np.log(rng.uniform(0.3, 3, B)), np.log(rng.uniform(0.01, 1, B))], axis=1)
+    ctx.set_times(t); ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    lml, grad = ctx.lgssm_logpdf_grad(3, ths)
+    assert relerr(lml, ctx.lgssm_logpdf(3, ths)) <= 1e-12
+    h = 1e-5
+    for i in range(3):
+        e = np.zeros(3); e[i] = h
+        fd = (ctx.lgssm_logpdf(3, ths + e) - ctx.lgssm_logpdf(3, ths - e)) / (2 * h)
+        assert np.max(np.abs(grad[:, i] - fd) / (np.abs(fd) + 1e-3 * np.max(np.abs(fd)))) <= 1e-5
+    N = 10_000_000
+    t = np.arange(N) / 30.0; y = np.sin(0.01 * t) + 0.1 * rng.normal(size=N)
+    th = np.log([1.0, 1.0, 0.1])
+    ctx.set_times(t); ctx.set_outputs(y)
+    lml, grad = ctx.lgssm_logpdf_grad(3, th)
+    for i in range(3):
+        e = np.zeros(3); e[i] = h
+        fd = (ctx.lgssm_logpdf(3, th + e)[0] - ctx.lgssm_logpdf(3, th - e)[0]) / (2 * h)
+        assert abs(grad[0, i] - fd) <= 1e-5 * abs(fd) + 1e-2
+
+
 def test_lgssm_full_size_config3(ctx):
     """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
     and one 10M-step sequence; every lml against the C oracle."""
