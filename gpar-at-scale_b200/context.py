@@ -107,6 +107,14 @@ class Context:
         self._check(self._lib.gpar_scaled_dtc(self._h, int(k_time), int(k_out), dptr(th), ctypes.byref(val), dptr(A)))
         return (val.value, A) if return_A else val.value
 
+    def scaled_dtc_grad(self, k_time, k_out, theta):
+        """-> (dtc, d dtc / d theta (5,))."""
+        th = as_f64(np.asarray(theta).ravel())
+        val = ctypes.c_double()
+        g = np.zeros(5)
+        self._check(self._lib.gpar_scaled_dtc_grad(self._h, int(k_time), int(k_out), dptr(th), ctypes.byref(val), dptr(g)))
+        return val.value, g
+
     def compute_q_u(self, k_time, k_out, params):
         p = as_f64(np.asarray(params).ravel())
         m_e = np.zeros(self.M)

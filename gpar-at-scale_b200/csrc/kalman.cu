@@ -192,7 +192,7 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
 // part: [b][c][2 NC] = (sum log S, sum alpha^2), each with its tangents.  SMOOTH additionally stores
 // the filtered states fs (f < D + NSYM, warp-coalesced) and the chunk smoothing element at reversed
 // index.  Dual instantiations also emit d alpha (dalpha[(j*batch + b)*N + k]) and the tangent rows of
-// the step table (dtable, layout in scaled.cu).
+// the step table: dtable row k = [sqrt(S_k), 0, then per tangent: dPhi (D*D), dK (D), dHA (D), dlog rs].
 template <int D, bool SMOOTH, class F>
 __global__ void __launch_bounds__(128, Scalar<F>::NC == 1 ? (SMOOTH ? 2 : KF_MIN_BLOCKS) : 1)
 kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
@@ -298,7 +298,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
         constexpr int TS = D * D + 2 * D + 1;
         double* row = table + k * TS;
         double* drow = nullptr;
-        if constexpr (NC > 1) { if (dtable) drow = dtable + k * (1 + (NC - 1) * TS); }
+        if constexpr (NC > 1) { if (dtable) drow = dtable + k * (2 + (NC - 1) * TS); }
         const F iS = 1.0 / S;
         F ent[TS];
 #pragma unroll
@@ -315,12 +315,13 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
         if constexpr (NC > 1) {
           if (drow) {
             drow[0] = value_of(S) * value_of(rs);       // sqrt(S): turns beta back into the innovation
+            drow[1] = 0.0;                              // (pad: keeps the tangent rows 16-byte aligned)
             const double irs = 1.0 / value_of(rs);
 #pragma unroll
             for (int j = 1; j < NC; j++) {
 #pragma unroll
-              for (int i = 0; i < TS - 1; i++) drow[1 + (j - 1) * TS + i] = SC::comp(ent[i], j);
-              drow[1 + (j - 1) * TS + TS - 1] = SC::comp(rs, j) * irs;   // d log rs
+              for (int i = 0; i < TS - 1; i++) drow[2 + (j - 1) * TS + i] = SC::comp(ent[i], j);
+              drow[2 + (j - 1) * TS + TS - 1] = SC::comp(rs, j) * irs;   // d log rs
             }
           }
         }

@@ -45,21 +45,24 @@ __device__ __forceinline__ void stage_table(double* buf, const double* __restric
 // pass 1: K panel + zero-state chunk response b_c[m] (D doubles) -> resp[(c*D + i)*Mpad + m].
 // Each thread carries CT columns (one per M-tile mt0..mt0+CT-1) so that a step's table row
 // (Phi_k, K_k — shared by every column) is loaded once per CT kernel evaluations.
-template <int KIND, int DX, int D, int CT>
+template <int KIND, int DX, int D, int CT, bool GRAD>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
-                    const double* __restrict__ table, double* __restrict__ panel, double* __restrict__ resp, int Mpad) {
+                    const double* __restrict__ table, double* __restrict__ panel, double* __restrict__ resp, int Mpad,
+                    double* __restrict__ panelD) {
   constexpr int TS = D * D + 2 * D + 1;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   double z[CT][DX], ms[CT][D];
   bool mvalid[CT];
   double* out[CT];
+  double* outd[CT];
   const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
   const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
 #pragma unroll
   for (int c = 0; c < CT; c++) {
     const int m = (mt0 + c) * GPAR_TILE + mi;
     mvalid[c] = m < M;
+    outd[c] = GRAD ? panelD + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4 : nullptr;
 #pragma unroll
     for (int d = 0; d < DX; d++) z[c][d] = mvalid[c] ? Z[(int64_t)m * DX + d] : 0.0;
 #pragma unroll
@@ -75,7 +78,7 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
     __syncthreads();
     const int64_t ge = (gs + WH_SUB / 4 < g1) ? gs + WH_SUB / 4 : g1;
     for (int64_t g = gs; g < ge; g++) {
-      double kv[CT][4];
+      double kv[CT][4], dv[GRAD ? CT : 1][4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int64_t n = g * 4 + j;
@@ -96,9 +99,10 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
           double d2 = 0.0;
 #pragma unroll
           for (int d = 0; d < DX; d++) { double df = x[d] - z[c][d]; d2 = fma(df, df, d2); }
-          double dummy; double k = base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
+          double ld = 0.0; double k = base_kernel_dev<KIND, GRAD>(d2 * inv_l2, ld);
           k = (valid && mvalid[c]) ? s * k : 0.0;
           kv[c][j] = k;
+          if (GRAD) dv[c][j] = (valid && mvalid[c]) ? s * ld : 0.0;
           if (valid) {   // m <- Phi m + K v
             double nm[D];
 #pragma unroll
@@ -116,6 +120,11 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
         reinterpret_cast<double2*>(out[c])[0] = make_double2(kv[c][0], kv[c][1]);
         reinterpret_cast<double2*>(out[c])[1] = make_double2(kv[c][2], kv[c][3]);
         out[c] += GPAR_TILE * 4;
+        if (GRAD) {
+          reinterpret_cast<double2*>(outd[c])[0] = make_double2(dv[c][0], dv[c][1]);
+          reinterpret_cast<double2*>(outd[c])[1] = make_double2(dv[c][2], dv[c][3]);
+          outd[c] += GPAR_TILE * 4;
+        }
       }
     }
     __syncthreads();
@@ -334,10 +343,226 @@ __global__ void panel_to_dense_t_kernel(const double* __restrict__ panel, int64_
   Bt[e] = panel[((((int64_t)(m / GPAR_TILE)) * NB4 + n / 4) * GPAR_TILE + (m % GPAR_TILE)) * 4 + (n % 4)];
 }
 
+// ---- gradient of the scaled objective (NEW: the reference has none) -------------------------------
+// With P = (cov(u) + G)^-1, w = P g, e = alpha - beta w (SURVEY Appendix A statistics, sigma^2 = 1 form
+// of the tail) the objective's differential is
+//   dF = <R, d beta> - <e, d alpha> - 1/2 d sum log S + (M x M terms of the tail),   R = -beta P + e w'.
+// d beta for the temporal parameters is the TANGENT of the whitening recursion (the tangent rows of the
+// step table come from the Dual Kalman pass), d beta for the output length scale is the whitening of
+// l dK/dl; both are produced on the fly here and contracted with R, so no N x M tangent is stored.
+constexpr int WB_SUB = 32;      // steps per staged window of the tangent pass
+
+template <int ROW>
+__device__ __forceinline__ void stage_rows(double* buf, const double* __restrict__ src, int64_t step0, int64_t N, int nsub) {
+  int64_t nrows = N - step0; if (nrows > nsub) nrows = nsub; if (nrows < 0) nrows = 0;
+  const int total = (int)nrows * ROW;
+  const double* p = src + step0 * ROW;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) cp_async8(buf + e, p + e);
+}
+
+// e = alpha - beta w: one warp per group of 4 steps, lanes over the columns (fixed-order shuffle sum)
+__global__ void __launch_bounds__(128)
+residual_kernel(const double* __restrict__ beta, const double* __restrict__ w, const double* __restrict__ alpha,
+                int64_t N, int64_t NB4, int T, int M, double* __restrict__ evec) {
+  const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g * 4 >= N) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int mt = 0; mt < T; mt++) {
+    const double* base = beta + ((int64_t)mt * NB4 + g) * GPAR_TILE * 4;
+#pragma unroll
+    for (int q = 0; q < GPAR_TILE / 32; q++) {
+      const int mi = q * 32 + lane, m = mt * GPAR_TILE + mi;
+      const double wm = m < M ? __ldg(w + m) : 0.0;
+      const double2 b01 = reinterpret_cast<const double2*>(base + mi * 4)[0], b23 = reinterpret_cast<const double2*>(base + mi * 4)[1];
+      a0 = fma(b01.x, wm, a0); a1 = fma(b01.y, wm, a1); a2 = fma(b23.x, wm, a2); a3 = fma(b23.y, wm, a3);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if (lane == 0) {
+    const double r[4] = {a0, a1, a2, a3};
+    for (int j = 0; j < 4; j++) { const int64_t n = g * 4 + j; if (n < N) evec[n] = alpha[n] - r[j]; }
+  }
+}
+
+// Bt (M x ns column-major) = rows [4 g_lo, 4 (g_lo + ng)) of the panel, transposed: feeds the library GEMM S' = P Bt
+__global__ void __launch_bounds__(256)
+panel_slab_to_dense_t_kernel(const double* __restrict__ panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* __restrict__ Bt) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * ng * GPAR_TILE) return;
+  const int mi = (int)(idx % GPAR_TILE); const int64_t r = idx / GPAR_TILE; const int64_t gl = r % ng; const int mt = (int)(r / ng);
+  const int m = mt * GPAR_TILE + mi;
+  if (m >= M) return;
+  const double* src = panel + (((int64_t)mt * NB4 + g_lo + gl) * GPAR_TILE + mi) * 4;
+  const double2 b01 = reinterpret_cast<const double2*>(src)[0], b23 = reinterpret_cast<const double2*>(src)[1];
+  double* dst = Bt + (gl * 4) * (int64_t)M + m;
+  dst[0] = b01.x; dst[M] = b01.y; dst[2 * (int64_t)M] = b23.x; dst[3 * (int64_t)M] = b23.y;
+}
+
+// Tangent whitening.  Per column the recursions
+//   mu'   = Phi mu + Kg v                       (v = beta sqrt(S) + HA mu: the un-whitened entry, recovered from beta)
+//   dmu_j' = dPhi_j mu + Phi dmu_j + dKg_j v,   d beta_j = beta dlog(rs)_j - rs (dHA_j mu + HA dmu_j)     j = 0, 1
+//   nu'   = Phi nu + Kg dk,                     d beta_l = rs (dk - HA nu)                                 (dk = l dK/dl)
+// FINAL = false: zero-start responses of (dmu_0, dmu_1, nu) over each chunk -> tstate (then carry-scanned);
+// FINAL = true : starts from the scanned states and accumulates <R, d beta_*> with R = -S + e w'.
+template <int D, int CT, bool FINAL>
+__global__ void __launch_bounds__(GPAR_TILE)
+whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ dtable,
+                      const double* __restrict__ beta, const double* __restrict__ panelD, const double* __restrict__ start,
+                      double* __restrict__ tstate, int nch, int chunk0, const double* __restrict__ St, const double* __restrict__ evec,
+                      const double* __restrict__ wvec, double* __restrict__ accpart, int Mpad, int M) {
+  constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
+  const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
+  const int chunk = chunk0 + blockIdx.y;
+  const int64_t g0 = (int64_t)chunk * WH_GROUPS;
+  const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const int64_t cstride = (int64_t)nch * D * Mpad;       // one tangent state array
+  const double *inb[CT], *ind[CT], *inS[CT];
+  double mu[CT][D], dm[CT][2][D], nu[CT][D], acc[CT][3], wm[CT];
+  bool mvalid[CT];
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    const int m = (mt0 + c) * GPAR_TILE + mi;
+    mvalid[c] = m < M;
+    inb[c] = beta + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
+    ind[c] = panelD + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
+    inS[c] = FINAL ? St + ((int64_t)blockIdx.y * WH_GROUPS * 4) * M + m : nullptr;
+    wm[c] = (FINAL && mvalid[c]) ? wvec[m] : 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const int64_t o = ((int64_t)chunk * D + i) * Mpad + m;
+      mu[c][i] = start[o];
+      dm[c][0][i] = FINAL ? tstate[o] : 0.0;
+      dm[c][1][i] = FINAL ? tstate[cstride + o] : 0.0;
+      nu[c][i] = FINAL ? tstate[2 * cstride + o] : 0.0;
+    }
+    acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+  }
+  __shared__ double tbl[2][WB_SUB * TS];
+  __shared__ double dtb[2][WB_SUB * DTS];
+  stage_rows<TS>(tbl[0], table, g0 * 4, N, WB_SUB); stage_rows<DTS>(dtb[0], dtable, g0 * 4, N, WB_SUB); cp_async_commit();
+  int cur = 0;
+  for (int64_t gs = g0; gs < g1; gs += WB_SUB / 4) {
+    if (gs + WB_SUB / 4 < g1) {
+      stage_rows<TS>(tbl[cur ^ 1], table, (gs + WB_SUB / 4) * 4, N, WB_SUB); stage_rows<DTS>(dtb[cur ^ 1], dtable, (gs + WB_SUB / 4) * 4, N, WB_SUB);
+      cp_async_commit(); cp_async_wait<1>();
+    } else cp_async_wait<0>();
+    __syncthreads();
+    const int64_t ge = (gs + WB_SUB / 4 < g1) ? gs + WB_SUB / 4 : g1;
+    for (int64_t g = gs; g < ge; g++) {
+      double kv[CT][4], dv[CT][4];
+#pragma unroll
+      for (int c = 0; c < CT; c++) {
+        const double2 a01 = reinterpret_cast<const double2*>(inb[c])[0], a23 = reinterpret_cast<const double2*>(inb[c])[1];
+        kv[c][0] = a01.x; kv[c][1] = a01.y; kv[c][2] = a23.x; kv[c][3] = a23.y;
+        const double2 d01 = reinterpret_cast<const double2*>(ind[c])[0], d23 = reinterpret_cast<const double2*>(ind[c])[1];
+        dv[c][0] = d01.x; dv[c][1] = d01.y; dv[c][2] = d23.x; dv[c][3] = d23.y;
+        inb[c] += GPAR_TILE * 4; ind[c] += GPAR_TILE * 4;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int64_t n = g * 4 + j;
+        if (n < N) {
+          const double* row = tbl[cur] + (int)(n - gs * 4) * TS;
+          const double* drow = dtb[cur] + (int)(n - gs * 4) * DTS;
+          double F[D * D], Kg[D], ha[D];
+#pragma unroll
+          for (int i = 0; i < D * D; i++) F[i] = row[i];
+#pragma unroll
+          for (int i = 0; i < D; i++) { Kg[i] = row[D * D + i]; ha[i] = row[D * D + D + i]; }
+          const double rs = row[D * D + 2 * D], sqS = drow[0];
+          const double en = FINAL ? __ldg(evec + n) : 0.0;
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            const double b = kv[c][j], dk = dv[c][j];
+            double pred = 0.0, predn = 0.0;
+#pragma unroll
+            for (int q = 0; q < D; q++) { pred = fma(ha[q], mu[c][q], pred); predn = fma(ha[q], nu[c][q], predn); }
+            const double v = fma(b, sqS, pred);
+            double rr = 0.0;
+            if (FINAL) {
+              const double sv = mvalid[c] ? __ldg(inS[c] + (int64_t)(n - g0 * 4) * M) : 0.0;
+              rr = fma(en, wm[c], -sv);
+              acc[c][2] = fma(rr, (dk - predn) * rs, acc[c][2]);
+            }
+            double nd[2][D];
+#pragma unroll
+            for (int tj = 0; tj < 2; tj++) {
+              const double* dr = drow + 2 + tj * TS;       // dPhi (D*D), dKg (D), dHA (D), dlog rs
+              if (FINAL) {
+                double t1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < D; q++) { t1 = fma(dr[D * D + D + q], mu[c][q], t1); t1 = fma(ha[q], dm[c][tj][q], t1); }
+                acc[c][tj] = fma(rr, fma(b, dr[D * D + 2 * D], -rs * t1), acc[c][tj]);
+              }
+#pragma unroll
+              for (int i = 0; i < D; i++) {
+                double x = dr[D * D + i] * v;
+#pragma unroll
+                for (int q = 0; q < D; q++) { x = fma(dr[i * D + q], mu[c][q], x); x = fma(F[i * D + q], dm[c][tj][q], x); }
+                nd[tj][i] = x;
+              }
+            }
+            double nn[D], nm[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+              double x = Kg[i] * dk, z = Kg[i] * v;
+#pragma unroll
+              for (int q = 0; q < D; q++) { x = fma(F[i * D + q], nu[c][q], x); z = fma(F[i * D + q], mu[c][q], z); }
+              nn[i] = x; nm[i] = z;
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) { mu[c][i] = nm[i]; nu[c][i] = nn[i]; dm[c][0][i] = nd[0][i]; dm[c][1][i] = nd[1][i]; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+#pragma unroll
+  for (int c = 0; c < CT; c++) {
+    const int m = (mt0 + c) * GPAR_TILE + mi;
+    if (FINAL) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) accpart[((int64_t)chunk * 3 + q) * Mpad + m] = acc[c][q];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        const int64_t o = ((int64_t)chunk * D + i) * Mpad + m;
+        tstate[o] = dm[c][0][i]; tstate[cstride + o] = dm[c][1][i]; tstate[2 * cstride + o] = nu[c][i];
+      }
+    }
+  }
+}
+
+// out[q] = sum over chunks and columns of accpart[chunk][q][m] (q < 3), out[3 + j] = sum_n e_n dalpha_j[n]; fixed order
+__global__ void __launch_bounds__(1024)
+grad_sums_kernel(const double* __restrict__ accpart, int nch, int Mpad, const double* __restrict__ evec, const double* __restrict__ dalpha,
+                 int64_t N, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int q = blockIdx.x;
+  double a = 0.0;
+  if (q < 3) {
+    for (int64_t i = threadIdx.x; i < (int64_t)nch * Mpad; i += blockDim.x) a += accpart[((i / Mpad) * 3 + q) * Mpad + (i % Mpad)];
+  } else {
+    const double* da = dalpha + (int64_t)(q - 3) * N;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) a = fma(evec[i], da[i], a);
+  }
+  const double r = block_sum(a, sh);
+  if (threadIdx.x == 0) out[q] = r;
+}
+
 template <int KIND, int D, int CT>
 int launch_pass1_dx(gpar_ctx* ctx, int DX, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
-                    const double* table, double* panel, double* resp, int Mpad) {
-#define CASE_DX(DD) case DD: LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad); break;
+                    const double* table, double* panel, double* resp, int Mpad, double* panelD) {
+#define CASE_DX(DD) case DD: \
+    if (panelD) LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, true>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD); \
+    else LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, false>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD); \
+    break;
   switch (DX) {
     CASE_DX(1) CASE_DX(2) CASE_DX(3) CASE_DX(4) CASE_DX(5) CASE_DX(6) CASE_DX(7) CASE_DX(8)
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "input dimension D=%d not supported (1..8)", DX);
@@ -347,77 +572,141 @@ int launch_pass1_dx(gpar_ctx* ctx, int DX, dim3 grid, const double* X, const dou
 }
 template <int D, int CT>
 int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
-                 const double* table, double* panel, double* resp, int Mpad) {
+                 const double* table, double* panel, double* resp, int Mpad, double* panelD) {
   switch (k_out) {
-    case GPAR_EQ: return launch_pass1_dx<GPAR_EQ, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
-    case GPAR_MATERN12: return launch_pass1_dx<GPAR_MATERN12, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
-    case GPAR_MATERN32: return launch_pass1_dx<GPAR_MATERN32, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
-    case GPAR_MATERN52: return launch_pass1_dx<GPAR_MATERN52, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad);
+    case GPAR_EQ: return launch_pass1_dx<GPAR_EQ, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
+    case GPAR_MATERN12: return launch_pass1_dx<GPAR_MATERN12, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
+    case GPAR_MATERN32: return launch_pass1_dx<GPAR_MATERN32, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
+    case GPAR_MATERN52: return launch_pass1_dx<GPAR_MATERN52, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
   }
 }
 
-struct ScaledStats { double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad; double *table, *alpha, *beta; int nch; };
+struct ScaledStats {
+  double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad;
+  double *table, *alpha, *beta; int nch;
+  // gradient mode only
+  double *dtable, *dalpha, *panelD, *start, *psi, *evec; double dsums[4];   // dsums: d sum log S (2), d sum alpha^2 (2)
+};
 
-// Steps 1-3 of the header comment.  Leaves G (M x M) and g (M) on the device.
+// Steps 1-3 of the header comment.  Leaves G (M x M) and g (M) on the device.  grad = true additionally
+// runs the filter in forward mode (tangents w.r.t. time_l and the noise of Sigma_y), keeps the
+// l dK/dl panel and the chunk-start states for the tangent pass.
 template <int D>
-int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st, bool keep_k) {
-  constexpr int TS = D * D + 2 * D + 1;
+int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st, bool grad) {
+  constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
   const int64_t N = ctx->N; const int M = (int)ctx->M;
   const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
-  const int64_t npad_to = keep_k ? 128 : GPAR_KT;        // the gradient's panel GEMM works on 128-step blocks
-  const int64_t Npad = (N + npad_to - 1) / npad_to * npad_to;
+  const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT;
   const int64_t NB4 = Npad / 4;
   const int nch = (int)((NB4 + WH_GROUPS - 1) / WH_GROUPS);
   const int T = Mpad / GPAR_TILE;
   CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
-  if (keep_k) CU(ctx->panelB.reserve((size_t)Npad * Mpad * sizeof(double)));
-  CU(ctx->kal_e.reserve(((size_t)N * TS + (size_t)N + 16) * sizeof(double)));                 // table, alpha, sums
-  CU(ctx->gpart.reserve(((size_t)nch * D * Mpad + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad) * sizeof(double)));
+  if (grad) CU(ctx->panelD.reserve((size_t)Npad * Mpad * sizeof(double)));
+  // table, alpha, sums (+ gradient: d alpha (2N), tangent table, e)
+  CU(ctx->kal_e.reserve(((size_t)N * TS + (size_t)N + 16 + (grad ? (size_t)N * (3 + DTS) : 0)) * sizeof(double)));
+  const size_t state_doubles = (size_t)nch * D * Mpad;
+  CU(ctx->gpart.reserve((state_doubles + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad
+                         + (grad ? 3 * state_doubles + (size_t)nch * 3 * Mpad : 0)) * sizeof(double)));
   const size_t MM = (size_t)M * M;
   CU(ctx->kal_d.reserve((MM + Mpad) * sizeof(double)));
-  double* table = ctx->kal_e.as<double>(); double* alpha = table + (size_t)N * TS; double* sums = alpha + N; double* lml = sums + 2;
-  double* resp = ctx->gpart.as<double>(); double* psi = resp + (size_t)nch * D * Mpad; double* gp = psi + (size_t)nch * D * D;
+  double* table = ctx->kal_e.as<double>(); double* alpha = table + (size_t)N * TS; double* sums = alpha + N; double* lml = sums + 8;
+  double* dalpha = lml + 8; double* dtable = dalpha + 2 * (size_t)N; double* evec = dtable + (size_t)N * DTS;
+  double* resp = ctx->gpart.as<double>(); double* psi = resp + state_doubles; double* gp = psi + (size_t)nch * D * D;
   double* G = ctx->kal_d.as<double>(); double* g = G + MM;
   const int kind_time = D == 1 ? GPAR_MATERN12 : (D == 2 ? GPAR_MATERN32 : GPAR_MATERN52);
-  CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, N, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
-                alpha, lml, nullptr, nullptr, table, sums));
+  if (grad) {
+    const int dirs[3] = {0, -1, 1};
+    CHK(lgssm_run_tangent(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, N, ctx->t.as<double>(), ctx->y.as<double>(), nullptr, dirs,
+                          alpha, nullptr, nullptr, sums, dalpha, table, dtable));
+  } else {
+    CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, N, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
+                  alpha, lml, nullptr, nullptr, table, sums));
+  }
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
   double* panel = ctx->panelK.as<double>();
-  double* beta = keep_k ? ctx->panelB.as<double>() : panel;     // in place unless K is needed again (gradient)
+  double* panelD = grad ? ctx->panelD.as<double>() : nullptr;
   // column tiles per thread: amortises the shared per-step table loads (registers limit it for large D)
   int CT = (T % 2 == 0) ? 2 : 1;   // measured best on B200 (CT = 1 / 2 / 4: 8.5 / 7.6 / 7.9 ms at N = 1M, M = 1024)
-  if (const char* e = getenv("GPAR_WH_CT")) { int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && T % v == 0) CT = v; }   // tuning knob
+  if (const char* e = getenv("GPAR_WH_CT")) { int v = atoi(e); if ((v == 1 || v == 2) && T % v == 0) CT = v; }   // tuning knob
   dim3 grid(T / CT, nch);
-  if (CT == 4) CHK((launch_pass1<D, 4>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
-  else if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
-  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad)));
+  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD)));
+  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD)));
   LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi);
   LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad);
-  if (CT == 4) LAUNCH(ctx, (whiten_pass2_kernel<D, 4>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
-  else if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
-  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, beta, resp, gp, Mpad);
+  if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
+  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
   cudaEventRecord(ctx->pev[0], ctx->stream);
-  CHK(panel_syrk_run(ctx, beta, nullptr, Npad, Mpad, M, false, G, nullptr));
+  CHK(panel_syrk_run(ctx, panel, nullptr, Npad, Mpad, M, false, G, nullptr));
   ctx->phase_valid = true;
-  double hs[2];
-  CU(cudaMemcpyAsync(hs, sums, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  double hs[6];
+  CU(cudaMemcpyAsync(hs, sums, (grad ? 6 : 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  st->G = G; st->g = g; st->sum_logS = hs[0]; st->sum_a2 = hs[1]; st->Mpad = Mpad; st->Npad = Npad;
-  st->table = table; st->alpha = alpha; st->beta = beta; st->nch = nch;
+  st->G = G; st->g = g; st->Mpad = Mpad; st->Npad = Npad;
+  st->table = table; st->alpha = alpha; st->beta = panel; st->nch = nch;
+  if (grad) {   // sums = [sum log S, its 2 tangents, sum alpha^2, its 2 tangents]
+    st->sum_logS = hs[0]; st->sum_a2 = hs[3]; st->dsums[0] = hs[1]; st->dsums[1] = hs[2]; st->dsums[2] = hs[4]; st->dsums[3] = hs[5];
+    st->dtable = dtable; st->dalpha = dalpha; st->panelD = panelD; st->start = resp; st->psi = psi; st->evec = evec;
+  } else { st->sum_logS = hs[0]; st->sum_a2 = hs[1]; }
   return GPAR_OK;
 }
 
 int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st,
-                 bool keep_k = false) {
+                 bool grad = false) {
   switch (k_time) {
-    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
-    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
-    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, keep_k);
+    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
+    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
+    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
   }
+}
+
+// The tangent pass of the gradient: <R, d beta_*> (3 sums) and <e, d alpha_j> (2 sums) -> out5 (host).
+template <int D>
+int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec, double* out5) {
+  const int64_t N = ctx->N; const int M = (int)ctx->M;
+  const int Mpad = st.Mpad, T = Mpad / GPAR_TILE, nch = st.nch;
+  const int64_t NB4 = st.Npad / 4;
+  const size_t state_doubles = (size_t)nch * D * Mpad;
+  double* tstate = st.psi + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad;       // after gp / g partials (layout of scaled_stats_d)
+  double* accpart = tstate + 3 * state_doubles;
+  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, st.beta, wvec, st.alpha, N, NB4, T, M, st.evec);
+  const int CT = (T % 2 == 0) ? 2 : 1;
+  dim3 grid(T / CT, nch);
+  if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
+                      tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
+  else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
+              tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
+  for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad);
+  // S' = P beta' slab by slab (library GEMM on the transposed slab), consumed at once by the final tangent pass
+  int slab_chunks = 128;                                                         // 131072 steps per slab
+  if (const char* e = getenv("GPAR_GRAD_SLAB")) { int v = atoi(e); if (v >= 1) slab_chunks = v; }
+  slab_chunks = std::min(slab_chunks, nch);
+  const size_t slab_steps = (size_t)slab_chunks * WH_GROUPS * 4;
+  CU(ctx->panelB.reserve(slab_steps * M * sizeof(double)));
+  CU(ctx->kal_f.reserve(slab_steps * M * sizeof(double)));
+  double* Bt = ctx->panelB.as<double>(); double* St = ctx->kal_f.as<double>();
+  cublasSetStream(ctx->blas, ctx->stream);
+  const double one = 1.0, zero = 0.0;
+  for (int c0 = 0; c0 < nch; c0 += slab_chunks) {
+    const int nc = std::min(slab_chunks, nch - c0);
+    const int64_t g_lo = (int64_t)c0 * WH_GROUPS, ng = std::min<int64_t>((int64_t)nc * WH_GROUPS, NB4 - g_lo);
+    const int64_t total = (int64_t)T * ng * GPAR_TILE;
+    LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, st.beta, NB4, g_lo, ng, T, M, Bt);
+    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, (int)(ng * 4), M, &one, Pm, M, Bt, M, &zero, St, M));
+    dim3 gs(T / CT, nc);
+    if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
+                        tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M);
+    else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
+                tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M);
+  }
+  CU(ctx->scal.reserve(8 * sizeof(double)));
+  LAUNCH(ctx, grad_sums_kernel, 5, 1024, 0, accpart, nch, Mpad, st.evec, st.dalpha, N, ctx->scal.as<double>());
+  CU(cudaMemcpyAsync(out5, ctx->scal.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
 }
 
 int check_scaled(gpar_ctx* ctx, const char* who) {
@@ -501,6 +790,55 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
   // dtc.jl:122-125 with logdet(noise_matrix) = sum log S_k
   *dtc = -0.5 * ((double)N * LOG2PI_S + st.sum_logS + hs[0] + st.sum_a2 - hs[1]);
+  return GPAR_OK;
+}
+
+// The scaled objective with its gradient with respect to the five raw parameters (NEW: the reference
+// optimises compute_gpar_dtc_objective with Nelder-Mead, dtc.jl:58-61).  Forward mode through the
+// filter for (time_l, noise of Sigma_y), reverse mode through the M x M tail (R = -beta P + e w'), the
+// out_l derivative from the whitened l dK/dl, and the scale identity
+//   time_s F_ts + out_s F_os + noise F_noise = -1/2 (N - (alpha'alpha - c'c))
+// (every covariance block is linear in (time_s, out_s, noise) jointly) for time_s.
+int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc, double* grad) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !dtc || !grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_grad: theta, dtc and grad must not be NULL");
+  CHK(check_scaled(ctx, "scaled_dtc_grad"));
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  double pv[5], ex[5];
+  for (int i = 0; i < 5; i++) { ex[i] = exp(theta[i]); pv[i] = ex[i] + 1e-3; }
+  const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
+  const int64_t N = ctx->N;
+  GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
+  // fork: cov(u) = Kuu + noise I, L_u, L_u^-1, cov(u)^-1 on the side stream, underneath the filter / whitening / SYRK
+  CHK(dtc_tail_prepare(ctx, k_out, p, 0, noise, true));
+  ScaledStats st;
+  CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, true));
+  double val = 0.0, g3[3], raw[8 + GPAR_NTR];
+  CHK(dtc_tail(ctx, k_out, p, 0, noise, N, st.G, nullptr, st.g, nullptr, st.sum_a2, &val, g3, raw));
+  TailBufs tb;
+  CHK(tail_layout(ctx, true, 0, &tb));
+  double s5[5];
+  switch (k_time) {
+    case GPAR_MATERN12: CHK(scaled_tangent_d<1>(ctx, st, tb.Pm, tb.wvec, s5)); break;
+    case GPAR_MATERN32: CHK(scaled_tangent_d<2>(ctx, st, tb.Pm, tb.wvec, s5)); break;
+    default: CHK(scaled_tangent_d<3>(ctx, st, tb.Pm, tb.wvec, s5)); break;
+  }
+  timer.stop();
+  *dtc = val - 0.5 * st.sum_logS;
+  const double* t = raw + 8;
+  const double cc = raw[2];
+  const double trTG = t[2] + t[3], trTKdK = t[4] + t[5] - t[6], trTKK = t[7] + t[8] - t[9], trTK = t[10] + t[12] - t[11], gw = t[16];
+  const double F_os = (-trTG + gw - 0.5 * (trTKK - noise * trTK)) / out_s;
+  const double F_logl = s5[2] - 0.5 * trTKdK;
+  const double F_tl = s5[0] - s5[3] - 0.5 * st.dsums[0];
+  const double F_noise = (s5[1] - s5[4] - 0.5 * st.dsums[1]) - 0.5 * trTK;
+  const double F_ts = (-0.5 * ((double)N - (st.sum_a2 - cc)) - out_s * F_os - noise * F_noise) / time_s;
+  grad[0] = F_tl * ex[0];
+  grad[1] = F_ts * 2.0 * pv[1] * ex[1];
+  grad[2] = F_logl / out_l * ex[2];
+  grad[3] = F_os * 2.0 * pv[3] * ex[3];
+  grad[4] = F_noise * 2.0 * pv[4] * ex[4];
   return GPAR_OK;
 }
 

@@ -86,6 +86,10 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
 int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc,
                     double* A_or_null);
 
+/* The same objective with its gradient d dtc / d theta[0..4] (NEW — the reference optimises it with
+ * Nelder-Mead, dtc.jl:58-61; a gradient lets Optim.LBFGS replace it). */
+int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc, double* grad);
+
 /* compute_q_u, src/gp/gpar_scaled_inference.jl:141-196: m_e (M), inv(D) (M x M), U_u (M x M upper).
  * params are the POSITIVE (already unpacked) values (time_l, time_var, out_l, out_var, noise_sigma),
  * as the reference passes kernels built from opt_params (gpar_scaled_inference.jl:57-73). */

@@ -75,6 +75,14 @@ function scaled_dtc(c::Ctx, k_time, k_out, theta::Vector{Float64}, N::Integer, M
     return val[], A
 end
 
+"compute_gpar_dtc_objective with d/d theta (5) — for Optim.LBFGS in place of NelderMead (dtc.jl:58-61)."
+function scaled_dtc_grad(c::Ctx, k_time, k_out, theta::Vector{Float64})
+    val = Ref{Float64}(0.0); grad = zeros(5)
+    check(c, ccall((:gpar_scaled_dtc_grad, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), theta, val, grad))
+    return val[], grad
+end
+
 "compute_q_u (src/gp/gpar_scaled_inference.jl:141-196): (m_e, inv(D), U_u); params are positive values."
 function compute_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, M::Integer)
     m_e = zeros(M); Dinv = zeros(M, M); U_u = zeros(M, M)

@@ -258,6 +258,53 @@ def test_scaled_dtc_vs_oracle(ctx, n, m, d, kt, ko):
     assert abs(v - v0) <= RTOL * abs(v0)
 
 
+@pytest.mark.parametrize("n,m,d,kt,ko", [(1, 1, 1, 3, 3), (40, 7, 1, 3, 3), (300, 20, 2, 3, 3), (1030, 129, 2, 3, 0), (1500, 40, 4, 2, 1), (900, 17, 7, 1, 2)])
+def test_scaled_dtc_grad_vs_autograd(ctx, n, m, d, kt, ko):
+    """gpar_scaled_dtc_grad against torch autograd of the oracle's scaled objective (sequential
+    differentiable filter).  Gradient tolerance 1e-6 relative to the largest component."""
+    from oracle.grad import scaled_dtc_value_and_grad
+    rng = np.random.default_rng(3 * n + m)
+    t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    th = rng.uniform(-1.0, 0.3, 5)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    v, g = ctx.scaled_dtc_grad(kt, ko, th)
+    assert v == pytest.approx(ctx.scaled_dtc(kt, ko, th), rel=1e-11)
+    v0, g0 = scaled_dtc_value_and_grad(th, X, Z, t, y, k_time=kt, k_out=ko)
+    assert abs(v - v0) <= RTOL * abs(v0)
+    assert np.all(np.abs(g - g0) <= 1e-6 * np.abs(g0) + 1e-7 * np.max(np.abs(g0))), (g, g0)
+
+
+def test_scaled_dtc_grad_multi_slab_and_full_size(ctx):
+    """(a) several GEMM slabs (GPAR_GRAD_SLAB=1: one 1024-step chunk per slab) give the same gradient
+    as one slab; (b) N = 1M, M = 1024: gradient against central differences of the device objective."""
+    rng = np.random.default_rng(77)
+    n, m, d = 5000, 64, 2
+    t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    th = rng.uniform(-1.0, 0.3, 5)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    v1, g1 = ctx.scaled_dtc_grad(3, 3, th)
+    os.environ["GPAR_GRAD_SLAB"] = "1"
+    try:
+        v2, g2 = ctx.scaled_dtc_grad(3, 3, th)
+    finally:
+        del os.environ["GPAR_GRAD_SLAB"]
+    assert v1 == v2 and relerr(g2, g1) <= 1e-12
+    N, M = 1_000_000, 1024
+    t = np.arange(N) / 30.0
+    x = rng.uniform(0, 100, N); z = np.linspace(0, 100, M)
+    y = np.sin(x) + 0.5 * np.sin(0.05 * t) + 0.1 * rng.normal(size=N)
+    th = np.log([2.0, 0.5, 1.0, 1.0, 0.1])
+    ctx.set_inputs(x); ctx.set_pseudo(z); ctx.set_times(t); ctx.set_outputs(y)
+    v, g = ctx.scaled_dtc_grad(3, 3, th)
+    h = 1e-4          # the value carries ~2e-11 relative rounding noise at |dtc| ~ 1e6: ~0.1 in the quotient
+    for i in range(5):
+        e = np.zeros(5); e[i] = h
+        fd = (ctx.scaled_dtc(3, 3, th + e) - ctx.scaled_dtc(3, 3, th - e)) / (2 * h)
+        assert abs(g[i] - fd) <= 1e-4 * abs(fd) + 0.3, (i, g[i], fd)
+    ms, launches = ctx.last_timing()
+    print("scaled objective + gradient N=1M M=1024: %.1f ms device" % ms)
+
+
 # ---- exact GP / GPAR -----------------------------------------------------------------------
 def test_exact_golden(ctx):
     z = np.load(os.path.join(G, "exact.npz"))

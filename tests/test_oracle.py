@@ -250,3 +250,20 @@ def test_lgssm_gradient_oracle_against_central_differences(kind):
     _, alpha = oracle.kalman_decorrelate(kind, t, y, l, var ** 2, sig ** 2)
     ds = g[1] / (2 * var * np.exp(th[1])); dn = g[2] / (2 * sig * np.exp(th[2]))
     assert abs(var ** 2 * ds + sig ** 2 * dn + 0.5 * (n - alpha @ alpha)) <= 1e-9 * n
+
+
+def test_scaled_gradient_oracle_against_central_differences():
+    """torch twin of the scaled objective == NumPy oracle value; autograd == central differences."""
+    from oracle.grad import scaled_dtc_value_and_grad
+    rng = np.random.default_rng(9)
+    n, m, d = 50, 6, 2
+    t = np.sort(rng.uniform(0, 3, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    th = rng.uniform(-1.0, 0.3, 5)
+    v, g = scaled_dtc_value_and_grad(th, X, Z, t, y, k_time=3, k_out=3)
+    f = lambda th_: scaled_gpar_objective(th_, X, Z, t, y, k_out=3, k_time=3)
+    assert abs(v - f(th)) <= 1e-10 * abs(v)
+    h = 1e-6
+    for i in range(5):
+        e = np.zeros(5); e[i] = h
+        fd = (f(th + e) - f(th - e)) / (2 * h)
+        assert abs(g[i] - fd) <= 1e-6 * max(1.0, abs(fd))
