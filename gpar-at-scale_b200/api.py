@@ -10,6 +10,7 @@ import numpy as np
 from . import _ffi
 from .context import Context
 from . import neldermead
+from . import lbfgs
 
 # ---- kernel structures (Stheno's EQ(), Matern12(), Matern32(), Matern52()) ---------------------
 
@@ -285,8 +286,9 @@ def smooth(lgssm, y, ctx=None):
 
 
 def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_structure=None, i_log_time_l=None, i_log_time_var=None,
-                        i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False):
-    """temporal_gp_inference.jl:45-114 -> (opt_lgssm, output_observations)."""
+                        i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False, optimizer="neldermead"):
+    """temporal_gp_inference.jl:45-114 -> (opt_lgssm, output_observations).  optimizer="lbfgs" replaces the
+    reference's Nelder-Mead (:82) by L-BFGS on the library's analytic gradient."""
     kernel_structure = kernel_structure or Matern52()
     ctx = ctx or default_context()
     data_locations = np.asarray(data_locations, dtype=np.float64); output_locations = np.asarray(output_locations, dtype=np.float64)
@@ -303,7 +305,13 @@ def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_s
         return -ctx.lgssm_logpdf(kernel_structure.code, params)[0]
 
     params = parse_initial_gp_params(i_log_time_l, i_log_time_var, i_log_noise_sigma, rng)
-    results = neldermead.optimize(nlml, params)                                                # :82
+    if optimizer == "lbfgs":
+        def nlml_fg(p_):
+            v, g = ctx.lgssm_logpdf_grad(kernel_structure.code, p_)
+            return -v[0], -g[0]
+        results = lbfgs.optimize(nlml_fg, params)
+    else:
+        results = neldermead.optimize(nlml, params)                                            # :82
     opt_l, opt_process_var, opt_noise_sigma = unpack_gp(results.minimizer)
     if debug:
         print("Finished optimizing parameters:\n\tOptimum L: %s \n\tOptimum Process Variance: %s\n\tOptimum noise: %s\n"
@@ -341,8 +349,9 @@ def compute_gpar_dtc_objective(f, u, time_loc, outputs, time_kernel=None, tempor
 def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_loc, outputs, out_kernel=None, time_kernel=None,
                                  i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                  optimization_time_limit=1000.0, show_optimization_trace=False, debug=False, ctx=None, rng=None,
-                                 iterations=1000, return_result=False):
-    """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma)."""
+                                 iterations=1000, return_result=False, optimizer="neldermead"):
+    """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma).  optimizer="lbfgs" replaces the
+    reference's Nelder-Mead (:58-61) by L-BFGS on gpar_scaled_dtc_grad."""
     out_kernel = out_kernel or Matern52(); time_kernel = time_kernel or Matern52()
     ctx = ctx or default_context()
     ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
@@ -354,7 +363,16 @@ def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_l
     params = parse_initial_gpar_params(i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma, rng)
     if debug:
         print("Generating scaled GPAR with initial parameters:\n\ti_time_l=%s; i_time_var=%s; i_out_l=%s; i_out_var=%s; i_noise_sigma=%s" % unpack_gpar(params))
-    results = neldermead.optimize(nlml, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
+    if optimizer == "lbfgs":
+        def nlml_fg(p_):
+            try:
+                v, g = ctx.scaled_dtc_grad(time_kernel.code, out_kernel.code, p_)
+            except _ffi.PosDefException:
+                return np.inf, np.zeros(5)
+            return -v, -g
+        results = lbfgs.optimize(nlml_fg, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
+    else:
+        results = neldermead.optimize(nlml, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
     opt_params = unpack_gpar(results.minimizer)
     if debug:
         print("Finished optimizing parameters:\n\tOptimum time L: %s \n\tOptimum time var: %s\n\tOptimum outputs l: %s\n"

@@ -10,7 +10,7 @@ Hyper-parameter restarts draw theta0 ~ U(0,1)^p like the reference's missing-par
 """
 import time
 import numpy as np
-from . import api, neldermead, parallel
+from . import api, lbfgs, neldermead, parallel
 from .context import Context
 
 
@@ -28,10 +28,13 @@ def make_tasks(n_outputs, n_restarts):
     return tasks, costs
 
 
-def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kernel=None, out_kernel=None, verbose=False):
+def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kernel=None, out_kernel=None, verbose=False,
+              optimizer="neldermead"):
     """Fits all outputs.  Y: (P, N) observed outputs on the sorted time grid t.  Tasks (output,
     restart) are partitioned over the ranks; every rank returns the gathered best parameters:
-    {output: (nlml, theta, restart)}, plus timing info."""
+    {output: (nlml, theta, restart)}, plus timing info.  optimizer: "neldermead" (the reference's,
+    dtc.jl:58-61) or "lbfgs" (uses the library's analytic gradients; `iterations` then bounds the
+    L-BFGS iterations)."""
     time_kernel = time_kernel or api.Matern52(); out_kernel = out_kernel or api.Matern52()
     rank, world = parallel.dist_info()
     ctx = ctx or api.default_context()
@@ -46,7 +49,13 @@ def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kern
             ctx.set_times(t); ctx.set_outputs(Y[0]); ctx.set_noise_vector(None)
             f = lambda th: -ctx.lgssm_logpdf(time_kernel.code, th)[0]                         # temporal_gp_inference.jl:69-79
             th0 = rng.random(3)
-            res = neldermead.optimize(f, th0, iterations=iterations)
+            if optimizer == "lbfgs":
+                def fg(th):
+                    v, g = ctx.lgssm_logpdf_grad(time_kernel.code, th)
+                    return -v[0], -g[0]
+                res = lbfgs.optimize(fg, th0, iterations=iterations)
+            else:
+                res = neldermead.optimize(f, th0, iterations=iterations)
             out = np.full(5, np.nan); out[:3] = res.minimizer
             evals[0] += res.f_calls
             return res.minimum, out
@@ -58,7 +67,16 @@ def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kern
                 return -ctx.scaled_dtc(time_kernel.code, out_kernel.code, th)
             except api._ffi.PosDefException:
                 return np.inf
-        res = neldermead.optimize(f, rng.random(5), iterations=iterations)
+        if optimizer == "lbfgs":
+            def fg(th):
+                try:
+                    v, g = ctx.scaled_dtc_grad(time_kernel.code, out_kernel.code, th)
+                except api._ffi.PosDefException:
+                    return np.inf, np.zeros(5)
+                return -v, -g
+            res = lbfgs.optimize(fg, rng.random(5), iterations=iterations)
+        else:
+            res = neldermead.optimize(f, rng.random(5), iterations=iterations)
         evals[0] += res.f_calls
         return res.minimum, res.minimizer
 

@@ -74,3 +74,24 @@ def test_chain_tasks_and_pseudo_inputs():
     assert chain.strided_pseudo_inputs(X, 50).shape == (10, 2)
     best = parallel.best_per_output([(0, 0), (0, 1), (1, 0)], np.array([3.0, 2.0, 5.0]), np.zeros((3, 5)))
     assert best[0][0] == 2.0 and best[0][2] == 1 and best[1][0] == 5.0
+
+
+def test_lbfgs_on_rosenbrock_and_failure_handling():
+    from gpar_at_scale_b200 import lbfgs
+
+    def fg(v):
+        f = (1 - v[0]) ** 2 + 100 * (v[1] - v[0] ** 2) ** 2
+        g = np.array([-2 * (1 - v[0]) - 400 * v[0] * (v[1] - v[0] ** 2), 200 * (v[1] - v[0] ** 2)])
+        return f, g
+    res = lbfgs.optimize(fg, np.array([-1.2, 1.0]), iterations=200, g_tol=1e-8, f_reltol=0.0)
+    assert res.minimum < 1e-12 and np.allclose(res.minimizer, [1, 1], atol=1e-5) and res.f_calls < 120
+    res = lbfgs.optimize(fg, np.array([-1.2, 1.0]), iterations=3)
+    assert res.iterations == 3 and not res.converged
+
+    # an objective that is +inf outside a box (a failed Cholesky reported as inf): the line search backs off
+    def fg_box(v):
+        if np.any(np.abs(v) > 2.0):
+            return np.inf, np.zeros(2)
+        return float(np.sum((v - 1.9) ** 2)), 2 * (v - 1.9)
+    res = lbfgs.optimize(fg_box, np.array([-1.5, 0.0]), iterations=50)
+    assert np.allclose(res.minimizer, [1.9, 1.9], atol=1e-4)
