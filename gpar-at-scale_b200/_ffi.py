@@ -28,6 +28,7 @@ SIGNATURES = {
     "gpar_set_inputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_pseudo": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_times": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),
+    "gpar_set_times_range": (ctypes.c_int, [_c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int64]),
     "gpar_set_outputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32]),
     "gpar_set_noise_vector": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),
     "gpar_dtc_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double,
@@ -67,7 +68,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("GPAR_B200_LIB") or LIB_PATH     # GPAR_B200_LIB: tuning builds of the same library
     if not os.path.exists(p):
         raise OSError("libgpar_b200.so not found at %s — build it with `make` or __graft_entry__.build()" % p)
     lib = ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)

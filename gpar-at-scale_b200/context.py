@@ -76,6 +76,11 @@ class Context:
         self._check(self._lib.gpar_set_times(self._h, dptr(t), t.shape[0]))
         self.Nt = t.shape[0]
 
+    def set_times_range(self, t0, dt, n):
+        """The regular grid t0 + k dt (Julia: an AbstractRange) — constant transition matrix per sequence."""
+        self._check(self._lib.gpar_set_times_range(self._h, float(t0), float(dt), int(n)))
+        self.Nt = int(n)
+
     def set_outputs(self, y):
         """y: (N,) or (batch, N) — sequence b contiguous."""
         y = as_f64(y)

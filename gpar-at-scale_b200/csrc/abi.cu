@@ -128,7 +128,21 @@ int gpar_set_times(gpar_ctx* ctx, const double* t, int64_t N) {
   if (!ctx) return GPAR_ERR_INVALID;
   if (!t || N < 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_times: need t != NULL, N >= 0");
   CHK(upload(ctx, ctx->t, t, (size_t)N));
-  ctx->Nt = N;
+  ctx->Nt = N; ctx->t_reg_dt = 0.0;
+  return GPAR_OK;
+}
+__global__ void fill_range_kernel(double* t, double t0, double dt, int64_t N) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < N) t[k] = fma((double)k, dt, t0);
+}
+int gpar_set_times_range(gpar_ctx* ctx, double t0, double dt, int64_t N) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (N < 0 || !(dt > 0.0)) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_times_range: need N >= 0 and dt > 0");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->t.reserve((size_t)std::max<int64_t>(N, 1) * sizeof(double)));
+  if (N > 0) LAUNCH(ctx, fill_range_kernel, (int)((N + 255) / 256), 256, 0, ctx->t.as<double>(), t0, dt, N);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->Nt = N; ctx->t_reg_dt = dt;
   return GPAR_OK;
 }
 int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch) {

@@ -120,7 +120,18 @@ __global__ void scan_down_kernel(Level cur, Level up, int batch) {
 }
 
 // dir_*: tangent slot of each parameter in the Dual instantiations (-1: not differentiated)
-struct SeqParams { const double *l, *s, *noise; int nparam; int dir_l, dir_s, dir_n; };
+// reg_dt > 0: regular time grid with that spacing (gpar_set_times_range) — the transition matrix is
+// then constant per sequence (what TemporalGPs does for a `range` input) and is hoisted out of the loops.
+struct SeqParams { const double *l, *s, *noise; int nparam; int dir_l, dir_s, dir_n; double reg_dt; };
+
+// inputs of one step (time, observation, per-step noise), loaded ahead of use
+struct StepIn {
+  double t = 0.0, y = 0.0, r = 0.0;
+  __device__ __forceinline__ void load(const double* __restrict__ tp, const double* __restrict__ yp, const double* __restrict__ rp,
+                                       int64_t k, int64_t N, bool reg) {
+    if (k < N) { y = __ldg(yp + k); if (!reg) t = __ldg(tp + k); if (rp) r = __ldg(rp + k); }
+  }
+};
 
 // P1: chunk filtering element.
 template <int D, class F>
@@ -148,23 +159,30 @@ kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__
   const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
   const double* yb = y + (int64_t)b * N;
+  const bool reg = sp.reg_dt > 0.0;
+  F A[D * D];
+  if (reg) lgssm_transition<D>(sp.reg_dt * il, A);
+  // each thread walks its own chunk, so its loads are strided across the warp: they are issued two steps
+  // ahead of their use (ncu: long_scoreboard was the top stall of these kernels)
+  StepIn in0, in1;
+  in0.load(t, yb, rvec, k0, N, reg); in1.load(t, yb, rvec, k0 + 1, N, reg);
   for (int64_t k = k0; k < k1; k++) {
-    const double tk = __ldg(t + k);
-    F A[D * D], Q[NSYM<D>], T[D * D], u[D], Cn[NSYM<D>];
-    lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
-    lgssm_q<D>(A, P0, Q);
+    F T[D * D], u[D], Cn[NSYM<D>];
+    const StepIn cur = in0; in0 = in1; in1.load(t, yb, rvec, k + 2, N, reg);
+    if (!reg) { lgssm_transition<D>((cur.t - tprev) * il, A); tprev = cur.t; }
+    else if (k <= 1) lgssm_transition<D>((k == 0 ? 1.0 : sp.reg_dt) * il, A);     // step 0 follows the t[0] - 1 prefix
     matmul<D>(A, Phi, T);
 #pragma unroll
     for (int i = 0; i < D * D; i++) Phi[i] = T[i];
     matvec<D>(A, bv, u);
 #pragma unroll
     for (int i = 0; i < D; i++) bv[i] = u[i];
-    asat<D>(A, C, Cn);
+    predict_cov<D>(A, C, P0, Cn);
 #pragma unroll
-    for (int i = 0; i < NSYM<D>; i++) C[i] = Cn[i] + Q[i];
-    const F S = rvec ? C[0] + __ldg(rvec + k) : C[0] + noise;
+    for (int i = 0; i < NSYM<D>; i++) C[i] = Cn[i];
+    const F S = rvec ? C[0] + cur.r : C[0] + noise;
     const F iS = 1.0 / S;
-    const F r = __ldg(yb + k) - bv[0];
+    const F r = cur.y - bv[0];
     F h[D], Kg[D];
 #pragma unroll
     for (int i = 0; i < D; i++) { h[i] = Phi[i]; Kg[i] = SYM(C, i, 0) * iS; }
@@ -227,16 +245,19 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
   const double* yb = y + (int64_t)b * N;
   F sum_logS = 0.0, sum_a2 = 0.0, prodS = 1.0;
   const int64_t kend = SMOOTH ? k1 + 1 : k1;    // one extra predict closes the chunk's last smoothing element
+  const bool reg = sp.reg_dt > 0.0;
+  F A[D * D];
+  if (reg) lgssm_transition<D>(sp.reg_dt * il, A);
+  StepIn in0, in1;
+  in0.load(t, yb, rvec, k0, N, reg); in1.load(t, yb, rvec, k0 + 1, N, reg);
   for (int64_t k = k0; k < kend; k++) {
-    F A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>];
+    F mp[D], Pp[NSYM<D>];
+    const StepIn cur = in0; in0 = in1; in1.load(t, yb, rvec, k + 2, N, reg);
     if (k < N) {
-      const double tk = __ldg(t + k);
-      lgssm_transition<D>((tk - tprev) * il, A); tprev = tk;
-      lgssm_q<D>(A, P0, Q);
+      if (!reg) { lgssm_transition<D>((cur.t - tprev) * il, A); tprev = cur.t; }
+      else if (k <= 1) lgssm_transition<D>((k == 0 ? 1.0 : sp.reg_dt) * il, A);   // step 0 follows the t[0] - 1 prefix
       matvec<D>(A, m, mp);
-      asat<D>(A, P, Pp);
-#pragma unroll
-      for (int i = 0; i < NSYM<D>; i++) Pp[i] += Q[i];
+      predict_cov<D>(A, P, P0, Pp);
     }
     if constexpr (SMOOTH) {
       if (k > k0) {
@@ -272,9 +293,9 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
       }
     }
     if (k >= k1) break;
-    const F S = rvec ? Pp[0] + __ldg(rvec + k) : Pp[0] + noise;
+    const F S = rvec ? Pp[0] + cur.r : Pp[0] + noise;
     const F rs = rsqrt(S);          // one reciprocal square root instead of sqrt + D+1 divisions
-    const F a = (__ldg(yb + k) - mp[0]) * rs;
+    const F a = (cur.y - mp[0]) * rs;
     F Bv[D];
 #pragma unroll
     for (int i = 0; i < D; i++) { Bv[i] = SYM(Pp, 0, i) * rs; m[i] = fma(Bv[i], a, mp[i]); }
@@ -384,17 +405,14 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
     for (int i = 0; i < NSYM<D>; i++) Ps[i] = suf.v[SmoothElem<D>::OL + i];
   }
   for (; k >= k0; k--) {
-    double m[D], P[NSYM<D>], A[D * D], Q[NSYM<D>], mp[D], Pp[NSYM<D>], W[D * D], G[D * D];
+    double m[D], P[NSYM<D>], A[D * D], mp[D], Pp[NSYM<D>], W[D * D], G[D * D];
 #pragma unroll
     for (int i = 0; i < D; i++) m[i] = fsb[((int64_t)i * L + (k - k0)) * 32];
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) P[i] = fsb[((int64_t)(D + i) * L + (k - k0)) * 32];
-    lgssm_transition<D>((__ldg(t + k + 1) - __ldg(t + k)) * il, A);
-    lgssm_q<D>(A, P0, Q);
+    lgssm_transition<D>((sp.reg_dt > 0.0 ? sp.reg_dt : __ldg(t + k + 1) - __ldg(t + k)) * il, A);
     matvec<D>(A, m, mp);
-    asat<D>(A, P, Pp);
-#pragma unroll
-    for (int i = 0; i < NSYM<D>; i++) Pp[i] += Q[i];
+    predict_cov<D>(A, P, P0, Pp);
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
@@ -572,7 +590,7 @@ int upload_params(gpar_ctx* ctx, const double* hl, const double* hs, const doubl
   CU(cudaMemcpyAsync(dp, hl, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(dp + nparam, hs, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(dp + 2 * nparam, hn, nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  *sp = SeqParams{dp, dp + nparam, dp + 2 * nparam, nparam, -1, -1, -1};
+  *sp = SeqParams{dp, dp + nparam, dp + 2 * nparam, nparam, -1, -1, -1, 0.0};
   return GPAR_OK;
 }
 
@@ -587,6 +605,7 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
   if (d_table && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
   SeqParams sp;
   CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
+  if (t == ctx->t.as<double>()) sp.reg_dt = ctx->t_reg_dt;
   LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums;
   switch (kind) {
     case GPAR_MATERN12: return lgssm_run_d<1, double>(ctx, sp, batch, N, t, y, rvec, o);
@@ -608,6 +627,7 @@ int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* h
   SeqParams sp;
   CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
   sp.dir_l = dirs[0]; sp.dir_s = dirs[1]; sp.dir_n = dirs[2];
+  if (t == ctx->t.as<double>()) sp.reg_dt = ctx->t_reg_dt;
   LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.dlml = d_dlml; o.sums = d_sums; o.dalpha = d_dalpha; o.table = d_table; o.dtable = d_dtable;
   switch (kind) {
     case GPAR_MATERN12: return lgssm_run_d<1, Dual<2>>(ctx, sp, batch, N, t, y, rvec, o);

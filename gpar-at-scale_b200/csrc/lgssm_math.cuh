@@ -87,6 +87,17 @@ template <int D, class F> __device__ __forceinline__ void lgssm_q(const F* A, co
   for (int i = 0; i < NSYM<D>; i++) Q[i] = P0[i] - R[i];
 }
 
+// Predicted covariance with the process noise folded in:
+//   A P A^T + Q,  Q = P0 - A P0 A^T   ==   P0 + A (P - P0) A^T      (one congruence instead of two)
+template <int D, class F> __device__ __forceinline__ void predict_cov(const F* A, const F* P, const F* P0, F* Pp) {
+  F Dl[NSYM<D>];
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) Dl[i] = P[i] - P0[i];
+  asat<D>(A, Dl, Pp);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) Pp[i] = Pp[i] + P0[i];
+}
+
 template <int D, class F> __device__ __forceinline__ void matvec(const F* A, const F* x, F* y) {
 #pragma unroll
   for (int i = 0; i < D; i++) { F v = 0.0;

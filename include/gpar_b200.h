@@ -63,6 +63,10 @@ int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N);
 int gpar_set_pseudo(gpar_ctx* ctx, const double* Z, int32_t D, int64_t M);
 /* time locations, ascending (callers sort: temporal_gp_inference.jl:61-66) */
 int gpar_set_times(gpar_ctx* ctx, const double* t, int64_t N);
+/* The regular grid t_k = t0 + k dt, k = 0..N-1 — the Julia shim calls this for an AbstractRange
+ * (range(0, step = 1/30, length = N), toy_data.jl:6).  TemporalGPs gives a range constant A, Q
+ * (RegularSpacing); so does the library: the transition matrix is built once per sequence, not per step. */
+int gpar_set_times_range(gpar_ctx* ctx, double t0, double dt, int64_t N);
 /* outputs: `batch` sequences of N values, sequence b at y + b*N */
 int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch);
 /* per-step observation noise R_k (the 1e10 trick, temporal_gp_inference.jl:93-97); NULL clears it */

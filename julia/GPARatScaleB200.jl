@@ -50,6 +50,9 @@ set_pseudo!(c::Ctx, Z::Matrix{Float64}) =
     check(c, ccall((:gpar_set_pseudo, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int64), c.h, Z, size(Z, 1), size(Z, 2)))
 set_times!(c::Ctx, t::Vector{Float64}) =
     check(c, ccall((:gpar_set_times, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), c.h, t, length(t)))
+# a range keeps TemporalGPs' RegularSpacing behaviour: constant transition matrix (toy_data.jl:6)
+set_times!(c::Ctx, t::AbstractRange) =
+    check(c, ccall((:gpar_set_times_range, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Int64), c.h, first(t), step(t), length(t)))
 set_outputs!(c::Ctx, y::VecOrMat{Float64}) =      # N or N x batch (column-major: sequence b contiguous)
     check(c, ccall((:gpar_set_outputs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32), c.h, y, size(y, 1), size(y, 2)))
 set_noise_vector!(c::Ctx, r::Union{Nothing, Vector{Float64}}) = r === nothing ?

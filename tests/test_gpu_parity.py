@@ -187,6 +187,29 @@ def test_lgssm_logpdf_grad_full_size(ctx):
         assert abs(grad[0, i] - fd) <= 1e-5 * abs(fd) + 1e-2
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_lgssm_regular_grid_range(ctx, kind):
+    """gpar_set_times_range (Julia AbstractRange -> TemporalGPs RegularSpacing: constant A, Q) gives the
+    vector-of-times results on the same grid: logpdf, alpha, smoother, gradient."""
+    rng = np.random.default_rng(60 + kind)
+    n, batch, dt = 5000, 3, 1 / 30
+    t = 0.25 + dt * np.arange(n)
+    Y = rng.normal(size=(batch, n)); ths = rng.uniform(-1.5, 0.5, (batch, 3))
+    ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    ctx.set_times(t)
+    a = (ctx.lgssm_logpdf(kind, ths), ctx.lgssm_decorrelate(kind, ths[0]), ctx.lgssm_smooth(kind, ths[0]), ctx.lgssm_logpdf_grad(kind, ths))
+    ctx.set_times_range(0.25, dt, n)
+    b = (ctx.lgssm_logpdf(kind, ths), ctx.lgssm_decorrelate(kind, ths[0]), ctx.lgssm_smooth(kind, ths[0]), ctx.lgssm_logpdf_grad(kind, ths))
+    assert relerr(b[0], a[0]) <= 1e-10
+    assert np.max(np.abs(b[1][1] - a[1][1])) <= 1e-9 * max(1.0, np.max(np.abs(a[1][1])))
+    assert np.max(np.abs(b[2][1] - a[2][1])) <= 1e-9 and relerr(b[2][2], a[2][2]) <= 1e-9
+    assert relerr(b[3][1], a[3][1]) <= 1e-8
+    pp = np.exp(ths) + 1e-3
+    lml0 = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2)
+    assert relerr(b[0], lml0) <= RTOL
+    ctx.set_times(t)
+
+
 def test_lgssm_full_size_config3(ctx):
     """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
     and one 10M-step sequence; every lml against the C oracle."""
