@@ -52,6 +52,7 @@ struct gpar_ctx {
   int32_t D = 0, Dz = 0, ybatch = 0;
   int64_t N = 0, M = 0, Nt = 0, Ny = 0, Nr = 0;
   bool has_rvec = false;
+  int ss_skip = 0;                    // calls for which the steady-state Kalman path stays off after a non-converged hand-over
   double t_reg_dt = 0.0;              // > 0: the resident times are the regular grid t0 + k dt (gpar_set_times_range)
 
   // scratch (grown on demand)

@@ -307,3 +307,28 @@ template <int D, class F = double> struct SmoothElem {
   // the smoother scans over REVERSED time: `first` is later in time
   __device__ __forceinline__ static SmoothElem scan_combine(const SmoothElem& first, const SmoothElem& second) { return combine(second, first); }
 };
+
+// ---- affine map x -> M x + r (steady-state mean recursion over a chunk); scan order == time order ----
+template <int D, class F = double> struct AffineElem {
+  static constexpr int NF = D * D + D;
+  static constexpr int OR = D * D;
+  typedef F scalar_t;
+  static constexpr int NFD = NF * Scalar<F>::NC;
+  F v[NF];
+  __device__ __forceinline__ void set_identity() {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) v[i] = (i / D == i % D) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) v[OR + i] = 0.0;
+  }
+  // first (earlier) then second (later): (M2 M1, M2 r1 + r2)
+  __device__ __forceinline__ static AffineElem scan_combine(const AffineElem& e1, const AffineElem& e2) {
+    AffineElem r;
+    F u[D];
+    matmul<D>(e2.v, e1.v, r.v);
+    matvec<D>(e2.v, e1.v + OR, u);
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[OR + i] = u[i] + e2.v[OR + i];
+    return r;
+  }
+};

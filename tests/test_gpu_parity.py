@@ -210,6 +210,42 @@ def test_lgssm_regular_grid_range(ctx, kind):
     ctx.set_times(t)
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_lgssm_steady_state_path(ctx, kind):
+    """Regular grid + scalar noise + N >= 8192: transient by the general scan, then the steady-state
+    affine recursion.  Against the sequential C oracle: lml 1e-8 relative, alpha 1e-8; a batch containing
+    a model that has NOT converged at the hand-over (l = e^6) falls back to the general path and is
+    still right; GPAR_KF_STEADY=0 (general path) agrees to 1e-11."""
+    rng = np.random.default_rng(80 + kind)
+    n, batch, dt = 20011, 5, 1 / 30
+    t = dt * np.arange(n)
+    Y = rng.normal(size=(batch, n))
+    ths = np.stack([np.log(rng.uniform(0.05, 5, batch)), np.log(rng.uniform(0.3, 3, batch)), np.log(rng.uniform(0.01, 1, batch))], axis=1)
+    pp = np.exp(ths) + 1e-3
+    ctx.set_times_range(0.0, dt, n); ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    lml = ctx.lgssm_logpdf(kind, ths)
+    lml0 = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2)
+    assert relerr(lml, lml0) <= RTOL
+    lml_s, alpha = ctx.lgssm_decorrelate(kind, ths[1])
+    l0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[1, 0], pp[1, 1] ** 2, pp[1, 2] ** 2, want_alpha=True)
+    assert relerr(lml_s, l0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
+    os.environ["GPAR_KF_STEADY"] = "0"
+    try:
+        lml_g = ctx.lgssm_logpdf(kind, ths)
+        _, alpha_g = ctx.lgssm_decorrelate(kind, ths[1])
+    finally:
+        del os.environ["GPAR_KF_STEADY"]
+    assert relerr(lml, lml_g) <= 1e-11 and np.max(np.abs(alpha - alpha_g)) <= 1e-10
+    slow = ths.copy(); slow[2, 0] = 6.0                      # l = e^6: far from converged after 2048 steps
+    pps = np.exp(slow) + 1e-3
+    lml = ctx.lgssm_logpdf(kind, slow)
+    lml0 = cport.kalman_filter_batch(kind, t, Y, pps[:, 0], pps[:, 1] ** 2, pps[:, 2] ** 2)
+    assert relerr(lml, lml0) <= RTOL
+    for _ in range(9):                                       # the fallback switches the fast path off for 8 calls
+        ctx.lgssm_logpdf(kind, ths)
+    ctx.set_times(t)
+
+
 def test_lgssm_full_size_config3(ctx):
     """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
     and one 10M-step sequence; every lml against the C oracle."""
@@ -230,6 +266,11 @@ def test_lgssm_full_size_config3(ctx):
     l0, a0 = cport.kalman_decorrelate(3, t, y, *(lambda p: (p[0], p[1] ** 2, p[2] ** 2))(oracle.unpack_gp(th)))
     assert abs(lml[0] - l0) <= RTOL * abs(l0)
     assert np.max(np.abs(alpha[0] - a0)) <= 1e-8 * np.max(np.abs(a0))
+    ctx.set_times_range(0.0, 1 / 30.0, N)                    # the same grid as a range: steady-state path
+    lml, alpha = ctx.lgssm_decorrelate(3, th)
+    assert abs(lml[0] - l0) <= RTOL * abs(l0)
+    assert np.max(np.abs(alpha[0] - a0)) <= 1e-8 * np.max(np.abs(a0))
+    ctx.set_times(t[:10])
 
 
 def test_sde_prediction_protocol_against_dense_gp(ctx):
