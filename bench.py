@@ -200,6 +200,29 @@ def run_ours(args):
         extra["kalman_filter_steps_per_s"] = B * NK / kal_ms * 1e3
         extra["kalman_filter_ms_1024x10k"] = kal_ms
         extra["kalman_smoother_steps_per_s"] = B * NK / float(np.median(ts[1:])) * 1e3
+
+        def med_ms(fn, n=6, skip=2):
+            out = []
+            for _ in range(n):
+                fn(); out.append(ctx.last_timing()[0])
+            return float(np.median(out[skip:]))
+        extra["kalman_logpdf_grad_ms_1024x10k"] = med_ms(lambda: ctx.lgssm_logpdf_grad(gp.MATERN52, ths), 4, 1)
+        # the same batch on the regular grid range(0, step = 1/30) (toy_data.jl:6): steady-state path
+        ctx.set_times_range(0.0, 1 / 30, NK)
+        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths))
+        extra["kalman_filter_regular_grid_steps_per_s"] = B * NK / ms * 1e3
+        # one 10M-step Matern-5/2 sequence (north-star shape): irregular grid, then the regular grid
+        N10 = 10_000_000
+        y10 = rng.normal(size=N10); th3 = np.log(np.array([1.0, 1.0, 0.1]))
+        ctx.set_outputs(y10); ctx.set_times(np.cumsum(rng.exponential(1 / 30, N10)))
+        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
+        extra["kalman_filter_1x10M_steps_per_s"] = N10 / ms * 1e3
+        extra["kalman_filter_1x10M_ms"] = ms
+        ctx.set_times_range(0.0, 1 / 30, N10)
+        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
+        extra["kalman_filter_1x10M_regular_grid_steps_per_s"] = N10 / ms * 1e3
+        extra["kalman_filter_1x10M_regular_grid_ms"] = ms
+        del y10
         tfull = np.arange(N_FULL) / 30.0
         ctx.set_inputs(xp); ctx.set_outputs(yp); ctx.set_times(tfull)
         th5 = np.log(np.array([1.0, 1.0, 1.0, 1.0, 0.1]))
@@ -207,6 +230,10 @@ def run_ours(args):
         for i in range(5):
             ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5); ts.append(ctx.last_timing()[0])
         extra["scaled_gpar_objective_ms_N1M_M1024"] = float(np.median(ts[2:]))
+        ts = []
+        for i in range(4):
+            ctx.scaled_dtc_grad(gp.MATERN52, gp.MATERN52, th5); ts.append(ctx.last_timing()[0])
+        extra["scaled_gpar_objective_and_grad_ms_N1M_M1024"] = float(np.median(ts[1:]))
 
     if rank == 0:
         flops = N_FULL * M_FULL * (M_FULL + 1) + 2.0 * N_FULL * M_FULL * M_FULL     # G (symmetric) + H (forward-mode dG/dl)
