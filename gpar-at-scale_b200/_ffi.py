@@ -37,6 +37,8 @@ SIGNATURES = {
     "gpar_scaled_dtc_grad": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_compute_q_u": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p,
                                         _c_double_p, _c_double_p]),
+    "gpar_sample_q_u": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_uint64, ctypes.c_int32,
+                                       _c_double_p, _c_double_p]),
     "gpar_scaled_predict": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int32,
                                            _c_double_p, _c_double_p]),
     "gpar_lgssm_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),

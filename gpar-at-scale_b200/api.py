@@ -397,7 +397,7 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 inference_input_locations, out_kernel_structure=None, time_kernel_structure=None,
                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                 optimization_time_limit=1000.0, debug=False, ctx=None, rng=None, iterations=1000, nsamples=100,
-                                opt_params=None):
+                                opt_params=None, sampler="host", seed=0):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
@@ -407,6 +407,8 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     X = to_ColVecs(input_locations); Z = to_ColVecs(pseudo_input_locations); Xs = to_ColVecs(inference_input_locations)
     time_loc = np.asarray(time_loc, dtype=np.float64); inference_time_loc = np.asarray(inference_time_loc, dtype=np.float64)
     outputs = np.asarray(outputs, dtype=np.float64)
+    # sampler="device": the q_u draws come from the library's seeded Philox stream (gpar_sample_q_u) and never
+    # leave the GPU; "host" draws them here from `rng` (the reference uses Julia's global RNG, :94)
     if opt_params is None:
         print("Starting optimization")                                                        # :42 (unconditional in the reference)
         opt_params = get_optim_scaled_gpar_params(X, Z, time_loc, outputs, out_kernel=Matern52(), time_kernel=Matern52(),   # :43-56 hard-codes Matern52
@@ -418,7 +420,10 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     params = np.array([opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma])
     # q(u) ~ p(u | y)  (:63-73)
     ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(time_loc); ctx.set_outputs(outputs); ctx.set_noise_vector(None)
-    m_e, Dinv, U_u = ctx.compute_q_u(time_kernel_structure.code, out_kernel_structure.code, params)
+    if sampler == "device":
+        ctx.sample_q_u(time_kernel_structure.code, out_kernel_structure.code, params, seed, nsamples)
+    else:
+        m_e, Dinv, U_u = ctx.compute_q_u(time_kernel_structure.code, out_kernel_structure.code, params)
     # merge + sort (:75-87)
     ntr = len(time_loc)
     time_loc_concat = np.concatenate([time_loc, inference_time_loc])
@@ -426,11 +431,13 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     input_loc_star = np.concatenate([X, Xs], axis=0)[sorting_perm]
     outputs_star = np.concatenate([outputs, np.zeros(len(inference_time_loc))])[sorting_perm]
     noise_vector_star = np.concatenate([np.full(ntr, opt_noise_sigma ** 2), np.full(len(inference_time_loc), 1e10)])[sorting_perm]   # :100-103
-    # draws eps_j ~ MvNormal(m_e, inv(D)) (:94) and the weights U_u \ eps_j (:96) — tiny M x S host work
-    Lc = np.linalg.cholesky(0.5 * (Dinv + Dinv.T))
-    eps = m_e[:, None] + Lc @ rng.standard_normal((len(m_e), nsamples))
-    from scipy.linalg import solve_triangular
-    W = solve_triangular(np.triu(U_u), eps, lower=False)
+    W = None
+    if sampler != "device":
+        # draws eps_j ~ MvNormal(m_e, inv(D)) (:94) and the weights U_u \ eps_j (:96) — tiny M x S host work
+        Lc = np.linalg.cholesky(0.5 * (Dinv + Dinv.T))
+        eps = m_e[:, None] + Lc @ rng.standard_normal((len(m_e), nsamples))
+        from scipy.linalg import solve_triangular
+        W = solve_triangular(np.triu(U_u), eps, lower=False)
     ctx.set_inputs(input_loc_star); ctx.set_times(time_loc_concat[sorting_perm]); ctx.set_outputs(outputs_star)
     ctx.set_noise_vector(noise_vector_star)
     mean, std = ctx.scaled_predict(time_kernel_structure.code, out_kernel_structure.code, params, W)      # :110-130 batched

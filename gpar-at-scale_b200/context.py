@@ -128,11 +128,25 @@ class Context:
         self._check(self._lib.gpar_compute_q_u(self._h, int(k_time), int(k_out), dptr(p), dptr(m_e), dptr(Dinv), dptr(U_u)))
         return m_e, Dinv, U_u
 
-    def scaled_predict(self, k_time, k_out, params, W):
-        """W: (M, S) — column j = U_u \\ eps_j.  -> (mean, std) over the merged, sorted locations."""
+    def sample_q_u(self, k_time, k_out, params, seed, nsamples, return_host=False):
+        """Seeded device draws from q_u; the weights W = U_u \\ eps stay resident for scaled_predict(W=None).
+        return_host -> (W, eps), each (M, S)."""
         p = as_f64(np.asarray(params).ravel())
-        W = np.asfortranarray(W, dtype=np.float64)
+        W = np.zeros((self.M, nsamples), order="F") if return_host else None
+        E = np.zeros((self.M, nsamples), order="F") if return_host else None
+        self._check(self._lib.gpar_sample_q_u(self._h, int(k_time), int(k_out), dptr(p), int(seed), int(nsamples), dptr(W), dptr(E)))
+        self._nsamples_resident = int(nsamples)
+        return (W, E) if return_host else None
+
+    def scaled_predict(self, k_time, k_out, params, W=None):
+        """W: (M, S) — column j = U_u \\ eps_j; None: the resident weights of the last sample_q_u.
+        -> (mean, std) over the merged, sorted locations."""
+        p = as_f64(np.asarray(params).ravel())
         mean = np.zeros(self.N); sd = np.zeros(self.N)
+        if W is None:
+            self._check(self._lib.gpar_scaled_predict(self._h, int(k_time), int(k_out), dptr(p), None, self._nsamples_resident, dptr(mean), dptr(sd)))
+            return mean, sd
+        W = np.asfortranarray(W, dtype=np.float64)
         self._check(self._lib.gpar_scaled_predict(self._h, int(k_time), int(k_out), dptr(p), W.ctypes.data_as(_ffi._c_double_p),
                                                   W.shape[1], dptr(mean), dptr(sd)))
         return mean, sd

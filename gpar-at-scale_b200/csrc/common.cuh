@@ -58,6 +58,7 @@ struct gpar_ctx {
   // scratch (grown on demand)
   DevBuf panelK, panelD, panelB, kal_f, partial, segs, jobs, gpart, scal, dense, tailws, info;
   DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
+  DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   void* pinned = nullptr; size_t pinned_cap = 0;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;

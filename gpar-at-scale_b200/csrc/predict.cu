@@ -71,7 +71,9 @@ __global__ void mc_reduce_kernel(const double* __restrict__ fx, const double* __
 extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W, int32_t S,
                                    double* mean, double* sd) {
   if (!ctx) return GPAR_ERR_INVALID;
-  if (!params || !W || !mean || !sd || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: NULL argument or S < 1");
+  if (!params || !mean || !sd || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: NULL argument or S < 1");
+  if (!W && (ctx->qW_S != S || ctx->qW_M != ctx->M))
+    return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: W == NULL needs a preceding gpar_sample_q_u with the same M and S");
   if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: merged inputs and pseudo-inputs must be set with equal D");
   if (ctx->Nt != ctx->N || ctx->Ny != ctx->N) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: times/outputs must have the merged length N+N* = %lld", (long long)ctx->N);
   if (ctx->has_rvec && ctx->Nr != ctx->N) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: noise vector length mismatch");
@@ -83,7 +85,8 @@ extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const d
   CU(ctx->kal_e.reserve(((size_t)4 * S * N + S + 2 * (size_t)N + (size_t)M * S) * sizeof(double)));
   double* fx = ctx->kal_e.as<double>(); double* ys = fx + (size_t)S * N; double* smean = ys + (size_t)S * N;
   double* svar = smean + (size_t)S * N; double* lml = svar + (size_t)S * N; double* dmean = lml + S; double* dsd = dmean + N; double* dW = dsd + N;
-  CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (W) CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  else CU(cudaMemcpyAsync(dW, ctx->qW.p, (size_t)M * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CallTimer timer(ctx); ctx->phase_valid = false;
   dim3 grid((unsigned)((N + 127) / 128), (S + SCHUNK - 1) / SCHUNK);
   const size_t smem = (size_t)128 * (DX + SCHUNK) * sizeof(double);

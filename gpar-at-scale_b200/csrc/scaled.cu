@@ -709,6 +709,37 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   return GPAR_OK;
 }
 
+// ---- seeded draws from q(u) on the device -------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011): counter = element index, key = seed;
+// two 53-bit uniforms -> Box-Muller -> two standard normals.  z is M x S column-major.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__global__ void philox_normal_kernel(double* __restrict__ z, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // pair index
+  if (2 * i >= n) return;
+  uint32_t c[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0u, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u1 = ((double)(((uint64_t)c[0] << 21) ^ (uint64_t)(c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);   // (0, 1)
+  const double u2 = ((double)(((uint64_t)c[2] << 21) ^ (uint64_t)(c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double r = sqrt(-2.0 * log(u1));
+  double sn, cs; sincospi(2.0 * u2, &sn, &cs);
+  z[2 * i] = r * cs;
+  if (2 * i + 1 < n) z[2 * i + 1] = r * sn;
+}
+// E[:, j] += m_e for every column j
+__global__ void add_column_vector_kernel(double* __restrict__ E, const double* __restrict__ v, int M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < total) E[e] += v[e % M];
+}
+
 int check_scaled(gpar_ctx* ctx, const char* who) {
   if (ctx->N < 1 || ctx->M < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: inputs and pseudo-inputs must be set", who);
   if (ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: X has D=%d but Z has D=%d", who, ctx->D, ctx->Dz);
@@ -842,12 +873,10 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   return GPAR_OK;
 }
 
-int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], double* m_e, double* Dinv, double* U_u) {
-  if (!ctx) return GPAR_ERR_INVALID;
-  if (!params || !m_e || !Dinv || !U_u) return gpar_fail(ctx, GPAR_ERR_INVALID, "compute_q_u: NULL argument");
-  CHK(check_scaled(ctx, "compute_q_u"));
-  CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx);
+// Shared front half of compute_q_u and the sampler: L_u = chol(Cuu) (bare, gpar_scaled_inference.jl:157-159),
+// L_D = chol(B_ef B_ef' + I) (:187), m_e = L_D^-T L_D^-1 L_u^-1 g (:189) — all left on the device.
+struct QuFactors { double *Lu, *LD, *Uu, *me; int* dinfo; int lwork; };
+static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params[5], QuFactors* q) {
   const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st));
@@ -862,9 +891,9 @@ int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5
   CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
   CU(ctx->info.reserve(4 * sizeof(int)));
   int* dinfo = ctx->info.as<int>();
+  CU(cudaMemsetAsync(dinfo, 0, 4 * sizeof(int), ctx->stream));
   CHK(launch_kuu_plain(ctx, k_out, out_l, out_s, 0.0, Lu));         // bare Cuu (gpar_scaled_inference.jl:157-159)
   CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
-  LAUNCH(ctx, lower_to_upper_kernel, (int)((MM + 255) / 256), 256, 0, Lu, M, Uu);
   CU(cudaMemcpyAsync(Dm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   const double one = 1.0;
   CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
@@ -876,18 +905,66 @@ int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5
   CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, vec, 1));
   CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Dm, M, vec, 1));
   CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Dm, M, vec, 1));
+  q->Lu = Lu; q->LD = Dm; q->Uu = Uu; q->me = vec; q->dinfo = dinfo; q->lwork = lwork;
+  return GPAR_OK;
+}
+
+int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], double* m_e, double* Dinv, double* U_u) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!params || !m_e || !Dinv || !U_u) return gpar_fail(ctx, GPAR_ERR_INVALID, "compute_q_u: NULL argument");
+  CHK(check_scaled(ctx, "compute_q_u"));
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  QuFactors q;
+  CHK(q_u_factors(ctx, k_time, k_out, params, &q));
+  const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
+  LAUNCH(ctx, lower_to_upper_kernel, (int)((MM + 255) / 256), 256, 0, q.Lu, M, q.Uu);
   // inv(D) (:192)
-  CS(cusolverDnDpotri(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Dm, M, ctx->tailws.as<double>(), lwork, dinfo + 2));
-  LAUNCH(ctx, mirror_lower_kernel, (int)((MM + 255) / 256), 256, 0, Dm, M);
+  CS(cusolverDnDpotri(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, q.LD, M, ctx->tailws.as<double>(), q.lwork, q.dinfo + 2));
+  LAUNCH(ctx, mirror_lower_kernel, (int)((MM + 255) / 256), 256, 0, q.LD, M);
   timer.stop();
   int hinfo[3];
-  CU(cudaMemcpyAsync(hinfo, dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(m_e, vec, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(Dinv, Dm, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(U_u, Uu, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(m_e, q.me, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(Dinv, q.LD, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(U_u, q.Uu, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
   if (hinfo[1] != 0 || hinfo[2] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
+  return GPAR_OK;
+}
+
+// S seeded draws eps_j ~ q_u = MvNormal(m_e, inv(D)) and the weights the prediction needs,
+// W[:, j] = U_u \ eps_j (gpar_scaled_inference.jl:94-96), entirely on the device:
+//   z ~ N(0, I) (Philox),  eps = m_e + L_D^-T z  (cov = L_D^-T L_D^-1 = inv(D): no explicit inverse),  W = L_u^-T eps.
+// W stays resident for gpar_scaled_predict(W = NULL); W_out / eps_out (nullable) receive host copies.
+int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], uint64_t seed, int32_t S, double* W_out, double* eps_out) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!params || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "sample_q_u: params must not be NULL and S >= 1");
+  CHK(check_scaled(ctx, "sample_q_u"));
+  CU(cudaSetDevice(ctx->device));
+  CallTimer timer(ctx);
+  QuFactors q;
+  CHK(q_u_factors(ctx, k_time, k_out, params, &q));
+  const int M = (int)ctx->M; const int64_t total = (int64_t)M * S;
+  CU(ctx->qW.reserve((size_t)2 * total * sizeof(double)));
+  double* W = ctx->qW.as<double>(); double* E = W + total;
+  LAUNCH(ctx, philox_normal_kernel, (int)(((total + 1) / 2 + 255) / 256), 256, 0, E, total, seed);
+  const double one = 1.0;
+  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, S, &one, q.LD, M, E, M));
+  LAUNCH(ctx, add_column_vector_kernel, (int)((total + 255) / 256), 256, 0, E, q.me, M, total);
+  CU(cudaMemcpyAsync(W, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, S, &one, q.Lu, M, W, M));
+  timer.stop();
+  int hinfo[2];
+  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  if (W_out) CU(cudaMemcpyAsync(W_out, W, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (eps_out) CU(cudaMemcpyAsync(eps_out, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->qW_M = 0; ctx->qW_S = 0;
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
+  ctx->qW_M = M; ctx->qW_S = S;
   return GPAR_OK;
 }
 

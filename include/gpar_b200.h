@@ -100,13 +100,22 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
 int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], double* m_e,
                      double* Dinv, double* U_u);
 
+/* Seeded draws from q_u on the device (replaces `rand(q_u)` + `U_u \ eps`, gpar_scaled_inference.jl:94-96,
+ * whose RNG is Julia's unseeded global one): S draws eps_j ~ MvNormal(m_e, inv(D)) from a Philox4x32-10
+ * stream keyed by `seed`, W[:, j] = U_u \ eps_j.  Needs the TRAINING data resident, like gpar_compute_q_u.
+ * W stays on the device for a following gpar_scaled_predict(..., W = NULL, S, ...); W_out / eps_out
+ * (M x S column-major, nullable) receive host copies. */
+int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5], uint64_t seed, int32_t S,
+                    double* W_out, double* eps_out);
+
 /* Monte-Carlo prediction of one scaled-GPAR output, get_gpar_scaled_predictions
  * (gpar_scaled_inference.jl:89-135), batched: resident data are the MERGED, time-SORTED train+test
  * inputs X* (set_inputs), times (set_times), outputs with 0 at test points (set_outputs, batch 1),
  * noise vector sigma^2 / 1e10 (set_noise_vector) and Z.  W (M x S column-major): column j =
  * U_u \ eps_j for the caller's draws eps_j ~ q_u (:91-97; the RNG stays with the caller).
  * Outputs (length N+N*, still in sorted order): sample mean and corrected std over the S draws of
- * f*_j = fx_j + smooth(y* - fx_j).m[1] (:113-125).  params: positive values as gpar_compute_q_u. */
+ * f*_j = fx_j + smooth(y* - fx_j).m[1] (:113-125).  params: positive values as gpar_compute_q_u.
+ * W == NULL: use the device-resident weights of the last gpar_sample_q_u (same M and S). */
 int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W,
                         int32_t S, double* mean, double* std);
 

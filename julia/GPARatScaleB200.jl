@@ -94,6 +94,15 @@ function compute_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, M::Integer)
     return m_e, Dinv, U_u
 end
 
+"Seeded device draws from q_u (replaces rand(q_u) and U_u \\ eps, gpar_scaled_inference.jl:94-96); W stays resident."
+function sample_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, seed::Integer, S::Integer, M::Integer; return_host::Bool = false)
+    W = return_host ? zeros(M, S) : zeros(0, 0); E = return_host ? zeros(M, S) : zeros(0, 0)
+    check(c, ccall((:gpar_sample_q_u, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), params, UInt64(seed), Int32(S),
+                   return_host ? pointer(W) : C_NULL, return_host ? pointer(E) : C_NULL))
+    return W, E
+end
+
 "logpdf(lgssm, y) for every resident sequence; theta is 3 x batch_theta (column per model)."
 function lgssm_logpdf(c::Ctx, k, theta::VecOrMat{Float64}, batch::Integer)
     lml = zeros(batch)

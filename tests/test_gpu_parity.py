@@ -410,6 +410,42 @@ def test_scaled_predict_against_oracle(ctx):
     assert np.max(np.abs(std - std0)) <= 1e-7 * max(1.0, np.max(np.abs(std0)))
 
 
+def test_sample_q_u_device_philox(ctx):
+    """gpar_sample_q_u (SURVEY 8f-2): seeded Philox draws on the device.  Deterministic per seed; U_u W = eps;
+    the sample mean / covariance of eps match (m_e, inv(D)) of gpar_compute_q_u within Monte-Carlo error
+    (the reference's own draws come from an unseeded RNG, so parity is distributional); predicting with
+    the resident weights equals predicting with the same weights passed from the host."""
+    rng = np.random.default_rng(21)
+    n, m, S = 600, 9, 40000
+    t = np.sort(rng.uniform(0, 20, n)); X = rng.normal(size=(n, 2)); Z = rng.normal(size=(m, 2)); y = rng.normal(size=n)
+    params = np.array([1.3, 0.9, 1.1, 0.8, 0.3])
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+    m_e, Dinv, U_u = ctx.compute_q_u(3, 3, params)
+    W, E = ctx.sample_q_u(3, 3, params, 1234, S, return_host=True)
+    W2, E2 = ctx.sample_q_u(3, 3, params, 1234, S, return_host=True)
+    W3, E3 = ctx.sample_q_u(3, 3, params, 1235, S, return_host=True)
+    assert np.array_equal(W, W2) and np.array_equal(E, E2) and not np.array_equal(E, E3)
+    assert np.max(np.abs(np.triu(U_u) @ W - E)) <= 1e-9 * np.max(np.abs(E))
+    sd = np.sqrt(np.diag(Dinv))
+    assert np.all(np.abs(E.mean(axis=1) - m_e) <= 5 * sd / np.sqrt(S))
+    C = np.cov(E)
+    assert np.max(np.abs(C - Dinv) / np.outer(sd, sd)) <= 5 * np.sqrt(2.0 / S)
+    zs = np.linalg.solve(np.linalg.cholesky(Dinv), E - m_e[:, None])          # back to the standard normals
+    assert abs(np.mean(zs ** 3)) <= 0.05 and abs(np.mean(zs ** 4) - 3.0) <= 0.1
+    # resident weights == host-passed weights
+    S2 = 16
+    W, E = ctx.sample_q_u(3, 3, params, 7, S2, return_host=True)
+    ns = 200
+    ts = np.sort(rng.uniform(0, 20, ns)); Xs = rng.normal(size=(ns, 2))
+    tc = np.concatenate([t, ts]); perm = np.argsort(tc, kind="stable")
+    ctx.set_inputs(np.concatenate([X, Xs])[perm]); ctx.set_times(tc[perm]); ctx.set_outputs(np.concatenate([y, np.zeros(ns)])[perm])
+    ctx.set_noise_vector(np.concatenate([np.full(n, params[4] ** 2), np.full(ns, 1e10)])[perm])
+    a = ctx.scaled_predict(3, 3, params)
+    b = ctx.scaled_predict(3, 3, params, W)
+    ctx.set_noise_vector(None)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_reference_example_chain_end_to_end(ctx):
     """examples/GPAR_scaled_examples.jl:86-175 through the host mirror (fit + predict, 3 outputs,
     N = 8 496, 20 000 prediction points): the predictions track the noise-free functions."""
