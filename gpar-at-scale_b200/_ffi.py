@@ -31,6 +31,9 @@ SIGNATURES = {
     "gpar_set_times_range": (ctypes.c_int, [_c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int64]),
     "gpar_set_outputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int32]),
     "gpar_set_noise_vector": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),
+    "gpar_set_merged": (ctypes.c_int, [_c_void_p, _c_double_p, _c_double_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
+                                       ctypes.c_int64, ctypes.c_int32, ctypes.c_double]),
+    "gpar_take_test": (ctypes.c_int, [_c_void_p, _c_double_p, _c_double_p]),
     "gpar_dtc_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double,
                                        _c_double_p, _c_double_p]),
     "gpar_scaled_dtc": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),

@@ -286,7 +286,8 @@ def smooth(lgssm, y, ctx=None):
 
 
 def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_structure=None, i_log_time_l=None, i_log_time_var=None,
-                        i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False, optimizer="neldermead"):
+                        i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False, optimizer="neldermead",
+                        device_merge=False):
     """temporal_gp_inference.jl:45-114 -> (opt_lgssm, output_observations).  optimizer="lbfgs" replaces the
     reference's Nelder-Mead (:82) by L-BFGS on the library's analytic gradient."""
     kernel_structure = kernel_structure or Matern52()
@@ -319,11 +320,17 @@ def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_s
     noise_vector = np.concatenate([np.full(len(data_locations), opt_noise_sigma ** 2), np.full(len(output_locations), 1e10)])   # :93-96
     s_noise_vector = noise_vector[sorting_perm]
     opt_lgssm = create_lgssm(s_latent_locations, opt_l, opt_process_var, opt_noise_sigma, kernel_structure, noise_vector=s_noise_vector)
-    ctx.set_times(s_latent_locations); ctx.set_outputs(s_outputs); ctx.set_noise_vector(s_noise_vector)
-    _, mean, var = ctx.lgssm_smooth(kernel_structure.code, results.minimizer)                  # :109
-    ctx.set_noise_vector(None)
-    nd = len(data_outputs)
-    mean = mean[0][reverse_perm][nd:]; var = var[0][reverse_perm][nd:]                         # :111-112
+    if device_merge:     # :55-66, :93-97, :111-112 on the device (gpar_set_merged / gpar_take_test)
+        ctx.set_merged(data_locations, data_outputs, output_locations, opt_noise_sigma ** 2)
+        ctx.lgssm_smooth(kernel_structure.code, results.minimizer, keep_on_device=True)
+        mean, var = ctx.take_test()
+        ctx.set_noise_vector(None)
+    else:
+        ctx.set_times(s_latent_locations); ctx.set_outputs(s_outputs); ctx.set_noise_vector(s_noise_vector)
+        _, mean, var = ctx.lgssm_smooth(kernel_structure.code, results.minimizer)              # :109
+        ctx.set_noise_vector(None)
+        nd = len(data_outputs)
+        mean = mean[0][reverse_perm][nd:]; var = var[0][reverse_perm][nd:]                     # :111-112
     if return_arrays:
         return opt_lgssm, (mean, var)
     return opt_lgssm, [Gaussian(m, v) for m, v in zip(mean, var)]
@@ -397,7 +404,7 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 inference_input_locations, out_kernel_structure=None, time_kernel_structure=None,
                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                 optimization_time_limit=1000.0, debug=False, ctx=None, rng=None, iterations=1000, nsamples=100,
-                                opt_params=None, sampler="host", seed=0):
+                                opt_params=None, sampler="host", seed=0, device_merge=False):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
@@ -438,6 +445,12 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
         eps = m_e[:, None] + Lc @ rng.standard_normal((len(m_e), nsamples))
         from scipy.linalg import solve_triangular
         W = solve_triangular(np.triu(U_u), eps, lower=False)
+    if device_merge:     # :75-87, :100-103, :132-133 on the device (gpar_set_merged / gpar_take_test)
+        ctx.set_merged(time_loc, outputs, inference_time_loc, opt_noise_sigma ** 2, X=X, Xs=Xs)
+        ctx.scaled_predict(time_kernel_structure.code, out_kernel_structure.code, params, W, keep_on_device=True)
+        mean, std = ctx.take_test()
+        ctx.set_noise_vector(None)
+        return mean, std
     ctx.set_inputs(input_loc_star); ctx.set_times(time_loc_concat[sorting_perm]); ctx.set_outputs(outputs_star)
     ctx.set_noise_vector(noise_vector_star)
     mean, std = ctx.scaled_predict(time_kernel_structure.code, out_kernel_structure.code, params, W)      # :110-130 batched

@@ -96,6 +96,26 @@ class Context:
         r = as_f64(np.asarray(r).ravel())
         self._check(self._lib.gpar_set_noise_vector(self._h, dptr(r), r.shape[0]))
 
+    def set_merged(self, t, y, ts, sigma2, X=None, Xs=None):
+        """Device merge/sort protocol (gpar_set_merged): train (t, y[, X]) + test (ts[, Xs]) -> resident sorted
+        times / outputs (0 at test points) / noise vector (sigma2 | 1e10) / inputs."""
+        t = as_f64(np.asarray(t).ravel()); y = as_f64(np.asarray(y).ravel()); ts = as_f64(np.asarray(ts).ravel())
+        D = 0
+        if X is not None:
+            X = as_f64(np.atleast_2d(X) if np.ndim(X) > 1 else np.asarray(X, dtype=np.float64).reshape(-1, 1))
+            Xs = as_f64(np.atleast_2d(Xs) if np.ndim(Xs) > 1 else np.asarray(Xs, dtype=np.float64).reshape(-1, 1))
+            D = X.shape[1]
+        self._check(self._lib.gpar_set_merged(self._h, dptr(t), dptr(y), dptr(X), t.shape[0], dptr(ts), dptr(Xs), ts.shape[0], D, float(sigma2)))
+        self.Nt = self.Ny = t.shape[0] + ts.shape[0]; self.batch = 1; self._merged_ns = ts.shape[0]
+        if D:
+            self.N, self.D = self.Nt, D
+
+    def take_test(self, two=True):
+        """(a, b) of the last smoother / prediction at the test locations of the merged problem, in test order."""
+        a = np.zeros(self._merged_ns); b = np.zeros(self._merged_ns) if two else None
+        self._check(self._lib.gpar_take_test(self._h, dptr(a), dptr(b)))
+        return (a, b) if two else a
+
     # -- compute --------------------------------------------------------------------------------
     def dtc_logpdf(self, kernel, theta, vfe=False, jitter=-1.0, grad=False):
         th = as_f64(np.asarray(theta).ravel())
@@ -138,10 +158,15 @@ class Context:
         self._nsamples_resident = int(nsamples)
         return (W, E) if return_host else None
 
-    def scaled_predict(self, k_time, k_out, params, W=None):
+    def scaled_predict(self, k_time, k_out, params, W=None, keep_on_device=False):
         """W: (M, S) — column j = U_u \\ eps_j; None: the resident weights of the last sample_q_u.
-        -> (mean, std) over the merged, sorted locations."""
+        -> (mean, std) over the merged, sorted locations (keep_on_device: nothing, use take_test())."""
         p = as_f64(np.asarray(params).ravel())
+        if keep_on_device:
+            Wf = None if W is None else np.asfortranarray(W, dtype=np.float64)
+            S = self._nsamples_resident if W is None else Wf.shape[1]
+            self._check(self._lib.gpar_scaled_predict(self._h, int(k_time), int(k_out), dptr(p), dptr(Wf), S, None, None))
+            return None
         mean = np.zeros(self.N); sd = np.zeros(self.N)
         if W is None:
             self._check(self._lib.gpar_scaled_predict(self._h, int(k_time), int(k_out), dptr(p), None, self._nsamples_resident, dptr(mean), dptr(sd)))
@@ -172,8 +197,12 @@ class Context:
         self._check(self._lib.gpar_lgssm_decorrelate(self._h, int(kernel), dptr(th), dptr(alpha), dptr(lml)))
         return lml, alpha
 
-    def lgssm_smooth(self, kernel, theta):
+    def lgssm_smooth(self, kernel, theta, keep_on_device=False):
         th = as_f64(np.asarray(theta).ravel())
+        if keep_on_device:      # results stay resident for take_test()
+            lml = np.zeros(self.batch)
+            self._check(self._lib.gpar_lgssm_smooth(self._h, int(kernel), dptr(th), None, None, dptr(lml)))
+            return lml
         mean = np.zeros((self.batch, self.Ny))
         var = np.zeros((self.batch, self.Ny))
         lml = np.zeros(self.batch)

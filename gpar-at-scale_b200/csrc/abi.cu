@@ -74,7 +74,7 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->panelB, &ctx->kal_f, &ctx->partial, &ctx->segs,
                     &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
-                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW};
+                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->mrg, &ctx->test_pos};
   for (DevBuf* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
@@ -128,7 +128,7 @@ int gpar_set_times(gpar_ctx* ctx, const double* t, int64_t N) {
   if (!ctx) return GPAR_ERR_INVALID;
   if (!t || N < 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_times: need t != NULL, N >= 0");
   CHK(upload(ctx, ctx->t, t, (size_t)N));
-  ctx->Nt = N; ctx->t_reg_dt = 0.0;
+  ctx->Nt = N; ctx->t_reg_dt = 0.0; ctx->merged_Ns = 0;
   return GPAR_OK;
 }
 __global__ void fill_range_kernel(double* t, double t0, double dt, int64_t N) {
@@ -142,7 +142,7 @@ int gpar_set_times_range(gpar_ctx* ctx, double t0, double dt, int64_t N) {
   CU(ctx->t.reserve((size_t)std::max<int64_t>(N, 1) * sizeof(double)));
   if (N > 0) LAUNCH(ctx, fill_range_kernel, (int)((N + 255) / 256), 256, 0, ctx->t.as<double>(), t0, dt, N);
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->Nt = N; ctx->t_reg_dt = dt;
+  ctx->Nt = N; ctx->t_reg_dt = dt; ctx->merged_Ns = 0;
   return GPAR_OK;
 }
 int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch) {

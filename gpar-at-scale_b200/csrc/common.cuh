@@ -58,6 +58,9 @@ struct gpar_ctx {
   // scratch (grown on demand)
   DevBuf panelK, panelD, panelB, kal_f, partial, segs, jobs, gpart, scal, dense, tailws, info;
   DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
+  // merged train+test problem (gpar_set_merged): staging, position of every test point in the sorted arrays,
+  // and the device arrays of the last smoother / prediction result (for gpar_take_test)
+  DevBuf mrg, test_pos; int64_t merged_N = 0, merged_Ns = 0; const double* res_a = nullptr; const double* res_b = nullptr; int64_t res_len = 0;
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   void* pinned = nullptr; size_t pinned_cap = 0;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`

@@ -1005,7 +1005,7 @@ int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], dou
 
 int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* mean, double* var, double* lml) {
   if (!ctx) return GPAR_ERR_INVALID;
-  if (!theta || !mean || !var) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_smooth: theta, mean and var must not be NULL");
+  if (!theta || ((mean == nullptr) != (var == nullptr))) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_smooth: theta must not be NULL; mean and var are given together or both NULL");
   CHK(check_seq(ctx, "lgssm_smooth"));
   const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
   CU(cudaSetDevice(ctx->device));
@@ -1016,8 +1016,11 @@ int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* 
   CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
                 ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, d_lml, d_mean, d_var, nullptr, nullptr));
   timer.stop();
-  CU(cudaMemcpyAsync(mean, d_mean, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(var, d_var, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->res_a = d_mean; ctx->res_b = d_var; ctx->res_len = (int64_t)batch * N;      // stays resident for gpar_take_test
+  if (mean) {
+    CU(cudaMemcpyAsync(mean, d_mean, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(var, d_var, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (lml) CU(cudaMemcpyAsync(lml, d_lml, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return GPAR_OK;

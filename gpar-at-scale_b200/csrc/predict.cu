@@ -71,7 +71,7 @@ __global__ void mc_reduce_kernel(const double* __restrict__ fx, const double* __
 extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W, int32_t S,
                                    double* mean, double* sd) {
   if (!ctx) return GPAR_ERR_INVALID;
-  if (!params || !mean || !sd || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: NULL argument or S < 1");
+  if (!params || ((mean == nullptr) != (sd == nullptr)) || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: NULL params, S < 1, or only one of mean / std given");
   if (!W && (ctx->qW_S != S || ctx->qW_M != ctx->M))
     return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: W == NULL needs a preceding gpar_sample_q_u with the same M and S");
   if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_predict: merged inputs and pseudo-inputs must be set with equal D");
@@ -103,8 +103,11 @@ extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const d
                 nullptr, lml, smean, svar, nullptr, nullptr));
   LAUNCH(ctx, mc_reduce_kernel, (unsigned)((N + 255) / 256), 256, 0, fx, smean, N, S, dmean, dsd);
   timer.stop();
-  CU(cudaMemcpyAsync(mean, dmean, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(sd, dsd, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->res_a = dmean; ctx->res_b = dsd; ctx->res_len = N;      // stays resident for gpar_take_test
+  if (mean) {
+    CU(cudaMemcpyAsync(mean, dmean, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(sd, dsd, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   return GPAR_OK;
 }

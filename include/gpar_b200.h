@@ -72,6 +72,20 @@ int gpar_set_outputs(gpar_ctx* ctx, const double* y, int64_t N, int32_t batch);
 /* per-step observation noise R_k (the 1e10 trick, temporal_gp_inference.jl:93-97); NULL clears it */
 int gpar_set_noise_vector(gpar_ctx* ctx, const double* r, int64_t N);
 
+/* The merge / sort / un-sort protocol of get_sde_predictions (temporal_gp_inference.jl:55-66,93-97,111-112)
+ * and get_gpar_scaled_predictions (gpar_scaled_inference.jl:75-87,100-103,132-133) on the device:
+ *   times = vcat(t, ts)[perm] with perm = sortperm (stable: at equal times the training point comes first),
+ *   outputs = vcat(y, zeros(Ns))[perm], noise vector = vcat(fill(sigma2, N), fill(1e10, Ns))[perm] and, when
+ *   D > 0, inputs = vcat(X, Xs)[perm] become the resident times / outputs / noise vector / inputs.
+ * X, Xs: N x D and Ns x D records (NULL with D = 0 for the time-only model).  After a smoother or a
+ * prediction on the merged problem (their host outputs may then be NULL), gpar_take_test returns the
+ * entries at the Ns test locations in the order of `ts` (result[reverse_perm][N+1:end]). */
+int gpar_set_merged(gpar_ctx* ctx, const double* t, const double* y, const double* X, int64_t N,
+                    const double* ts, const double* Xs, int64_t Ns, int32_t D, double sigma2);
+/* a_test, b_test (Ns each; b_test nullable): (mean, var) of the last gpar_lgssm_smooth (batch 1) or
+ * (mean, std) of the last gpar_scaled_predict, at the test locations. */
+int gpar_take_test(gpar_ctx* ctx, double* a_test, double* b_test);
+
 /* ---- pseudo-point approximation, diagonal noise: Stheno dtc / elbo --------------------------
  * Replaces Stheno's `dtc(f(X, sigma^2), y, u)` / `elbo(...)` (restated at
  * examples/dtc_example.jl:10-23) for f = GP(kernel(k; l, s = var^2)), theta = (log l, log var,
@@ -115,7 +129,8 @@ int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5]
  * U_u \ eps_j for the caller's draws eps_j ~ q_u (:91-97; the RNG stays with the caller).
  * Outputs (length N+N*, still in sorted order): sample mean and corrected std over the S draws of
  * f*_j = fx_j + smooth(y* - fx_j).m[1] (:113-125).  params: positive values as gpar_compute_q_u.
- * W == NULL: use the device-resident weights of the last gpar_sample_q_u (same M and S). */
+ * W == NULL: use the device-resident weights of the last gpar_sample_q_u (same M and S).
+ * mean = std = NULL: results stay on the device (gpar_take_test). */
 int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double params[5], const double* W,
                         int32_t S, double* mean, double* std);
 
@@ -134,7 +149,8 @@ int gpar_lgssm_logpdf_grad(gpar_ctx* ctx, int kernel, const double* theta, int32
 /* decorrelate (dtc.jl:106,115): alpha (N x batch) and lml (batch) for every resident sequence. */
 int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], double* alpha, double* lml);
 /* smooth (temporal_gp_inference.jl:109; gpar_scaled_inference.jl:117): mean = m_s[1], var = P_s[1,1]
- * per step and sequence (N x batch each), lml (batch, nullable). */
+ * per step and sequence (N x batch each), lml (batch, nullable).  mean = var = NULL: results stay on the
+ * device (gpar_take_test). */
 int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* mean, double* var, double* lml);
 
 /* ---- exact GP / GPAR (dense), src/gp/optimized.jl ------------------------------------------

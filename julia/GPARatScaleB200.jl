@@ -94,6 +94,20 @@ function compute_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, M::Integer)
     return m_e, Dinv, U_u
 end
 
+"vcat / sortperm / gather / 1e10 noise vector on the device (temporal_gp_inference.jl:55-66,93-97; gpar_scaled_inference.jl:75-87,100-103)."
+function set_merged!(c::Ctx, t::Vector{Float64}, y::Vector{Float64}, ts::Vector{Float64}, sigma2::Float64;
+                     X::Matrix{Float64} = zeros(0, 0), Xs::Matrix{Float64} = zeros(0, 0))
+    D = size(X, 1)
+    check(c, ccall((:gpar_set_merged, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Float64),
+                   c.h, t, y, D > 0 ? pointer(X) : C_NULL, length(t), ts, D > 0 ? pointer(Xs) : C_NULL, length(ts), Int32(D), sigma2))
+end
+"result[reverse_perm][N+1:end] of the last smoother / prediction (temporal_gp_inference.jl:111-112; gpar_scaled_inference.jl:132-133)."
+function take_test(c::Ctx, Ns::Integer)
+    a = zeros(Ns); b = zeros(Ns)
+    check(c, ccall((:gpar_take_test, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), c.h, a, b))
+    return a, b
+end
+
 "Seeded device draws from q_u (replaces rand(q_u) and U_u \\ eps, gpar_scaled_inference.jl:94-96); W stays resident."
 function sample_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, seed::Integer, S::Integer, M::Integer; return_host::Bool = false)
     W = return_host ? zeros(M, S) : zeros(0, 0); E = return_host ? zeros(M, S) : zeros(0, 0)

@@ -410,6 +410,47 @@ def test_scaled_predict_against_oracle(ctx):
     assert np.max(np.abs(std - std0)) <= 1e-7 * max(1.0, np.max(np.abs(std0)))
 
 
+def test_device_merge_sort_protocol(ctx):
+    """gpar_set_merged / gpar_take_test against the host protocol (stable argsort, gather, 1e10
+    noise vector, un-sort), with train/test time collisions (ties keep the training point first, like Julia's
+    stable sortperm): bit-identical smoother and prediction results."""
+    from gpar_at_scale_b200 import api
+    rng = np.random.default_rng(33)
+    n, ns, d, m = 3000, 2500, 2, 30
+    t = np.sort(rng.uniform(0, 100, n)); ts = np.sort(rng.uniform(-5, 110, ns))
+    ts[::7] = t[rng.integers(0, n, len(ts[::7]))]                     # exact collisions with training times
+    ts = np.sort(ts)
+    y = np.sin(t) + 0.1 * rng.normal(size=n)
+    X = rng.normal(size=(n, d)); Xs = rng.normal(size=(ns, d)); Z = rng.normal(size=(m, d))
+    th = np.log([1.5, 1.0, 0.2]); sig2 = (np.exp(th[2]) + 1e-3) ** 2
+    tc = np.concatenate([t, ts]); perm = np.argsort(tc, kind="stable"); rev = np.argsort(perm, kind="stable")
+    # time-only model: smoother
+    ctx.set_times(tc[perm]); ctx.set_outputs(np.concatenate([y, np.zeros(ns)])[perm])
+    ctx.set_noise_vector(np.concatenate([np.full(n, sig2), np.full(ns, 1e10)])[perm])
+    _, mean, var = ctx.lgssm_smooth(3, th)
+    ctx.set_merged(t, y, ts, sig2)
+    ctx.lgssm_smooth(3, th, keep_on_device=True)
+    a, b = ctx.take_test()
+    assert np.array_equal(a, mean[0][rev][n:]) and np.array_equal(b, var[0][rev][n:])
+    # scaled-GPAR prediction with inputs
+    params = np.array([1.3, 0.9, 1.1, 0.8, 0.3]); W = rng.normal(size=(m, 8))
+    ctx.set_pseudo(Z)
+    ctx.set_inputs(np.concatenate([X, Xs])[perm]); ctx.set_times(tc[perm]); ctx.set_outputs(np.concatenate([y, np.zeros(ns)])[perm])
+    ctx.set_noise_vector(np.concatenate([np.full(n, params[4] ** 2), np.full(ns, 1e10)])[perm])
+    pm, ps = ctx.scaled_predict(3, 3, params, W)
+    ctx.set_merged(t, y, ts, params[4] ** 2, X=X, Xs=Xs)
+    ctx.scaled_predict(3, 3, params, W, keep_on_device=True)
+    a, b = ctx.take_test()
+    assert np.array_equal(a, pm[rev][n:]) and np.array_equal(b, ps[rev][n:])
+    ctx.set_noise_vector(None)
+    # host mirror: device_merge=True gives the same predictions as the host protocol
+    m1 = api.get_sde_predictions(t, y, ts, i_log_time_l=0.3, i_log_time_var=0.0, i_log_noise_sigma=-1.5, debug=False, ctx=ctx, return_arrays=True)[1]
+    m2 = api.get_sde_predictions(t, y, ts, i_log_time_l=0.3, i_log_time_var=0.0, i_log_noise_sigma=-1.5, debug=False, ctx=ctx, return_arrays=True, device_merge=True)[1]
+    assert np.array_equal(m1[0], m2[0]) and np.array_equal(m1[1], m2[1])
+    with pytest.raises(Exception):
+        ctx.set_times(t); ctx.take_test()                               # the merged problem is gone
+
+
 def test_sample_q_u_device_philox(ctx):
     """gpar_sample_q_u (SURVEY 8f-2): seeded Philox draws on the device.  Deterministic per seed; U_u W = eps;
     the sample mean / covariance of eps match (m_e, inv(D)) of gpar_compute_q_u within Monte-Carlo error
