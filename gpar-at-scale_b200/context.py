@@ -125,6 +125,14 @@ class Context:
                                               ctypes.byref(val), dptr(g)))
         return (val.value, g) if grad else val.value
 
+    def dtc_logpdf_zgrad(self, kernel, theta, vfe=False, jitter=-1.0):
+        """-> (value, d/dtheta (3,), d/dZ (M, D)): pseudo-input gradients of the DTC / VFE objective."""
+        th = as_f64(np.asarray(theta).ravel())
+        val = ctypes.c_double(); g = np.zeros(3); gz = np.zeros((self.M, self.D))
+        self._check(self._lib.gpar_dtc_logpdf_zgrad(self._h, int(kernel), dptr(th), int(bool(vfe)), float(jitter),
+                                                    ctypes.byref(val), dptr(g), dptr(gz)))
+        return val.value, g, gz
+
     def scaled_dtc(self, k_time, k_out, theta, return_A=False):
         th = as_f64(np.asarray(theta).ravel())
         val = ctypes.c_double()

@@ -178,6 +178,9 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
 int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
                       const double* t, const double* y, const double* rvec, const int dirs[3],
                       double* d_alpha, double* d_lml, double* d_dlml, double* d_sums, double* d_dalpha, double* d_table, double* d_dtable);
+// scaled.cu: e = a - panel w (panel in the operand layout), and rows [4 g_lo, 4 (g_lo + ng)) of a panel as a dense M x 4ng matrix
+int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, const double* a, int64_t N, int64_t NB4, int T, int M, double* e);
+int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* Bt);
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;

@@ -764,6 +764,17 @@ int launch_kuu_plain(gpar_ctx* ctx, int kind, double l, double s, double jitter,
 
 }  // namespace
 
+// helpers shared with zgrad.cu
+int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, const double* a, int64_t N, int64_t NB4, int T, int M, double* e) {
+  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, panel, w, a, N, NB4, T, M, e);
+  return GPAR_OK;
+}
+int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* Bt) {
+  const int64_t total = (int64_t)T * ng * GPAR_TILE;
+  LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, panel, NB4, g_lo, ng, T, M, Bt);
+  return GPAR_OK;
+}
+
 static const double LOG2PI_S = 1.8378770664093454835606594728112;
 
 extern "C" {

@@ -97,6 +97,13 @@ int gpar_take_test(gpar_ctx* ctx, double* a_test, double* b_test);
 int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, double jitter,
                     double* val, double* grad);
 
+/* The same objective with, additionally, its gradient with respect to the pseudo-inputs: grad_Z is M x D
+ * records like Z (NEW — the reference keeps Z fixed, dtc_example.jl:82-90; pseudo-input optimisation is what the
+ * Titsias bound vfe = 1 is for).  Matern-1/2 is not differentiable where a pseudo-input coincides with an
+ * input: that pair contributes 0 (a subgradient). */
+int gpar_dtc_logpdf_zgrad(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, double jitter,
+                          double* val, double* grad_theta, double* grad_Z);
+
 /* ---- scaled GPAR objective: compute_gpar_dtc_objective, src/gp/dtc.jl:83-128 ---------------
  * theta = unpack_gpar parameters (util.jl:45-55).  Returns dtc (the nlml closure dtc.jl:29-47
  * returns -dtc).  A_or_null: optional M x N column-major output of the `A` the reference also

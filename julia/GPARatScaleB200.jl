@@ -69,6 +69,14 @@ function dtc_logpdf(c::Ctx, k, theta::Vector{Float64}; vfe::Bool = false, jitter
     return grad ? (val[], g) : val[]
 end
 
+"DTC / VFE objective with d/dtheta (3) and d/dZ (D x M, the ColVecs layout of Z) — pseudo-input optimisation."
+function dtc_logpdf_zgrad(c::Ctx, k, theta::Vector{Float64}, D::Integer, M::Integer; vfe::Bool = false, jitter::Float64 = -1.0)
+    val = Ref{Float64}(0.0); g = zeros(3); gz = zeros(D, M)
+    check(c, ccall((:gpar_dtc_logpdf_zgrad, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Float64, Ref{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, kernel_code(k), theta, vfe ? 1 : 0, jitter, val, g, gz))
+    return val[], g, gz
+end
+
 "compute_gpar_dtc_objective (src/gp/dtc.jl:83-128): returns (dtc, A) like the reference."
 function scaled_dtc(c::Ctx, k_time, k_out, theta::Vector{Float64}, N::Integer, M::Integer; return_A::Bool = false)
     val = Ref{Float64}(0.0)

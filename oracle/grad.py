@@ -56,16 +56,20 @@ def dtc_diag_t(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
     return val
 
 
-def dtc_diag_value_and_grad(theta, X, Z, y, kind, vfe=False, jitter=-1.0):
+def dtc_diag_value_and_grad(theta, X, Z, y, kind, vfe=False, jitter=-1.0, wrt_Z=False):
+    """-> (value, d/dtheta) or, with wrt_Z, (value, d/dtheta, d/dZ (M x D)) — pseudo-input gradients."""
     th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
     X = torch.as_tensor(X, dtype=torch.float64)
-    Z = torch.as_tensor(Z, dtype=torch.float64)
+    Z = torch.tensor(Z, dtype=torch.float64)
     if X.ndim == 1:
         X = X[:, None]
     if Z.ndim == 1:
         Z = Z[:, None]
+    Z = Z.clone().requires_grad_(wrt_Z)
     v = dtc_diag_t(th, X, Z, torch.as_tensor(y, dtype=torch.float64), kind, vfe, jitter)
     v.backward()
+    if wrt_Z:
+        return float(v.detach()), th.grad.numpy().copy(), Z.grad.numpy().copy()
     return float(v.detach()), th.grad.numpy().copy()
 
 

@@ -47,6 +47,44 @@ def test_dtc_vs_oracle_ragged_shapes(ctx, kind, n, m, d):
         assert np.all(np.abs(grad - g0) <= 1e-6 * np.abs(g0) + 1e-7 * np.max(np.abs(g0)))
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,m,d", [(5, 3, 2), (300, 17, 1), (1000, 64, 3), (4099, 130, 2), (2000, 40, 7)])
+def test_dtc_pseudo_input_gradient_vs_autograd(ctx, kind, n, m, d):
+    """gpar_dtc_logpdf_zgrad: dF/dZ of DTC and VFE against torch autograd of the oracle; 1e-6
+    relative to the largest entry (Z distinct from X: Matern-1/2 is not differentiable at coincidences)."""
+    rng = np.random.default_rng(500 * kind + n + m)
+    X = rng.normal(size=(n, d)) * 2; Z = rng.normal(size=(m, d)) * 2; y = rng.normal(size=n)
+    th = rng.uniform(-1, 0.5, 3)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y)
+    for vfe in (False, True):
+        val, g, gz = ctx.dtc_logpdf_zgrad(kind, th, vfe=vfe)
+        v0, g0, gz0 = dtc_diag_value_and_grad(th, X, Z, y, kind, vfe, wrt_Z=True)
+        assert abs(val - v0) <= RTOL * abs(v0)
+        assert np.all(np.abs(g - g0) <= 1e-6 * np.abs(g0) + 1e-7 * np.max(np.abs(g0)))
+        assert gz.shape == (m, d) and np.max(np.abs(gz - gz0)) <= 1e-6 * np.max(np.abs(gz0)), (np.max(np.abs(gz - gz0)), np.max(np.abs(gz0)))
+
+
+def test_dtc_pseudo_input_gradient_full_size(ctx):
+    """N = 1M, M = 1024 (several GEMM slabs): dF/dZ against central differences of the device value along
+    two random directions in Z-space."""
+    rng = np.random.default_rng(8)
+    N, M = 1_000_000, 1024
+    x = rng.uniform(0, 100, N); z = np.linspace(0, 100, M) + 0.01 * rng.normal(size=M)
+    y = np.sin(x) + 0.3 * np.cos(3.1 * x) + 0.1 * rng.normal(size=N)
+    th = np.log([1.0, 1.0, 0.1])
+    ctx.set_inputs(x); ctx.set_pseudo(z); ctx.set_outputs(y)
+    val, g, gz = ctx.dtc_logpdf_zgrad(3, th, vfe=True)
+    ms, launches = ctx.last_timing()
+    print("VFE value + d/dtheta + d/dZ at N=1M, M=1024: %.1f ms device" % ms)
+    for trial in range(2):
+        u = rng.normal(size=M); u /= np.linalg.norm(u)
+        h = 1e-4
+        ctx.set_pseudo(z + h * u); fp = ctx.dtc_logpdf(3, th, vfe=True)
+        ctx.set_pseudo(z - h * u); fm = ctx.dtc_logpdf(3, th, vfe=True)
+        fd = (fp - fm) / (2 * h); an = float(gz[:, 0] @ u)
+        assert abs(an - fd) <= 1e-4 * abs(fd) + 0.5, (an, fd)
+
+
 def test_dtc_full_size_properties(ctx):
     """BASELINE config 2 at full size (N = 1M, M = 1024): size-independent properties.
     (a) duplicating the data set doubles the sufficient statistics: dtc(2 copies) is reproduced by the
