@@ -52,6 +52,8 @@ struct gpar_ctx {
   int32_t D = 0, Dz = 0, ybatch = 0;
   int64_t N = 0, M = 0, Nt = 0, Ny = 0, Nr = 0;
   bool has_rvec = false;
+  bool ss_deferred_ok = false;        // the running entry point checks lgssm_steady_failed() after its final synchronisation
+  bool ss_pending = false;            // the single-pass steady-state path ran: its flags are on their way to ctx->pinned
   int ss_skip = 0;                    // calls for which the steady-state Kalman path stays off after a non-converged hand-over
   double t_reg_dt = 0.0;              // > 0: the resident times are the regular grid t0 + k dt (gpar_set_times_range)
 

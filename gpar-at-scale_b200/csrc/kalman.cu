@@ -792,6 +792,451 @@ __global__ void ss_finish_kernel(const double* __restrict__ sums_tr, const doubl
   flags[b] = cst[SSLayout<D>::OK];
 }
 
+// ---- single-pass steady-state path for LONG sequences (few sequences, N >> transient) -----------------
+// The two-pass scheme above reads y twice and needs ~18 launches.  For a long sequence the mean recursion
+// m_k = Phi m_{k-1} + K y_k forgets its start state geometrically (rho(Phi) < 1), so a block that starts W
+// steps BEFORE its segment from a zero state arrives with the exact state to working precision once
+// ||Phi^W|| <= 1e-18 ("burn-in"; W is found by repeated squaring).  Every block is then independent:
+// one pass over y (plus W / segment re-reads), no inter-block scan, three launches in total:
+//   ss2_setup : per sequence, the steady-state covariance by DOUBLING — the filtering element of one step
+//               combined with itself (FiltElem::combine) covers 2, 4, 8, ... steps and its C converges to
+//               the fixed point of the Riccati map quadratically; one Riccati step verifies it (1e-12);
+//               steady constants, the powers Phi^(32 2^j) of the block scan, the 4-step blocking constants, W;
+//   ss2_main  : block = 256 sub-chunks of 32 steps staged in shared memory (cp.async, coalesced);
+//               sub-chunk responses (4 steps per dependent mat-vec) -> block-level scan with the constant
+//               powers (warp shuffles) -> emit alpha, sum alpha^2.  The first block of a sequence walks the
+//               Riccati transient from the prior sequentially (one lane) until P has stopped moving (1e-13,
+//               twice) and hands the exact state to its remaining sub-chunks — it runs underneath the others;
+//   ss2_finish: fixed-order sums -> lml.
+constexpr int SS2_LS = 32, SS2_THREADS = 256, SS2_STEPS = SS2_LS * SS2_THREADS;     // 8192 steps per block (incl. burn-in)
+constexpr int SS2_WCAP = 2048, SS2_WFIX = 1024;
+template <int D> struct SS2Layout {      // per-sequence constants (doubles)
+  static constexpr int TR = D * D + 2 * D + 2;                                     // Phi, K, HA, rs, log S
+  static constexpr int NPOW = 6;                                                    // Phi^(LS 2^j), j = 0..5 (sub-chunk ... warp)
+  static constexpr int ROW = 0, POWS = TR, PHI4 = POWS + NPOW * D * D, G4 = PHI4 + D * D, KSTAR = G4 + 4 * D, W = KSTAR + 1, OK = W + 1,
+                       SIZE = OK + 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(32)
+ss2_setup_kernel(SeqParams sp, int batch, double* __restrict__ cst) {
+  typedef SS2Layout<D> SL;
+  typedef FiltElem<D> FE;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int pb = sp.nparam == 1 ? 0 : b;
+  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
+  double P0[NSYM<D>], Zs[NSYM<D>], Q[NSYM<D>], A[D * D];
+  lgssm_pinf<D>(P0);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) { P0[i] *= s; Zs[i] = 0.0; }
+  lgssm_transition<D>(sp.reg_dt * il, A);
+  predict_cov<D>(A, Zs, P0, Q);                              // Q = P0 - A P0 A'
+  // filtering element of one step, data parts zero
+  FE e; e.set_identity();
+  {
+    const double S = Q[0] + noise, iS = 1.0 / S;
+    double Kg[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) Kg[i] = SYM(Q, i, 0) * iS;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+      for (int j = 0; j < D; j++) e.v[i * D + j] = fma(-Kg[i], A[j], A[i * D + j]);
+#pragma unroll
+      for (int j = i; j < D; j++) { SYM((e.v + FE::OC), i, j) = fma(-S * Kg[i], Kg[j], SYM(Q, i, j)); SYM((e.v + FE::OJ), i, j) = A[i] * A[j] * iS; }
+    }
+  }
+  bool conv = false;
+  for (int it = 0; it < 16 && !conv; it++) {                 // 2^16 steps: far beyond any model the burn-in cap admits
+    FE n = FE::combine(e, e);
+    double dmax = 0.0, pmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) { dmax = fmax(dmax, fabs(n.v[FE::OC + i] - e.v[FE::OC + i])); pmax = fmax(pmax, fabs(n.v[FE::OC + i])); }
+    conv = dmax <= 1e-14 * pmax;
+    e = n;
+  }
+  double P[NSYM<D>], Pp[NSYM<D>], Kg[D], row[SL::TR];
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) P[i] = e.v[FE::OC + i];
+  predict_cov<D>(A, P, P0, Pp);
+  const double S = Pp[0] + noise, iS = 1.0 / S;
+  double dmax = 0.0, pmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) Kg[i] = SYM(Pp, i, 0) * iS;
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = i; j < D; j++) { const double pn = fma(-S * Kg[i], Kg[j], SYM(Pp, i, j)); dmax = fmax(dmax, fabs(pn - SYM(P, i, j))); pmax = fmax(pmax, fabs(pn)); }
+  bool ok = conv && dmax <= 1e-12 * pmax;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+#pragma unroll
+    for (int j = 0; j < D; j++) row[i * D + j] = fma(-Kg[i], A[j], A[i * D + j]);
+    row[D * D + i] = Kg[i]; row[D * D + D + i] = A[i];
+  }
+  row[D * D + 2 * D] = rsqrt(S); row[D * D + 2 * D + 1] = log(S);
+  double* o = cst + (int64_t)b * SL::SIZE;
+#pragma unroll
+  for (int i = 0; i < SL::TR; i++) o[SL::ROW + i] = row[i];
+  // 4-step blocking: x_{k+4} = Phi^4 x_k + sum_i (Phi^(3-i) K) y_{k+i}
+  {
+    double v[D], u[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { v[i] = Kg[i]; o[SL::G4 + 3 * D + i] = v[i]; }
+    for (int q = 2; q >= 0; q--) {
+      matvec<D>(row, v, u);
+#pragma unroll
+      for (int i = 0; i < D; i++) { v[i] = u[i]; o[SL::G4 + q * D + i] = v[i]; }
+    }
+  }
+  // powers Phi^(LS 2^j) for the block-level scan, and the burn-in length W: first W >= LS with ||Phi^W||_inf <= 1e-18
+  double M[D * D], T[D * D];
+#pragma unroll
+  for (int i = 0; i < D * D; i++) M[i] = row[i];
+  int W = 0, cur = 1;
+  for (int q = 0; q < 12; q++) {                             // cur = 2^q
+    if (cur == 4) {
+#pragma unroll
+      for (int i = 0; i < D * D; i++) o[SL::PHI4 + i] = M[i];
+    }
+    for (int j = 0; j < SL::NPOW; j++)
+      if (cur == (SS2_LS << j)) {
+#pragma unroll
+        for (int i = 0; i < D * D; i++) o[SL::POWS + j * D * D + i] = M[i];
+      }
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) { double r = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) r += fabs(M[i * D + j]);
+      nrm = fmax(nrm, r); }
+    if (W == 0 && nrm <= 1e-18 && cur >= SS2_LS) W = cur;
+    if (cur >= (SS2_LS << (SL::NPOW - 1)) && (W > 0 || cur >= SS2_WCAP)) break;
+    matmul<D>(M, M, T);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) M[i] = T[i];
+    cur *= 2;
+  }
+  if (W == 0) { W = SS2_WCAP; ok = false; }                    // start state not forgotten within the cap: the caller falls back
+  if (W > SS2_WFIX) ok = false;                                // the fixed burn-in of the main pass would be too short
+  o[SL::KSTAR] = 0.0; o[SL::W] = (double)W; o[SL::OK] = ok ? 1.0 : 0.0;
+}
+
+// HEAD = true: the first block of every sequence (transient + hand-over), launched on the side stream so that
+// it runs underneath the HEAD = false blocks (all the others); scratchS: SS2_STEPS doubles per sequence.
+template <int D, bool HEAD>
+__global__ void __launch_bounds__(SS2_THREADS, HEAD ? 1 : 3)
+ss2_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, SeqParams sp, double* __restrict__ cst,
+                int W, int nseg, double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ scratchS) {
+  typedef SS2Layout<D> SL;
+  extern __shared__ double ysm[];                            // SS2_STEPS values, padded by one per sub-chunk
+  __shared__ double wtot[SS2_THREADS / 32][D];
+  __shared__ double inject[D], trsum[2], red[32];
+  __shared__ int kst_sh;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.y, seg = HEAD ? 0 : blockIdx.x + 1;
+  const double* c = cst + (int64_t)b * SL::SIZE;
+  const int payload = SS2_STEPS - W;
+  // block 0 of a sequence: window [0, 8192) (transient + exact hand-over); block s >= 1: W burn-in steps, then its payload
+  const int64_t load_start = HEAD ? 0 : (int64_t)SS2_STEPS + (int64_t)(seg - 1) * payload - W;
+  if (load_start + (HEAD ? 0 : W) >= N) return;               // nothing to emit (uniform per block)
+  const double* yb = y + (int64_t)b * ystride;
+  {
+    static_assert(SS2_THREADS % SS2_LS == 0, "a pass of the block covers whole sub-chunks");
+    const double* src = yb + load_start + tid;
+    double* dst = ysm + tid + tid / SS2_LS;
+    constexpr int ROWS_PER_PASS = SS2_THREADS / SS2_LS;
+    if (load_start + SS2_STEPS <= N) {
+#pragma unroll 8
+      for (int i = 0; i < SS2_LS; i++) ss_cp_async8(dst + i * (SS2_THREADS + ROWS_PER_PASS), src + i * SS2_THREADS);
+    } else {
+      for (int i = 0; i < SS2_LS; i++) {
+        const int64_t k = load_start + tid + (int64_t)i * SS2_THREADS;
+        if (k < N) ss_cp_async8(dst + i * (SS2_THREADS + ROWS_PER_PASS), src + i * SS2_THREADS);
+        else dst[i * (SS2_THREADS + ROWS_PER_PASS)] = 0.0;
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  double Phi[D * D], Kg[D], ha[D];
+#pragma unroll
+  for (int i = 0; i < D * D; i++) Phi[i] = c[SL::ROW + i];
+#pragma unroll
+  for (int i = 0; i < D; i++) { Kg[i] = c[SL::ROW + D * D + i]; ha[i] = c[SL::ROW + D * D + D + i]; }
+  const double rs = c[SL::ROW + D * D + 2 * D];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  int kst = W;                                                // first emitting step of this block's window (local index)
+  if constexpr (HEAD) {
+    double* Sk = scratchS + (int64_t)b * SS2_STEPS;
+    if (tid == 0) {
+      // the Riccati transient from the prior, sequentially: covariance + mean recursion only; the innovations
+      // replace y in place and S_k goes to scratch — alpha_k and log S_k are formed afterwards by all threads
+      const int pb = sp.nparam == 1 ? 0 : b;
+      const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
+      double P0[NSYM<D>], P[NSYM<D>], A[D * D], x[D];
+      lgssm_pinf<D>(P0);
+#pragma unroll
+      for (int i = 0; i < NSYM<D>; i++) { P0[i] *= s; P[i] = P0[i]; }
+#pragma unroll
+      for (int i = 0; i < D; i++) x[i] = 0.0;
+      lgssm_transition<D>(1.0 * il, A);                      // step 0 follows the t[0] - 1 prefix
+      int conv = 0, found = -1;
+      const int kmax = (int)(N < SS2_STEPS - SS2_LS ? N : SS2_STEPS - SS2_LS);
+      int k = 0;
+      for (; k < kmax; k++) {
+        if (k == 1) lgssm_transition<D>(sp.reg_dt * il, A);
+        double Pp[NSYM<D>], mp[D], Kt[D];
+        predict_cov<D>(A, P, P0, Pp);
+        matvec<D>(A, x, mp);
+        const double S = Pp[0] + noise, iS = 1.0 / S, inn = ysm[k + k / SS2_LS] - mp[0];
+        ysm[k + k / SS2_LS] = inn;
+        Sk[k] = S;
+        double dmax = 0.0, pmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { Kt[i] = SYM(Pp, i, 0) * iS; x[i] = fma(Kt[i], inn, mp[i]); }
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+          for (int j = i; j < D; j++) {
+            const double pn = fma(-S * Kt[i], Kt[j], SYM(Pp, i, j));
+            dmax = fmax(dmax, fabs(pn - SYM(P, i, j))); pmax = fmax(pmax, fabs(pn));
+            SYM(P, i, j) = pn;
+          }
+        conv = (k >= 2 && dmax <= 1e-13 * pmax) ? conv + 1 : 0;
+        if (conv >= 2 && (k + 1) % SS2_LS == 0) { found = k + 1; break; }
+      }
+      if (found < 0 && k >= N) found = (int)((N + SS2_LS - 1) / SS2_LS * SS2_LS);   // the sequence ended inside the transient
+      if (found < 0) { found = SS2_STEPS; cst[(int64_t)b * SL::SIZE + SL::OK] = 0.0; }   // not converged: the caller falls back
+      kst_sh = found;
+      cst[(int64_t)b * SL::SIZE + SL::KSTAR] = (double)(found < N ? found : N);
+#pragma unroll
+      for (int i = 0; i < D; i++) inject[i] = x[i];
+      __threadfence_block();
+    }
+    __syncthreads();
+    kst = kst_sh;
+    // alpha_k = innovation / sqrt(S_k), sum log S_k, sum alpha_k^2 over the transient, in parallel
+    double sl = 0.0, sa = 0.0;
+    const int ntr = (int)(kst < N ? kst : N);
+    for (int k = tid; k < ntr; k += SS2_THREADS) {
+      const double S = Sk[k], a = ysm[k + k / SS2_LS] * rsqrt(S);
+      ysm[k + k / SS2_LS] = a; sl += log(S); sa = fma(a, a, sa);
+    }
+    const double r0 = block_sum(sl, red);
+    const double r1 = block_sum(sa, red);
+    if (tid == 0) { trsum[0] = r0; trsum[1] = r1; }
+    __syncthreads();
+  }
+  // phase 1: response of sub-chunk tid (zero start state; the hand-over sub-chunk of block 0 starts exactly)
+  const int64_t k0 = load_start + (int64_t)tid * SS2_LS;     // first step of this sub-chunk
+  const bool steady = tid * SS2_LS >= kst || !HEAD;           // block 0: sub-chunks before kst were done by the transient
+  const bool active = k0 < N && steady;
+  const bool pay = active && tid * SS2_LS >= kst;             // emits (burn-in sub-chunks only warm up)
+  const bool injected = HEAD && tid * SS2_LS == kst;
+  const int nv = !active ? 0 : (N - k0 >= SS2_LS ? SS2_LS : (int)(N - k0));
+  const double* row = ysm + tid * (SS2_LS + 1);
+  double rsp[D];                                             // state at the end of the sub-chunk for a zero state at its start
+#pragma unroll
+  for (int i = 0; i < D; i++) rsp[i] = 0.0;
+  if (active && nv == SS2_LS) {                               // (a partial last sub-chunk has no successor)
+    double P4[D * D], G[4][D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) P4[i] = c[SL::PHI4 + i];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int i = 0; i < D; i++) G[q][i] = c[SL::G4 + q * D + i];
+    if (injected) {
+#pragma unroll
+      for (int i = 0; i < D; i++) rsp[i] = inject[i];        // (everything before it in the block is identically zero)
+    }
+#pragma unroll
+    for (int j = 0; j < SS2_LS; j += 4) {
+      double nx[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double v = G[0][i] * row[j];
+        v = fma(G[1][i], row[j + 1], v); v = fma(G[2][i], row[j + 2], v); v = fma(G[3][i], row[j + 3], v);
+#pragma unroll
+        for (int q = 0; q < D; q++) v = fma(P4[i * D + q], rsp[q], v);
+        nx[i] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) rsp[i] = nx[i];
+    }
+  }
+  // phase 2: block-level scan of the sub-chunk responses.  All sub-chunks span SS2_LS steps, so the combine
+  // at distance 2^j only needs the constant power Phi^(LS 2^j):  x_i <- Phi^(LS 2^j) x_(i - 2^j) + x_i.
+  const double* pw = c + SL::POWS;
+  auto warp_scan = [&](double* v) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      double o[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) o[i] = __shfl_up_sync(0xffffffffu, v[i], 1 << j);
+      if (lane >= (1 << j)) {
+#pragma unroll
+        for (int i = 0; i < D; i++) { double a = v[i];
+#pragma unroll
+          for (int q = 0; q < D; q++) a = fma(__ldg(pw + j * D * D + i * D + q), o[q], a);
+          v[i] = a; }
+      }
+    }
+  };
+  double tot[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) tot[i] = rsp[i];
+  warp_scan(tot);                                             // lane 31: state at the end of the warp for a zero state at its start
+  if (lane == 31) {
+#pragma unroll
+    for (int i = 0; i < D; i++) wtot[wid][i] = tot[i];
+  }
+  __syncthreads();
+  double carry[D];                                            // state at the start of this warp (block start state: zero)
+#pragma unroll
+  for (int i = 0; i < D; i++) carry[i] = 0.0;
+  for (int w2 = 0; w2 < wid; w2++) {
+    double nx[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { double a = wtot[w2][i];
+#pragma unroll
+      for (int q = 0; q < D; q++) a = fma(__ldg(pw + 5 * D * D + i * D + q), carry[q], a);
+      nx[i] = a; }
+#pragma unroll
+    for (int i = 0; i < D; i++) carry[i] = nx[i];
+  }
+  if (lane == 0) {                                            // the warp's carry-in enters through its first sub-chunk
+#pragma unroll
+    for (int i = 0; i < D; i++) { double a = rsp[i];
+#pragma unroll
+      for (int q = 0; q < D; q++) a = fma(__ldg(pw + i * D + q), carry[q], a);
+      rsp[i] = a; }
+  }
+  warp_scan(rsp);                                             // inclusive: state at the end of sub-chunk tid
+  double xs[D];                                               // state at the start of sub-chunk tid
+#pragma unroll
+  for (int i = 0; i < D; i++) { xs[i] = __shfl_up_sync(0xffffffffu, rsp[i], 1); if (lane == 0) xs[i] = carry[i]; }
+  // phase 3: payload sub-chunks restart from their start state and emit
+  double a2 = 0.0;
+  if (pay) {
+    double x[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) x[i] = injected ? inject[i] : xs[i];
+    double* rw = ysm + tid * (SS2_LS + 1);
+#pragma unroll 8
+    for (int j = 0; j < SS2_LS; j++) {
+      if (j < nv) {
+        const double yv = rw[j];
+        double pred = 0.0, nx[D];
+#pragma unroll
+        for (int q = 0; q < D; q++) pred = fma(ha[q], x[q], pred);
+        const double a = (yv - pred) * rs;
+        a2 = fma(a, a, a2);
+        rw[j] = a;
+#pragma unroll
+        for (int i = 0; i < D; i++) { double v = Kg[i] * yv;
+#pragma unroll
+          for (int q = 0; q < D; q++) v = fma(Phi[i * D + q], x[q], v);
+          nx[i] = v; }
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = nx[i];
+      }
+    }
+  }
+  __syncthreads();
+  if (alpha) {
+    double* ab = alpha + (int64_t)b * ystride;
+    for (int e2 = (HEAD ? 0 : W) + tid; e2 < SS2_STEPS; e2 += SS2_THREADS) {
+      const int64_t k = load_start + e2;
+      if (k < N) ab[k] = ysm[e2 + e2 / SS2_LS];
+    }
+  }
+  const double a2tot = block_sum(a2, red);
+  if (tid == 0) {
+    part[((int64_t)b * nseg + seg) * 2] = HEAD ? trsum[0] : 0.0;
+    part[((int64_t)b * nseg + seg) * 2 + 1] = a2tot + (HEAD ? trsum[1] : 0.0);
+  }
+}
+
+template <int D>
+__global__ void ss2_flags_kernel(const double* __restrict__ cst, int batch, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double ok = 1.0;
+  for (int b = 0; b < batch; b++) if (cst[(int64_t)b * SS2Layout<D>::SIZE + SS2Layout<D>::OK] != 1.0) ok = 0.0;
+  out[0] = ok;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+ss2_finish_kernel(const double* __restrict__ part, int nseg, const double* __restrict__ cst, int64_t N, int W, double* __restrict__ lml,
+                  double* __restrict__ sums) {
+  typedef SS2Layout<D> SL;
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  const double* c = cst + (int64_t)b * SL::SIZE;
+  const int64_t kstar = (int64_t)c[SL::KSTAR];
+  const int payload = SS2_STEPS - W;
+  const int64_t used = N <= SS2_STEPS ? 1 : 1 + (N - SS2_STEPS + payload - 1) / payload;     // blocks that did work
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t sg = threadIdx.x; sg < used && sg < nseg; sg += blockDim.x) { a0 += part[((int64_t)b * nseg + sg) * 2]; a1 += part[((int64_t)b * nseg + sg) * 2 + 1]; }
+  const double r0 = block_sum(a0, sh);
+  const double r1 = block_sum(a1, sh);
+  if (threadIdx.x == 0) {
+    const double slog = r0 + (double)(N > kstar ? N - kstar : 0) * c[SL::ROW + D * D + 2 * D + 1];
+    if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + slog + r1);
+    if (sums) { sums[2 * b] = slog; sums[2 * b + 1] = r1; }
+  }
+}
+
+template <int D>
+int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* y, const LgssmOut& o, bool* used) {
+  typedef SS2Layout<D> SL;
+  *used = false;
+  if (!(sp.reg_dt > 0.0) || batch > 16 || N < 32 * (int64_t)SS2_STEPS || o.mean || o.table || o.dlml || o.dalpha || o.dtable) return GPAR_OK;
+  if (const char* e = getenv("GPAR_KF_STEADY")) { if (atoi(e) != 1 && atoi(e) != 3) return GPAR_OK; }   // 0: off, 2: two-pass only
+  if (ctx->ss_skip > 0 || !ctx->ss_deferred_ok) return GPAR_OK;   // (ss_skip is decremented by the two-pass path's own check)
+  CU(ctx->kal_f.reserve(((size_t)batch * (SL::SIZE + SS2_STEPS) + 8) * sizeof(double)));
+  double* cst = ctx->kal_f.as<double>(); double* scratchS = cst + (size_t)batch * SL::SIZE;
+  LAUNCH(ctx, ss2_setup_kernel<D>, (batch + 31) / 32, 32, 0, sp, batch, cst);
+  // Fixed burn-in of SS2_WFIX steps (14 % re-reads): the grid layout then does not depend on the model, so no
+  // host round trip separates the set-up from the main pass; a model that needs more (or whose covariance
+  // has not settled) is FLAGGED by the kernels and the caller falls back after its own final synchronisation.
+  const int W = SS2_WFIX;
+  const int payload = SS2_STEPS - W;
+  const int nseg = (int)(1 + (N - SS2_STEPS + payload - 1) / payload);
+  CU(ctx->kal_b.reserve((size_t)batch * nseg * 2 * sizeof(double)));
+  double* part = ctx->kal_b.as<double>();
+  const size_t smem = (size_t)(SS2_STEPS + SS2_THREADS) * sizeof(double);
+  CU(cudaFuncSetAttribute((ss2_main_kernel<D, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute((ss2_main_kernel<D, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ystride = o.ystride > 0 ? o.ystride : N;
+  // the head blocks (sequential transient) on the side stream, underneath all the other blocks
+  cudaStream_t main_stream = ctx->stream;
+  CU(cudaEventRecord(ctx->ev_fork, main_stream));
+  CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  ctx->stream = ctx->stream2;
+  int rc = [&]() -> int {
+    LAUNCH(ctx, (ss2_main_kernel<D, true>), dim3(1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
+    return GPAR_OK;
+  }();
+  cudaEventRecord(ctx->ev_side, ctx->stream2);
+  ctx->stream = main_stream;
+  CHK(rc);
+  if (nseg > 1) LAUNCH(ctx, (ss2_main_kernel<D, false>), dim3(nseg - 1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+  LAUNCH(ctx, ss2_finish_kernel<D>, batch, 256, 0, part, nseg, cst, N, W, o.lml, o.sums);
+  // flags (set-up: doubling converged / burn-in long enough; head block: transient settled) go to pinned host
+  // memory WITHOUT a synchronisation: lgssm_steady_failed() reads them after the caller's final sync
+  if (!ctx->pinned) { CU(cudaMallocHost(&ctx->pinned, 4096)); ctx->pinned_cap = 4096; }
+  LAUNCH(ctx, ss2_flags_kernel<D>, 1, 32, 0, cst, batch, ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS));
+  CU(cudaMemcpyAsync(ctx->pinned, ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->ss_pending = true;
+  *used = true;
+  return GPAR_OK;
+}
+
 constexpr int64_t SS_KTR = 2048;       // steps given to the general scan before the hand-over
 
 // Returns GPAR_OK and *used = true when every sequence had converged at the hand-over (results are then
@@ -802,7 +1247,7 @@ int lgssm_run_steady(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const do
   typedef AffineElem<D> AE;
   *used = false;
   if (!(sp.reg_dt > 0.0) || N < 4 * SS_KTR || o.mean || o.table || o.dlml || o.dalpha || o.dtable) return GPAR_OK;
-  if (const char* e = getenv("GPAR_KF_STEADY")) { if (atoi(e) == 0) return GPAR_OK; }
+  if (const char* e = getenv("GPAR_KF_STEADY")) { if (atoi(e) != 2 && atoi(e) != 3) return GPAR_OK; }   // 0: off, 1: single-pass only
   if (ctx->ss_skip > 0) { ctx->ss_skip--; return GPAR_OK; }
   const int64_t Ns = N - SS_KTR;
   // chunk length (multiple of 32): a block's time grows with L and the grid runs in ceil(blocks / resident) waves
@@ -878,6 +1323,13 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
   LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums;
   if (!rvec && sp.reg_dt > 0.0) {       // regular grid, scalar noise: steady-state path when every model converges early
     bool used = false;
+    switch (kind) {      // long sequences: single-pass burn-in scheme
+      case GPAR_MATERN12: CHK(lgssm_run_steady_long<1>(ctx, sp, batch, N, y, o, &used)); break;
+      case GPAR_MATERN32: CHK(lgssm_run_steady_long<2>(ctx, sp, batch, N, y, o, &used)); break;
+      case GPAR_MATERN52: CHK(lgssm_run_steady_long<3>(ctx, sp, batch, N, y, o, &used)); break;
+      default: break;
+    }
+    if (used) return GPAR_OK;
     switch (kind) {
       case GPAR_MATERN12: CHK(lgssm_run_steady<1>(ctx, sp, batch, N, t, y, o, &used)); break;
       case GPAR_MATERN32: CHK(lgssm_run_steady<2>(ctx, sp, batch, N, t, y, o, &used)); break;
@@ -917,6 +1369,14 @@ int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* h
 }
 
 namespace {
+// After the caller's final stream synchronisation: did the steady-state path flag a model it cannot handle?
+bool lgssm_steady_failed(gpar_ctx* ctx) {
+  if (!ctx->ss_pending) return false;
+  ctx->ss_pending = false;
+  if (*reinterpret_cast<const double*>(ctx->pinned) == 1.0) return false;
+  ctx->ss_skip = 8;                 // general path now, and for the next calls
+  return true;
+}
 int check_seq(gpar_ctx* ctx, const char* who) {
   if (ctx->Nt < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: times not set (gpar_set_times)", who);
   if (ctx->ybatch < 1 || ctx->Ny != ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "%s: outputs length %lld != number of times %lld", who, (long long)ctx->Ny, (long long)ctx->Nt);
@@ -938,11 +1398,17 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
   for (int b = 0; b < batch_theta; b++) { GpParams p = unpack_gp3(theta + 3 * b); hl[b] = p.l; hs[b] = p.s; hn[b] = p.noise; }
   CU(ctx->kal_d.reserve((size_t)batch * sizeof(double)));
-  CHK(lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
-                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr));
-  timer.stop();
-  CU(cudaMemcpyAsync(lml, ctx->kal_d.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  for (int attempt = 0; attempt < 2; attempt++) {      // a second pass only when the steady-state path flagged a model it cannot handle
+    ctx->ss_deferred_ok = true;
+    int rc = lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
+                       ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr);
+    ctx->ss_deferred_ok = false;
+    CHK(rc);
+    timer.stop();
+    CU(cudaMemcpyAsync(lml, ctx->kal_d.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!lgssm_steady_failed(ctx)) break;
+  }
   return GPAR_OK;
 }
 
@@ -994,12 +1460,18 @@ int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], dou
   GpParams p = unpack_gp3(theta);
   CU(ctx->kal_d.reserve(((size_t)batch * N + batch) * sizeof(double)));
   double* d_alpha = ctx->kal_d.as<double>(); double* d_lml = d_alpha + (size_t)batch * N;
-  CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
-                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml, nullptr, nullptr, nullptr, nullptr));
-  timer.stop();
-  CU(cudaMemcpyAsync(alpha, d_alpha, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (lml) CU(cudaMemcpyAsync(lml, d_lml, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  for (int attempt = 0; attempt < 2; attempt++) {      // see gpar_lgssm_logpdf
+    ctx->ss_deferred_ok = true;
+    int rc = lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                       ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml, nullptr, nullptr, nullptr, nullptr);
+    ctx->ss_deferred_ok = false;
+    CHK(rc);
+    timer.stop();
+    CU(cudaMemcpyAsync(alpha, d_alpha, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (lml) CU(cudaMemcpyAsync(lml, d_lml, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!lgssm_steady_failed(ctx)) break;
+  }
   return GPAR_OK;
 }
 

@@ -284,6 +284,40 @@ def test_lgssm_steady_state_path(ctx, kind):
     ctx.set_times(t)
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_lgssm_steady_state_single_pass_long_sequences(ctx, kind):
+    """Few long sequences on a regular grid (N >= 262 144): Riccati transient tabulated by the set-up
+    kernel, then ONE pass with burn-in blocks.  lml 1e-8 / alpha 1e-8 against the sequential C oracle,
+    1e-11 / 1e-10 against the general scan; a slow model (l = e^6) falls back and is still right."""
+    rng = np.random.default_rng(90 + kind)
+    n, batch, dt = 300_017, 2, 1 / 30
+    t = dt * np.arange(n)
+    Y = rng.normal(size=(batch, n))
+    ths = np.array([[0.0, 0.0, -2.0], [-1.0, 0.5, -0.5]])
+    pp = np.exp(ths) + 1e-3
+    ctx.set_times_range(0.0, dt, n); ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    lml = ctx.lgssm_logpdf(kind, ths)
+    lml0 = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2)
+    assert relerr(lml, lml0) <= RTOL
+    lml_s, alpha = ctx.lgssm_decorrelate(kind, ths[1])
+    l0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[1, 0], pp[1, 1] ** 2, pp[1, 2] ** 2, want_alpha=True)
+    assert relerr(lml_s, l0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
+    os.environ["GPAR_KF_STEADY"] = "0"
+    try:
+        lml_g = ctx.lgssm_logpdf(kind, ths)
+        _, alpha_g = ctx.lgssm_decorrelate(kind, ths[1])
+    finally:
+        del os.environ["GPAR_KF_STEADY"]
+    assert relerr(lml, lml_g) <= 1e-11 and np.max(np.abs(alpha - alpha_g)) <= 1e-10
+    slow = ths.copy(); slow[0, 0] = 6.0
+    pps = np.exp(slow) + 1e-3
+    lml = ctx.lgssm_logpdf(kind, slow)
+    assert relerr(lml, cport.kalman_filter_batch(kind, t, Y, pps[:, 0], pps[:, 1] ** 2, pps[:, 2] ** 2)) <= RTOL
+    for _ in range(9):
+        ctx.lgssm_logpdf(kind, ths)
+    ctx.set_times(t[:10])
+
+
 def test_lgssm_full_size_config3(ctx):
     """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
     and one 10M-step sequence; every lml against the C oracle."""
