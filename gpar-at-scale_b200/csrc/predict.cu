@@ -13,28 +13,30 @@
 #include <algorithm>
 
 namespace {
-constexpr int SCHUNK = 8;
 
-template <int KIND>
+// fx[s][n] = sum_m k(x*_n, z_m) W[m][s], ys = y* - fx.  One thread per location n; a block-y covers SC samples so
+// that every kernel value (one exp, ~50 FP64 slots) feeds SC FMAs — SC is chosen per call to minimise
+// ceil(S / SC) (50 + SC) (S = 100 -> SC = 50: k is evaluated twice per location, not thirteen times as with 8).
+template <int KIND, int SC>
 __global__ void __launch_bounds__(128)
 fx_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int DX, double inv_l2, double s_out,
           const double* __restrict__ W, int S, const double* __restrict__ y, double* __restrict__ fx, double* __restrict__ ys) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double* zs = sm;                    // 128 x DX
-  double* ws = sm + 128 * DX;         // 128 x SCHUNK
+  double* ws = sm + 128 * DX;         // 128 x SC (SC even): 16-byte aligned for the double2 reads
   const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  const int s0 = blockIdx.y * SCHUNK;
-  double acc[SCHUNK];
+  const int s0 = blockIdx.y * SC;
+  double acc[SC];
 #pragma unroll
-  for (int j = 0; j < SCHUNK; j++) acc[j] = 0.0;
+  for (int j = 0; j < SC; j++) acc[j] = 0.0;
   double x[8];
   for (int d = 0; d < DX; d++) x[d] = n < N ? X[n * DX + d] : 0.0;
   for (int m0 = 0; m0 < M; m0 += 128) {
     const int mc = min(128, M - m0);
     __syncthreads();
     for (int e = threadIdx.x; e < mc * DX; e += 128) zs[e] = Z[(int64_t)m0 * DX + e];
-    for (int e = threadIdx.x; e < mc * SCHUNK; e += 128) {
-      int mm = e / SCHUNK, j = e % SCHUNK;
+    for (int e = threadIdx.x; e < mc * SC; e += 128) {
+      int mm = e / SC, j = e % SC;
       ws[e] = (s0 + j < S) ? W[(int64_t)(s0 + j) * M + m0 + mm] : 0.0;
     }
     __syncthreads();
@@ -42,15 +44,32 @@ fx_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N,
       double d2 = 0.0;
       for (int d = 0; d < DX; d++) { double df = x[d] - zs[mm * DX + d]; d2 = fma(df, df, d2); }
       double dummy; const double k = s_out * base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
+      const double2* w2 = reinterpret_cast<const double2*>(ws + mm * SC);
 #pragma unroll
-      for (int j = 0; j < SCHUNK; j++) acc[j] = fma(k, ws[mm * SCHUNK + j], acc[j]);
+      for (int j = 0; j < SC / 2; j++) { const double2 w = w2[j]; acc[2 * j] = fma(k, w.x, acc[2 * j]); acc[2 * j + 1] = fma(k, w.y, acc[2 * j + 1]); }
     }
   }
   if (n >= N) return;
   const double yn = y[n];
 #pragma unroll
-  for (int j = 0; j < SCHUNK; j++)
+  for (int j = 0; j < SC; j++)
     if (s0 + j < S) { fx[(int64_t)(s0 + j) * N + n] = acc[j]; ys[(int64_t)(s0 + j) * N + n] = yn - acc[j]; }
+}
+
+template <int KIND>
+int launch_fx(gpar_ctx* ctx, const double* X, const double* Z, int64_t N, int M, int DX, double inv_l2, double s_out,
+              const double* W, int S, const double* y, double* fx, double* ys) {
+  const int cands[4] = {8, 16, 32, 50};
+  int SC = 8; long best = -1;
+  for (int c : cands) { const long cost = (long)((S + c - 1) / c) * (50 + c); if (best < 0 || cost < best) { best = cost; SC = c; } }
+  dim3 grid((unsigned)((N + 127) / 128), (S + SC - 1) / SC);
+  const size_t smem = (size_t)(128 * DX + 128 * SC) * sizeof(double);
+#define FXCASE(C) case C: \
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute((fx_kernel<KIND, C>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    LAUNCH(ctx, (fx_kernel<KIND, C>), grid, 128, smem, X, Z, N, M, DX, inv_l2, s_out, W, S, y, fx, ys); break;
+  switch (SC) { FXCASE(8) FXCASE(16) FXCASE(32) FXCASE(50) }
+#undef FXCASE
+  return GPAR_OK;
 }
 
 // mean_n = mean_s(fx + sm), std_n = corrected sample std (Julia `std`), 0 for S == 1
@@ -88,15 +107,13 @@ extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const d
   if (W) CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   else CU(cudaMemcpyAsync(dW, ctx->qW.p, (size_t)M * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CallTimer timer(ctx); ctx->phase_valid = false;
-  dim3 grid((unsigned)((N + 127) / 128), (S + SCHUNK - 1) / SCHUNK);
-  const size_t smem = (size_t)128 * (DX + SCHUNK) * sizeof(double);
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>(); const double* y = ctx->y.as<double>();
   switch (k_out) {
-    case GPAR_EQ: LAUNCH(ctx, fx_kernel<GPAR_EQ>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
-    case GPAR_MATERN12: LAUNCH(ctx, fx_kernel<GPAR_MATERN12>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
-    case GPAR_MATERN32: LAUNCH(ctx, fx_kernel<GPAR_MATERN32>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
-    case GPAR_MATERN52: LAUNCH(ctx, fx_kernel<GPAR_MATERN52>, grid, 128, smem, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys); break;
+    case GPAR_EQ: CHK(launch_fx<GPAR_EQ>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
+    case GPAR_MATERN12: CHK(launch_fx<GPAR_MATERN12>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
+    case GPAR_MATERN32: CHK(launch_fx<GPAR_MATERN32>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
+    case GPAR_MATERN52: CHK(launch_fx<GPAR_MATERN52>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
   }
   CHK(lgssm_run(ctx, k_time, &time_l, &time_s, &noise, 1, S, N, ctx->t.as<double>(), ys, ctx->has_rvec ? ctx->rvec.as<double>() : nullptr,
