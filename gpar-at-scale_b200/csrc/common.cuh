@@ -63,6 +63,7 @@ struct gpar_ctx {
   // merged train+test problem (gpar_set_merged): staging, position of every test point in the sorted arrays,
   // and the device arrays of the last smoother / prediction result (for gpar_take_test)
   DevBuf mrg, test_pos; int64_t merged_N = 0, merged_Ns = 0; const double* res_a = nullptr; const double* res_b = nullptr; int64_t res_len = 0;
+  DevBuf shbuf;                       // shared-model smoother: tables, chunk states, filtered means (smooth_shared.cu)
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   void* pinned = nullptr; size_t pinned_cap = 0;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
@@ -183,6 +184,11 @@ int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* h
 // scaled.cu: e = a - panel w (panel in the operand layout), and rows [4 g_lo, 4 (g_lo + ng)) of a panel as a dense M x 4ng matrix
 int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, const double* a, int64_t N, int64_t NB4, int T, int M, double* e);
 int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* Bt);
+// smooth_shared.cu: smoothed means of Sp (multiple of 128) TIME-MAJOR sequences yt[n][Sp] that share one model
+int lgssm_smooth_shared(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, const double* t, const double* y1,
+                        const double* rvec, const double* yt, int Sp, double* mean_t);
+int lgssm_smooth_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
+                                 const double* y, const double* rvec, double* d_mean, double* d_var, double* d_lml);
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;

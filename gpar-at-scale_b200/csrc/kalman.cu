@@ -387,7 +387,7 @@ __global__ void smooth_pad_kernel(Level s0, int nC, int batch) {
 template <int D>
 __global__ void __launch_bounds__(128)
 ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L, int nC, Level s0, Level s1, int batch,
-                   const double* __restrict__ fs, double* __restrict__ mean, double* __restrict__ var) {
+                   const double* __restrict__ fs, double* __restrict__ mean, double* __restrict__ var, double* __restrict__ table2) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= nC) return;
   const int pb = sp.nparam == 1 ? 0 : b;
@@ -405,6 +405,10 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) Ps[i] = fsb[((int64_t)(D + i) * L + (k - k0)) * 32];
     mean[(int64_t)b * N + k] = ms[0]; var[(int64_t)b * N + k] = Ps[0];
+    if (table2) {      // last step: m^s_N = m_N  (B = I, G = 0)
+#pragma unroll
+      for (int i = 0; i < D * D; i++) { table2[k * 2 * D * D + i] = (i / D == i % D) ? 1.0 : 0.0; table2[k * 2 * D * D + D * D + i] = 0.0; }
+    }
     k--;
   } else {
     SmoothElem<D> suf = inclusive_prefix<SmoothElem<D>>(s0, s1, batch, b, nC - 2 - c);
@@ -430,6 +434,12 @@ ks_backward_kernel(const double* __restrict__ t, SeqParams sp, int64_t N, int L,
         for (int q = 0; q < D; q++) v = fma(SYM(P, i, q), A[j * D + q], v);
         W[i * D + j] = v; }
     solve_spd_right<D>(W, Pp, kSmoothJitter, G);
+    if (table2) {      // shared-model smoothing of further sequences: m^s_k = B_k m_k + G_k m^s_{k+1},  B_k = I - G_k A_{k+1}
+      double GA[D * D];
+      matmul<D>(G, A, GA);
+#pragma unroll
+      for (int i = 0; i < D * D; i++) { table2[k * 2 * D * D + i] = ((i / D == i % D) ? 1.0 : 0.0) - GA[i]; table2[k * 2 * D * D + D * D + i] = G[i]; }
+    }
     double dm[D], dP[NSYM<D>], u[D], R[NSYM<D>];
 #pragma unroll
     for (int i = 0; i < D; i++) dm[i] = ms[i] - mp[i];
@@ -580,7 +590,7 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
              (double*)nullptr, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr);
       if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
       CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
-      LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var);
+      LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var, o.table);     // (smoother: o.table = backward table)
     } else {
       LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
              o.table, (double*)nullptr, (double*)nullptr, ystride, o.fstate);
@@ -1485,8 +1495,16 @@ int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* 
   GpParams p = unpack_gp3(theta);
   CU(ctx->kal_d.reserve((2 * (size_t)batch * N + batch) * sizeof(double)));
   double* d_mean = ctx->kal_d.as<double>(); double* d_var = d_mean + (size_t)batch * N; double* d_lml = d_var + (size_t)batch * N;
-  CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
-                ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, d_lml, d_mean, d_var, nullptr, nullptr));
+  // several sequences always share theta here: covariances and gains once, then two affine passes per sequence
+  bool shared_path = batch >= 4;
+  if (const char* e = getenv("GPAR_SMOOTH_SHARED")) shared_path = atoi(e) != 0 && batch >= 2;      // tuning / testing knob
+  if (shared_path) {
+    CHK(lgssm_smooth_shared_seqmajor(ctx, kernel, p.l, p.s, p.noise, N, batch, ctx->t.as<double>(), ctx->y.as<double>(),
+                                     ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_mean, d_var, d_lml));
+  } else {
+    CHK(lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                  ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, d_lml, d_mean, d_var, nullptr, nullptr));
+  }
   timer.stop();
   ctx->res_a = d_mean; ctx->res_b = d_var; ctx->res_len = (int64_t)batch * N;      // stays resident for gpar_take_test
   if (mean) {

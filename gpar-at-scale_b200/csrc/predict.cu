@@ -20,7 +20,7 @@ namespace {
 template <int KIND, int SC>
 __global__ void __launch_bounds__(128)
 fx_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int DX, double inv_l2, double s_out,
-          const double* __restrict__ W, int S, const double* __restrict__ y, double* __restrict__ fx, double* __restrict__ ys) {
+          const double* __restrict__ W, int S, const double* __restrict__ y, double* __restrict__ fx, double* __restrict__ ys, int Sp) {
   extern __shared__ __align__(16) double sm[];
   double* zs = sm;                    // 128 x DX
   double* ws = sm + 128 * DX;         // 128 x SC (SC even): 16-byte aligned for the double2 reads
@@ -53,12 +53,12 @@ fx_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N,
   const double yn = y[n];
 #pragma unroll
   for (int j = 0; j < SC; j++)
-    if (s0 + j < S) { fx[(int64_t)(s0 + j) * N + n] = acc[j]; ys[(int64_t)(s0 + j) * N + n] = yn - acc[j]; }
+    if (s0 + j < S) { fx[n * Sp + s0 + j] = acc[j]; ys[n * Sp + s0 + j] = yn - acc[j]; }      // time-major [n][Sp]
 }
 
 template <int KIND>
 int launch_fx(gpar_ctx* ctx, const double* X, const double* Z, int64_t N, int M, int DX, double inv_l2, double s_out,
-              const double* W, int S, const double* y, double* fx, double* ys) {
+              const double* W, int S, const double* y, double* fx, double* ys, int Sp) {
   const int cands[4] = {8, 16, 32, 50};
   int SC = 8; long best = -1;
   for (int c : cands) { const long cost = (long)((S + c - 1) / c) * (50 + c); if (best < 0 || cost < best) { best = cost; SC = c; } }
@@ -66,24 +66,29 @@ int launch_fx(gpar_ctx* ctx, const double* X, const double* Z, int64_t N, int M,
   const size_t smem = (size_t)(128 * DX + 128 * SC) * sizeof(double);
 #define FXCASE(C) case C: \
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute((fx_kernel<KIND, C>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    LAUNCH(ctx, (fx_kernel<KIND, C>), grid, 128, smem, X, Z, N, M, DX, inv_l2, s_out, W, S, y, fx, ys); break;
+    LAUNCH(ctx, (fx_kernel<KIND, C>), grid, 128, smem, X, Z, N, M, DX, inv_l2, s_out, W, S, y, fx, ys, Sp); break;
   switch (SC) { FXCASE(8) FXCASE(16) FXCASE(32) FXCASE(50) }
 #undef FXCASE
   return GPAR_OK;
 }
 
-// mean_n = mean_s(fx + sm), std_n = corrected sample std (Julia `std`), 0 for S == 1
-__global__ void mc_reduce_kernel(const double* __restrict__ fx, const double* __restrict__ smean, int64_t N, int S,
-                                 double* __restrict__ mean, double* __restrict__ sd) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// mean_n = mean_s(fx + sm), std_n = corrected sample std (Julia `std`), 0 for S == 1; fx, smean time-major [n][Sp].
+// One warp per location: coalesced row reads, fixed-order shuffle sums.
+__global__ void __launch_bounds__(256)
+mc_reduce_kernel(const double* __restrict__ fx, const double* __restrict__ smean, int64_t N, int S, int Sp,
+                 double* __restrict__ mean, double* __restrict__ sd) {
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (n >= N) return;
+  const double* a = fx + n * Sp; const double* b = smean + n * Sp;
   double m = 0.0;
-  for (int s = 0; s < S; s++) m += fx[(int64_t)s * N + n] + smean[(int64_t)s * N + n];
+  for (int s = lane; s < S; s += 32) m += a[s] + b[s];
+  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
   m /= S;
   double v = 0.0;
-  for (int s = 0; s < S; s++) { double d = fx[(int64_t)s * N + n] + smean[(int64_t)s * N + n] - m; v = fma(d, d, v); }
-  mean[n] = m;
-  sd[n] = S > 1 ? sqrt(v / (S - 1)) : 0.0;
+  for (int s = lane; s < S; s += 32) { const double d = a[s] + b[s] - m; v = fma(d, d, v); }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) { mean[n] = m; sd[n] = S > 1 ? sqrt(v / (S - 1)) : 0.0; }
 }
 }  // namespace
 
@@ -100,25 +105,28 @@ extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const d
   CU(cudaSetDevice(ctx->device));
   const int64_t N = ctx->N; const int M = (int)ctx->M, DX = ctx->D;
   const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
-  // fx | ys | smoothed mean | smoothed var | lml | mean | sd | W
-  CU(ctx->kal_e.reserve(((size_t)4 * S * N + S + 2 * (size_t)N + (size_t)M * S) * sizeof(double)));
-  double* fx = ctx->kal_e.as<double>(); double* ys = fx + (size_t)S * N; double* smean = ys + (size_t)S * N;
-  double* svar = smean + (size_t)S * N; double* lml = svar + (size_t)S * N; double* dmean = lml + S; double* dsd = dmean + N; double* dW = dsd + N;
+  // time-major, S padded to a multiple of 128: fx | ys | smoothed means ; then mean | sd | W
+  const int Sp = (S + 127) / 128 * 128;
+  CU(ctx->kal_e.reserve(((size_t)3 * Sp * N + 2 * (size_t)N + (size_t)M * S) * sizeof(double)));
+  double* fx = ctx->kal_e.as<double>(); double* ys = fx + (size_t)Sp * N; double* smean = ys + (size_t)Sp * N;
+  double* dmean = smean + (size_t)Sp * N; double* dsd = dmean + N; double* dW = dsd + N;
   if (W) CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   else CU(cudaMemcpyAsync(dW, ctx->qW.p, (size_t)M * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CallTimer timer(ctx); ctx->phase_valid = false;
+  if (Sp != S) CU(cudaMemsetAsync(fx, 0, (size_t)2 * Sp * N * sizeof(double), ctx->stream));      // padding sequences: zero data
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>(); const double* y = ctx->y.as<double>();
   switch (k_out) {
-    case GPAR_EQ: CHK(launch_fx<GPAR_EQ>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
-    case GPAR_MATERN12: CHK(launch_fx<GPAR_MATERN12>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
-    case GPAR_MATERN32: CHK(launch_fx<GPAR_MATERN32>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
-    case GPAR_MATERN52: CHK(launch_fx<GPAR_MATERN52>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys)); break;
+    case GPAR_EQ: CHK(launch_fx<GPAR_EQ>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys, Sp)); break;
+    case GPAR_MATERN12: CHK(launch_fx<GPAR_MATERN12>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys, Sp)); break;
+    case GPAR_MATERN32: CHK(launch_fx<GPAR_MATERN32>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys, Sp)); break;
+    case GPAR_MATERN52: CHK(launch_fx<GPAR_MATERN52>(ctx, X, Z, N, M, DX, inv_l2, out_s, dW, S, y, fx, ys, Sp)); break;
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
   }
-  CHK(lgssm_run(ctx, k_time, &time_l, &time_s, &noise, 1, S, N, ctx->t.as<double>(), ys, ctx->has_rvec ? ctx->rvec.as<double>() : nullptr,
-                nullptr, lml, smean, svar, nullptr, nullptr));
-  LAUNCH(ctx, mc_reduce_kernel, (unsigned)((N + 255) / 256), 256, 0, fx, smean, N, S, dmean, dsd);
+  // the S residual sequences share the LGSSM: gains and smoother gains once, then two affine passes per sequence
+  CHK(lgssm_smooth_shared(ctx, k_time, time_l, time_s, noise, N, ctx->t.as<double>(), y, ctx->has_rvec ? ctx->rvec.as<double>() : nullptr,
+                          ys, Sp, smean));
+  LAUNCH(ctx, mc_reduce_kernel, (unsigned)((N + 7) / 8), 256, 0, fx, smean, N, S, Sp, dmean, dsd);
   timer.stop();
   ctx->res_a = dmean; ctx->res_b = dsd; ctx->res_len = N;      // stays resident for gpar_take_test
   if (mean) {

@@ -318,6 +318,37 @@ def test_lgssm_steady_state_single_pass_long_sequences(ctx, kind):
     ctx.set_times(t[:10])
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+@pytest.mark.parametrize("n,batch", [(1, 4), (50, 5), (1025, 7), (3000, 130)])
+def test_lgssm_smooth_shared_model_path(ctx, kind, n, batch):
+    """gpar_lgssm_smooth with >= 4 sequences runs the shared-model scheme (covariances and smoother gains once, two
+    affine passes per sequence): mean / var / lml against the sequential C oracle and against the general scan
+    (GPAR_SMOOTH_SHARED=0), with and without a noise vector, including a duplicated time stamp."""
+    rng = np.random.default_rng(300 * kind + n + batch)
+    t = np.cumsum(rng.exponential(1 / 30, n))
+    if n > 40:
+        t[n // 2] = t[n // 2 - 1]
+    Y = rng.normal(size=(batch, n))
+    rv = np.where(rng.uniform(size=n) < 0.1, 1e10, 0.09)
+    th = rng.uniform(-1.0, 0.5, 3); pp = np.exp(th) + 1e-3
+    ctx.set_times(t); ctx.set_outputs(Y)
+    for rvec in (None, rv):
+        ctx.set_noise_vector(rvec)
+        lml, mean, var = ctx.lgssm_smooth(kind, th)
+        l0, m0, v0 = cport.kalman_smooth_batch(kind, t, Y, pp[0], pp[1] ** 2, rvec if rvec is not None else pp[2] ** 2)
+        assert relerr(lml, l0) <= RTOL
+        assert np.max(np.abs(mean - m0)) <= 1e-8 * max(1.0, np.max(np.abs(m0)))
+        assert np.max(np.abs(var - v0) / v0) <= 1e-7
+        os.environ["GPAR_SMOOTH_SHARED"] = "0"
+        try:
+            lml_g, mean_g, var_g = ctx.lgssm_smooth(kind, th)
+        finally:
+            del os.environ["GPAR_SMOOTH_SHARED"]
+        assert relerr(lml, lml_g) <= 1e-11 and np.max(np.abs(mean - mean_g)) <= 1e-9 * max(1.0, np.max(np.abs(mean_g)))
+        assert np.max(np.abs(var - var_g) / var_g) <= 1e-9
+    ctx.set_noise_vector(None)
+
+
 def test_lgssm_full_size_config3(ctx):
     """BASELINE config 3 at full size: 1024 sequences x 10 000 steps, independent Matern-5/2 models,
     and one 10M-step sequence; every lml against the C oracle."""
