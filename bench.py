@@ -207,6 +207,8 @@ def run_ours(args):
                 fn(); out.append(ctx.last_timing()[0])
             return float(np.median(out[skip:]))
         extra["kalman_logpdf_grad_ms_1024x10k"] = med_ms(lambda: ctx.lgssm_logpdf_grad(gp.MATERN52, ths), 4, 1)
+        # the same 1024 sequences under ONE model (batching over data, the reference's M+1-column / MC-sample pattern)
+        extra["kalman_filter_shared_model_steps_per_s"] = B * NK / med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths[0])) * 1e3
         # the same batch on the regular grid range(0, step = 1/30) (toy_data.jl:6): steady-state path
         ctx.set_times_range(0.0, 1 / 30, NK)
         ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths))

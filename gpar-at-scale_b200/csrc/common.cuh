@@ -189,6 +189,8 @@ int lgssm_smooth_shared(gpar_ctx* ctx, int kind, double l, double s, double nois
                         const double* rvec, const double* yt, int Sp, double* mean_t);
 int lgssm_smooth_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
                                  const double* y, const double* rvec, double* d_mean, double* d_var, double* d_lml);
+int lgssm_filter_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
+                                 const double* y, const double* rvec, double* d_alpha, double* d_lml);
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;

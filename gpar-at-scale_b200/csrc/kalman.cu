@@ -1408,11 +1408,19 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
   for (int b = 0; b < batch_theta; b++) { GpParams p = unpack_gp3(theta + 3 * b); hl[b] = p.l; hs[b] = p.s; hn[b] = p.noise; }
   CU(ctx->kal_d.reserve((size_t)batch * sizeof(double)));
+  bool shared_path = batch_theta == 1 && batch >= 4;      // one model, many sequences: covariance recursion once (smooth_shared.cu)
+  if (const char* e = getenv("GPAR_FILTER_SHARED")) shared_path = shared_path && atoi(e) != 0;
   for (int attempt = 0; attempt < 2; attempt++) {      // a second pass only when the steady-state path flagged a model it cannot handle
-    ctx->ss_deferred_ok = true;
-    int rc = lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
-                       ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr);
-    ctx->ss_deferred_ok = false;
+    int rc;
+    if (shared_path) {
+      rc = lgssm_filter_shared_seqmajor(ctx, kernel, hl[0], hs[0], hn[0], ctx->Nt, batch, ctx->t.as<double>(), ctx->y.as<double>(),
+                                        ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>());
+    } else {
+      ctx->ss_deferred_ok = true;
+      rc = lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
+                     ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr);
+      ctx->ss_deferred_ok = false;
+    }
     CHK(rc);
     timer.stop();
     CU(cudaMemcpyAsync(lml, ctx->kal_d.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1470,11 +1478,19 @@ int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], dou
   GpParams p = unpack_gp3(theta);
   CU(ctx->kal_d.reserve(((size_t)batch * N + batch) * sizeof(double)));
   double* d_alpha = ctx->kal_d.as<double>(); double* d_lml = d_alpha + (size_t)batch * N;
+  bool shared_path = batch >= 4;                          // decorrelate always shares theta
+  if (const char* e = getenv("GPAR_FILTER_SHARED")) shared_path = shared_path && atoi(e) != 0;
   for (int attempt = 0; attempt < 2; attempt++) {      // see gpar_lgssm_logpdf
-    ctx->ss_deferred_ok = true;
-    int rc = lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
-                       ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml, nullptr, nullptr, nullptr, nullptr);
-    ctx->ss_deferred_ok = false;
+    int rc;
+    if (shared_path) {
+      rc = lgssm_filter_shared_seqmajor(ctx, kernel, p.l, p.s, p.noise, N, batch, ctx->t.as<double>(), ctx->y.as<double>(),
+                                        ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml);
+    } else {
+      ctx->ss_deferred_ok = true;
+      rc = lgssm_run(ctx, kernel, &p.l, &p.s, &p.noise, 1, batch, N, ctx->t.as<double>(), ctx->y.as<double>(),
+                     ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, d_alpha, d_lml, nullptr, nullptr, nullptr, nullptr);
+      ctx->ss_deferred_ok = false;
+    }
     CHK(rc);
     timer.stop();
     CU(cudaMemcpyAsync(alpha, d_alpha, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

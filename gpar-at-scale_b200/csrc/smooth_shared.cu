@@ -117,7 +117,8 @@ template <int D, bool FINAL>
 __global__ void __launch_bounds__(128)
 sh_forward_kernel(int64_t N, int LC, const double* __restrict__ table, const double* __restrict__ yt, int Sp,
                   double* __restrict__ state /* [nch][D][Sp]: start states (FINAL) or responses */, double* __restrict__ mst /* [N][D][Sp] */,
-                  double* __restrict__ a2part /* nullable [nch][Sp]: sum alpha^2 of the chunk (FINAL) */) {
+                  double* __restrict__ a2part /* nullable [nch][Sp]: sum alpha^2 of the chunk (FINAL) */,
+                  double* __restrict__ alpha_t /* nullable [N][Sp]: whitened innovations (FINAL) */) {
   constexpr int TS = D * D + 2 * D + 1;
   __shared__ double tbl[2][SH_SUB * TS];
   const int s = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
@@ -143,6 +144,7 @@ sh_forward_kernel(int64_t N, int LC, const double* __restrict__ table, const dou
         for (int j = 0; j < D; j++) pred = fma(r[D * D + D + j], x[j], pred);
         const double a = (yv - pred) * r[D * D + 2 * D];
         a2 = fma(a, a, a2);
+        if (alpha_t) alpha_t[(kw + q) * Sp + s] = a;
       }
 #pragma unroll
       for (int i = 0; i < D; i++) { double v = r[D * D + i] * yv;
@@ -150,7 +152,7 @@ sh_forward_kernel(int64_t N, int LC, const double* __restrict__ table, const dou
         for (int j = 0; j < D; j++) v = fma(r[i * D + j], x[j], v);
         nx[i] = v; }
 #pragma unroll
-      for (int i = 0; i < D; i++) { x[i] = nx[i]; if (FINAL) mst[((kw + q) * D + i) * Sp + s] = nx[i]; }
+      for (int i = 0; i < D; i++) { x[i] = nx[i]; if (FINAL && mst) mst[((kw + q) * D + i) * Sp + s] = nx[i]; }
     }
     __syncthreads();
   }
@@ -226,15 +228,36 @@ int smooth_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
   CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, nullptr, nullptr, table, lml1 + 2));     // lml1[2] = sum log S
   CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, m1, v1, table2, nullptr));
   dim3 grid(Sp / 128, nch);
-  LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, (double*)nullptr);
+  LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, (double*)nullptr, (double*)nullptr);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, false>), nch, 32, 0, table, TS, 0, N, LC, psi);
   LAUNCH(ctx, (sh_carry_kernel<D, false>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
-  LAUNCH(ctx, (sh_forward_kernel<D, true>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, a2part);
+  LAUNCH(ctx, (sh_forward_kernel<D, true>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, a2part, (double*)nullptr);
   LAUNCH(ctx, (sh_backward_kernel<D, false>), grid, 128, 0, N, LC, table2, mst, Sp, state, mean_t);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, true>), nch, 32, 0, table2, TS2, D * D, N, LC, psi);
   LAUNCH(ctx, (sh_carry_kernel<D, true>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
   LAUNCH(ctx, (sh_backward_kernel<D, true>), grid, 128, 0, N, LC, table2, mst, Sp, state, mean_t);
   if (ex) { ex->var1 = v1; ex->sum_logS = lml1 + 2; ex->a2part = a2part; ex->nch = nch; }
+  return GPAR_OK;
+}
+
+// filter only (logpdf / decorrelate of many sequences sharing one model): forward passes, no filtered means stored
+template <int D>
+int filter_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, const double* t, const double* y1,
+                    const double* rvec, const double* yt, int Sp, double* alpha_t, SharedSmoothExtra* ex) {
+  constexpr int TS = D * D + 2 * D + 1;
+  int LC = (int)std::min<int64_t>(1024, std::max<int64_t>(64, ((int64_t)Sp * N / 150000 + 31) / 32 * 32));
+  const int nch = (int)((N + LC - 1) / LC);
+  const size_t state_doubles = (size_t)nch * D * Sp;
+  CU(ctx->shbuf.reserve(((size_t)N * TS + (size_t)nch * D * D + state_doubles + 16 + (size_t)nch * Sp) * sizeof(double)));
+  double* table = ctx->shbuf.as<double>(); double* psi = table + (size_t)N * TS; double* state = psi + (size_t)nch * D * D;
+  double* lml1 = state + state_doubles; double* a2part = lml1 + 16;
+  CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, nullptr, nullptr, table, lml1 + 2));
+  dim3 grid(Sp / 128, nch);
+  LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, (double*)nullptr, (double*)nullptr, (double*)nullptr);
+  LAUNCH(ctx, (sh_chunk_product_kernel<D, false>), nch, 32, 0, table, TS, 0, N, LC, psi);
+  LAUNCH(ctx, (sh_carry_kernel<D, false>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
+  LAUNCH(ctx, (sh_forward_kernel<D, true>), grid, 128, 0, N, LC, table, yt, Sp, state, (double*)nullptr, a2part, alpha_t);
+  ex->var1 = nullptr; ex->sum_logS = lml1 + 2; ex->a2part = a2part; ex->nch = nch;
   return GPAR_OK;
 }
 
@@ -264,7 +287,7 @@ time_to_seq_major_kernel(const double* __restrict__ mt, int64_t N, int batch, in
 __global__ void shared_finish_kernel(const double* __restrict__ var1, const double* __restrict__ sum_logS, const double* __restrict__ a2part,
                                      int nch, int Sp, int64_t N, int batch, double* __restrict__ var, double* __restrict__ lml) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (int64_t)batch * N) var[i] = var1[i % N];
+  if (var && i < (int64_t)batch * N) var[i] = var1[i % N];
   if (lml && i < batch) {
     double a = 0.0;
     for (int c = 0; c < nch; c++) a += a2part[(int64_t)c * Sp + i];
@@ -305,5 +328,26 @@ int lgssm_smooth_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, do
   LAUNCH(ctx, time_to_seq_major_kernel, tg, 256, 0, mt, N, batch, Sp, d_mean);
   const int64_t total = (int64_t)batch * N;
   LAUNCH(ctx, shared_finish_kernel, (unsigned)((total + 255) / 256), 256, 0, ex.var1, ex.sum_logS, ex.a2part, ex.nch, Sp, N, batch, d_var, d_lml);
+  return GPAR_OK;
+}
+
+// logpdf / decorrelate of `batch` sequence-major sequences sharing one model: lml [batch], alpha [batch][N] (nullable).
+int lgssm_filter_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
+                                 const double* y, const double* rvec, double* d_alpha, double* d_lml) {
+  const int Sp = (batch + 127) / 128 * 128;
+  CU(ctx->panelB.reserve((size_t)(d_alpha ? 2 : 1) * N * Sp * sizeof(double)));
+  double* yt = ctx->panelB.as<double>(); double* at = d_alpha ? yt + (size_t)N * Sp : nullptr;
+  dim3 tg((unsigned)((N + 31) / 32), Sp / 32);
+  LAUNCH(ctx, seq_to_time_major_kernel, tg, 256, 0, y, N, batch, Sp, yt);
+  SharedSmoothExtra ex;
+  switch (kind) {
+    case GPAR_MATERN12: CHK(filter_shared_d<1>(ctx, kind, l, s, noise, N, t, y, rvec, yt, Sp, at, &ex)); break;
+    case GPAR_MATERN32: CHK(filter_shared_d<2>(ctx, kind, l, s, noise, N, t, y, rvec, yt, Sp, at, &ex)); break;
+    case GPAR_MATERN52: CHK(filter_shared_d<3>(ctx, kind, l, s, noise, N, t, y, rvec, yt, Sp, at, &ex)); break;
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "kernel code %d has no state-space form (use Matern12/32/52)", kind);
+  }
+  if (d_alpha) LAUNCH(ctx, time_to_seq_major_kernel, tg, 256, 0, at, N, batch, Sp, d_alpha);
+  LAUNCH(ctx, shared_finish_kernel, (unsigned)((batch + 255) / 256), 256, 0, (const double*)nullptr, ex.sum_logS, ex.a2part, ex.nch, Sp, N, batch,
+         (double*)nullptr, d_lml);
   return GPAR_OK;
 }

@@ -337,6 +337,11 @@ def test_lgssm_smooth_shared_model_path(ctx, kind, n, batch):
         lml, mean, var = ctx.lgssm_smooth(kind, th)
         l0, m0, v0 = cport.kalman_smooth_batch(kind, t, Y, pp[0], pp[1] ** 2, rvec if rvec is not None else pp[2] ** 2)
         assert relerr(lml, l0) <= RTOL
+        # the filter-only shared path: logpdf with one theta for all sequences, decorrelate
+        lf0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[0], pp[1] ** 2, pp[2] ** 2, rvec=rvec, want_alpha=True)
+        assert relerr(ctx.lgssm_logpdf(kind, th), lf0) <= RTOL
+        lf, alpha = ctx.lgssm_decorrelate(kind, th)
+        assert relerr(lf, lf0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
         assert np.max(np.abs(mean - m0)) <= 1e-8 * max(1.0, np.max(np.abs(m0)))
         assert np.max(np.abs(var - v0) / v0) <= 1e-7
         os.environ["GPAR_SMOOTH_SHARED"] = "0"
