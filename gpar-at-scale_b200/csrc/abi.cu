@@ -195,13 +195,28 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   double* ypart = ctx->gpart.as<double>() + (size_t)nsplit * 2 * Mpad;
   LAUNCH(ctx, sumsq_kernel, 1024, 256, 0, ctx->y.as<double>(), N, ypart);
   LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
+  // value-only calls: when cov(u) is poorly conditioned, whiten the panel by L_u before the SYRK (A = L_u^-1 Kuf as the
+  // reference forms it, dtc_example.jl:14-16) instead of collapsing to Kuf Kfu first — see gpar_needs_whitened_panel
+  bool whitened = false;
+  if (!want_grad) {
+    TailBufs tb;
+    CHK(tail_layout(ctx, false, vfe, &tb));
+    double mm[2] = {1.0, 1.0};
+    CU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->stream2));              // the panel producer is already running on the main stream
+    if (gpar_needs_whitened_panel(mm)) {
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+      CHK(panel_left_solve(ctx, ctx->panelK.as<double>(), Npad, Mpad, M, tb.Lu));
+      whitened = true;
+    }
+  }
   cudaEventRecord(ctx->pev[0], ctx->stream);
   CHK(panel_syrk_run(ctx, ctx->panelK.as<double>(), ctx->panelD.as<double>(), Npad, Mpad, M, want_grad, G, H));
   ctx->phase_valid = true;
   double yy = 0.0;
   CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad);
+  return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened);
 }
 
 }  // extern "C"

@@ -202,4 +202,8 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
 // raw_out (nullable): host array of 8 + GPAR_NTR doubles receiving [trB, logdetLambda, c'c, -, ..., traces]
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
-             double* val, double* grad, double* raw_out = nullptr);
+             double* val, double* grad, double* raw_out = nullptr, bool whitened_G = false);
+// scaled.cu: conditioning decision and the panel whitening by L_u (see gpar_needs_whitened_panel)
+int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
+bool gpar_needs_whitened_panel(const double minmax[2]);
+int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2);

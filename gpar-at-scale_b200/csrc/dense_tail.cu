@@ -153,6 +153,7 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
     }
     CU(cudaMemcpyAsync(b.Lu, b.Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, b.Lu, M, ctx->tailws.as<double>() + b.lwork, b.lwork, b.dinfo));
+    CHK(launch_diag_minmax(ctx, b.Lu, M, b.sc + 4));        // conditioning estimate for the value-only path (abi.cu)
     if (want_grad) {
       const double one = 1.0, zero = 0.0;
       LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, b.V, M);
@@ -169,7 +170,7 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
 
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_in, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
-             double* val, double* grad, double* raw_out) {
+             double* val, double* grad, double* raw_out, bool whitened_G) {
   const int M = (int)ctx->M;
   const size_t MM = (size_t)M * M;
   const bool want_grad = grad != nullptr;
@@ -190,8 +191,12 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
   if (!want_grad) {
     // value only — the reference's own sequence of triangular solves (dtc_example.jl:14-21)
     CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
+    if (whitened_G) {      // the panel was whitened by L_u before the SYRK: G is already A A' (sigma^2 apart)
+      CB(cublasDscal(ctx->blas, (int)MM, &ip, Bm, 1));
+    } else {
+      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
+    }
     LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
     CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
     LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);

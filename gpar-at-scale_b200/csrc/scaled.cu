@@ -17,6 +17,11 @@
 #include "lgssm_math.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
+
+int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
+bool gpar_needs_whitened_panel(const double minmax[2]);
+int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2);
 
 namespace {
 
@@ -402,6 +407,33 @@ panel_slab_to_dense_t_kernel(const double* __restrict__ panel, int64_t NB4, int6
   dst[0] = b01.x; dst[M] = b01.y; dst[2 * (int64_t)M] = b23.x; dst[3 * (int64_t)M] = b23.y;
 }
 
+// inverse of the above: rows [4 g_lo, 4 (g_lo + ng)) of the panel <- the dense M x 4ng matrix Bt
+__global__ void __launch_bounds__(256)
+dense_t_to_panel_slab_kernel(const double* __restrict__ Bt, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* __restrict__ panel) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * ng * GPAR_TILE) return;
+  const int mi = (int)(idx % GPAR_TILE); const int64_t r = idx / GPAR_TILE; const int64_t gl = r % ng; const int mt = (int)(r / ng);
+  const int m = mt * GPAR_TILE + mi;
+  if (m >= M) return;
+  const double* src = Bt + (gl * 4) * (int64_t)M + m;
+  double* dst = panel + (((int64_t)mt * NB4 + g_lo + gl) * GPAR_TILE + mi) * 4;
+  reinterpret_cast<double2*>(dst)[0] = make_double2(src[0], src[M]);
+  reinterpret_cast<double2*>(dst)[1] = make_double2(src[2 * (int64_t)M], src[3 * (int64_t)M]);
+}
+// out[0] = min, out[1] = max of diag(L): (max / min)^2 is a lower bound of cond(L L')
+__global__ void diag_minmax_kernel(const double* __restrict__ L, int M, double* __restrict__ out) {
+  __shared__ double smin[32], smax[32];
+  double lo = 1e300, hi = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { const double d = L[(int64_t)i * M + i]; lo = fmin(lo, d); hi = fmax(hi, d); }
+  for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { lo = fmin(lo, smin[w]); hi = fmax(hi, smax[w]); }
+    out[0] = lo; out[1] = hi;
+  }
+}
+
 // Tangent whitening.  Per column the recursions
 //   mu'   = Phi mu + Kg v                       (v = beta sqrt(S) + HA mu: the un-whitened entry, recovered from beta)
 //   dmu_j' = dPhi_j mu + Phi dmu_j + dKg_j v,   d beta_j = beta dlog(rs)_j - rs (dHA_j mu + HA dmu_j)     j = 0, 1
@@ -582,6 +614,9 @@ int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const dou
   }
 }
 
+// before_syrk (nullable): called with the whitened panel right before the SYRK is enqueued (the whitening kernels are
+// already running, so a host-side wait in it costs no device time); may transform the panel in place
+typedef std::function<int(double* panel, int64_t Npad, int Mpad)> PanelHook;
 struct ScaledStats {
   double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad;
   double *table, *alpha, *beta; int nch;
@@ -593,7 +628,8 @@ struct ScaledStats {
 // runs the filter in forward mode (tangents w.r.t. time_l and the noise of Sigma_y), keeps the
 // l dK/dl panel and the chunk-start states for the tangent pass.
 template <int D>
-int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st, bool grad) {
+int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st, bool grad,
+                   const PanelHook* before_syrk) {
   constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
   const int64_t N = ctx->N; const int M = (int)ctx->M;
   const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
@@ -638,6 +674,7 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
   else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
+  if (before_syrk) CHK((*before_syrk)(panel, Npad, Mpad));
   cudaEventRecord(ctx->pev[0], ctx->stream);
   CHK(panel_syrk_run(ctx, panel, nullptr, Npad, Mpad, M, false, G, nullptr));
   ctx->phase_valid = true;
@@ -654,11 +691,11 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
 }
 
 int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, ScaledStats* st,
-                 bool grad = false) {
+                 bool grad = false, const PanelHook* before_syrk = nullptr) {
   switch (k_time) {
-    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
-    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
-    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad);
+    case GPAR_MATERN12: return scaled_stats_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad, before_syrk);
+    case GPAR_MATERN32: return scaled_stats_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad, before_syrk);
+    case GPAR_MATERN52: return scaled_stats_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, st, grad, before_syrk);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
   }
 }
@@ -764,6 +801,39 @@ int launch_kuu_plain(gpar_ctx* ctx, int kind, double l, double s, double jitter,
 
 }  // namespace
 
+// Ill-conditioned cov(u): the collapsed statistic G = beta'beta followed by L_u^-1 G L_u^-T carries an error
+// ~ cond(cov(u)) eps, the reference's A = L_u^-1 beta' (dtc.jl:119-120) only ~ sqrt(cond) eps.  When the cheap
+// estimate (max / min of diag L_u)^2 exceeds GPAR_ROBUST_COND the panel itself is whitened by L_u before the SYRK
+// (one N M^2 triangular solve — the library TRSM on transposed slabs), so that the SYRK yields A A' directly.
+bool gpar_needs_whitened_panel(const double minmax[2]) {
+  double thr = 1e5;
+  if (const char* e = getenv("GPAR_ROBUST_COND")) thr = atof(e);
+  if (!(minmax[0] > 0.0)) return false;           // failed factorisation: reported by the caller
+  const double r = minmax[1] / minmax[0];
+  return r * r > thr;
+}
+int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2) {
+  LAUNCH(ctx, diag_minmax_kernel, 1, 256, 0, L, M, out2);
+  return GPAR_OK;
+}
+// panel (operand layout, N x M) <- panel L_u^-T  i.e. every row beta_n' becomes (L_u^-1 beta_n)'
+int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu) {
+  const int T = Mpad / GPAR_TILE; const int64_t NB4 = Npad / 4;
+  const int64_t slab_groups = std::min<int64_t>(NB4, 32768);                       // 131072 steps per slab
+  CU(ctx->panelB.reserve((size_t)slab_groups * 4 * M * sizeof(double)));
+  double* Bt = ctx->panelB.as<double>();
+  cublasSetStream(ctx->blas, ctx->stream);
+  const double one = 1.0;
+  for (int64_t g_lo = 0; g_lo < NB4; g_lo += slab_groups) {
+    const int64_t ng = std::min<int64_t>(slab_groups, NB4 - g_lo);
+    const int64_t total = (int64_t)T * ng * GPAR_TILE;
+    LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, panel, NB4, g_lo, ng, T, M, Bt);
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, (int)(ng * 4), &one, Lu, M, Bt, M));
+    LAUNCH(ctx, dense_t_to_panel_slab_kernel, (int)((total + 255) / 256), 256, 0, Bt, NB4, g_lo, ng, T, M, panel);
+  }
+  return GPAR_OK;
+}
+
 // helpers shared with zgrad.cu
 int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, const double* a, int64_t N, int64_t NB4, int T, int M, double* e) {
   LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, panel, w, a, N, NB4, T, M, e);
@@ -777,6 +847,40 @@ int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4
 
 static const double LOG2PI_S = 1.8378770664093454835606594728112;
 
+// cov(u) = Kuu + jitter I and its Cholesky factor on the SIDE stream (underneath the filter / whitening), plus
+// min / max of diag(L_u) for the conditioning decision.  Records ctx->ev_side.
+static int factor_cov_u_side(gpar_ctx* ctx, int k_out, double out_l, double out_s, double jitter, double* Lu, int lwork, int* dinfo,
+                             double* minmax_dev) {
+  const int M = (int)ctx->M;
+  cudaStream_t main_stream = ctx->stream;
+  CU(cudaEventRecord(ctx->ev_fork, main_stream));
+  CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  ctx->stream = ctx->stream2;
+  cusolverDnSetStream(ctx->solver, ctx->stream);
+  int rc = [&]() -> int {
+    CHK(launch_kuu_plain(ctx, k_out, out_l, out_s, jitter, Lu));
+    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+    CHK(launch_diag_minmax(ctx, Lu, M, minmax_dev));
+    return GPAR_OK;
+  }();
+  cudaEventRecord(ctx->ev_side, ctx->stream2);
+  ctx->stream = main_stream;
+  cusolverDnSetStream(ctx->solver, ctx->stream);
+  return rc;
+}
+// The hook of scaled_stats: wait for L_u, decide on the conditioning, whiten the panel by L_u when it is poor.
+static PanelHook make_whitening_hook(gpar_ctx* ctx, const double* Lu, const double* minmax_dev, bool* robust) {
+  return [ctx, Lu, minmax_dev, robust](double* panel, int64_t Npad, int Mpad) -> int {
+    double mm[2] = {1.0, 1.0};
+    CU(cudaMemcpyAsync(mm, minmax_dev, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->stream2));             // the whitening kernels are already running on the main stream
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    *robust = gpar_needs_whitened_panel(mm);
+    if (*robust) CHK(panel_left_solve(ctx, panel, Npad, Mpad, (int)ctx->M, Lu));
+    return GPAR_OK;
+  };
+}
+
 extern "C" {
 
 int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc, double* A_or_null) {
@@ -789,8 +893,6 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   double pv[5];
   for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;
   const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
-  ScaledStats st;
-  CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st));
   const int M = (int)ctx->M; const int64_t N = ctx->N; const size_t MM = (size_t)M * M;
   cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(ctx->dense.reserve((2 * MM + 2 * (size_t)M + 16) * sizeof(double)));
@@ -800,15 +902,23 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
   CU(ctx->info.reserve(4 * sizeof(int)));
   int* dinfo = ctx->info.as<int>();
-  CHK(launch_kuu_plain(ctx, k_out, out_l, out_s, noise, Lu));       // cov(u) = Kuu + noise_sigma^2 I (dtc.jl:35,119)
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+  // cov(u) = Kuu + noise_sigma^2 I (dtc.jl:35,119) and L_u on the side stream
+  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, Lu, lwork, dinfo, sc + 4));
+  bool robust = false;
+  PanelHook hook = make_whitening_hook(ctx, Lu, sc + 4, &robust);
+  ScaledStats st;
+  CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, false, &hook));
+  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(cudaMemcpyAsync(Bm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   const double one = 1.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+  if (!robust) {      // collapsed statistic: B = L_u^-1 (beta'beta) L_u^-T;  whitened panel: G is already A A'
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+  }
   LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Bm, M);
   CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
   LAUNCH(ctx, logdet2_kernel, 1, 256, 0, Bm, M, sc);
+  // c = L_Lambda^-1 (A alpha), A alpha = L_u^-1 g with g = beta'alpha (accumulated by the whitening pass, before the hook)
   CU(cudaMemcpyAsync(cvec, st.g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
   CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
@@ -820,7 +930,7 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
     CU(ctx->kal_b.reserve((size_t)N * M * sizeof(double)));
     double* Bt = ctx->kal_b.as<double>();
     LAUNCH(ctx, panel_to_dense_t_kernel, (int)(((size_t)N * M + 255) / 256), 256, 0, ctx->panelK.as<double>(), N, M, st.Npad / 4, Bt);
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, (int)N, &one, Lu, M, Bt, M));
+    if (!robust) CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, (int)N, &one, Lu, M, Bt, M));
   }
   timer.stop();
   double hs[2]; int hinfo[2];
@@ -889,12 +999,10 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
 struct QuFactors { double *Lu, *LD, *Uu, *me; int* dinfo; int lwork; };
 static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params[5], QuFactors* q) {
   const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
-  ScaledStats st;
-  CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st));
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
   cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(ctx->dense.reserve((3 * MM + 2 * (size_t)M + 16) * sizeof(double)));
-  double* Lu = ctx->dense.as<double>(); double* Dm = Lu + MM; double* Uu = Dm + MM; double* vec = Uu + MM;
+  double* Lu = ctx->dense.as<double>(); double* Dm = Lu + MM; double* Uu = Dm + MM; double* vec = Uu + MM; double* mmdev = vec + 2 * M;
   int lwork = 0, lwork2 = 0;
   CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, &lwork));
   CS(cusolverDnDpotri_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Dm, M, &lwork2));
@@ -903,12 +1011,20 @@ static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params
   CU(ctx->info.reserve(4 * sizeof(int)));
   int* dinfo = ctx->info.as<int>();
   CU(cudaMemsetAsync(dinfo, 0, 4 * sizeof(int), ctx->stream));
-  CHK(launch_kuu_plain(ctx, k_out, out_l, out_s, 0.0, Lu));         // bare Cuu (gpar_scaled_inference.jl:157-159)
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+  // bare Cuu (gpar_scaled_inference.jl:157-159) — no jitter, usually poorly conditioned: the panel is then whitened by
+  // L_u before the SYRK (B_ef = U_u' \ beta', :179, as the reference forms it) instead of collapsing to beta'beta first
+  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, 0.0, Lu, lwork, dinfo, mmdev));
+  bool robust = false;
+  PanelHook hook = make_whitening_hook(ctx, Lu, mmdev, &robust);
+  ScaledStats st;
+  CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, false, &hook));
+  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(cudaMemcpyAsync(Dm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   const double one = 1.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
+  if (!robust) {
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
+    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
+  }
   LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Dm, M);          // D = B_ef B_ef' + I (:187)
   CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Dm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
   // m_e = chol_D \ (B_ef b_y) = L_D^{-T} L_D^{-1} L_u^{-1} g  (:189)

@@ -477,6 +477,52 @@ def test_scaled_dtc_grad_multi_slab_and_full_size(ctx):
     print("scaled objective + gradient N=1M M=1024: %.1f ms device" % ms)
 
 
+def test_ill_conditioned_cov_u_keeps_parity(ctx):
+    """cov(u) with cond ~ 1e7 ... 1e10 (large output variance, small jitter): the collapsed statistic beta'beta would lose
+    cond(cov(u)) eps (6e-8 ... 4e-3 here); the library then whitens the panel by L_u before the SYRK (A = L_u^-1 beta' as the
+    reference forms it, dtc.jl:119-120) and keeps the 1e-8 bar — scaled objective, plain DTC / VFE values, q(u)."""
+    from gpar_at_scale_b200 import data, chain
+    rng = np.random.default_rng(5)
+    x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
+    Y = np.stack(y_obs); o = 2
+    X = np.ascontiguousarray(Y[:o].T); Z = chain.strided_pseudo_inputs(X, 40)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(x); ctx.set_outputs(Y[o]); ctx.set_noise_vector(None)
+    for th3 in (4.0, 6.0, 8.0, 9.2):
+        th = np.array([4.65, 2.31, 4.10, th3, -0.43])
+        v = ctx.scaled_dtc(3, 3, th)
+        v0 = scaled_gpar_objective(th, X, Z, x, Y[o], k_out=3, k_time=3, decorrelate=cport.kalman_decorrelate)
+        assert abs(v - v0) <= RTOL * abs(v0), (th3, v, v0)
+    # the A the reference returns (dtc.jl:127) is the whitened panel itself on this path
+    th = np.array([4.65, 2.31, 4.10, 8.0, -0.43])
+    v, A = ctx.scaled_dtc(3, 3, th, return_A=True)
+    tl, tv, ol, ov, ns = oracle.unpack_gpar(th)
+    Cfu = oracle.pairwise(3, X, Z, l=ol, s=ov ** 2); cov_u = oracle.pairwise(3, Z, Z, l=ol, s=ov ** 2) + ns ** 2 * np.eye(len(Z))
+    _, A0 = oracle.compute_gpar_dtc_objective(Cfu, cov_u, x, Y[o], 3, tl, tv ** 2, ns ** 2, decorrelate=cport.kalman_decorrelate)
+    assert np.max(np.abs(A - A0)) <= 1e-7 * np.max(np.abs(A0))
+    # q(u): bare Cuu (no jitter at all)
+    # (the Cholesky factor of a bare kernel matrix is itself only determined to ~ eps cond(Cuu): both sides are float64 with
+    # kernel values differing in the last bit, so the bound scales with cond(Cuu) through U_u — but no longer squared)
+    params = np.array([tl, tv, 2.0, 3.0, ns])
+    m_e, Dinv, U_u = ctx.compute_q_u(3, 3, params)
+    Cfu = oracle.pairwise(3, X, Z, l=2.0, s=9.0); Cuu = oracle.pairwise(3, Z, Z, l=2.0, s=9.0)
+    m0, D0, U0 = oracle.compute_q_u(Cfu, Cuu, x, Y[o], 3, tl, tv ** 2, ns ** 2, decorrelate=cport.kalman_decorrelate)
+    cu = np.linalg.cond(U0)
+    tol = max(1e-8, 100 * np.finfo(float).eps * cu ** 2)
+    print("q_u: cond(U_u) %.1e  errors U_u %.1e m_e %.1e inv(D) %.1e  (tolerance %.1e)" % (cu, relerr(U_u, U0), relerr(m_e, m0), relerr(Dinv, D0), tol))
+    assert relerr(U_u, U0) <= tol and relerr(m_e, m0) <= tol and relerr(Dinv, D0) <= tol
+    # plain DTC / VFE values, diagonal noise, explicit tiny jitter
+    n, m = 5000, 80
+    xs = rng.uniform(0, 10, n); zs = np.linspace(0, 10, m); ys = np.sin(xs) + 0.1 * rng.normal(size=n)
+    th3 = np.log([2.0, 30.0, 0.1])
+    ctx.set_inputs(xs); ctx.set_pseudo(zs); ctx.set_outputs(ys)
+    l, var, sig = oracle.unpack_gp(th3)
+    Cfu = oracle.pairwise(0, xs[:, None], zs[:, None], l=l, s=var ** 2); cov_u = oracle.pairwise(0, zs[:, None], zs[:, None], l=l, s=var ** 2) + 1e-6 * np.eye(m)
+    d0, _ = oracle.dtc_diag(Cfu, cov_u, sig ** 2, ys)
+    e0 = oracle.elbo_diag(Cfu, cov_u, n * var ** 2, sig ** 2, ys)
+    assert abs(ctx.dtc_logpdf(0, th3, jitter=1e-6) - d0) <= RTOL * abs(d0)
+    assert abs(ctx.dtc_logpdf(0, th3, vfe=True, jitter=1e-6) - e0) <= RTOL * abs(e0)
+
+
 # ---- exact GP / GPAR -----------------------------------------------------------------------
 def test_exact_golden(ctx):
     z = np.load(os.path.join(G, "exact.npz"))
