@@ -1200,6 +1200,275 @@ ss2_finish_kernel(const double* __restrict__ part, int nseg, const double* __res
   }
 }
 
+// ---- ss3: the non-head part of the single pass as a PERSISTENT, software-pipelined kernel ---------------------
+// ss2_main<false> gives every block one 8192-step window: load it all, then compute — the three co-resident
+// blocks of an SM start together, so the SM alternates between "all waiting for HBM" and "all computing"
+// (measured 1.8 TB/s, FP64 pipe 39 %), and every block pays the W-step burn-in (14 % re-reads).
+// Here a CTA owns ONE contiguous range of a sequence and walks it tile by tile (THREADS sub-chunks of 32 steps):
+//   * tiles arrive through an NBUF-deep cp.async ring (16-byte copies, rows padded to 34 doubles so that both the
+//     coalesced fill and the per-thread LDS.128 reads are bank-conflict free) — the loads of tiles i+1.. are in
+//     flight while tile i is computed;
+//   * the state is carried from tile to tile, so the burn-in is paid once per CTA (W / range = 3 % at 1 x 10M);
+//   * the emit pass is blocked by 4 steps like the response pass: the four predictions of a group are
+//     h_j . x + (ha Phi^m K) y terms, the state advances with Phi^4 — 12.75 instead of 16 FMA per step and one
+//     dependent mat-vec per four steps;
+//   * one warp scan per tile: the warp's carry enters through the per-lane constant power Phi^(32 (lane+1)).
+// Algorithmic traffic: 8 B/step read (+ 8 B/step when alpha is written).
+constexpr int SS3_LS = 32, SS3_ROW = SS3_LS + 2;
+__device__ __forceinline__ void ss_cp_async16(double* dst, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+template <int NB> __device__ __forceinline__ void ss_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NB) : "memory"); }
+
+template <int D, int THREADS, int NBUF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const double* __restrict__ cst, int W, int64_t R, int nseg,
+                double* __restrict__ alpha, double* __restrict__ part) {
+  typedef SS2Layout<D> SL;
+  constexpr int TILE = THREADS * SS3_LS, BUF = THREADS * SS3_ROW, NW = THREADS / 32, WT = 32 * SS3_LS;
+  extern __shared__ __align__(16) double ysm[];              // NBUF buffers of THREADS padded rows
+  __shared__ double wtot[2][NW][D], xin[2][D], red[32], pws[SL::NPOW * D * D];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.y, seg = blockIdx.x + 1;
+  const double* c = cst + (int64_t)b * SL::SIZE;
+  const int64_t r0 = (int64_t)SS2_STEPS + (int64_t)blockIdx.x * R;            // first emitted step of this CTA
+  const int64_t r1 = r0 + R < N ? r0 + R : N;                                 // one past its last
+  if (r0 >= N) { if (tid == 0) { part[((int64_t)b * nseg + seg) * 2] = 0.0; part[((int64_t)b * nseg + seg) * 2 + 1] = 0.0; } return; }
+  const int64_t s0 = r0 - W;                                                  // burn-in start (r0 >= SS2_STEPS > W)
+  const int ntile = (int)((r1 - s0 + TILE - 1) / TILE);
+  const double* yb = y + (int64_t)b * ystride;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(yb + s0) & 15) == 0);
+  // Every warp fills (and later drains) only ITS OWN 32 rows = one contiguous 8 KB run of the sequence, so that
+  // "tile landed" and "buffer free" are warp-local conditions: no block barrier around the ring.
+  auto issue = [&](int ti) {                                                  // rows of this warp in buffer ti % NBUF (zeros beyond r1)
+    if (ti < ntile) {
+      double* wbuf = ysm + (ti % NBUF) * BUF + wid * 32 * SS3_ROW;
+      const int64_t base = s0 + (int64_t)ti * TILE + (int64_t)wid * WT;
+      if (al16 && base + WT <= r1) {
+#pragma unroll
+        for (int i = 0; i < SS3_LS / 2; i++) {
+          const int q = lane + i * 32;                                        // 16-byte chunk of the warp's run
+          ss_cp_async16(wbuf + (q >> 4) * SS3_ROW + ((q & 15) << 1), yb + base + 2 * q);
+        }
+      } else {
+        for (int i = 0; i < SS3_LS; i++) {
+          const int e = lane + i * 32;
+          double* dst = wbuf + (e >> 5) * SS3_ROW + (e & 31);
+          if (base + e < r1) ss_cp_async8(dst, yb + base + e); else *dst = 0.0;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int i = 0; i < NBUF - 1; i++) issue(i);
+  // constants (once per CTA): 4-step blocking of the state and of the predictions, scan powers
+  double P4[D * D], G[4][D], hj[4][D], cm[3], PL[D * D];
+  const double rs = c[SL::ROW + D * D + 2 * D];
+  {
+    double Phi[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) { Phi[i] = c[SL::ROW + i]; P4[i] = c[SL::PHI4 + i]; }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int i = 0; i < D; i++) G[q][i] = c[SL::G4 + q * D + i];
+#pragma unroll
+    for (int i = 0; i < D; i++) hj[0][i] = c[SL::ROW + D * D + D + i];
+#pragma unroll
+    for (int j = 1; j < 4; j++)                                                // h_(j+1) = h_j Phi
+#pragma unroll
+      for (int i = 0; i < D; i++) { double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) v = fma(hj[j - 1][q], Phi[q * D + i], v);
+        hj[j][i] = v; }
+#pragma unroll
+    for (int m = 0; m < 3; m++) { double v = 0.0;                              // c_m = ha Phi^m K = ha . G[3 - m]
+#pragma unroll
+      for (int q = 0; q < D; q++) v = fma(hj[0][q], G[3 - m][q], v);
+      cm[m] = v; }
+    // PL = Phi^(32 (lane + 1)) from the binary powers Phi^(32 2^j)
+#pragma unroll
+    for (int i = 0; i < D * D; i++) PL[i] = (i / D == i % D) ? 1.0 : 0.0;
+    for (int j = 0; j < SL::NPOW; j++)
+      if (((lane + 1) >> j) & 1) {
+        double Pj[D * D], T[D * D];
+#pragma unroll
+        for (int i = 0; i < D * D; i++) Pj[i] = c[SL::POWS + j * D * D + i];
+        matmul<D>(PL, Pj, T);
+#pragma unroll
+        for (int i = 0; i < D * D; i++) PL[i] = T[i];
+      }
+  }
+  for (int i = tid; i < SL::NPOW * D * D; i += THREADS) pws[i] = c[SL::POWS + i];
+  if (tid < D) { xin[0][tid] = 0.0; xin[1][tid] = 0.0; }
+  __syncthreads();
+  double a2s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int ti = 0; ti < ntile; ti++) {
+    ss_cp_wait<NBUF - 2>();
+    __syncwarp();                                             // the warp's rows of tile ti landed; it is done with its rows of tile ti - 1
+    issue(ti + NBUF - 1);
+    double* row = ysm + (ti % NBUF) * BUF + tid * SS3_ROW;
+    const int64_t k0 = s0 + (int64_t)ti * TILE + (int64_t)tid * SS3_LS;
+    // phase 1: zero-start response of the sub-chunk (4 steps per dependent mat-vec)
+    double rsp[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) rsp[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < SS3_LS; j += 4) {
+      const double2 ya = *reinterpret_cast<const double2*>(row + j), yc = *reinterpret_cast<const double2*>(row + j + 2);
+      double nx[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double u = G[0][i] * ya.x;
+        u = fma(G[1][i], ya.y, u); u = fma(G[2][i], yc.x, u); u = fma(G[3][i], yc.y, u);
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) v = fma(P4[i * D + q], rsp[q], v);
+        nx[i] = u + v;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) rsp[i] = nx[i];
+    }
+    // phase 2: inclusive warp scan with the constant powers, warp carries, per-lane fix-up
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      double o[D], pj[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; i++) pj[i] = pws[j * D * D + i];
+#pragma unroll
+      for (int i = 0; i < D; i++) o[i] = __shfl_up_sync(0xffffffffu, rsp[i], 1 << j);
+      if (lane >= (1 << j)) {
+#pragma unroll
+        for (int i = 0; i < D; i++) { double a = rsp[i];
+#pragma unroll
+          for (int q = 0; q < D; q++) a = fma(pj[i * D + q], o[q], a);
+          rsp[i] = a; }
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < D; i++) wtot[ti & 1][wid][i] = rsp[i];
+    }
+    __syncthreads();                                          // the only block barrier of a tile (wtot, xin: parity double-buffered)
+    double carry[D];                                          // state at the start of this warp's first sub-chunk
+#pragma unroll
+    for (int i = 0; i < D; i++) carry[i] = xin[ti & 1][i];
+    for (int w2 = 0; w2 < wid; w2++) {
+      double nx[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = wtot[ti & 1][w2][i];
+#pragma unroll
+        for (int q = 0; q < D; q++) a = fma(pws[5 * D * D + i * D + q], carry[q], a);
+        nx[i] = a; }
+#pragma unroll
+      for (int i = 0; i < D; i++) carry[i] = nx[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) { double a = rsp[i];          // true state at the end of sub-chunk tid
+#pragma unroll
+      for (int q = 0; q < D; q++) a = fma(PL[i * D + q], carry[q], a);
+      rsp[i] = a; }
+    if (tid == THREADS - 1) {
+#pragma unroll
+      for (int i = 0; i < D; i++) xin[(ti + 1) & 1][i] = rsp[i];
+    }
+    double x[D];                                              // true state at its start
+#pragma unroll
+    for (int i = 0; i < D; i++) { x[i] = __shfl_up_sync(0xffffffffu, rsp[i], 1); if (lane == 0) x[i] = carry[i]; }
+    // phase 3: payload sub-chunks emit, again four steps per dependent mat-vec
+    const bool pay = k0 >= r0 && k0 < r1;
+    if (pay) {
+      const int nv = r1 - k0 >= SS3_LS ? SS3_LS : (int)(r1 - k0);
+#pragma unroll
+      for (int j = 0; j < SS3_LS; j += 4) {
+        const double2 ya = *reinterpret_cast<const double2*>(row + j), yc = *reinterpret_cast<const double2*>(row + j + 2);
+        double p0 = 0.0, p1 = cm[0] * ya.x, p2 = cm[1] * ya.x, p3 = cm[2] * ya.x;
+        p2 = fma(cm[0], ya.y, p2); p3 = fma(cm[1], ya.y, p3); p3 = fma(cm[0], yc.x, p3);
+#pragma unroll
+        for (int q = 0; q < D; q++) { p0 = fma(hj[0][q], x[q], p0); p1 = fma(hj[1][q], x[q], p1); p2 = fma(hj[2][q], x[q], p2); p3 = fma(hj[3][q], x[q], p3); }
+        double al[4] = {(ya.x - p0) * rs, (ya.y - p1) * rs, (yc.x - p2) * rs, (yc.y - p3) * rs};
+        if (alpha) { *reinterpret_cast<double2*>(row + j) = make_double2(al[0], al[1]); *reinterpret_cast<double2*>(row + j + 2) = make_double2(al[2], al[3]); }
+        if (nv != SS3_LS) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (j + q >= nv) al[q] = 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) a2s[q] = fma(al[q], al[q], a2s[q]);      // four independent accumulators
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double u = G[0][i] * ya.x;
+          u = fma(G[1][i], ya.y, u); u = fma(G[2][i], yc.x, u); u = fma(G[3][i], yc.y, u);
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < D; q++) v = fma(P4[i * D + q], x[q], v);
+          nx[i] = u + v;
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = nx[i];
+      }
+    }
+    if (alpha) {                                              // alpha leaves through the warp's own rows, coalesced
+      __syncwarp();
+      double* ab = alpha + (int64_t)b * ystride;
+      const double* wbuf = ysm + (ti % NBUF) * BUF + wid * 32 * SS3_ROW;
+      const int64_t base = s0 + (int64_t)ti * TILE + (int64_t)wid * WT;
+      if (al16 && base >= r0 && base + WT <= r1) {
+#pragma unroll 4
+        for (int i = 0; i < SS3_LS / 2; i++) {
+          const int q = lane + i * 32;
+          *reinterpret_cast<double2*>(ab + base + 2 * q) = *reinterpret_cast<const double2*>(wbuf + (q >> 4) * SS3_ROW + ((q & 15) << 1));
+        }
+      } else {
+        for (int i = 0; i < SS3_LS; i++) {
+          const int e = lane + i * 32;
+          const int64_t k = base + e;
+          if (k >= r0 && k < r1) ab[k] = wbuf[(e >> 5) * SS3_ROW + (e & 31)];
+        }
+      }
+    }
+  }
+  ss_cp_wait<0>();
+  const double a2tot = block_sum((a2s[0] + a2s[1]) + (a2s[2] + a2s[3]), red);
+  if (tid == 0) { part[((int64_t)b * nseg + seg) * 2] = 0.0; part[((int64_t)b * nseg + seg) * 2 + 1] = a2tot; }
+}
+
+// all sequences in one launch: warp w sums the partials of sequence w in fixed order; thread 0 folds the flags
+template <int D>
+__global__ void __launch_bounds__(512)
+ss3_finish_kernel(const double* __restrict__ part, int nseg, const double* __restrict__ cst, int64_t N, int batch,
+                  double* __restrict__ lml, double* __restrict__ sums, double* __restrict__ flag_out) {
+  typedef SS2Layout<D> SL;
+  const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (b < batch) {
+    const double* c = cst + (int64_t)b * SL::SIZE;
+    double a0 = 0.0, a1 = 0.0;
+    for (int sg = lane; sg < nseg; sg += 32) { a0 += part[((int64_t)b * nseg + sg) * 2]; a1 += part[((int64_t)b * nseg + sg) * 2 + 1]; }
+    for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    if (lane == 0) {
+      const int64_t kstar = (int64_t)c[SL::KSTAR];
+      const double slog = a0 + (double)(N > kstar ? N - kstar : 0) * c[SL::ROW + D * D + 2 * D + 1];
+      if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + slog + a1);
+      if (sums) { sums[2 * b] = slog; sums[2 * b + 1] = a1; }
+    }
+  }
+  if (threadIdx.x == 0) {
+    double ok = 1.0;
+    for (int q = 0; q < batch; q++) if (cst[(int64_t)q * SL::SIZE + SL::OK] != 1.0) ok = 0.0;
+    flag_out[0] = ok;
+  }
+}
+
+template <int D, int THREADS, int NBUF, int MINB>
+int ss3_launch(gpar_ctx* ctx, int batch, int64_t N, const double* y, int64_t ystride, const double* cst, int W, double* alpha, double* part,
+               int nc, int64_t R) {
+  const size_t smem = (size_t)NBUF * THREADS * SS3_ROW * sizeof(double);
+  CU(cudaFuncSetAttribute((ss3_main_kernel<D, THREADS, NBUF, MINB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LAUNCH(ctx, (ss3_main_kernel<D, THREADS, NBUF, MINB>), dim3(nc, batch), THREADS, smem, y, ystride, N, cst, W, R, nc + 1, alpha, part);
+  return GPAR_OK;
+}
+
 template <int D>
 int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* y, const LgssmOut& o, bool* used) {
   typedef SS2Layout<D> SL;
@@ -1214,8 +1483,20 @@ int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, con
   // host round trip separates the set-up from the main pass; a model that needs more (or whose covariance
   // has not settled) is FLAGGED by the kernels and the caller falls back after its own final synchronisation.
   const int W = SS2_WFIX;
+  // variant of the non-head pass: 0 = ss2 (one window per block), 1..3 = ss3 (persistent, pipelined)
+  int variant = 1;
+  if (const char* e = getenv("GPAR_SS3_VARIANT")) variant = atoi(e);
   const int payload = SS2_STEPS - W;
-  const int nseg = (int)(1 + (N - SS2_STEPS + payload - 1) / payload);
+  int nseg, nc = 0; int64_t R = 0;
+  if (variant == 0) nseg = (int)(1 + (N - SS2_STEPS + payload - 1) / payload);
+  else {
+    // CTAs per SM of the variant; every sequence gets the same number of CTAs, one slot per sequence is left to the head blocks
+    const int per_sm = variant == 1 ? 2 : (variant == 2 ? 3 : 1);
+    nc = std::max(1, (ctx->num_sms * per_sm - batch) / batch);
+    R = ((N - SS2_STEPS + nc - 1) / nc + SS3_LS - 1) / SS3_LS * SS3_LS;
+    if (R < 4 * W) { R = 4 * W; nc = (int)((N - SS2_STEPS + R - 1) / R); }      // keep the burn-in below a quarter of a CTA's range
+    nseg = nc + 1;
+  }
   CU(ctx->kal_b.reserve((size_t)batch * nseg * 2 * sizeof(double)));
   double* part = ctx->kal_b.as<double>();
   const size_t smem = (size_t)(SS2_STEPS + SS2_THREADS) * sizeof(double);
@@ -1234,14 +1515,23 @@ int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, con
   cudaEventRecord(ctx->ev_side, ctx->stream2);
   ctx->stream = main_stream;
   CHK(rc);
-  if (nseg > 1) LAUNCH(ctx, (ss2_main_kernel<D, false>), dim3(nseg - 1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
-  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-  LAUNCH(ctx, ss2_finish_kernel<D>, batch, 256, 0, part, nseg, cst, N, W, o.lml, o.sums);
+  double* flag_dev = ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS);
+  if (!ctx->pinned) { CU(cudaMallocHost(&ctx->pinned, 4096)); ctx->pinned_cap = 4096; }
+  if (variant == 0) {
+    if (nseg > 1) LAUNCH(ctx, (ss2_main_kernel<D, false>), dim3(nseg - 1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    LAUNCH(ctx, ss2_finish_kernel<D>, batch, 256, 0, part, nseg, cst, N, W, o.lml, o.sums);
+    LAUNCH(ctx, ss2_flags_kernel<D>, 1, 32, 0, cst, batch, flag_dev);
+  } else {
+    if (variant == 1) CHK((ss3_launch<D, 128, 3, 2>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
+    else if (variant == 2) CHK((ss3_launch<D, 128, 2, 3>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
+    else CHK((ss3_launch<D, 256, 3, 1>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    LAUNCH(ctx, ss3_finish_kernel<D>, 1, 512, 0, part, nseg, cst, N, batch, o.lml, o.sums, flag_dev);
+  }
   // flags (set-up: doubling converged / burn-in long enough; head block: transient settled) go to pinned host
   // memory WITHOUT a synchronisation: lgssm_steady_failed() reads them after the caller's final sync
-  if (!ctx->pinned) { CU(cudaMallocHost(&ctx->pinned, 4096)); ctx->pinned_cap = 4096; }
-  LAUNCH(ctx, ss2_flags_kernel<D>, 1, 32, 0, cst, batch, ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS));
-  CU(cudaMemcpyAsync(ctx->pinned, ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->pinned, flag_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->ss_pending = true;
   *used = true;
   return GPAR_OK;

@@ -318,6 +318,34 @@ def test_lgssm_steady_state_single_pass_long_sequences(ctx, kind):
     ctx.set_times(t[:10])
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("kind", [1, 3])
+def test_lgssm_single_pass_variants(ctx, kind, variant):
+    """Every variant of the non-head pass of the single-pass scheme (GPAR_SS3_VARIANT: 0 = one window per block,
+    1..3 = persistent pipelined CTAs with 2 / 3 / 1 CTAs per SM): lml and alpha against the sequential C oracle.
+    N is odd, so the second sequence starts at an odd element (8-byte copies instead of 16-byte ones), and the
+    last CTA ends in a partial sub-chunk."""
+    rng = np.random.default_rng(190 + kind)
+    n, batch, dt = 700_001, 3, 1 / 25
+    t = dt * np.arange(n)
+    Y = rng.normal(size=(batch, n))
+    ths = np.array([[0.0, 0.0, -2.0], [-1.0, 0.5, -0.5], [0.3, -0.2, -1.0]])
+    pp = np.exp(ths) + 1e-3
+    ctx.set_times_range(0.0, dt, n); ctx.set_outputs(Y); ctx.set_noise_vector(None)
+    os.environ["GPAR_SS3_VARIANT"] = variant
+    os.environ["GPAR_FILTER_SHARED"] = "0"
+    try:
+        lml = ctx.lgssm_logpdf(kind, ths)
+        lml_s, alpha = ctx.lgssm_decorrelate(kind, ths[1])
+    finally:
+        del os.environ["GPAR_SS3_VARIANT"]; del os.environ["GPAR_FILTER_SHARED"]
+    lml0 = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2)
+    assert relerr(lml, lml0) <= RTOL
+    l0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[1, 0], pp[1, 1] ** 2, pp[1, 2] ** 2, want_alpha=True)
+    assert relerr(lml_s, l0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
+    ctx.set_times(t[:10])
+
+
 @pytest.mark.parametrize("kind", [1, 2, 3])
 @pytest.mark.parametrize("n,batch", [(1, 4), (50, 5), (1025, 7), (3000, 130)])
 def test_lgssm_smooth_shared_model_path(ctx, kind, n, batch):
