@@ -37,6 +37,16 @@ N_FULL, M_FULL = 1_000_000, 1024
 THETA = np.log(np.array([1.0, 1.0, 0.1]))
 METRIC = "pseudo-point logpdf+grad evals/s (N=1M,M=1024)"
 FP64_PEAK_TFLOPS_FALLBACK = 36.96     # profiles/peaks_r01.json: DMMA m8n8k4 microbenchmark on this pool's B200
+def _hbm_peak_gbps():
+    """Measured copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the value it held in round 1."""
+    try:
+        import json
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6554.2
+
+
+HBM_PEAK_GBPS = _hbm_peak_gbps()
 NCU_SYRK_DRAM_BYTES = 30.93e9          # dram__bytes_read.sum + dram__bytes_write.sum of panel_syrk_kernel, one ncu launch (profiles/ncu_syrk_traffic_r01c.csv)
 
 
@@ -225,6 +235,17 @@ def run_ours(args):
         extra["kalman_filter_1x10M_regular_grid_steps_per_s"] = N10 / ms * 1e3
         extra["kalman_filter_1x10M_regular_grid_ms"] = ms
         del y10
+        # eight 10M-step sequences, each with its own model (hyper-parameter candidates): the HBM-bound shape of
+        # the single-pass steady-state filter; algorithmic traffic 8 B/step (y read once), peak = measured copy bandwidth
+        B8 = 8
+        ctx.set_outputs(rng.normal(size=(B8, N10)))
+        ths8 = np.tile(th3, (B8, 1)) + 0.05 * rng.normal(size=(B8, 3))
+        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths8))
+        extra["kalman_filter_8x10M_regular_grid_steps_per_s"] = B8 * N10 / ms * 1e3
+        extra["kalman_filter_8x10M_regular_grid_ms"] = ms
+        extra["kalman_filter_8x10M_regular_grid_hbm"] = {"achieved_GBps": B8 * N10 * 8 / (ms * 1e-3) / 1e9, "peak_GBps": HBM_PEAK_GBPS,
+                                                         "frac": B8 * N10 * 8 / (ms * 1e-3) / 1e9 / HBM_PEAK_GBPS,
+                                                         "note": "whole blocking call (set-up, head, main pass, finish), 8 B/step algorithmic"}
         tfull = np.arange(N_FULL) / 30.0
         ctx.set_inputs(xp); ctx.set_outputs(yp); ctx.set_times(tfull)
         th5 = np.log(np.array([1.0, 1.0, 1.0, 1.0, 0.1]))

@@ -1003,18 +1003,23 @@ ss2_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, SeqPar
         const double S = Pp[0] + noise, iS = 1.0 / S, inn = ysm[k + k / SS2_LS] - mp[0];
         ysm[k + k / SS2_LS] = inn;
         Sk[k] = S;
-        double dmax = 0.0, pmax = 0.0;
+        double Pn[NSYM<D>];
 #pragma unroll
         for (int i = 0; i < D; i++) { Kt[i] = SYM(Pp, i, 0) * iS; x[i] = fma(Kt[i], inn, mp[i]); }
 #pragma unroll
         for (int i = 0; i < D; i++)
 #pragma unroll
-          for (int j = i; j < D; j++) {
-            const double pn = fma(-S * Kt[i], Kt[j], SYM(Pp, i, j));
-            dmax = fmax(dmax, fabs(pn - SYM(P, i, j))); pmax = fmax(pmax, fabs(pn));
-            SYM(P, i, j) = pn;
-          }
-        conv = (k >= 2 && dmax <= 1e-13 * pmax) ? conv + 1 : 0;
+          for (int j = i; j < D; j++) SYM(Pn, i, j) = fma(-S * Kt[i], Kt[j], SYM(Pp, i, j));
+        // "P has stopped moving" is only looked at on the last two steps of a sub-chunk (a hand-over is only
+        // possible at its end), so that the max-reductions stay off the sequential critical path elsewhere
+        if ((k + 2) % SS2_LS < 2 && k >= 2) {
+          double dmax = 0.0, pmax = 0.0;
+#pragma unroll
+          for (int i = 0; i < NSYM<D>; i++) { dmax = fmax(dmax, fabs(Pn[i] - P[i])); pmax = fmax(pmax, fabs(Pn[i])); }
+          conv = dmax <= 1e-13 * pmax ? conv + 1 : 0;
+        } else conv = 0;
+#pragma unroll
+        for (int i = 0; i < NSYM<D>; i++) P[i] = Pn[i];
         if (conv >= 2 && (k + 1) % SS2_LS == 0) { found = k + 1; break; }
       }
       if (found < 0 && k >= N) found = (int)((N + SS2_LS - 1) / SS2_LS * SS2_LS);   // the sequence ended inside the transient
@@ -1287,6 +1292,12 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
 #pragma unroll
       for (int q = 0; q < D; q++) v = fma(hj[0][q], G[3 - m][q], v);
       cm[m] = v; }
+#pragma unroll
+    for (int m = 0; m < 3; m++) cm[m] *= -rs;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < D; i++) hj[j][i] *= -rs;
     // PL = Phi^(32 (lane + 1)) from the binary powers Phi^(32 2^j)
 #pragma unroll
     for (int i = 0; i < D * D; i++) PL[i] = (i / D == i % D) ? 1.0 : 0.0;
@@ -1320,12 +1331,11 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
       double nx[D];
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        double u = G[0][i] * ya.x;
+        double u = G[0][i] * ya.x;                            // (independent of the state: off the dependent chain)
         u = fma(G[1][i], ya.y, u); u = fma(G[2][i], yc.x, u); u = fma(G[3][i], yc.y, u);
-        double v = 0.0;
 #pragma unroll
-        for (int q = 0; q < D; q++) v = fma(P4[i * D + q], rsp[q], v);
-        nx[i] = u + v;
+        for (int q = 0; q < D; q++) u = fma(P4[i * D + q], rsp[q], u);
+        nx[i] = u;
       }
 #pragma unroll
       for (int i = 0; i < D; i++) rsp[i] = nx[i];
@@ -1383,11 +1393,15 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
 #pragma unroll
       for (int j = 0; j < SS3_LS; j += 4) {
         const double2 ya = *reinterpret_cast<const double2*>(row + j), yc = *reinterpret_cast<const double2*>(row + j + 2);
-        double p0 = 0.0, p1 = cm[0] * ya.x, p2 = cm[1] * ya.x, p3 = cm[2] * ya.x;
-        p2 = fma(cm[0], ya.y, p2); p3 = fma(cm[1], ya.y, p3); p3 = fma(cm[0], yc.x, p3);
+        // alpha_k = rs (y_k - pred_k) with rs and the sign folded into the constants (hj, cm hold -rs h_j, -rs c_m)
+        double al[4] = {rs * ya.x, rs * ya.y, rs * yc.x, rs * yc.y};
+        al[1] = fma(cm[0], ya.x, al[1]); al[2] = fma(cm[1], ya.x, al[2]); al[3] = fma(cm[2], ya.x, al[3]);
+        al[2] = fma(cm[0], ya.y, al[2]); al[3] = fma(cm[1], ya.y, al[3]); al[3] = fma(cm[0], yc.x, al[3]);
 #pragma unroll
-        for (int q = 0; q < D; q++) { p0 = fma(hj[0][q], x[q], p0); p1 = fma(hj[1][q], x[q], p1); p2 = fma(hj[2][q], x[q], p2); p3 = fma(hj[3][q], x[q], p3); }
-        double al[4] = {(ya.x - p0) * rs, (ya.y - p1) * rs, (yc.x - p2) * rs, (yc.y - p3) * rs};
+        for (int q = 0; q < D; q++) {
+#pragma unroll
+          for (int r = 0; r < 4; r++) al[r] = fma(hj[r][q], x[q], al[r]);
+        }
         if (alpha) { *reinterpret_cast<double2*>(row + j) = make_double2(al[0], al[1]); *reinterpret_cast<double2*>(row + j + 2) = make_double2(al[2], al[3]); }
         if (nv != SS3_LS) {
 #pragma unroll
@@ -1400,10 +1414,9 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
         for (int i = 0; i < D; i++) {
           double u = G[0][i] * ya.x;
           u = fma(G[1][i], ya.y, u); u = fma(G[2][i], yc.x, u); u = fma(G[3][i], yc.y, u);
-          double v = 0.0;
 #pragma unroll
-          for (int q = 0; q < D; q++) v = fma(P4[i * D + q], x[q], v);
-          nx[i] = u + v;
+          for (int q = 0; q < D; q++) u = fma(P4[i * D + q], x[q], u);
+          nx[i] = u;
         }
 #pragma unroll
         for (int i = 0; i < D; i++) x[i] = nx[i];
@@ -1484,7 +1497,9 @@ int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, con
   // has not settled) is FLAGGED by the kernels and the caller falls back after its own final synchronisation.
   const int W = SS2_WFIX;
   // variant of the non-head pass: 0 = ss2 (one window per block), 1..3 = ss3 (persistent, pipelined)
-  int variant = 1;
+  // (measured, 10M steps: one sequence 61 us with 1 CTA of 256 threads per SM, 65 / 75 us with 3 / 2 CTAs of 128;
+  //  eight sequences 200 us with 3 CTAs per SM, 216 / 224 us with 2 / 1 — the window-per-block pass took 72 / 340 us)
+  int variant = batch <= 2 ? 3 : 2;
   if (const char* e = getenv("GPAR_SS3_VARIANT")) variant = atoi(e);
   const int payload = SS2_STEPS - W;
   int nseg, nc = 0; int64_t R = 0;
