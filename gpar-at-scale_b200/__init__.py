@@ -7,8 +7,8 @@ ABI with ctypes.  Import it as `gpar_at_scale_b200` (the loader at the repo root
 directory to that module name).
 """
 from ._ffi import (EQ, MATERN12, MATERN32, MATERN52, GparError, PosDefException, load_library, LIB_PATH)
-from .context import Context
+from .context import Context, Group
 from . import api, neldermead, parallel, data, chain
 
 __all__ = ["EQ", "MATERN12", "MATERN32", "MATERN52", "GparError", "PosDefException", "load_library",
-           "LIB_PATH", "Context"]
+           "LIB_PATH", "Context", "Group"]

@@ -53,7 +53,26 @@ SIGNATURES = {
     "gpar_exact_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),
     "gpar_exact_posterior": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32,
                                             _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
+    "gpar_group_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.POINTER(_c_void_p)]),
+    "gpar_group_destroy": (ctypes.c_int, [_c_void_p]),
+    "gpar_group_size": (ctypes.c_int32, [_c_void_p]),
+    "gpar_group_ctx": (_c_void_p, [_c_void_p, ctypes.c_int32]),
+    "gpar_group_last_error": (ctypes.c_char_p, [_c_void_p]),
+    "gpar_group_dtc_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double,
+                                             _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32)]),
+    "gpar_group_scaled_dtc": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p,
+                                             _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32)]),
+    "gpar_group_fit": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64, _c_void_p, ctypes.c_int32, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int32, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "gpar_group_broadcast": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p]),
+    "gpar_set_inputs_column": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p]),
 }
+
+
+class FitTask(ctypes.Structure):
+    """struct gpar_fit_task (include/gpar_b200.h)"""
+    _fields_ = [("X", _c_double_p), ("D", ctypes.c_int32), ("Z", _c_double_p), ("M", ctypes.c_int64), ("y", _c_double_p),
+                ("theta0", ctypes.c_double * 5)]
 
 _lib = None
 

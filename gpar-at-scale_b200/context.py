@@ -10,8 +10,15 @@ class Context:
     evaluations, as the optimiser closures of the reference re-evaluate the objective hundreds of
     times on fixed data (src/gp/dtc.jl:29-61)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self._lib = _ffi.load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:       # a member context of a Group: the group owns the handle
+            self._h = ctypes.c_void_p(_borrowed)
+            self.device = int(device)
+            self.N = self.M = self.D = 0
+            self.batch = 0
+            return
         h = ctypes.c_void_p()
         st = self._lib.gpar_ctx_create(int(device), ctypes.byref(h))
         if st != _ffi.GPAR_OK:
@@ -32,7 +39,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            self._lib.gpar_ctx_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._lib.gpar_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -65,6 +73,11 @@ class Context:
         X = as_f64(np.atleast_2d(X) if np.ndim(X) > 1 else np.asarray(X, dtype=np.float64).reshape(-1, 1))
         self._check(self._lib.gpar_set_inputs(self._h, dptr(X), X.shape[1], X.shape[0]))
         self.N, self.D = X.shape
+
+    def set_inputs_column(self, d, col=None):
+        """Column d of the resident inputs <- col, or (col=None) the chain buffer a Group.broadcast filled."""
+        c = None if col is None else as_f64(np.asarray(col).ravel())
+        self._check(self._lib.gpar_set_inputs_column(self._h, int(d), dptr(c)))
 
     def set_pseudo(self, Z):
         Z = as_f64(np.atleast_2d(Z) if np.ndim(Z) > 1 else np.asarray(Z, dtype=np.float64).reshape(-1, 1))
@@ -231,3 +244,92 @@ class Context:
         self._check(self._lib.gpar_exact_posterior(self._h, int(k_time), int(k_out), dptr(th), th.shape[0],
                                                    dptr(Xs), Xs.shape[0], dptr(mean), dptr(var)))
         return mean, var
+
+
+class Group:
+    """Several devices of one box from ONE process (gpar_group_*, include/gpar_b200.h): one member Context per
+    device; concurrent objective evaluations, whole Nelder-Mead fits of a task list, NCCL all-gather of the scalars
+    and broadcast of posterior means down the GPAR chain."""
+
+    def __init__(self, devices):
+        self._lib = _ffi.load_library()
+        devs = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        st = self._lib.gpar_group_create(devs, len(devices), ctypes.byref(h))
+        if st != _ffi.GPAR_OK:
+            raise _ffi.GparError(st, "gpar_group_create(%s) failed (devices / NCCL unavailable?)" % (list(devices),))
+        self._h = h
+        self.devices = [int(d) for d in devices]
+        self.members = [Context(d, _borrowed=self._lib.gpar_group_ctx(h, i)) for i, d in enumerate(self.devices)]
+
+    def __len__(self):
+        return len(self.members)
+
+    def _check(self, st):
+        if st != _ffi.GPAR_OK:
+            msg = self._lib.gpar_group_last_error(self._h).decode("utf-8", "replace")
+            raise (_ffi.PosDefException if st == _ffi.GPAR_ERR_NOT_POSDEF else _ffi.GparError)(st, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            for m in self.members:
+                m._h = None
+            self._lib.gpar_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dtc_logpdf(self, kernel, thetas, vfe=False, jitter=-1.0, grad=False):
+        """thetas: (ndev, 3), member i evaluates row i on its resident data -> vals (ndev,), [grads (ndev, 3)], codes."""
+        th = as_f64(np.atleast_2d(thetas)); n = len(self)
+        assert th.shape == (n, 3)
+        vals = np.zeros(n); grads = np.zeros((n, 3)) if grad else None; codes = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.gpar_group_dtc_logpdf(self._h, int(kernel), dptr(th), int(bool(vfe)), float(jitter), dptr(vals), dptr(grads),
+                                                    codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return (vals, grads, codes) if grad else (vals, codes)
+
+    def scaled_dtc(self, k_time, k_out, thetas, grad=False):
+        th = as_f64(np.atleast_2d(thetas)); n = len(self)
+        assert th.shape == (n, 5)
+        vals = np.zeros(n); grads = np.zeros((n, 5)) if grad else None; codes = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.gpar_group_scaled_dtc(self._h, int(k_time), int(k_out), dptr(th), dptr(vals), dptr(grads),
+                                                    codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return (vals, grads, codes) if grad else (vals, codes)
+
+    def fit(self, t, tasks, k_time, k_out, iterations):
+        """tasks: list of dicts {X (N, D) or None, Z (M, D) or None, y (N,), theta0} -> (minimum, minimizer (ntasks, 5),
+        f_calls, member_of)."""
+        t = as_f64(np.asarray(t).ravel())
+        arr = (_ffi.FitTask * len(tasks))()
+        keep = []
+        for k, tk in enumerate(tasks):
+            y = as_f64(np.asarray(tk["y"]).ravel()); keep.append(y)
+            arr[k].y = dptr(y)
+            if tk.get("X") is not None:
+                X = as_f64(np.atleast_2d(tk["X"])); Z = as_f64(np.atleast_2d(tk["Z"])); keep += [X, Z]
+                arr[k].X = dptr(X); arr[k].D = X.shape[1]; arr[k].Z = dptr(Z); arr[k].M = Z.shape[0]
+            else:
+                arr[k].X = None; arr[k].D = 0; arr[k].Z = None; arr[k].M = 0
+            th0 = np.asarray(tk["theta0"], dtype=np.float64)
+            for j in range(5):
+                arr[k].theta0[j] = float(th0[j]) if j < th0.size else 0.0
+        n = len(tasks)
+        minimum = np.full(n, np.nan); minimizer = np.full((n, 5), np.nan)
+        calls = np.zeros(n, dtype=np.int32); member = np.full(n, -1, dtype=np.int32)
+        self._check(self._lib.gpar_group_fit(self._h, dptr(t), t.shape[0], ctypes.cast(arr, ctypes.c_void_p), n, int(k_time), int(k_out),
+                                             int(iterations), dptr(minimum), dptr(minimizer),
+                                             calls.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), member.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return minimum, minimizer, calls, member
+
+    def broadcast(self, src, values=None, n=None):
+        """values (host) or the resident result of member src's last smooth / predict -> every member's chain
+        buffer; returns the host copy read back from a receiving member."""
+        v = None if values is None else as_f64(np.asarray(values).ravel())
+        n = int(v.shape[0] if v is not None else n)
+        out = np.zeros(n)
+        self._check(self._lib.gpar_group_broadcast(self._h, int(src), dptr(v), n, dptr(out)))
+        return out

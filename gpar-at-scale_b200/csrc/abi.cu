@@ -74,7 +74,7 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->panelB, &ctx->kal_f, &ctx->partial, &ctx->segs,
                     &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
-                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->mrg, &ctx->test_pos, &ctx->shbuf};
+                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->mrg, &ctx->test_pos, &ctx->shbuf, &ctx->chain};
   for (DevBuf* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);

@@ -65,6 +65,7 @@ struct gpar_ctx {
   DevBuf mrg, test_pos; int64_t merged_N = 0, merged_Ns = 0; const double* res_a = nullptr; const double* res_b = nullptr; int64_t res_len = 0;
   DevBuf shbuf;                       // shared-model smoother: tables, chunk states, filtered means (smooth_shared.cu)
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
+  DevBuf chain; int64_t chain_n = 0;                  // values passed down the GPAR chain (gpar_group_broadcast / gpar_set_inputs_column)
   void* pinned = nullptr; size_t pinned_cap = 0;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;

@@ -1,0 +1,357 @@
+// group.cu — several devices of one box driven from ONE host process through the C ABI (SURVEY 8e, 8b
+// `gpar_group_*`): the Julia package is a single process, so "one process per GPU + torch.distributed"
+// (gpar-at-scale_b200/parallel.py, bench.py --gpus N) is not available to it.
+//
+// The shards are the ones the reference's drivers expose: per-output conditional GPs and hyper-parameter
+// restarts (examples/GPAR_scaled_examples.jl:132-175 fits output i on the OBSERVED outputs < i, so the fits are
+// independent; util.jl:128-134 draws the restart start points).  A group owns one gpar_ctx per device and
+//   * evaluates one objective per member concurrently (one host thread per device: every entry point of the
+//     single-device ABI blocks on its own stream),
+//   * runs whole Nelder-Mead fits (dtc.jl:58-61; temporal_gp_inference.jl:82) of a task list, tasks handed out
+//     dynamically, longest first,
+//   * all-gathers the SCALARS (status, value, gradient / minimum, minimiser) with NCCL so that every device holds
+//     the table, and broadcasts posterior means down the GPAR chain (GPAR_scaled_examples.jl:172) with ncclBroadcast
+//     over NVLink.  No collective touches the data path.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the library has no link-time dependency on it).
+#include "common.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <thread>
+
+struct gpar_group {
+  std::vector<gpar_ctx*> ctx;
+  std::vector<int> dev;
+  std::vector<ncclComm_t> comm;
+  std::vector<DevBuf> send, recv;       // scalar tables
+  void* lib = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string err;
+};
+
+namespace {
+
+int group_fail(gpar_group* g, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (g) g->err = buf;
+  return code;
+}
+#define GCU(call)                                                                                                   \
+  do { cudaError_t e_ = (call);                                                                                     \
+       if (e_ != cudaSuccess) return group_fail(g, GPAR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define GNC(call)                                                                                                   \
+  do { ncclResult_t r_ = (call);                                                                                    \
+       if (r_ != ncclSuccess) return group_fail(g, GPAR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, g->GetErrorString(r_), __FILE__, __LINE__); } while (0)
+
+int load_nccl(gpar_group* g) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g->lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g->lib) break; }
+  if (!g->lib) return group_fail(g, GPAR_ERR_CUDA, "gpar_group_create: libnccl.so.2 not found (%s)", dlerror());
+#define BIND(field, sym)                                                                                            \
+  g->field = reinterpret_cast<decltype(g->field)>(dlsym(g->lib, sym));                                               \
+  if (!g->field) return group_fail(g, GPAR_ERR_CUDA, "gpar_group_create: symbol %s missing in libnccl", sym)
+  BIND(CommInitAll, "ncclCommInitAll"); BIND(CommDestroy, "ncclCommDestroy"); BIND(AllGather, "ncclAllGather");
+  BIND(Broadcast, "ncclBroadcast"); BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd");
+  BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+  return GPAR_OK;
+}
+
+// rows: per member `width` doubles (host, member-major).  Every device ends up with the ndev x width table
+// (g->recv[i]); `table` (host, nullable) receives member 0's copy.
+int allgather_rows(gpar_group* g, const double* rows, int width, double* table) {
+  const int n = (int)g->ctx.size();
+  for (int i = 0; i < n; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    GCU(g->send[i].reserve((size_t)width * sizeof(double)));
+    GCU(g->recv[i].reserve((size_t)width * n * sizeof(double)));
+    GCU(cudaMemcpyAsync(g->send[i].p, rows + (size_t)i * width, (size_t)width * sizeof(double), cudaMemcpyHostToDevice, g->ctx[i]->stream));
+  }
+  GNC(g->GroupStart());
+  for (int i = 0; i < n; i++) GNC(g->AllGather(g->send[i].p, g->recv[i].p, (size_t)width, ncclDouble, g->comm[i], g->ctx[i]->stream));
+  GNC(g->GroupEnd());
+  for (int i = 0; i < n; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    if (i == 0 && table) GCU(cudaMemcpyAsync(table, g->recv[0].p, (size_t)width * n * sizeof(double), cudaMemcpyDeviceToHost, g->ctx[0]->stream));
+    GCU(cudaStreamSynchronize(g->ctx[i]->stream));
+  }
+  return GPAR_OK;
+}
+
+// one host thread per member; fn(i) -> status of member i
+template <class Fn>
+void run_members(gpar_group* g, std::vector<int>& codes, Fn fn) {
+  const int n = (int)g->ctx.size();
+  codes.assign(n, GPAR_OK);
+  if (n == 1) { codes[0] = fn(0); return; }
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; i++) th.emplace_back([&, i]() { cudaSetDevice(g->dev[i]); codes[i] = fn(i); });
+  for (auto& t : th) t.join();
+}
+
+// The Nelder-Mead of gpar-at-scale_b200/neldermead.py (the restatement of Optim.jl's defaults: AffineSimplexer
+// a = 0.025, b = 0.5; adaptive parameters; g_tol = 1e-8 on sqrt(var(f) n/(n+1)); the centroid is also tried at the
+// end), operation for operation, so that both host layers walk the same simplices.
+template <class F>
+void nelder_mead(F f, const double* x0, int n, int iterations, double g_tol, double* xbest, double* fbest, int* calls_out) {
+  const int m = n + 1;
+  const double alpha = 1.0, beta = 1.0 + 2.0 / n, gamma = 0.75 - 1.0 / (2.0 * n), delta = 1.0 - 1.0 / n;
+  std::vector<std::vector<double>> sx(m, std::vector<double>(x0, x0 + n));
+  for (int i = 0; i < n; i++) sx[i + 1][i] = 1.5 * x0[i] + 0.025;
+  std::vector<double> fv(m);
+  for (int i = 0; i < m; i++) fv[i] = f(sx[i].data());
+  int calls = m, it = 0;
+  std::vector<double> cen(n), xr(n), xe(n), xc(n);
+  while (it < iterations) {
+    std::vector<int> order(m);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fv[a] < fv[b]; });
+    { std::vector<std::vector<double>> s2(m); std::vector<double> f2(m);
+      for (int i = 0; i < m; i++) { s2[i] = sx[order[i]]; f2[i] = fv[order[i]]; }
+      sx.swap(s2); fv.swap(f2); }
+    double mean = 0.0; for (double v : fv) mean += v; mean /= m;
+    double var = 0.0; for (double v : fv) var += (v - mean) * (v - mean); var /= (m - 1);
+    if (std::sqrt(var * ((double)n / m)) <= g_tol) break;
+    it++;
+    for (int j = 0; j < n; j++) { double s = 0.0; for (int i = 0; i < m - 1; i++) s += sx[i][j]; cen[j] = s / (m - 1); }
+    for (int j = 0; j < n; j++) xr[j] = cen[j] + alpha * (cen[j] - sx[m - 1][j]);
+    const double fr = f(xr.data()); calls++;
+    if (fr < fv[0]) {
+      for (int j = 0; j < n; j++) xe[j] = cen[j] + beta * (xr[j] - cen[j]);
+      const double fe = f(xe.data()); calls++;
+      if (fe < fr) { sx[m - 1] = xe; fv[m - 1] = fe; } else { sx[m - 1] = xr; fv[m - 1] = fr; }
+    } else if (fr < fv[m - 2]) {
+      sx[m - 1] = xr; fv[m - 1] = fr;
+    } else {
+      bool ok; double fc;
+      if (fr < fv[m - 1]) { for (int j = 0; j < n; j++) xc[j] = cen[j] + gamma * (xr[j] - cen[j]); fc = f(xc.data()); calls++; ok = fc <= fr; }
+      else { for (int j = 0; j < n; j++) xc[j] = cen[j] - gamma * (xr[j] - cen[j]); fc = f(xc.data()); calls++; ok = fc < fv[m - 1]; }
+      if (ok) { sx[m - 1] = xc; fv[m - 1] = fc; }
+      else for (int i = 1; i < m; i++) { for (int j = 0; j < n; j++) sx[i][j] = sx[0][j] + delta * (sx[i][j] - sx[0][j]); fv[i] = f(sx[i].data()); calls++; }
+    }
+  }
+  int best = 0;
+  for (int i = 1; i < m; i++) if (fv[i] < fv[best]) best = i;
+  for (int j = 0; j < n; j++) { double s = 0.0; for (int i = 0; i < m; i++) s += sx[i][j]; cen[j] = s / m; }
+  const double fcen = f(cen.data()); calls++;
+  if (fcen < fv[best]) { std::copy(cen.begin(), cen.end(), xbest); *fbest = fcen; }
+  else { std::copy(sx[best].begin(), sx[best].end(), xbest); *fbest = fv[best]; }
+  *calls_out = calls;
+}
+
+// Member i evaluates thetas[:, i] on ITS OWN resident data (gpar_set_* on gpar_group_ctx(g, i)), all members at once.
+// codes[i] = the member's status: a failed Cholesky (GPAR_ERR_NOT_POSDEF) does not fail the call — an optimiser treats
+// it as +Inf — any other member error does.  width 8 rows (status, value, gradient) are all-gathered with NCCL.
+int group_eval(gpar_group* g, int ntheta, const double* thetas, double* vals, double* grads, int32_t* codes,
+                      const std::function<int(int, const double*, double*, double*)>& eval) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!thetas || !vals) return group_fail(g, GPAR_ERR_INVALID, "group evaluation: thetas and vals must not be NULL");
+  const int n = (int)g->ctx.size();
+  std::vector<double> rows((size_t)n * 8, 0.0), table((size_t)n * 8);
+  std::vector<int> st;
+  run_members(g, st, [&](int i) {
+    double v = std::numeric_limits<double>::quiet_NaN(), gr[5] = {0, 0, 0, 0, 0};
+    int rc = eval(i, thetas + (size_t)ntheta * i, &v, grads ? gr : nullptr);
+    rows[(size_t)i * 8] = rc; rows[(size_t)i * 8 + 1] = v;
+    for (int j = 0; j < ntheta; j++) rows[(size_t)i * 8 + 2 + j] = gr[j];
+    return rc;
+  });
+  for (int i = 0; i < n; i++)
+    if (st[i] != GPAR_OK && st[i] != GPAR_ERR_NOT_POSDEF) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  int rc = allgather_rows(g, rows.data(), 8, table.data());
+  if (rc != GPAR_OK) return rc;
+  for (int i = 0; i < n; i++) {
+    if (codes) codes[i] = (int32_t)table[(size_t)i * 8];
+    vals[i] = table[(size_t)i * 8 + 1];
+    if (grads) for (int j = 0; j < ntheta; j++) grads[(size_t)ntheta * i + j] = table[(size_t)i * 8 + 2 + j];
+  }
+  return GPAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpar_group_create(const int32_t* devices, int32_t ndev, gpar_group** out) {
+  if (!out) return GPAR_ERR_INVALID;
+  *out = nullptr;
+  if (!devices || ndev < 1) return GPAR_ERR_INVALID;
+  gpar_group* g = new gpar_group();
+  auto bail = [&](int code) { for (gpar_ctx* c : g->ctx) gpar_ctx_destroy(c); if (g->lib) dlclose(g->lib); delete g; return code; };
+  for (int i = 0; i < ndev; i++) {
+    for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return bail(GPAR_ERR_INVALID);      // one member per device
+    gpar_ctx* c = nullptr;
+    int rc = gpar_ctx_create(devices[i], &c);
+    if (rc != GPAR_OK) return bail(rc);
+    g->ctx.push_back(c); g->dev.push_back(devices[i]);
+  }
+  if (load_nccl(g) != GPAR_OK) { fprintf(stderr, "%s\n", g->err.c_str()); return bail(GPAR_ERR_CUDA); }
+  g->comm.resize(ndev); g->send.resize(ndev); g->recv.resize(ndev);
+  ncclResult_t r = g->CommInitAll(g->comm.data(), ndev, g->dev.data());
+  if (r != ncclSuccess) { fprintf(stderr, "gpar_group_create: ncclCommInitAll failed: %s\n", g->GetErrorString(r)); g->comm.clear(); return bail(GPAR_ERR_CUDA); }
+  *out = g;
+  return GPAR_OK;
+}
+
+int gpar_group_destroy(gpar_group* g) {
+  if (!g) return GPAR_OK;
+  for (size_t i = 0; i < g->ctx.size(); i++) {
+    cudaSetDevice(g->dev[i]);
+    cudaStreamSynchronize(g->ctx[i]->stream);
+    if (i < g->comm.size()) g->CommDestroy(g->comm[i]);
+    g->send[i].release(); g->recv[i].release();
+    gpar_ctx_destroy(g->ctx[i]);
+  }
+  if (g->lib) dlclose(g->lib);
+  delete g;
+  return GPAR_OK;
+}
+
+int32_t gpar_group_size(const gpar_group* g) { return g ? (int32_t)g->ctx.size() : 0; }
+gpar_ctx* gpar_group_ctx(gpar_group* g, int32_t member) { return (g && member >= 0 && member < (int32_t)g->ctx.size()) ? g->ctx[member] : nullptr; }
+const char* gpar_group_last_error(const gpar_group* g) { return g ? g->err.c_str() : "null group"; }
+
+int gpar_group_dtc_logpdf(gpar_group* g, int kernel, const double* thetas, int vfe, double jitter, double* vals, double* grads, int32_t* codes) {
+  return group_eval(g, 3, thetas, vals, grads, codes, [&](int i, const double* th, double* v, double* gr) {
+    return gpar_dtc_logpdf(g->ctx[i], kernel, th, vfe, jitter, v, gr);
+  });
+}
+
+int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* thetas, double* vals, double* grads, int32_t* codes) {
+  return group_eval(g, 5, thetas, vals, grads, codes, [&](int i, const double* th, double* v, double* gr) {
+    return gr ? gpar_scaled_dtc_grad(g->ctx[i], k_time, k_out, th, v, gr) : gpar_scaled_dtc(g->ctx[i], k_time, k_out, th, v, nullptr);
+  });
+}
+
+// n doubles from member src — `host` if given, else the resident result of its last gpar_lgssm_smooth /
+// gpar_scaled_predict (posterior means) — to EVERY member's chain buffer (ncclBroadcast); out (nullable): host copy.
+int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t n, double* out) {
+  if (!g) return GPAR_ERR_INVALID;
+  const int nm = (int)g->ctx.size();
+  if (src < 0 || src >= nm || n < 1) return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: bad source member %d or length %lld", src, (long long)n);
+  gpar_ctx* sc = g->ctx[src];
+  if (!host && (!sc->res_a || sc->res_len < n)) return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: member %d holds no resident result of length >= %lld", src, (long long)n);
+  for (int i = 0; i < nm; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    GCU(g->ctx[i]->chain.reserve((size_t)n * sizeof(double)));
+    g->ctx[i]->chain_n = n;
+  }
+  GCU(cudaSetDevice(g->dev[src]));
+  if (host) GCU(cudaMemcpyAsync(sc->chain.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, sc->stream));
+  else GCU(cudaMemcpyAsync(sc->chain.p, sc->res_a, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, sc->stream));
+  GNC(g->GroupStart());
+  for (int i = 0; i < nm; i++) GNC(g->Broadcast(g->ctx[i]->chain.p, g->ctx[i]->chain.p, (size_t)n, ncclDouble, src, g->comm[i], g->ctx[i]->stream));
+  GNC(g->GroupEnd());
+  for (int i = 0; i < nm; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    if (out && i == (src + 1) % nm) GCU(cudaMemcpyAsync(out, g->ctx[i]->chain.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g->ctx[i]->stream));   // a RECEIVER's copy
+    GCU(cudaStreamSynchronize(g->ctx[i]->stream));
+  }
+  return GPAR_OK;
+}
+
+// Whole fits of a task list: every member takes the next task (longest first) until none is left; per task the
+// data go to the member's device once and Nelder-Mead runs `iterations` iterations on the blocking objective
+// (dtc.jl:29-61: minimise -dtc; temporal_gp_inference.jl:69-82: minimise -logpdf for a time-only task, D = 0).
+// minimum[k], minimizer[5 k .. 5 k + 4] (NaN-padded for 3-parameter tasks), f_calls[k], member_of[k] (nullable).
+int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
+                   int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!t || N < 1 || !tasks || ntasks < 1 || !minimum || !minimizer) return group_fail(g, GPAR_ERR_INVALID, "group_fit: t, tasks, minimum and minimizer must be given");
+  for (int k = 0; k < ntasks; k++)
+    if (!tasks[k].y || (tasks[k].D > 0 && (!tasks[k].X || !tasks[k].Z || tasks[k].M < 1)) || tasks[k].D < 0)
+      return group_fail(g, GPAR_ERR_INVALID, "group_fit: task %d is incomplete", k);
+  const int n = (int)g->ctx.size();
+  std::vector<int> order(ntasks);
+  std::iota(order.begin(), order.end(), 0);
+  auto cost = [&](int k) { return tasks[k].D == 0 ? 0.02 : (1.0 + 0.03 * tasks[k].D) * (double)tasks[k].M * (double)tasks[k].M; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+  std::atomic<int> next(0);
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<double> rows((size_t)n * ntasks * 8, nan);      // per member: its tasks' (task, minimum, minimiser[5], calls)
+  std::vector<int> st;
+  run_members(g, st, [&](int i) {
+    gpar_ctx* c = g->ctx[i];
+    int rc = gpar_set_times(c, t, N);
+    if (rc != GPAR_OK) return rc;
+    for (;;) {
+      const int q = next.fetch_add(1);
+      if (q >= ntasks) break;
+      const int k = order[q];
+      const gpar_fit_task& tk = tasks[k];
+      rc = gpar_set_noise_vector(c, nullptr, 0);
+      if (rc == GPAR_OK) rc = gpar_set_outputs(c, tk.y, N, 1);
+      if (rc == GPAR_OK && tk.D > 0) rc = gpar_set_inputs(c, tk.X, tk.D, N);
+      if (rc == GPAR_OK && tk.D > 0) rc = gpar_set_pseudo(c, tk.Z, tk.D, tk.M);
+      if (rc != GPAR_OK) return rc;
+      const int np = tk.D > 0 ? 5 : 3;
+      int hard = GPAR_OK;
+      auto f = [&](const double* th) -> double {
+        double v = 0.0;
+        int r = tk.D > 0 ? gpar_scaled_dtc(c, k_time, k_out, th, &v, nullptr) : gpar_lgssm_logpdf(c, k_time, th, 1, &v);
+        if (r == GPAR_ERR_NOT_POSDEF) return std::numeric_limits<double>::infinity();      // what the Python mirror does with a PosDefException
+        if (r != GPAR_OK) { hard = r; return std::numeric_limits<double>::infinity(); }
+        return -v;
+      };
+      double xb[5] = {nan, nan, nan, nan, nan}, fb = nan; int calls = 0;
+      nelder_mead(f, tk.theta0, np, iterations, 1e-8, xb, &fb, &calls);
+      if (hard != GPAR_OK) return hard;
+      double* row = rows.data() + ((size_t)i * ntasks + k) * 8;
+      row[0] = k; row[1] = fb; for (int j = 0; j < 5; j++) row[2 + j] = xb[j]; row[7] = calls;
+    }
+    return (int)GPAR_OK;
+  });
+  for (int i = 0; i < n; i++)
+    if (st[i] != GPAR_OK) return group_fail(g, st[i], "group_fit: member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  std::vector<double> table((size_t)n * ntasks * 8);
+  int rc = allgather_rows(g, rows.data(), ntasks * 8, table.data());
+  if (rc != GPAR_OK) return rc;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < ntasks; k++) {
+      const double* row = table.data() + ((size_t)i * ntasks + k) * 8;
+      if (row[0] != row[0]) continue;       // not this member's task
+      minimum[k] = row[1];
+      for (int j = 0; j < 5; j++) minimizer[(size_t)5 * k + j] = row[2 + j];
+      if (f_calls) f_calls[k] = (int32_t)row[7];
+      if (member_of) member_of[k] = i;
+    }
+  return GPAR_OK;
+}
+
+// Column d of the resident inputs X (N records of D doubles) <- col (host), or, with col == NULL, the context's
+// chain buffer (filled by gpar_group_broadcast): the predicted means of an earlier output become an input feature
+// of the later ones without a host round trip (GPAR_scaled_examples.jl:172).
+__global__ void set_column_kernel(double* __restrict__ X, int D, int d, const double* __restrict__ col, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) X[i * D + d] = col[i];
+}
+
+int gpar_set_inputs_column(gpar_ctx* ctx, int32_t d, const double* col) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (ctx->N < 1 || d < 0 || d >= ctx->D) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_inputs_column: column %d outside the resident inputs (D = %d, N = %lld)", d, ctx->D, (long long)ctx->N);
+  CU(cudaSetDevice(ctx->device));
+  if (col) {
+    CU(ctx->chain.reserve((size_t)ctx->N * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->chain.p, col, (size_t)ctx->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->chain_n = ctx->N;
+  } else if (ctx->chain_n != ctx->N) {
+    return gpar_fail(ctx, GPAR_ERR_INVALID, "set_inputs_column: chain buffer holds %lld values, the inputs have %lld records", (long long)ctx->chain_n, (long long)ctx->N);
+  }
+  LAUNCH(ctx, set_column_kernel, (unsigned)((ctx->N + 255) / 256), 256, 0, ctx->X.as<double>(), ctx->D, d, ctx->chain.as<double>(), ctx->N);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+}  // extern "C"

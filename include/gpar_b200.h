@@ -169,6 +169,51 @@ int gpar_exact_logpdf(gpar_ctx* ctx, int k_time, int k_out, const double* theta,
 int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* theta, int32_t ntheta,
                          const double* Xs, int64_t Ns, double* mean, double* var);
 
+/* ---- several devices of one box from ONE host process --------------------------
+ * The shards are the reference's own: per-output conditional GPs (examples/GPAR_scaled_examples.jl:132-175 fits
+ * output i on the OBSERVED outputs < i, so the fits are independent) and hyper-parameter restarts (util.jl:128-134).
+ * A group owns one context per device; load each member's data with the gpar_set_* calls on gpar_group_ctx(g, i).
+ * No collective touches the data path: NCCL (bound at run time from libnccl.so.2) all-gathers the scalars —
+ * (status, value, gradient) or (minimum, minimiser) — so that every device holds the table, and broadcasts posterior
+ * means down the GPAR chain (GPAR_scaled_examples.jl:172).  Group calls are blocking and not thread-safe. */
+typedef struct gpar_group gpar_group;
+int gpar_group_create(const int32_t* devices, int32_t ndev, gpar_group** out);   /* distinct device ordinals */
+int gpar_group_destroy(gpar_group* g);
+int32_t gpar_group_size(const gpar_group* g);
+gpar_ctx* gpar_group_ctx(gpar_group* g, int32_t member);                         /* borrowed, owned by the group */
+const char* gpar_group_last_error(const gpar_group* g);
+
+/* Member i evaluates thetas[:, i] (3 x ndev / 5 x ndev column-major) on ITS resident data, all members concurrently
+ * (one host thread per device).  vals[ndev]; grads (nullable) 3 x ndev / 5 x ndev; codes (nullable) receives each
+ * member's status — GPAR_ERR_NOT_POSDEF of a member does not fail the call (an optimiser reads it as +Inf). */
+int gpar_group_dtc_logpdf(gpar_group* g, int kernel, const double* thetas, int vfe, double jitter,
+                          double* vals, double* grads, int32_t* codes);             /* gpar_dtc_logpdf per member */
+int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* thetas,
+                          double* vals, double* grads, int32_t* codes);             /* gpar_scaled_dtc(_grad) per member */
+
+/* One conditional-GP fit of the chain: inputs X (D x N ColVecs = the observed earlier outputs; D = 0: a time-only
+ * state-space GP with 3 parameters, temporal_gp_inference.jl:69-82), pseudo-inputs Z (D x M), outputs y (N),
+ * start point theta0 (the first 3 or 5 entries are used). */
+typedef struct gpar_fit_task {
+  const double* X; int32_t D;
+  const double* Z; int64_t M;
+  const double* y;
+  double theta0[5];
+} gpar_fit_task;
+/* Nelder-Mead fits (src/gp/dtc.jl:58-61 with an iteration budget instead of a time limit) of all tasks on the common
+ * sorted time grid t (N): members take tasks dynamically, longest first.  minimum[ntasks] (of the NEGATED objective,
+ * as the reference minimises), minimizer 5 x ntasks (NaN-padded), f_calls / member_of (nullable) per task. */
+int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
+                   int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
+
+/* n doubles from member src — `host` if given, else the resident result of its last gpar_lgssm_smooth /
+ * gpar_scaled_predict (the posterior means) — into EVERY member's chain buffer (ncclBroadcast over NVLink);
+ * out (nullable) receives a host copy read from a receiving member. */
+int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t n, double* out);
+/* Column d of the resident inputs X <- col (host, N values) or, with col == NULL, the context's chain buffer: the
+ * predicted means of an earlier output become an input feature of the later outputs without a host round trip. */
+int gpar_set_inputs_column(gpar_ctx* ctx, int32_t d, const double* col);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,171 @@
+"""GPU: the single-process multi-device part of the C ABI (gpar_group_*).  With one member the group
+must reproduce the single-context entry points bit for bit; with two devices (skipped on a one-GPU box) the
+members work on different data concurrently and the NCCL-gathered tables must equal the per-context results."""
+import ctypes
+import numpy as np
+import pytest
+import oracle
+from oracle.dtc import scaled_gpar_objective
+
+pytestmark = pytest.mark.gpu
+
+
+def device_count():
+    lib = ctypes.CDLL("libcudart.so.12")
+    n = ctypes.c_int(0)
+    lib.cudaGetDeviceCount(ctypes.byref(n))
+    return n.value
+
+
+def problem(seed, n=3000, m=48, d=2):
+    rng = np.random.default_rng(seed)
+    t = np.cumsum(rng.exponential(1 / 30, n))
+    X = rng.normal(size=(n, d)); Z = X[:: n // m][:m].copy()
+    y = np.sin(t) + 0.5 * X[:, 0] + 0.1 * rng.normal(size=n)
+    return t, X, Z, y
+
+
+def load(c, t, X, Z, y):
+    c.set_times(t); c.set_inputs(X); c.set_pseudo(Z); c.set_outputs(y); c.set_noise_vector(None)
+
+
+def test_group_of_one_reproduces_the_context_entry_points(ctx):
+    import gpar_at_scale_b200 as gp
+    t, X, Z, y = problem(7)
+    g = gp.Group([0])
+    try:
+        load(g.members[0], t, X, Z, y); load(ctx, t, X, Z, y)
+        th3 = np.array([[0.1, -0.2, -1.5]]); th5 = np.array([[0.2, 0.1, -0.3, 0.2, -1.0]])
+        v, gr, codes = g.dtc_logpdf(gp.MATERN52, th3, grad=True)
+        v0, g0 = ctx.dtc_logpdf(gp.MATERN52, th3[0], grad=True)
+        assert codes[0] == 0 and v[0] == v0 and np.array_equal(gr[0], g0)
+        v, gr, codes = g.scaled_dtc(gp.MATERN52, gp.MATERN52, th5, grad=True)
+        v0, g0 = ctx.scaled_dtc_grad(gp.MATERN52, gp.MATERN52, th5[0])
+        assert codes[0] == 0 and v[0] == v0 and np.array_equal(gr[0], g0)
+        # and against the oracle, through the group
+        ref = scaled_gpar_objective(th5[0], X, Z, t, y)
+        assert abs(g.scaled_dtc(gp.MATERN52, gp.MATERN52, th5)[0][0] - ref) <= 1e-8 * abs(ref)
+        # a non-PD member evaluation is reported in codes, not raised
+        bad = np.array([[0.0, 40.0, 0.0, 40.0, -30.0]])
+        _, codes = g.scaled_dtc(gp.MATERN52, gp.MATERN52, bad)
+        assert codes[0] in (0, 3)
+    finally:
+        g.close()
+
+
+def test_group_chain_broadcast_and_input_column(ctx):
+    """Posterior means passed down the chain: broadcast (host values, then a resident smoother result) and
+    gpar_set_inputs_column; the objective must equal the one on host-assembled inputs."""
+    import gpar_at_scale_b200 as gp
+    t, X, Z, y = problem(8)
+    g = gp.Group([0])
+    try:
+        m = g.members[0]
+        load(m, t, X, Z, y)
+        col = np.cos(t)
+        back = g.broadcast(0, values=col)
+        assert np.array_equal(back, col)
+        m.set_inputs_column(1)                         # from the chain buffer
+        X2 = X.copy(); X2[:, 1] = col
+        load(ctx, t, X2, Z, y)
+        th5 = np.array([0.2, 0.1, -0.3, 0.2, -1.0])
+        assert m.scaled_dtc(gp.MATERN52, gp.MATERN52, th5) == ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5)
+        # resident result of a smoother -> chain buffer -> column 0
+        _, mean, _ = m.lgssm_smooth(gp.MATERN52, np.array([0.0, 0.0, -1.0]), keep_on_device=False)
+        back = g.broadcast(0, n=len(t))
+        assert np.array_equal(back, mean[0])
+        m.set_inputs_column(0)
+        X2[:, 0] = mean[0]
+        ctx.set_inputs(X2)
+        assert m.scaled_dtc(gp.MATERN52, gp.MATERN52, th5) == ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5)
+        with pytest.raises(gp.GparError):
+            m.set_inputs_column(5)
+    finally:
+        g.close()
+
+
+def chain_tasks(seed, n=2500, m=40, outputs=3, restarts=2):
+    rng = np.random.default_rng(seed)
+    t = np.cumsum(rng.exponential(1 / 30, n))
+    Y = np.zeros((outputs, n))
+    Y[0] = np.sin(t) + 0.1 * rng.normal(size=n)
+    for o in range(1, outputs):
+        Y[o] = np.cos(0.7 * t) + 0.5 * Y[o - 1] + 0.1 * rng.normal(size=n)
+    tasks = []
+    for o in range(outputs):
+        for r in range(restarts):
+            th0 = np.random.default_rng([seed, o, r]).random(3 if o == 0 else 5)
+            if o == 0:
+                tasks.append({"X": None, "Z": None, "y": Y[0], "theta0": th0})
+            else:
+                X = np.ascontiguousarray(Y[:o].T)
+                tasks.append({"X": X, "Z": np.ascontiguousarray(X[:: n // m][:m]), "y": Y[o], "theta0": th0})
+    return t, tasks
+
+
+def python_fit(ctx, t, tk, iterations):
+    import gpar_at_scale_b200 as gp
+    from gpar_at_scale_b200 import neldermead
+    ctx.set_times(t); ctx.set_outputs(tk["y"]); ctx.set_noise_vector(None)
+    if tk["X"] is None:
+        f = lambda th: -ctx.lgssm_logpdf(gp.MATERN52, th)[0]
+    else:
+        ctx.set_inputs(tk["X"]); ctx.set_pseudo(tk["Z"])
+
+        def f(th):
+            try:
+                return -ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th)
+            except gp.PosDefException:
+                return np.inf
+    return neldermead.optimize(f, tk["theta0"], iterations=iterations)
+
+
+def test_group_fit_walks_the_same_simplices_as_the_python_mirror(ctx):
+    """gpar_group_fit (C++ Nelder-Mead inside the library) against neldermead.py over the single-context ABI:
+    same objective values in the same order, so minimum, minimiser and evaluation count are identical."""
+    import gpar_at_scale_b200 as gp
+    t, tasks = chain_tasks(11)
+    g = gp.Group([0])
+    try:
+        minimum, minimizer, calls, member = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=12)
+    finally:
+        g.close()
+    for k, tk in enumerate(tasks):
+        res = python_fit(ctx, t, tk, 12)
+        p = 3 if tk["X"] is None else 5
+        assert calls[k] == res.f_calls and member[k] == 0
+        assert minimum[k] == pytest.approx(res.minimum, rel=1e-13)
+        assert np.allclose(minimizer[k, :p], res.minimizer, rtol=1e-13, atol=0) and np.all(np.isnan(minimizer[k, p:]))
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs two devices (gpurun --gpus 2)")
+def test_group_of_two_devices():
+    import gpar_at_scale_b200 as gp
+    g = gp.Group([0, 1]); g1 = gp.Group([0])
+    try:
+        probs = [problem(21), problem(22, n=4100, m=33, d=3)]
+        for mbr, pr in zip(g.members, probs):
+            load(mbr, *pr)
+        th5 = np.array([[0.2, 0.1, -0.3, 0.2, -1.0], [-0.1, 0.3, 0.1, -0.2, -0.7]])
+        v, gr, codes = g.scaled_dtc(gp.MATERN52, gp.MATERN52, th5, grad=True)
+        for i, pr in enumerate(probs):
+            load(g1.members[0], *pr)
+            v0, g0, _ = g1.scaled_dtc(gp.MATERN52, gp.MATERN52, th5[i:i + 1], grad=True)
+            assert codes[i] == 0 and v[i] == v0[0] and np.array_equal(gr[i], g0[0])
+        # chain: member 1 smooths, its means reach member 0's inputs over NCCL
+        _, mean, _ = g.members[1].lgssm_smooth(gp.MATERN52, np.array([0.0, 0.0, -1.0]))
+        n0 = probs[0][0].shape[0]
+        back = g.broadcast(1, n=n0)
+        assert np.array_equal(back, mean[0][:n0])
+        g.members[0].set_inputs_column(1)
+        X2 = probs[0][1].copy(); X2[:, 1] = mean[0][:n0]
+        load(g1.members[0], probs[0][0], X2, probs[0][2], probs[0][3])
+        assert g.members[0].scaled_dtc(gp.MATERN52, gp.MATERN52, th5[0]) == g1.members[0].scaled_dtc(gp.MATERN52, gp.MATERN52, th5[0])
+        # fits: dynamic hand-out over two members, same results as one member
+        t, tasks = chain_tasks(12)
+        a = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=6)
+        b = g1.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=6)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2])
+        assert set(a[3].tolist()) == {0, 1}
+    finally:
+        g.close(); g1.close()
