@@ -170,4 +170,71 @@ function exact_posterior(c::Ctx, k_time, k_out, theta::Vector{Float64}, Xs::Matr
     return mean, var
 end
 
+# ---- several devices from this one Julia process (gpar_group_*): one member context per device -------------
+struct FitTask                       # struct gpar_fit_task (include/gpar_b200.h); isbits, C layout
+    X::Ptr{Float64}; D::Int32
+    Z::Ptr{Float64}; M::Int64
+    y::Ptr{Float64}
+    theta0::NTuple{5, Float64}
+end
+
+mutable struct Group
+    h::Ptr{Cvoid}
+    members::Vector{Ctx}
+    function Group(devices::Vector{<:Integer})
+        r = Ref{Ptr{Cvoid}}(C_NULL); devs = Int32.(devices)
+        st = ccall((:gpar_group_create, LIB), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), r)
+        st == GPAR_OK || error("gpar_group_create failed with status $st (devices / NCCL unavailable?)")
+        ms = [borrowed_ctx(ccall((:gpar_group_ctx, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), r[], i - 1)) for i in 1:length(devs)]
+        g = new(r[], ms)
+        finalizer(x -> ccall((:gpar_group_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), g)
+        return g
+    end
+end
+borrowed_ctx(h::Ptr{Cvoid}) = (c = ccall(:jl_new_struct_uninit, Any, (Any,), Ctx)::Ctx; c.h = h; c)   # no finalizer: the group owns it
+
+function gcheck(g::Group, st::Integer)
+    st == GPAR_OK && return nothing
+    error("libgpar_b200 group status $st: " * unsafe_string(ccall((:gpar_group_last_error, LIB), Cstring, (Ptr{Cvoid},), g.h)))
+end
+
+# member i evaluates thetas[:, i] on its resident data, all members at once -> (vals, grads, codes)
+function group_scaled_dtc(g::Group, k_time, k_out, thetas::Matrix{Float64}; grad::Bool = false)
+    n = length(g.members); vals = zeros(n); codes = zeros(Int32, n); grads = grad ? zeros(5, n) : nothing
+    gcheck(g, ccall((:gpar_group_scaled_dtc, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                    g.h, kernel_code(k_time), kernel_code(k_out), thetas, vals, grad ? grads : C_NULL, codes))
+    return vals, grads, codes
+end
+function group_dtc_logpdf(g::Group, k, thetas::Matrix{Float64}; vfe::Bool = false, jitter::Float64 = -1.0, grad::Bool = false)
+    n = length(g.members); vals = zeros(n); codes = zeros(Int32, n); grads = grad ? zeros(3, n) : nothing
+    gcheck(g, ccall((:gpar_group_dtc_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                    g.h, kernel_code(k), thetas, vfe, jitter, vals, grad ? grads : C_NULL, codes))
+    return vals, grads, codes
+end
+
+# whole Nelder-Mead fits of the chain's conditional GPs; Xs[k] (D x N) / Zs[k] (D x M) are `nothing` for a time-only task
+function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float64}}, theta0s::Vector{Vector{Float64}}, k_time, k_out; iterations::Integer = 200)
+    nt = length(ys)
+    GC.@preserve Xs Zs ys begin
+        tasks = [FitTask(Xs[k] === nothing ? C_NULL : pointer(Xs[k]), Xs[k] === nothing ? 0 : size(Xs[k], 1),
+                         Zs[k] === nothing ? C_NULL : pointer(Zs[k]), Zs[k] === nothing ? 0 : size(Zs[k], 2), pointer(ys[k]),
+                         ntuple(j -> j <= length(theta0s[k]) ? theta0s[k][j] : 0.0, 5)) for k in 1:nt]
+        minimum = fill(NaN, nt); minimizer = fill(NaN, 5, nt); calls = zeros(Int32, nt); member = fill(Int32(-1), nt)
+        gcheck(g, ccall((:gpar_group_fit, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{FitTask}, Int32, Cint, Cint, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                        g.h, t, length(t), tasks, nt, kernel_code(k_time), kernel_code(k_out), iterations, minimum, minimizer, calls, member))
+    end
+    return minimum, minimizer, calls, member
+end
+
+# posterior means down the chain: resident result of member `src` (or `values`) -> every member's chain buffer
+function group_broadcast(g::Group, src::Integer, n::Integer; values::Union{Nothing, Vector{Float64}} = nothing)
+    out = zeros(n)
+    gcheck(g, ccall((:gpar_group_broadcast, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Ptr{Float64}),
+                    g.h, src, values === nothing ? C_NULL : values, n, out))
+    return out
+end
+set_inputs_column!(c::Ctx, d::Integer, col::Union{Nothing, Vector{Float64}} = nothing) =
+    check(c, ccall((:gpar_set_inputs_column, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), c.h, d, col === nothing ? C_NULL : col))
+
 end # module
