@@ -26,6 +26,7 @@ mutable struct Ctx
         finalizer(x -> ccall((:gpar_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
         return c
     end
+    Ctx(h::Ptr{Cvoid}, ::Val{:borrowed}) = new(h)      # member of a Group: the group owns the handle, no finalizer
 end
 
 function check(c::Ctx, st::Integer)
@@ -185,13 +186,12 @@ mutable struct Group
         r = Ref{Ptr{Cvoid}}(C_NULL); devs = Int32.(devices)
         st = ccall((:gpar_group_create, LIB), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), r)
         st == GPAR_OK || error("gpar_group_create failed with status $st (devices / NCCL unavailable?)")
-        ms = [borrowed_ctx(ccall((:gpar_group_ctx, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), r[], i - 1)) for i in 1:length(devs)]
+        ms = [Ctx(ccall((:gpar_group_ctx, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), r[], i - 1), Val(:borrowed)) for i in 1:length(devs)]
         g = new(r[], ms)
         finalizer(x -> ccall((:gpar_group_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), g)
         return g
     end
 end
-borrowed_ctx(h::Ptr{Cvoid}) = (c = ccall(:jl_new_struct_uninit, Any, (Any,), Ctx)::Ctx; c.h = h; c)   # no finalizer: the group owns it
 
 function gcheck(g::Group, st::Integer)
     st == GPAR_OK && return nothing
