@@ -300,7 +300,7 @@ class Group:
                                                     codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         return (vals, grads, codes) if grad else (vals, codes)
 
-    def fit(self, t, tasks, k_time, k_out, iterations):
+    def fit(self, t, tasks, k_time, k_out, iterations, optimizer="neldermead"):
         """tasks: list of dicts {X (N, D) or None, Z (M, D) or None, y (N,), theta0} -> (minimum, minimizer (ntasks, 5),
         f_calls, member_of)."""
         t = as_f64(np.asarray(t).ravel())
@@ -321,7 +321,7 @@ class Group:
         minimum = np.full(n, np.nan); minimizer = np.full((n, 5), np.nan)
         calls = np.zeros(n, dtype=np.int32); member = np.full(n, -1, dtype=np.int32)
         self._check(self._lib.gpar_group_fit(self._h, dptr(t), t.shape[0], ctypes.cast(arr, ctypes.c_void_p), n, int(k_time), int(k_out),
-                                             int(iterations), dptr(minimum), dptr(minimizer),
+                                             {"neldermead": 0, "lbfgs": 1}[optimizer], int(iterations), dptr(minimum), dptr(minimizer),
                                              calls.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), member.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         return minimum, minimizer, calls, member
 

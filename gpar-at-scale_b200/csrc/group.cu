@@ -151,6 +151,55 @@ void nelder_mead(F f, const double* x0, int n, int iterations, double g_tol, dou
   *calls_out = calls;
 }
 
+// The L-BFGS of gpar-at-scale_b200/lbfgs.py (two-loop recursion, memory 10, backtracking line search with a
+// safeguarded quadratic step on the Armijo condition, curvature-guarded updates), on the library's analytic gradients.
+template <class FG>
+void lbfgs(FG fg, const double* x0, int n, int iterations, double g_tol, double f_reltol, double* xbest, double* fbest, int* calls_out) {
+  typedef std::vector<double> V;
+  auto dot = [&](const V& a, const V& b) { double s = 0.0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; };
+  const int memory = 10;
+  V x(x0, x0 + n), g(n), xn(n), gn(n), q(n), d(n);
+  double f = fg(x.data(), g.data());
+  int calls = 1, it = 0;
+  std::vector<V> S, Y;
+  if (std::isfinite(f)) {
+    const double step0 = 1.0 / std::max(std::sqrt(dot(g, g)), 1.0);
+    while (it < iterations) {
+      double gmax = 0.0; for (double v : g) gmax = std::max(gmax, std::fabs(v));
+      if (gmax <= g_tol) break;
+      it++;
+      q = g;
+      V alphas;
+      for (int k = (int)S.size() - 1; k >= 0; k--) { const double a = dot(S[k], q) / dot(Y[k], S[k]); alphas.push_back(a); for (int i = 0; i < n; i++) q[i] -= a * Y[k][i]; }
+      if (!S.empty()) { const double sc = dot(S.back(), Y.back()) / dot(Y.back(), Y.back()); for (double& v : q) v *= sc; }
+      for (size_t k = 0; k < S.size(); k++) { const double a = alphas[S.size() - 1 - k], b = dot(Y[k], q) / dot(Y[k], S[k]); for (int i = 0; i < n; i++) q[i] += (a - b) * S[k][i]; }
+      for (int i = 0; i < n; i++) d[i] = -q[i];
+      double dg = dot(d, g);
+      if (dg >= 0) { S.clear(); Y.clear(); for (int i = 0; i < n; i++) d[i] = -g[i]; dg = dot(d, g); }
+      double step = S.empty() ? step0 : 1.0, fn = std::numeric_limits<double>::infinity();
+      bool found = false;
+      for (int ls = 0; ls < 25; ls++) {
+        for (int i = 0; i < n; i++) xn[i] = x[i] + step * d[i];
+        fn = fg(xn.data(), gn.data()); calls++;
+        if (std::isfinite(fn) && fn <= f + 1e-4 * step * dg) { found = true; break; }
+        if (std::isfinite(fn)) { const double nw = -dg * step * step / (2.0 * (fn - f - dg * step)); step = std::min(std::max(nw, 0.1 * step), 0.5 * step); }
+        else step *= 0.25;
+      }
+      if (!found) break;
+      V sv(n), yv(n);
+      for (int i = 0; i < n; i++) { sv[i] = xn[i] - x[i]; yv[i] = gn[i] - g[i]; }
+      if (dot(sv, yv) > 1e-12 * std::sqrt(dot(sv, sv)) * std::sqrt(dot(yv, yv))) {
+        S.push_back(sv); Y.push_back(yv);
+        if ((int)S.size() > memory) { S.erase(S.begin()); Y.erase(Y.begin()); }
+      }
+      const double df = f - fn;
+      x = xn; f = fn; g = gn;
+      if (df <= f_reltol * std::fabs(f)) break;
+    }
+  }
+  std::copy(x.begin(), x.end(), xbest); *fbest = f; *calls_out = calls;
+}
+
 // Member i evaluates thetas[:, i] on ITS OWN resident data (gpar_set_* on gpar_group_ctx(g, i)), all members at once.
 // codes[i] = the member's status: a failed Cholesky (GPAR_ERR_NOT_POSDEF) does not fail the call — an optimiser treats
 // it as +Inf — any other member error does.  width 8 rows (status, value, gradient) are all-gathered with NCCL.
@@ -263,13 +312,15 @@ int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t
 }
 
 // Whole fits of a task list: every member takes the next task (longest first) until none is left; per task the
-// data go to the member's device once and Nelder-Mead runs `iterations` iterations on the blocking objective
-// (dtc.jl:29-61: minimise -dtc; temporal_gp_inference.jl:69-82: minimise -logpdf for a time-only task, D = 0).
+// data go to the member's device once and the optimiser — Nelder-Mead (the reference's, dtc.jl:58-61) or L-BFGS on
+// the analytic gradients — runs `iterations` iterations on the blocking objective (dtc.jl:29-61: minimise -dtc;
+// temporal_gp_inference.jl:69-82: minimise -logpdf for a time-only task, D = 0).
 // minimum[k], minimizer[5 k .. 5 k + 4] (NaN-padded for 3-parameter tasks), f_calls[k], member_of[k] (nullable).
 int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
-                   int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of) {
+                   int32_t optimizer, int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of) {
   if (!g) return GPAR_ERR_INVALID;
   if (!t || N < 1 || !tasks || ntasks < 1 || !minimum || !minimizer) return group_fail(g, GPAR_ERR_INVALID, "group_fit: t, tasks, minimum and minimizer must be given");
+  if (optimizer != GPAR_OPT_NELDER_MEAD && optimizer != GPAR_OPT_LBFGS) return group_fail(g, GPAR_ERR_INVALID, "group_fit: unknown optimizer %d", optimizer);
   for (int k = 0; k < ntasks; k++)
     if (!tasks[k].y || (tasks[k].D > 0 && (!tasks[k].X || !tasks[k].Z || tasks[k].M < 1)) || tasks[k].D < 0)
       return group_fail(g, GPAR_ERR_INVALID, "group_fit: task %d is incomplete", k);
@@ -305,8 +356,16 @@ int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_tas
         if (r != GPAR_OK) { hard = r; return std::numeric_limits<double>::infinity(); }
         return -v;
       };
+      auto fgr = [&](const double* th, double* gr) -> double {      // value and gradient of the NEGATED objective
+        double v = 0.0;
+        int r = tk.D > 0 ? gpar_scaled_dtc_grad(c, k_time, k_out, th, &v, gr) : gpar_lgssm_logpdf_grad(c, k_time, th, 1, &v, gr);
+        if (r != GPAR_OK) { if (r != GPAR_ERR_NOT_POSDEF) hard = r; for (int j = 0; j < np; j++) gr[j] = 0.0; return std::numeric_limits<double>::infinity(); }
+        for (int j = 0; j < np; j++) gr[j] = -gr[j];
+        return -v;
+      };
       double xb[5] = {nan, nan, nan, nan, nan}, fb = nan; int calls = 0;
-      nelder_mead(f, tk.theta0, np, iterations, 1e-8, xb, &fb, &calls);
+      if (optimizer == GPAR_OPT_LBFGS) lbfgs(fgr, tk.theta0, np, iterations, 1e-6, 1e-10, xb, &fb, &calls);
+      else nelder_mead(f, tk.theta0, np, iterations, 1e-8, xb, &fb, &calls);
       if (hard != GPAR_OK) return hard;
       double* row = rows.data() + ((size_t)i * ntasks + k) * 8;
       row[0] = k; row[1] = fb; for (int j = 0; j < 5; j++) row[2 + j] = xb[j]; row[7] = calls;

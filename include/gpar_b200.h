@@ -200,11 +200,12 @@ typedef struct gpar_fit_task {
   const double* y;
   double theta0[5];
 } gpar_fit_task;
-/* Nelder-Mead fits (src/gp/dtc.jl:58-61 with an iteration budget instead of a time limit) of all tasks on the common
+/* Fits (Nelder-Mead: src/gp/dtc.jl:58-61 with an iteration budget instead of a time limit) of all tasks on the common
  * sorted time grid t (N): members take tasks dynamically, longest first.  minimum[ntasks] (of the NEGATED objective,
  * as the reference minimises), minimizer 5 x ntasks (NaN-padded), f_calls / member_of (nullable) per task. */
+enum gpar_optimizer { GPAR_OPT_NELDER_MEAD = 0, GPAR_OPT_LBFGS = 1 };   /* L-BFGS uses the library's analytic gradients */
 int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
-                   int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
+                   int32_t optimizer, int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
 
 /* n doubles from member src — `host` if given, else the resident result of its last gpar_lgssm_smooth /
  * gpar_scaled_predict (the posterior means) — into EVERY member's chain buffer (ncclBroadcast over NVLink);

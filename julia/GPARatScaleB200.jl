@@ -213,7 +213,7 @@ function group_dtc_logpdf(g::Group, k, thetas::Matrix{Float64}; vfe::Bool = fals
 end
 
 # whole Nelder-Mead fits of the chain's conditional GPs; Xs[k] (D x N) / Zs[k] (D x M) are `nothing` for a time-only task
-function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float64}}, theta0s::Vector{Vector{Float64}}, k_time, k_out; iterations::Integer = 200)
+function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float64}}, theta0s::Vector{Vector{Float64}}, k_time, k_out; iterations::Integer = 200, optimizer::Symbol = :neldermead)
     nt = length(ys)
     GC.@preserve Xs Zs ys begin
         tasks = [FitTask(Xs[k] === nothing ? C_NULL : pointer(Xs[k]), Xs[k] === nothing ? 0 : size(Xs[k], 1),
@@ -221,8 +221,8 @@ function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float
                          ntuple(j -> j <= length(theta0s[k]) ? theta0s[k][j] : 0.0, 5)) for k in 1:nt]
         minimum = fill(NaN, nt); minimizer = fill(NaN, 5, nt); calls = zeros(Int32, nt); member = fill(Int32(-1), nt)
         gcheck(g, ccall((:gpar_group_fit, LIB), Cint,
-                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{FitTask}, Int32, Cint, Cint, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
-                        g.h, t, length(t), tasks, nt, kernel_code(k_time), kernel_code(k_out), iterations, minimum, minimizer, calls, member))
+                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{FitTask}, Int32, Cint, Cint, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                        g.h, t, length(t), tasks, nt, kernel_code(k_time), kernel_code(k_out), optimizer === :lbfgs ? 1 : 0, iterations, minimum, minimizer, calls, member))
     end
     return minimum, minimizer, calls, member
 end

@@ -138,6 +138,36 @@ def test_group_fit_walks_the_same_simplices_as_the_python_mirror(ctx):
         assert np.allclose(minimizer[k, :p], res.minimizer, rtol=1e-13, atol=0) and np.all(np.isnan(minimizer[k, p:]))
 
 
+def test_group_fit_lbfgs_matches_the_python_mirror(ctx):
+    """L-BFGS inside the library (analytic gradients) against lbfgs.py over the single-context ABI: the same
+    algorithm (dot products may round differently), so the minima agree tightly and are below Nelder-Mead's."""
+    import gpar_at_scale_b200 as gp
+    from gpar_at_scale_b200 import lbfgs
+    t, tasks = chain_tasks(13, outputs=2, restarts=1)
+    g = gp.Group([0])
+    try:
+        minimum, minimizer, calls, _ = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=10, optimizer="lbfgs")
+        nm_minimum = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=10)[0]
+    finally:
+        g.close()
+    for k, tk in enumerate(tasks):
+        ctx.set_times(t); ctx.set_outputs(tk["y"]); ctx.set_noise_vector(None)
+        if tk["X"] is None:
+            def fg(th):
+                v, gr = ctx.lgssm_logpdf_grad(gp.MATERN52, th)
+                return -v[0], -gr[0]
+        else:
+            ctx.set_inputs(tk["X"]); ctx.set_pseudo(tk["Z"])
+
+            def fg(th):
+                v, gr = ctx.scaled_dtc_grad(gp.MATERN52, gp.MATERN52, th)
+                return -v, -gr
+        res = lbfgs.optimize(fg, tk["theta0"], iterations=10)
+        assert minimum[k] == pytest.approx(res.minimum, rel=1e-7)
+        assert abs(int(calls[k]) - res.f_calls) <= 2
+        assert minimum[k] <= nm_minimum[k] + 1e-9 * abs(nm_minimum[k])
+
+
 @pytest.mark.skipif(device_count() < 2, reason="needs two devices (gpurun --gpus 2)")
 def test_group_of_two_devices():
     import gpar_at_scale_b200 as gp
