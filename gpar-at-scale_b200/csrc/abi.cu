@@ -216,7 +216,22 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   double yy = 0.0;
   CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened);
+  CHK(dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened));
+  if (want_grad) {
+    // poorly conditioned cov(u): the analytic gradient (collapsed statistic, explicit inverse) loses cond * eps —
+    // take value and gradient from the whitened-panel value path instead (see gpar_fd_gradient)
+    TailBufs tb;
+    CHK(tail_layout(ctx, true, vfe, &tb));
+    double mm[2] = {1.0, 1.0};
+    CU(cudaMemcpy(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost));
+    bool fd = gpar_needs_whitened_panel(mm);
+    if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;
+    if (fd) {
+      CHK(gpar_dtc_logpdf(ctx, kernel, theta, vfe, jitter, val, nullptr));
+      CHK(gpar_fd_gradient([&](const double* th, double* v) { return gpar_dtc_logpdf(ctx, kernel, th, vfe, jitter, v, nullptr); }, theta, 3, grad));
+    }
+  }
+  return GPAR_OK;
 }
 
 }  // extern "C"

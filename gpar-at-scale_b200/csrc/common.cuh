@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -207,4 +208,22 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter,
 // scaled.cu: conditioning decision and the panel whitening by L_u (see gpar_needs_whitened_panel)
 int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
 bool gpar_needs_whitened_panel(const double minmax[2]);
+// Gradient of a value entry point by the 4-point central stencil (h = 1e-2 in the raw log-space parameters; env
+// GPAR_FD_STEP): the fallback of the analytic-gradient entry points when cov(u) is too poorly conditioned for the
+// collapsed statistic ("Conditioning") — the value path whitens the panel by L_u and keeps 1e-8.
+template <class ValFn>
+int gpar_fd_gradient(ValFn f, const double* theta, int n, double* grad) {
+  double h = 1e-2;      // log-space parameters: the h^4 truncation stays below the round-off noise of the value / h
+  if (const char* e = getenv("GPAR_FD_STEP")) { const double v = atof(e); if (v > 0.0) h = v; }
+  double th[8];
+  for (int i = 0; i < n; i++) th[i] = theta[i];
+  for (int i = 0; i < n; i++) {
+    double v[4];
+    const double off[4] = {-2.0 * h, -h, h, 2.0 * h};
+    for (int q = 0; q < 4; q++) { th[i] = theta[i] + off[q]; CHK(f(th, &v[q])); }
+    th[i] = theta[i];
+    grad[i] = (v[0] - 8.0 * v[1] + 8.0 * v[2] - v[3]) / (12.0 * h);
+  }
+  return GPAR_OK;
+}
 int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2);

@@ -991,6 +991,16 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   grad[2] = F_logl / out_l * ex[2];
   grad[3] = F_os * 2.0 * pv[3] * ex[3];
   grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+  // cov(u) too poorly conditioned for the collapsed statistic and the explicit P = (cov(u) + G)^-1 of the analytic
+  // gradient (error ~ cond * eps): value and gradient from the whitened-panel value path instead (slow, but right)
+  double mm[2] = {1.0, 1.0};
+  CU(cudaMemcpy(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost));
+  bool fd = gpar_needs_whitened_panel(mm);
+  if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
+  if (fd) {
+    CHK(gpar_scaled_dtc(ctx, k_time, k_out, theta, dtc, nullptr));
+    CHK(gpar_fd_gradient([&](const double* th, double* v) { return gpar_scaled_dtc(ctx, k_time, k_out, th, v, nullptr); }, theta, 5, grad));
+  }
   return GPAR_OK;
 }
 

@@ -505,6 +505,50 @@ def test_scaled_dtc_grad_multi_slab_and_full_size(ctx):
     print("scaled objective + gradient N=1M M=1024: %.1f ms device" % ms)
 
 
+def test_ill_conditioned_cov_u_gradient_falls_back_to_the_value_path(ctx):
+    """The analytic gradients work on the collapsed statistic and an explicit (cov(u) + G)^-1: error ~ cond eps (4e-7 at
+    cond 2e7, useless beyond 1e9).  Above the conditioning threshold the gradient entry points therefore difference the
+    whitened-panel VALUE path (4-point stencil): against torch autograd of the oracle 1e-5 relative at cond 1e9 and 1e-3 at
+    1e10, where the analytic form is off by up to O(1); value keeps 1e-8.  GPAR_GRAD_FD=0 shows what the analytic form alone would give."""
+    from gpar_at_scale_b200 import data, chain
+    from oracle.grad import scaled_dtc_value_and_grad
+    rng = np.random.default_rng(5)
+    x, y_obs, _, _ = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
+    Y = np.stack(y_obs); o = 2
+    X = np.ascontiguousarray(Y[:o].T); Z = chain.strided_pseudo_inputs(X, 40)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(x); ctx.set_outputs(Y[o]); ctx.set_noise_vector(None)
+    worst_analytic = 0.0
+    for th3, gtol in ((8.0, 1e-5), (9.2, 1e-3)):      # cond ~ 1e9 / 1e10: the stencil inherits the value's own 1e-10 / 1e-9 noise
+        th = np.array([4.65, 2.31, 4.10, th3, -0.43])
+        v, g = ctx.scaled_dtc_grad(3, 3, th)
+        v0, g0 = scaled_dtc_value_and_grad(th, X, Z, x, Y[o], 3, 3)
+        assert abs(v - v0) <= RTOL * abs(v0)
+        assert np.max(np.abs(g - g0)) <= gtol * np.max(np.abs(g0)), (th3, g, g0)
+        os.environ["GPAR_GRAD_FD"] = "0"
+        try:
+            _, ga = ctx.scaled_dtc_grad(3, 3, th)
+        finally:
+            del os.environ["GPAR_GRAD_FD"]
+        worst_analytic = max(worst_analytic, float(np.max(np.abs(ga - g0)) / np.max(np.abs(g0))))
+    print("analytic gradient alone: worst relative error %.1e" % worst_analytic)
+    # the stencil itself, forced on a well-conditioned problem, agrees with the analytic gradient
+    th = np.array([0.2, 0.1, -0.3, 0.2, -1.0])
+    _, ga = ctx.scaled_dtc_grad(3, 3, th)
+    os.environ["GPAR_GRAD_FD"] = "1"
+    try:
+        _, gf = ctx.scaled_dtc_grad(3, 3, th)
+        n, m = 5000, 80
+        xs = rng.uniform(0, 10, n); zs = np.linspace(0, 10, m); ys = np.sin(xs) + 0.1 * rng.normal(size=n)
+        ctx.set_inputs(xs); ctx.set_pseudo(zs); ctx.set_outputs(ys)
+        th3 = np.log([1.0, 1.0, 0.1])
+        vf, gf3 = ctx.dtc_logpdf(3, th3, grad=True)
+    finally:
+        del os.environ["GPAR_GRAD_FD"]
+    assert np.max(np.abs(gf - ga)) <= 1e-6 * np.max(np.abs(ga))
+    va, ga3 = ctx.dtc_logpdf(3, th3, grad=True)
+    assert abs(vf - va) <= 1e-10 * abs(va) and np.max(np.abs(gf3 - ga3)) <= 1e-6 * np.max(np.abs(ga3))
+
+
 def test_ill_conditioned_cov_u_keeps_parity(ctx):
     """cov(u) with cond ~ 1e7 ... 1e10 (large output variance, small jitter): the collapsed statistic beta'beta would lose
     cond(cov(u)) eps (6e-8 ... 4e-3 here); the library then whitens the panel by L_u before the SYRK (A = L_u^-1 beta' as the
