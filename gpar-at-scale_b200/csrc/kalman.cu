@@ -827,12 +827,54 @@ template <int D> struct SS2Layout {      // per-sequence constants (doubles)
                        SIZE = OK + 1;
 };
 
+// Last-CTA-done epilogue of the single pass (ss3 variants): every CTA of the main and of the head launch takes a ticket
+// after publishing its partial sums; the holder of the last ticket sums all sequences in fixed order, writes lml / sums
+// and folds the "cannot handle this model" flags — no separate finish launch.  ticket == nullptr: epilogue off.
+struct SSFin { int* ticket; int total; int batch; double* lml; double* sums; double* flag_out; };
+
+template <int D>
+__device__ __forceinline__ void ss_ticket_finish(const SSFin fin, const double* part, int nseg, const double* cst, int64_t N, int* sh_last) {
+  typedef SS2Layout<D> SL;
+  if (!fin.ticket) return;
+  __syncthreads();                                           // the CTA's partials were written by thread 0
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *sh_last = atomicAdd(fin.ticket, 1) == fin.total - 1;
+  }
+  __syncthreads();
+  if (!*sh_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = threadIdx.x >> 5; b < fin.batch; b += nw) {
+    const double* c = cst + (int64_t)b * SL::SIZE;
+    double a0 = 0.0, a1 = 0.0;
+    for (int sg = lane; sg < nseg; sg += 32) { a0 += __ldcg(part + ((int64_t)b * nseg + sg) * 2); a1 += __ldcg(part + ((int64_t)b * nseg + sg) * 2 + 1); }
+    for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    if (lane == 0) {
+      const int64_t kstar = (int64_t)__ldcg(c + SL::KSTAR);
+      const double slog = a0 + (double)(N > kstar ? N - kstar : 0) * __ldcg(c + SL::ROW + D * D + 2 * D + 1);
+      if (fin.lml) fin.lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + slog + a1);
+      if (fin.sums) { fin.sums[2 * b] = slog; fin.sums[2 * b + 1] = a1; }
+    }
+  }
+  if (threadIdx.x == 0) {
+    double ok = 1.0;
+    for (int q = 0; q < fin.batch; q++) if (__ldcg(cst + (int64_t)q * SL::SIZE + SL::OK) != 1.0) ok = 0.0;
+    fin.flag_out[0] = ok;
+    *fin.ticket = 0;                                         // ready for the next call
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(32)
-ss2_setup_kernel(SeqParams sp, int batch, double* __restrict__ cst) {
+ss2_setup_kernel(SeqParams sp, int batch, double* __restrict__ cst, int* __restrict__ ticket) {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;");        // the main pass may start loading its first tiles now (it waits before reading cst)
+#endif
   typedef SS2Layout<D> SL;
   typedef FiltElem<D> FE;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && ticket) *ticket = 0;
   if (b >= batch) return;
   const int pb = sp.nparam == 1 ? 0 : b;
   const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
@@ -938,10 +980,11 @@ ss2_setup_kernel(SeqParams sp, int batch, double* __restrict__ cst) {
 template <int D, bool HEAD>
 __global__ void __launch_bounds__(SS2_THREADS, HEAD ? 1 : 3)
 ss2_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, SeqParams sp, double* __restrict__ cst,
-                int W, int nseg, double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ scratchS) {
+                int W, int nseg, double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ scratchS, SSFin fin) {
   typedef SS2Layout<D> SL;
   extern __shared__ double ysm[];                            // SS2_STEPS values, padded by one per sub-chunk
   __shared__ double wtot[SS2_THREADS / 32][D];
+  __shared__ int fin_last;
   __shared__ double inject[D], trsum[2], red[32];
   __shared__ int kst_sh;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1173,6 +1216,7 @@ ss2_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, SeqPar
     part[((int64_t)b * nseg + seg) * 2] = HEAD ? trsum[0] : 0.0;
     part[((int64_t)b * nseg + seg) * 2 + 1] = a2tot + (HEAD ? trsum[1] : 0.0);
   }
+  ss_ticket_finish<D>(fin, part, nseg, cst, N, &fin_last);
 }
 
 template <int D>
@@ -1228,17 +1272,25 @@ template <int NB> __device__ __forceinline__ void ss_cp_wait() { asm volatile("c
 template <int D, int THREADS, int NBUF, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const double* __restrict__ cst, int W, int64_t R, int nseg,
-                double* __restrict__ alpha, double* __restrict__ part) {
+                double* __restrict__ alpha, double* __restrict__ part, SSFin fin) {
   typedef SS2Layout<D> SL;
   constexpr int TILE = THREADS * SS3_LS, BUF = THREADS * SS3_ROW, NW = THREADS / 32, WT = 32 * SS3_LS;
   extern __shared__ __align__(16) double ysm[];              // NBUF buffers of THREADS padded rows
   __shared__ double wtot[2][NW][D], xin[2][D], red[32], pws[SL::NPOW * D * D];
+  __shared__ int fin_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int b = blockIdx.y, seg = blockIdx.x + 1;
   const double* c = cst + (int64_t)b * SL::SIZE;
   const int64_t r0 = (int64_t)SS2_STEPS + (int64_t)blockIdx.x * R;            // first emitted step of this CTA
   const int64_t r1 = r0 + R < N ? r0 + R : N;                                 // one past its last
-  if (r0 >= N) { if (tid == 0) { part[((int64_t)b * nseg + seg) * 2] = 0.0; part[((int64_t)b * nseg + seg) * 2 + 1] = 0.0; } return; }
+  if (r0 >= N) {
+    if (tid == 0) { part[((int64_t)b * nseg + seg) * 2] = 0.0; part[((int64_t)b * nseg + seg) * 2 + 1] = 0.0; }
+#if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    ss_ticket_finish<D>(fin, part, nseg, cst, N, &fin_last);
+    return;
+  }
   const int64_t s0 = r0 - W;                                                  // burn-in start (r0 >= SS2_STEPS > W)
   const int ntile = (int)((r1 - s0 + TILE - 1) / TILE);
   const double* yb = y + (int64_t)b * ystride;
@@ -1267,6 +1319,11 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
   };
 #pragma unroll
   for (int i = 0; i < NBUF - 1; i++) issue(i);
+  // programmatic dependent launch: everything above needs only y; the set-up kernel's constants (and the zeroed
+  // ticket) are complete and visible after this wait
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   // constants (once per CTA): 4-step blocking of the state and of the predictions, scan powers
   double P4[D * D], G[4][D], hj[4][D], cm[3], PL[D * D];
   const double rs = c[SL::ROW + D * D + 2 * D];
@@ -1445,6 +1502,7 @@ ss3_main_kernel(const double* __restrict__ y, int64_t ystride, int64_t N, const 
   ss_cp_wait<0>();
   const double a2tot = block_sum((a2s[0] + a2s[1]) + (a2s[2] + a2s[3]), red);
   if (tid == 0) { part[((int64_t)b * nseg + seg) * 2] = 0.0; part[((int64_t)b * nseg + seg) * 2 + 1] = a2tot; }
+  ss_ticket_finish<D>(fin, part, nseg, cst, N, &fin_last);
 }
 
 // all sequences in one launch: warp w sums the partials of sequence w in fixed order; thread 0 folds the flags
@@ -1475,10 +1533,16 @@ ss3_finish_kernel(const double* __restrict__ part, int nseg, const double* __res
 
 template <int D, int THREADS, int NBUF, int MINB>
 int ss3_launch(gpar_ctx* ctx, int batch, int64_t N, const double* y, int64_t ystride, const double* cst, int W, double* alpha, double* part,
-               int nc, int64_t R) {
+               int nc, int64_t R, SSFin fin, bool pdl) {
   const size_t smem = (size_t)NBUF * THREADS * SS3_ROW * sizeof(double);
   CU(cudaFuncSetAttribute((ss3_main_kernel<D, THREADS, NBUF, MINB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LAUNCH(ctx, (ss3_main_kernel<D, THREADS, NBUF, MINB>), dim3(nc, batch), THREADS, smem, y, ystride, N, cst, W, R, nc + 1, alpha, part);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nc, batch); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, ss3_main_kernel<D, THREADS, NBUF, MINB>, y, ystride, N, cst, W, R, nc + 1, alpha, part, fin));
+  ctx->launches++;
   return GPAR_OK;
 }
 
@@ -1491,7 +1555,8 @@ int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, con
   if (ctx->ss_skip > 0 || !ctx->ss_deferred_ok) return GPAR_OK;   // (ss_skip is decremented by the two-pass path's own check)
   CU(ctx->kal_f.reserve(((size_t)batch * (SL::SIZE + SS2_STEPS) + 8) * sizeof(double)));
   double* cst = ctx->kal_f.as<double>(); double* scratchS = cst + (size_t)batch * SL::SIZE;
-  LAUNCH(ctx, ss2_setup_kernel<D>, (batch + 31) / 32, 32, 0, sp, batch, cst);
+  int* ticket = reinterpret_cast<int*>(cst + (size_t)batch * (SL::SIZE + SS2_STEPS) + 4);      // (the flag double sits at + 0)
+  LAUNCH(ctx, ss2_setup_kernel<D>, (batch + 31) / 32, 32, 0, sp, batch, cst, ticket);
   // Fixed burn-in of SS2_WFIX steps (14 % re-reads): the grid layout then does not depend on the model, so no
   // host round trip separates the set-up from the main pass; a model that needs more (or whose covariance
   // has not settled) is FLAGGED by the kernels and the caller falls back after its own final synchronisation.
@@ -1523,26 +1588,30 @@ int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, con
   CU(cudaEventRecord(ctx->ev_fork, main_stream));
   CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
   ctx->stream = ctx->stream2;
+  double* flag_dev = ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS);
+  bool fused_finish = variant != 0, pdl = variant != 0;
+  if (const char* e = getenv("GPAR_SS3_FUSED")) { fused_finish = fused_finish && (atoi(e) & 1); pdl = pdl && (atoi(e) & 2); }   // bit 0: ticket epilogue, bit 1: PDL
+  SSFin fin{fused_finish ? ticket : nullptr, (nc + 1) * batch, batch, o.lml, o.sums, flag_dev};
+  const SSFin nofin{nullptr, 0, 0, nullptr, nullptr, nullptr};
   int rc = [&]() -> int {
-    LAUNCH(ctx, (ss2_main_kernel<D, true>), dim3(1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
+    LAUNCH(ctx, (ss2_main_kernel<D, true>), dim3(1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS, fin);
     return GPAR_OK;
   }();
   cudaEventRecord(ctx->ev_side, ctx->stream2);
   ctx->stream = main_stream;
   CHK(rc);
-  double* flag_dev = ctx->kal_f.as<double>() + (size_t)batch * (SL::SIZE + SS2_STEPS);
   if (!ctx->pinned) { CU(cudaMallocHost(&ctx->pinned, 4096)); ctx->pinned_cap = 4096; }
   if (variant == 0) {
-    if (nseg > 1) LAUNCH(ctx, (ss2_main_kernel<D, false>), dim3(nseg - 1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS);
+    if (nseg > 1) LAUNCH(ctx, (ss2_main_kernel<D, false>), dim3(nseg - 1, batch), SS2_THREADS, smem, y, ystride, N, sp, cst, W, nseg, o.alpha, part, scratchS, nofin);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
     LAUNCH(ctx, ss2_finish_kernel<D>, batch, 256, 0, part, nseg, cst, N, W, o.lml, o.sums);
     LAUNCH(ctx, ss2_flags_kernel<D>, 1, 32, 0, cst, batch, flag_dev);
   } else {
-    if (variant == 1) CHK((ss3_launch<D, 128, 3, 2>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
-    else if (variant == 2) CHK((ss3_launch<D, 128, 2, 3>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
-    else CHK((ss3_launch<D, 256, 3, 1>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R)));
+    if (variant == 1) CHK((ss3_launch<D, 128, 3, 2>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R, fin, pdl)));
+    else if (variant == 2) CHK((ss3_launch<D, 128, 2, 3>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R, fin, pdl)));
+    else CHK((ss3_launch<D, 256, 3, 1>(ctx, batch, N, y, ystride, cst, W, o.alpha, part, nc, R, fin, pdl)));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-    LAUNCH(ctx, ss3_finish_kernel<D>, 1, 512, 0, part, nseg, cst, N, batch, o.lml, o.sums, flag_dev);
+    if (!fused_finish) LAUNCH(ctx, ss3_finish_kernel<D>, 1, 512, 0, part, nseg, cst, N, batch, o.lml, o.sums, flag_dev);
   }
   // flags (set-up: doubling converged / burn-in long enough; head block: transient settled) go to pinned host
   // memory WITHOUT a synchronisation: lgssm_steady_failed() reads them after the caller's final sync

@@ -35,3 +35,23 @@ for batch in (1, 8):
         print("batch %d variant %-7s logpdf best %.1f us median %.1f us (%.2f TB/s of y) decorrelate %.1f us | rel dlml %.2e  max dalpha %.2e"
               % (batch, var, min(ms) * 1e3, med * 1e3, batch * N * 8 / (med * 1e-3) / 1e12, min(msd) * 1e3,
                  float(np.max(np.abs(v - ref[0]) / np.abs(ref[0]))), da), flush=True)
+
+# ticket-fused finish (bit 0) and programmatic dependent launch of the main pass (bit 1), default variant per batch
+os.environ.pop("GPAR_SS3_VARIANT", None)
+for batch in (1, 8, 16):
+    Y = rng.normal(size=(batch, N))
+    ctx.set_outputs(Y); ctx.set_times_range(0.0, 1 / 30, N)
+    ths = np.tile(th, (batch, 1))
+    ref = None
+    for fused in ("0", "1", "3"):
+        os.environ["GPAR_SS3_FUSED"] = fused
+        ms = []
+        for i in range(9):
+            v = ctx.lgssm_logpdf(3, ths); ms.append(ctx.last_timing()[0])
+        if ref is None:
+            ref = v.copy()
+        med = float(np.median(ms[2:]))
+        print("batch %2d fused %s logpdf best %.1f us median %.1f us (%.2f TB/s of y) launches %d | max rel dlml %.2e"
+              % (batch, fused, min(ms) * 1e3, med * 1e3, batch * N * 8 / (med * 1e-3) / 1e12, ctx.last_timing()[1],
+                 float(np.max(np.abs(v - ref) / np.abs(ref)))), flush=True)
+os.environ.pop("GPAR_SS3_FUSED", None)
