@@ -52,6 +52,23 @@ def test_no_gpu_means_loud_failure_not_fallback():
         gp.Context(0)
 
 
+def test_no_gpu_means_the_group_fails_loudly_too():
+    from conftest import _has_gpu
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    import gpar_at_scale_b200 as gp
+    with pytest.raises(gp.GparError):
+        gp.Group([0])
+
+
+def test_fit_task_struct_matches_the_header_layout():
+    """struct gpar_fit_task: X*, int32 D, Z*, int64 M, y*, double[5] -> offsets 0, 8, 16, 24, 32, 40; 80 bytes (LP64)."""
+    from gpar_at_scale_b200 import _ffi
+    T = _ffi.FitTask
+    assert (T.X.offset, T.D.offset, T.Z.offset, T.M.offset, T.y.offset, T.theta0.offset) == (0, 8, 16, 24, 32, 40)
+    assert ctypes.sizeof(T) == 80
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gpar-at-scale_b200")
     for dirpath, _, files in os.walk(pkg):
