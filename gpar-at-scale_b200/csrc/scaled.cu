@@ -441,7 +441,7 @@ __global__ void diag_minmax_kernel(const double* __restrict__ L, int M, double* 
 // FINAL = false: zero-start responses of (dmu_0, dmu_1, nu) over each chunk -> tstate (then carry-scanned);
 // FINAL = true : starts from the scanned states and accumulates <R, d beta_*> with R = -S + e w'.
 template <int D, int CT, bool FINAL>
-__global__ void __launch_bounds__(GPAR_TILE)
+__global__ void __launch_bounds__(GPAR_TILE, CT == 1 ? 3 : 2)
 whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ dtable,
                       const double* __restrict__ beta, const double* __restrict__ panelD, const double* __restrict__ start,
                       double* __restrict__ tstate, int nch, int chunk0, const double* __restrict__ St, const double* __restrict__ evec,
@@ -473,6 +473,26 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
     }
     acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
   }
+  struct GroupIn { double kv[CT][4], dv[CT][4], sv[CT][4], en[4]; };
+  auto load_group = [&](int64_t g, GroupIn& o) {
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+      const int64_t off = (g - g0) * GPAR_TILE * 4;
+      const double2 a01 = reinterpret_cast<const double2*>(inb[c] + off)[0], a23 = reinterpret_cast<const double2*>(inb[c] + off)[1];
+      o.kv[c][0] = a01.x; o.kv[c][1] = a01.y; o.kv[c][2] = a23.x; o.kv[c][3] = a23.y;
+      const double2 d01 = reinterpret_cast<const double2*>(ind[c] + off)[0], d23 = reinterpret_cast<const double2*>(ind[c] + off)[1];
+      o.dv[c][0] = d01.x; o.dv[c][1] = d01.y; o.dv[c][2] = d23.x; o.dv[c][3] = d23.y;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int64_t n = g * 4 + j;
+        o.sv[c][j] = (FINAL && mvalid[c] && n < N) ? __ldg(inS[c] + (n - g0 * 4) * M) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const int64_t n = g * 4 + j; o.en[j] = (FINAL && n < N) ? __ldg(evec + n) : 0.0; }
+  };
+  GroupIn nxt;
+  if (g0 < g1) load_group(g0, nxt);
   __shared__ double tbl[2][WB_SUB * TS];
   __shared__ double dtb[2][WB_SUB * DTS];
   stage_rows<TS>(tbl[0], table, g0 * 4, N, WB_SUB); stage_rows<DTS>(dtb[0], dtable, g0 * 4, N, WB_SUB); cp_async_commit();
@@ -485,15 +505,10 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
     __syncthreads();
     const int64_t ge = (gs + WB_SUB / 4 < g1) ? gs + WB_SUB / 4 : g1;
     for (int64_t g = gs; g < ge; g++) {
-      double kv[CT][4], dv[CT][4];
-#pragma unroll
-      for (int c = 0; c < CT; c++) {
-        const double2 a01 = reinterpret_cast<const double2*>(inb[c])[0], a23 = reinterpret_cast<const double2*>(inb[c])[1];
-        kv[c][0] = a01.x; kv[c][1] = a01.y; kv[c][2] = a23.x; kv[c][3] = a23.y;
-        const double2 d01 = reinterpret_cast<const double2*>(ind[c])[0], d23 = reinterpret_cast<const double2*>(ind[c])[1];
-        dv[c][0] = d01.x; dv[c][1] = d01.y; dv[c][2] = d23.x; dv[c][3] = d23.y;
-        inb[c] += GPAR_TILE * 4; ind[c] += GPAR_TILE * 4;
-      }
+      // the global operands of group g were loaded one group ahead (ncu: long_scoreboard 4.3 stall cycles per issue at
+      // the 8-12 warps/SM this kernel's register count allows); fetch group g + 1 now
+      GroupIn in = nxt;
+      if (g + 1 < g1) load_group(g + 1, nxt);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int64_t n = g * 4 + j;
@@ -506,18 +521,17 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
 #pragma unroll
           for (int i = 0; i < D; i++) { Kg[i] = row[D * D + i]; ha[i] = row[D * D + D + i]; }
           const double rs = row[D * D + 2 * D], sqS = drow[0];
-          const double en = FINAL ? __ldg(evec + n) : 0.0;
+          const double en = in.en[j];
 #pragma unroll
           for (int c = 0; c < CT; c++) {
-            const double b = kv[c][j], dk = dv[c][j];
+            const double b = in.kv[c][j], dk = in.dv[c][j];
             double pred = 0.0, predn = 0.0;
 #pragma unroll
             for (int q = 0; q < D; q++) { pred = fma(ha[q], mu[c][q], pred); predn = fma(ha[q], nu[c][q], predn); }
             const double v = fma(b, sqS, pred);
             double rr = 0.0;
             if (FINAL) {
-              const double sv = mvalid[c] ? __ldg(inS[c] + (int64_t)(n - g0 * 4) * M) : 0.0;
-              rr = fma(en, wm[c], -sv);
+              rr = fma(en, wm[c], -in.sv[c][j]);
               acc[c][2] = fma(rr, (dk - predn) * rs, acc[c][2]);
             }
             double nd[2][D];
@@ -710,7 +724,8 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   double* tstate = st.psi + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad;       // after gp / g partials (layout of scaled_stats_d)
   double* accpart = tstate + 3 * state_doubles;
   LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, st.beta, wvec, st.alpha, N, NB4, T, M, st.evec);
-  const int CT = (T % 2 == 0) ? 2 : 1;
+  int CT = (T % 2 == 0) ? 2 : 1;                      // columns per thread: two halve the table reads (218 registers, 2 CTAs/SM; one: 164, 3 CTAs/SM)
+  if (const char* e = getenv("GPAR_TANGENT_CT")) { if (atoi(e) == 1) CT = 1; }
   dim3 grid(T / CT, nch);
   if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
                       tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
@@ -718,7 +733,12 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
               tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
   for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad);
   // S' = P beta' slab by slab (library GEMM on the transposed slab), consumed at once by the final tangent pass
-  int slab_chunks = 128;                                                         // 131072 steps per slab
+  int slab_chunks = 128;                                                         // ~131072 steps per slab ...
+  {                                                                              // ... rounded to whole waves of the final tangent pass
+    const int resident = ctx->num_sms * (CT == 1 ? 3 : 2), per_chunk = T / CT;
+    const int waves = std::max(1, (128 * per_chunk + resident / 2) / resident);
+    slab_chunks = std::max(1, waves * resident / per_chunk);
+  }
   if (const char* e = getenv("GPAR_GRAD_SLAB")) { int v = atoi(e); if (v >= 1) slab_chunks = v; }
   slab_chunks = std::min(slab_chunks, nch);
   const size_t slab_steps = (size_t)slab_chunks * WH_GROUPS * 4;
