@@ -150,6 +150,29 @@ __device__ __forceinline__ double base_kernel_dev(double d2, double& l_dkdl) {
   }
 }
 
+// The same kernels from r = ||x - z|| / l directly: with one input dimension r = |x - z| / l needs no FP64 square
+// root (~15 of the ~60 FP64 issue slots of a Matern-5/2 element), which the panel producers exploit for D = 1.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double base_kernel_from_r(double r, double& l_dkdl) {
+  if (KIND == GPAR_EQ) {
+    double k = exp(-0.5 * r * r);
+    if (GRAD) l_dkdl = r * r * k;
+    return k;
+  } else if (KIND == GPAR_MATERN12) {
+    double k = exp(-r);
+    if (GRAD) l_dkdl = r * k;
+    return k;
+  } else if (KIND == GPAR_MATERN32) {
+    double a = 1.7320508075688772935274463415059 * r, e = exp(-a);
+    if (GRAD) l_dkdl = a * a * e;
+    return (1.0 + a) * e;
+  } else {
+    double a = 2.2360679774997896964091736687313 * r, e = exp(-a);
+    if (GRAD) l_dkdl = a * a * (1.0 + a) * e * (1.0 / 3.0);
+    return (1.0 + a + a * a * (1.0 / 3.0)) * e;
+  }
+}
+
 // deterministic block reduction of one double (blockDim.x multiple of 32, <= 1024)
 __device__ __forceinline__ double block_sum(double v, double* sh) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -26,6 +26,7 @@ kuf_panel_kernel(const double* __restrict__ X, const double* __restrict__ Z, con
   int64_t g0 = (int64_t)blockIdx.y * groups_per_split;
   int64_t g1 = g0 + groups_per_split; if (g1 > NB4) g1 = NB4;
   double gacc = 0.0, hacc = 0.0;
+  const double inv_l = sqrt(inv_l2);
   double* outK = panelK + (((int64_t)mt * NB4 + g0) * GPAR_TILE + mi) * 4;
   double* outD = GRAD ? panelD + (((int64_t)mt * NB4 + g0) * GPAR_TILE + mi) * 4 : nullptr;
   for (int64_t g = g0; g < g1; g++) {
@@ -35,10 +36,14 @@ kuf_panel_kernel(const double* __restrict__ X, const double* __restrict__ Z, con
       int64_t n = g * 4 + j;
       bool valid = mvalid && n < N;
       int64_t nn = n < N ? n : N - 1;
-      double d2 = 0.0;
+      double ld, k;
+      if (D == 1) k = base_kernel_from_r<KIND, GRAD>(fabs(__ldg(X + nn) - z[0]) * inv_l, ld);      // no square root in one dimension
+      else {
+        double d2 = 0.0;
 #pragma unroll
-      for (int d = 0; d < D; d++) { double df = __ldg(X + nn * D + d) - z[d]; d2 = fma(df, df, d2); }
-      double ld; double k = base_kernel_dev<KIND, GRAD>(d2 * inv_l2, ld);
+        for (int d = 0; d < D; d++) { double df = __ldg(X + nn * D + d) - z[d]; d2 = fma(df, df, d2); }
+        k = base_kernel_dev<KIND, GRAD>(d2 * inv_l2, ld);
+      }
       double yn = __ldg(y + nn);
       k = valid ? s * k : 0.0;
       kv[j] = k; gacc = fma(k, yn, gacc);

@@ -63,6 +63,7 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
   double* outd[CT];
   const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
   const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const double inv_l = sqrt(inv_l2);
 #pragma unroll
   for (int c = 0; c < CT; c++) {
     const int m = (mt0 + c) * GPAR_TILE + mi;
@@ -101,10 +102,14 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
         }
 #pragma unroll
         for (int c = 0; c < CT; c++) {
-          double d2 = 0.0;
+          double ld = 0.0, k;
+          if (DX == 1) k = base_kernel_from_r<KIND, GRAD>(fabs(x[0] - z[c][0]) * inv_l, ld);          // no square root in one dimension
+          else {
+            double d2 = 0.0;
 #pragma unroll
-          for (int d = 0; d < DX; d++) { double df = x[d] - z[c][d]; d2 = fma(df, df, d2); }
-          double ld = 0.0; double k = base_kernel_dev<KIND, GRAD>(d2 * inv_l2, ld);
+            for (int d = 0; d < DX; d++) { double df = x[d] - z[c][d]; d2 = fma(df, df, d2); }
+            k = base_kernel_dev<KIND, GRAD>(d2 * inv_l2, ld);
+          }
           k = (valid && mvalid[c]) ? s * k : 0.0;
           kv[c][j] = k;
           if (GRAD) dv[c][j] = (valid && mvalid[c]) ? s * ld : 0.0;
