@@ -857,10 +857,11 @@ __device__ __forceinline__ void ss_ticket_finish(const SSFin fin, const double* 
       if (fin.sums) { fin.sums[2 * b] = slog; fin.sums[2 * b + 1] = a1; }
     }
   }
+  int bad = 0;
+  for (int q = threadIdx.x; q < fin.batch; q += blockDim.x) bad |= __ldcg(cst + (int64_t)q * SL::SIZE + SL::OK) != 1.0;
+  bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) {
-    double ok = 1.0;
-    for (int q = 0; q < fin.batch; q++) if (__ldcg(cst + (int64_t)q * SL::SIZE + SL::OK) != 1.0) ok = 0.0;
-    fin.flag_out[0] = ok;
+    fin.flag_out[0] = bad ? 0.0 : 1.0;
     *fin.ticket = 0;                                         // ready for the next call
   }
 }
@@ -1550,7 +1551,10 @@ template <int D>
 int lgssm_run_steady_long(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* y, const LgssmOut& o, bool* used) {
   typedef SS2Layout<D> SL;
   *used = false;
-  if (!(sp.reg_dt > 0.0) || batch > 16 || N < 32 * (int64_t)SS2_STEPS || o.mean || o.table || o.dlml || o.dalpha || o.dtable) return GPAR_OK;
+  int64_t min_n = 32 * (int64_t)SS2_STEPS; int max_batch = 16;
+  if (const char* e = getenv("GPAR_SS_LONG_MIN_N")) min_n = std::max<int64_t>(atoll(e), SS2_STEPS + 2 * SS2_WFIX);      // tuning knobs
+  if (const char* e = getenv("GPAR_SS_LONG_MAX_BATCH")) max_batch = atoi(e);
+  if (!(sp.reg_dt > 0.0) || batch > max_batch || N < min_n || o.mean || o.table || o.dlml || o.dalpha || o.dtable) return GPAR_OK;
   if (const char* e = getenv("GPAR_KF_STEADY")) { if (atoi(e) != 1 && atoi(e) != 3) return GPAR_OK; }   // 0: off, 2: two-pass only
   if (ctx->ss_skip > 0 || !ctx->ss_deferred_ok) return GPAR_OK;   // (ss_skip is decremented by the two-pass path's own check)
   CU(ctx->kal_f.reserve(((size_t)batch * (SL::SIZE + SS2_STEPS) + 8) * sizeof(double)));
