@@ -198,16 +198,27 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   // value-only calls: when cov(u) is poorly conditioned, whiten the panel by L_u before the SYRK (A = L_u^-1 Kuf as the
   // reference forms it, dtc_example.jl:14-16) instead of collapsing to Kuf Kfu first — see gpar_needs_whitened_panel
   bool whitened = false;
-  if (!want_grad) {
+  {
     TailBufs tb;
-    CHK(tail_layout(ctx, false, vfe, &tb));
+    CHK(tail_layout(ctx, want_grad, vfe, &tb));
     double mm[2] = {1.0, 1.0};
     CU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
     CU(cudaStreamSynchronize(ctx->stream2));              // the panel producer is already running on the main stream
-    if (gpar_needs_whitened_panel(mm)) {
+    bool ill = gpar_needs_whitened_panel(mm);
+    if (!want_grad && ill) {
       CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
       CHK(panel_left_solve(ctx, ctx->panelK.as<double>(), Npad, Mpad, M, tb.Lu));
       whitened = true;
+    }
+    if (want_grad) {
+      // poorly conditioned cov(u): the analytic gradient (collapsed statistic, explicit inverse) loses cond * eps and its
+      // Lambda may not even factor — take value and gradient from the whitened-panel value path (see gpar_fd_gradient)
+      if (const char* e = getenv("GPAR_GRAD_FD")) ill = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
+      if (ill) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+        CHK(gpar_dtc_logpdf(ctx, kernel, theta, vfe, jitter, val, nullptr));
+        return gpar_fd_gradient([&](const double* th, double* v) { return gpar_dtc_logpdf(ctx, kernel, th, vfe, jitter, v, nullptr); }, theta, 3, grad);
+      }
     }
   }
   cudaEventRecord(ctx->pev[0], ctx->stream);
@@ -216,22 +227,7 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   double yy = 0.0;
   CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CHK(dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened));
-  if (want_grad) {
-    // poorly conditioned cov(u): the analytic gradient (collapsed statistic, explicit inverse) loses cond * eps —
-    // take value and gradient from the whitened-panel value path instead (see gpar_fd_gradient)
-    TailBufs tb;
-    CHK(tail_layout(ctx, true, vfe, &tb));
-    double mm[2] = {1.0, 1.0};
-    CU(cudaMemcpy(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost));
-    bool fd = gpar_needs_whitened_panel(mm);
-    if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;
-    if (fd) {
-      CHK(gpar_dtc_logpdf(ctx, kernel, theta, vfe, jitter, val, nullptr));
-      CHK(gpar_fd_gradient([&](const double* th, double* v) { return gpar_dtc_logpdf(ctx, kernel, th, vfe, jitter, v, nullptr); }, theta, 3, grad));
-    }
-  }
-  return GPAR_OK;
+  return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened);
 }
 
 }  // extern "C"

@@ -18,6 +18,7 @@
 //    workspace slot and a second kernel sums the slots of each job in fixed order (deterministic,
 //    no atomics) and writes G (mirrored) / H column-major.
 #include "common.cuh"
+#include <algorithm>
 #include "syrk_plan.h"
 
 namespace {
@@ -193,8 +194,16 @@ syrk_reduce_kernel(const Job* __restrict__ jobs, const double* __restrict__ part
   const int r0 = blockIdx.y * 16;
   for (int e = threadIdx.x; e < 16 * GPAR_TILE; e += blockDim.x) {
     int r = r0 + e / GPAR_TILE, c = e % GPAR_TILE;
-    double v = 0.0;
-    for (int s = 0; s < jb.nslots; s++) v += partial[(int64_t)(jb.slot0 + s) * (GPAR_TILE * GPAR_TILE) + r * GPAR_TILE + c];
+    // fixed order (deterministic), four independent chains so that the loads of a long slot list overlap
+    double v4[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* p0 = partial + (int64_t)jb.slot0 * (GPAR_TILE * GPAR_TILE) + r * GPAR_TILE + c;
+    int s = 0;
+    for (; s + 4 <= jb.nslots; s += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v4[q] += p0[(int64_t)(s + q) * (GPAR_TILE * GPAR_TILE)];
+    }
+    for (; s < jb.nslots; s++) v4[0] += p0[(int64_t)s * (GPAR_TILE * GPAR_TILE)];
+    const double v = (v4[0] + v4[1]) + (v4[2] + v4[3]);
     int gr = jb.a_tile * GPAR_TILE + r, gc = jb.b_tile * GPAR_TILE + c;
     if (gr >= M || gc >= M) continue;
     if (jb.b_panel == 0) {
@@ -215,7 +224,11 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
   const int64_t NBK = Npad / GPAR_KT;
   // the optimiser re-evaluates on fixed shapes: plan once, keep the segment tables on the device
   if (ctx->plan_T != T || ctx->plan_NBK != NBK || ctx->plan_h != (int)with_h) {
-    SyrkPlan pl = plan_syrk(T, NBK, with_h, ctx->num_sms);
+    // small problems: a CTA should own at least 16 k-blocks (512 steps) of work, otherwise the 148-way stream-K split
+    // produces 148 partial tiles of a few k-blocks each and the fixed-order reduction dominates (290 us at N = 8 496)
+    const int64_t njobs = (int64_t)T * (T + 1) / 2 + (with_h ? (int64_t)T * T : 0);
+    const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, njobs * NBK / 16));
+    SyrkPlan pl = plan_syrk(T, NBK, with_h, ctas);
     const size_t nseg = pl.segs.size();
     const int Jn = (int)pl.jobs.size();
     CU(ctx->partial.reserve(nseg * GPAR_TILE * GPAR_TILE * sizeof(double)));

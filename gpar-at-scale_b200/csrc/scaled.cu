@@ -25,7 +25,8 @@ int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2);
 
 namespace {
 
-constexpr int WH_GROUPS = 256;   // 4-step groups per whitening chunk (1024 steps)
+constexpr int WH_GROUPS_MAX = 256;   // 4-step groups per whitening chunk (1024 steps) of a large problem; small problems use shorter
+                                      // chunks (whg, a multiple of 16) so that the passes still fill the machine (choose_whg)
 
 
 // ---- shared-memory staging of the per-step table (Phi_k, K_k, HA_k, S_k^-1/2) -------------------
@@ -54,15 +55,15 @@ template <int KIND, int DX, int D, int CT, bool GRAD>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
                     const double* __restrict__ table, double* __restrict__ panel, double* __restrict__ resp, int Mpad,
-                    double* __restrict__ panelD) {
+                    double* __restrict__ panelD, int whg) {
   constexpr int TS = D * D + 2 * D + 1;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   double z[CT][DX], ms[CT][D];
   bool mvalid[CT];
   double* out[CT];
   double* outd[CT];
-  const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
-  const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const int64_t g0 = (int64_t)blockIdx.y * whg;
+  const int64_t g1 = (g0 + whg < NB4) ? g0 + whg : NB4;
   const double inv_l = sqrt(inv_l2);
 #pragma unroll
   for (int c = 0; c < CT; c++) {
@@ -151,11 +152,11 @@ whiten_pass1_kernel(const double* __restrict__ X, const double* __restrict__ Z, 
 // the 32 partial products (later steps on the left).
 template <int D>
 __global__ void __launch_bounds__(32)
-chunk_transition_kernel(const double* __restrict__ table, int64_t N, double* __restrict__ psi) {
+chunk_transition_kernel(const double* __restrict__ table, int64_t N, double* __restrict__ psi, int whg) {
   constexpr int TS = D * D + 2 * D + 1;
   const int c = blockIdx.x, lane = threadIdx.x;
-  const int64_t k0 = (int64_t)c * WH_GROUPS * 4, k1 = (k0 + (int64_t)WH_GROUPS * 4 < N) ? k0 + (int64_t)WH_GROUPS * 4 : N;
-  constexpr int PER = WH_GROUPS * 4 / 32;
+  const int64_t k0 = (int64_t)c * whg * 4, k1 = (k0 + (int64_t)whg * 4 < N) ? k0 + (int64_t)whg * 4 : N;
+  const int PER = whg * 4 / 32;
   double Pm[D * D];
 #pragma unroll
   for (int i = 0; i < D * D; i++) Pm[i] = (i / D == i % D) ? 1.0 : 0.0;
@@ -235,11 +236,11 @@ carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int
 template <int D, int CT>
 __global__ void __launch_bounds__(GPAR_TILE)
 whiten_pass2_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ alpha,
-                    const double* pin, double* pout, const double* __restrict__ start, double* __restrict__ gpart, int Mpad) {
+                    const double* pin, double* pout, const double* __restrict__ start, double* __restrict__ gpart, int Mpad, int whg) {
   constexpr int TS = D * D + 2 * D + 1;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
-  const int64_t g0 = (int64_t)blockIdx.y * WH_GROUPS;
-  const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const int64_t g0 = (int64_t)blockIdx.y * whg;
+  const int64_t g1 = (g0 + whg < NB4) ? g0 + whg : NB4;
   const double* in[CT];
   double* io[CT];
   double ms[CT][D], gacc[CT];
@@ -450,12 +451,12 @@ __global__ void __launch_bounds__(GPAR_TILE, CT == 1 ? 3 : 2)
 whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ dtable,
                       const double* __restrict__ beta, const double* __restrict__ panelD, const double* __restrict__ start,
                       double* __restrict__ tstate, int nch, int chunk0, const double* __restrict__ St, const double* __restrict__ evec,
-                      const double* __restrict__ wvec, double* __restrict__ accpart, int Mpad, int M) {
+                      const double* __restrict__ wvec, double* __restrict__ accpart, int Mpad, int M, int whg) {
   constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   const int chunk = chunk0 + blockIdx.y;
-  const int64_t g0 = (int64_t)chunk * WH_GROUPS;
-  const int64_t g1 = (g0 + WH_GROUPS < NB4) ? g0 + WH_GROUPS : NB4;
+  const int64_t g0 = (int64_t)chunk * whg;
+  const int64_t g1 = (g0 + whg < NB4) ? g0 + whg : NB4;
   const int64_t cstride = (int64_t)nch * D * Mpad;       // one tangent state array
   const double *inb[CT], *ind[CT], *inS[CT];
   double mu[CT][D], dm[CT][2][D], nu[CT][D], acc[CT][3], wm[CT];
@@ -466,7 +467,7 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
     mvalid[c] = m < M;
     inb[c] = beta + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
     ind[c] = panelD + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
-    inS[c] = FINAL ? St + ((int64_t)blockIdx.y * WH_GROUPS * 4) * M + m : nullptr;
+    inS[c] = FINAL ? St + ((int64_t)blockIdx.y * whg * 4) * M + m : nullptr;
     wm[c] = (FINAL && mvalid[c]) ? wvec[m] : 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -609,10 +610,10 @@ grad_sums_kernel(const double* __restrict__ accpart, int nch, int Mpad, const do
 
 template <int KIND, int D, int CT>
 int launch_pass1_dx(gpar_ctx* ctx, int DX, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
-                    const double* table, double* panel, double* resp, int Mpad, double* panelD) {
+                    const double* table, double* panel, double* resp, int Mpad, double* panelD, int whg) {
 #define CASE_DX(DD) case DD: \
-    if (panelD) LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, true>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD); \
-    else LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, false>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD); \
+    if (panelD) LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, true>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg); \
+    else LAUNCH(ctx, (whiten_pass1_kernel<KIND, DD, D, CT, false>), grid, GPAR_TILE, 0, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg); \
     break;
   switch (DX) {
     CASE_DX(1) CASE_DX(2) CASE_DX(3) CASE_DX(4) CASE_DX(5) CASE_DX(6) CASE_DX(7) CASE_DX(8)
@@ -623,12 +624,12 @@ int launch_pass1_dx(gpar_ctx* ctx, int DX, dim3 grid, const double* X, const dou
 }
 template <int D, int CT>
 int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const double* Z, int64_t N, int M, int64_t NB4, double inv_l2, double s,
-                 const double* table, double* panel, double* resp, int Mpad, double* panelD) {
+                 const double* table, double* panel, double* resp, int Mpad, double* panelD, int whg) {
   switch (k_out) {
-    case GPAR_EQ: return launch_pass1_dx<GPAR_EQ, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
-    case GPAR_MATERN12: return launch_pass1_dx<GPAR_MATERN12, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
-    case GPAR_MATERN32: return launch_pass1_dx<GPAR_MATERN32, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
-    case GPAR_MATERN52: return launch_pass1_dx<GPAR_MATERN52, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD);
+    case GPAR_EQ: return launch_pass1_dx<GPAR_EQ, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg);
+    case GPAR_MATERN12: return launch_pass1_dx<GPAR_MATERN12, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg);
+    case GPAR_MATERN32: return launch_pass1_dx<GPAR_MATERN32, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg);
+    case GPAR_MATERN52: return launch_pass1_dx<GPAR_MATERN52, D, CT>(ctx, ctx->D, grid, X, Z, N, M, NB4, inv_l2, s, table, panel, resp, Mpad, panelD, whg);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
   }
 }
@@ -638,7 +639,7 @@ int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const dou
 typedef std::function<int(double* panel, int64_t Npad, int Mpad)> PanelHook;
 struct ScaledStats {
   double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad;
-  double *table, *alpha, *beta; int nch;
+  double *table, *alpha, *beta; int nch; int whg;      // whg: 4-step groups per whitening chunk of this call
   // gradient mode only
   double *dtable, *dalpha, *panelD, *start, *psi, *evec; double dsums[4];   // dsums: d sum log S (2), d sum alpha^2 (2)
 };
@@ -654,8 +655,19 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
   const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT;
   const int64_t NB4 = Npad / 4;
-  const int nch = (int)((NB4 + WH_GROUPS - 1) / WH_GROUPS);
   const int T = Mpad / GPAR_TILE;
+  // chunk length of the whitening / tangent passes: 1024 steps for large problems; shorter (a multiple of 64 steps) when
+  // 1024-step chunks would leave most SMs idle — at the reference's own sizes (N = 8 496, M = 50) nine blocks each walked
+  // 1024 steps sequentially (250 us per pass)
+  int whg = WH_GROUPS_MAX;
+  {
+    const int col_blocks = std::max(1, T / ((T % 2 == 0) ? 2 : 1));
+    const int64_t want_chunks = (2 * (int64_t)ctx->num_sms + col_blocks - 1) / col_blocks;
+    const int64_t g = (NB4 + want_chunks - 1) / want_chunks;
+    whg = (int)std::min<int64_t>(WH_GROUPS_MAX, std::max<int64_t>(16, (g + 15) / 16 * 16));
+    if (const char* e = getenv("GPAR_WH_GROUPS")) { int v = atoi(e); if (v >= 16 && v <= WH_GROUPS_MAX && v % 16 == 0) whg = v; }
+  }
+  const int nch = (int)((NB4 + whg - 1) / whg);
   CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
   if (grad) CU(ctx->panelD.reserve((size_t)Npad * Mpad * sizeof(double)));
   // table, alpha, sums (+ gradient: d alpha (2N), tangent table, e)
@@ -686,12 +698,12 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   int CT = (T % 2 == 0) ? 2 : 1;   // measured best on B200 (CT = 1 / 2 / 4: 8.5 / 7.6 / 7.9 ms at N = 1M, M = 1024)
   if (const char* e = getenv("GPAR_WH_CT")) { int v = atoi(e); if ((v == 1 || v == 2) && T % v == 0) CT = v; }   // tuning knob
   dim3 grid(T / CT, nch);
-  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD)));
-  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD)));
-  LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi);
+  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD, whg)));
+  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD, whg)));
+  LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi, whg);
   LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad);
-  if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
-  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad);
+  if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad, whg);
+  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad, whg);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
   if (before_syrk) CHK((*before_syrk)(panel, Npad, Mpad));
   cudaEventRecord(ctx->pev[0], ctx->stream);
@@ -701,7 +713,7 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   CU(cudaMemcpyAsync(hs, sums, (grad ? 6 : 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   st->G = G; st->g = g; st->Mpad = Mpad; st->Npad = Npad;
-  st->table = table; st->alpha = alpha; st->beta = panel; st->nch = nch;
+  st->table = table; st->alpha = alpha; st->beta = panel; st->nch = nch; st->whg = whg;
   if (grad) {   // sums = [sum log S, its 2 tangents, sum alpha^2, its 2 tangents]
     st->sum_logS = hs[0]; st->sum_a2 = hs[3]; st->dsums[0] = hs[1]; st->dsums[1] = hs[2]; st->dsums[2] = hs[4]; st->dsums[3] = hs[5];
     st->dtable = dtable; st->dalpha = dalpha; st->panelD = panelD; st->start = resp; st->psi = psi; st->evec = evec;
@@ -733,20 +745,21 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   if (const char* e = getenv("GPAR_TANGENT_CT")) { if (atoi(e) == 1) CT = 1; }
   dim3 grid(T / CT, nch);
   if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                      tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
+                      tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-              tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M);
+              tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad);
   // S' = P beta' slab by slab (library GEMM on the transposed slab), consumed at once by the final tangent pass
-  int slab_chunks = 128;                                                         // ~131072 steps per slab ...
+  const int base_chunks = std::max(1, 131072 / (st.whg * 4));
+  int slab_chunks = base_chunks;                                                 // ~131072 steps per slab ...
   {                                                                              // ... rounded to whole waves of the final tangent pass
     const int resident = ctx->num_sms * (CT == 1 ? 3 : 2), per_chunk = T / CT;
-    const int waves = std::max(1, (128 * per_chunk + resident / 2) / resident);
+    const int waves = std::max(1, (base_chunks * per_chunk + resident / 2) / resident);
     slab_chunks = std::max(1, waves * resident / per_chunk);
   }
   if (const char* e = getenv("GPAR_GRAD_SLAB")) { int v = atoi(e); if (v >= 1) slab_chunks = v; }
   slab_chunks = std::min(slab_chunks, nch);
-  const size_t slab_steps = (size_t)slab_chunks * WH_GROUPS * 4;
+  const size_t slab_steps = (size_t)slab_chunks * st.whg * 4;
   CU(ctx->panelB.reserve(slab_steps * M * sizeof(double)));
   CU(ctx->kal_f.reserve(slab_steps * M * sizeof(double)));
   double* Bt = ctx->panelB.as<double>(); double* St = ctx->kal_f.as<double>();
@@ -754,15 +767,15 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   const double one = 1.0, zero = 0.0;
   for (int c0 = 0; c0 < nch; c0 += slab_chunks) {
     const int nc = std::min(slab_chunks, nch - c0);
-    const int64_t g_lo = (int64_t)c0 * WH_GROUPS, ng = std::min<int64_t>((int64_t)nc * WH_GROUPS, NB4 - g_lo);
+    const int64_t g_lo = (int64_t)c0 * st.whg, ng = std::min<int64_t>((int64_t)nc * st.whg, NB4 - g_lo);
     const int64_t total = (int64_t)T * ng * GPAR_TILE;
     LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, st.beta, NB4, g_lo, ng, T, M, Bt);
     CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, (int)(ng * 4), M, &one, Pm, M, Bt, M, &zero, St, M));
     dim3 gs(T / CT, nc);
     if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                        tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M);
+                        tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M, st.whg);
     else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M);
+                tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M, st.whg);
   }
   CU(ctx->scal.reserve(8 * sizeof(double)));
   LAUNCH(ctx, grad_sums_kernel, 5, 1024, 0, accpart, nch, Mpad, st.evec, st.dalpha, N, ctx->scal.as<double>());
@@ -989,6 +1002,22 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
   // fork: cov(u) = Kuu + noise I, L_u, L_u^-1, cov(u)^-1 on the side stream, underneath the filter / whitening / SYRK
   CHK(dtc_tail_prepare(ctx, k_out, p, 0, noise, true));
+  {
+    // cov(u) too poorly conditioned for the collapsed statistic and the explicit P = (cov(u) + G)^-1 of the analytic
+    // gradient (error ~ cond * eps; Lambda may not even factor): value and gradient from the whitened-panel value path
+    // instead (slow, but right).  Decided before anything else is spent: L_u is a sub-millisecond side-stream job.
+    TailBufs tb0;
+    CHK(tail_layout(ctx, true, 0, &tb0));
+    double mm[2] = {1.0, 1.0};
+    CU(cudaMemcpyAsync(mm, tb0.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->stream2));
+    bool fd = gpar_needs_whitened_panel(mm);
+    if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
+    if (fd) {
+      CHK(gpar_scaled_dtc(ctx, k_time, k_out, theta, dtc, nullptr));
+      return gpar_fd_gradient([&](const double* th, double* v) { return gpar_scaled_dtc(ctx, k_time, k_out, th, v, nullptr); }, theta, 5, grad);
+    }
+  }
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, true));
   double val = 0.0, g3[3], raw[8 + GPAR_NTR];
@@ -1016,16 +1045,6 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   grad[2] = F_logl / out_l * ex[2];
   grad[3] = F_os * 2.0 * pv[3] * ex[3];
   grad[4] = F_noise * 2.0 * pv[4] * ex[4];
-  // cov(u) too poorly conditioned for the collapsed statistic and the explicit P = (cov(u) + G)^-1 of the analytic
-  // gradient (error ~ cond * eps): value and gradient from the whitened-panel value path instead (slow, but right)
-  double mm[2] = {1.0, 1.0};
-  CU(cudaMemcpy(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost));
-  bool fd = gpar_needs_whitened_panel(mm);
-  if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
-  if (fd) {
-    CHK(gpar_scaled_dtc(ctx, k_time, k_out, theta, dtc, nullptr));
-    CHK(gpar_fd_gradient([&](const double* th, double* v) { return gpar_scaled_dtc(ctx, k_time, k_out, th, v, nullptr); }, theta, 5, grad));
-  }
   return GPAR_OK;
 }
 

@@ -510,6 +510,7 @@ def test_ill_conditioned_cov_u_gradient_falls_back_to_the_value_path(ctx):
     cond 2e7, useless beyond 1e9).  Above the conditioning threshold the gradient entry points therefore difference the
     whitened-panel VALUE path (4-point stencil): against torch autograd of the oracle 1e-5 relative at cond 1e9 and 1e-3 at
     1e10, where the analytic form is off by up to O(1); value keeps 1e-8.  GPAR_GRAD_FD=0 shows what the analytic form alone would give."""
+    import gpar_at_scale_b200 as gp
     from gpar_at_scale_b200 import data, chain
     from oracle.grad import scaled_dtc_value_and_grad
     rng = np.random.default_rng(5)
@@ -527,9 +528,11 @@ def test_ill_conditioned_cov_u_gradient_falls_back_to_the_value_path(ctx):
         os.environ["GPAR_GRAD_FD"] = "0"
         try:
             _, ga = ctx.scaled_dtc_grad(3, 3, th)
+            worst_analytic = max(worst_analytic, float(np.max(np.abs(ga - g0)) / np.max(np.abs(g0))))
+        except gp.PosDefException:                      # the collapsed Lambda may not even factor in this corner
+            worst_analytic = float("inf")
         finally:
             del os.environ["GPAR_GRAD_FD"]
-        worst_analytic = max(worst_analytic, float(np.max(np.abs(ga - g0)) / np.max(np.abs(g0))))
     print("analytic gradient alone: worst relative error %.1e" % worst_analytic)
     # the stencil itself, forced on a well-conditioned problem, agrees with the analytic gradient
     th = np.array([0.2, 0.1, -0.3, 0.2, -1.0])

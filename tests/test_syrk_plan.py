@@ -31,3 +31,12 @@ def test_headline_shape_is_phase_aligned(exe):
     # N = 1M, M = 1024 with gradient: the 92 regular jobs' first pieces share one k range
     out = subprocess.run([exe, "8", "31250", "1", "148"], capture_output=True, text=True).stdout.split()
     assert float(out[4]) >= 0.55
+
+
+@pytest.mark.parametrize("T,NBK,with_h,ctas", [(1, 266, 0, 16), (1, 266, 1, 33), (1, 5, 0, 1), (2, 40, 1, 17), (1, 20, 0, 1), (2, 9, 0, 1), (3, 100, 1, 93)])
+def test_plan_with_a_capped_cta_count(exe, T, NBK, with_h, ctas):
+    """Small problems cap the CTA count (panel_syrk_run: at least 16 k-blocks per CTA): coverage must still be exact."""
+    out = subprocess.run([exe, str(T), str(NBK), str(with_h), str(ctas)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    tag, C, nseg, imbalance, aligned = out.stdout.split()
+    assert tag == "ok" and 1 <= int(C) <= ctas
