@@ -84,6 +84,44 @@ def test_group_chain_broadcast_and_input_column(ctx):
         g.close()
 
 
+def test_group_abi_error_behaviour():
+    """Status codes and messages instead of crashes: duplicate devices, missing resident result, incomplete task,
+    unknown optimiser, member without data."""
+    import gpar_at_scale_b200 as gp
+    from gpar_at_scale_b200 import _ffi
+    with pytest.raises(gp.GparError):
+        gp.Group([0, 0])                                  # one member per device
+    with pytest.raises(gp.GparError):
+        gp.Group([])
+    g = gp.Group([0])
+    try:
+        with pytest.raises(gp.GparError, match="resident result"):
+            g.broadcast(0, n=10)                          # nothing smoothed / predicted yet
+        with pytest.raises(gp.GparError, match="source member"):
+            g.broadcast(3, values=np.zeros(4))
+        with pytest.raises(gp.GparError, match="must be set|not set|inputs"):
+            g.scaled_dtc(gp.MATERN52, gp.MATERN52, np.zeros((1, 5)))       # member has no data: the member's message surfaces
+        t = np.arange(50) / 30.0
+        bad = [{"X": np.zeros((50, 2)), "Z": None, "y": np.zeros(50), "theta0": np.zeros(5)}]
+        lib = g._lib
+        arr = (_ffi.FitTask * 1)()
+        y = _ffi.as_f64(np.zeros(50)); X = _ffi.as_f64(np.zeros((50, 2)))
+        arr[0].y = _ffi.dptr(y); arr[0].X = _ffi.dptr(X); arr[0].D = 2; arr[0].Z = None; arr[0].M = 0
+        out = np.zeros(1); th = np.zeros(5)
+        st = lib.gpar_group_fit(g._h, _ffi.dptr(_ffi.as_f64(t)), 50, ctypes.cast(arr, ctypes.c_void_p), 1, 3, 3, 0, 2, _ffi.dptr(out), _ffi.dptr(th), None, None)
+        assert st == _ffi.GPAR_ERR_INVALID and b"incomplete" in lib.gpar_group_last_error(g._h)
+        arr[0].X = None; arr[0].D = 0
+        st = lib.gpar_group_fit(g._h, _ffi.dptr(_ffi.as_f64(t)), 50, ctypes.cast(arr, ctypes.c_void_p), 1, 3, 3, 7, 2, _ffi.dptr(out), _ffi.dptr(th), None, None)
+        assert st == _ffi.GPAR_ERR_INVALID and b"optimizer" in lib.gpar_group_last_error(g._h)
+        # a time-only task with valid arguments runs
+        arr[0].theta0[0] = 0.1; arr[0].theta0[1] = 0.0; arr[0].theta0[2] = -1.0
+        yy = _ffi.as_f64(np.sin(t)); arr[0].y = _ffi.dptr(yy)
+        st = lib.gpar_group_fit(g._h, _ffi.dptr(_ffi.as_f64(t)), 50, ctypes.cast(arr, ctypes.c_void_p), 1, 3, 3, 0, 3, _ffi.dptr(out), _ffi.dptr(th), None, None)
+        assert st == _ffi.GPAR_OK and np.isfinite(out[0]) and np.all(np.isfinite(th[:3])) and np.all(np.isnan(th[3:]))
+    finally:
+        g.close()
+
+
 def chain_tasks(seed, n=2500, m=40, outputs=3, restarts=2):
     rng = np.random.default_rng(seed)
     t = np.cumsum(rng.exponential(1 / 30, n))
