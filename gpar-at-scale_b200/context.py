@@ -292,6 +292,14 @@ class Group:
                                                     codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         return (vals, grads, codes) if grad else (vals, codes)
 
+    def dtc_logpdf_sharded(self, kernel, theta, vfe=False, jitter=-1.0, grad=False):
+        """ONE DTC / VFE objective over the data slices resident on the members (same pseudo-inputs everywhere):
+        per-slice statistics, one NCCL all-reduce, tail on member 0 -> value[, gradient (3,)]."""
+        th = as_f64(np.asarray(theta).ravel())
+        val = ctypes.c_double(); g3 = np.zeros(3) if grad else None
+        self._check(self._lib.gpar_group_dtc_logpdf_sharded(self._h, int(kernel), dptr(th), int(bool(vfe)), float(jitter), ctypes.byref(val), dptr(g3)))
+        return (val.value, g3) if grad else val.value
+
     def scaled_dtc(self, k_time, k_out, thetas, grad=False):
         th = as_f64(np.atleast_2d(thetas)); n = len(self)
         assert th.shape == (n, 5)

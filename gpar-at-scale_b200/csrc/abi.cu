@@ -38,6 +38,40 @@ __global__ void sum_final_kernel(const double* part, int n, double* out) {
 }
 }  // namespace
 
+// Sufficient statistics of the plain DTC objective over THIS context's resident slice of the data: panel producers and
+// the DMMA SYRK are enqueued on the context's stream, nothing is read back.  *stats -> [G (M*M) | H (M*M) | g (Mpad) |
+// h (Mpad) | y'y (1)], *count doubles.  Every term is a sum over data points, so slices on different devices add up
+// (gpar_group_dtc_logpdf_sharded all-reduces this buffer).
+int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count) {
+  if (ctx->N < 1 || ctx->M < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: inputs (set_inputs) and pseudo-inputs (set_pseudo) must be set");
+  if (ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: X has D=%d but Z has D=%d", ctx->D, ctx->Dz);
+  if (ctx->Ny != ctx->N || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: outputs length %lld != N %lld", (long long)ctx->Ny, (long long)ctx->N);
+  CU(cudaSetDevice(ctx->device));
+  const int64_t N = ctx->N; const int M = (int)ctx->M;
+  const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
+  const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT;
+  const size_t panel_bytes = (size_t)Npad * Mpad * sizeof(double);
+  CU(ctx->panelK.reserve(panel_bytes));
+  if (want_grad) CU(ctx->panelD.reserve(panel_bytes));
+  const int T = Mpad / GPAR_TILE;
+  int nsplit = std::max(1, (ctx->num_sms * 16) / T);
+  nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, Npad / 4));
+  CU(ctx->gpart.reserve((size_t)nsplit * 2 * Mpad * sizeof(double) + 1024 * sizeof(double)));
+  const size_t MM = (size_t)M * M;
+  CU(ctx->kal_a.reserve((2 * MM + 2 * (size_t)Mpad + 8) * sizeof(double)));
+  double* G = ctx->kal_a.as<double>(); double* H = G + MM; double* gh = H + MM; double* dyy = gh + 2 * Mpad;
+  if (!want_grad) CU(cudaMemsetAsync(H, 0, MM * sizeof(double), ctx->stream));       // the whole buffer is reduced
+  CHK(launch_kuf_panels(ctx, kernel, want_grad, p.l, p.s, ctx->panelK.as<double>(), ctx->panelD.as<double>(),
+                        ctx->gpart.as<double>(), nsplit, Npad, Mpad));
+  CHK(launch_reduce_gh(ctx, ctx->gpart.as<double>(), nsplit, Mpad, 2, gh));
+  double* ypart = ctx->gpart.as<double>() + (size_t)nsplit * 2 * Mpad;
+  LAUNCH(ctx, sumsq_kernel, 1024, 256, 0, ctx->y.as<double>(), N, ypart);
+  LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
+  CHK(panel_syrk_run(ctx, ctx->panelK.as<double>(), ctx->panelD.as<double>(), Npad, Mpad, M, want_grad, G, H));
+  *stats = G; *count = 2 * MM + 2 * (size_t)Mpad + 1;
+  return GPAR_OK;
+}
+
 extern "C" {
 
 int gpar_abi_version(void) { return GPAR_ABI_VERSION; }

@@ -216,6 +216,8 @@ int lgssm_smooth_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, do
                                  const double* y, const double* rvec, double* d_mean, double* d_var, double* d_lml);
 int lgssm_filter_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
                                  const double* y, const double* rvec, double* d_alpha, double* d_lml);
+// abi.cu: sufficient statistics of the plain DTC objective over the context's resident data slice (async on its stream)
+int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count);
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;

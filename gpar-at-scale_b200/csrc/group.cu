@@ -33,6 +33,7 @@ struct gpar_group {
   decltype(&ncclCommInitAll) CommInitAll = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
@@ -62,7 +63,7 @@ int load_nccl(gpar_group* g) {
 #define BIND(field, sym)                                                                                            \
   g->field = reinterpret_cast<decltype(g->field)>(dlsym(g->lib, sym));                                               \
   if (!g->field) return group_fail(g, GPAR_ERR_CUDA, "gpar_group_create: symbol %s missing in libnccl", sym)
-  BIND(CommInitAll, "ncclCommInitAll"); BIND(CommDestroy, "ncclCommDestroy"); BIND(AllGather, "ncclAllGather");
+  BIND(CommInitAll, "ncclCommInitAll"); BIND(CommDestroy, "ncclCommDestroy"); BIND(AllGather, "ncclAllGather"); BIND(AllReduce, "ncclAllReduce");
   BIND(Broadcast, "ncclBroadcast"); BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd");
   BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
@@ -282,6 +283,50 @@ int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* th
   return group_eval(g, 5, thetas, vals, grads, codes, [&](int i, const double* th, double* v, double* gr) {
     return gr ? gpar_scaled_dtc_grad(g->ctx[i], k_time, k_out, th, v, gr) : gpar_scaled_dtc(g->ctx[i], k_time, k_out, th, v, nullptr);
   });
+}
+
+// ONE plain DTC / VFE objective whose data are sharded over the members by rows (SURVEY 8e "intra-output N-sharding"):
+// every member evaluates the sufficient statistics G = Kuf Kfu, H, g, h, y'y of ITS slice (same pseudo-inputs on every
+// member; slices may differ in length), ONE ncclAllReduce sums the M x M + ... buffer over NVLink, member 0 runs the tail.
+// The only data-path collective of the library: 8 (2 M^2 + 2 M + 1) bytes per evaluation (16.8 MB at M = 1024).
+int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!theta || !val) return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: theta and val must not be NULL");
+  if (kernel < GPAR_EQ || kernel > GPAR_MATERN52) return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: unknown kernel code %d", kernel);
+  const int n = (int)g->ctx.size();
+  int64_t Ntot = 0;
+  for (int i = 0; i < n; i++) {
+    if (g->ctx[i]->M != g->ctx[0]->M || g->ctx[i]->Dz != g->ctx[0]->Dz)
+      return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: member %d holds %lld pseudo-inputs of dimension %d, member 0 %lld of %d",
+                        i, (long long)g->ctx[i]->M, g->ctx[i]->Dz, (long long)g->ctx[0]->M, g->ctx[0]->Dz);
+    Ntot += g->ctx[i]->N;
+  }
+  const GpParams p = unpack_gp3(theta);
+  const bool want_grad = grad != nullptr;
+  gpar_ctx* c0 = g->ctx[0];
+  GCU(cudaSetDevice(g->dev[0]));
+  int rc = dtc_tail_prepare(c0, kernel, p, vfe, jitter, want_grad);      // cov(u), L_u, ... on member 0's side stream
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  std::vector<double*> stats(n, nullptr);
+  std::vector<size_t> count(n, 0);
+  std::vector<int> st;
+  run_members(g, st, [&](int i) { return dtc_slice_stats(g->ctx[i], kernel, p, want_grad, &stats[i], &count[i]); });
+  for (int i = 0; i < n; i++)
+    if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  GNC(g->GroupStart());
+  for (int i = 0; i < n; i++) GNC(g->AllReduce(stats[i], stats[i], count[i], ncclDouble, ncclSum, g->comm[i], g->ctx[i]->stream));
+  GNC(g->GroupEnd());
+  GCU(cudaSetDevice(g->dev[0]));
+  const int M = (int)c0->M, Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
+  const size_t MM = (size_t)M * M;
+  double* G = stats[0]; double* H = G + MM; double* gh = H + MM; double* dyy = gh + 2 * Mpad;
+  double yy = 0.0;
+  GCU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+  for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
+  GCU(cudaSetDevice(g->dev[0]));
+  rc = dtc_tail(c0, kernel, p, vfe, jitter, Ntot, G, H, gh, gh + Mpad, yy, val, grad, nullptr, false);
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  return GPAR_OK;
 }
 
 // n doubles from member src — `host` if given, else the resident result of its last gpar_lgssm_smooth /

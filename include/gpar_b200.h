@@ -191,6 +191,12 @@ int gpar_group_dtc_logpdf(gpar_group* g, int kernel, const double* thetas, int v
 int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* thetas,
                           double* vals, double* grads, int32_t* codes);             /* gpar_scaled_dtc(_grad) per member */
 
+/* ONE plain DTC / VFE objective (gpar_dtc_logpdf) whose data rows are sharded over the members — SURVEY 8e's optional
+ * intra-output N-sharding: load slice i of (X, y) and the SAME pseudo-inputs on member i; each member evaluates the
+ * sufficient statistics of its slice, one ncclAllReduce (8 (2 M^2 + 2 M + 1) bytes) sums them over NVLink, member 0
+ * runs the M x M tail.  The only data-path collective of the library. */
+int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad);
+
 /* One conditional-GP fit of the chain: inputs X (D x N ColVecs = the observed earlier outputs; D = 0: a time-only
  * state-space GP with 3 parameters, temporal_gp_inference.jl:69-82), pseudo-inputs Z (D x M), outputs y (N),
  * start point theta0 (the first 3 or 5 entries are used). */

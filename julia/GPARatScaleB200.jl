@@ -212,6 +212,14 @@ function group_dtc_logpdf(g::Group, k, thetas::Matrix{Float64}; vfe::Bool = fals
     return vals, grads, codes
 end
 
+# ONE DTC / VFE objective whose rows are sharded over the members (same Z everywhere): all-reduce of the statistics
+function group_dtc_logpdf_sharded(g::Group, k, theta::Vector{Float64}; vfe::Bool = false, jitter::Float64 = -1.0, grad::Bool = false)
+    val = Ref{Float64}(0.0); gr = grad ? zeros(3) : nothing
+    gcheck(g, ccall((:gpar_group_dtc_logpdf_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Float64, Ref{Float64}, Ptr{Float64}),
+                    g.h, kernel_code(k), theta, vfe, jitter, val, grad ? gr : C_NULL))
+    return grad ? (val[], gr) : val[]
+end
+
 # whole Nelder-Mead fits of the chain's conditional GPs; Xs[k] (D x N) / Zs[k] (D x M) are `nothing` for a time-only task
 function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float64}}, theta0s::Vector{Vector{Float64}}, k_time, k_out; iterations::Integer = 200, optimizer::Symbol = :neldermead)
     nt = length(ys)

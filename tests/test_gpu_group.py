@@ -84,6 +84,53 @@ def test_group_chain_broadcast_and_input_column(ctx):
         g.close()
 
 
+def test_group_sharded_dtc_single_member_is_the_plain_entry_point(ctx):
+    """gpar_group_dtc_logpdf_sharded with one member: same kernels, an all-reduce over one rank -> identical numbers,
+    value and gradient, DTC and VFE."""
+    import gpar_at_scale_b200 as gp
+    rng = np.random.default_rng(31)
+    n, m = 6000, 70
+    x = rng.uniform(0, 10, n); z = np.linspace(0, 10, m); y = np.sin(x) + 0.1 * rng.normal(size=n)
+    th = np.log([1.3, 0.9, 0.2])
+    g = gp.Group([0])
+    try:
+        mb = g.members[0]
+        mb.set_inputs(x); mb.set_pseudo(z); mb.set_outputs(y)
+        ctx.set_inputs(x); ctx.set_pseudo(z); ctx.set_outputs(y)
+        for vfe in (False, True):
+            v, gr = g.dtc_logpdf_sharded(gp.MATERN52, th, vfe=vfe, grad=True)
+            v0, g0 = ctx.dtc_logpdf(gp.MATERN52, th, vfe=vfe, grad=True)
+            assert v == v0 and np.array_equal(gr, g0)
+            assert g.dtc_logpdf_sharded(gp.MATERN52, th, vfe=vfe) == pytest.approx(v0, rel=1e-12)
+    finally:
+        g.close()
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs two devices (gpurun --gpus 2)")
+def test_group_sharded_dtc_two_devices(ctx):
+    """Rows split unevenly over two devices: the all-reduced statistics give the objective of the whole data set."""
+    import gpar_at_scale_b200 as gp
+    rng = np.random.default_rng(32)
+    n, m, d = 9001, 130, 2
+    X = rng.normal(size=(n, d)) * 2; Z = rng.normal(size=(m, d)) * 2; y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    th = np.log([1.5, 1.1, 0.15])
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y)
+    g = gp.Group([0, 1])
+    try:
+        cut = 3777
+        for mb, sl in zip(g.members, (slice(0, cut), slice(cut, n))):
+            mb.set_inputs(X[sl]); mb.set_pseudo(Z); mb.set_outputs(y[sl])
+        for vfe in (False, True):
+            v, gr = g.dtc_logpdf_sharded(gp.MATERN52, th, vfe=vfe, grad=True)
+            v0, g0 = ctx.dtc_logpdf(gp.MATERN52, th, vfe=vfe, grad=True)
+            assert abs(v - v0) <= 1e-11 * abs(v0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0))
+        g.members[1].set_pseudo(Z[:100])
+        with pytest.raises(gp.GparError, match="pseudo-inputs"):
+            g.dtc_logpdf_sharded(gp.MATERN52, th)
+    finally:
+        g.close()
+
+
 def test_group_abi_error_behaviour():
     """Status codes and messages instead of crashes: duplicate devices, missing resident result, incomplete task,
     unknown optimiser, member without data."""
