@@ -69,6 +69,13 @@ def test_fit_task_struct_matches_the_header_layout():
     assert ctypes.sizeof(T) == 80
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/gpar_b200.h must compile as C99 (what cgo / Julia's Clang.jl / ctypesgen parse)."""
+    src = tmp_path / "hdr_check.c"
+    src.write_text('#include "gpar_b200.h"\nint main(void) { gpar_fit_task t; (void)t; return GPAR_OPT_LBFGS == 1 && GPAR_ERR_NOT_POSDEF == 3 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "gpar-at-scale_b200")
     for dirpath, _, files in os.walk(pkg):
