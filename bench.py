@@ -1,32 +1,44 @@
 #!/usr/bin/env python
-"""bench.py — the headline metric of BASELINE.json on B200:
+"""bench.py — the three metrics of BASELINE.json on B200, in one run:
 
-    pseudo-point logpdf+grad evals/s at N = 1M, M = 1024   (config 2: examples/dtc_example.jl-shaped
-    single-output DTC pseudo-point GP, synthetic 1-D inputs, Matern-5/2)
+    pseudo-point logpdf+grad evals/s (N=1M, M=1024)   <- the headline line (`metric`, `value`, `e2e`, `roofline`)
+    Kalman time-steps/s                                 <- extra.kalman_* (with their own roofline blocks)
+    GPAR fit s                                          <- extra.gpar_fit (BASELINE configs[4], STRONG scaling over --gpus)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-fit] [--no-extra] [--no-cpu]
 
-A "step" is one blocking evaluation of the DTC log-pdf and its gradient through the C ABI
-(gpar_dtc_logpdf): Kuf/dKuf panel evaluation -> DMMA stream-K SYRK/GEMM -> M x M tail.
- * value : evals/s with X, Z, y resident in HBM (the optimiser's situation: dtc.jl:29-61 re-evaluates
-           the closure on fixed data).
- * e2e   : the same call with HOST buffers re-uploaded every step (gpar_set_inputs/outputs from
-           pinned memory inside the timed region) and the scalar + gradient read back.
- * N > 1 : one process per GPU (torchrun); the shards are independent objective evaluations
-           (per-output conditional GPs x hyper-parameter restarts), no data-path collective; NCCL only
-           all-gathers the (logpdf, gradient) scalars every step.  scaling = "weak".
- * --impl reference : the CPU restatement of the reference's algorithm (oracle port, all host
-           threads) on a bounded sample, linearly extrapolated in N (every term is O(N)).
-Extra keys report the other two BASELINE metrics measured in the same run (Kalman time-steps/s on
-1024 x 10k independent Matern-5/2 sequences; the scaled-GPAR objective at N = 1M).
+A "step" of the headline is one blocking evaluation of the DTC log-pdf and its gradient through the C ABI
+(gpar_dtc_logpdf): Kuf/dKuf panel evaluation -> DMMA stream-K SYRK/GEMM -> M x M tail (configs[1]:
+examples/dtc_example.jl-shaped single-output pseudo-point GP, synthetic 1-D inputs, Matern-5/2).
+ * value : evals/s with X, Z, y resident in HBM (the optimiser's situation: dtc.jl:29-61 re-evaluates the closure on
+           fixed data).
+ * e2e   : the same call with HOST buffers re-uploaded every step (gpar_set_inputs/outputs from pinned memory inside
+           the timed region) and the scalar + gradient read back.
+ * N > 1 : one process per GPU (torchrun); the shards are independent objective evaluations (per-output conditional
+           GPs x hyper-parameter restarts), no data-path collective; NCCL only all-gathers the (logpdf, gradient)
+           scalars every step.  scaling = "weak".
+ * roofline.peak is MEASURED IN THIS RUN (gpar_measure_peaks: register-only DMMA loop, ~50 ms).
+ * extra.gpar_fit : the 8-output GPAR chain fit of configs[4] (examples/GPAR_scaled_examples.jl:132-175 call pattern):
+           N = 2 097 152, M = 2048, 8 restarts = 64 independent (output, restart) Nelder-Mead tasks with a FIXED
+           iteration budget, partitioned over the ranks — total work fixed, so this is the strong-scaling curve of the
+           run.  With >= 2 GPUs rank 0 then repeats the restart-0 tasks through the one-process group path
+           (gpar_group_fit over all devices) and checks that both paths reach identical optima.
+ * --impl reference : the CPU restatement of the reference's algorithm (oracle port, all host threads) on a bounded
+           sample, linearly extrapolated in N (every term is O(N)).
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is "the CPU path with all the host threads it can use"
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -36,18 +48,41 @@ sys.path.insert(0, ROOT)
 N_FULL, M_FULL = 1_000_000, 1024
 THETA = np.log(np.array([1.0, 1.0, 0.1]))
 METRIC = "pseudo-point logpdf+grad evals/s (N=1M,M=1024)"
-FP64_PEAK_TFLOPS_FALLBACK = 36.96     # profiles/peaks_r01.json: DMMA m8n8k4 microbenchmark on this pool's B200
+FP64_PEAK_TFLOPS_FALLBACK = 36.96     # profiles/peaks_r01.json; used only if the in-run measurement fails
+FIT = {"outputs": 8, "N": 2_097_152, "M": 2048, "restarts": 8, "iterations": 10}
+
+
 def _hbm_peak_gbps():
     """Measured copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the value it held in round 1."""
     try:
-        import json
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         return 6554.2
 
 
 HBM_PEAK_GBPS = _hbm_peak_gbps()
-NCU_SYRK_DRAM_BYTES = 30.93e9          # dram__bytes_read.sum + dram__bytes_write.sum of panel_syrk_kernel, one ncu launch (profiles/ncu_syrk_traffic_r01c.csv)
+
+
+def ncu_traffic(kernel="panel_syrk_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the newest committed ncu capture
+    (profiles/ncu_syrk_traffic_r*.csv) -> (bytes, file name); (None, None) if there is none."""
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_syrk_traffic_r*.csv"))):
+        rd = wr = None
+        try:
+            for line in open(path):
+                if kernel not in line:
+                    continue
+                cols = [c.strip('"') for c in line.rstrip("\n").split('","')]
+                if "dram__bytes_read.sum" in cols and rd is None:
+                    rd = float(cols[-1].replace(",", "").strip('"'))
+                if "dram__bytes_write.sum" in cols and wr is None:
+                    wr = float(cols[-1].replace(",", "").strip('"'))
+        except Exception:
+            continue
+        if rd is not None and wr is not None:
+            best = (rd + wr, os.path.basename(path))
+    return best
 
 
 def make_data(seed, n=N_FULL, m=M_FULL):
@@ -58,6 +93,18 @@ def make_data(seed, n=N_FULL, m=M_FULL):
     z = np.linspace(x.min(), x.max(), m)
     y = np.sin(x) + 0.3 * np.cos(3.1 * x) + 0.1 * rng.normal(size=n)
     return x, z, y
+
+
+def synth_chain(P, N, seed=4):
+    """the big-set recipe of src/data/toy_data.jl:79-87 extended to P outputs, y_i = f(x, y_<i) + noise
+    (std 0.64), on the regular grid x = k/30 (toy_data.jl:6)."""
+    rng = np.random.default_rng(seed)
+    x = np.arange(N) / 30.0
+    Y = np.zeros((P, N))
+    Y[0] = 3 - np.sin(np.pi / 10 * (x + 1) * 0.01) - (x * 0.01) ** 0.3 + 0.64 * rng.normal(size=N)
+    for i in range(1, P):
+        Y[i] = np.cos(Y[i - 1]) ** 2 + np.sin(np.pi / 20 * x * 0.01 * (i + 1)) + 0.1 * Y[max(i - 2, 0)] + 0.64 * rng.normal(size=N)
+    return x, Y
 
 
 class ClockSampler(threading.Thread):
@@ -111,6 +158,14 @@ def time_cpu_port(sample_n, steps, warmup, seed=1):
     return evals_per_s, dt, os.cpu_count()
 
 
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -121,11 +176,155 @@ def run_reference(args):
     sample = "N=%d of %d (1/32), M=%d, all data; %.2f s per sampled step, linearly extrapolated in N" % (sample_n, N_FULL, M_FULL, dt)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dtc_logpdf_grad N=1000000 M=1024 D=1 Matern52 (BASELINE configs[1])", "note": "CPU restatement of the reference algorithm (no Julia in the image); the reference itself has no gradient"},
-            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "dtc_logpdf_grad N=1000000 M=1024 D=1 Matern52 (BASELINE configs[1])", "note": "CPU restatement of the reference algorithm (no Julia in the image); the reference itself has no gradient; one CPU run whatever --gpus says"},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "blas_threads": blas_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def kalman_roofline(steps, ms, bytes_per_step, peaks, note):
+    """a Kalman step is 250 FP64 flop by the sequential count and `bytes_per_step` algorithmic HBM bytes; report
+    both fractions and name the binding roof (the larger fraction)."""
+    tf = steps * 250.0 / (ms * 1e-3) / 1e12
+    gb = steps * bytes_per_step / (ms * 1e-3) / 1e9
+    f_fp, f_hbm = tf / peaks["dfma_tflops"], gb / HBM_PEAK_GBPS
+    return {"ms": ms, "steps_per_s": steps / ms * 1e3, "bound": "fp64" if f_fp >= f_hbm else "hbm",
+            "fp64": {"achieved_TFLOPs": tf, "peak_TFLOPs": peaks["dfma_tflops"], "frac": f_fp, "flop_per_step": 250},
+            "hbm": {"achieved_GBps": gb, "peak_GBps": HBM_PEAK_GBPS, "frac": f_hbm, "bytes_per_step": bytes_per_step},
+            "frac": max(f_fp, f_hbm), "note": note}
+
+
+def run_extra(ctx, gp, xp, yp, peaks):
+    """The Kalman metric (BASELINE configs[2] and the north star's 10M-step sequence) and the scaled-GPAR objective at
+    N = 1M, device-resident, CUDA-event timed by the library."""
+    extra = {}
+    rng = np.random.default_rng(2)
+    B, NK = 1024, 10000
+    tk = np.cumsum(rng.exponential(1 / 30, NK)); Yk = rng.normal(size=(B, NK))
+    ths = np.stack([np.log(rng.uniform(0.05, 5, B)), np.log(rng.uniform(0.3, 3, B)), np.log(rng.uniform(0.01, 1, B))], axis=1)
+    ctx.set_times(tk); ctx.set_outputs(Yk)
+
+    def med_ms(fn, n=7, skip=3):
+        out = []
+        for _ in range(n):
+            fn(); out.append(ctx.last_timing()[0])
+        return float(np.median(out[skip:]))
+
+    kal_ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths), 8, 3)
+    extra["kalman_filter_steps_per_s"] = B * NK / kal_ms * 1e3
+    extra["kalman_filter_ms_1024x10k"] = kal_ms
+    extra["kalman_filter_1024x10k_roofline"] = kalman_roofline(
+        B * NK, kal_ms, 8, peaks, "cfg 3: 1024 independent Matern-5/2 models x 10k steps on one irregular grid; y read once (8 B/step), t shared")
+    sm_ms = med_ms(lambda: ctx.lgssm_smooth(gp.MATERN52, ths[0], keep_on_device=True), 5, 2)
+    extra["kalman_smoother_steps_per_s"] = B * NK / sm_ms * 1e3
+    extra["kalman_smoother_1024x10k_roofline"] = kalman_roofline(
+        B * NK, sm_ms, 24, peaks, "cfg 3 filter + RTS smoother, 1024 sequences sharing one model: y in, mean out per sequence (+ shared var): 16-24 B/step; 250 flop/step is the per-model count — with a shared model the per-sequence work is ~30 flop/step, so HBM is the binding roof")
+    extra["kalman_logpdf_grad_ms_1024x10k"] = med_ms(lambda: ctx.lgssm_logpdf_grad(gp.MATERN52, ths), 4, 1)
+    # the same 1024 sequences under ONE model (batching over data, the reference's M+1-column / MC-sample pattern)
+    extra["kalman_filter_shared_model_steps_per_s"] = B * NK / med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths[0])) * 1e3
+    # the same batch on the regular grid range(0, step = 1/30) (toy_data.jl:6): steady-state path
+    ctx.set_times_range(0.0, 1 / 30, NK)
+    ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths))
+    extra["kalman_filter_regular_grid_steps_per_s"] = B * NK / ms * 1e3
+    # one 10M-step Matern-5/2 sequence (north-star shape): irregular grid, then the regular grid
+    N10 = 10_000_000
+    y10 = rng.normal(size=N10); th3 = np.log(np.array([1.0, 1.0, 0.1]))
+    ctx.set_outputs(y10); ctx.set_times(np.cumsum(rng.exponential(1 / 30, N10)))
+    ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
+    extra["kalman_filter_1x10M_steps_per_s"] = N10 / ms * 1e3
+    extra["kalman_filter_1x10M_ms"] = ms
+    extra["kalman_filter_1x10M_irregular_roofline"] = kalman_roofline(
+        N10, ms, 16, peaks, "one 10M-step sequence, irregular grid: (t_k, y_k) read once = 16 B/step")
+    ctx.set_times_range(0.0, 1 / 30, N10)
+    ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
+    extra["kalman_filter_1x10M_regular_grid_steps_per_s"] = N10 / ms * 1e3
+    extra["kalman_filter_1x10M_regular_grid_ms"] = ms
+    del y10
+    # sixteen 10M-step sequences, each with its own model (hyper-parameter candidates): the HBM-bound shape of
+    # the single-pass steady-state filter; algorithmic traffic 8 B/step (y read once), peak = measured copy bandwidth
+    B8 = 16
+    ctx.set_outputs(rng.normal(size=(B8, N10)))
+    ths8 = np.tile(th3, (B8, 1)) + 0.05 * rng.normal(size=(B8, 3))
+    ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths8))
+    extra["kalman_filter_16x10M_regular_grid_steps_per_s"] = B8 * N10 / ms * 1e3
+    extra["kalman_filter_16x10M_regular_grid_ms"] = ms
+    extra["kalman_filter_16x10M_regular_grid_hbm"] = {"achieved_GBps": B8 * N10 * 8 / (ms * 1e-3) / 1e9, "peak_GBps": HBM_PEAK_GBPS,
+                                                     "frac": B8 * N10 * 8 / (ms * 1e-3) / 1e9 / HBM_PEAK_GBPS,
+                                                     "note": "whole blocking call (set-up, head, main pass with fused finish), 8 B/step algorithmic"}
+    tfull = np.arange(N_FULL) / 30.0
+    ctx.set_inputs(xp); ctx.set_outputs(yp); ctx.set_times(tfull)
+    th5 = np.log(np.array([1.0, 1.0, 1.0, 1.0, 0.1]))
+    extra["scaled_gpar_objective_ms_N1M_M1024"] = med_ms(lambda: ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5), 5, 2)
+    ms = med_ms(lambda: ctx.scaled_dtc_grad(gp.MATERN52, gp.MATERN52, th5), 4, 1)
+    extra["scaled_gpar_objective_and_grad_ms_N1M_M1024"] = ms
+    fl = N_FULL * M_FULL * (M_FULL + 1) + 2.0 * N_FULL * M_FULL * M_FULL      # SYRK (symmetric) + S = beta P
+    extra["scaled_gpar_objective_and_grad_roofline"] = {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+                                                        "frac": fl / (ms * 1e-3) / 1e12 / peaks["dmma_tflops"],
+                                                        "note": "whole blocking call; DMMA work = N M (M+1) + 2 N M^2 (panel_syrk_kernel + panel_gemm_kernel, no library GEMM)"}
+    return extra
+
+
+def run_gpar_fit(ctx, gp, world, rank, local, iterations, side_group):
+    """BASELINE configs[4]: 8 outputs x 8 restarts = 64 independent Nelder-Mead fits (fixed iteration budget) over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from gpar_at_scale_b200 import chain
+    P, N, M, R = FIT["outputs"], FIT["N"], FIT["M"], FIT["restarts"]
+    t, Y = synth_chain(P, N)
+    X = np.ascontiguousarray(Y[:1].T)          # warm-up: one evaluation allocates the panels and plans the SYRK
+    ctx.set_inputs(X); ctx.set_pseudo(chain.strided_pseudo_inputs(X, M)); ctx.set_times(t); ctx.set_outputs(Y[1]); ctx.set_noise_vector(None)
+    ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, np.zeros(5))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    sync(); t0 = time.perf_counter()
+    best, info = chain.fit_chain(t, Y, M, n_restarts=R, iterations=iterations, seed=4, ctx=ctx)
+    sync(); dt = time.perf_counter() - t0
+    stat = torch.tensor([float(info["objective_evals_this_rank"]), info["busy_seconds"], dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        stats = [torch.zeros_like(stat) for _ in range(world)]
+        dist.all_gather(stats, stat)
+        stats = [s.tolist() for s in stats]
+    else:
+        stats = [stat.tolist()]
+    evals = [int(s[0]) for s in stats]; busy = [s[1] for s in stats]; dt = max(s[2] for s in stats)
+    vals, thetas = info["minimum"], info["minimizer"]
+    out = {"metric": "GPAR fit s", "seconds": dt, "scaling": "strong", "n_gpus": world,
+           "workload": "GPAR chain fit: outputs=%d N=%d M=%d restarts=%d -> %d (output, restart) tasks, Nelder-Mead with a fixed budget of %d iterations per task (Optim.jl defaults), Matern-5/2 time and output kernels; output 1 is the time-only state-space GP (BASELINE configs[4], GPAR_scaled_examples.jl:132-175)" % (P, N, M, R, P * R, iterations),
+           "objective_evaluations_total": int(sum(evals)), "objective_evaluations_per_rank": evals,
+           "busy_seconds_per_rank": busy, "idle_fraction_slowest_vs_mean": 1.0 - float(np.mean(busy)) / max(busy),
+           "evaluations_per_task_mean": float(sum(evals)) / (P * R),
+           "best_nlml_per_output": {str(o): repr(best[o][0]) for o in sorted(best)},
+           "optima_checksum": repr(float(np.sum(vals))),
+           "identical_optima_note": "every task is a deterministic Nelder-Mead run on its own data: best_nlml_per_output / optima_checksum must be bit-identical for every --gpus"}
+    # one process, all devices: the restart-0 task of every output through gpar_group_fit (dynamic hand-out over the
+    # members, C++ Nelder-Mead twin) — must reproduce the torchrun path's optima for those tasks exactly
+    if world > 1:
+        if rank == 0:
+            g = gp.Group(list(range(world)))
+            tasks = []
+            for o in range(P):
+                th0 = np.random.default_rng([4, o, 0]).random(3 if o == 0 else 5)
+                if o == 0:
+                    tasks.append({"X": None, "Z": None, "y": Y[0], "theta0": th0})
+                else:
+                    Xo = np.ascontiguousarray(Y[:o].T)
+                    tasks.append({"X": Xo, "Z": chain.strided_pseudo_inputs(Xo, M), "y": Y[o], "theta0": th0})
+            tg = time.perf_counter()
+            gmin, gth, calls, member = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations)
+            tg = time.perf_counter() - tg
+            ref = np.array([vals[o * R] for o in range(P)])
+            out["group_fit"] = {"path": "gpar_group_fit, one process, %d devices, %d tasks (restart 0 of every output)" % (world, P), "seconds": tg,
+                                "f_calls": calls.tolist(), "member_of": member.tolist(), "members_used": int(len(set(member.tolist()))),
+                                "max_rel_diff_vs_torchrun_path": float(np.max(np.abs(gmin - ref) / np.abs(ref))),
+                                "identical_optima": bool(np.all(gmin == ref))}
+            g.close()
+        dist.barrier(group=side_group)       # host-side wait (gloo): no NCCL kernel spins on the GPUs the group leg uses
+    return out
 
 
 def run_ours(args):
@@ -139,8 +338,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    side_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        side_group = dist.new_group(backend="gloo")
     K, W = args.steps, max(args.warmup, 3)
 
     x, z, y = make_data(1 + rank)        # each rank: its own independent problem of the named shape (weak scaling)
@@ -149,6 +350,11 @@ def run_ours(args):
     yh = torch.empty(N_FULL, dtype=torch.float64).pin_memory(); yh.numpy()[:] = y
     xp, yp = xh.numpy(), yh.numpy()
     ctx = gp.Context(local)
+    try:
+        peaks = ctx.measure_peaks(); peaks["source"] = "measured in this run (gpar_measure_peaks: register-only mma.sync.m8n8k4.f64 / DFMA loops, best of 3; 1 GiB copy)"
+    except Exception as e:      # noqa: BLE001
+        peaks = {"dmma_tflops": FP64_PEAK_TFLOPS_FALLBACK, "dfma_tflops": FP64_PEAK_TFLOPS_FALLBACK, "hbm_copy_gbs": HBM_PEAK_GBPS,
+                 "source": "fallback profiles/peaks_r01.json (%s)" % e}
     ctx.set_inputs(xp); ctx.set_pseudo(z); ctx.set_outputs(yp)
     gathered = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
 
@@ -194,75 +400,18 @@ def run_ours(args):
 
     extra = {}
     if rank == 0 and not args.no_extra:
-        # the other two BASELINE metrics, same run (device-resident, CUDA-event timed by the library)
-        rng = np.random.default_rng(2)
-        B, NK = 1024, 10000
-        tk = np.cumsum(rng.exponential(1 / 30, NK)); Yk = rng.normal(size=(B, NK))
-        ths = np.stack([np.log(rng.uniform(0.05, 5, B)), np.log(rng.uniform(0.3, 3, B)), np.log(rng.uniform(0.01, 1, B))], axis=1)
-        ctx.set_times(tk); ctx.set_outputs(Yk)
-        ts = []
-        for i in range(8):
-            ctx.lgssm_logpdf(gp.MATERN52, ths); ts.append(ctx.last_timing()[0])
-        kal_ms = float(np.median(ts[3:]))
-        ts = []
-        for i in range(4):
-            ctx.lgssm_smooth(gp.MATERN52, ths[0]); ts.append(ctx.last_timing()[0])
-        extra["kalman_filter_steps_per_s"] = B * NK / kal_ms * 1e3
-        extra["kalman_filter_ms_1024x10k"] = kal_ms
-        extra["kalman_smoother_steps_per_s"] = B * NK / float(np.median(ts[1:])) * 1e3
-
-        def med_ms(fn, n=6, skip=2):
-            out = []
-            for _ in range(n):
-                fn(); out.append(ctx.last_timing()[0])
-            return float(np.median(out[skip:]))
-        extra["kalman_logpdf_grad_ms_1024x10k"] = med_ms(lambda: ctx.lgssm_logpdf_grad(gp.MATERN52, ths), 4, 1)
-        # the same 1024 sequences under ONE model (batching over data, the reference's M+1-column / MC-sample pattern)
-        extra["kalman_filter_shared_model_steps_per_s"] = B * NK / med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths[0])) * 1e3
-        # the same batch on the regular grid range(0, step = 1/30) (toy_data.jl:6): steady-state path
-        ctx.set_times_range(0.0, 1 / 30, NK)
-        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths))
-        extra["kalman_filter_regular_grid_steps_per_s"] = B * NK / ms * 1e3
-        # one 10M-step Matern-5/2 sequence (north-star shape): irregular grid, then the regular grid
-        N10 = 10_000_000
-        y10 = rng.normal(size=N10); th3 = np.log(np.array([1.0, 1.0, 0.1]))
-        ctx.set_outputs(y10); ctx.set_times(np.cumsum(rng.exponential(1 / 30, N10)))
-        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
-        extra["kalman_filter_1x10M_steps_per_s"] = N10 / ms * 1e3
-        extra["kalman_filter_1x10M_ms"] = ms
-        ctx.set_times_range(0.0, 1 / 30, N10)
-        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, th3))
-        extra["kalman_filter_1x10M_regular_grid_steps_per_s"] = N10 / ms * 1e3
-        extra["kalman_filter_1x10M_regular_grid_ms"] = ms
-        del y10
-        # sixteen 10M-step sequences, each with its own model (hyper-parameter candidates): the HBM-bound shape of
-        # the single-pass steady-state filter; algorithmic traffic 8 B/step (y read once), peak = measured copy bandwidth
-        B8 = 16
-        ctx.set_outputs(rng.normal(size=(B8, N10)))
-        ths8 = np.tile(th3, (B8, 1)) + 0.05 * rng.normal(size=(B8, 3))
-        ms = med_ms(lambda: ctx.lgssm_logpdf(gp.MATERN52, ths8))
-        extra["kalman_filter_16x10M_regular_grid_steps_per_s"] = B8 * N10 / ms * 1e3
-        extra["kalman_filter_16x10M_regular_grid_ms"] = ms
-        extra["kalman_filter_16x10M_regular_grid_hbm"] = {"achieved_GBps": B8 * N10 * 8 / (ms * 1e-3) / 1e9, "peak_GBps": HBM_PEAK_GBPS,
-                                                         "frac": B8 * N10 * 8 / (ms * 1e-3) / 1e9 / HBM_PEAK_GBPS,
-                                                         "note": "whole blocking call (set-up, head, main pass with fused finish), 8 B/step algorithmic"}
-        tfull = np.arange(N_FULL) / 30.0
-        ctx.set_inputs(xp); ctx.set_outputs(yp); ctx.set_times(tfull)
-        th5 = np.log(np.array([1.0, 1.0, 1.0, 1.0, 0.1]))
-        ts = []
-        for i in range(5):
-            ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5); ts.append(ctx.last_timing()[0])
-        extra["scaled_gpar_objective_ms_N1M_M1024"] = float(np.median(ts[2:]))
-        ts = []
-        for i in range(4):
-            ctx.scaled_dtc_grad(gp.MATERN52, gp.MATERN52, th5); ts.append(ctx.last_timing()[0])
-        extra["scaled_gpar_objective_and_grad_ms_N1M_M1024"] = float(np.median(ts[1:]))
+        extra = run_extra(ctx, gp, xp, yp, peaks)
+    if not args.no_fit:
+        fit = run_gpar_fit(ctx, gp, world, rank, local, args.fit_iterations, side_group)
+        if rank == 0:
+            extra["gpar_fit"] = fit
 
     if rank == 0:
         flops = N_FULL * M_FULL * (M_FULL + 1) + 2.0 * N_FULL * M_FULL * M_FULL     # G (symmetric) + H (forward-mode dG/dl)
         syrk = float(np.mean(syrk_ms))
         achieved = flops / (syrk * 1e-3) / 1e12
-        peak = FP64_PEAK_TFLOPS_FALLBACK
+        peak = peaks["dmma_tflops"]
+        traffic, traffic_src = ncu_traffic()
         do_cpu = (not args.no_cpu) and world == 1
         cpu_v, cpu_dt, cores = time_cpu_port(31250, 2, 1) if do_cpu else (None, None, 0)
         line = {
@@ -271,16 +420,19 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "dtc_logpdf_grad N=1000000 M=1024 D=1 Matern52 (BASELINE configs[1])", "theta": THETA.tolist(),
                        "jitter": "sigma^2 (dtc.jl:35)", "l2": "inputs larger than L2: 2 x 8.4 GB operand panels streamed per step",
-                       "parallelism": "independent evaluations per GPU (restarts/outputs); NCCL all-gather of scalars only"},
+                       "parallelism": "independent evaluations per GPU (restarts/outputs); NCCL all-gather of scalars only",
+                       "strong_scaling_metric": "extra.gpar_fit.seconds (BASELINE configs[4], fixed total work over --gpus)"},
             "clocks": sampler.summary(),
             "e2e": {"value": world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(16 * N_FULL), "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_SYRK_DRAM_BYTES,
-                         "kernel": "panel_syrk_kernel (FP64 DMMA.8x8x4)", "traffic_note": "operand panels: 16.8 GB unique; L2 hit 74% with the two-level phase-aligned stream-K (plain stream-K: 181.9 GB)", "kernel_ms": syrk, "algorithmic_flops_per_launch": flops,
-                         "peak_source": "FP64 DMMA peak measured on this pool (profiles/peaks_r01.json; cuBLAS DGEMM 8192^3 = 35.9); MEASURED_PEAKS.json has no FP64 entry",
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "panel_syrk_kernel (FP64 DMMA.8x8x4)",
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed from profiles/%s; operand panels: 16.8 GB unique (phase-aligned stream-K keeps the re-reads in L2)" % traffic_src,
+                         "kernel_ms": syrk, "algorithmic_flops_per_launch": flops,
+                         "peak_source": peaks["source"], "peaks": peaks,
                          "step_breakdown_ms": {"panel_producer": float(np.mean(prod_ms)), "dmma_syrk": syrk, "reduce_and_tail": float(np.mean(tail_ms)),
                                                "device_total": float(np.mean(dev_ms))}},
-            "cpu_baseline": None if not do_cpu else {"value": cpu_v, "unit": "evals/s", "cores": cores, "kind": "port",
+            "cpu_baseline": None if not do_cpu else {"value": cpu_v, "unit": "evals/s", "cores": cores, "blas_threads": blas_threads(), "kind": "port",
                                                        "sample": "N=31250 of 1000000 (1/32), M=1024; %.2f s per sampled eval, linearly extrapolated in N" % cpu_dt},
             "value_check": {"logpdf": val, "grad": list(map(float, grad))},
             "extra": extra,
@@ -299,6 +451,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the Kalman / scaled-GPAR extra metrics")
+    ap.add_argument("--no-fit", action="store_true", help="skip the GPAR chain fit (BASELINE configs[4], ~5 min on one GPU)")
+    ap.add_argument("--fit-iterations", type=int, default=FIT["iterations"], help="Nelder-Mead iteration budget per (output, restart) task")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

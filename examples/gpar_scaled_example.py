@@ -13,8 +13,10 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(1, os.path.dirname(os.path.abspath(__file__)))
 import gpar_at_scale_b200 as gp
-from gpar_at_scale_b200 import api, data
+from gpar_at_scale_b200 import api
+import toy_data as data
 
 
 def main(iterations=150, seed=0, true_samples=100000, quiet=False):

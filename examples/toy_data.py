@@ -1,5 +1,6 @@
 """Synthetic 3-output GPAR data — host-side mirror of src/data/toy_data.jl (the only file under the
-reference's src/data).  O(N) element-wise work: stays on the host, as in the reference; it is the
+reference's src/data).  NOT part of the product package: SURVEY 2.1 #7 keeps the data generators in Julia; this
+copy only feeds the example driver and the tests.  O(N) element-wise work: stays on the host, as in the reference; it is the
 shape source for the benchmark inputs.  The reference draws from Julia's unseeded global RNG
 (toy_data.jl:34-36); here a numpy Generator can be passed for reproducibility."""
 import numpy as np

@@ -8,7 +8,7 @@ directory to that module name).
 """
 from ._ffi import (EQ, MATERN12, MATERN32, MATERN52, GparError, PosDefException, load_library, LIB_PATH)
 from .context import Context, Group
-from . import api, neldermead, parallel, data, chain
+from . import api, neldermead, parallel, chain
 
 __all__ = ["EQ", "MATERN12", "MATERN32", "MATERN52", "GparError", "PosDefException", "load_library",
            "LIB_PATH", "Context", "Group"]

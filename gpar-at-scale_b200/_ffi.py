@@ -25,6 +25,7 @@ SIGNATURES = {
     "gpar_last_error": (ctypes.c_char_p, [_c_void_p]),
     "gpar_last_timing": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
     "gpar_last_profile": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32]),
+    "gpar_measure_peaks": (ctypes.c_int, [_c_void_p, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_set_inputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_pseudo": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_times": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),
@@ -67,6 +68,7 @@ SIGNATURES = {
                                       ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "gpar_group_broadcast": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p]),
     "gpar_set_inputs_column": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p]),
+    "gpar_set_merged_test_column": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p]),
 }
 
 

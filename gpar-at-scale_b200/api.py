@@ -404,7 +404,7 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 inference_input_locations, out_kernel_structure=None, time_kernel_structure=None,
                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                 optimization_time_limit=1000.0, debug=False, ctx=None, rng=None, iterations=1000, nsamples=100,
-                                opt_params=None, sampler="host", seed=0, device_merge=False):
+                                opt_params=None, sampler="device", seed=0, device_merge=True):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
@@ -414,8 +414,10 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     X = to_ColVecs(input_locations); Z = to_ColVecs(pseudo_input_locations); Xs = to_ColVecs(inference_input_locations)
     time_loc = np.asarray(time_loc, dtype=np.float64); inference_time_loc = np.asarray(inference_time_loc, dtype=np.float64)
     outputs = np.asarray(outputs, dtype=np.float64)
-    # sampler="device": the q_u draws come from the library's seeded Philox stream (gpar_sample_q_u) and never
-    # leave the GPU; "host" draws them here from `rng` (the reference uses Julia's global RNG, :94)
+    # sampler="device" (default): the q_u draws come from the library's seeded Philox stream (gpar_sample_q_u, keyed by
+    # `seed`) and never leave the GPU, so the product path has no host numerics; sampler="host" draws them here from
+    # `rng` instead (the reference uses Julia's unseeded global RNG, :94) — kept for callers that bring their own draws.
+    # device_merge (default): the merge / sort / un-sort protocol (:75-87, :100-103, :132-133) runs on the device too.
     if opt_params is None:
         print("Starting optimization")                                                        # :42 (unconditional in the reference)
         opt_params = get_optim_scaled_gpar_params(X, Z, time_loc, outputs, out_kernel=Matern52(), time_kernel=Matern52(),   # :43-56 hard-codes Matern52

@@ -87,13 +87,15 @@ def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kern
         import torch.distributed as dist
         if dist.get_backend() == "nccl":
             device = torch.device("cuda", ctx.device)
-    vals, thetas = parallel.fit_tasks(tasks, costs, run_task, 5, device)
+    timing = {}
+    vals, thetas = parallel.fit_tasks(tasks, costs, run_task, 5, device, timing)
     dt = time.perf_counter() - t0
     best = parallel.best_per_output(tasks, vals, thetas)
     if verbose and rank == 0:
         for o in sorted(best):
             print("output %d: nlml %.6g theta %s (restart %d)" % (o, best[o][0], np.round(best[o][1], 4), best[o][2]))
-    return best, {"seconds": dt, "objective_evals_this_rank": evals[0], "tasks": len(tasks), "world": world}
+    return best, {"seconds": dt, "objective_evals_this_rank": evals[0], "tasks": len(tasks), "world": world,
+                  "busy_seconds": timing.get("busy_seconds", dt), "minimum": vals, "minimizer": thetas}
 
 
 def predict_chain(t, Y, t_star, M, best, nsamples=100, seed=0, ctx=None, time_kernel=None, out_kernel=None):
@@ -117,7 +119,7 @@ def predict_chain(t, Y, t_star, M, best, nsamples=100, seed=0, ctx=None, time_ke
         X = np.ascontiguousarray(Y[:o].T)
         Xs = np.ascontiguousarray(means[:o].T)
         mo, so = api.get_gpar_scaled_predictions(X, strided_pseudo_inputs(X, M), t, Y[o], t_star, Xs, out_kernel_structure=out_kernel,
-                                                 time_kernel_structure=time_kernel, ctx=ctx, rng=np.random.default_rng([seed, o]),
+                                                 time_kernel_structure=time_kernel, ctx=ctx, seed=(int(seed) << 8) + o,
                                                  nsamples=nsamples, opt_params=api.unpack_gpar(best[o][1]))
         means[o] = mo; spreads[o] = so
     return means, spreads

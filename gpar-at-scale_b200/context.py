@@ -67,6 +67,12 @@ class Context:
         self._check(self._lib.gpar_last_profile(self._h, dptr(out), 3))
         return tuple(out.tolist())
 
+    def measure_peaks(self):
+        """-> {"dmma_tflops", "dfma_tflops", "hbm_copy_gbs"} measured on this context's device (roofline denominators)."""
+        a = ctypes.c_double(); b = ctypes.c_double(); c = ctypes.c_double()
+        self._check(self._lib.gpar_measure_peaks(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"dmma_tflops": a.value, "dfma_tflops": b.value, "hbm_copy_gbs": c.value}
+
     # -- resident data ------------------------------------------------------------------------
     def set_inputs(self, X):
         """X: (N, D) records (memory image of the reference's D x N ColVecs, util.jl:16-31)."""
@@ -78,6 +84,11 @@ class Context:
         """Column d of the resident inputs <- col, or (col=None) the chain buffer a Group.broadcast filled."""
         c = None if col is None else as_f64(np.asarray(col).ravel())
         self._check(self._lib.gpar_set_inputs_column(self._h, int(d), dptr(c)))
+
+    def set_merged_test_column(self, d, col=None):
+        """Column d of the merged inputs at the test locations <- col (N* values, test order), or the chain buffer."""
+        c = None if col is None else as_f64(np.asarray(col).ravel())
+        self._check(self._lib.gpar_set_merged_test_column(self._h, int(d), dptr(c)))
 
     def set_pseudo(self, Z):
         Z = as_f64(np.atleast_2d(Z) if np.ndim(Z) > 1 else np.asarray(Z, dtype=np.float64).reshape(-1, 1))

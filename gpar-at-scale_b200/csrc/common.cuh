@@ -206,9 +206,14 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
 int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
                       const double* t, const double* y, const double* rvec, const int dirs[3],
                       double* d_alpha, double* d_lml, double* d_dlml, double* d_sums, double* d_dalpha, double* d_table, double* d_dtable);
-// scaled.cu: e = a - panel w (panel in the operand layout), and rows [4 g_lo, 4 (g_lo + ng)) of a panel as a dense M x 4ng matrix
+// scaled.cu: e = a - panel w (panel in the operand layout)
 int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, const double* a, int64_t N, int64_t NB4, int T, int M, double* e);
-int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* Bt);
+// panel_gemm.cu: out[n, m'] = sum_m C[m', m] in[n, m] on DMMA (C pre-arranged by launch_dense_to_operand / launch_tri_operand)
+int launch_dense_to_operand(gpar_ctx* ctx, const double* Q, int M, int Mpad, double* Aop);
+int panel_gemm_run(gpar_ctx* ctx, const double* Aop, int Mpad, const double* in, int64_t in_groups, double* out, int64_t out_groups,
+                   int64_t g_lo, int64_t ng, int64_t out_g0, int mt_lo, int n_mt, bool triangular);
+int launch_tri_operand(gpar_ctx* ctx, const double* L, int M, int Mpad, double* Yd, double* Aop);
+int panel_tri_solve_run(gpar_ctx* ctx, const double* Aop, int Mpad, double* panel, int64_t groups, int64_t g_lo, int64_t ng);
 // smooth_shared.cu: smoothed means of Sp (multiple of 128) TIME-MAJOR sequences yt[n][Sp] that share one model
 int lgssm_smooth_shared(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, const double* t, const double* y1,
                         const double* rvec, const double* yt, int Sp, double* mean_t);
@@ -216,6 +221,11 @@ int lgssm_smooth_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, do
                                  const double* y, const double* rvec, double* d_mean, double* d_var, double* d_lml);
 int lgssm_filter_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, int batch, const double* t,
                                  const double* y, const double* rvec, double* d_alpha, double* d_lml);
+// merge.cu: result of the last smoother / prediction on a merged problem, gathered at the test locations (device arrays)
+int merged_gather_test(gpar_ctx* ctx, double* dst_a, double* dst_b);
+// Entry points that overwrite the buffers the resident result lives in call this first, so that a later gpar_take_test /
+// gpar_group_broadcast fails loudly instead of reading stale memory.
+static inline void gpar_drop_result(gpar_ctx* c) { c->res_a = nullptr; c->res_b = nullptr; c->res_len = 0; }
 // abi.cu: sufficient statistics of the plain DTC objective over the context's resident data slice (async on its stream)
 int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count);
 // dense_tail.cu

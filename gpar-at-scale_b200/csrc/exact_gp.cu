@@ -114,7 +114,7 @@ int gpar_exact_logpdf(gpar_ctx* ctx, int k_time, int k_out, const double* theta,
   ExactKernel ek; double noise, kss;
   CHK(setup_kernel(ctx, k_time, k_out, theta, ntheta, &ek, &noise, &kss));
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   const int n = (int)ctx->N, batch = ctx->ybatch;
   CU(ctx->dense.reserve(((size_t)n * n + (size_t)n * batch + batch + 8) * sizeof(double)));
@@ -145,7 +145,7 @@ int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* the
   CU(ctx->kal_b.reserve(((size_t)Ns * D + (size_t)n * Ns + (size_t)Ns * batch + Ns) * sizeof(double)));
   double* dXs = ctx->kal_b.as<double>(); double* V = dXs + (size_t)Ns * D; double* dmean = V + (size_t)n * Ns; double* dq = dmean + (size_t)Ns * batch;
   CU(cudaMemcpyAsync(dXs, Xs, (size_t)Ns * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(ctx->dense.reserve(((size_t)n * n + (size_t)n * batch + 8) * sizeof(double)));
   CU(ctx->info.reserve(4 * sizeof(int)));

@@ -209,6 +209,20 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
   GCU(cudaSetDevice(g->dev[0]));
   int rc = dtc_tail_prepare(c0, kernel, p, vfe, jitter, want_grad);      // cov(u), L_u, ... on member 0's side stream
   if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  {
+    // The sharded path sums the COLLAPSED statistic G = Kuf Kfu over the members; with a poorly conditioned cov(u) that
+    // loses cond * eps ("Conditioning") where the one-device entry point whitens the panel by L_u.  Say so
+    // instead of returning a result that depends on how the rows were sharded.
+    TailBufs tb;
+    rc = tail_layout(c0, want_grad, vfe, &tb);
+    if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+    double mm[2] = {1.0, 1.0};
+    GCU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, c0->stream2));
+    GCU(cudaStreamSynchronize(c0->stream2));
+    if (gpar_needs_whitened_panel(mm))
+      return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: cov(u) is too poorly conditioned for the row-sharded statistic "
+                        "((max/min diag L_u)^2 = %.3g > GPAR_ROBUST_COND); evaluate it with gpar_dtc_logpdf on one device", (mm[1] / mm[0]) * (mm[1] / mm[0]));
+  }
   std::vector<double*> stats(n, nullptr);
   std::vector<size_t> count(n, 0);
   std::vector<int> st;
@@ -238,7 +252,13 @@ int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t
   const int nm = (int)g->ctx.size();
   if (src < 0 || src >= nm || n < 1) return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: bad source member %d or length %lld", src, (long long)n);
   gpar_ctx* sc = g->ctx[src];
-  if (!host && (!sc->res_a || sc->res_len < n)) return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: member %d holds no resident result of length >= %lld", src, (long long)n);
+  // a merged train+test problem (gpar_set_merged): the resident result is in SORTED train+test order — what goes down the
+  // chain is its gather at the N* test locations in test order (gpar_take_test's first array), n = N*
+  const bool merged = !host && sc->merged_Ns > 0 && sc->res_a && sc->res_len == sc->merged_N + sc->merged_Ns;
+  if (merged && n != sc->merged_Ns)
+    return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: member %d holds a merged result with %lld test locations, asked for %lld values",
+                      src, (long long)sc->merged_Ns, (long long)n);
+  if (!host && !merged && (!sc->res_a || sc->res_len < n)) return group_fail(g, GPAR_ERR_INVALID, "group_broadcast: member %d holds no resident result of length >= %lld", src, (long long)n);
   for (int i = 0; i < nm; i++) {
     GCU(cudaSetDevice(g->dev[i]));
     GCU(g->ctx[i]->chain.reserve((size_t)n * sizeof(double)));
@@ -246,6 +266,7 @@ int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t
   }
   GCU(cudaSetDevice(g->dev[src]));
   if (host) GCU(cudaMemcpyAsync(sc->chain.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, sc->stream));
+  else if (merged) { const int rc = merged_gather_test(sc, sc->chain.as<double>(), nullptr); if (rc != GPAR_OK) return group_fail(g, rc, "member %d: %s", src, gpar_last_error(sc)); }
   else GCU(cudaMemcpyAsync(sc->chain.p, sc->res_a, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, sc->stream));
   GNC(g->GroupStart());
   for (int i = 0; i < nm; i++) GNC(g->Broadcast(g->ctx[i]->chain.p, g->ctx[i]->chain.p, (size_t)n, ncclDouble, src, g->comm[i], g->ctx[i]->stream));

@@ -1782,7 +1782,7 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   const int batch = ctx->ybatch;
   if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: batch_theta=%d must be 1 or the outputs batch %d", batch_theta, batch);
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
   for (int b = 0; b < batch_theta; b++) { GpParams p = unpack_gp3(theta + 3 * b); hl[b] = p.l; hs[b] = p.s; hn[b] = p.noise; }
   CU(ctx->kal_d.reserve((size_t)batch * sizeof(double)));
@@ -1820,7 +1820,7 @@ int gpar_lgssm_logpdf_grad(gpar_ctx* ctx, int kernel, const double* theta, int32
   const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
   if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf_grad: batch_theta=%d must be 1 or the outputs batch %d", batch_theta, batch);
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   std::vector<GpParams> ps(batch_theta);
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
   for (int b = 0; b < batch_theta; b++) { ps[b] = unpack_gp3(theta + 3 * b); hl[b] = ps[b].l; hs[b] = ps[b].s; hn[b] = ps[b].noise; }
@@ -1852,7 +1852,7 @@ int gpar_lgssm_decorrelate(gpar_ctx* ctx, int kernel, const double theta[3], dou
   CHK(check_seq(ctx, "lgssm_decorrelate"));
   const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   GpParams p = unpack_gp3(theta);
   CU(ctx->kal_d.reserve(((size_t)batch * N + batch) * sizeof(double)));
   double* d_alpha = ctx->kal_d.as<double>(); double* d_lml = d_alpha + (size_t)batch * N;
@@ -1885,7 +1885,7 @@ int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* 
   CHK(check_seq(ctx, "lgssm_smooth"));
   const int batch = ctx->ybatch; const int64_t N = ctx->Nt;
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   GpParams p = unpack_gp3(theta);
   CU(ctx->kal_d.reserve((2 * (size_t)batch * N + batch) * sizeof(double)));
   double* d_mean = ctx->kal_d.as<double>(); double* d_var = d_mean + (size_t)batch * N; double* d_lml = d_var + (size_t)batch * N;

@@ -46,7 +46,22 @@ __global__ void take_test_kernel(const double* __restrict__ a, const double* __r
   if (b) ob[i] = b[j];
 }
 
+// column d of the merged, sorted inputs at the test locations <- vals (test order)
+__global__ void scatter_test_column_kernel(double* __restrict__ X, int D, int d, const int32_t* __restrict__ test_pos,
+                                           const double* __restrict__ vals, int64_t Ns) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Ns) X[(int64_t)test_pos[i] * D + d] = vals[i];
+}
+
 }  // namespace
+
+// The test-ordered gather of the last result of a merged problem into dst (device, Ns doubles), on the context's stream:
+// what gpar_take_test copies to the host and what gpar_group_broadcast sends down the chain.
+int merged_gather_test(gpar_ctx* ctx, double* dst_a, double* dst_b) {
+  const int64_t Ns = ctx->merged_Ns;
+  LAUNCH(ctx, take_test_kernel, (int)((Ns + 255) / 256), 256, 0, ctx->res_a, dst_b ? ctx->res_b : nullptr, ctx->test_pos.as<int32_t>(), Ns, dst_a, dst_b);
+  return GPAR_OK;
+}
 
 extern "C" {
 
@@ -106,9 +121,33 @@ int gpar_take_test(gpar_ctx* ctx, double* a_test, double* b_test) {
   const int64_t Ns = ctx->merged_Ns;
   CU(ctx->scal.reserve((size_t)2 * Ns * sizeof(double)));
   double* oa = ctx->scal.as<double>(); double* ob = oa + Ns;
-  LAUNCH(ctx, take_test_kernel, (int)((Ns + 255) / 256), 256, 0, ctx->res_a, b_test ? ctx->res_b : nullptr, ctx->test_pos.as<int32_t>(), Ns, oa, ob);
+  CHK(merged_gather_test(ctx, oa, b_test ? ob : nullptr));
   CU(cudaMemcpyAsync(a_test, oa, (size_t)Ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (b_test) CU(cudaMemcpyAsync(b_test, ob, (size_t)Ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+
+// Column d of the merged inputs at the Ns test locations <- col (host, test order) or, with col == NULL, the context's
+// chain buffer (gpar_group_broadcast): the predicted means of an earlier output become the test-time input feature of a
+// later output (GPAR_scaled_examples.jl:172 `[test_y1, y2_out]`) without a host round trip.
+int gpar_set_merged_test_column(gpar_ctx* ctx, int32_t d, const double* col) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (ctx->merged_Ns < 1 || ctx->N != ctx->merged_N + ctx->merged_Ns)
+    return gpar_fail(ctx, GPAR_ERR_INVALID, "set_merged_test_column: no merged problem with inputs is resident (gpar_set_merged with D > 0)");
+  if (d < 0 || d >= ctx->D) return gpar_fail(ctx, GPAR_ERR_INVALID, "set_merged_test_column: column %d outside the resident inputs (D = %d)", d, ctx->D);
+  CU(cudaSetDevice(ctx->device));
+  const int64_t Ns = ctx->merged_Ns;
+  if (col) {
+    CU(ctx->chain.reserve((size_t)Ns * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->chain.p, col, (size_t)Ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->chain_n = Ns;
+  } else if (ctx->chain_n != Ns) {
+    return gpar_fail(ctx, GPAR_ERR_INVALID, "set_merged_test_column: chain buffer holds %lld values, the merged problem has %lld test locations",
+                     (long long)ctx->chain_n, (long long)Ns);
+  }
+  LAUNCH(ctx, scatter_test_column_kernel, (int)((Ns + 255) / 256), 256, 0, ctx->X.as<double>(), ctx->D, (int)d, ctx->test_pos.as<int32_t>(),
+         ctx->chain.as<double>(), Ns);
   CU(cudaStreamSynchronize(ctx->stream));
   return GPAR_OK;
 }

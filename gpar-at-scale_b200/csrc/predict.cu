@@ -112,7 +112,7 @@ extern "C" int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const d
   double* dmean = smean + (size_t)Sp * N; double* dsd = dmean + N; double* dW = dsd + N;
   if (W) CU(cudaMemcpyAsync(dW, W, (size_t)M * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   else CU(cudaMemcpyAsync(dW, ctx->qW.p, (size_t)M * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CallTimer timer(ctx); ctx->phase_valid = false;
+  CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   if (Sp != S) CU(cudaMemsetAsync(fx, 0, (size_t)2 * Sp * N * sizeof(double), ctx->stream));      // padding sequences: zero data
   const double inv_l2 = 1.0 / (out_l * out_l);
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>(); const double* y = ctx->y.as<double>();

@@ -399,33 +399,6 @@ residual_kernel(const double* __restrict__ beta, const double* __restrict__ w, c
   }
 }
 
-// Bt (M x ns column-major) = rows [4 g_lo, 4 (g_lo + ng)) of the panel, transposed: feeds the library GEMM S' = P Bt
-__global__ void __launch_bounds__(256)
-panel_slab_to_dense_t_kernel(const double* __restrict__ panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* __restrict__ Bt) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)T * ng * GPAR_TILE) return;
-  const int mi = (int)(idx % GPAR_TILE); const int64_t r = idx / GPAR_TILE; const int64_t gl = r % ng; const int mt = (int)(r / ng);
-  const int m = mt * GPAR_TILE + mi;
-  if (m >= M) return;
-  const double* src = panel + (((int64_t)mt * NB4 + g_lo + gl) * GPAR_TILE + mi) * 4;
-  const double2 b01 = reinterpret_cast<const double2*>(src)[0], b23 = reinterpret_cast<const double2*>(src)[1];
-  double* dst = Bt + (gl * 4) * (int64_t)M + m;
-  dst[0] = b01.x; dst[M] = b01.y; dst[2 * (int64_t)M] = b23.x; dst[3 * (int64_t)M] = b23.y;
-}
-
-// inverse of the above: rows [4 g_lo, 4 (g_lo + ng)) of the panel <- the dense M x 4ng matrix Bt
-__global__ void __launch_bounds__(256)
-dense_t_to_panel_slab_kernel(const double* __restrict__ Bt, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* __restrict__ panel) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)T * ng * GPAR_TILE) return;
-  const int mi = (int)(idx % GPAR_TILE); const int64_t r = idx / GPAR_TILE; const int64_t gl = r % ng; const int mt = (int)(r / ng);
-  const int m = mt * GPAR_TILE + mi;
-  if (m >= M) return;
-  const double* src = Bt + (gl * 4) * (int64_t)M + m;
-  double* dst = panel + (((int64_t)mt * NB4 + g_lo + gl) * GPAR_TILE + mi) * 4;
-  reinterpret_cast<double2*>(dst)[0] = make_double2(src[0], src[M]);
-  reinterpret_cast<double2*>(dst)[1] = make_double2(src[2 * (int64_t)M], src[3 * (int64_t)M]);
-}
 // out[0] = min, out[1] = max of diag(L): (max / min)^2 is a lower bound of cond(L L')
 __global__ void diag_minmax_kernel(const double* __restrict__ L, int M, double* __restrict__ out) {
   __shared__ double smin[32], smax[32];
@@ -450,8 +423,8 @@ template <int D, int CT, bool FINAL>
 __global__ void __launch_bounds__(GPAR_TILE, CT == 1 ? 3 : 2)
 whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, const double* __restrict__ dtable,
                       const double* __restrict__ beta, const double* __restrict__ panelD, const double* __restrict__ start,
-                      double* __restrict__ tstate, int nch, int chunk0, const double* __restrict__ St, const double* __restrict__ evec,
-                      const double* __restrict__ wvec, double* __restrict__ accpart, int Mpad, int M, int whg) {
+                      double* __restrict__ tstate, int nch, int chunk0, const double* __restrict__ St, int64_t s_groups,
+                      const double* __restrict__ evec, const double* __restrict__ wvec, double* __restrict__ accpart, int Mpad, int M, int whg) {
   constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
   const int mt0 = blockIdx.x * CT, mi = threadIdx.x;
   const int chunk = chunk0 + blockIdx.y;
@@ -467,7 +440,7 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
     mvalid[c] = m < M;
     inb[c] = beta + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
     ind[c] = panelD + (((int64_t)(mt0 + c) * NB4 + g0) * GPAR_TILE + mi) * 4;
-    inS[c] = FINAL ? St + ((int64_t)blockIdx.y * whg * 4) * M + m : nullptr;
+    inS[c] = FINAL ? St + (((int64_t)(mt0 + c) * s_groups + (int64_t)blockIdx.y * whg) * GPAR_TILE + mi) * 4 : nullptr;   // slab panel of S = beta P
     wm[c] = (FINAL && mvalid[c]) ? wvec[m] : 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -488,10 +461,12 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
       o.kv[c][0] = a01.x; o.kv[c][1] = a01.y; o.kv[c][2] = a23.x; o.kv[c][3] = a23.y;
       const double2 d01 = reinterpret_cast<const double2*>(ind[c] + off)[0], d23 = reinterpret_cast<const double2*>(ind[c] + off)[1];
       o.dv[c][0] = d01.x; o.dv[c][1] = d01.y; o.dv[c][2] = d23.x; o.dv[c][3] = d23.y;
+      if (FINAL) {
+        const double2 s01 = reinterpret_cast<const double2*>(inS[c] + off)[0], s23 = reinterpret_cast<const double2*>(inS[c] + off)[1];
+        o.sv[c][0] = s01.x; o.sv[c][1] = s01.y; o.sv[c][2] = s23.x; o.sv[c][3] = s23.y;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int64_t n = g * 4 + j;
-        o.sv[c][j] = (FINAL && mvalid[c] && n < N) ? __ldg(inS[c] + (n - g0 * 4) * M) : 0.0;
+        for (int j = 0; j < 4; j++) o.sv[c][j] = 0.0;
       }
     }
 #pragma unroll
@@ -745,11 +720,12 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   if (const char* e = getenv("GPAR_TANGENT_CT")) { if (atoi(e) == 1) CT = 1; }
   dim3 grid(T / CT, nch);
   if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                      tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
+                      tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-              tstate, nch, 0, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
+              tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad);
-  // S' = P beta' slab by slab (library GEMM on the transposed slab), consumed at once by the final tangent pass
+  // S = beta P slab by slab on the DMMA panel-GEMM (panel_gemm.cu): P goes once into the operand layout, every slab of S
+  // comes out in the panel layout and is consumed at once by the final tangent pass, so only one slab buffer exists
   const int base_chunks = std::max(1, 131072 / (st.whg * 4));
   int slab_chunks = base_chunks;                                                 // ~131072 steps per slab ...
   {                                                                              // ... rounded to whole waves of the final tangent pass
@@ -759,23 +735,20 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   }
   if (const char* e = getenv("GPAR_GRAD_SLAB")) { int v = atoi(e); if (v >= 1) slab_chunks = v; }
   slab_chunks = std::min(slab_chunks, nch);
-  const size_t slab_steps = (size_t)slab_chunks * st.whg * 4;
-  CU(ctx->panelB.reserve(slab_steps * M * sizeof(double)));
-  CU(ctx->kal_f.reserve(slab_steps * M * sizeof(double)));
-  double* Bt = ctx->panelB.as<double>(); double* St = ctx->kal_f.as<double>();
-  cublasSetStream(ctx->blas, ctx->stream);
-  const double one = 1.0, zero = 0.0;
+  const int64_t slab_groups = (int64_t)slab_chunks * st.whg;
+  CU(ctx->panelB.reserve((size_t)Mpad * Mpad * sizeof(double)));
+  CU(ctx->kal_f.reserve((size_t)slab_groups * 4 * Mpad * sizeof(double)));
+  double* Pop = ctx->panelB.as<double>(); double* Ss = ctx->kal_f.as<double>();
+  CHK(launch_dense_to_operand(ctx, Pm, M, Mpad, Pop));
   for (int c0 = 0; c0 < nch; c0 += slab_chunks) {
     const int nc = std::min(slab_chunks, nch - c0);
     const int64_t g_lo = (int64_t)c0 * st.whg, ng = std::min<int64_t>((int64_t)nc * st.whg, NB4 - g_lo);
-    const int64_t total = (int64_t)T * ng * GPAR_TILE;
-    LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, st.beta, NB4, g_lo, ng, T, M, Bt);
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, (int)(ng * 4), M, &one, Pm, M, Bt, M, &zero, St, M));
+    CHK(panel_gemm_run(ctx, Pop, Mpad, st.beta, NB4, Ss, slab_groups, g_lo, ng, g_lo, 0, T, false));
     dim3 gs(T / CT, nc);
     if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                        tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M, st.whg);
+                        tstate, nch, c0, Ss, slab_groups, st.evec, wvec, accpart, Mpad, M, st.whg);
     else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
-                tstate, nch, c0, St, st.evec, wvec, accpart, Mpad, M, st.whg);
+                tstate, nch, c0, Ss, slab_groups, st.evec, wvec, accpart, Mpad, M, st.whg);
   }
   CU(ctx->scal.reserve(8 * sizeof(double)));
   LAUNCH(ctx, grad_sums_kernel, 5, 1024, 0, accpart, nch, Mpad, st.evec, st.dalpha, N, ctx->scal.as<double>());
@@ -854,22 +827,14 @@ int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2) {
   LAUNCH(ctx, diag_minmax_kernel, 1, 256, 0, L, M, out2);
   return GPAR_OK;
 }
-// panel (operand layout, N x M) <- panel L_u^-T  i.e. every row beta_n' becomes (L_u^-1 beta_n)'
+// panel (operand layout, N x M) <- panel L_u^-T  i.e. every row beta_n' becomes (L_u^-1 beta_n)': the blocked triangular
+// solve of panel_gemm.cu (inverted 128 x 128 diagonal blocks, DMMA products over the tile rows above), in place
 int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu) {
   const int T = Mpad / GPAR_TILE; const int64_t NB4 = Npad / 4;
-  const int64_t slab_groups = std::min<int64_t>(NB4, 32768);                       // 131072 steps per slab
-  CU(ctx->panelB.reserve((size_t)slab_groups * 4 * M * sizeof(double)));
-  double* Bt = ctx->panelB.as<double>();
-  cublasSetStream(ctx->blas, ctx->stream);
-  const double one = 1.0;
-  for (int64_t g_lo = 0; g_lo < NB4; g_lo += slab_groups) {
-    const int64_t ng = std::min<int64_t>(slab_groups, NB4 - g_lo);
-    const int64_t total = (int64_t)T * ng * GPAR_TILE;
-    LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, panel, NB4, g_lo, ng, T, M, Bt);
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, (int)(ng * 4), &one, Lu, M, Bt, M));
-    LAUNCH(ctx, dense_t_to_panel_slab_kernel, (int)((total + 255) / 256), 256, 0, Bt, NB4, g_lo, ng, T, M, panel);
-  }
-  return GPAR_OK;
+  CU(ctx->panelB.reserve(((size_t)Mpad * Mpad + (size_t)T * GPAR_TILE * GPAR_TILE) * sizeof(double)));
+  double* Aop = ctx->panelB.as<double>(); double* Yd = Aop + (size_t)Mpad * Mpad;
+  CHK(launch_tri_operand(ctx, Lu, M, Mpad, Yd, Aop));
+  return panel_tri_solve_run(ctx, Aop, Mpad, panel, NB4, 0, NB4);
 }
 
 // helpers shared with zgrad.cu
@@ -877,12 +842,6 @@ int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, c
   LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, panel, w, a, N, NB4, T, M, e);
   return GPAR_OK;
 }
-int launch_panel_slab_to_dense_t(gpar_ctx* ctx, const double* panel, int64_t NB4, int64_t g_lo, int64_t ng, int T, int M, double* Bt) {
-  const int64_t total = (int64_t)T * ng * GPAR_TILE;
-  LAUNCH(ctx, panel_slab_to_dense_t_kernel, (int)((total + 255) / 256), 256, 0, panel, NB4, g_lo, ng, T, M, Bt);
-  return GPAR_OK;
-}
-
 static const double LOG2PI_S = 1.8378770664093454835606594728112;
 
 // cov(u) = Kuu + jitter I and its Cholesky factor on the SIDE stream (underneath the filter / whitening), plus
@@ -926,7 +885,7 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   if (!theta || !dtc) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc: theta and dtc must not be NULL");
   CHK(check_scaled(ctx, "scaled_dtc"));
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx);
+  CallTimer timer(ctx); gpar_drop_result(ctx);
   // unpack_gpar (util.jl:45-55); variances squared, noise squared (dtc.jl:31-37)
   double pv[5];
   for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;
@@ -994,7 +953,7 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   if (!theta || !dtc || !grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_grad: theta, dtc and grad must not be NULL");
   CHK(check_scaled(ctx, "scaled_dtc_grad"));
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx);
+  CallTimer timer(ctx); gpar_drop_result(ctx);
   double pv[5], ex[5];
   for (int i = 0; i < 5; i++) { ex[i] = exp(theta[i]); pv[i] = ex[i] + 1e-3; }
   const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
@@ -1095,7 +1054,7 @@ int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5
   if (!params || !m_e || !Dinv || !U_u) return gpar_fail(ctx, GPAR_ERR_INVALID, "compute_q_u: NULL argument");
   CHK(check_scaled(ctx, "compute_q_u"));
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx);
+  CallTimer timer(ctx); gpar_drop_result(ctx);
   QuFactors q;
   CHK(q_u_factors(ctx, k_time, k_out, params, &q));
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
@@ -1124,7 +1083,7 @@ int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5]
   if (!params || S < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "sample_q_u: params must not be NULL and S >= 1");
   CHK(check_scaled(ctx, "sample_q_u"));
   CU(cudaSetDevice(ctx->device));
-  CallTimer timer(ctx);
+  CallTimer timer(ctx); gpar_drop_result(ctx);
   QuFactors q;
   CHK(q_u_factors(ctx, k_time, k_out, params, &q));
   const int M = (int)ctx->M; const int64_t total = (int64_t)M * S;

@@ -7,8 +7,8 @@
 //                                               q = (y - Kfu w/sigma^2)/sigma^4
 //   dF/dcov(u)    = -1/2 (T - cov(u)^-1)  (- 1/2 cov(u)^-1 G cov(u)^-1/sigma^2 for VFE)
 //   dk(x, z)/dz   = s f'(d2) 2 (z - x)/l^2,  d2 = |x - z|^2/l^2
-// S = A Kuf is one M x M x N GEMM — a plain library GEMM (cuBLAS) on slabs of the transposed K panel, as
-// in the scaled gradient; the contraction with dk/dz is a kernel of this file (one thread per pseudo-input).
+// S = A Kuf is one M x M x N contraction — the DMMA panel-GEMM of panel_gemm.cu on slabs of the K panel, as in the
+// scaled gradient; the contraction with dk/dz is a kernel of this file (one thread per pseudo-input).
 #include "common.cuh"
 #include <algorithm>
 
@@ -37,7 +37,7 @@ __global__ void zgrad_matrices_kernel(int M, const double* __restrict__ P, const
 // partial[(split * D + d) * Mpad + m] = sum over the split's steps of (S'[m, n] + w_m q_n) s f'(d2) 2 (z_md - x_nd)/l^2
 template <int KIND, int D>
 __global__ void __launch_bounds__(GPAR_TILE)
-zgrad_cross_kernel(const double* __restrict__ X, const double* __restrict__ Z, const double* __restrict__ St, const double* __restrict__ q,
+zgrad_cross_kernel(const double* __restrict__ X, const double* __restrict__ Z, const double* __restrict__ St, int64_t s_groups, const double* __restrict__ q,
                    const double* __restrict__ w, int64_t n_lo, int64_t n_hi, int64_t per_split, int M, int Mpad, double inv_l2, double s,
                    double* __restrict__ partial) {
   const int m = blockIdx.x * GPAR_TILE + threadIdx.x;
@@ -47,11 +47,12 @@ zgrad_cross_kernel(const double* __restrict__ X, const double* __restrict__ Z, c
   for (int d = 0; d < D; d++) { z[d] = mvalid ? Z[(int64_t)m * D + d] : 0.0; acc[d] = 0.0; }
   const double wm = mvalid ? w[m] : 0.0;
   const int64_t a = n_lo + (int64_t)blockIdx.y * per_split, b = a + per_split < n_hi ? a + per_split : n_hi;
+  const double* Sp = St + ((int64_t)blockIdx.x * s_groups * GPAR_TILE + threadIdx.x) * 4;      // slab panel of S: [mt][group][m%128][n%4]
   for (int64_t n = a; n < b; n++) {
     double df[D], d2 = 0.0;
 #pragma unroll
     for (int d = 0; d < D; d++) { df[d] = z[d] - __ldg(X + n * D + d); d2 = fma(df[d], df[d], d2); }
-    const double r = mvalid ? fma(wm, __ldg(q + n), __ldg(St + (n - n_lo) * M + m)) : 0.0;
+    const double r = mvalid ? fma(wm, __ldg(q + n), __ldg(Sp + ((n - n_lo) >> 2) * (GPAR_TILE * 4) + ((n - n_lo) & 3))) : 0.0;
     const double c = r * s * base_kernel_dd2<KIND>(d2 * inv_l2) * 2.0 * inv_l2;
 #pragma unroll
     for (int d = 0; d < D; d++) acc[d] = fma(c, df[d], acc[d]);
@@ -102,27 +103,27 @@ int zgrad_run(gpar_ctx* ctx, const GpParams& p, int vfe, double* grad_Z) {
   CHK(launch_panel_residual(ctx, ctx->panelK.as<double>(), ws, ctx->y.as<double>(), N, NB4, T, M, q));
   const double ip2 = ip * ip;
   CB(cublasDscal(ctx->blas, (int)N, &ip2, q, 1));
-  // slabs: K' (M x ns) -> S' = A K' (library GEMM) -> contraction with dk/dz
+  // slabs of the K panel -> S = K A (DMMA panel-GEMM, A symmetric) -> contraction with dk/dz
   const int64_t slab_steps = std::min<int64_t>(Npad, 131072);
   const int nslab = (int)((Npad + slab_steps - 1) / slab_steps);
   int nsplit = std::max(1, (ctx->num_sms * 8) / T);
   nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, slab_steps / 64));
-  CU(ctx->panelB.reserve((size_t)slab_steps * M * sizeof(double)));
-  CU(ctx->kal_f.reserve((size_t)slab_steps * M * sizeof(double)));
+  CU(ctx->panelB.reserve((size_t)Mpad * Mpad * sizeof(double)));
+  CU(ctx->kal_f.reserve((size_t)slab_steps * Mpad * sizeof(double)));
   CU(ctx->gpart.reserve((size_t)nslab * nsplit * D * Mpad * sizeof(double)));
-  double* Kt = ctx->panelB.as<double>(); double* St = ctx->kal_f.as<double>(); double* partial = ctx->gpart.as<double>();
-  const double one = 1.0, zero = 0.0, inv_l2 = 1.0 / (p.l * p.l);
+  double* Aop = ctx->panelB.as<double>(); double* St = ctx->kal_f.as<double>(); double* partial = ctx->gpart.as<double>();
+  const double inv_l2 = 1.0 / (p.l * p.l);
+  CHK(launch_dense_to_operand(ctx, A, M, Mpad, Aop));
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
   for (int sl = 0; sl < nslab; sl++) {
     const int64_t n_lo = (int64_t)sl * slab_steps, g_lo = n_lo / 4, ng = std::min<int64_t>(slab_steps / 4, NB4 - g_lo);
     const int64_t n_hi = std::min<int64_t>(N, n_lo + ng * 4);
     if (n_hi <= n_lo) { CU(cudaMemsetAsync(partial + (size_t)sl * nsplit * D * Mpad, 0, (size_t)nsplit * D * Mpad * sizeof(double), ctx->stream)); continue; }
-    CHK(launch_panel_slab_to_dense_t(ctx, ctx->panelK.as<double>(), NB4, g_lo, ng, T, M, Kt));
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, (int)(ng * 4), M, &one, A, M, Kt, M, &zero, St, M));
+    CHK(panel_gemm_run(ctx, Aop, Mpad, ctx->panelK.as<double>(), NB4, St, slab_steps / 4, g_lo, ng, g_lo, 0, T, false));
     const int64_t per = (n_hi - n_lo + nsplit - 1) / nsplit;
     dim3 grid(T, nsplit);
     double* part = partial + (size_t)sl * nsplit * D * Mpad;
-#define ZCASE(DD) case DD: LAUNCH(ctx, (zgrad_cross_kernel<KIND, DD>), grid, GPAR_TILE, 0, X, Z, St, q, tb.wvec, n_lo, n_hi, per, M, Mpad, inv_l2, p.s, part); break;
+#define ZCASE(DD) case DD: LAUNCH(ctx, (zgrad_cross_kernel<KIND, DD>), grid, GPAR_TILE, 0, X, Z, St, slab_steps / 4, q, tb.wvec, n_lo, n_hi, per, M, Mpad, inv_l2, p.s, part); break;
     switch (D) {
       ZCASE(1) ZCASE(2) ZCASE(3) ZCASE(4) ZCASE(5) ZCASE(6) ZCASE(7) ZCASE(8)
       default: return gpar_fail(ctx, GPAR_ERR_INVALID, "input dimension D=%d not supported (1..8)", D);
@@ -147,7 +148,7 @@ extern "C" int gpar_dtc_logpdf_zgrad(gpar_ctx* ctx, int kernel, const double the
   const double t_prev = ctx->last_ms; const int64_t l_prev = ctx->last_launches;
   int rc;
   {
-    CallTimer timer(ctx);
+    CallTimer timer(ctx); gpar_drop_result(ctx);
     switch (kernel) {
       case GPAR_EQ: rc = zgrad_run<GPAR_EQ>(ctx, p, vfe, grad_Z); break;
       case GPAR_MATERN12: rc = zgrad_run<GPAR_MATERN12>(ctx, p, vfe, grad_Z); break;

@@ -82,14 +82,20 @@ def broadcast_means(means, src, device=None):
     return t.cpu().numpy()
 
 
-def fit_tasks(tasks, costs, run_task, nparam, device=None):
+def fit_tasks(tasks, costs, run_task, nparam, device=None, timing=None):
     """Runs `run_task(task) -> (minimum, minimizer)` for this rank's share of `tasks` and gathers
-    everything.  -> (minimum[len(tasks)], minimizer[len(tasks), nparam])."""
+    everything.  -> (minimum[len(tasks)], minimizer[len(tasks), nparam]).  timing (dict, optional) receives
+    "busy_seconds": this rank's own fitting time, before it waits for the others in the gather."""
+    import time
     rank, world = dist_info()
     mine = shard_tasks(costs, world, rank)
     local = {}
+    t0 = time.perf_counter()
     for ti in mine:
         local[ti] = run_task(tasks[ti])
+    if timing is not None:
+        timing["busy_seconds"] = time.perf_counter() - t0
+        timing["tasks_this_rank"] = len(mine)
     return gather_results(local, len(tasks), nparam, device)
 
 

@@ -57,6 +57,11 @@ int gpar_last_timing(const gpar_ctx* ctx, double* device_ms, int64_t* kernel_lau
  * panel-SYRK kernel alone, [2] = everything after it (partial-tile reduction, M x M tail). n >= 3. */
 int gpar_last_profile(const gpar_ctx* ctx, double* phase_ms, int32_t n);
 
+/* Roofline denominators measured on this context's device (bench.py, SURVEY 8d "measure the FP64 DMMA peak on the box"):
+ * issue peaks of mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) and of DFMA from register-only loops, and the HBM copy bandwidth
+ * (1 GiB each way, read + write bytes).  Any pointer may be NULL.  ~60 ms. */
+int gpar_measure_peaks(gpar_ctx* ctx, double* dmma_tflops, double* dfma_tflops, double* hbm_copy_gbs);
+
 /* ---- resident data (host -> device copies) ------------------------------------------------ */
 /* ColVecs inputs, src/gp/dtc.jl:26-27, gpar_scaled_inference.jl:38-40 (to_ColVecs, util.jl:16-31) */
 int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N);
@@ -213,13 +218,20 @@ enum gpar_optimizer { GPAR_OPT_NELDER_MEAD = 0, GPAR_OPT_LBFGS = 1 };   /* L-BFG
 int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
                    int32_t optimizer, int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
 
-/* n doubles from member src — `host` if given, else the resident result of its last gpar_lgssm_smooth /
- * gpar_scaled_predict (the posterior means) — into EVERY member's chain buffer (ncclBroadcast over NVLink);
- * out (nullable) receives a host copy read from a receiving member. */
+/* n doubles from member src into EVERY member's chain buffer (ncclBroadcast over NVLink): `host` if given, else the
+ * resident result of its last gpar_lgssm_smooth / gpar_scaled_predict — for a merged train+test problem
+ * (gpar_set_merged) the posterior means AT THE N* TEST LOCATIONS IN TEST ORDER (what gpar_take_test returns first;
+ * n must be N*), otherwise the first n values of the result.  out (nullable) receives a host copy read from a
+ * receiving member. */
 int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t n, double* out);
 /* Column d of the resident inputs X <- col (host, N values) or, with col == NULL, the context's chain buffer: the
  * predicted means of an earlier output become an input feature of the later outputs without a host round trip. */
 int gpar_set_inputs_column(gpar_ctx* ctx, int32_t d, const double* col);
+/* The same for a MERGED problem (gpar_set_merged with D > 0): column d of the inputs at the N* test locations <- col
+ * (host, N* values in test order) or the chain buffer — the chain step `[test_y1, y2_out]` of
+ * GPAR_scaled_examples.jl:172 device to device: gpar_group_broadcast(g, owner, NULL, N*, NULL) after the earlier
+ * output's prediction, then gpar_set_merged (any placeholder in column d of Xs) + this call on the later output. */
+int gpar_set_merged_test_column(gpar_ctx* ctx, int32_t d, const double* col);
 
 #ifdef __cplusplus
 }

@@ -244,5 +244,15 @@ function group_broadcast(g::Group, src::Integer, n::Integer; values::Union{Nothi
 end
 set_inputs_column!(c::Ctx, d::Integer, col::Union{Nothing, Vector{Float64}} = nothing) =
     check(c, ccall((:gpar_set_inputs_column, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), c.h, d, col === nothing ? C_NULL : col))
+# merged train+test problem (set_merged!): feature d (0-based) of the inputs AT THE TEST LOCATIONS <- col (N* values, test
+# order) or the chain buffer filled by group_broadcast — `[test_y1, y2_out]`, GPAR_scaled_examples.jl:172
+set_merged_test_column!(c::Ctx, d::Integer, col::Union{Nothing, Vector{Float64}} = nothing) =
+    check(c, ccall((:gpar_set_merged_test_column, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), c.h, d, col === nothing ? C_NULL : col))
+# roofline denominators of the context's device: (dmma_tflops, dfma_tflops, hbm_copy_gbs)
+function measure_peaks(c::Ctx)
+    a = Ref{Float64}(0); b = Ref{Float64}(0); h = Ref{Float64}(0)
+    check(c, ccall((:gpar_measure_peaks, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ref{Float64}), c.h, a, b, h))
+    return (dmma_tflops = a[], dfma_tflops = b[], hbm_copy_gbs = h[])
+end
 
 end # module

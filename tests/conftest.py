@@ -5,6 +5,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+EXAMPLES = os.path.join(ROOT, "examples")        # toy_data.py (mirror of src/data/toy_data.jl) lives with the example drivers
+if EXAMPLES not in sys.path:
+    sys.path.insert(1, EXAMPLES)
 
 
 def pytest_configure(config):

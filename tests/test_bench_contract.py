@@ -34,3 +34,12 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     p = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still time the CPU path on all host cores
+    (round-1 SCALE ratios at N >= 2 were inflated by a single-threaded reference arm)."""
+    p = run({"OMP_NUM_THREADS": "1"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["blas_threads"] == (os.cpu_count() or 1)

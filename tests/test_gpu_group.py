@@ -84,6 +84,54 @@ def test_group_chain_broadcast_and_input_column(ctx):
         g.close()
 
 
+def test_group_chain_merged_means_reach_the_next_output(ctx):
+    """The prediction chain `[test_y1, y2_out]` (GPAR_scaled_examples.jl:172) device to device.  After a smoother /
+    prediction on a MERGED train+test problem the resident result is in sorted train+test order; what
+    gpar_group_broadcast sends down the chain is the N* test means in TEST order (gpar_take_test's first array), and
+    gpar_set_merged_test_column writes them into the later output's merged inputs at the test locations."""
+    import gpar_at_scale_b200 as gp
+    t, X, Z, y = problem(9)
+    rng = np.random.default_rng(90)
+    ns = 1700
+    ts = np.sort(rng.uniform(t[0] - 1.0, t[-1] + 2.0, ns)); ts[::9] = t[rng.integers(0, len(t), len(ts[::9]))]; ts = np.sort(ts)
+    Xs = rng.normal(size=(ns, X.shape[1]))
+    th = np.log([1.5, 1.0, 0.2]); sig2 = (np.exp(th[2]) + 1e-3) ** 2
+    params = np.array([1.3, 0.9, 1.1, 0.8, 0.3]); W = rng.normal(size=(Z.shape[0], 8))
+    g = gp.Group([0])
+    try:
+        m = g.members[0]
+        m.set_merged(t, y, ts, sig2)                                  # earlier output: time-only smoother on the merged grid
+        m.lgssm_smooth(gp.MATERN52, th, keep_on_device=True)
+        means, _ = m.take_test()
+        back = g.broadcast(0, n=ns)
+        assert np.array_equal(back, means)                            # test order, not the first N* sorted entries
+        with pytest.raises(gp.GparError):
+            g.broadcast(0, n=len(t) + ns)                             # a merged result is N* values, nothing else
+        Xs0 = Xs.copy(); Xs0[:, 1] = 0.0                              # later output: column 1 of the test inputs comes from the chain
+        m.set_pseudo(Z); m.set_merged(t, y, ts, params[4] ** 2, X=X, Xs=Xs0)
+        m.set_merged_test_column(1)
+        m.scaled_predict(gp.MATERN52, gp.MATERN52, params, W, keep_on_device=True)
+        a1, b1 = m.take_test()
+        Xs1 = Xs.copy(); Xs1[:, 1] = means                            # host path of chain.predict_chain
+        ctx.set_pseudo(Z); ctx.set_merged(t, y, ts, params[4] ** 2, X=X, Xs=Xs1)
+        ctx.scaled_predict(gp.MATERN52, gp.MATERN52, params, W, keep_on_device=True)
+        a2, b2 = ctx.take_test()
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+        ctx.set_merged_test_column(1, means + 1.0)                    # host values through the same entry point
+        with pytest.raises(gp.GparError):
+            ctx.set_merged_test_column(7)
+        # a later compute call reuses the result buffers: take_test / broadcast must fail loudly, not read stale memory
+        m.set_merged(t, y, ts, sig2); m.lgssm_smooth(gp.MATERN52, th, keep_on_device=True); m.take_test()
+        m.lgssm_logpdf(gp.MATERN52, th)
+        with pytest.raises(gp.GparError):
+            m.take_test()
+        with pytest.raises(gp.GparError):
+            g.broadcast(0, n=ns)
+    finally:
+        ctx.set_noise_vector(None)
+        g.close()
+
+
 def test_group_sharded_dtc_single_member_is_the_plain_entry_point(ctx):
     """gpar_group_dtc_logpdf_sharded with one member: same kernels, an all-reduce over one rank -> identical numbers,
     value and gradient, DTC and VFE."""
@@ -276,6 +324,21 @@ def test_group_of_two_devices():
         X2 = probs[0][1].copy(); X2[:, 1] = mean[0][:n0]
         load(g1.members[0], probs[0][0], X2, probs[0][2], probs[0][3])
         assert g.members[0].scaled_dtc(gp.MATERN52, gp.MATERN52, th5[0]) == g1.members[0].scaled_dtc(gp.MATERN52, gp.MATERN52, th5[0])
+        # merged chain: member 1 smooths a merged train+test problem, the N* test means (test order) reach member 0
+        tA, XA, ZA, yA = probs[0]
+        rs = np.random.default_rng(5); ns = 900
+        ts = np.sort(rs.uniform(tA[0], tA[-1], ns)); XsA = rs.normal(size=(ns, XA.shape[1]))
+        g.members[1].set_merged(tA, yA, ts, 0.04)
+        g.members[1].lgssm_smooth(gp.MATERN52, np.array([0.0, 0.0, -1.0]), keep_on_device=True)
+        mt, _ = g.members[1].take_test()
+        assert np.array_equal(g.broadcast(1, n=ns), mt)
+        par = np.array([1.3, 0.9, 1.1, 0.8, 0.3]); Wm = rs.normal(size=(ZA.shape[0], 4))
+        g.members[0].set_pseudo(ZA); g.members[0].set_merged(tA, yA, ts, par[4] ** 2, X=XA, Xs=XsA); g.members[0].set_merged_test_column(0)
+        g.members[0].scaled_predict(gp.MATERN52, gp.MATERN52, par, Wm, keep_on_device=True)
+        XsB = XsA.copy(); XsB[:, 0] = mt
+        g1.members[0].set_pseudo(ZA); g1.members[0].set_merged(tA, yA, ts, par[4] ** 2, X=XA, Xs=XsB)
+        g1.members[0].scaled_predict(gp.MATERN52, gp.MATERN52, par, Wm, keep_on_device=True)
+        assert np.array_equal(g.members[0].take_test()[0], g1.members[0].take_test()[0])
         # fits: dynamic hand-out over two members, same results as one member
         t, tasks = chain_tasks(12)
         a = g.fit(t, tasks, gp.MATERN52, gp.MATERN52, iterations=6)

@@ -511,7 +511,8 @@ def test_ill_conditioned_cov_u_gradient_falls_back_to_the_value_path(ctx):
     whitened-panel VALUE path (4-point stencil): against torch autograd of the oracle 1e-5 relative at cond 1e9 and 1e-3 at
     1e10, where the analytic form is off by up to O(1); value keeps 1e-8.  GPAR_GRAD_FD=0 shows what the analytic form alone would give."""
     import gpar_at_scale_b200 as gp
-    from gpar_at_scale_b200 import data, chain
+    from gpar_at_scale_b200 import chain
+    import toy_data as data
     from oracle.grad import scaled_dtc_value_and_grad
     rng = np.random.default_rng(5)
     x, y_obs, _, _ = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
@@ -556,7 +557,8 @@ def test_ill_conditioned_cov_u_keeps_parity(ctx):
     """cov(u) with cond ~ 1e7 ... 1e10 (large output variance, small jitter): the collapsed statistic beta'beta would lose
     cond(cov(u)) eps (6e-8 ... 4e-3 here); the library then whitens the panel by L_u before the SYRK (A = L_u^-1 beta' as the
     reference forms it, dtc.jl:119-120) and keeps the 1e-8 bar — scaled objective, plain DTC / VFE values, q(u)."""
-    from gpar_at_scale_b200 import data, chain
+    from gpar_at_scale_b200 import chain
+    import toy_data as data
     rng = np.random.default_rng(5)
     x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
     Y = np.stack(y_obs); o = 2
@@ -730,7 +732,8 @@ def test_reference_example_chain_end_to_end(ctx):
 
 
 def test_chain_fit_and_predict_small(ctx):
-    from gpar_at_scale_b200 import chain, data
+    from gpar_at_scale_b200 import chain
+    import toy_data as data
     rng = np.random.default_rng(5)
     x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
     Y = np.stack(y_obs)
@@ -746,7 +749,8 @@ def test_chain_fit_lbfgs_beats_nelder_mead_at_equal_budget(ctx):
     """the gradient-based fit (L-BFGS on gpar_lgssm_logpdf_grad / gpar_scaled_dtc_grad)
     against the reference's Nelder-Mead loop from the same starting points: with no more objective
     evaluations than Nelder-Mead spends, every output's nlml is at least as low."""
-    from gpar_at_scale_b200 import chain, data
+    from gpar_at_scale_b200 import chain
+    import toy_data as data
     rng = np.random.default_rng(5)
     x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
     Y = np.stack(y_obs)

@@ -2,7 +2,8 @@
 import numpy as np
 import pytest
 import gpar_at_scale_b200 as gp
-from gpar_at_scale_b200 import api, data, neldermead, chain, parallel
+from gpar_at_scale_b200 import api, neldermead, chain, parallel
+import toy_data as data
 
 
 def test_to_colvecs_layout_matches_reference():

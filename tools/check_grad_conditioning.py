@@ -4,7 +4,9 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import gpar_at_scale_b200 as gp
-from gpar_at_scale_b200 import data, chain
+from gpar_at_scale_b200 import chain
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+import toy_data as data
 from oracle.grad import scaled_dtc_value_and_grad
 rng = np.random.default_rng(5)
 x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
