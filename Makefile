@@ -15,7 +15,7 @@ build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) includ
 
 $(LIBDIR)/libgpar_b200.so: $(OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared -o $@ $(OBJS) -L/usr/local/cuda/lib64 -lcublas -lcusolver -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+	$(NVCC) -shared -o $@ $(OBJS)
 
 oracle: oracle/_build/liboracle_c.so
 oracle/_build/liboracle_c.so: $(wildcard oracle/c/*.c)

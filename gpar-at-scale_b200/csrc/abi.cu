@@ -91,8 +91,7 @@ int gpar_ctx_create(int device, gpar_ctx** out) {
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[0]) != cudaSuccess || cudaEventCreate(&ctx->pev[1]) != cudaSuccess ||
-      cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess ||
-      cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) {
+      cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess) {
     delete ctx;
     return GPAR_ERR_CUDA;
   }
@@ -108,11 +107,9 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->panelB, &ctx->kal_f, &ctx->partial, &ctx->segs,
                     &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
-                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->mrg, &ctx->test_pos, &ctx->shbuf, &ctx->chain};
+                    &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->dla_ws, &ctx->dla_ws_side, &ctx->dla_ws2, &ctx->mrg, &ctx->test_pos, &ctx->shbuf, &ctx->chain};
   for (DevBuf* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  if (ctx->solver) cusolverDnDestroy(ctx->solver);
-  if (ctx->blas) cublasDestroy(ctx->blas);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);

@@ -9,8 +9,6 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
-#include <cublas_v2.h>
-#include <cusolverDn.h>
 #include "../../include/gpar_b200.h"
 
 #define GPAR_TILE 128          // M-tile of the panel layout and of the DMMA kernel
@@ -37,8 +35,6 @@ struct gpar_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;     // side stream: the G-independent part of the M x M tail overlaps the SYRK
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
-  cublasHandle_t blas = nullptr;
-  cusolverDnHandle_t solver = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};   // phase marks: producers done, main kernel start/end
   bool phase_valid = false;
@@ -65,6 +61,7 @@ struct gpar_ctx {
   // and the device arrays of the last smoother / prediction result (for gpar_take_test)
   DevBuf mrg, test_pos; int64_t merged_N = 0, merged_Ns = 0; const double* res_a = nullptr; const double* res_b = nullptr; int64_t res_len = 0;
   DevBuf shbuf;                       // shared-model smoother: tables, chunk states, filtered means (smooth_shared.cu)
+  DevBuf dla_ws, dla_ws_side, dla_ws2;                // scratch of the dense M x M routines (dense_la.cu): main / side stream, transposes
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   DevBuf chain; int64_t chain_n = 0;                  // values passed down the GPAR chain (gpar_group_broadcast / gpar_set_inputs_column)
   void* pinned = nullptr; size_t pinned_cap = 0;
@@ -93,18 +90,6 @@ struct CallTimer {
     if (e_ != cudaSuccess)                                                                \
       return gpar_fail(ctx, e_ == cudaErrorMemoryAllocation ? GPAR_ERR_NOMEM : GPAR_ERR_CUDA, \
                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
-#define CB(call)                                                                          \
-  do {                                                                                    \
-    cublasStatus_t s_ = (call);                                                           \
-    if (s_ != CUBLAS_STATUS_SUCCESS)                                                      \
-      return gpar_fail(ctx, GPAR_ERR_CUDA, "%s failed: cublas status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
-  } while (0)
-#define CS(call)                                                                          \
-  do {                                                                                    \
-    cusolverStatus_t s_ = (call);                                                         \
-    if (s_ != CUSOLVER_STATUS_SUCCESS)                                                    \
-      return gpar_fail(ctx, GPAR_ERR_CUDA, "%s failed: cusolver status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
   } while (0)
 #define CHK(call) do { int r_ = (call); if (r_ != GPAR_OK) return r_; } while (0)
 
@@ -228,10 +213,28 @@ int merged_gather_test(gpar_ctx* ctx, double* dst_a, double* dst_b);
 static inline void gpar_drop_result(gpar_ctx* c) { c->res_a = nullptr; c->res_b = nullptr; c->res_len = 0; }
 // abi.cu: sufficient statistics of the plain DTC objective over the context's resident data slice (async on its stream)
 int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count);
+// dense_la.cu: hand-written dense linear algebra on column-major FP64 device matrices (no cuBLAS / cuSOLVER anywhere in
+// the library), enqueued on ctx->stream.  Triangular-operand flags restrict the k range of a product and mask the other
+// triangle at load time.
+enum { DLA_LOWER_TILES = 1,   // compute only the 64 x 64 tiles on / below the diagonal of C
+       DLA_A_LOWER = 2, DLA_A_UPPER = 4,     // op(A) is lower / upper triangular
+       DLA_B_UPPER = 8, DLA_B_LOWER = 16 };  // op(B) is upper / lower triangular
+int dla_gemm(gpar_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+             double beta, double* C, int ldc, int flags = 0);
+int dla_gemm_batched(gpar_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda, long long sA,
+                     const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags = 0);
+int dla_potrf(gpar_ctx* ctx, int n, double* A, int lda, int* dinfo);                 // lower; *dinfo = 0 or failing minor (1-based)
+int dla_potrf_batched(gpar_ctx* ctx, int n, double* A, int lda, long long sA, int batch, int* dinfo);
+int dla_trtri(gpar_ctx* ctx, int n, const double* L, int ldl, double* V, int ldv);   // V = L^-1 (upper triangle zeroed)
+int dla_trsm_left(gpar_ctx* ctx, bool trans, int n, int nrhs, const double* L, int ldl, double* B, int ldb);
+int dla_trsv(gpar_ctx* ctx, bool trans, int n, const double* L, int ldl, double* x, double scale = 1.0);
+int dla_dot(gpar_ctx* ctx, int n, const double* x, const double* y, double* out_dev);
+int dla_scal(gpar_ctx* ctx, long long n, double a, double* x);
+int dla_symmetrize(gpar_ctx* ctx, int n, double* A, int lda);                         // mirror the lower triangle up
 // dense_tail.cu
 struct TailBufs {   // M x M scratch of the tail inside ctx->dense
   double *Kj, *Lu, *Bm, *dKu, *V, *Kinv, *R, *Pm, *Tm, *Cm, *cvec, *wvec, *sc;
-  int* dinfo; int lwork;
+  int* dinfo;
 };
 constexpr int GPAR_NTR = 20;      // number of trace scalars produced by the tail (after 8 header scalars)
 int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b);

@@ -11,8 +11,8 @@
 //   dF = -1/(2 sigma^2) tr(T dG) + w'dg/sigma^4 - 1/2 tr((T - cov(u)^{-1}) dcov(u)) + direct sigma^2 term
 // with dG/dlog l = H + H' from the forward-mode panel (panel_syrk.cu).  DESIGN.md has the derivation;
 // tests pin it on torch autograd of the oracle.
-// M^3-class pieces (potrf / trsm / gemm on M x M) are plain library calls (cuSOLVER / cuBLAS);
-// the element-wise and reduction pieces are kernels of this file.
+// The M^3-class pieces (Cholesky, triangular inverse / solves, M x M products) are the hand-written routines of
+// dense_la.cu; the element-wise and reduction pieces are kernels of this file.  No library call anywhere.
 #include "common.cuh"
 #include <algorithm>
 
@@ -31,12 +31,6 @@ __global__ void kuu_kernel(const double* __restrict__ Z, int M, int D, double in
   if (dKu) dKu[(int64_t)a + (int64_t)b * M] = s * ld;
 }
 
-__global__ void set_identity_kernel(double* A, int M) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)M * M) return;
-  A[i] = (i % M == i / M) ? 1.0 : 0.0;
-}
-
 // out[0] = tr(B); then B += I.   single block.
 __global__ void trace_add_identity_kernel(double* B, int M, double* out) {
   __shared__ double sh[32];
@@ -53,11 +47,6 @@ __global__ void logdet_kernel(const double* L, int M, double* out) {
   for (int i = threadIdx.x; i < M; i += blockDim.x) acc += log(L[(int64_t)i * M + i]);
   double r = block_sum(acc, sh);
   if (threadIdx.x == 0) out[0] = 2.0 * r;
-}
-
-__global__ void scale_kernel(double* v, int n, double a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] *= a;
 }
 
 constexpr int NTR = GPAR_NTR;
@@ -109,7 +98,7 @@ static const double LOG2PI = 1.8378770664093454835606594728112;
 int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b) {
   const int M = (int)ctx->M;
   const size_t MM = (size_t)M * M;
-  const int nmat = want_grad ? (vfe ? 10 : 8) : 3;
+  const int nmat = (want_grad && vfe) ? 10 : 8;
   CU(ctx->dense.reserve(nmat * MM * sizeof(double) + 8 * (size_t)M * sizeof(double) + 64 * sizeof(double)));
   double* base = ctx->dense.as<double>();
   b->Kj = base; b->Lu = base + MM; b->Bm = base + 2 * MM;
@@ -118,10 +107,7 @@ int tail_layout(gpar_ctx* ctx, bool want_grad, int vfe, TailBufs* b) {
   b->Tm = base + 8 * MM; b->Cm = base + 9 * MM;
   double* vecs = base + nmat * MM;
   b->cvec = vecs; b->wvec = vecs + M;
-  b->sc = vecs + 8 * (size_t)M;   // device scalars: [0]=trB [1]=logdetLam [2]=cc [8..8+NTR) traces
-  b->lwork = 0;
-  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, b->Lu, M, &b->lwork));
-  CU(ctx->tailws.reserve((size_t)2 * b->lwork * sizeof(double)));      // two potrf workspaces (side + main stream)
+  b->sc = vecs + 8 * (size_t)M;   // device scalars: [0]=trB [1]=logdetLam [2]=cc [4,5]=min/max diag L_u [8..8+NTR) traces
   CU(ctx->info.reserve(4 * sizeof(int)));
   b->dinfo = ctx->info.as<int>();
   return GPAR_OK;
@@ -139,8 +125,7 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
   cudaStream_t main_stream = ctx->stream;
   CU(cudaEventRecord(ctx->ev_fork, main_stream));
   CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-  ctx->stream = ctx->stream2;                 // LAUNCH() and the library handles follow ctx->stream
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
+  ctx->stream = ctx->stream2;                 // LAUNCH() and the dense routines follow ctx->stream
   int rc = [&]() -> int {
     const double inv_l2 = 1.0 / (p.l * p.l);
     dim3 kgrid((M + 127) / 128, M);
@@ -152,19 +137,14 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
       default: LAUNCH(ctx, kuu_kernel<GPAR_MATERN52>, kgrid, 128, 0, Zd, M, D, inv_l2, p.s, jitter, b.Kj, b.dKu); break;
     }
     CU(cudaMemcpyAsync(b.Lu, b.Kj, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, b.Lu, M, ctx->tailws.as<double>() + b.lwork, b.lwork, b.dinfo));
+    CHK(dla_potrf(ctx, M, b.Lu, M, b.dinfo));
     CHK(launch_diag_minmax(ctx, b.Lu, M, b.sc + 4));        // conditioning estimate for the value-only path (abi.cu)
-    if (want_grad) {
-      const double one = 1.0, zero = 0.0;
-      LAUNCH(ctx, set_identity_kernel, (int)((MM + 255) / 256), 256, 0, b.V, M);
-      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, b.Lu, M, b.V, M));
-      CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, b.V, M, b.V, M, &zero, b.Kinv, M));
-    }
+    CHK(dla_trtri(ctx, M, b.Lu, M, b.V, M));                 // V = L_u^-1: B = V G V' below; cov(u)^-1 = V'V for gradients
+    if (want_grad) CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, b.V, M, b.V, M, 0.0, b.Kinv, M, DLA_A_UPPER | DLA_B_LOWER));
     return GPAR_OK;
   }();
   cudaEventRecord(ctx->ev_side, ctx->stream2);
   ctx->stream = main_stream;
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   return rc;
 }
 
@@ -177,65 +157,46 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
   const bool jit_is_noise = jitter_in < 0.0;
   const double jitter = jit_is_noise ? p.noise : jitter_in;
   const double ip = 1.0 / p.noise;
-  cublasSetStream(ctx->blas, ctx->stream);
-  cusolverDnSetStream(ctx->solver, ctx->stream);
   TailBufs tb;
   CHK(tail_layout(ctx, want_grad, vfe, &tb));
   double *Kj = tb.Kj, *Lu = tb.Lu, *Bm = tb.Bm, *dKu = tb.dKu, *V = tb.V, *Kinv = tb.Kinv, *R = tb.R, *Pm = tb.Pm, *Tm = tb.Tm, *Cm = tb.Cm;
   double *cvec = tb.cvec, *wvec = tb.wvec, *sc = tb.sc;
-  int* dinfo = tb.dinfo; const int lwork = tb.lwork;
+  int* dinfo = tb.dinfo;
   (void)kind;
-  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));     // join: L_u (and V, cov(u)^-1) are ready
-  const double one = 1.0, zero = 0.0;
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));     // join: L_u, V = L_u^-1 (and cov(u)^-1) are ready
   int trace_blocks = 0;
-  if (!want_grad) {
-    // value only — the reference's own sequence of triangular solves (dtc_example.jl:14-21)
+  // B = L_u^-1 G L_u^-T / sigma^2 = V G V' / sigma^2 (lower tiles: only chol(Lambda) reads it); with a panel whitened by
+  // L_u before the SYRK, G is already A A' (sigma^2 apart)
+  if (whitened_G) {
     CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (whitened_G) {      // the panel was whitened by L_u before the SYRK: G is already A A' (sigma^2 apart)
-      CB(cublasDscal(ctx->blas, (int)MM, &ip, Bm, 1));
-    } else {
-      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
-      CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &ip, Lu, M, Bm, M));
-    }
-    LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
-    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
-    LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
-    CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
-    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
+    CHK(dla_scal(ctx, (long long)MM, ip, Bm));
   } else {
-    // with gradient: the explicit triangular inverses are needed anyway (P, cov(u)^-1), so B is formed
-    // from them with two GEMMs instead of two more triangular solves:
-    //   V = L_u^-1;  B = V G V'/sigma^2;  R = L_Lambda^-1 V;  Kinv = V'V;  P = R'R
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, V, M, G, M, &zero, Pm, M));        // Pm = V G (scratch)
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_T, M, M, M, &ip, Pm, M, V, M, &zero, Bm, M));         // B
-    LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
-    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
-    LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
-    CU(cudaMemcpyAsync(R, V, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Bm, M, R, M));
-    CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, M, M, M, &one, R, M, R, M, &zero, Pm, M));
-    // c and w through backward-stable triangular solves, NOT through the explicit inverses: the gradient
-    // sums cancel terms of size g'w / sigma^4 and need w to satisfy Q w = g to working accuracy
-    // (with w = P g the s-derivative at N = 1M, M = 1024 was off by 1 %).
-    CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
-    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, cvec, M, ip);
-    CU(cudaMemcpyAsync(wvec, cvec, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Bm, M, wvec, 1));
-    CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Lu, M, wvec, 1));
-    LAUNCH(ctx, scale_kernel, (M + 255) / 256, 256, 0, wvec, M, p.noise);
+    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, G, M, 0.0, Pm, M, DLA_A_LOWER));                       // Pm = V G (scratch)
+    CHK(dla_gemm(ctx, false, true, M, M, M, ip, Pm, M, V, M, 0.0, Bm, M, DLA_B_UPPER | DLA_LOWER_TILES));       // B
   }
-  CB(cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_DEVICE));
-  cublasStatus_t st = cublasDdot(ctx->blas, M, cvec, 1, cvec, 1, sc + 2);
-  cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_HOST);
-  CB(st);
+  LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
+  CHK(dla_potrf(ctx, M, Bm, M, dinfo + 1));
+  LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
+  // c = L_Lambda^-1 L_u^-1 g / sigma^2 (and w below) through backward-stable substitutions, NOT through explicit
+  // inverses: the gradient sums cancel terms of size g'w / sigma^4 and need w to satisfy Q w = g to working accuracy
+  // (with w = P g the s-derivative at N = 1M, M = 1024 was off by 1 %).
+  CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsv(ctx, false, M, Lu, M, cvec));
+  CHK(dla_trsv(ctx, false, M, Bm, M, cvec, ip));
+  if (want_grad) {
+    //   R = L_Lambda^-1 V (= (L_u L_Lambda)^-1);  P = Q^-1 = R'R,  Q = cov(u) + G/sigma^2 = L_u Lambda L_u'
+    CHK(dla_trtri(ctx, M, Bm, M, Pm, M));                                                                        // Pm = L_Lambda^-1 (scratch)
+    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, Pm, M, V, M, 0.0, R, M, DLA_A_LOWER | DLA_B_LOWER));
+    CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, R, M, R, M, 0.0, Pm, M, DLA_A_UPPER | DLA_B_LOWER));
+    CU(cudaMemcpyAsync(wvec, cvec, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CHK(dla_trsv(ctx, true, M, Bm, M, wvec));
+    CHK(dla_trsv(ctx, true, M, Lu, M, wvec, p.noise));
+  }
+  CHK(dla_dot(ctx, M, cvec, cvec, sc + 2));
   if (want_grad) {
     if (vfe) {
-      CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Kinv, M, G, M, &zero, Tm, M));
-      CB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, M, M, M, &one, Tm, M, Kinv, M, &zero, Cm, M));
+      CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, Kinv, M, G, M, 0.0, Tm, M));
+      CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, Tm, M, Kinv, M, 0.0, Cm, M));
     }
     trace_blocks = (int)std::min<size_t>((MM + 255) / 256, (size_t)ctx->num_sms * 4);
     CU(ctx->scal.reserve((size_t)trace_blocks * NTR * sizeof(double)));

@@ -7,7 +7,8 @@
 // ntheta = 5: GPAR kernel time_var^2 k_t(|dx_1|/time_l) + out_var^2 k_o(||dx_2:D||/out_l)
 // (create_gpar_kernel, optimized.jl:132-144).  One factorisation serves every resident output
 // sequence (batch of right-hand sides).  Latency-bound: kernel-matrix evaluation and reductions are
-// kernels of this file, the N^3/3 factorisation and the triangular solves are library calls.
+// kernels of this file; the N^3/3 factorisation, the blocked triangular solves and the products are the hand-written
+// routines of dense_la.cu (no library call).
 #include "common.cuh"
 #include <algorithm>
 
@@ -86,14 +87,9 @@ int factor_and_whiten(gpar_ctx* ctx, const ExactKernel& ek, double noise, double
   const double* X = ctx->X.as<double>();
   dim3 grid((n + 127) / 128, n);
   LAUNCH(ctx, exact_kernel_matrix, grid, 128, 0, X, n, X, n, ctx->D, ek, noise, L, n);
-  int lwork = 0;
-  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, L, n, &lwork));
-  CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, L, n, ctx->tailws.as<double>(), lwork, dinfo));
+  CHK(dla_potrf(ctx, n, L, n, dinfo));
   CU(cudaMemcpyAsync(W, ctx->y.p, (size_t)n * batch * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  const double one = 1.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, batch, &one, L, n, W, n));
-  return GPAR_OK;
+  return dla_trsm_left(ctx, false, n, batch, L, n, W, n);
 }
 
 int check_exact(gpar_ctx* ctx, const char* who) {
@@ -115,7 +111,6 @@ int gpar_exact_logpdf(gpar_ctx* ctx, int k_time, int k_out, const double* theta,
   CHK(setup_kernel(ctx, k_time, k_out, theta, ntheta, &ek, &noise, &kss));
   CU(cudaSetDevice(ctx->device));
   CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   const int n = (int)ctx->N, batch = ctx->ybatch;
   CU(ctx->dense.reserve(((size_t)n * n + (size_t)n * batch + batch + 8) * sizeof(double)));
   CU(ctx->info.reserve(4 * sizeof(int)));
@@ -146,7 +141,6 @@ int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* the
   double* dXs = ctx->kal_b.as<double>(); double* V = dXs + (size_t)Ns * D; double* dmean = V + (size_t)n * Ns; double* dq = dmean + (size_t)Ns * batch;
   CU(cudaMemcpyAsync(dXs, Xs, (size_t)Ns * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
   CU(ctx->dense.reserve(((size_t)n * n + (size_t)n * batch + 8) * sizeof(double)));
   CU(ctx->info.reserve(4 * sizeof(int)));
   double* L = ctx->dense.as<double>(); double* W = L + (size_t)n * n;
@@ -154,9 +148,8 @@ int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* the
   // V = L^{-1} K_{f*}  (n x Ns);  mean = V^T W;  var = k** - colsum(V^2) + 1e-18
   dim3 grid((n + 127) / 128, (unsigned)Ns);
   LAUNCH(ctx, exact_kernel_matrix, grid, 128, 0, ctx->X.as<double>(), n, dXs, (int)Ns, D, ek, 0.0, V, n);
-  const double one = 1.0, zero = 0.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, (int)Ns, &one, L, n, V, n));
-  CB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, (int)Ns, batch, n, &one, V, n, W, n, &zero, dmean, (int)Ns));
+  CHK(dla_trsm_left(ctx, false, n, (int)Ns, L, n, V, n));
+  CHK(dla_gemm(ctx, true, false, (int)Ns, batch, n, 1.0, V, n, W, n, 0.0, dmean, (int)Ns));
   LAUNCH(ctx, colsumsq_kernel, (int)Ns, 128, 0, V, n, dq);
   timer.stop();
   std::vector<double> hq(Ns); int hinfo = 0;

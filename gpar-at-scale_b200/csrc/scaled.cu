@@ -340,12 +340,6 @@ __global__ void lower_to_upper_kernel(const double* __restrict__ L, int M, doubl
   int r = (int)(e % M), c = (int)(e / M);
   U[e] = (r <= c) ? L[(int64_t)c + (int64_t)r * M] : 0.0;
 }
-__global__ void mirror_lower_kernel(double* A, int M) {
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= (int64_t)M * M) return;
-  int r = (int)(e % M), c = (int)(e / M);
-  if (r < c) A[e] = A[(int64_t)c + (int64_t)r * M];
-}
 // Bt (M x N col-major) from the panel: Bt[m + n*M] = panel(m, n)
 __global__ void panel_to_dense_t_kernel(const double* __restrict__ panel, int64_t N, int M, int64_t NB4, double* __restrict__ Bt) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -844,25 +838,24 @@ int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, c
 }
 static const double LOG2PI_S = 1.8378770664093454835606594728112;
 
-// cov(u) = Kuu + jitter I and its Cholesky factor on the SIDE stream (underneath the filter / whitening), plus
-// min / max of diag(L_u) for the conditioning decision.  Records ctx->ev_side.
-static int factor_cov_u_side(gpar_ctx* ctx, int k_out, double out_l, double out_s, double jitter, double* Lu, int lwork, int* dinfo,
+// cov(u) = Kuu + jitter I, its Cholesky factor L_u and V = L_u^-1 on the SIDE stream (underneath the filter /
+// whitening), plus min / max of diag(L_u) for the conditioning decision.  Records ctx->ev_side.
+static int factor_cov_u_side(gpar_ctx* ctx, int k_out, double out_l, double out_s, double jitter, double* Lu, double* V, int* dinfo,
                              double* minmax_dev) {
   const int M = (int)ctx->M;
   cudaStream_t main_stream = ctx->stream;
   CU(cudaEventRecord(ctx->ev_fork, main_stream));
   CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
   ctx->stream = ctx->stream2;
-  cusolverDnSetStream(ctx->solver, ctx->stream);
   int rc = [&]() -> int {
     CHK(launch_kuu_plain(ctx, k_out, out_l, out_s, jitter, Lu));
-    CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, ctx->tailws.as<double>(), lwork, dinfo));
+    CHK(dla_potrf(ctx, M, Lu, M, dinfo));
     CHK(launch_diag_minmax(ctx, Lu, M, minmax_dev));
+    CHK(dla_trtri(ctx, M, Lu, M, V, M));
     return GPAR_OK;
   }();
   cudaEventRecord(ctx->ev_side, ctx->stream2);
   ctx->stream = main_stream;
-  cusolverDnSetStream(ctx->solver, ctx->stream);
   return rc;
 }
 // The hook of scaled_stats: wait for L_u, decide on the conditioning, whiten the panel by L_u when it is poor.
@@ -891,43 +884,35 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;
   const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
   const int M = (int)ctx->M; const int64_t N = ctx->N; const size_t MM = (size_t)M * M;
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
-  CU(ctx->dense.reserve((2 * MM + 2 * (size_t)M + 16) * sizeof(double)));
-  double* Lu = ctx->dense.as<double>(); double* Bm = Lu + MM; double* cvec = Bm + MM; double* sc = cvec + 2 * M;
-  int lwork = 0;
-  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, &lwork));
-  CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
+  CU(ctx->dense.reserve((4 * MM + 2 * (size_t)M + 16) * sizeof(double)));
+  double* Lu = ctx->dense.as<double>(); double* Bm = Lu + MM; double* V = Bm + MM; double* Tm = V + MM; double* cvec = Tm + MM; double* sc = cvec + 2 * M;
   CU(ctx->info.reserve(4 * sizeof(int)));
   int* dinfo = ctx->info.as<int>();
-  // cov(u) = Kuu + noise_sigma^2 I (dtc.jl:35,119) and L_u on the side stream
-  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, Lu, lwork, dinfo, sc + 4));
+  // cov(u) = Kuu + noise_sigma^2 I (dtc.jl:35,119), L_u and L_u^-1 on the side stream
+  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, Lu, V, dinfo, sc + 4));
   bool robust = false;
   PanelHook hook = make_whitening_hook(ctx, Lu, sc + 4, &robust);
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, false, &hook));
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
-  CU(cudaMemcpyAsync(Bm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  const double one = 1.0;
-  if (!robust) {      // collapsed statistic: B = L_u^-1 (beta'beta) L_u^-T;  whitened panel: G is already A A'
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Bm, M));
+  if (!robust) {      // collapsed statistic: B = L_u^-1 (beta'beta) L_u^-T = V G V';  whitened panel: G is already A A'
+    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, st.G, M, 0.0, Tm, M, DLA_A_LOWER));
+    CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, Tm, M, V, M, 0.0, Bm, M, DLA_B_UPPER | DLA_LOWER_TILES));
+  } else {
+    CU(cudaMemcpyAsync(Bm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Bm, M);
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Bm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
+  CHK(dla_potrf(ctx, M, Bm, M, dinfo + 1));
   LAUNCH(ctx, logdet2_kernel, 1, 256, 0, Bm, M, sc);
   // c = L_Lambda^-1 (A alpha), A alpha = L_u^-1 g with g = beta'alpha (accumulated by the whitening pass, before the hook)
   CU(cudaMemcpyAsync(cvec, st.g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, cvec, 1));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Bm, M, cvec, 1));
-  CB(cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_DEVICE));
-  cublasStatus_t bst = cublasDdot(ctx->blas, M, cvec, 1, cvec, 1, sc + 1);
-  cublasSetPointerMode(ctx->blas, CUBLAS_POINTER_MODE_HOST);
-  CB(bst);
+  CHK(dla_trsv(ctx, false, M, Lu, M, cvec));
+  CHK(dla_trsv(ctx, false, M, Bm, M, cvec));
+  CHK(dla_dot(ctx, M, cvec, cvec, sc + 1));
   if (A_or_null) {   // A = chol(cov(u)).U' \ beta'  (dtc.jl:119), M x N column-major — small problems only
     CU(ctx->kal_b.reserve((size_t)N * M * sizeof(double)));
     double* Bt = ctx->kal_b.as<double>();
     LAUNCH(ctx, panel_to_dense_t_kernel, (int)(((size_t)N * M + 255) / 256), 256, 0, ctx->panelK.as<double>(), N, M, st.Npad / 4, Bt);
-    if (!robust) CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, (int)N, &one, Lu, M, Bt, M));
+    if (!robust) CHK(dla_trsm_left(ctx, false, M, (int)N, Lu, M, Bt, M));
   }
   timer.stop();
   double hs[2]; int hinfo[2];
@@ -1009,43 +994,37 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
 
 // Shared front half of compute_q_u and the sampler: L_u = chol(Cuu) (bare, gpar_scaled_inference.jl:157-159),
 // L_D = chol(B_ef B_ef' + I) (:187), m_e = L_D^-T L_D^-1 L_u^-1 g (:189) — all left on the device.
-struct QuFactors { double *Lu, *LD, *Uu, *me; int* dinfo; int lwork; };
+struct QuFactors { double *Lu, *LD, *Uu, *me, *tmp; int* dinfo; };
 static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params[5], QuFactors* q) {
   const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
-  CU(ctx->dense.reserve((3 * MM + 2 * (size_t)M + 16) * sizeof(double)));
-  double* Lu = ctx->dense.as<double>(); double* Dm = Lu + MM; double* Uu = Dm + MM; double* vec = Uu + MM; double* mmdev = vec + 2 * M;
-  int lwork = 0, lwork2 = 0;
-  CS(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Lu, M, &lwork));
-  CS(cusolverDnDpotri_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Dm, M, &lwork2));
-  lwork = std::max(lwork, lwork2);
-  CU(ctx->tailws.reserve((size_t)lwork * sizeof(double)));
+  CU(ctx->dense.reserve((5 * MM + 2 * (size_t)M + 16) * sizeof(double)));
+  double* Lu = ctx->dense.as<double>(); double* Dm = Lu + MM; double* Uu = Dm + MM; double* V = Uu + MM; double* Tm = V + MM;
+  double* vec = Tm + MM; double* mmdev = vec + 2 * M;
   CU(ctx->info.reserve(4 * sizeof(int)));
   int* dinfo = ctx->info.as<int>();
   CU(cudaMemsetAsync(dinfo, 0, 4 * sizeof(int), ctx->stream));
   // bare Cuu (gpar_scaled_inference.jl:157-159) — no jitter, usually poorly conditioned: the panel is then whitened by
   // L_u before the SYRK (B_ef = U_u' \ beta', :179, as the reference forms it) instead of collapsing to beta'beta first
-  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, 0.0, Lu, lwork, dinfo, mmdev));
+  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, 0.0, Lu, V, dinfo, mmdev));
   bool robust = false;
   PanelHook hook = make_whitening_hook(ctx, Lu, mmdev, &robust);
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, false, &hook));
-  cublasSetStream(ctx->blas, ctx->stream); cusolverDnSetStream(ctx->solver, ctx->stream);
-  CU(cudaMemcpyAsync(Dm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  const double one = 1.0;
   if (!robust) {
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
-    CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one, Lu, M, Dm, M));
+    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, st.G, M, 0.0, Tm, M, DLA_A_LOWER));
+    CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, Tm, M, V, M, 0.0, Dm, M, DLA_B_UPPER | DLA_LOWER_TILES));
+  } else {
+    CU(cudaMemcpyAsync(Dm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Dm, M);          // D = B_ef B_ef' + I (:187)
-  CS(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, Dm, M, ctx->tailws.as<double>(), lwork, dinfo + 1));
+  CHK(dla_potrf(ctx, M, Dm, M, dinfo + 1));
   // m_e = chol_D \ (B_ef b_y) = L_D^{-T} L_D^{-1} L_u^{-1} g  (:189)
   CU(cudaMemcpyAsync(vec, st.g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Lu, M, vec, 1));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, M, Dm, M, vec, 1));
-  CB(cublasDtrsv(ctx->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, Dm, M, vec, 1));
-  q->Lu = Lu; q->LD = Dm; q->Uu = Uu; q->me = vec; q->dinfo = dinfo; q->lwork = lwork;
+  CHK(dla_trsv(ctx, false, M, Lu, M, vec));
+  CHK(dla_trsv(ctx, false, M, Dm, M, vec));
+  CHK(dla_trsv(ctx, true, M, Dm, M, vec));
+  q->Lu = Lu; q->LD = Dm; q->Uu = Uu; q->me = vec; q->tmp = Tm; q->dinfo = dinfo;
   return GPAR_OK;
 }
 
@@ -1059,9 +1038,9 @@ int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5
   CHK(q_u_factors(ctx, k_time, k_out, params, &q));
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
   LAUNCH(ctx, lower_to_upper_kernel, (int)((MM + 255) / 256), 256, 0, q.Lu, M, q.Uu);
-  // inv(D) (:192)
-  CS(cusolverDnDpotri(ctx->solver, CUBLAS_FILL_MODE_LOWER, M, q.LD, M, ctx->tailws.as<double>(), q.lwork, q.dinfo + 2));
-  LAUNCH(ctx, mirror_lower_kernel, (int)((MM + 255) / 256), 256, 0, q.LD, M);
+  // inv(D) = L_D^-T L_D^-1 (:192): triangular inverse, then one product (the full symmetric matrix comes out)
+  CHK(dla_trtri(ctx, M, q.LD, M, q.tmp, M));
+  CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, q.tmp, M, q.tmp, M, 0.0, q.LD, M, DLA_A_UPPER | DLA_B_LOWER));
   timer.stop();
   int hinfo[3];
   CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1090,11 +1069,10 @@ int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5]
   CU(ctx->qW.reserve((size_t)2 * total * sizeof(double)));
   double* W = ctx->qW.as<double>(); double* E = W + total;
   LAUNCH(ctx, philox_normal_kernel, (int)(((total + 1) / 2 + 255) / 256), 256, 0, E, total, seed);
-  const double one = 1.0;
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, S, &one, q.LD, M, E, M));
+  CHK(dla_trsm_left(ctx, true, M, S, q.LD, M, E, M));
   LAUNCH(ctx, add_column_vector_kernel, (int)((total + 255) / 256), 256, 0, E, q.me, M, total);
   CU(cudaMemcpyAsync(W, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CB(cublasDtrsm(ctx->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, S, &one, q.Lu, M, W, M));
+  CHK(dla_trsm_left(ctx, true, M, S, q.Lu, M, W, M));
   timer.stop();
   int hinfo[2];
   CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));

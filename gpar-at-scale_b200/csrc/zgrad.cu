@@ -98,11 +98,10 @@ int zgrad_run(gpar_ctx* ctx, const GpParams& p, int vfe, double* grad_Z) {
   LAUNCH(ctx, zgrad_matrices_kernel, (int)((MM + 255) / 256), 256, 0, M, tb.Pm, tb.Kinv, vfe ? tb.Cm : nullptr, tb.wvec, ip, A, Cb);
   // q = (y - K w/sigma^2)/sigma^4: residual with the scaled weights, then a scale
   CU(cudaMemcpyAsync(ws, tb.wvec, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  cublasSetStream(ctx->blas, ctx->stream);
-  CB(cublasDscal(ctx->blas, M, &ip, ws, 1));
+  CHK(dla_scal(ctx, M, ip, ws));
   CHK(launch_panel_residual(ctx, ctx->panelK.as<double>(), ws, ctx->y.as<double>(), N, NB4, T, M, q));
   const double ip2 = ip * ip;
-  CB(cublasDscal(ctx->blas, (int)N, &ip2, q, 1));
+  CHK(dla_scal(ctx, (long long)N, ip2, q));
   // slabs of the K panel -> S = K A (DMMA panel-GEMM, A symmetric) -> contraction with dk/dz
   const int64_t slab_steps = std::min<int64_t>(Npad, 131072);
   const int nslab = (int)((Npad + slab_steps - 1) / slab_steps);

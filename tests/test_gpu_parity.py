@@ -862,3 +862,60 @@ def test_abi_error_behaviour():
     with pytest.raises(gp.GparError, match="ntheta"):
         c.exact_logpdf(3, 3, np.zeros(4))
     c.close()
+
+
+@pytest.mark.parametrize("n,ns,batch", [(1, 3, 1), (63, 5, 2), (64, 64, 1), (65, 70, 3), (200, 129, 2), (517, 300, 5), (1100, 257, 1)])
+def test_exact_gp_dense_routines_ragged_sizes(ctx, n, ns, batch):
+    """The hand-written dense routines (dense_la.cu: blocked Cholesky with 64 x 64 diagonal blocks, blocked triangular
+    solves, DMMA products) behind the exact-GP entry points (optimized.jl:34,152,94,236), at sizes around and across the
+    block boundaries, several right-hand sides: log-pdf, posterior mean and variance against the oracle."""
+    rng = np.random.default_rng(1000 + n)
+    D = 3
+    X = rng.normal(size=(n, D)); X[:, 0] = np.sort(rng.uniform(0, 5, n))
+    Y = rng.normal(size=(batch, n)); Xs = rng.normal(size=(ns, D))
+    th = np.array([0.3, -0.2, 0.1, 0.2, -1.0])
+    tl, tv, ol, ov, sg = oracle.unpack_gpar(th)
+    ctx.set_inputs(X); ctx.set_outputs(Y)
+    K = oracle.gpar_kernel_matrix(3, 0, X, X, tl, tv, ol, ov)
+    lml = ctx.exact_logpdf(3, 0, th)
+    for b in range(batch):
+        ref = oracle.exact_logpdf(K, sg ** 2, Y[b])
+        assert abs(lml[b] - ref) <= RTOL * abs(ref), (n, b, lml[b], ref)
+    mean, var = ctx.exact_posterior(3, 0, th, Xs)
+    Ksf = oracle.gpar_kernel_matrix(3, 0, Xs, X, tl, tv, ol, ov)
+    for b in range(batch):
+        m0, v0 = oracle.exact_posterior(K, Ksf, np.full(ns, tv ** 2 + ov ** 2), sg ** 2, Y[b])
+        assert np.max(np.abs(mean[b] - m0)) <= RTOL * max(1.0, np.max(np.abs(m0)))
+        assert np.max(np.abs(var - v0)) <= RTOL * max(1.0, np.max(np.abs(v0)))
+
+
+def test_exact_gp_not_posdef_is_reported(ctx):
+    """A non-positive pivot of the hand-written Cholesky is reported like LAPACK's info / Julia's PosDefException."""
+    import gpar_at_scale_b200 as gp
+    x = np.linspace(0, 1, 300)[:, None]          # very smooth EQ kernel, huge variance: K + 1e-6 I is numerically indefinite
+    ctx.set_inputs(x); ctx.set_outputs(np.ones(300))
+    with pytest.raises(gp.PosDefException):
+        ctx.exact_logpdf(0, 0, np.array([3.0, 12.0, -40.0]))
+    assert np.isfinite(ctx.exact_logpdf(0, 0, np.array([-2.0, 0.0, -1.0]))[0])        # and the context stays usable
+
+
+@pytest.mark.parametrize("m", [7, 64, 100, 200, 333])
+def test_q_u_and_draws_dense_routines_ragged_m(ctx, m):
+    """compute_q_u / sample_q_u (gpar_scaled_inference.jl:141-196, :94-96) over pseudo-point counts across the 64-block
+    boundaries of the dense routines: m_e, inv(D), U_u against the oracle; U_u W = eps for the seeded draws."""
+    rng = np.random.default_rng(2000 + m)
+    n = 1500
+    t = np.sort(rng.uniform(0, 50, n)); X = rng.normal(size=(n, 2)); Z = rng.normal(size=(m, 2)) * 1.5
+    y = np.sin(t) + 0.3 * X[:, 0] + 0.1 * rng.normal(size=n)
+    params = np.array([1.3, 0.9, 0.7, 0.8, 0.3])
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+    m_e, Dinv, U_u = ctx.compute_q_u(3, 3, params)
+    Cfu = oracle.pairwise(3, X, Z, l=params[2], s=params[3] ** 2); Cuu = oracle.pairwise(3, Z, Z, l=params[2], s=params[3] ** 2)
+    from oracle.cport import kalman_decorrelate as fast_dec
+    m0, D0, U0 = oracle.compute_q_u(Cfu, Cuu, t, y, 3, params[0], params[1] ** 2, params[4] ** 2, decorrelate=fast_dec)
+    tol = max(RTOL, 100 * 2.2e-16 * np.linalg.cond(U0) ** 2)          # bare Cuu (quirk B-2): the documented tolerance exception
+    assert np.max(np.abs(np.triu(U_u) - U0)) <= tol * np.max(np.abs(U0))
+    assert np.max(np.abs(m_e - m0)) <= tol * max(1.0, np.max(np.abs(m0)))
+    assert np.max(np.abs(Dinv - D0)) <= tol * max(1.0, np.max(np.abs(D0)))
+    W, E = ctx.sample_q_u(3, 3, params, 99, 16, return_host=True)
+    assert np.max(np.abs(np.triu(U_u) @ W - E)) <= 1e-8 * max(1.0, np.max(np.abs(E))) * max(1.0, np.linalg.cond(U0))

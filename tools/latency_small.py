@@ -1,9 +1,10 @@
 """Per-evaluation latency at the reference's own problem sizes (N = 8 496, M = 50 / 81; EEG N = M = 156)."""
-import sys, time
+import sys, os, time
 import numpy as np
 sys.path.insert(0, ".")
 import gpar_at_scale_b200 as gp
-from gpar_at_scale_b200 import data
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples'))
+import toy_data as data
 rng = np.random.default_rng(0)
 x, y_obs, x_true, y_true = data.generate_big_dataset(rng, true_samples=1000)
 ctx = gp.Context(0)
