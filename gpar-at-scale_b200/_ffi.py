@@ -26,6 +26,7 @@ SIGNATURES = {
     "gpar_last_timing": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
     "gpar_last_profile": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32]),
     "gpar_measure_peaks": (ctypes.c_int, [_c_void_p, _c_double_p, _c_double_p, _c_double_p]),
+    "gpar_dense_bench": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p]),
     "gpar_set_inputs": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_pseudo": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int32, ctypes.c_int64]),
     "gpar_set_times": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64]),
@@ -52,6 +53,8 @@ SIGNATURES = {
     "gpar_lgssm_decorrelate": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_lgssm_smooth": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_exact_logpdf": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p]),
+    "gpar_exact_logpdf_batch": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32, ctypes.c_int32, _c_double_p,
+                                               ctypes.POINTER(ctypes.c_int32)]),
     "gpar_exact_posterior": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32,
                                             _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
     "gpar_group_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.POINTER(_c_void_p)]),

@@ -73,6 +73,12 @@ class Context:
         self._check(self._lib.gpar_measure_peaks(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"dmma_tflops": a.value, "dfma_tflops": b.value, "hbm_copy_gbs": c.value}
 
+    def dense_bench(self, n):
+        """Device ms of the dense routines at order n: potrf, trtri, triangular / lower-tile / full gemm, trsv, trsv^T."""
+        out = np.zeros(7)
+        self._check(self._lib.gpar_dense_bench(self._h, int(n), dptr(out)))
+        return dict(zip(["potrf", "trtri", "gemm_tri", "gemm_lower", "gemm_full", "trsv", "trsv_t"], out.tolist()))
+
     # -- resident data ------------------------------------------------------------------------
     def set_inputs(self, X):
         """X: (N, D) records (memory image of the reference's D x N ColVecs, util.jl:16-31)."""
@@ -209,8 +215,10 @@ class Context:
         return mean, sd
 
     def lgssm_logpdf(self, kernel, theta):
+        """theta: (3,) shared, (batch, 3) one per resident sequence, or — with ONE resident sequence — (ncand, 3)
+        hyper-parameter candidates evaluated in one pass -> lml per sequence / candidate."""
         th = as_f64(np.atleast_2d(theta))
-        out = np.zeros(self.batch)
+        out = np.zeros(max(self.batch, th.shape[0]))
         self._check(self._lib.gpar_lgssm_logpdf(self._h, int(kernel), dptr(th), th.shape[0], dptr(out)))
         return out
 
@@ -246,6 +254,15 @@ class Context:
         out = np.zeros(self.batch)
         self._check(self._lib.gpar_exact_logpdf(self._h, int(k_time), int(k_out), dptr(th), th.shape[0], dptr(out)))
         return out
+
+    def exact_logpdf_batch(self, k_time, k_out, thetas):
+        """thetas: (ncand, 3 or 5) hyper-parameter candidates on the resident data, one launch -> (lml (ncand, batch),
+        codes (ncand,): non-zero where a candidate's Cholesky failed, its lml then NaN)."""
+        th = as_f64(np.atleast_2d(thetas))
+        out = np.zeros((th.shape[0], self.batch)); codes = np.zeros(th.shape[0], dtype=np.int32)
+        self._check(self._lib.gpar_exact_logpdf_batch(self._h, int(k_time), int(k_out), dptr(th), th.shape[1], th.shape[0], dptr(out),
+                                                      codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out, codes
 
     def exact_posterior(self, k_time, k_out, theta, Xs):
         th = as_f64(np.asarray(theta).ravel())

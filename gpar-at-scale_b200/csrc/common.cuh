@@ -49,6 +49,7 @@ struct gpar_ctx {
   int32_t D = 0, Dz = 0, ybatch = 0;
   int64_t N = 0, M = 0, Nt = 0, Ny = 0, Nr = 0;
   bool has_rvec = false;
+  bool y_broadcast = false;           // transient: the running lgssm call evaluates parameter candidates on ONE resident sequence
   bool ss_deferred_ok = false;        // the running entry point checks lgssm_steady_failed() after its final synchronisation
   bool ss_pending = false;            // the single-pass steady-state path ran: its flags are on their way to ctx->pinned
   int ss_skip = 0;                    // calls for which the steady-state Kalman path stays off after a non-converged hand-over
@@ -61,6 +62,7 @@ struct gpar_ctx {
   // and the device arrays of the last smoother / prediction result (for gpar_take_test)
   DevBuf mrg, test_pos; int64_t merged_N = 0, merged_Ns = 0; const double* res_a = nullptr; const double* res_b = nullptr; int64_t res_len = 0;
   DevBuf shbuf;                       // shared-model smoother: tables, chunk states, filtered means (smooth_shared.cu)
+  bool dla_optin = false;
   DevBuf dla_ws, dla_ws_side, dla_ws2;                // scratch of the dense M x M routines (dense_la.cu): main / side stream, transposes
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   DevBuf chain; int64_t chain_n = 0;                  // values passed down the GPAR chain (gpar_group_broadcast / gpar_set_inputs_column)

@@ -38,12 +38,18 @@ struct GemmP {
 };
 
 // op(A) is m x k, op(B) is k x n.  Shared layout [k/4][row or col][k%4]: a DMMA fragment is 32 consecutive doubles.
-// The global loads of stage s + 1 are issued into registers before the DMMAs of stage s (software pipelining).
+// Operands move global -> shared with 8-byte cp.async (zero-filled where masked: outside the matrix or in the ignored
+// triangle of a triangular operand) through a 3-stage ring, two k-blocks ahead of the DMMAs; one barrier per k-block.
+constexpr int DST = 3;
+__device__ __forceinline__ void cp_async8_zfill(double* dst, const double* src, bool valid) {
+  const unsigned sz = valid ? 8u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(sz) : "memory");
+}
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128)
 dla_gemm_kernel(const GemmP p) {
-  __shared__ double As[DK / 4 * DT * 4];
-  __shared__ double Bs[DK / 4 * DT * 4];
+  __shared__ double As[DST][DK / 4 * DT * 4];
+  __shared__ double Bs[DST][DK / 4 * DT * 4];
   const int i0 = blockIdx.x * DT, j0 = blockIdx.y * DT;
   if ((p.flags & DLA_LOWER_TILES) && j0 > i0) return;
   const double* A = p.A + (long long)blockIdx.z * p.sA;
@@ -58,28 +64,37 @@ dla_gemm_kernel(const GemmP p) {
   if (p.flags & DLA_A_UPPER) kbeg = max(kbeg, i0);               // op(A)[i, q] = 0 for q < i
   if (p.flags & DLA_B_LOWER) kbeg = max(kbeg, j0);               // op(B)[q, j] = 0 for q < j
   kbeg = kbeg / DK * DK;
-  // this thread's 8 + 8 elements of a stage: (row / col, k) inside the tile and their shared-memory slots
-  int ai[8], aq[8], bj[8], bq[8];
+  const int nst = kend > kbeg ? (kend - kbeg + DK - 1) / DK : 0;
+  // this thread's 8 + 8 elements of a k-block: position inside the tile, shared-memory slot, global pointer at k = 0
+  int agi[8], aq[8], bgj[8], bq[8], aslot[8], bslot[8];
+  const double* ap[8]; const double* bp[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int e = tid + 128 * r;
-    if (TA) { aq[r] = e & 15; ai[r] = e >> 4; } else { ai[r] = e & 63; aq[r] = e >> 6; }
-    if (TB) { bj[r] = e & 63; bq[r] = e >> 6; } else { bq[r] = e & 15; bj[r] = e >> 4; }
+    int ai, bj;
+    if (TA) { aq[r] = e & 15; ai = e >> 4; } else { ai = e & 63; aq[r] = e >> 6; }
+    if (TB) { bj = e & 63; bq[r] = e >> 6; } else { bq[r] = e & 15; bj = e >> 4; }
+    agi[r] = i0 + ai; bgj[r] = j0 + bj;
+    aslot[r] = (aq[r] >> 2) * (DT * 4) + ai * 4 + (aq[r] & 3);
+    bslot[r] = (bq[r] >> 2) * (DT * 4) + bj * 4 + (bq[r] & 3);
+    ap[r] = TA ? A + (long long)agi[r] * p.lda + aq[r] : A + (long long)agi[r] + (long long)aq[r] * p.lda;
+    bp[r] = TB ? B + (long long)bgj[r] + (long long)bq[r] * p.ldb : B + (long long)bgj[r] * p.ldb + bq[r];
   }
-  double ra[8], rb[8];
-  auto fetch = [&](int q0) {
+  const long long astep = TA ? 1 : p.lda, bstep = TB ? p.ldb : 1;      // pointer advance per unit of k
+  auto issue = [&](int st) {
+    const int q0 = kbeg + st * DK, buf = st % DST;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const int gi = i0 + ai[r], gq = q0 + aq[r];
-      bool keep = gi < p.m && gq < p.k;
-      if ((p.flags & DLA_A_LOWER) && gq > gi) keep = false;
-      if ((p.flags & DLA_A_UPPER) && gq < gi) keep = false;
-      ra[r] = keep ? (TA ? A[(long long)gq + (long long)gi * p.lda] : A[(long long)gi + (long long)gq * p.lda]) : 0.0;
-      const int gj = j0 + bj[r], hq = q0 + bq[r];
-      bool keepb = gj < p.n && hq < p.k;
-      if ((p.flags & DLA_B_UPPER) && hq > gj) keepb = false;
-      if ((p.flags & DLA_B_LOWER) && hq < gj) keepb = false;
-      rb[r] = keepb ? (TB ? B[(long long)gj + (long long)hq * p.ldb] : B[(long long)hq + (long long)gj * p.ldb]) : 0.0;
+      const int gq = q0 + aq[r];
+      bool keep = agi[r] < p.m && gq < p.k;
+      if ((p.flags & DLA_A_LOWER) && gq > agi[r]) keep = false;
+      if ((p.flags & DLA_A_UPPER) && gq < agi[r]) keep = false;
+      cp_async8_zfill(&As[buf][aslot[r]], keep ? ap[r] + (long long)q0 * astep : A, keep);
+      const int hq = q0 + bq[r];
+      bool keepb = bgj[r] < p.n && hq < p.k;
+      if ((p.flags & DLA_B_UPPER) && hq > bgj[r]) keepb = false;
+      if ((p.flags & DLA_B_LOWER) && hq < bgj[r]) keepb = false;
+      cp_async8_zfill(&Bs[buf][bslot[r]], keepb ? bp[r] + (long long)q0 * bstep : B, keepb);
     }
   };
   double acc[4][4][2];
@@ -87,29 +102,28 @@ dla_gemm_kernel(const GemmP p) {
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-  if (kbeg < kend) fetch(kbeg);
-  for (int q0 = kbeg; q0 < kend; q0 += DK) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      As[(aq[r] >> 2) * (DT * 4) + ai[r] * 4 + (aq[r] & 3)] = ra[r];
-      Bs[(bq[r] >> 2) * (DT * 4) + bj[r] * 4 + (bq[r] & 3)] = rb[r];
-    }
-    __syncthreads();
-    if (q0 + DK < kend) fetch(q0 + DK);
+  for (int st = 0; st < DST - 1; st++) { if (st < nst) issue(st); asm volatile("cp.async.commit_group;" ::: "memory"); }
+  for (int st = 0; st < nst; st++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DST - 2) : "memory");
+    __syncthreads();                 // k-block st has landed for every thread; buffer (st - 1) % DST is free again
+    if (st + DST - 1 < nst) issue(st + DST - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* as = As[st % DST]; const double* bs = Bs[st % DST];
 #pragma unroll
     for (int k4 = 0; k4 < DK / 4; k4++) {
       double af[4], bf[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) af[a] = As[k4 * (DT * 4) + (wr * 32 + a * 8) * 4 + lane];
+      for (int a = 0; a < 4; a++) af[a] = as[k4 * (DT * 4) + (wr * 32 + a * 8) * 4 + lane];
 #pragma unroll
-      for (int b = 0; b < 4; b++) bf[b] = Bs[k4 * (DT * 4) + (wc * 32 + b * 8) * 4 + lane];
+      for (int b = 0; b < 4; b++) bf[b] = bs[k4 * (DT * 4) + (wc * 32 + b * 8) * 4 + lane];
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -142,52 +156,86 @@ __device__ __forceinline__ void tri_inverse_column(const double (*S)[DT + 1], do
 }
 
 // In-place Cholesky of the nb x nb (nb <= 64) diagonal block at A (lower triangle; the upper one is not touched) by one
-// CTA of 64 threads in shared memory — left-looking, thread i owns row i: column j costs two barriers of two warps and a
-// length-j dot product per row — and Y = L^-1 (64 x 64 column-major scratch, zeros above the diagonal) for the panel
-// product.  info: set to j0 + j + 1 at the first non-positive pivot (if still 0); the block is then filled with NaN.
-__global__ void __launch_bounds__(DT)
+// CTA of 256 threads in shared memory, and Y = L^-1 (64 x 64 column-major scratch, zeros above the diagonal) for the panel
+// product.  Both loops are right-looking with DEFERRED scaling, so a column costs one barrier and one sweep of
+// independent updates: trailing(i, c) -= a_ij a_cj / d_j with the unscaled column j (l_ij = a_ij / sqrt(d_j) is applied
+// once at the end); the inverse is the Gauss-Jordan elimination of [L | I] with the row scalings deferred likewise.
+// info: set to j0 + j + 1 at the first non-positive pivot (if still 0); the block is then filled with NaN.
+__global__ void __launch_bounds__(256)
 dla_chol_diag_kernel(double* Ab, int lda, int nb, int j0, double* Yb, int* infob, long long sA, long long sY) {
   extern __shared__ double dla_sm[];            // 2 x 64 x 65 doubles (opt-in dynamic shared memory)
   double (*S)[DT + 1] = reinterpret_cast<double (*)[DT + 1]>(dla_sm);
   double (*Ys)[DT + 1] = reinterpret_cast<double (*)[DT + 1]>(dla_sm + DT * (DT + 1));
-  __shared__ int bad;
   double* A = Ab + (long long)blockIdx.x * sA;
   double* Y = Yb ? Yb + (long long)blockIdx.x * sY : nullptr;
   int* info = infob + blockIdx.x;
-  const int i = threadIdx.x;
-  for (int c = 0; c < nb; c++) S[i][c] = (i < nb && i >= c) ? A[(long long)i + (long long)c * lda] : 0.0;
-  if (i == 0) bad = 0;
-  __syncthreads();
-  for (int j = 0; j < nb; j++) {
-    double t = 0.0;
-    if (i >= j && i < nb) {
-      double t0 = S[i][j], t1 = 0.0, t2 = 0.0, t3 = 0.0;
-      int q = 0;
-      for (; q + 3 < j; q += 4) {
-        t0 = fma(-S[i][q], S[j][q], t0); t1 = fma(-S[i][q + 1], S[j][q + 1], t1);
-        t2 = fma(-S[i][q + 2], S[j][q + 2], t2); t3 = fma(-S[i][q + 3], S[j][q + 3], t3);
-      }
-      for (; q < j; q++) t0 = fma(-S[i][q], S[j][q], t0);
-      t = (t0 + t1) + (t2 + t3);
-    }
-    if (i == j) { if (!(t > 0.0)) { bad = j + 1; S[j][j] = nan(""); } else S[j][j] = sqrt(t); }      // (nobody reads S[j][j] in the dots)
-    __syncthreads();
-    if (bad) break;
-    if (i > j && i < nb) S[i][j] = t / S[j][j];
-    __syncthreads();                                   // column j is complete before the next column's dot products read it
+  const int tid = threadIdx.x;
+  for (int e = tid; e < DT * DT; e += 256) {
+    const int i = e & 63, c = e >> 6;
+    S[i][c] = (i < nb && c < nb && i >= c) ? A[(long long)i + (long long)c * lda] : 0.0;
+    Ys[i][c] = (i == c) ? 1.0 : 0.0;
   }
   __syncthreads();
+  // threads as a 16 x 16 grid over (row, column) residues of the trailing block: no integer division in the column loop,
+  // the column's entries a thread needs are read once into registers
+  const int ti = tid & 15, tc = tid >> 4;
+  int bad = 0;
+  for (int j = 0; j < nb; j++) {
+    const double d = S[j][j];
+    if (!(d > 0.0)) { bad = j + 1; break; }           // uniform: every thread reads the same pivot
+    const double inv = 1.0 / d;
+    double li[4], lc[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { const int i = j + 1 + ti + 16 * a; li[a] = (i < nb) ? S[i][j] * inv : 0.0; }
+#pragma unroll
+    for (int b = 0; b < 4; b++) { const int c = j + 1 + tc + 16 * b; lc[b] = (c < nb) ? S[c][j] : 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int i = j + 1 + ti + 16 * a, c = j + 1 + tc + 16 * b;
+        if (i < nb && c <= i) S[i][c] = fma(-li[a], lc[b], S[i][c]);
+      }
+    __syncthreads();
+  }
   if (bad) {
-    if (i == 0 && *info == 0) *info = j0 + bad;
-    for (int c = 0; c < nb; c++) if (i < nb && i >= c) A[(long long)i + (long long)c * lda] = nan("");
-    if (Y) for (int e = i; e < DT * DT; e += DT) Y[e] = nan("");
+    if (tid == 0 && *info == 0) *info = j0 + bad;
+    for (int e = tid; e < nb * nb; e += 256) { const int i = e % nb, c = e / nb; if (i >= c) A[(long long)i + (long long)c * lda] = nan(""); }
+    if (Y) for (int e = tid; e < DT * DT; e += 256) Y[e] = nan("");
     return;
   }
-  for (int c = 0; c < nb; c++) if (i < nb && i >= c) A[(long long)i + (long long)c * lda] = S[i][c];
+  // l_ij = a_ij / sqrt(d_j)
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e % nb, c = e / nb;
+    if (i >= c) { const double v = (i == c) ? sqrt(S[c][c]) : S[i][c] * rsqrt(S[c][c]); A[(long long)i + (long long)c * lda] = v; }
+  }
   if (!Y) return;
-  if (i < nb) tri_inverse_column(S, Ys, nb, i);
   __syncthreads();
-  for (int c = 0; c < DT; c++) Y[i + c * DT] = (i < nb && c < nb) ? Ys[i][c] : ((i == c) ? 1.0 : 0.0);
+  for (int e = tid; e < nb * nb; e += 256) { const int i = e % nb, c = e / nb; if (i > c) S[i][c] *= rsqrt(S[c][c]); }
+  __syncthreads();
+  for (int e = tid; e < nb; e += 256) S[e][e] = sqrt(S[e][e]);
+  __syncthreads();
+  // Y = L^-1: for column j of L, rows i > j: Y[i][c] -= (L[i][j] / L[j][j]) Y~[j][c] for c <= j, with Y~[j] row j before its scaling
+  for (int j = 0; j < nb; j++) {
+    const double inv = 1.0 / S[j][j];
+    double li[4], yc[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { const int i = j + 1 + ti + 16 * a; li[a] = (i < nb) ? S[i][j] * inv : 0.0; }
+#pragma unroll
+    for (int b = 0; b < 4; b++) { const int c = tc + 16 * b; yc[b] = (c <= j) ? Ys[j][c] : 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int i = j + 1 + ti + 16 * a, c = tc + 16 * b;
+        if (i < nb && c <= j) Ys[i][c] = fma(-li[a], yc[b], Ys[i][c]);
+      }
+    __syncthreads();
+  }
+  for (int e = tid; e < DT * DT; e += 256) {
+    const int i = e & 63, c = e >> 6;
+    Y[e] = (i < nb && c < nb) ? ((i >= c) ? Ys[i][c] / S[i][i] : 0.0) : ((i == c) ? 1.0 : 0.0);
+  }
 }
 
 // Inverses of the 64 x 64 diagonal blocks of the lower-triangular L (n x n): block blockIdx.x -> out + blockIdx.x * sblk
@@ -223,11 +271,13 @@ dla_trsv_pipe_kernel(const double* __restrict__ L, int ldl, int n, double* x, in
   __shared__ double xs[DT];
   __shared__ double red[4][DT];
   __shared__ double Ds[DT][DT + 1];
+  __shared__ double rdg[DT];
   const int nblk = (n + DT - 1) / DT;
   const int p = blockIdx.x, b = TRANS ? nblk - 1 - p : p;
   const int k0 = b * DT, nb = min(DT, n - k0);
   const int tid = threadIdx.x, r = tid & 63, g = tid >> 6;
   for (int e = tid; e < nb * nb; e += 256) { const int i = e % nb, c = e / nb; Ds[i][c] = (i >= c) ? L[(long long)(k0 + i) + (long long)(k0 + c) * ldl] : 0.0; }
+  if (tid < nb) rdg[tid] = 1.0 / L[(long long)(k0 + tid) + (long long)(k0 + tid) * ldl];
   double acc = 0.0;
   for (int pj = 0; pj < p; pj++) {
     const int j = TRANS ? nblk - 1 - pj : pj, j0 = j * DT;
@@ -255,7 +305,7 @@ dla_trsv_pipe_kernel(const double* __restrict__ L, int ldl, int n, double* x, in
     for (int s = 0; s < nb; s++) {
       const int j = TRANS ? nb - 1 - s : s;
       double xj = (j < 32) ? va : vb;
-      xj = __shfl_sync(0xffffffffu, xj, j & 31) / Ds[j][j];
+      xj = __shfl_sync(0xffffffffu, xj, j & 31) * rdg[j];
       if (ra == j) va = xj;
       if (rb == j) vb = xj;
       // remaining rows: below j for the lower solve, above j for the transposed (upper) one; T(row, j) = L(row, j) or L(j, row)
@@ -292,6 +342,8 @@ __global__ void dla_symmetrize_kernel(double* A, int lda, int n) {
 
 constexpr size_t DLA_DIAG_SMEM = (size_t)2 * DT * (DT + 1) * sizeof(double);
 int dla_diag_smem_optin(gpar_ctx* ctx) {
+  if (ctx->dla_optin) return GPAR_OK;            // once per context (= per device): the attribute is sticky
+  ctx->dla_optin = true;
   CU(cudaFuncSetAttribute(dla_chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DLA_DIAG_SMEM));
   CU(cudaFuncSetAttribute(dla_tri_inv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DLA_DIAG_SMEM));
   return GPAR_OK;
@@ -333,7 +385,7 @@ int dla_potrf_batched(gpar_ctx* ctx, int n, double* A, int lda, long long sA, in
   for (int k0 = 0; k0 < n; k0 += DT) {
     const int nb = std::min(DT, n - k0), rem = n - k0 - nb;
     double* Akk = A + (size_t)k0 + (size_t)k0 * lda;
-    LAUNCH(ctx, dla_chol_diag_kernel, batch, DT, DLA_DIAG_SMEM, Akk, lda, nb, k0, rem > 0 ? Y : (double*)nullptr, dinfo, sA, (long long)DT * DT);
+    LAUNCH(ctx, dla_chol_diag_kernel, batch, 256, DLA_DIAG_SMEM, Akk, lda, nb, k0, rem > 0 ? Y : (double*)nullptr, dinfo, sA, (long long)DT * DT);
     if (rem > 0) {
       double* A21 = Akk + nb;
       // L21 = A21 L_kk^-T = A21 Y^T: one tile column, so every CTA reads exactly the rows it overwrites (in place)
@@ -379,8 +431,8 @@ int dla_trsm_left(gpar_ctx* ctx, bool trans, int n, int nrhs, const double* L, i
   if (n <= 0 || nrhs <= 0) return GPAR_OK;
   const int nblk = (n + DT - 1) / DT;
   double* ws;
-  CHK(dla_scratch(ctx, (size_t)nblk * DT * DT + (size_t)DT * nrhs, &ws));
-  double* Yd = ws; double* tmp = ws + (size_t)nblk * DT * DT;
+  CHK(dla_scratch(ctx, (size_t)nblk * DT * DT, &ws));
+  double* Yd = ws;
   // inverted diagonal blocks, block k at Yd + k * 64 * 64 (ld 64, identity-padded)
   CHK(dla_diag_smem_optin(ctx));
   LAUNCH(ctx, dla_tri_inv_diag_kernel, dim3(nblk, 1), DT, DLA_DIAG_SMEM, L, ldl, n, Yd, DT, (long long)DT * DT, 0LL, 0LL, 1);
@@ -430,5 +482,56 @@ int dla_scal(gpar_ctx* ctx, long long n, double a, double* x) {
 }
 int dla_symmetrize(gpar_ctx* ctx, int n, double* A, int lda) {
   LAUNCH(ctx, dla_symmetrize_kernel, (unsigned)(((long long)n * n + 255) / 256), 256, 0, A, lda, n);
+  return GPAR_OK;
+}
+
+namespace {
+__global__ void dla_fill_spd_kernel(double* A, int n, unsigned seed) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n * n) return;
+  const int i = (int)(e % n), j = (int)(e / n);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  unsigned h = (unsigned)(lo * 2654435761u) ^ (unsigned)(hi * 40503u) ^ seed; h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+  A[e] = (double)(h & 0xffff) / 65536.0 * 0.01 + (i == j ? 1.0 + 0.01 * n : 0.0);      // symmetric, diagonally dominant
+}
+}  // namespace
+
+// Diagnostics: device time (ms, CUDA events, best of 3) of the dense routines at order n on a synthetic SPD matrix:
+// out[0] potrf, [1] trtri, [2] gemm V G (triangular A), [3] gemm (V G) V' (lower tiles), [4] full gemm, [5] trsv (forward),
+// [6] trsv (transposed).  Measurement support (profiles/), not part of the reference's interface.
+extern "C" int gpar_dense_bench(gpar_ctx* ctx, int32_t n, double* out7) {
+  if (!ctx || !out7 || n < 1) return GPAR_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  const size_t nn = (size_t)n * n;
+  CU(ctx->dense.reserve((5 * nn + 2 * (size_t)n) * sizeof(double) + 64));
+  CU(ctx->info.reserve(4 * sizeof(int)));
+  double* A = ctx->dense.as<double>(); double* Lm = A + nn; double* V = Lm + nn; double* T1 = V + nn; double* T2 = T1 + nn; double* x = T2 + nn;
+  LAUNCH(ctx, dla_fill_spd_kernel, (unsigned)((nn + 255) / 256), 256, 0, A, (int)n, 12345u);
+  cudaEvent_t e0 = ctx->pev[0], e1 = ctx->pev[3];
+  auto timeit = [&](int slot, auto fn) -> int {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      CU(cudaMemcpyAsync(Lm, A, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      if (slot > 0) CHK(dla_potrf(ctx, n, Lm, n, ctx->info.as<int>()));
+      if (slot > 1) CHK(dla_trtri(ctx, n, Lm, n, V, n));
+      CU(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), ctx->stream));
+      CU(cudaEventRecord(e0, ctx->stream));
+      CHK(fn());
+      CU(cudaEventRecord(e1, ctx->stream));
+      CU(cudaEventSynchronize(e1));
+      float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    out7[slot] = best;
+    return GPAR_OK;
+  };
+  CHK(timeit(0, [&]() { return dla_potrf(ctx, n, Lm, n, ctx->info.as<int>()); }));
+  CHK(timeit(1, [&]() { return dla_trtri(ctx, n, Lm, n, V, n); }));
+  CHK(timeit(2, [&]() { return dla_gemm(ctx, false, false, n, n, n, 1.0, V, n, A, n, 0.0, T1, n, DLA_A_LOWER); }));
+  CHK(timeit(3, [&]() { return dla_gemm(ctx, false, true, n, n, n, 1.0, T1, n, V, n, 0.0, T2, n, DLA_B_UPPER | DLA_LOWER_TILES); }));
+  CHK(timeit(4, [&]() { return dla_gemm(ctx, false, false, n, n, n, 1.0, A, n, A, n, 0.0, T1, n, 0); }));
+  CHK(timeit(5, [&]() { return dla_trsv(ctx, false, n, Lm, n, x, 1.0); }));
+  CHK(timeit(6, [&]() { return dla_trsv(ctx, true, n, Lm, n, x, 1.0); }));
+  ctx->phase_valid = false;
   return GPAR_OK;
 }

@@ -139,8 +139,10 @@ __global__ void __launch_bounds__(128, Scalar<F>::NC == 1 ? KF_MIN_BLOCKS : 1)
 kf_chunk_summary_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride) {
   typedef FiltElem<D, F> E;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (c >= l0.P) return;
+  // threads are numbered over (sequence, chunk) jointly: no lane idles when the chunks of a sequence do not fill whole blocks
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= (int64_t)batch * l0.P) return;
+  const int b = (int)(gidx / l0.P), c = (int)(gidx % l0.P);
   E e;
   if (c >= nC) { e.set_identity(); store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c); return; }
   const int pb = sp.nparam == 1 ? 0 : b;
@@ -220,8 +222,9 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
                        int64_t ystride, double* __restrict__ fstate) {
   typedef Scalar<F> SC;
   constexpr int NC = SC::NC;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (c >= nC) return;
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (sequence, chunk) jointly, as in the summary pass
+  if (gidx >= (int64_t)batch * nC) return;
+  const int b = (int)(gidx / nC), c = (int)(gidx % nC);
   const int pb = sp.nparam == 1 ? 0 : b;
   const F il = 1.0 / Seed<F>::make(sp.l[pb], sp.dir_l), s = Seed<F>::make(sp.s[pb], sp.dir_s), noise = Seed<F>::make(sp.noise[pb], sp.dir_n);
   F P0[NSYM<D>]; lgssm_pinf<D>(P0);
@@ -551,6 +554,7 @@ struct LgssmOut {
   double* dlml = nullptr; double* dalpha = nullptr; double* dtable = nullptr;    // tangent outputs (Dual runs)
   double* fstate = nullptr;      // per sequence (m, P) after the last step
   int64_t ystride = 0;           // distance between sequences in y / alpha (0: N)
+  bool ybroadcast = false;       // every "sequence" of the batch reads the SAME y (hyper-parameter candidates on one sequence)
 };
 
 template <int D, class F>
@@ -558,7 +562,8 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   constexpr int NC = Scalar<F>::NC;
   typedef FiltElem<D, F> FE;
   const bool smooth = o.mean != nullptr;
-  const int64_t ystride = o.ystride > 0 ? o.ystride : N;
+  if (o.ybroadcast && (o.alpha || o.mean)) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: candidates on one sequence yield log-pdfs only");
+  const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
   // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel
   const int64_t total_steps = N * (int64_t)batch;
   int L = total_steps <= (1 << 19) ? 8 : (total_steps <= (1 << 21) ? 16 : 32);
@@ -579,10 +584,11 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   double* fs = smooth ? ctx->kal_b.as<double>() : nullptr;
   const Level none{nullptr, 0, 0};
   const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
-  dim3 g1((f0.P + 127) / 128, batch);
+  const unsigned g1 = (unsigned)(((int64_t)batch * f0.P + 127) / 128);
   LAUNCH(ctx, (kf_chunk_summary_kernel<D, F>), g1, 128, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride);
   CHK(run_scan<FE>(ctx, fp, batch));
-  dim3 g3((nC + 127) / 128, batch);
+  const unsigned g3 = (unsigned)(((int64_t)batch * nC + 127) / 128);
+  dim3 g3b((nC + 127) / 128, batch);
   if constexpr (NC == 1) {
     if (smooth) {
       const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
@@ -590,7 +596,7 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
              (double*)nullptr, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr);
       if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
       CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
-      LAUNCH(ctx, ks_backward_kernel<D>, g3, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var, o.table);     // (smoother: o.table = backward table)
+      LAUNCH(ctx, ks_backward_kernel<D>, g3b, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var, o.table);     // (smoother: o.table = backward table)
     } else {
       LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
              o.table, (double*)nullptr, (double*)nullptr, ystride, o.fstate);
@@ -1709,7 +1715,8 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
   CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
   if (t == ctx->t.as<double>()) sp.reg_dt = ctx->t_reg_dt;
   LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums;
-  if (!rvec && sp.reg_dt > 0.0) {       // regular grid, scalar noise: steady-state path when every model converges early
+  o.ybroadcast = ctx->y_broadcast;
+  if (!rvec && sp.reg_dt > 0.0 && !o.ybroadcast) {       // regular grid, scalar noise: steady-state path when every model converges early
     bool used = false;
     switch (kind) {      // long sequences: single-pass burn-in scheme
       case GPAR_MATERN12: CHK(lgssm_run_steady_long<1>(ctx, sp, batch, N, y, o, &used)); break;
@@ -1779,8 +1786,11 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   if (!ctx) return GPAR_ERR_INVALID;
   if (!theta || !lml) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: theta and lml must not be NULL");
   CHK(check_seq(ctx, "lgssm_logpdf"));
-  const int batch = ctx->ybatch;
-  if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: batch_theta=%d must be 1 or the outputs batch %d", batch_theta, batch);
+  // one resident sequence, several parameter sets: hyper-parameter CANDIDATES (simplex vertices x restarts of
+  // temporal_gp_inference.jl:82) evaluated in one pass, every candidate reading the same y
+  const bool candidates = ctx->ybatch == 1 && batch_theta > 1;
+  const int batch = candidates ? batch_theta : ctx->ybatch;
+  if (batch_theta != 1 && batch_theta != batch) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm_logpdf: batch_theta=%d must be 1 or the outputs batch %d (or any number with ONE resident sequence)", batch_theta, batch);
   CU(cudaSetDevice(ctx->device));
   CallTimer timer(ctx); ctx->phase_valid = false; gpar_drop_result(ctx);
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
@@ -1794,10 +1804,10 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
       rc = lgssm_filter_shared_seqmajor(ctx, kernel, hl[0], hs[0], hn[0], ctx->Nt, batch, ctx->t.as<double>(), ctx->y.as<double>(),
                                         ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>());
     } else {
-      ctx->ss_deferred_ok = true;
+      ctx->ss_deferred_ok = true; ctx->y_broadcast = candidates;
       rc = lgssm_run(ctx, kernel, hl.data(), hs.data(), hn.data(), batch_theta, batch, ctx->Nt, ctx->t.as<double>(), ctx->y.as<double>(),
                      ctx->has_rvec ? ctx->rvec.as<double>() : nullptr, nullptr, ctx->kal_d.as<double>(), nullptr, nullptr, nullptr, nullptr);
-      ctx->ss_deferred_ok = false;
+      ctx->ss_deferred_ok = false; ctx->y_broadcast = false;
     }
     CHK(rc);
     timer.stop();

@@ -22,7 +22,11 @@ class OptimResult:
         self.stopped_by_time = stopped_by_time
 
 
-def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_trace=False):
+def _simplex_steps(x0, iterations, g_tol, time_limit, show_trace):
+    """The algorithm as a coroutine: yields the list of points it needs evaluated next, receives their values, and
+    finally returns the OptimResult.  `optimize` drives it with a scalar objective; `optimize_batch` drives several
+    instances in lockstep so that one BATCHED objective call (gpar_exact_logpdf_batch, gpar_lgssm_logpdf with one
+    parameter set per candidate) serves all of them — simplex vertices x restarts evaluated concurrently."""
     x0 = np.asarray(x0, dtype=np.float64)
     n = x0.size
     m = n + 1
@@ -30,7 +34,7 @@ def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_t
     simplex = np.tile(x0, (m, 1))
     for i in range(n):
         simplex[i + 1, i] = 1.5 * x0[i] + 0.025          # AffineSimplexer: (1 + b) x_i + a
-    fv = np.array([f(v) for v in simplex])
+    fv = np.array((yield [v.copy() for v in simplex]), dtype=np.float64)
     calls = m
     t0 = time.time()
     it = 0
@@ -48,10 +52,10 @@ def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_t
         it += 1
         centroid = simplex[:-1].mean(axis=0)
         xr = centroid + alpha * (centroid - simplex[-1])
-        fr = f(xr); calls += 1
+        fr = (yield [xr])[0]; calls += 1
         if fr < fv[0]:
             xe = centroid + beta * (xr - centroid)
-            fe = f(xe); calls += 1
+            fe = (yield [xe])[0]; calls += 1
             if fe < fr:
                 simplex[-1], fv[-1] = xe, fe
             else:
@@ -61,24 +65,58 @@ def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_t
         else:
             if fr < fv[-1]:       # outside contraction
                 xc = centroid + gamma * (xr - centroid)
-                fc = f(xc); calls += 1
+                fc = (yield [xc])[0]; calls += 1
                 ok = fc <= fr
             else:                 # inside contraction
                 xc = centroid - gamma * (xr - centroid)
-                fc = f(xc); calls += 1
+                fc = (yield [xc])[0]; calls += 1
                 ok = fc < fv[-1]
             if ok:
                 simplex[-1], fv[-1] = xc, fc
-            else:                 # shrink towards the best vertex
+            else:                 # shrink towards the best vertex: the n new vertices are one batch
                 for i in range(1, m):
                     simplex[i] = simplex[0] + delta * (simplex[i] - simplex[0])
-                    fv[i] = f(simplex[i]); calls += 1
+                fv[1:] = (yield [simplex[i].copy() for i in range(1, m)]); calls += m - 1
         if show_trace:
             print("%6d   %.6e" % (it, float(np.min(fv))))
     best = int(np.argmin(fv))
     xbest, fbest = simplex[best].copy(), float(fv[best])
     centroid = simplex.mean(axis=0)
-    fcen = f(centroid); calls += 1
+    fcen = (yield [centroid])[0]; calls += 1
     if fcen < fbest:
         xbest, fbest = centroid, float(fcen)
     return OptimResult(xbest, fbest, it, calls, converged, stopped_by_time)
+
+
+def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_trace=False):
+    gen = _simplex_steps(x0, iterations, g_tol, time_limit, show_trace)
+    pts = next(gen)
+    while True:
+        try:
+            pts = gen.send([f(p) for p in pts])
+        except StopIteration as e:
+            return e.value
+
+
+def optimize_batch(fbatch, X0, iterations=1000, g_tol=1e-8):
+    """len(X0) independent Nelder-Mead runs (restarts) in lockstep: every round, the points all runs need next go to ONE
+    call `fbatch(points (K, n)) -> values (K,)`.  Each run performs exactly the operations `optimize` would (same minimum,
+    minimiser, iteration and call counts); only the evaluation is shared.  -> list of OptimResult."""
+    gens = [_simplex_steps(x, iterations, g_tol, float("nan"), False) for x in X0]
+    pending = {k: next(g) for k, g in enumerate(gens)}
+    results = [None] * len(gens)
+    while pending:
+        keys = sorted(pending)
+        pts = np.array([p for k in keys for p in pending[k]], dtype=np.float64)
+        vals = np.asarray(fbatch(pts), dtype=np.float64)
+        pos = 0
+        nxt = {}
+        for k in keys:
+            cnt = len(pending[k])
+            try:
+                nxt[k] = gens[k].send(list(vals[pos:pos + cnt]))
+            except StopIteration as e:
+                results[k] = e.value
+            pos += cnt
+        pending = nxt
+    return results

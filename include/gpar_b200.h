@@ -62,6 +62,10 @@ int gpar_last_profile(const gpar_ctx* ctx, double* phase_ms, int32_t n);
  * (1 GiB each way, read + write bytes).  Any pointer may be NULL.  ~60 ms. */
 int gpar_measure_peaks(gpar_ctx* ctx, double* dmma_tflops, double* dfma_tflops, double* hbm_copy_gbs);
 
+/* Diagnostics: device time (ms) of the library's dense M x M routines at order n on a synthetic SPD matrix — out7 =
+ * [potrf, trtri, triangular gemm, lower-tile gemm, full gemm, trsv, transposed trsv].  Measurement support only. */
+int gpar_dense_bench(gpar_ctx* ctx, int32_t n, double* out7);
+
 /* ---- resident data (host -> device copies) ------------------------------------------------ */
 /* ColVecs inputs, src/gp/dtc.jl:26-27, gpar_scaled_inference.jl:38-40 (to_ColVecs, util.jl:16-31) */
 int gpar_set_inputs(gpar_ctx* ctx, const double* X, int32_t D, int64_t N);
@@ -152,7 +156,9 @@ int gpar_scaled_predict(gpar_ctx* ctx, int k_time, int k_out, const double param
  * theta = unpack_gp parameters (log l, log var, log sigma).
  * gpar_lgssm_logpdf: `batch_theta` parameter sets (theta + 3*b); with batch_theta == outputs batch,
  *   sequence b uses theta b (independent models); with batch_theta == 1 all sequences share it.
- *   lml: one value per sequence (temporal_gp_inference.jl:78). */
+ *   lml: one value per sequence (temporal_gp_inference.jl:78).
+ *   With ONE resident sequence and batch_theta > 1 the parameter sets are hyper-parameter CANDIDATES (simplex vertices x
+ *   restarts of the Nelder-Mead loop, temporal_gp_inference.jl:82) evaluated on that sequence in one pass: lml[batch_theta]. */
 int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t batch_theta, double* lml);
 /* The same log-pdf with its gradient (NEW — the reference's optimisers are derivative-free,
  * temporal_gp_inference.jl:82): grad + 3*b = d lml[b] / d theta of the parameter set sequence b uses
@@ -170,6 +176,12 @@ int gpar_lgssm_smooth(gpar_ctx* ctx, int kernel, const double theta[3], double* 
  * ntheta = 5: GPAR kernel time_var^2 k_time(|dx_1|/time_l) + out_var^2 k_out(||dx_2:D||/out_l)
  * (optimized.jl:132-154).  logpdf per resident output sequence. */
 int gpar_exact_logpdf(gpar_ctx* ctx, int k_time, int k_out, const double* theta, int32_t ntheta, double* lml);
+/* `ncand` hyper-parameter candidates at once (NEW): thetas is ntheta x ncand column-major — e.g. the vertices
+ * of a Nelder-Mead simplex times the restarts of optimized.jl:45,164 — evaluated on the SAME resident data in one launch
+ * (one CTA per candidate when N <= 200).  lml[c * batch + b]; codes (nullable, ncand): 0, or non-zero where the candidate's
+ * Cholesky failed (its lml entries are NaN) — with codes == NULL such a failure returns GPAR_ERR_NOT_POSDEF. */
+int gpar_exact_logpdf_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int32_t ntheta, int32_t ncand,
+                            double* lml, int32_t* codes);
 /* posterior marginals at Xs (D x Ns ColVecs): mean and variance (optimized.jl:94,236; eeg.jl:185-208) */
 int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* theta, int32_t ntheta,
                          const double* Xs, int64_t Ns, double* mean, double* var);

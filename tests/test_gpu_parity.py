@@ -919,3 +919,68 @@ def test_q_u_and_draws_dense_routines_ragged_m(ctx, m):
     assert np.max(np.abs(Dinv - D0)) <= tol * max(1.0, np.max(np.abs(D0)))
     W, E = ctx.sample_q_u(3, 3, params, 99, 16, return_host=True)
     assert np.max(np.abs(np.triu(U_u) @ W - E)) <= 1e-8 * max(1.0, np.max(np.abs(E))) * max(1.0, np.linalg.cond(U0))
+
+
+def test_exact_logpdf_batch_of_candidates(ctx):
+    """gpar_exact_logpdf_batch: the simplex vertices x restarts of optimized.jl:45,164 in ONE launch (one CTA
+    per candidate, packed Cholesky in shared memory) — every candidate against the oracle, and against the single-candidate
+    entry point; a candidate whose Cholesky fails is flagged in `codes` without failing the others."""
+    rng = np.random.default_rng(77)
+    n, D, B = 156, 5, 37
+    X = rng.normal(size=(n, D)); X[:, 0] = np.sort(rng.uniform(0, 2, n)); Y = rng.normal(size=(2, n))
+    ctx.set_inputs(X); ctx.set_outputs(Y)
+    thetas = rng.uniform(-1.0, 0.8, size=(B, 5)); thetas[:, 4] = rng.uniform(-2.5, -0.5, B)
+    lml, codes = ctx.exact_logpdf_batch(3, 3, thetas)
+    assert lml.shape == (B, 2) and np.all(codes == 0)
+    for c in range(B):
+        tl, tv, ol, ov, sg = oracle.unpack_gpar(thetas[c])
+        K = oracle.gpar_kernel_matrix(3, 3, X, X, tl, tv, ol, ov)
+        for b in range(2):
+            ref = oracle.exact_logpdf(K, sg ** 2, Y[b])
+            assert abs(lml[c, b] - ref) <= RTOL * abs(ref), (c, b)
+        assert np.array_equal(ctx.exact_logpdf(3, 3, thetas[c]), lml[c])
+    # 3-parameter GP on all features, EQ, through the same path
+    th3 = rng.uniform(-1.0, 0.5, size=(9, 3))
+    l3, c3 = ctx.exact_logpdf_batch(0, 0, th3)
+    for c in range(9):
+        l, var, sig = oracle.unpack_gp(th3[c])
+        ref = oracle.exact_logpdf(oracle.pairwise(0, X, X, l=l, s=var ** 2), sig ** 2, Y[0])
+        assert abs(l3[c, 0] - ref) <= RTOL * abs(ref)
+    # a numerically indefinite candidate among good ones
+    xs = np.linspace(0, 1, 150)[:, None]
+    ctx.set_inputs(xs); ctx.set_outputs(np.ones(150))
+    th = np.array([[-2.0, 0.0, -1.0], [3.0, 12.0, -40.0], [-1.0, 0.3, -0.5]])
+    lm, cd = ctx.exact_logpdf_batch(0, 0, th)
+    assert cd[0] == 0 and cd[2] == 0 and cd[1] != 0 and np.isnan(lm[1, 0]) and np.isfinite(lm[0, 0]) and np.isfinite(lm[2, 0])
+
+
+def test_lgssm_logpdf_candidates_on_one_sequence(ctx):
+    """gpar_lgssm_logpdf with ONE resident sequence and many parameter sets: the candidates of the Nelder-Mead loop
+    temporal_gp_inference.jl:69-82 in one pass (every candidate reads the same y).  Against the C oracle per candidate,
+    scalar noise and the 1e10 noise vector; and a batched Nelder-Mead over restarts reaches the optima of separate runs."""
+    from gpar_at_scale_b200 import neldermead
+    rng = np.random.default_rng(78)
+    n, B = 8496, 41
+    t = np.cumsum(rng.exponential(1 / 30, n)); y = np.sin(0.7 * t) + 0.4 * rng.normal(size=n)
+    ths = np.stack([np.log(rng.uniform(0.05, 5, B)), np.log(rng.uniform(0.3, 3, B)), np.log(rng.uniform(0.05, 1, B))], axis=1)
+    ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+    for kind in (1, 2, 3):
+        lml = ctx.lgssm_logpdf(kind, ths)
+        assert lml.shape == (B,)
+        for c in range(B):
+            l, var, sig = oracle.unpack_gp(ths[c])
+            ref = cport.kalman_logpdf(kind, t, y, l, var ** 2, sig ** 2)
+            assert abs(lml[c] - ref) <= RTOL * abs(ref), (kind, c)
+    rv = np.full(n, 0.09); rv[rng.choice(n, 800, replace=False)] = 1e10
+    ctx.set_noise_vector(rv)
+    lml = ctx.lgssm_logpdf(3, ths[:7])
+    for c in range(7):
+        l, var, sig = oracle.unpack_gp(ths[c])
+        ref = cport.kalman_logpdf(3, t, y, l, var ** 2, rv)
+        assert abs(lml[c] - ref) <= RTOL * abs(ref)
+    ctx.set_noise_vector(None)
+    X0 = rng.random((6, 3))
+    res = neldermead.optimize_batch(lambda P: -ctx.lgssm_logpdf(3, P), X0, iterations=40)
+    for k in range(6):
+        one = neldermead.optimize(lambda th: -ctx.lgssm_logpdf(3, th)[0], X0[k], iterations=40)
+        assert abs(res[k].minimum - one.minimum) <= 1e-9 * abs(one.minimum) and res[k].f_calls == one.f_calls
