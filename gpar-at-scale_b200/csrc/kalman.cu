@@ -97,7 +97,9 @@ scan_up_kernel(Level cur, Level up, int batch) {
     if (lane == 0) { Elem id; id.set_identity(); store_elem(id, up.base, (int64_t)batch * up.P, (int64_t)b * up.P + tile); }
     return;
   }
-  Elem e; load_elem(e, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + tile * 32 + lane);
+  Elem e;
+  if (tile * 32 + lane < cur.n) load_elem(e, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + tile * 32 + lane);
+  else e.set_identity();                  // padding slots need not have been written
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     Elem o;
@@ -130,6 +132,12 @@ struct StepIn {
   __device__ __forceinline__ void load(const double* __restrict__ tp, const double* __restrict__ yp, const double* __restrict__ rp,
                                        int64_t k, int64_t N, bool reg) {
     if (k < N) { y = __ldg(yp + k); if (!reg) t = __ldg(tp + k); if (rp) r = __ldg(rp + k); }
+  }
+  // the same without a branch around the loads: indices beyond the sequence re-read its last step
+  __device__ __forceinline__ void load_clamped(const double* __restrict__ tp, const double* __restrict__ yp, const double* __restrict__ rp,
+                                               int64_t k, int64_t N, bool reg) {
+    k = k < N ? k : N - 1;
+    y = __ldg(yp + k); if (!reg) t = __ldg(tp + k); if (rp) r = __ldg(rp + k);
   }
 };
 
@@ -547,6 +555,194 @@ int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
   return GPAR_OK;
 }
 
+// ---- log-pdf only: ONE pass over the data ------------------------------------------------------------
+// The value temporal_gp_inference.jl:78 needs is a sum over steps, and a chunk's share of it is a closed
+// form of the chunk's filtering element and the state the chunk starts from, so the second walk over the
+// data (P3) is not needed.  Conditional on the start state x0 the chunk's observations have
+//   log p(y_c | x0) = -1/2 [ sum_k log 2 pi S0_k + sum_k (v0_k - h_k' x0)^2 / S0_k ]
+//                   = -1/2 (n_c log 2 pi + sum log S0 + sum v0^2/S0) + eta' x0 - 1/2 x0' J x0,
+// where (S0, v0) are the innovation variances / innovations of the filter started from x0 = 0 EXACTLY
+// known and (eta, J) are the element's information pair — everything P1 accumulates anyway.  With
+// x0 ~ N(m, P) from the scanned prefix and P = Lc Lc', B = I + Lc' J Lc, a = Lc'(eta - J m):
+//   log p(y_c | y_<c) = log p(y_c | x0 = m) + 1/2 a' B^-1 a - 1/2 log det B.
+// B has eigenvalues >= 1, so its Cholesky factorisation is unconditionally stable.  The two sums the
+// callers use (sum log S_k and sum alpha_k^2 of the real filter) are recovered exactly: the determinant
+// and the quadratic form of the chunk's marginal covariance factor both ways.
+// kf_chunk_element: P1 in deviation form (dC = C - P_inf: one congruence per step, no Q), threads numbered
+// densely over (sequence, chunk); aux rows (field-major, stride batch * nC): sum log S0, sum v0^2/S0, eta, J.
+template <int D, int TPB, int MINB, bool REG>
+__global__ void __launch_bounds__(TPB, MINB)
+kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
+                        SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux) {
+  typedef FiltElem<D> E;
+  const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
+  if (gidx >= ntot) return;
+  const int b = (int)(gidx / nC), c = (int)(gidx % nC);
+  const int pb = sp.nparam == 1 ? 0 : b;
+  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
+  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
+  E e;
+  double* Phi = e.v; double* bv = e.v + E::OB; double* dC = e.v + E::OC; double* eta = e.v + E::OE; double* J = e.v + E::OJ;
+  e.set_identity();
+  if (c == 0) {           // the prior: x_0 ~ N(0, P_inf) whatever came before
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Phi[i] = 0.0;
+  } else {                // start state known exactly: C = 0
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) dC[i] = -P0[i];
+  }
+  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
+  double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
+  const double* yb = y + (int64_t)b * ystride;
+  constexpr bool reg = REG;
+  double A[D * D];
+  if constexpr (REG) lgssm_transition<D>(sp.reg_dt * il, A);
+  double sum_q = 0.0, prodS = 1.0;
+  int eacc = 0;            // sum log S = log(prodS) + eacc log 2: the exponent of the running product is peeled off every step
+  StepIn in0, in1;
+  in0.load_clamped(t, yb, rvec, k0, N, reg); in1.load_clamped(t, yb, rvec, k0 + 1, N, reg);
+  // irregular grid: (a, e = exp(-lam a)) of the step about to run; the pair of the step after it is formed inside the
+  // iteration, where its long dependent chain (range reduction + polynomial) overlaps the state recursion
+  double a_cur = 0.0, e_cur = 1.0;
+  if constexpr (!REG) { a_cur = (in0.t - tprev) * il; e_cur = exp_nonpos(-lgssm_lambda<D>() * a_cur); }
+  for (int64_t k = k0; k < k1; k++) {
+    double T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D];
+    const StepIn cur = in0; in0 = in1; in1.load_clamped(t, yb, rvec, k + 2, N, reg);
+    if constexpr (!REG) {
+      lgssm_transition_from<D>(a_cur, e_cur, A);
+      a_cur = (in0.t - cur.t) * il;                    // (beyond the sequence: the clamped load gives a = 0, never used)
+      e_cur = exp_nonpos(-lgssm_lambda<D>() * a_cur);
+    } else if (k <= 1) lgssm_transition<D>((k == 0 ? 1.0 : sp.reg_dt) * il, A);     // step 0 follows the t[0] - 1 prefix
+    matmul<D>(A, Phi, T);
+    matvec<D>(A, bv, u);
+    asat<D>(A, dC, Cn);
+#pragma unroll
+    for (int i = 0; i < D; i++) col[i] = SYM(Cn, i, 0) + SYM(P0, i, 0);
+    const double S = col[0] + (rvec ? cur.r : noise);
+    const double iS = rcp_pos(S);
+    const double r = cur.y - u[0], w = iS * r;
+#pragma unroll
+    for (int i = 0; i < D; i++) Kg[i] = col[i] * iS;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      eta[i] = fma(w, T[i], eta[i]);
+      const double hi = iS * T[i];
+#pragma unroll
+      for (int j = i; j < D; j++) SYM(J, i, j) = fma(hi, T[j], SYM(J, i, j));
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+      for (int j = 0; j < D; j++) Phi[i * D + j] = fma(-Kg[i], T[j], T[i * D + j]);
+      bv[i] = fma(Kg[i], r, u[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = i; j < D; j++) SYM(dC, i, j) = fma(-Kg[i], col[j], SYM(Cn, i, j));
+    sum_q = fma(w, r, sum_q);
+    prodS *= S;         // S > 0 and normal: mantissa stays in [1, 2), the exponent goes to the integer accumulator
+    const int hi = __double2hiint(prodS);
+    eacc += (hi >> 20) - 1023;
+    prodS = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(prodS));
+  }
+  const double sum_logS = fma((double)eacc, 0.693147180559945309417232121458, log(prodS));
+  aux[gidx] = sum_logS; aux[ntot + gidx] = sum_q;
+#pragma unroll
+  for (int i = 0; i < D; i++) aux[(2 + i) * ntot + gidx] = eta[i];
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) aux[(2 + D + i) * ntot + gidx] = J[i];
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) dC[i] += P0[i];
+  store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c);
+}
+
+// Every chunk's share of (sum log S, sum alpha^2) from its aux row and the scanned state it starts from;
+// block (x, b) sums 128 chunks of sequence b in fixed order -> part2[b][x][2].
+template <int D>
+__global__ void __launch_bounds__(128)
+kf_chunk_lml_kernel(Level l0, Level l1, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  double r0 = 0.0, r1 = 0.0;
+  if (c < nC) {
+    const int64_t ntot = (int64_t)batch * nC, idx = (int64_t)b * nC + c;
+    r0 = aux[idx]; r1 = aux[ntot + idx];
+    if (c > 0) {
+      typedef FiltElem<D> E;
+      const E pre = inclusive_prefix<E>(l0, l1, batch, b, c - 1);
+      const double* m = pre.v + E::OB; const double* P = pre.v + E::OC;
+      double eta[D], J[NSYM<D>];
+#pragma unroll
+      for (int i = 0; i < D; i++) eta[i] = aux[(2 + i) * ntot + idx];
+#pragma unroll
+      for (int i = 0; i < NSYM<D>; i++) J[i] = aux[(2 + D + i) * ntot + idx];
+      // P = Lc Lc' (lower; a non-positive pivot — P singular to working precision — zeroes its column)
+      double Lc[D * D];
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        double inv = 0.0;
+#pragma unroll
+        for (int i = j; i < D; i++) {
+          double v = SYM(P, i, j);
+#pragma unroll
+          for (int q = 0; q < j; q++) v -= Lc[i * D + q] * Lc[j * D + q];
+          if (i == j) { const double d = v > 0.0 ? sqrt(v) : 0.0; Lc[j * D + j] = d; inv = d > 0.0 ? 1.0 / d : 0.0; }
+          else Lc[i * D + j] = v * inv;
+        }
+      }
+      double Jm[D], a[D], W[D * D], Bm[NSYM<D>];
+      symvec<D>(J, m, Jm);
+      double em = 0.0, mJm = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) { em = fma(eta[i], m[i], em); mJm = fma(m[i], Jm[i], mJm); }
+#pragma unroll
+      for (int j = 0; j < D; j++) { double v = 0.0;
+#pragma unroll
+        for (int i = j; i < D; i++) v = fma(Lc[i * D + j], eta[i] - Jm[i], v);
+        a[j] = v; }
+#pragma unroll
+      for (int i = 0; i < D; i++)           // W = J Lc
+#pragma unroll
+        for (int j = 0; j < D; j++) { double v = 0.0;
+#pragma unroll
+          for (int q = j; q < D; q++) v = fma(SYM(J, i, q), Lc[q * D + j], v);
+          W[i * D + j] = v; }
+#pragma unroll
+      for (int i = 0; i < D; i++)           // B = I + Lc' W (symmetric)
+#pragma unroll
+        for (int j = i; j < D; j++) { double v = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = i; q < D; q++) v = fma(Lc[q * D + i], W[q * D + j], v);
+          SYM(Bm, i, j) = v; }
+      // B = Lb Lb': log det B and |Lb^-1 a|^2
+      double Lb[D * D], z[D], det = 1.0, zz = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        double inv = 0.0;
+#pragma unroll
+        for (int i = j; i < D; i++) {
+          double v = SYM(Bm, i, j);
+#pragma unroll
+          for (int q = 0; q < j; q++) v -= Lb[i * D + q] * Lb[j * D + q];
+          if (i == j) { det *= v; const double d = sqrt(v); Lb[j * D + j] = d; inv = 1.0 / d; }
+          else Lb[i * D + j] = v * inv;
+        }
+        double v = a[j];
+#pragma unroll
+        for (int q = 0; q < j; q++) v -= Lb[j * D + q] * z[q];
+        z[j] = v * inv; zz = fma(z[j], z[j], zz);
+      }
+      r0 += log(det);
+      r1 += mJm - 2.0 * em - zz;
+    }
+  }
+  r0 = block_sum(r0, sh); r1 = block_sum(r1, sh);
+  if (threadIdx.x == 0) { part2[((int64_t)b * gridDim.x + blockIdx.x) * 2] = r0; part2[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r1; }
+}
+
 // Outputs of one filter / smoother run (device pointers, all nullable except lml or sums).
 struct LgssmOut {
   double* alpha = nullptr; double* lml = nullptr; double* mean = nullptr; double* var = nullptr;
@@ -557,12 +753,74 @@ struct LgssmOut {
   bool ybroadcast = false;       // every "sequence" of the batch reads the SAME y (hyper-parameter candidates on one sequence)
 };
 
+// chunk length of the one-pass log-pdf: the element pass should fill the device in whole waves of resident
+// threads (every thread walks the same number of steps, so a partly filled last wave costs a full one)
+int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads) {
+  const int64_t total = N * (int64_t)batch;
+  if (total <= (1 << 19)) return 8;
+  if (total <= (1 << 21)) return 16;
+  int64_t L = 32;
+  for (int w = 1; w <= 4096; w++) {
+    const int64_t nCmax = w * resident_threads / batch;
+    if (nCmax < 1) continue;
+    L = (N + nCmax - 1) / nCmax;
+    if (L <= 192) break;
+  }
+  return (int)std::max<int64_t>(L, 32);
+}
+
+template <int D>
+int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec,
+                         const LgssmOut& o) {
+  typedef FiltElem<D> FE;
+  const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
+  int variant = 0;
+  if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
+  const int tpb = variant == 2 ? 64 : 128, minb = variant == 1 ? 3 : (variant == 2 ? 8 : (variant == 3 ? 5 : 4));
+  int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
+  if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
+  const int nC = (int)((N + L - 1) / L);
+  LevelPlan fp = plan_levels(nC, FE::NFD, batch);
+  const int64_t ntot = (int64_t)batch * nC;
+  const int nblk = (nC + 127) / 128;
+  constexpr int NAUX = 2 + D + NSYM<D>;
+  CU(ctx->kal_a.reserve((fp.doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk) * sizeof(double)));
+  double* base = ctx->kal_a.as<double>();
+  bind_levels(fp, base, FE::NFD, batch);
+  double* aux = base + fp.doubles;
+  double* part2 = aux + (size_t)NAUX * ntot;
+  const Level none{nullptr, 0, 0};
+  const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
+  const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
+#define KF1_LAUNCH(TPB_, MINB_)                                                                                              \
+  do {                                                                                                                      \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
+  } while (0)
+  switch (variant) {
+    case 1: KF1_LAUNCH(128, 3); break;
+    case 2: KF1_LAUNCH(64, 8); break;
+    case 3: KF1_LAUNCH(128, 5); break;
+    default: KF1_LAUNCH(128, 4); break;
+  }
+#undef KF1_LAUNCH
+  if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
+  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, nC, batch, aux, part2);
+  LAUNCH(ctx, lml_reduce_kernel<1>, batch, 64, 0, part2, nblk, N, o.lml, (double*)nullptr, o.sums);
+  return GPAR_OK;
+}
+
 template <int D, class F>
 int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec, const LgssmOut& o) {
   constexpr int NC = Scalar<F>::NC;
   typedef FiltElem<D, F> FE;
   const bool smooth = o.mean != nullptr;
   if (o.ybroadcast && (o.alpha || o.mean)) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: candidates on one sequence yield log-pdfs only");
+  if constexpr (NC == 1) {      // nothing per step asked for: the log-pdf needs one pass over the data
+    bool onepass = !smooth && !o.alpha && !o.table && !o.fstate;
+    if (const char* e = getenv("GPAR_KF_ONEPASS")) onepass = onepass && atoi(e) != 0;       // testing knob: 0 = three-phase path
+    if (onepass) return lgssm_logpdf_onepass<D>(ctx, sp, batch, N, t, y, rvec, o);
+  }
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
   // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel
   const int64_t total_steps = N * (int64_t)batch;

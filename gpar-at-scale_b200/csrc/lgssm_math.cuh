@@ -43,6 +43,60 @@ template <int D, class F> __device__ __forceinline__ void lgssm_transition(F a, 
   }
 }
 
+// Branch-free exp(x) for x <= 0 (clamped at -700, where the result is ~1e-304 and every use of it rounds to zero) and
+// branch-free 1/s for normal s > 0.  The library versions carry special-case branches, i.e. basic-block boundaries the
+// instruction scheduler cannot move work across; inside the one-pass Kalman loop these two dependent chains are meant
+// to overlap the matrix recursion.  Accuracy: ~1 ulp (13-term Taylor on |r| <= ln2/2: truncation 4e-18 relative; the
+// reciprocal is MUFU.RCP64H refined by one cubic and one quadratic Newton step, as the compiler's own fast path).
+__device__ __forceinline__ double exp_nonpos(double x) {
+  x = fmax(x, -700.0);
+  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);        // round(x / ln 2) in the low word
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;              // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);            // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);           // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);           // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);          // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);            // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);           // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);           // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);           // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);          // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);          // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));      // p in [0.70, 1.42], n >= -1010: stays normal
+}
+__device__ __forceinline__ double rcp_pos(double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  double e = fma(-s, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);
+  e = fma(-s, r, 1.0);
+  return fma(r, e, r);
+}
+
+// The same matrix from a and e = exp(-lam a) computed elsewhere (the one-pass kernel evaluates the exponential of the
+// NEXT step while the current step's recursion runs: it does not depend on the state).
+template <int D> __device__ __forceinline__ void lgssm_transition_from(double a, double e, double* A) {
+  const double lam = lgssm_lambda<D>();
+  if (D == 1) { A[0] = e; }
+  else if (D == 2) {
+    A[0] = e * (1.0 + lam * a); A[1] = e * a;
+    A[2] = e * (-lam * lam * a); A[3] = e * (1.0 - lam * a);
+  } else {
+    const double l2 = lam * lam, l3 = l2 * lam, l4 = l2 * l2; const double h = 0.5 * a * a;
+    A[0] = e * (1.0 + lam * a + l2 * h);  A[1] = e * (a + 2.0 * lam * h);            A[2] = e * h;
+    A[3] = e * (-l3 * h);                 A[4] = e * (1.0 + lam * a - 2.0 * l2 * h);  A[5] = e * (a - lam * h);
+    A[6] = e * (-l3 * a + l4 * h);        A[7] = e * (-3.0 * l2 * a + 2.0 * l3 * h);  A[8] = e * (1.0 - 2.0 * lam * a + l2 * h);
+  }
+}
+
 // R = A S A^T  (S symmetric packed; result packed)
 template <int D, class F> __device__ __forceinline__ void asat(const F* A, const F* S, F* R) {
   F T[D * D];

@@ -984,3 +984,43 @@ def test_lgssm_logpdf_candidates_on_one_sequence(ctx):
     for k in range(6):
         one = neldermead.optimize(lambda th: -ctx.lgssm_logpdf(3, th)[0], X0[k], iterations=40)
         assert abs(res[k].minimum - one.minimum) <= 1e-9 * abs(one.minimum) and res[k].f_calls == one.f_calls
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_lgssm_logpdf_one_pass_equals_three_phase(ctx, kind, monkeypatch):
+    """The one-pass log-pdf (kf_chunk_element -> scan -> closed-form chunk shares, temporal_gp_inference.jl:78) against
+    the C oracle and against the three-phase path (GPAR_KF_ONEPASS=0) it replaces: irregular grids with duplicated time
+    stamps, the 1e10 noise vector, near-noiseless and noise-dominated models, chunk lengths that do and do not divide N,
+    regular grids with a noise vector (no steady state)."""
+    rng = np.random.default_rng(4000 + kind)
+    for n, batch, L in [(40, 2, None), (4097, 3, 8), (33000, 2, 32), (33000, 2, 100), (150001, 1, None), (2_100_000, 1, None)]:
+        t = np.cumsum(rng.exponential(1 / 30, n)); t[n // 3] = t[n // 3 - 1]
+        Y = np.sin(0.3 * t)[None, :] + 0.3 * rng.normal(size=(batch, n))
+        rv = np.where(rng.uniform(size=n) < 0.2, 1e10, 0.04)
+        ths = np.stack([rng.uniform(-2.5, 1.5, batch), rng.uniform(-1, 1, batch), rng.uniform(-4.5, 0.5, batch)], axis=1)
+        ths[0, 2] = -4.5                      # sigma ~ 0.012: P nearly singular after every observation
+        pp = np.exp(ths) + 1e-3
+        ctx.set_times(t); ctx.set_outputs(Y)
+        if L is not None:
+            monkeypatch.setenv("GPAR_KF_L", str(L))
+        for rvec in (None, rv):
+            ctx.set_noise_vector(rvec)
+            lml = ctx.lgssm_logpdf(kind, ths)
+            monkeypatch.setenv("GPAR_KF_ONEPASS", "0")
+            lml3 = ctx.lgssm_logpdf(kind, ths)
+            monkeypatch.delenv("GPAR_KF_ONEPASS")
+            ref = cport.kalman_filter_batch(kind, t, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2, rvec=rvec)
+            assert relerr(lml, ref) <= RTOL, (n, L, rvec is None)
+            assert relerr(lml, lml3) <= RTOL
+        monkeypatch.delenv("GPAR_KF_L", raising=False)
+        ctx.set_noise_vector(None)
+    # regular grid + noise vector: constant transition, no steady state
+    n = 50000
+    ctx.set_times_range(0.0, 1 / 30, n); tt = np.arange(n) / 30.0
+    Y = rng.normal(size=(2, n)); rv = np.where(rng.uniform(size=n) < 0.1, 1e10, 0.09)
+    ctx.set_outputs(Y); ctx.set_noise_vector(rv)
+    ths = rng.uniform(-1.0, 0.5, (2, 3)); pp = np.exp(ths) + 1e-3
+    lml = ctx.lgssm_logpdf(kind, ths)
+    ref = cport.kalman_filter_batch(kind, tt, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2, rvec=rv)
+    assert relerr(lml, ref) <= RTOL
+    ctx.set_noise_vector(None)
