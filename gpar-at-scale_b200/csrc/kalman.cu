@@ -570,19 +570,18 @@ int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
 // and the quadratic form of the chunk's marginal covariance factor both ways.
 // kf_chunk_element: P1 in deviation form (dC = C - P_inf: one congruence per step, no Q), threads numbered
 // densely over (sequence, chunk); aux rows (field-major, stride batch * nC): sum log S0, sum v0^2/S0, eta, J.
-template <int D, int TPB, int MINB, bool REG>
+template <int D, int TPB, int MINB, bool REG, bool LOCKSTEP>
 __global__ void __launch_bounds__(TPB, MINB)
 kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux) {
   typedef FiltElem<D> E;
   const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
-  if (gidx >= ntot) return;
-  const int b = (int)(gidx / nC), c = (int)(gidx % nC);
+  const bool live = gidx < ntot;
+  if (!LOCKSTEP && !live) return;
+  const int b = live ? (int)(gidx / nC) : 0, c = live ? (int)(gidx % nC) : 0;
   const int pb = sp.nparam == 1 ? 0 : b;
   const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
-  double P0[NSYM<D>]; lgssm_pinf<D>(P0);
-#pragma unroll
-  for (int i = 0; i < NSYM<D>; i++) P0[i] *= s;
+  double P0[NSYM<D>]; lgssm_pinf_jordan<D>(s, P0);        // the whole pass runs in Jordan coordinates (lgssm_math.cuh)
   E e;
   double* Phi = e.v; double* bv = e.v + E::OB; double* dC = e.v + E::OC; double* eta = e.v + E::OE; double* J = e.v + E::OJ;
   e.set_identity();
@@ -593,31 +592,37 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) dC[i] = -P0[i];
   }
-  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
+  const int64_t k0 = (int64_t)c * L, k1 = !live ? k0 : ((k0 + L < N) ? k0 + L : N);
   double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
   const double* yb = y + (int64_t)b * ystride;
   constexpr bool reg = REG;
-  double A[D * D];
-  if constexpr (REG) lgssm_transition<D>(sp.reg_dt * il, A);
   double sum_q = 0.0, prodS = 1.0;
   int eacc = 0;            // sum log S = log(prodS) + eacc log 2: the exponent of the running product is peeled off every step
   StepIn in0, in1;
   in0.load_clamped(t, yb, rvec, k0, N, reg); in1.load_clamped(t, yb, rvec, k0 + 1, N, reg);
   // irregular grid: (a, e = exp(-lam a)) of the step about to run; the pair of the step after it is formed inside the
   // iteration, where its long dependent chain (range reduction + polynomial) overlaps the state recursion
-  double a_cur = 0.0, e_cur = 1.0;
-  if constexpr (!REG) { a_cur = (in0.t - tprev) * il; e_cur = exp_nonpos(-lgssm_lambda<D>() * a_cur); }
-  for (int64_t k = k0; k < k1; k++) {
-    double T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D];
+  const double lam = lgssm_lambda<D>();
+  const double a_reg = sp.reg_dt * il, e_reg = REG ? exp_nonpos(-lam * a_reg) : 1.0;
+  double a_cur = REG ? (k0 == 0 ? il : a_reg) : (in0.t - tprev) * il;     // step 0 follows the t[0] - 1 prefix
+  double e_cur = exp_nonpos(-lam * a_cur);
+  // LOCKSTEP: the block is all the warps of its SM and meets at a barrier every 8 steps.  The warp schedulers favour
+  // the oldest warp; left alone, the warps of a one-wave launch finish one after the other and the FP64 pipe runs
+  // under-occupied for the last third of the kernel (ncu: 11.4 of 16 resident warps active on average).
+  for (int64_t k = k0; k < (LOCKSTEP ? k0 + L : k1); k++) {
+    if constexpr (LOCKSTEP) { if (((k - k0) & 7) == 0) __syncthreads(); if (k >= k1) continue; }
+    double T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D], hr[D];
     const StepIn cur = in0; in0 = in1; in1.load_clamped(t, yb, rvec, k + 2, N, reg);
+    const double a = a_cur, ee = e_cur, h = 0.5 * a * a;
     if constexpr (!REG) {
-      lgssm_transition_from<D>(a_cur, e_cur, A);
       a_cur = (in0.t - cur.t) * il;                    // (beyond the sequence: the clamped load gives a = 0, never used)
-      e_cur = exp_nonpos(-lgssm_lambda<D>() * a_cur);
-    } else if (k <= 1) lgssm_transition<D>((k == 0 ? 1.0 : sp.reg_dt) * il, A);     // step 0 follows the t[0] - 1 prefix
-    matmul<D>(A, Phi, T);
-    matvec<D>(A, bv, u);
-    asat<D>(A, dC, Cn);
+      e_cur = exp_nonpos(-lam * a_cur);
+    } else { a_cur = a_reg; e_cur = e_reg; }
+    jordan_rows<D>(a, h, Phi, T);                      // the scalar e is applied where the rows are used
+    jordan_vec<D>(a, h, bv, u);
+#pragma unroll
+    for (int i = 0; i < D; i++) { u[i] *= ee; hr[i] = ee * T[i]; }        // hr = H A Phi
+    jordan_congruence<D>(a, h, ee * ee, dC, Cn);
 #pragma unroll
     for (int i = 0; i < D; i++) col[i] = SYM(Cn, i, 0) + SYM(P0, i, 0);
     const double S = col[0] + (rvec ? cur.r : noise);
@@ -627,17 +632,20 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     for (int i = 0; i < D; i++) Kg[i] = col[i] * iS;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-      eta[i] = fma(w, T[i], eta[i]);
-      const double hi = iS * T[i];
+      eta[i] = fma(w, hr[i], eta[i]);
+      const double hi = iS * hr[i];
 #pragma unroll
-      for (int j = i; j < D; j++) SYM(J, i, j) = fma(hi, T[j], SYM(J, i, j));
+      for (int j = i; j < D; j++) SYM(J, i, j) = fma(hi, hr[j], SYM(J, i, j));
     }
+    const double omk = 1.0 - Kg[0];
 #pragma unroll
-    for (int i = 0; i < D; i++) {
+    for (int j = 0; j < D; j++) Phi[j] = omk * hr[j];                      // row 0: e T_0 - Kg_0 hr = (1 - Kg_0) hr
 #pragma unroll
-      for (int j = 0; j < D; j++) Phi[i * D + j] = fma(-Kg[i], T[j], T[i * D + j]);
-      bv[i] = fma(Kg[i], r, u[i]);
-    }
+    for (int i = 1; i < D; i++)
+#pragma unroll
+      for (int j = 0; j < D; j++) Phi[i * D + j] = fma(-Kg[i], hr[j], ee * T[i * D + j]);
+#pragma unroll
+    for (int i = 0; i < D; i++) bv[i] = fma(Kg[i], r, u[i]);
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
@@ -648,6 +656,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     eacc += (hi >> 20) - 1023;
     prodS = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(prodS));
   }
+  if (LOCKSTEP && !live) return;
   const double sum_logS = fma((double)eacc, 0.693147180559945309417232121458, log(prodS));
   aux[gidx] = sum_logS; aux[ntot + gidx] = sum_q;
 #pragma unroll
@@ -776,7 +785,7 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
   int variant = 0;
   if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
-  const int tpb = variant == 2 ? 64 : 128, minb = variant == 1 ? 3 : (variant == 2 ? 8 : (variant == 3 ? 5 : 4));
+  const int tpb = variant == 2 ? 512 : (variant == 3 ? 256 : (variant == 4 ? 384 : 128)), minb = variant == 1 ? 3 : (variant == 2 || variant == 4 ? 1 : (variant == 3 ? 2 : 4));
   int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
   const int nC = (int)((N + L - 1) / L);
@@ -792,16 +801,17 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   const Level none{nullptr, 0, 0};
   const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
   const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
-#define KF1_LAUNCH(TPB_, MINB_)                                                                                              \
+#define KF1_LAUNCH(TPB_, MINB_, LS_)                                                                                              \
   do {                                                                                                                      \
-    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
-    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true, LS_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false, LS_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
   } while (0)
   switch (variant) {
-    case 1: KF1_LAUNCH(128, 3); break;
-    case 2: KF1_LAUNCH(64, 8); break;
-    case 3: KF1_LAUNCH(128, 5); break;
-    default: KF1_LAUNCH(128, 4); break;
+    case 1: KF1_LAUNCH(128, 3, false); break;
+    case 2: KF1_LAUNCH(512, 1, true); break;
+    case 3: KF1_LAUNCH(256, 2, true); break;
+    case 4: KF1_LAUNCH(384, 1, true); break;
+    default: KF1_LAUNCH(128, 4, false); break;
   }
 #undef KF1_LAUNCH
   if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));

@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"onepass": os.environ.get("GPAR_KF_ONEPASS", "1"), "variant": os.environ.get("GPAR_KF1_VARIANT", "0"), "L": os.environ.get("GPAR_KF_L", "auto"),
                       "cfg3_filter_ms": round(a, 4), "cfg3_launches": la, "1x10M_irregular_ms": round(c, 4), "1x10M_launches": lc}))
 else:
-    runs = [("0", "0", None)] + [("1", v, L) for v in ("0", "1", "2") for L in (None, "68", "192")]
+    runs = [("1", v, L) for v in ("0", "2", "3", "4") for L in (None, "66")]
     for op, v, L in runs:
         env = dict(os.environ); env["GPAR_KF_ONEPASS"] = op; env["GPAR_KF1_VARIANT"] = v
         if L: env["GPAR_KF_L"] = L
