@@ -121,6 +121,82 @@ __global__ void scan_down_kernel(Level cur, Level up, int batch) {
   store_elem(r, cur.base, (int64_t)batch * cur.P, (int64_t)b * cur.P + i);
 }
 
+// Block-level scan with a running carry: block (x, b) owns elements [x span, (x+1) span) of sequence b and walks them
+// in rounds of NW*32*K.  Every lane owns K consecutive elements: it combines them serially, the lane totals go through a
+// warp-shuffle scan, the NW warp totals are scanned by warp 0 through shared memory (with the carry of the earlier
+// rounds), and the lane walks its K elements again from its exclusive prefix.  Per lane that is 2K + 6 + log2(NW)
+// dependent combines — the scans of this file are latency-bound (a FiltElem<3> combine is ~300 dependent-ish FP64
+// instructions), so depth, not work, is what is minimised.  Writes the block-local inclusive prefixes in place and the
+// block total to `up` (if any).  With span >= cur.n one block finishes a whole sequence in one launch; two launches
+// cover 10M-step sequences that the 32-ary scan_up / scan_down pyramid needs six for.
+template <class Elem, int NW>
+__global__ void __launch_bounds__(NW * 32)
+scan_span_kernel(Level cur, Level up, int batch, int span, int K) {
+  constexpr int NFD = Elem::NFD;
+  __shared__ double sh[(NW + 1) * NFD];             // slot w < NW: warp totals of the round; slot NW: carry of the earlier rounds
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+  const int start = blockIdx.x * span, end = min(start + span, cur.n);
+  const int64_t fstride = (int64_t)batch * cur.P, off0 = (int64_t)b * cur.P;
+  if (threadIdx.x == 0) { Elem id; id.set_identity(); store_elem(id, sh, NW + 1, NW); }
+  __syncthreads();
+  for (int base = start; base < end; base += NW * 32 * K) {
+    const int my0 = base + threadIdx.x * K, my1 = min(my0 + K, end);
+    Elem tot; tot.set_identity();
+    for (int idx = my0; idx < my1; idx++) {
+      Elem e; load_elem(e, cur.base, fstride, off0 + idx);
+      tot = (idx == my0) ? e : Elem::scan_combine(tot, e);
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Elem o;
+      shfl_up_elem(o, tot, d);
+      if (lane >= d) tot = Elem::scan_combine(o, tot);
+    }
+    if (lane == 31) store_elem(tot, sh, NW + 1, w);
+    __syncthreads();
+    if (w == 0) {                                   // sh[w] <- carry o (warp totals 0..w)
+      Elem tt;
+      if (lane < NW) load_elem(tt, sh, NW + 1, lane); else tt.set_identity();
+#pragma unroll
+      for (int d = 1; d < NW; d <<= 1) {
+        Elem o;
+        shfl_up_elem(o, tt, d);
+        if (lane >= d) tt = Elem::scan_combine(o, tt);
+      }
+      Elem cy; load_elem(cy, sh, NW + 1, NW);
+      tt = Elem::scan_combine(cy, tt);
+      __syncwarp();
+      if (lane < NW) store_elem(tt, sh, NW + 1, lane);
+    }
+    __syncthreads();
+    // exclusive prefix of this lane: (everything before its warp) o (lane totals before it)
+    Elem p; shfl_up_elem(p, tot, 1);
+    if (lane == 0) p.set_identity();
+    { Elem wp; load_elem(wp, sh, NW + 1, w > 0 ? w - 1 : NW); p = Elem::scan_combine(wp, p); }
+    for (int idx = my0; idx < my1; idx++) {
+      Elem e; load_elem(e, cur.base, fstride, off0 + idx);
+      p = Elem::scan_combine(p, e);
+      store_elem(p, cur.base, fstride, off0 + idx);
+      if (up.base && idx == end - 1) store_elem(p, up.base, (int64_t)batch * up.P, (int64_t)b * up.P + blockIdx.x);
+    }
+    __syncthreads();
+    if (threadIdx.x < NFD) sh[threadIdx.x * (NW + 1) + NW] = sh[threadIdx.x * (NW + 1) + NW - 1];      // next round's carry
+    __syncthreads();
+  }
+}
+// inclusive prefix of element idx after scan_span passes: level 0 holds block-local prefixes over `span` elements,
+// level 1 (if any) the finished prefixes of the block totals
+template <class Elem>
+__device__ __forceinline__ Elem inclusive_prefix_span(const Level l0, const Level l1, int span, int batch, int b, int idx) {
+  Elem loc; load_elem(loc, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + idx);
+  const int T = idx / span;
+  if (T > 0 && l1.base) {
+    Elem upe; load_elem(upe, l1.base, (int64_t)batch * l1.P, (int64_t)b * l1.P + (T - 1));
+    return Elem::scan_combine(upe, loc);
+  }
+  return loc;
+}
+
 // dir_*: tangent slot of each parameter in the Dual instantiations (-1: not differentiated)
 // reg_dt > 0: regular time grid with that spacing (gpar_set_times_range) — the transition matrix is
 // then constant per sequence (what TemporalGPs does for a `range` input) and is hoisted out of the loops.
@@ -555,6 +631,15 @@ int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
   return GPAR_OK;
 }
 
+#ifndef KF1_PD
+#define KF1_PD 4          // steps between the issue of a cp.async group and its use
+#endif
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
 // ---- log-pdf only: ONE pass over the data ------------------------------------------------------------
 // The value temporal_gp_inference.jl:78 needs is a sum over steps, and a chunk's share of it is a closed
 // form of the chunk's filtering element and the state the chunk starts from, so the second walk over the
@@ -570,15 +655,14 @@ int run_scan(gpar_ctx* ctx, LevelPlan& p, int batch) {
 // and the quadratic form of the chunk's marginal covariance factor both ways.
 // kf_chunk_element: P1 in deviation form (dC = C - P_inf: one congruence per step, no Q), threads numbered
 // densely over (sequence, chunk); aux rows (field-major, stride batch * nC): sum log S0, sum v0^2/S0, eta, J.
-template <int D, int TPB, int MINB, bool REG, bool LOCKSTEP>
+template <int D, int TPB, int MINB, bool REG>
 __global__ void __launch_bounds__(TPB, MINB)
 kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux) {
   typedef FiltElem<D> E;
   const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
-  const bool live = gidx < ntot;
-  if (!LOCKSTEP && !live) return;
-  const int b = live ? (int)(gidx / nC) : 0, c = live ? (int)(gidx % nC) : 0;
+  if (gidx >= ntot) return;
+  const int b = (int)(gidx / nC), c = (int)(gidx % nC);
   const int pb = sp.nparam == 1 ? 0 : b;
   const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
   double P0[NSYM<D>]; lgssm_pinf_jordan<D>(s, P0);        // the whole pass runs in Jordan coordinates (lgssm_math.cuh)
@@ -592,32 +676,48 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 #pragma unroll
     for (int i = 0; i < NSYM<D>; i++) dC[i] = -P0[i];
   }
-  const int64_t k0 = (int64_t)c * L, k1 = !live ? k0 : ((k0 + L < N) ? k0 + L : N);
-  double tprev = (k0 == 0) ? __ldg(t) - 1.0 : __ldg(t + k0 - 1);
+  const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   const double* yb = y + (int64_t)b * ystride;
-  constexpr bool reg = REG;
   double sum_q = 0.0, prodS = 1.0;
   int eacc = 0;            // sum log S = log(prodS) + eacc log 2: the exponent of the running product is peeled off every step
-  StepIn in0, in1;
-  in0.load_clamped(t, yb, rvec, k0, N, reg); in1.load_clamped(t, yb, rvec, k0 + 1, N, reg);
+  // Every lane streams its own chunk, so its (t, y, R) loads are lane-strided and their latency is a full trip to L2 /
+  // HBM every fourth step.  A register pipeline needs a move per stage and iteration — which waits on the load it
+  // moves (ncu: 19 % of the kernel's stall samples sat on that one instruction) — so the inputs travel through a
+  // per-thread ring in shared memory instead: 8-byte cp.async copies issued KF1_PD steps ahead, read back with LDS.
+  // Group j = { t[k0+j+1], y[k0+j], R[k0+j] } (the time of the NEXT step: its exponential is formed one step early).
+  constexpr int PD = KF1_PD, RING = PD + 1;
+  __shared__ double ring[(REG ? 2 : 3) * RING * TPB];
+  double* sy = ring + threadIdx.x; double* sr = sy + RING * TPB; double* st = sr + RING * TPB;
+  auto issue = [&](int j, int slot) {
+    int64_t kk = k0 + j; kk = kk < N ? kk : N - 1;
+    cp_async8(sy + slot, yb + kk);
+    if (rvec) cp_async8(sr + slot, rvec + kk);
+    if constexpr (!REG) { const int64_t kt = kk + 1 < N ? kk + 1 : N - 1; cp_async8(st + slot, t + kt); }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int j = 0; j < PD; j++) issue(j, j * TPB);
   // irregular grid: (a, e = exp(-lam a)) of the step about to run; the pair of the step after it is formed inside the
   // iteration, where its long dependent chain (range reduction + polynomial) overlaps the state recursion
   const double lam = lgssm_lambda<D>();
   const double a_reg = sp.reg_dt * il, e_reg = REG ? exp_nonpos(-lam * a_reg) : 1.0;
-  double a_cur = REG ? (k0 == 0 ? il : a_reg) : (in0.t - tprev) * il;     // step 0 follows the t[0] - 1 prefix
+  double t_cur = REG ? 0.0 : __ldg(t + k0);
+  double a_cur = REG ? (k0 == 0 ? il : a_reg) : (t_cur - ((k0 == 0) ? t_cur - 1.0 : __ldg(t + k0 - 1))) * il;     // step 0 follows the t[0] - 1 prefix
   double e_cur = exp_nonpos(-lam * a_cur);
-  // LOCKSTEP: the block is all the warps of its SM and meets at a barrier every 8 steps.  The warp schedulers favour
-  // the oldest warp; left alone, the warps of a one-wave launch finish one after the other and the FP64 pipe runs
-  // under-occupied for the last third of the kernel (ncu: 11.4 of 16 resident warps active on average).
-  for (int64_t k = k0; k < (LOCKSTEP ? k0 + L : k1); k++) {
-    if constexpr (LOCKSTEP) { if (((k - k0) & 7) == 0) __syncthreads(); if (k >= k1) continue; }
+  const int nsteps = (int)(k1 - k0);
+  int slot = 0, wslot = PD * TPB;           // ring positions (in doubles) of the group read now / issued now
+  for (int j = 0; j < nsteps; j++) {
     double T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D], hr[D];
-    const StepIn cur = in0; in0 = in1; in1.load_clamped(t, yb, rvec, k + 2, N, reg);
+    cp_async_wait<PD - 1>();
+    const double y_cur = sy[slot], r_cur = rvec ? sr[slot] : noise;
     const double a = a_cur, ee = e_cur, h = 0.5 * a * a;
     if constexpr (!REG) {
-      a_cur = (in0.t - cur.t) * il;                    // (beyond the sequence: the clamped load gives a = 0, never used)
+      const double t_next = st[slot];                  // (beyond the sequence: the clamped copy gives a = 0, never used)
+      a_cur = (t_next - t_cur) * il; t_cur = t_next;
       e_cur = exp_nonpos(-lam * a_cur);
     } else { a_cur = a_reg; e_cur = e_reg; }
+    issue(j + PD, wslot);
+    slot = slot + TPB == RING * TPB ? 0 : slot + TPB; wslot = wslot + TPB == RING * TPB ? 0 : wslot + TPB;
     jordan_rows<D>(a, h, Phi, T);                      // the scalar e is applied where the rows are used
     jordan_vec<D>(a, h, bv, u);
 #pragma unroll
@@ -625,9 +725,9 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     jordan_congruence<D>(a, h, ee * ee, dC, Cn);
 #pragma unroll
     for (int i = 0; i < D; i++) col[i] = SYM(Cn, i, 0) + SYM(P0, i, 0);
-    const double S = col[0] + (rvec ? cur.r : noise);
+    const double S = col[0] + r_cur;
     const double iS = rcp_pos(S);
-    const double r = cur.y - u[0], w = iS * r;
+    const double r = y_cur - u[0], w = iS * r;
 #pragma unroll
     for (int i = 0; i < D; i++) Kg[i] = col[i] * iS;
 #pragma unroll
@@ -656,7 +756,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     eacc += (hi >> 20) - 1023;
     prodS = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(prodS));
   }
-  if (LOCKSTEP && !live) return;
+  cp_async_wait<0>();
   const double sum_logS = fma((double)eacc, 0.693147180559945309417232121458, log(prodS));
   aux[gidx] = sum_logS; aux[ntot + gidx] = sum_q;
 #pragma unroll
@@ -672,7 +772,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 // block (x, b) sums 128 chunks of sequence b in fixed order -> part2[b][x][2].
 template <int D>
 __global__ void __launch_bounds__(128)
-kf_chunk_lml_kernel(Level l0, Level l1, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2) {
+kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2) {
   __shared__ double sh[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   double r0 = 0.0, r1 = 0.0;
@@ -681,7 +781,7 @@ kf_chunk_lml_kernel(Level l0, Level l1, int nC, int batch, const double* __restr
     r0 = aux[idx]; r1 = aux[ntot + idx];
     if (c > 0) {
       typedef FiltElem<D> E;
-      const E pre = inclusive_prefix<E>(l0, l1, batch, b, c - 1);
+      const E pre = inclusive_prefix_span<E>(l0, l1, span, batch, b, c - 1);
       const double* m = pre.v + E::OB; const double* P = pre.v + E::OC;
       double eta[D], J[NSYM<D>];
 #pragma unroll
@@ -785,37 +885,47 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
   int variant = 0;
   if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
-  const int tpb = variant == 2 ? 512 : (variant == 3 ? 256 : (variant == 4 ? 384 : 128)), minb = variant == 1 ? 3 : (variant == 2 || variant == 4 ? 1 : (variant == 3 ? 2 : 4));
+  const int tpb = 128, minb = variant == 1 ? 3 : 4;
   int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
   const int nC = (int)((N + L - 1) / L);
-  LevelPlan fp = plan_levels(nC, FE::NFD, batch);
+  // scan plan: one block per sequence when it has at most 2048 chunks, else blocks of 256 chunks (2 per lane) + one block
+  // over their totals
+  const bool two_level = nC > 2048;
+  const int span = two_level ? 256 : nC, n1 = two_level ? (nC + span - 1) / span : 0;
+  Level f0{nullptr, nC, (nC + 31) / 32 * 32}, f1{nullptr, n1, (n1 + 31) / 32 * 32};
+  const size_t lev_doubles = (size_t)FE::NFD * batch * ((size_t)f0.P + f1.P);
   const int64_t ntot = (int64_t)batch * nC;
   const int nblk = (nC + 127) / 128;
   constexpr int NAUX = 2 + D + NSYM<D>;
-  CU(ctx->kal_a.reserve((fp.doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk) * sizeof(double)));
+  CU(ctx->kal_a.reserve((lev_doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk) * sizeof(double)));
   double* base = ctx->kal_a.as<double>();
-  bind_levels(fp, base, FE::NFD, batch);
-  double* aux = base + fp.doubles;
+  f0.base = base; if (two_level) f1.base = base + (size_t)FE::NFD * batch * f0.P;
+  double* aux = base + lev_doubles;
   double* part2 = aux + (size_t)NAUX * ntot;
   const Level none{nullptr, 0, 0};
-  const Level f0 = fp.lv[0], f1 = fp.lv.size() > 1 ? fp.lv[1] : none;
   const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
-#define KF1_LAUNCH(TPB_, MINB_, LS_)                                                                                              \
+#define KF1_LAUNCH(TPB_, MINB_)                                                                                              \
   do {                                                                                                                      \
-    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true, LS_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
-    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false, LS_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
   } while (0)
   switch (variant) {
-    case 1: KF1_LAUNCH(128, 3, false); break;
-    case 2: KF1_LAUNCH(512, 1, true); break;
-    case 3: KF1_LAUNCH(256, 2, true); break;
-    case 4: KF1_LAUNCH(384, 1, true); break;
-    default: KF1_LAUNCH(128, 4, false); break;
+    case 1: KF1_LAUNCH(128, 3); break;
+    default: KF1_LAUNCH(128, 4); break;
   }
 #undef KF1_LAUNCH
-  if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
-  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, nC, batch, aux, part2);
+  if (two_level) {
+    LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(n1, batch), 128, 0, f0, f1, batch, span, 2);
+    LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f1, none, batch, n1, std::min(8, (n1 + 255) / 256));
+  } else if (nC > 1) {        // one block per sequence; few sequences: more warps, many sequences: more elements per lane
+    const int want_lanes = batch >= 256 ? (nC + 2) / 3 : (nC + 1) / 2;
+    if (want_lanes > 128) LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f0, none, batch, span, std::min(8, (nC + 255) / 256));
+    else if (want_lanes > 64) LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(1, batch), 128, 0, f0, none, batch, span, (nC + 127) / 128);
+    else if (want_lanes > 32) LAUNCH(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), 64, 0, f0, none, batch, span, (nC + 63) / 64);
+    else LAUNCH(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), 32, 0, f0, none, batch, span, (nC + 31) / 32);
+  }
+  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2);
   LAUNCH(ctx, lml_reduce_kernel<1>, batch, 64, 0, part2, nblk, N, o.lml, (double*)nullptr, o.sums);
   return GPAR_OK;
 }

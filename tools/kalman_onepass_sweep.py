@@ -19,12 +19,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     N10 = 10_000_000
     ctx.set_outputs(rng.normal(size=N10)); ctx.set_times(np.cumsum(rng.exponential(1 / 30, N10)))
     c, lc = med(lambda: ctx.lgssm_logpdf(3, np.log([1.0, 1.0, 0.1])))
-    print(json.dumps({"onepass": os.environ.get("GPAR_KF_ONEPASS", "1"), "variant": os.environ.get("GPAR_KF1_VARIANT", "0"), "L": os.environ.get("GPAR_KF_L", "auto"),
+    print(json.dumps({"onepass": os.environ.get("GPAR_KF_ONEPASS", "1"), "variant": os.environ.get("GPAR_KF1_VARIANT", "0"), "L": os.environ.get("GPAR_KF_L", "auto"), "pf": os.environ.get("GPAR_KF1_PREFETCH"),
                       "cfg3_filter_ms": round(a, 4), "cfg3_launches": la, "1x10M_irregular_ms": round(c, 4), "1x10M_launches": lc}))
 else:
-    runs = [("1", v, L) for v in ("0", "2", "3", "4") for L in (None, "66")]
+    runs = [("1", v, pf) for v in ("0", "1") for pf in ("0",)]
     for op, v, L in runs:
         env = dict(os.environ); env["GPAR_KF_ONEPASS"] = op; env["GPAR_KF1_VARIANT"] = v
-        if L: env["GPAR_KF_L"] = L
+        env["GPAR_KF1_PREFETCH"] = L
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)
         print(p.stdout.strip() or p.stderr[-800:], flush=True)
