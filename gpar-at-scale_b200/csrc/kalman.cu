@@ -142,11 +142,12 @@ scan_span_kernel(Level cur, Level up, int batch, int span, int K) {
   for (int base = start; base < end; base += NW * 32 * K) {
     const int my0 = base + threadIdx.x * K, my1 = min(my0 + K, end);
     Elem tot; tot.set_identity();
+#pragma unroll 1
     for (int idx = my0; idx < my1; idx++) {
       Elem e; load_elem(e, cur.base, fstride, off0 + idx);
       tot = (idx == my0) ? e : Elem::scan_combine(tot, e);
     }
-#pragma unroll
+#pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
       Elem o;
       shfl_up_elem(o, tot, d);
@@ -157,7 +158,7 @@ scan_span_kernel(Level cur, Level up, int batch, int span, int K) {
     if (w == 0) {                                   // sh[w] <- carry o (warp totals 0..w)
       Elem tt;
       if (lane < NW) load_elem(tt, sh, NW + 1, lane); else tt.set_identity();
-#pragma unroll
+#pragma unroll 1
       for (int d = 1; d < NW; d <<= 1) {
         Elem o;
         shfl_up_elem(o, tt, d);
@@ -173,6 +174,7 @@ scan_span_kernel(Level cur, Level up, int batch, int span, int K) {
     Elem p; shfl_up_elem(p, tot, 1);
     if (lane == 0) p.set_identity();
     { Elem wp; load_elem(wp, sh, NW + 1, w > 0 ? w - 1 : NW); p = Elem::scan_combine(wp, p); }
+#pragma unroll 1
     for (int idx = my0; idx < my1; idx++) {
       Elem e; load_elem(e, cur.base, fstride, off0 + idx);
       p = Elem::scan_combine(p, e);
@@ -658,10 +660,11 @@ template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volat
 template <int D, int TPB, int MINB, bool REG>
 __global__ void __launch_bounds__(TPB, MINB)
 kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
-                        SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux) {
+                        SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux, int* __restrict__ tickets) {
   typedef FiltElem<D> E;
   const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
   if (gidx >= ntot) return;
+  if (gidx < batch) tickets[gidx] = 0;            // per-sequence tickets of the fused final reduction (kf_chunk_lml_kernel)
   const int b = (int)(gidx / nC), c = (int)(gidx % nC);
   const int pb = sp.nparam == 1 ? 0 : b;
   const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
@@ -772,8 +775,10 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 // block (x, b) sums 128 chunks of sequence b in fixed order -> part2[b][x][2].
 template <int D>
 __global__ void __launch_bounds__(128)
-kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2) {
+kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2,
+                    int* __restrict__ tickets, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
   __shared__ double sh[32];
+  __shared__ int last;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   double r0 = 0.0, r1 = 0.0;
   if (c < nC) {
@@ -849,7 +854,23 @@ kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const doubl
     }
   }
   r0 = block_sum(r0, sh); r1 = block_sum(r1, sh);
-  if (threadIdx.x == 0) { part2[((int64_t)b * gridDim.x + blockIdx.x) * 2] = r0; part2[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r1; }
+  // the last block of a sequence to arrive sums the sequence's block partials in fixed order (no separate reduce launch)
+  if (threadIdx.x == 0) {
+    part2[((int64_t)b * gridDim.x + blockIdx.x) * 2] = r0; part2[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r1;
+    __threadfence();
+    last = atomicAdd(tickets + b, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x >= 32) return;
+  __threadfence();
+  double a0 = 0.0, a1 = 0.0;
+  for (int x = threadIdx.x; x < (int)gridDim.x; x += 32) { a0 += __ldcg(part2 + ((int64_t)b * gridDim.x + x) * 2); a1 += __ldcg(part2 + ((int64_t)b * gridDim.x + x) * 2 + 1); }
+  for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+  if (threadIdx.x == 0) {
+    if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + a0 + a1);
+    if (sums) { sums[2 * b] = a0; sums[2 * b + 1] = a1; }
+    tickets[b] = 0;
+  }
 }
 
 // Outputs of one filter / smoother run (device pointers, all nullable except lml or sums).
@@ -883,9 +904,9 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
                          const LgssmOut& o) {
   typedef FiltElem<D> FE;
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
-  int variant = 0;
+  int variant = 1;          // 3 resident blocks of 128 threads (no register cap) measured slightly ahead of 4 capped ones
   if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
-  const int tpb = 128, minb = variant == 1 ? 3 : 4;
+  const int tpb = 128, minb = variant == 0 ? 4 : 3;
   int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
   const int nC = (int)((N + L - 1) / L);
@@ -898,21 +919,22 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   const int64_t ntot = (int64_t)batch * nC;
   const int nblk = (nC + 127) / 128;
   constexpr int NAUX = 2 + D + NSYM<D>;
-  CU(ctx->kal_a.reserve((lev_doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk) * sizeof(double)));
+  CU(ctx->kal_a.reserve((lev_doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk + (size_t)(batch + 1) / 2) * sizeof(double)));
   double* base = ctx->kal_a.as<double>();
   f0.base = base; if (two_level) f1.base = base + (size_t)FE::NFD * batch * f0.P;
   double* aux = base + lev_doubles;
   double* part2 = aux + (size_t)NAUX * ntot;
+  int* tickets = reinterpret_cast<int*>(part2 + (size_t)2 * batch * nblk);
   const Level none{nullptr, 0, 0};
   const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
 #define KF1_LAUNCH(TPB_, MINB_)                                                                                              \
   do {                                                                                                                      \
-    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux); \
-    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux);               \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets);               \
   } while (0)
   switch (variant) {
-    case 1: KF1_LAUNCH(128, 3); break;
-    default: KF1_LAUNCH(128, 4); break;
+    case 0: KF1_LAUNCH(128, 4); break;
+    default: KF1_LAUNCH(128, 3); break;
   }
 #undef KF1_LAUNCH
   if (two_level) {
@@ -925,8 +947,7 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
     else if (want_lanes > 32) LAUNCH(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), 64, 0, f0, none, batch, span, (nC + 63) / 64);
     else LAUNCH(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), 32, 0, f0, none, batch, span, (nC + 31) / 32);
   }
-  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2);
-  LAUNCH(ctx, lml_reduce_kernel<1>, batch, 64, 0, part2, nblk, N, o.lml, (double*)nullptr, o.sums);
+  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.sums);
   return GPAR_OK;
 }
 
