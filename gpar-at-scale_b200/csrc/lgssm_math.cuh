@@ -48,27 +48,24 @@ template <int D, class F> __device__ __forceinline__ void lgssm_transition(F a, 
 // instruction scheduler cannot move work across; inside the one-pass Kalman loop these two dependent chains are meant
 // to overlap the matrix recursion.  Accuracy: ~1 ulp (13-term Taylor on |r| <= ln2/2: truncation 4e-18 relative; the
 // reciprocal is MUFU.RCP64H refined by one cubic and one quadratic Newton step, as the compiler's own fast path).
+// (constants live in constant memory: as immediates every 64-bit coefficient costs two UMOV issue slots per use, and in
+// the one-pass Kalman loop every non-FP64 instruction delays the FP64 pipe by a cycle)
+__constant__ double kExpC[18] = {
+    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
+    1.6666666666666666e-01, 0.5, 1.0, -700.0};
 __device__ __forceinline__ double exp_nonpos(double x) {
-  x = fmax(x, -700.0);
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);        // round(x / ln 2) in the low word
+  x = fmax(x, kExpC[17]);
+  const double t = fma(x, kExpC[0], kExpC[1]);               // round(x / ln 2) in the low word
   const int n = __double2loint(t);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;              // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);            // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);           // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);           // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);          // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);            // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);           // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);           // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);           // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);          // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);          // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  const double nf = t - kExpC[1];
+  double r = fma(nf, kExpC[2], x);
+  r = fma(nf, kExpC[3], r);
+  double p = kExpC[4];                                       // 1/13!, then 1/12! ... 1/2!, 1, 1
+#pragma unroll
+  for (int i = 5; i <= 16; i++) p = fma(p, r, kExpC[i]);
+  p = fma(p, r, kExpC[16]);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));      // p in [0.70, 1.42], n >= -1010: stays normal
 }
 __device__ __forceinline__ double rcp_pos(double s) {
