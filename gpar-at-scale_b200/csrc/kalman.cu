@@ -661,7 +661,7 @@ template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volat
 // and the quadratic form of the chunk's marginal covariance factor both ways.
 // kf_chunk_element: P1 in deviation form (dC = C - P_inf: one congruence per step, no Q), threads numbered
 // densely over (sequence, chunk); aux rows (field-major, stride batch * nC): sum log S0, sum v0^2/S0, eta, J.
-template <int D, int TPB, int MINB, bool REG>
+template <int D, int TPB, int MINB, bool REG, int PD>
 __global__ void __launch_bounds__(TPB, MINB)
 kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux, int* __restrict__ tickets) {
@@ -692,7 +692,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
   // moves (ncu: 19 % of the kernel's stall samples sat on that one instruction) — so the inputs travel through a
   // per-thread ring in shared memory instead: 8-byte cp.async copies issued KF1_PD steps ahead, read back with LDS.
   // Group j = { t[k0+j+1], y[k0+j], R[k0+j] } (the time of the NEXT step: its exponential is formed one step early).
-  constexpr int PD = KF1_PD, RING = PD + 1;
+  constexpr int RING = PD + 1;
   __shared__ double ring[(REG ? 2 : 3) * RING * TPB];
   double* sy = ring + threadIdx.x; double* sr = sy + RING * TPB; double* st = sr + RING * TPB;
   // copies are predicated on staying inside the sequence (only its last chunk can run past the end; a slot that is not
@@ -934,14 +934,14 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   int* tickets = reinterpret_cast<int*>(part2 + (size_t)2 * batch * nblk);
   const Level none{nullptr, 0, 0};
   const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
-#define KF1_LAUNCH(TPB_, MINB_)                                                                                              \
+#define KF1_LAUNCH(TPB_, MINB_, PD_)                                                                                              \
   do {                                                                                                                      \
-    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets); \
-    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets);               \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets);               \
   } while (0)
   switch (variant) {
-    case 0: KF1_LAUNCH(128, 4); break;
-    default: KF1_LAUNCH(128, 3); break;
+    case 0: KF1_LAUNCH(128, 4, KF1_PD); break;
+    default: KF1_LAUNCH(128, 3, KF1_PD); break;
   }
 #undef KF1_LAUNCH
   if (two_level) {
