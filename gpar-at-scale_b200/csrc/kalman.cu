@@ -661,20 +661,22 @@ template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volat
 // and the quadratic form of the chunk's marginal covariance factor both ways.
 // kf_chunk_element: P1 in deviation form (dC = C - P_inf: one congruence per step, no Q), threads numbered
 // densely over (sequence, chunk); aux rows (field-major, stride batch * nC): sum log S0, sum v0^2/S0, eta, J.
-template <int D, int TPB, int MINB, bool REG, int PD>
+template <int D, class F, int TPB, int MINB, bool REG, int PD>
 __global__ void __launch_bounds__(TPB, MINB)
 kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ rvec,
                         SeqParams sp, int64_t N, int L, int nC, Level l0, int batch, int64_t ystride, double* __restrict__ aux, int* __restrict__ tickets) {
-  typedef FiltElem<D> E;
+  typedef FiltElem<D, F> E;
+  typedef Scalar<F> SC;
+  constexpr int NC = SC::NC;
   const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
   if (gidx >= ntot) return;
   if (gidx < batch) tickets[gidx] = 0;            // per-sequence tickets of the fused final reduction (kf_chunk_lml_kernel)
   const int b = (int)(gidx / nC), c = (int)(gidx % nC);
   const int pb = sp.nparam == 1 ? 0 : b;
-  const double il = 1.0 / sp.l[pb], s = sp.s[pb], noise = sp.noise[pb];
-  double P0[NSYM<D>]; lgssm_pinf_jordan<D>(s, P0);        // the whole pass runs in Jordan coordinates (lgssm_math.cuh)
+  const F il = 1.0 / Seed<F>::make(sp.l[pb], sp.dir_l), s = Seed<F>::make(sp.s[pb], sp.dir_s), noise = Seed<F>::make(sp.noise[pb], sp.dir_n);
+  F P0[NSYM<D>]; lgssm_pinf_jordan<D, F>(s, P0);        // the whole pass runs in Jordan coordinates (lgssm_math.cuh)
   E e;
-  double* Phi = e.v; double* bv = e.v + E::OB; double* dC = e.v + E::OC; double* eta = e.v + E::OE; double* J = e.v + E::OJ;
+  F* Phi = e.v; F* bv = e.v + E::OB; F* dC = e.v + E::OC; F* eta = e.v + E::OE; F* J = e.v + E::OJ;
   e.set_identity();
   if (c == 0) {           // the prior: x_0 ~ N(0, P_inf) whatever came before
 #pragma unroll
@@ -685,7 +687,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
   }
   const int64_t k0 = (int64_t)c * L, k1 = (k0 + L < N) ? k0 + L : N;
   const double* yb = y + (int64_t)b * ystride;
-  double sum_q = 0.0, prodS = 1.0;
+  F sum_q = 0.0, prodS = 1.0;
   int eacc = 0;            // sum log S = log(prodS) + eacc log 2: the exponent of the running product is peeled off every step
   // Every lane streams its own chunk, so its (t, y, R) loads are lane-strided and their latency is a full trip to L2 /
   // HBM every fourth step.  A register pipeline needs a move per stage and iteration — which waits on the load it
@@ -710,17 +712,18 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
   // irregular grid: (a, e = exp(-lam a)) of the step about to run; the pair of the step after it is formed inside the
   // iteration, where its long dependent chain (range reduction + polynomial) overlaps the state recursion
   const double lam = lgssm_lambda<D>();
-  const double a_reg = sp.reg_dt * il, e_reg = REG ? exp_nonpos(-lam * a_reg) : 1.0;
+  const F a_reg = sp.reg_dt * il, e_reg = REG ? exp_nonpos(-lam * a_reg) : F(1.0);
   double t_cur = REG ? 0.0 : __ldg(t + k0);
-  double a_cur = REG ? (k0 == 0 ? il : a_reg) : (t_cur - ((k0 == 0) ? t_cur - 1.0 : __ldg(t + k0 - 1))) * il;     // step 0 follows the t[0] - 1 prefix
-  double e_cur = exp_nonpos(-lam * a_cur);
+  F a_cur = REG ? (k0 == 0 ? il : a_reg) : (t_cur - ((k0 == 0) ? t_cur - 1.0 : __ldg(t + k0 - 1))) * il;     // step 0 follows the t[0] - 1 prefix
+  F e_cur = exp_nonpos(-lam * a_cur);
   const int nsteps = (int)(k1 - k0);
   int slot = 0, wslot = PD * TPB;           // ring positions (in doubles) of the group read now / issued now
   for (int j = 0; j < nsteps; j++) {
-    double T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D], hr[D];
+    F T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D], hr[D];
     cp_async_wait<PD - 1>();
-    const double y_cur = sy[slot], r_cur = rvec ? sr[slot] : noise;
-    const double a = a_cur, ee = e_cur, h = 0.5 * a * a;
+    const double y_cur = sy[slot];
+    const F r_cur = rvec ? F(sr[slot]) : noise;
+    const F a = a_cur, ee = e_cur, h = 0.5 * a * a;
     if constexpr (!REG) {
       const double t_next = st[slot];                  // (beyond the sequence: the clamped copy gives a = 0, never used)
       a_cur = (t_next - t_cur) * il; t_cur = t_next;
@@ -728,26 +731,26 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     } else { a_cur = a_reg; e_cur = e_reg; }
     issue(j + PD, wslot);
     slot = slot + TPB == RING * TPB ? 0 : slot + TPB; wslot = wslot + TPB == RING * TPB ? 0 : wslot + TPB;
-    jordan_rows<D>(a, h, Phi, T);                      // the scalar e is applied where the rows are used
-    jordan_vec<D>(a, h, bv, u);
+    jordan_rows<D, F>(a, h, Phi, T);                      // the scalar e is applied where the rows are used
+    jordan_vec<D, F>(a, h, bv, u);
 #pragma unroll
-    for (int i = 0; i < D; i++) { u[i] *= ee; hr[i] = ee * T[i]; }        // hr = H A Phi
-    jordan_congruence<D>(a, h, ee * ee, dC, Cn);
+    for (int i = 0; i < D; i++) { u[i] = u[i] * ee; hr[i] = ee * T[i]; }        // hr = H A Phi
+    jordan_congruence<D, F>(a, h, ee * ee, dC, Cn);
 #pragma unroll
     for (int i = 0; i < D; i++) col[i] = SYM(Cn, i, 0) + SYM(P0, i, 0);
-    const double S = col[0] + r_cur;
-    const double iS = rcp_pos(S);
-    const double r = y_cur - u[0], w = iS * r;
+    const F S = col[0] + r_cur;
+    const F iS = rcp_pos(S);
+    const F r = y_cur - u[0], w = iS * r;
 #pragma unroll
     for (int i = 0; i < D; i++) Kg[i] = col[i] * iS;
 #pragma unroll
     for (int i = 0; i < D; i++) {
       eta[i] = fma(w, hr[i], eta[i]);
-      const double hi = iS * hr[i];
+      const F hi = iS * hr[i];
 #pragma unroll
       for (int j = i; j < D; j++) SYM(J, i, j) = fma(hi, hr[j], SYM(J, i, j));
     }
-    const double omk = 1.0 - Kg[0];
+    const F omk = 1.0 - Kg[0];
 #pragma unroll
     for (int j = 0; j < D; j++) Phi[j] = omk * hr[j];                      // row 0: e T_0 - Kg_0 hr = (1 - Kg_0) hr
 #pragma unroll
@@ -761,121 +764,149 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 #pragma unroll
       for (int j = i; j < D; j++) SYM(dC, i, j) = fma(-Kg[i], col[j], SYM(Cn, i, j));
     sum_q = fma(w, r, sum_q);
-    prodS *= S;         // S > 0 and normal: mantissa stays in [1, 2), the exponent goes to the integer accumulator
-    const int hi = __double2hiint(prodS);
-    eacc += (hi >> 20) - 1023;
-    prodS = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(prodS));
+    prodS = prodS * S;         // S > 0 and normal: mantissa stays in [1, 2), the exponent goes to the integer accumulator
+    peel_exponent(prodS, eacc);
   }
   cp_async_wait<0>();
-  const double sum_logS = fma((double)eacc, 0.693147180559945309417232121458, log(prodS));
-  aux[gidx] = sum_logS; aux[ntot + gidx] = sum_q;
+  const F sum_logS = log(prodS) + (double)eacc * 0.693147180559945309417232121458;
+  // aux rows: field-major, each field with its NC components
 #pragma unroll
-  for (int i = 0; i < D; i++) aux[(2 + i) * ntot + gidx] = eta[i];
+  for (int cc = 0; cc < NC; cc++) {
+    aux[(0 * NC + cc) * ntot + gidx] = SC::comp(sum_logS, cc); aux[(1 * NC + cc) * ntot + gidx] = SC::comp(sum_q, cc);
 #pragma unroll
-  for (int i = 0; i < NSYM<D>; i++) aux[(2 + D + i) * ntot + gidx] = J[i];
+    for (int i = 0; i < D; i++) aux[((2 + i) * NC + cc) * ntot + gidx] = SC::comp(eta[i], cc);
 #pragma unroll
-  for (int i = 0; i < NSYM<D>; i++) dC[i] += P0[i];
+    for (int i = 0; i < NSYM<D>; i++) aux[((2 + D + i) * NC + cc) * ntot + gidx] = SC::comp(J[i], cc);
+  }
+#pragma unroll
+  for (int i = 0; i < NSYM<D>; i++) dC[i] = dC[i] + P0[i];
   store_elem(e, l0.base, (int64_t)batch * l0.P, (int64_t)b * l0.P + c);
 }
 
 // Every chunk's share of (sum log S, sum alpha^2) from its aux row and the scanned state it starts from;
 // block (x, b) sums 128 chunks of sequence b in fixed order -> part2[b][x][2].
-template <int D>
+template <int D, class F>
 __global__ void __launch_bounds__(128)
 kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const double* __restrict__ aux, double* __restrict__ part2,
-                    int* __restrict__ tickets, int64_t N, double* __restrict__ lml, double* __restrict__ sums) {
+                    int* __restrict__ tickets, int64_t N, double* __restrict__ lml, double* __restrict__ dlml, double* __restrict__ sums) {
+  typedef Scalar<F> SC;
+  constexpr int NC = SC::NC;
   __shared__ double sh[32];
   __shared__ int last;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  double r0 = 0.0, r1 = 0.0;
+  F r0 = 0.0, r1 = 0.0;
   if (c < nC) {
     const int64_t ntot = (int64_t)batch * nC, idx = (int64_t)b * nC + c;
-    r0 = aux[idx]; r1 = aux[ntot + idx];
+    auto ld = [&](int f) { F x;
+#pragma unroll
+      for (int cc = 0; cc < NC; cc++) SC::comp(x, cc) = aux[((int64_t)f * NC + cc) * ntot + idx];
+      return x; };
+    r0 = ld(0); r1 = ld(1);
     if (c > 0) {
-      typedef FiltElem<D> E;
+      typedef FiltElem<D, F> E;
       const E pre = inclusive_prefix_span<E>(l0, l1, span, batch, b, c - 1);
-      const double* m = pre.v + E::OB; const double* P = pre.v + E::OC;
-      double eta[D], J[NSYM<D>];
+      const F* m = pre.v + E::OB; const F* P = pre.v + E::OC;
+      F eta[D], J[NSYM<D>];
 #pragma unroll
-      for (int i = 0; i < D; i++) eta[i] = aux[(2 + i) * ntot + idx];
+      for (int i = 0; i < D; i++) eta[i] = ld(2 + i);
 #pragma unroll
-      for (int i = 0; i < NSYM<D>; i++) J[i] = aux[(2 + D + i) * ntot + idx];
+      for (int i = 0; i < NSYM<D>; i++) J[i] = ld(2 + D + i);
       // P = Lc Lc' (lower; a non-positive pivot — P singular to working precision — zeroes its column)
-      double Lc[D * D];
+      F Lc[D * D];
 #pragma unroll
       for (int j = 0; j < D; j++) {
-        double inv = 0.0;
+        F inv = 0.0;
 #pragma unroll
         for (int i = j; i < D; i++) {
-          double v = SYM(P, i, j);
+          F v = SYM(P, i, j);
 #pragma unroll
-          for (int q = 0; q < j; q++) v -= Lc[i * D + q] * Lc[j * D + q];
-          if (i == j) { const double d = v > 0.0 ? sqrt(v) : 0.0; Lc[j * D + j] = d; inv = d > 0.0 ? 1.0 / d : 0.0; }
-          else Lc[i * D + j] = v * inv;
+          for (int q = 0; q < j; q++) v = v - Lc[i * D + q] * Lc[j * D + q];
+          if (i == j) {
+            const bool pos = value_of(v) > 0.0;
+            const F d = pos ? sqrt(v) : F(0.0); Lc[j * D + j] = d; inv = pos ? 1.0 / d : F(0.0);
+          } else Lc[i * D + j] = v * inv;
         }
       }
-      double Jm[D], a[D], W[D * D], Bm[NSYM<D>];
+      F Jm[D], a[D], W[D * D], Bm[NSYM<D>];
       symvec<D>(J, m, Jm);
-      double em = 0.0, mJm = 0.0;
+      F em = 0.0, mJm = 0.0;
 #pragma unroll
       for (int i = 0; i < D; i++) { em = fma(eta[i], m[i], em); mJm = fma(m[i], Jm[i], mJm); }
 #pragma unroll
-      for (int j = 0; j < D; j++) { double v = 0.0;
+      for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
         for (int i = j; i < D; i++) v = fma(Lc[i * D + j], eta[i] - Jm[i], v);
         a[j] = v; }
 #pragma unroll
       for (int i = 0; i < D; i++)           // W = J Lc
 #pragma unroll
-        for (int j = 0; j < D; j++) { double v = 0.0;
+        for (int j = 0; j < D; j++) { F v = 0.0;
 #pragma unroll
           for (int q = j; q < D; q++) v = fma(SYM(J, i, q), Lc[q * D + j], v);
           W[i * D + j] = v; }
 #pragma unroll
       for (int i = 0; i < D; i++)           // B = I + Lc' W (symmetric)
 #pragma unroll
-        for (int j = i; j < D; j++) { double v = (i == j) ? 1.0 : 0.0;
+        for (int j = i; j < D; j++) { F v = (i == j) ? 1.0 : 0.0;
 #pragma unroll
           for (int q = i; q < D; q++) v = fma(Lc[q * D + i], W[q * D + j], v);
           SYM(Bm, i, j) = v; }
       // B = Lb Lb': log det B and |Lb^-1 a|^2
-      double Lb[D * D], z[D], det = 1.0, zz = 0.0;
+      F Lb[D * D], z[D], det = 1.0, zz = 0.0;
 #pragma unroll
       for (int j = 0; j < D; j++) {
-        double inv = 0.0;
+        F inv = 0.0;
 #pragma unroll
         for (int i = j; i < D; i++) {
-          double v = SYM(Bm, i, j);
+          F v = SYM(Bm, i, j);
 #pragma unroll
-          for (int q = 0; q < j; q++) v -= Lb[i * D + q] * Lb[j * D + q];
-          if (i == j) { det *= v; const double d = sqrt(v); Lb[j * D + j] = d; inv = 1.0 / d; }
+          for (int q = 0; q < j; q++) v = v - Lb[i * D + q] * Lb[j * D + q];
+          if (i == j) { det = det * v; const F d = sqrt(v); Lb[j * D + j] = d; inv = 1.0 / d; }
           else Lb[i * D + j] = v * inv;
         }
-        double v = a[j];
+        F v = a[j];
 #pragma unroll
-        for (int q = 0; q < j; q++) v -= Lb[j * D + q] * z[q];
+        for (int q = 0; q < j; q++) v = v - Lb[j * D + q] * z[q];
         z[j] = v * inv; zz = fma(z[j], z[j], zz);
       }
-      r0 += log(det);
-      r1 += mJm - 2.0 * em - zz;
+      r0 = r0 + log(det);
+      r1 = r1 + (mJm - 2.0 * em - zz);
     }
   }
-  r0 = block_sum(r0, sh); r1 = block_sum(r1, sh);
   // the last block of a sequence to arrive sums the sequence's block partials in fixed order (no separate reduce launch)
+  constexpr int NP = 2 * NC;
+  double rr[NP];
+#pragma unroll
+  for (int cc = 0; cc < NC; cc++) { rr[cc] = block_sum(SC::comp(r0, cc), sh); rr[NC + cc] = block_sum(SC::comp(r1, cc), sh); }
   if (threadIdx.x == 0) {
-    part2[((int64_t)b * gridDim.x + blockIdx.x) * 2] = r0; part2[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r1;
+#pragma unroll
+    for (int i = 0; i < NP; i++) part2[((int64_t)b * gridDim.x + blockIdx.x) * NP + i] = rr[i];
     __threadfence();
     last = atomicAdd(tickets + b, 1) == (int)gridDim.x - 1;
   }
   __syncthreads();
   if (!last || threadIdx.x >= 32) return;
   __threadfence();
-  double a0 = 0.0, a1 = 0.0;
-  for (int x = threadIdx.x; x < (int)gridDim.x; x += 32) { a0 += __ldcg(part2 + ((int64_t)b * gridDim.x + x) * 2); a1 += __ldcg(part2 + ((int64_t)b * gridDim.x + x) * 2 + 1); }
-  for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+  double acc[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) acc[i] = 0.0;
+  for (int x = threadIdx.x; x < (int)gridDim.x; x += 32) {
+#pragma unroll
+    for (int i = 0; i < NP; i++) acc[i] += __ldcg(part2 + ((int64_t)b * gridDim.x + x) * NP + i);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; i++)
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
   if (threadIdx.x == 0) {
-    if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + a0 + a1);
-    if (sums) { sums[2 * b] = a0; sums[2 * b + 1] = a1; }
+    if (lml) lml[b] = -0.5 * ((double)N * 1.8378770664093454835606594728112 + acc[0] + acc[NC]);
+    if (dlml) {
+#pragma unroll
+      for (int j = 1; j < NC; j++) dlml[b * (NC - 1) + (j - 1)] = -0.5 * (acc[j] + acc[NC + j]);
+    }
+    if (sums) {
+#pragma unroll
+      for (int i = 0; i < NP; i++) sums[b * NP + i] = acc[i];
+    }
     tickets[b] = 0;
   }
 }
@@ -906,55 +937,67 @@ int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads) {
   return (int)std::max<int64_t>(L, 32);
 }
 
-template <int D>
+template <int D, class F>
 int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double* t, const double* y, const double* rvec,
                          const LgssmOut& o) {
-  typedef FiltElem<D> FE;
+  typedef FiltElem<D, F> FE;
+  constexpr int NC = Scalar<F>::NC;
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
-  int variant = 1;          // 3 resident blocks of 128 threads (no register cap) measured slightly ahead of 4 capped ones
+  int variant = NC == 1 ? 1 : 2;          // 3 resident blocks of 128 threads (no register cap) measured slightly ahead of 4 capped ones
   if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
-  const int tpb = 128, minb = variant == 0 ? 4 : 3;
+  const int tpb = variant == 3 ? 64 : 128, minb = variant == 0 ? 4 : (variant == 2 ? 1 : (variant == 3 ? 4 : (variant == 4 ? 2 : 3)));
   int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
   const int nC = (int)((N + L - 1) / L);
-  // scan plan: one block per sequence when it has at most 2048 chunks, else blocks of 256 chunks (2 per lane) + one block
-  // over their totals
-  const bool two_level = nC > 2048;
-  const int span = two_level ? 256 : nC, n1 = two_level ? (nC + span - 1) / span : 0;
+  // scan plan (values): one block per sequence when it has at most 2048 chunks, else blocks of 256 chunks (2 per lane) +
+  // one block over their totals.  Tangent runs keep the 32-ary pyramid: the block-level kernel does not survive register
+  // allocation with 81-double elements.
+  LevelPlan fp;
+  if constexpr (NC > 1) fp = plan_levels(nC, FE::NFD, batch);
+  const bool two_level = NC == 1 && nC > 2048;
+  const int span = NC > 1 ? 32 : (two_level ? 256 : nC), n1 = two_level ? (nC + span - 1) / span : 0;
   Level f0{nullptr, nC, (nC + 31) / 32 * 32}, f1{nullptr, n1, (n1 + 31) / 32 * 32};
-  const size_t lev_doubles = (size_t)FE::NFD * batch * ((size_t)f0.P + f1.P);
+  const size_t lev_doubles = NC > 1 ? fp.doubles : (size_t)FE::NFD * batch * ((size_t)f0.P + f1.P);
   const int64_t ntot = (int64_t)batch * nC;
   const int nblk = (nC + 127) / 128;
-  constexpr int NAUX = 2 + D + NSYM<D>;
-  CU(ctx->kal_a.reserve((lev_doubles + (size_t)NAUX * ntot + (size_t)2 * batch * nblk + (size_t)(batch + 1) / 2) * sizeof(double)));
+  constexpr int NAUX = (2 + D + NSYM<D>) * NC;
+  CU(ctx->kal_a.reserve((lev_doubles + (size_t)NAUX * ntot + (size_t)2 * NC * batch * nblk + (size_t)(batch + 1) / 2) * sizeof(double)));
   double* base = ctx->kal_a.as<double>();
-  f0.base = base; if (two_level) f1.base = base + (size_t)FE::NFD * batch * f0.P;
+  if constexpr (NC > 1) {
+    bind_levels(fp, base, FE::NFD, batch);
+    f0 = fp.lv[0]; f1 = fp.lv.size() > 1 ? fp.lv[1] : Level{nullptr, 0, 0};
+  } else { f0.base = base; if (two_level) f1.base = base + (size_t)FE::NFD * batch * f0.P; }
   double* aux = base + lev_doubles;
   double* part2 = aux + (size_t)NAUX * ntot;
-  int* tickets = reinterpret_cast<int*>(part2 + (size_t)2 * batch * nblk);
+  int* tickets = reinterpret_cast<int*>(part2 + (size_t)2 * NC * batch * nblk);
   const Level none{nullptr, 0, 0};
   const unsigned g1 = (unsigned)((ntot + tpb - 1) / tpb);
 #define KF1_LAUNCH(TPB_, MINB_, PD_)                                                                                              \
   do {                                                                                                                      \
-    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, true, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets); \
-    else LAUNCH(ctx, (kf_chunk_element_kernel<D, TPB_, MINB_, false, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets);               \
+    if (sp.reg_dt > 0.0) LAUNCH(ctx, (kf_chunk_element_kernel<D, F, TPB_, MINB_, true, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets); \
+    else LAUNCH(ctx, (kf_chunk_element_kernel<D, F, TPB_, MINB_, false, PD_>), g1, TPB_, 0, t, y, rvec, sp, N, L, nC, f0, batch, ystride, aux, tickets);               \
   } while (0)
   switch (variant) {
     case 0: KF1_LAUNCH(128, 4, KF1_PD); break;
+    case 2: KF1_LAUNCH(128, 1, KF1_PD); break;
+    case 3: KF1_LAUNCH(64, 4, KF1_PD); break;
+    case 4: KF1_LAUNCH(128, 2, KF1_PD); break;
     default: KF1_LAUNCH(128, 3, KF1_PD); break;
   }
 #undef KF1_LAUNCH
-  if (two_level) {
+  if constexpr (NC > 1) {
+    if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
+  } else if (two_level) {
     LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(n1, batch), 128, 0, f0, f1, batch, span, 2);
     LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f1, none, batch, n1, std::min(8, (n1 + 255) / 256));
   } else if (nC > 1) {        // one block per sequence; few sequences: more warps, many sequences: more elements per lane
     const int want_lanes = batch >= 256 ? (nC + 2) / 3 : (nC + 1) / 2;
     if (want_lanes > 128) LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f0, none, batch, span, std::min(8, (nC + 255) / 256));
     else if (want_lanes > 64) LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(1, batch), 128, 0, f0, none, batch, span, (nC + 127) / 128);
-    else if (want_lanes > 32) LAUNCH(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), 64, 0, f0, none, batch, span, (nC + 63) / 64);
+    else if (want_lanes > 64 / 2) LAUNCH(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), 64, 0, f0, none, batch, span, (nC + 63) / 64);
     else LAUNCH(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), 32, 0, f0, none, batch, span, (nC + 31) / 32);
   }
-  LAUNCH(ctx, kf_chunk_lml_kernel<D>, dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.sums);
+  LAUNCH(ctx, (kf_chunk_lml_kernel<D, F>), dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.dlml, o.sums);
   return GPAR_OK;
 }
 
@@ -964,10 +1007,10 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   typedef FiltElem<D, F> FE;
   const bool smooth = o.mean != nullptr;
   if (o.ybroadcast && (o.alpha || o.mean)) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: candidates on one sequence yield log-pdfs only");
-  if constexpr (NC == 1) {      // nothing per step asked for: the log-pdf needs one pass over the data
-    bool onepass = !smooth && !o.alpha && !o.table && !o.fstate;
+  {      // nothing per step asked for: the log-pdf (and its tangents) needs one pass over the data
+    bool onepass = !smooth && !o.alpha && !o.table && !o.fstate && !o.dalpha && !o.dtable;
     if (const char* e = getenv("GPAR_KF_ONEPASS")) onepass = onepass && atoi(e) != 0;       // testing knob: 0 = three-phase path
-    if (onepass) return lgssm_logpdf_onepass<D>(ctx, sp, batch, N, t, y, rvec, o);
+    if (onepass) return lgssm_logpdf_onepass<D, F>(ctx, sp, batch, N, t, y, rvec, o);
   }
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
   // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel

@@ -78,6 +78,33 @@ __device__ __forceinline__ double rcp_pos(double s) {
   return fma(r, e, r);
 }
 
+template <int NT> __device__ __forceinline__ Dual<NT> exp_nonpos(const Dual<NT>& x) {       // (the clamp only acts where the value is ~0)
+  Dual<NT> r; r.v = exp_nonpos(x.v);
+#pragma unroll
+  for (int i = 0; i < NT; i++) r.d[i] = r.v * x.d[i];
+  return r;
+}
+template <int NT> __device__ __forceinline__ Dual<NT> rcp_pos(const Dual<NT>& s) {
+  Dual<NT> r; r.v = rcp_pos(s.v);
+  const double f = -r.v * r.v;
+#pragma unroll
+  for (int i = 0; i < NT; i++) r.d[i] = f * s.d[i];
+  return r;
+}
+// x = m 2^e with m in [1, 2): x <- m (tangents scaled alike, so log x keeps its tangent), e added to eacc.  x > 0 normal.
+__device__ __forceinline__ void peel_exponent(double& x, int& eacc) {
+  const int hi = __double2hiint(x);
+  eacc += (hi >> 20) - 1023;
+  x = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+}
+template <int NT> __device__ __forceinline__ void peel_exponent(Dual<NT>& x, int& eacc) {
+  const int e = (__double2hiint(x.v) >> 20) - 1023;
+  const double sc = __hiloint2double((1023 - e) << 20, 0);          // 2^-e  (|e| < 1000 by construction)
+  eacc += e; x.v *= sc;
+#pragma unroll
+  for (int i = 0; i < NT; i++) x.d[i] *= sc;
+}
+
 // The same matrix from a and e = exp(-lam a) computed elsewhere (the one-pass kernel evaluates the exponential of the
 // NEXT step while the current step's recursion runs: it does not depend on the state).
 template <int D> __device__ __forceinline__ void lgssm_transition_from(double a, double e, double* A) {
@@ -122,7 +149,7 @@ template <int D, class F> __device__ __forceinline__ void asat(const F* A, const
 // e^2 U S U' 12 FMA + 6 MUL instead of 45 FMA, and no matrix has to be formed from (a, e).  Everything a caller sees
 // (log-pdf, innovations, first state component = x_0 = z_0) is invariant under the change of basis; FiltElem / SmoothElem
 // combine generic matrices, so elements built in z scan with the same operators.
-template <int D> __device__ __forceinline__ void lgssm_pinf_jordan(double s, double* Pz) {     // s V^-1 P_inf V^-T (packed)
+template <int D, class F> __device__ __forceinline__ void lgssm_pinf_jordan(F s, F* Pz) {     // s V^-1 P_inf V^-T (packed)
   const double lam = lgssm_lambda<D>();
   double P[NSYM<D>]; lgssm_pinf<D>(P);
   if (D == 1) { Pz[0] = s * P[0]; return; }
@@ -137,7 +164,7 @@ template <int D> __device__ __forceinline__ void lgssm_pinf_jordan(double s, dou
   for (int i = 0; i < NSYM<D>; i++) Pz[i] = s * R[i];
 }
 // T = U(a) X  (h = a^2/2; X, T row-major D x D; the last row is X's own)
-template <int D> __device__ __forceinline__ void jordan_rows(double a, double h, const double* X, double* T) {
+template <int D, class F> __device__ __forceinline__ void jordan_rows(F a, F h, const F* X, F* T) {
 #pragma unroll
   for (int j = 0; j < D; j++) {
     if (D == 1) T[j] = X[j];
@@ -145,23 +172,23 @@ template <int D> __device__ __forceinline__ void jordan_rows(double a, double h,
     else { T[j] = fma(h, X[2 * D + j], fma(a, X[D + j], X[j])); T[D + j] = fma(a, X[2 * D + j], X[D + j]); T[2 * D + j] = X[2 * D + j]; }
   }
 }
-template <int D> __device__ __forceinline__ void jordan_vec(double a, double h, const double* x, double* u) {
+template <int D, class F> __device__ __forceinline__ void jordan_vec(F a, F h, const F* x, F* u) {
   if (D == 1) u[0] = x[0];
   else if (D == 2) { u[0] = fma(a, x[1], x[0]); u[1] = x[1]; }
   else { u[0] = fma(h, x[2], fma(a, x[1], x[0])); u[1] = fma(a, x[2], x[1]); u[2] = x[2]; }
 }
 // R = e2 U(a) S U(a)'  (S, R symmetric packed)
-template <int D> __device__ __forceinline__ void jordan_congruence(double a, double h, double e2, const double* S, double* R) {
+template <int D, class F> __device__ __forceinline__ void jordan_congruence(F a, F h, F e2, const F* S, F* R) {
   if (D == 1) { R[0] = e2 * S[0]; }
   else if (D == 2) {
-    const double t01 = fma(a, S[2], S[1]), t00 = fma(a, S[1], S[0]);
+    const F t01 = fma(a, S[2], S[1]), t00 = fma(a, S[1], S[0]);
     R[0] = e2 * fma(a, t01, t00); R[1] = e2 * t01; R[2] = e2 * S[2];
   } else {      // packed [00 01 02 11 12 22]
-    const double t02 = fma(h, S[5], fma(a, S[4], S[2]));
-    const double t01 = fma(h, S[4], fma(a, S[3], S[1]));
-    const double t00 = fma(h, S[2], fma(a, S[1], S[0]));
-    const double t12 = fma(a, S[5], S[4]);
-    const double t11 = fma(a, S[4], S[3]);
+    const F t02 = fma(h, S[5], fma(a, S[4], S[2]));
+    const F t01 = fma(h, S[4], fma(a, S[3], S[1]));
+    const F t00 = fma(h, S[2], fma(a, S[1], S[0]));
+    const F t12 = fma(a, S[5], S[4]);
+    const F t11 = fma(a, S[4], S[3]);
     R[0] = e2 * fma(h, t02, fma(a, t01, t00));
     R[1] = e2 * fma(a, t02, t01);
     R[2] = e2 * t02;
