@@ -41,6 +41,7 @@ SIGNATURES = {
     "gpar_dtc_logpdf_zgrad": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double,
                                              _c_double_p, _c_double_p, _c_double_p]),
     "gpar_scaled_dtc": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
+    "gpar_scaled_dtc_batch": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int32, _c_double_p, ctypes.POINTER(ctypes.c_int32)]),
     "gpar_scaled_dtc_grad": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_compute_q_u": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p,
                                         _c_double_p, _c_double_p]),

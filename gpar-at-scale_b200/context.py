@@ -170,6 +170,15 @@ class Context:
         self._check(self._lib.gpar_scaled_dtc(self._h, int(k_time), int(k_out), dptr(th), ctypes.byref(val), dptr(A)))
         return (val.value, A) if return_A else val.value
 
+    def scaled_dtc_batch(self, k_time, k_out, thetas):
+        """thetas: (ncand, 5) candidates on the resident data, evaluated concurrently on the context's lanes ->
+        (dtc (ncand,), codes (ncand,): non-zero where a Cholesky failed, value NaN)."""
+        th = as_f64(np.atleast_2d(thetas))
+        out = np.zeros(th.shape[0]); codes = np.zeros(th.shape[0], dtype=np.int32)
+        self._check(self._lib.gpar_scaled_dtc_batch(self._h, int(k_time), int(k_out), dptr(th), th.shape[0], dptr(out),
+                                                    codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out, codes
+
     def scaled_dtc_grad(self, k_time, k_out, theta):
         """-> (dtc, d dtc / d theta (5,))."""
         th = as_f64(np.asarray(theta).ravel())

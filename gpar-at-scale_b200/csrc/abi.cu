@@ -102,6 +102,8 @@ int gpar_ctx_create(int device, gpar_ctx** out) {
 
 int gpar_ctx_destroy(gpar_ctx* ctx) {
   if (!ctx) return GPAR_OK;
+  for (gpar_ctx* lane : ctx->lanes) gpar_ctx_destroy(lane);
+  ctx->lanes.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);

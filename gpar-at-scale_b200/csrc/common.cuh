@@ -18,15 +18,18 @@
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;          // a view of another context's resident buffer (lanes of the batched entry points): never freed here
+  void borrow(const DevBuf& o) { if (!borrowed) release(); p = o.p; cap = o.cap; borrowed = true; }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    if (borrowed) return cudaErrorInvalidValue;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -67,6 +70,9 @@ struct gpar_ctx {
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   DevBuf chain; int64_t chain_n = 0;                  // values passed down the GPAR chain (gpar_group_broadcast / gpar_set_inputs_column)
   void* pinned = nullptr; size_t pinned_cap = 0;
+  // lanes: worker contexts on the same device (own streams and scratch, resident data borrowed from this context) that
+  // evaluate hyper-parameter candidates concurrently (gpar_scaled_dtc_batch)
+  std::vector<gpar_ctx*> lanes;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;
 };

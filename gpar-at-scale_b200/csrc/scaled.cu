@@ -18,6 +18,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
+#include <thread>
+#include <chrono>
+#include <limits>
 
 int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
 bool gpar_needs_whitened_panel(const double minmax[2]);
@@ -924,6 +927,66 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
   // dtc.jl:122-125 with logdet(noise_matrix) = sum log S_k
   *dtc = -0.5 * ((double)N * LOG2PI_S + st.sum_logS + hs[0] + st.sum_a2 - hs[1]);
+  return GPAR_OK;
+}
+
+// `ncand` hyper-parameter candidates of the scaled objective on the SAME resident data (the simplex vertices x
+// restarts that the Nelder-Mead loop dtc.jl:58-61 evaluates one after the other).  At the reference's own sizes
+// (N = 8 496, M = 50 ... 156) one evaluation is ~30 short, latency-bound launches on an otherwise idle device, so the
+// candidates run CONCURRENTLY: up to 16 lanes — worker contexts on the same device with their own streams and scratch,
+// the resident (X, Z, t, y) borrowed from this context — each driven by a host thread through the ordinary single-
+// candidate path (bit-identical values).  Problems whose operand panel exceeds 256 MB per lane run on this context
+// alone, one candidate after the other.  codes (nullable): per candidate 0 or GPAR_ERR_NOT_POSDEF (its value is NaN);
+// with codes == NULL such a failure fails the call.  gpar_last_timing then reports the wall-clock time of the batch.
+int gpar_scaled_dtc_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int32_t ncand, double* dtc, int32_t* codes) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!thetas || !dtc || ncand < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_batch: thetas and dtc must not be NULL, ncand >= 1");
+  CHK(check_scaled(ctx, "scaled_dtc_batch"));
+  CU(cudaSetDevice(ctx->device));
+  const int Mpad = ((int)ctx->M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
+  const size_t panel_bytes = (size_t)((ctx->N + GPAR_KT - 1) / GPAR_KT * GPAR_KT) * Mpad * sizeof(double);
+  int max_lanes = 16;
+  if (const char* e = getenv("GPAR_LANES")) max_lanes = std::max(1, std::min(64, atoi(e)));
+  const int W = panel_bytes > ((size_t)256 << 20) ? 1 : std::min<int>(ncand, max_lanes);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<int> rc(ncand, GPAR_OK);
+  int64_t launches = 0;
+  if (W == 1) {
+    for (int c = 0; c < ncand; c++) { rc[c] = gpar_scaled_dtc(ctx, k_time, k_out, thetas + 5 * c, dtc + c, nullptr); launches += ctx->last_launches; }
+  } else {
+    while ((int)ctx->lanes.size() < W) {
+      gpar_ctx* lane = nullptr;
+      if (gpar_ctx_create(ctx->device, &lane) != GPAR_OK) return gpar_fail(ctx, GPAR_ERR_CUDA, "scaled_dtc_batch: cannot create lane %d", (int)ctx->lanes.size());
+      ctx->lanes.push_back(lane);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));            // resident data complete before other streams read it
+    for (int w = 0; w < W; w++) {
+      gpar_ctx* l = ctx->lanes[w];
+      l->X.borrow(ctx->X); l->Z.borrow(ctx->Z); l->t.borrow(ctx->t); l->y.borrow(ctx->y); l->rvec.borrow(ctx->rvec);
+      l->D = ctx->D; l->Dz = ctx->Dz; l->ybatch = ctx->ybatch; l->N = ctx->N; l->M = ctx->M; l->Nt = ctx->Nt; l->Ny = ctx->Ny; l->Nr = ctx->Nr;
+      l->has_rvec = ctx->has_rvec; l->t_reg_dt = ctx->t_reg_dt;
+    }
+    std::vector<std::thread> th;
+    std::vector<int64_t> ln(W, 0);
+    for (int w = 0; w < W; w++)
+      th.emplace_back([&, w]() {
+        gpar_ctx* l = ctx->lanes[w];
+        for (int c = w; c < ncand; c += W) { rc[c] = gpar_scaled_dtc(l, k_time, k_out, thetas + 5 * c, dtc + c, nullptr); ln[w] += l->last_launches; }
+      });
+    for (auto& t : th) t.join();
+    for (int w = 0; w < W; w++) launches += ln[w];
+  }
+  ctx->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  ctx->last_launches = launches;
+  for (int c = 0; c < ncand; c++) {
+    if (codes) codes[c] = rc[c] == GPAR_ERR_NOT_POSDEF ? rc[c] : 0;
+    if (rc[c] == GPAR_ERR_NOT_POSDEF) dtc[c] = std::numeric_limits<double>::quiet_NaN();
+    if (rc[c] != GPAR_OK && !(codes && rc[c] == GPAR_ERR_NOT_POSDEF)) {
+      gpar_ctx* src = W == 1 ? ctx : ctx->lanes[c % W];
+      const std::string msg = src->err;
+      return gpar_fail(ctx, rc[c], "scaled_dtc_batch: candidate %d: %s", c, msg.c_str());
+    }
+  }
   return GPAR_OK;
 }
 

@@ -120,6 +120,13 @@ int gpar_dtc_logpdf_zgrad(gpar_ctx* ctx, int kernel, const double theta[3], int 
 int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc,
                     double* A_or_null);
 
+/* `ncand` hyper-parameter candidates of the same objective on the SAME resident data (NEW): thetas is
+ * 5 x ncand column-major — the simplex vertices x restarts that the Nelder-Mead loop dtc.jl:58-61 evaluates one after
+ * the other — evaluated concurrently on up to 16 internal lanes (streams + scratch of their own) of this device; every
+ * value is bit-identical to gpar_scaled_dtc.  codes (nullable, ncand): 0 or GPAR_ERR_NOT_POSDEF (value NaN); with
+ * codes == NULL a failed Cholesky fails the call.  gpar_last_timing reports the wall-clock ms of the batch. */
+int gpar_scaled_dtc_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int32_t ncand, double* dtc, int32_t* codes);
+
 /* The same objective with its gradient d dtc / d theta[0..4] (NEW — the reference optimises it with
  * Nelder-Mead, dtc.jl:58-61; a gradient lets Optim.LBFGS replace it). */
 int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], double* dtc, double* grad);

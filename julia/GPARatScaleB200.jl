@@ -87,6 +87,15 @@ function scaled_dtc(c::Ctx, k_time, k_out, theta::Vector{Float64}, N::Integer, M
     return val[], A
 end
 
+"compute_gpar_dtc_objective for the columns of `thetas` (5 x ncand) at once, on the resident data (simplex vertices x restarts
+of the loop dtc.jl:58-61): (values, codes); a candidate whose Cholesky fails has value NaN and a non-zero code."
+function scaled_dtc_batch(c::Ctx, k_time, k_out, thetas::Matrix{Float64})
+    n = size(thetas, 2); vals = zeros(n); codes = zeros(Int32, n)
+    check(c, ccall((:gpar_scaled_dtc_batch, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Int32}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), thetas, n, vals, codes))
+    return vals, codes
+end
+
 "compute_gpar_dtc_objective with d/d theta (5) — for Optim.LBFGS in place of NelderMead (dtc.jl:58-61)."
 function scaled_dtc_grad(c::Ctx, k_time, k_out, theta::Vector{Float64})
     val = Ref{Float64}(0.0); grad = zeros(5)

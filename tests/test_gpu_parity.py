@@ -1024,3 +1024,43 @@ def test_lgssm_logpdf_one_pass_equals_three_phase(ctx, kind, monkeypatch):
     ref = cport.kalman_filter_batch(kind, tt, Y, pp[:, 0], pp[:, 1] ** 2, pp[:, 2] ** 2, rvec=rv)
     assert relerr(lml, ref) <= RTOL
     ctx.set_noise_vector(None)
+
+
+def test_scaled_dtc_batch_of_candidates(ctx):
+    """gpar_scaled_dtc_batch: the candidates of the Nelder-Mead loop dtc.jl:58-61 evaluated concurrently on
+    the context's lanes.  Every value is bit-identical to the single-candidate entry point (same kernels, same order) and
+    within 1e-8 of the oracle; a candidate whose Cholesky fails is flagged without failing the others; the resident data
+    can change between batches (the lanes borrow it anew); a lock-step Nelder-Mead over restarts walks the simplices of
+    separate runs."""
+    from gpar_at_scale_b200 import neldermead
+    rng = np.random.default_rng(81)
+    n, m, d, B = 2000, 50, 2, 37
+    t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    ths = rng.uniform(-1.0, 0.3, (B, 5))
+    vals, codes = ctx.scaled_dtc_batch(3, 3, ths)
+    assert vals.shape == (B,) and np.all(codes == 0)
+    for c in range(B):
+        assert vals[c] == ctx.scaled_dtc(3, 3, ths[c]), c
+    for c in (0, 17, 36):
+        v0 = scaled_gpar_objective(ths[c], X, Z, t, y, k_out=3, k_time=3, decorrelate=cport.kalman_decorrelate)
+        assert abs(vals[c] - v0) <= RTOL * abs(v0)
+    # new resident data, other kernels, fewer candidates than lanes
+    n2 = 700; t2 = np.sort(rng.uniform(0, 20, n2)); X2 = rng.normal(size=(n2, 1)); y2 = rng.normal(size=n2)
+    ctx.set_inputs(X2); ctx.set_pseudo(np.linspace(-2, 2, 17)[:, None]); ctx.set_times(t2); ctx.set_outputs(y2)
+    v2, c2 = ctx.scaled_dtc_batch(2, 0, ths[:3])
+    assert np.all(c2 == 0) and all(v2[c] == ctx.scaled_dtc(2, 0, ths[c]) for c in range(3))
+    # an indefinite candidate among good ones: duplicated pseudo-inputs and a vanishing jitter
+    Zd = np.repeat(np.linspace(-2, 2, 9), 2)[:, None]
+    ctx.set_pseudo(Zd)
+    bad = np.array([0.0, 0.0, 0.0, 0.0, -40.0])
+    v3, c3 = ctx.scaled_dtc_batch(2, 0, np.stack([ths[0], bad, ths[1]]))
+    assert c3[0] == 0 and c3[2] == 0 and np.isfinite(v3[0]) and np.isfinite(v3[2])
+    assert (c3[1] != 0 and np.isnan(v3[1])) or np.isfinite(v3[1])     # (the 1e-3 floor of unpack_gpar may still let it factor)
+    # lock-step Nelder-Mead over restarts
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    X0 = rng.random((5, 5))
+    res = neldermead.optimize_batch(lambda P: -ctx.scaled_dtc_batch(3, 3, P)[0], X0, iterations=12)
+    for k in range(5):
+        one = neldermead.optimize(lambda th: -ctx.scaled_dtc(3, 3, th), X0[k], iterations=12)
+        assert res[k].minimum == one.minimum and res[k].f_calls == one.f_calls

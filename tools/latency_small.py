@@ -26,3 +26,12 @@ print("scaled_dtc N=8496 M=81 D=2: %.3f ms/eval (device %.3f, launches %d)" % (b
 Xe = rng.normal(size=(156, 5)); ctx.set_inputs(Xe); ctx.set_pseudo(Xe); ctx.set_times(np.arange(156) / 256.0); ctx.set_outputs(rng.normal(size=156))
 print("scaled_dtc EEG N=M=156 D=5: %.3f ms/eval (device %.3f)" % (bench(lambda: ctx.scaled_dtc(3, 3, th5)), ctx.last_timing()[0]))
 print("exact_logpdf GPAR N=156 D=5: %.3f ms/eval (device %.3f)" % (bench(lambda: ctx.exact_logpdf(3, 3, th5)), ctx.last_timing()[0]))
+# batched candidates (gpar_scaled_dtc_batch) at the reference's own size
+X = y_obs[0][:, None]; Z = np.linspace(X.min(), X.max(), 50)[:, None]
+ctx.set_times(x); ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y_obs[1])
+ths = np.tile(th5, (64, 1)) + 0.05 * rng.normal(size=(64, 5))
+for lanes in (1, 4, 8, 16, 32):
+    os.environ["GPAR_LANES"] = str(lanes)
+    ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
+    print("scaled_dtc_batch N=8496 M=50, 64 candidates, %2d lanes: %.3f ms per batch = %.4f ms per candidate" % (lanes, ms, ms / 64))
+os.environ.pop("GPAR_LANES")
