@@ -136,6 +136,7 @@ function sample_q_u(c::Ctx, k_time, k_out, params::Vector{Float64}, seed::Intege
 end
 
 "logpdf(lgssm, y) for every resident sequence; theta is 3 x batch_theta (column per model)."
+# (with ONE resident sequence and several columns in `theta`, the columns are hyper-parameter candidates: pass batch = size(theta, 2))
 function lgssm_logpdf(c::Ctx, k, theta::VecOrMat{Float64}, batch::Integer)
     lml = zeros(batch)
     check(c, ccall((:gpar_lgssm_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int32, Ptr{Float64}),
@@ -170,6 +171,15 @@ function exact_logpdf(c::Ctx, k_time, k_out, theta::Vector{Float64}, batch::Inte
     check(c, ccall((:gpar_exact_logpdf, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int32, Ptr{Float64}),
                    c.h, kernel_code(k_time), kernel_code(k_out), theta, length(theta), lml))
     return lml
+end
+
+"`ncand` hyper-parameter candidates (columns of `thetas`, 3 or 5 rows) of the exact log-pdf in one launch — the simplex
+vertices x restarts of optimized.jl:45,164: (lml (batch x ncand), codes); a failed Cholesky gives NaN and a non-zero code."
+function exact_logpdf_batch(c::Ctx, k_time, k_out, thetas::Matrix{Float64}, batch::Integer = 1)
+    n = size(thetas, 2); lml = zeros(batch, n); codes = zeros(Int32, n)
+    check(c, ccall((:gpar_exact_logpdf_batch, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Int32}),
+                   c.h, kernel_code(k_time), kernel_code(k_out), thetas, size(thetas, 1), n, lml, codes))
+    return lml, codes
 end
 
 function exact_posterior(c::Ctx, k_time, k_out, theta::Vector{Float64}, Xs::Matrix{Float64}, batch::Integer = 1)
