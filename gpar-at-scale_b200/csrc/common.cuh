@@ -109,6 +109,30 @@ struct CallTimer {
     CU(cudaGetLastError());                                                               \
   } while (0)
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream still runs; it must
+// execute pdl_wait() before it touches anything the predecessor writes.  A predecessor that calls pdl_trigger() early
+// lets the dependent's CTAs become resident (and run their prologue) underneath it.
+#define LAUNCH_PDL(ctx, kern, grid, block, smem, ...)                                       \
+  do {                                                                                    \
+    cudaLaunchConfig_t cfg_ = {};                                                         \
+    cfg_.gridDim = (grid); cfg_.blockDim = (block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = (ctx)->stream; \
+    cudaLaunchAttribute at_[1];                                                           \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at_[0].val.programmaticStreamSerializationAllowed = 1; \
+    cfg_.attrs = at_; cfg_.numAttrs = 1;                                                  \
+    CU(cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__));                                     \
+    (ctx)->launches++;                                                                    \
+  } while (0)
+__device__ __forceinline__ void pdl_wait() {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+
 struct GpParams { double l, var, s, sigma, noise; double dl, ds_dv, dn; };
 // exp(theta)+1e-3 (src/util.jl:36-43), s = var^2, noise = sigma^2; d*/dtheta chain factors.
 static inline GpParams unpack_gp3(const double* th) {

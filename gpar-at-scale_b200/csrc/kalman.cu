@@ -138,6 +138,8 @@ scan_span_kernel(Level cur, Level up, int batch, int span, int K) {
   const int start = blockIdx.x * span, end = min(start + span, cur.n);
   const int64_t fstride = (int64_t)batch * cur.P, off0 = (int64_t)b * cur.P;
   if (threadIdx.x == 0) { Elem id; id.set_identity(); store_elem(id, sh, NW + 1, NW); }
+  pdl_trigger();
+  pdl_wait();                                      // (launched as a programmatic dependent of the pass that writes `cur`)
   __syncthreads();
   for (int base = start; base < end; base += NW * 32 * K) {
     const int my0 = base + threadIdx.x * K, my1 = min(my0 + K, end);
@@ -669,6 +671,7 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
   typedef Scalar<F> SC;
   constexpr int NC = SC::NC;
   const int64_t gidx = (int64_t)blockIdx.x * TPB + threadIdx.x, ntot = (int64_t)batch * nC;
+  pdl_trigger();                                   // the scan's CTAs may become resident underneath this pass
   if (gidx >= ntot) return;
   if (gidx < batch) tickets[gidx] = 0;            // per-sequence tickets of the fused final reduction (kf_chunk_lml_kernel)
   const int b = (int)(gidx / nC), c = (int)(gidx % nC);
@@ -715,10 +718,18 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
   const F a_reg = sp.reg_dt * il, e_reg = REG ? exp_nonpos(-lam * a_reg) : F(1.0);
   double t_cur = REG ? 0.0 : __ldg(t + k0);
   F a_cur = REG ? (k0 == 0 ? il : a_reg) : (t_cur - ((k0 == 0) ? t_cur - 1.0 : __ldg(t + k0 - 1))) * il;     // step 0 follows the t[0] - 1 prefix
+  if (value_of(a_cur) > 1e4) a_cur = F(1e4);
   F e_cur = exp_nonpos(-lam * a_cur);
   const int nsteps = (int)(k1 - k0);
   int slot = 0, wslot = PD * TPB;           // ring positions (in doubles) of the group read now / issued now
-  for (int j = 0; j < nsteps; j++) {
+  // Phi is carried as g * PhiHat: the scalar e^{-lam a} of every transition goes into g (one multiplication) instead of
+  // into the nine entries, and is folded back every 16 steps (PhiHat grows at most by (1 + a + a^2/2) per step; a is
+  // clamped at 1e4, far beyond the point where e^{-lam a} has underflowed, so 16 steps cannot overflow)
+  F g = 1.0;
+  for (int j0 = 0; j0 < nsteps; j0 += 16) {
+  const int j1 = j0 + 16 < nsteps ? j0 + 16 : nsteps;
+#pragma unroll 1
+  for (int j = j0; j < j1; j++) {
     F T[D * D], u[D], Cn[NSYM<D>], col[D], Kg[D], hr[D];
     cp_async_wait<PD - 1>();
     const double y_cur = sy[slot];
@@ -727,14 +738,16 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     if constexpr (!REG) {
       const double t_next = st[slot];                  // (beyond the sequence: the clamped copy gives a = 0, never used)
       a_cur = (t_next - t_cur) * il; t_cur = t_next;
+      if (value_of(a_cur) > 1e4) a_cur = F(1e4);
       e_cur = exp_nonpos(-lam * a_cur);
     } else { a_cur = a_reg; e_cur = e_reg; }
     issue(j + PD, wslot);
     slot = slot + TPB == RING * TPB ? 0 : slot + TPB; wslot = wslot + TPB == RING * TPB ? 0 : wslot + TPB;
     jordan_rows<D, F>(a, h, Phi, T);                      // the scalar e is applied where the rows are used
     jordan_vec<D, F>(a, h, bv, u);
+    g = g * ee;
 #pragma unroll
-    for (int i = 0; i < D; i++) { u[i] = u[i] * ee; hr[i] = ee * T[i]; }        // hr = H A Phi
+    for (int i = 0; i < D; i++) { u[i] = u[i] * ee; hr[i] = g * T[i]; }         // hr = H A Phi
     jordan_congruence<D, F>(a, h, ee * ee, dC, Cn);
 #pragma unroll
     for (int i = 0; i < D; i++) col[i] = SYM(Cn, i, 0) + SYM(P0, i, 0);
@@ -750,13 +763,10 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
 #pragma unroll
       for (int j = i; j < D; j++) SYM(J, i, j) = fma(hi, hr[j], SYM(J, i, j));
     }
-    const F omk = 1.0 - Kg[0];
 #pragma unroll
-    for (int j = 0; j < D; j++) Phi[j] = omk * hr[j];                      // row 0: e T_0 - Kg_0 hr = (1 - Kg_0) hr
+    for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int i = 1; i < D; i++)
-#pragma unroll
-      for (int j = 0; j < D; j++) Phi[i * D + j] = fma(-Kg[i], hr[j], ee * T[i * D + j]);
+      for (int jj = 0; jj < D; jj++) Phi[i * D + jj] = fma(-Kg[i], T[jj], T[i * D + jj]);       // PhiHat <- (I - K H) U PhiHat
 #pragma unroll
     for (int i = 0; i < D; i++) bv[i] = fma(Kg[i], r, u[i]);
 #pragma unroll
@@ -766,6 +776,10 @@ kf_chunk_element_kernel(const double* __restrict__ t, const double* __restrict__
     sum_q = fma(w, r, sum_q);
     prodS = prodS * S;         // S > 0 and normal: mantissa stays in [1, 2), the exponent goes to the integer accumulator
     peel_exponent(prodS, eacc);
+  }
+#pragma unroll
+  for (int i = 0; i < D * D; i++) Phi[i] = Phi[i] * g;
+  g = 1.0;
   }
   cp_async_wait<0>();
   const F sum_logS = log(prodS) + (double)eacc * 0.693147180559945309417232121458;
@@ -794,6 +808,7 @@ kf_chunk_lml_kernel(Level l0, Level l1, int span, int nC, int batch, const doubl
   __shared__ double sh[32];
   __shared__ int last;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  pdl_wait();
   F r0 = 0.0, r1 = 0.0;
   if (c < nC) {
     const int64_t ntot = (int64_t)batch * nC, idx = (int64_t)b * nC + c;
@@ -988,16 +1003,16 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   if constexpr (NC > 1) {
     if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
   } else if (two_level) {
-    LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(n1, batch), 128, 0, f0, f1, batch, span, 2);
-    LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f1, none, batch, n1, std::min(8, (n1 + 255) / 256));
+    LAUNCH_PDL(ctx, (scan_span_kernel<FE, 4>), dim3(n1, batch), dim3(128), 0, f0, f1, batch, span, 2);
+    LAUNCH_PDL(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), dim3(256), 0, f1, none, batch, n1, std::min(8, (n1 + 255) / 256));
   } else if (nC > 1) {        // one block per sequence; few sequences: more warps, many sequences: more elements per lane
     const int want_lanes = batch >= 256 ? (nC + 2) / 3 : (nC + 1) / 2;
-    if (want_lanes > 128) LAUNCH(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), 256, 0, f0, none, batch, span, std::min(8, (nC + 255) / 256));
-    else if (want_lanes > 64) LAUNCH(ctx, (scan_span_kernel<FE, 4>), dim3(1, batch), 128, 0, f0, none, batch, span, (nC + 127) / 128);
-    else if (want_lanes > 64 / 2) LAUNCH(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), 64, 0, f0, none, batch, span, (nC + 63) / 64);
-    else LAUNCH(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), 32, 0, f0, none, batch, span, (nC + 31) / 32);
+    if (want_lanes > 128) LAUNCH_PDL(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), dim3(256), 0, f0, none, batch, span, std::min(8, (nC + 255) / 256));
+    else if (want_lanes > 64) LAUNCH_PDL(ctx, (scan_span_kernel<FE, 4>), dim3(1, batch), dim3(128), 0, f0, none, batch, span, (nC + 127) / 128);
+    else if (want_lanes > 64 / 2) LAUNCH_PDL(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), dim3(64), 0, f0, none, batch, span, (nC + 63) / 64);
+    else LAUNCH_PDL(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), dim3(32), 0, f0, none, batch, span, (nC + 31) / 32);
   }
-  LAUNCH(ctx, (kf_chunk_lml_kernel<D, F>), dim3(nblk, batch), 128, 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.dlml, o.sums);
+  LAUNCH_PDL(ctx, (kf_chunk_lml_kernel<D, F>), dim3(nblk, batch), dim3(128), 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.dlml, o.sums);
   return GPAR_OK;
 }
 

@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"onepass": os.environ.get("GPAR_KF_ONEPASS", "1"), "variant": os.environ.get("GPAR_KF1_VARIANT", "0"), "L": os.environ.get("GPAR_KF_L", "auto"), "pf": os.environ.get("GPAR_KF1_PREFETCH"),
                       "cfg3_filter_ms": round(a, 4), "cfg3_launches": la, "1x10M_irregular_ms": round(c, 4), "1x10M_launches": lc}))
 else:
-    runs = [("1", v, pf) for v in ("0", "1", "2", "3", "4") for pf in ("0",)]
+    runs = [("1", v, pf) for v in ("0", "1", "1") for pf in ("0",)]
     for op, v, L in runs:
         env = dict(os.environ); env["GPAR_KF_ONEPASS"] = op; env["GPAR_KF1_VARIANT"] = v
         env["GPAR_KF1_PREFETCH"] = L
