@@ -218,7 +218,7 @@ int panel_syrk_run(gpar_ctx* ctx, const double* panelK, const double* panelD, in
 // sums (nullable): per sequence (sum log S, sum alpha^2).
 int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
               const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
-              double* d_table, double* d_sums);
+              double* d_table, double* d_sums, double* d_table_fwd = nullptr);      // (smoother runs: d_table = backward table, d_table_fwd = filter table)
 // forward-mode variant: values and two tangents (dirs = tangent slot 0/1/-1 of l, s, noise) in one pass
 int lgssm_run_tangent(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
                       const double* t, const double* y, const double* rvec, const int dirs[3],

@@ -406,8 +406,8 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
         for (int j = 1; j < NC; j++) dalpha[((int64_t)(j - 1) * batch + b) * N + k] = SC::comp(a, j);
       }
     }
-    if constexpr (!SMOOTH) {
-      if (table) {   // shared-model step table for the affine mean scans (scaled.cu)
+    {
+      if (table) {   // shared-model step table for the affine mean scans (scaled.cu, smooth_shared.cu)
         constexpr int TS = D * D + 2 * D + 1;
         double* row = table + k * TS;
         double* drow = nullptr;
@@ -933,6 +933,7 @@ struct LgssmOut {
   double* dlml = nullptr; double* dalpha = nullptr; double* dtable = nullptr;    // tangent outputs (Dual runs)
   double* fstate = nullptr;      // per sequence (m, P) after the last step
   int64_t ystride = 0;           // distance between sequences in y / alpha (0: N)
+  double* table_fwd = nullptr;   // smoother runs: the forward (filter) step table next to the backward one in `table`
   bool ybroadcast = false;       // every "sequence" of the batch reads the SAME y (hyper-parameter candidates on one sequence)
 };
 
@@ -1057,7 +1058,7 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
     if (smooth) {
       const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
       LAUNCH(ctx, (kf_chunk_filter_kernel<D, true, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, s0,
-             (double*)nullptr, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr);
+             o.table_fwd, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr);
       if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
       CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
       LAUNCH(ctx, ks_backward_kernel<D>, g3b, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var, o.table);     // (smoother: o.table = backward table)
@@ -2172,13 +2173,14 @@ int upload_params(gpar_ctx* ctx, const double* hl, const double* hs, const doubl
 // params: host arrays (nparam = 1 or batch) of positive (l, s, noise).
 int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const double* hn, int nparam, int batch, int64_t N,
               const double* t, const double* y, const double* rvec, double* d_alpha, double* d_lml, double* d_mean, double* d_var,
-              double* d_table, double* d_sums) {
+              double* d_table, double* d_sums, double* d_table_fwd) {
   if (N < 1 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: need at least one time step and one sequence");
-  if (d_table && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
+  if (d_table_fwd && !d_mean) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: a separate forward table belongs to a smoother run");
+  if ((d_table || d_table_fwd) && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
   SeqParams sp;
   CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
   if (t == ctx->t.as<double>()) sp.reg_dt = ctx->t_reg_dt;
-  LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums;
+  LgssmOut o; o.alpha = d_alpha; o.lml = d_lml; o.mean = d_mean; o.var = d_var; o.table = d_table; o.sums = d_sums; o.table_fwd = d_table_fwd;
   o.ybroadcast = ctx->y_broadcast;
   // log-pdf only on short sequences: the one-pass path (constant transition, no exponentials) beats the steady-state
   // scheme, whose 2048-step transient is a large share of a 10k-step sequence (1024 x 10k: 0.25 -> 0.13 ms)
@@ -2264,8 +2266,10 @@ int gpar_lgssm_logpdf(gpar_ctx* ctx, int kernel, const double* theta, int32_t ba
   std::vector<double> hl(batch_theta), hs(batch_theta), hn(batch_theta);
   for (int b = 0; b < batch_theta; b++) { GpParams p = unpack_gp3(theta + 3 * b); hl[b] = p.l; hs[b] = p.s; hn[b] = p.noise; }
   CU(ctx->kal_d.reserve((size_t)batch * sizeof(double)));
-  bool shared_path = batch_theta == 1 && batch >= 4;      // one model, many sequences: covariance recursion once (smooth_shared.cu)
-  if (const char* e = getenv("GPAR_FILTER_SHARED")) shared_path = shared_path && atoi(e) != 0;
+  // one model, many sequences: covariance recursion once (smooth_shared.cu) — unless the whole batch is so small that the
+  // fixed cost of that path (two transposes, a single-sequence table run) exceeds the one-pass path (1024 x 10k: 0.20 vs 0.15 ms)
+  bool shared_path = batch_theta == 1 && batch >= 4 && (double)batch * (double)ctx->Nt > 1.5e7;
+  if (const char* e = getenv("GPAR_FILTER_SHARED")) shared_path = batch_theta == 1 && batch >= 4 && atoi(e) != 0;
   for (int attempt = 0; attempt < 2; attempt++) {      // a second pass only when the steady-state path flagged a model it cannot handle
     int rc;
     if (shared_path) {

@@ -263,8 +263,8 @@ int smooth_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
   double* mst = lml1 + 16;
   double* a2part = ex ? mst + (size_t)N * D * Sp : nullptr;
   // the data-independent part, once: forward table from a filter pass, backward table from a smoother pass (one sequence)
-  CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, nullptr, nullptr, table, lml1 + 2));     // lml1[2] = sum log S
-  CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, m1, v1, table2, nullptr));
+  // (one smoother run leaves both tables and the sums: lml1[2] = sum log S)
+  CHK(lgssm_run(ctx, kind, &l, &s, &noise, 1, 1, N, t, y1, rvec, nullptr, lml1, m1, v1, table2, lml1 + 2, table));
   dim3 grid(Sp / 128, nch);
   LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, (double*)nullptr, (double*)nullptr);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, false>), nch, 32, 0, table, TS, 0, N, LC, psi);

@@ -367,7 +367,12 @@ def test_lgssm_smooth_shared_model_path(ctx, kind, n, batch):
         assert relerr(lml, l0) <= RTOL
         # the filter-only shared path: logpdf with one theta for all sequences, decorrelate
         lf0, a0 = cport.kalman_filter_batch(kind, t, Y, pp[0], pp[1] ** 2, pp[2] ** 2, rvec=rvec, want_alpha=True)
-        assert relerr(ctx.lgssm_logpdf(kind, th), lf0) <= RTOL
+        assert relerr(ctx.lgssm_logpdf(kind, th), lf0) <= RTOL               # (small batches: the one-pass path)
+        os.environ["GPAR_FILTER_SHARED"] = "1"                                # force the shared-model filter path
+        try:
+            assert relerr(ctx.lgssm_logpdf(kind, th), lf0) <= RTOL
+        finally:
+            del os.environ["GPAR_FILTER_SHARED"]
         lf, alpha = ctx.lgssm_decorrelate(kind, th)
         assert relerr(lf, lf0) <= RTOL and np.max(np.abs(alpha - a0)) <= 1e-8 * max(1.0, np.max(np.abs(a0)))
         assert np.max(np.abs(mean - m0)) <= 1e-8 * max(1.0, np.max(np.abs(m0)))
