@@ -14,6 +14,7 @@
 // 24 + 8 B/step backward).
 #include "lgssm_math.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 struct SharedSmoothExtra { const double* var1; const double* sum_logS; const double* a2part; int nch; };   // device pointers into ctx->shbuf
 
@@ -253,6 +254,7 @@ int smooth_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
   constexpr int TS = D * D + 2 * D + 1, TS2 = 2 * D * D;
   // chunk length: enough threads to fill the machine, multiple of 32
   int LC = (int)std::min<int64_t>(1024, std::max<int64_t>(64, ((int64_t)Sp * N / 150000 + 31) / 32 * 32));
+  if (const char* e = getenv("GPAR_SH_LC")) { int v = atoi(e); if (v >= 32 && v <= 4096 && v % 32 == 0) LC = v; }      // tuning knob
   const int nch = (int)((N + LC - 1) / LC);
   const size_t state_doubles = (size_t)nch * D * Sp;
   // tables | psi | states | single-sequence scratch (alpha-free: lml, mean, var) | filtered means of all sequences
@@ -284,6 +286,7 @@ int filter_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
                     const double* rvec, const double* yt, int Sp, double* alpha_t, SharedSmoothExtra* ex) {
   constexpr int TS = D * D + 2 * D + 1;
   int LC = (int)std::min<int64_t>(1024, std::max<int64_t>(64, ((int64_t)Sp * N / 150000 + 31) / 32 * 32));
+  if (const char* e = getenv("GPAR_SH_LC")) { int v = atoi(e); if (v >= 32 && v <= 4096 && v % 32 == 0) LC = v; }      // tuning knob
   const int nch = (int)((N + LC - 1) / LC);
   const size_t state_doubles = (size_t)nch * D * Sp;
   CU(ctx->shbuf.reserve(((size_t)N * TS + (size_t)nch * D * D + state_doubles + 16 + (size_t)nch * Sp) * sizeof(double)));
