@@ -307,7 +307,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
                        SeqParams sp, int64_t N, int L, int nC, Level l0, Level l1, int batch,
                        double* __restrict__ alpha, double* __restrict__ part, double* __restrict__ fs, Level s0,
                        double* __restrict__ table, double* __restrict__ dalpha, double* __restrict__ dtable,
-                       int64_t ystride, double* __restrict__ fstate) {
+                       int64_t ystride, double* __restrict__ fstate, int64_t astride, int64_t tstride) {
   typedef Scalar<F> SC;
   constexpr int NC = SC::NC;
   const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (sequence, chunk) jointly, as in the summary pass
@@ -399,7 +399,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
     prodS = prodS * S;
     if (((k - k0) & 7) == 7) { sum_logS += log(prodS); prodS = 1.0; }
     sum_a2 = fma(a, a, sum_a2);
-    if (alpha) alpha[(int64_t)b * ystride + k] = value_of(a);
+    if (alpha) alpha[(int64_t)b * astride + k] = value_of(a);      // (astride != ystride when the sequences share one y: candidates)
     if constexpr (NC > 1) {
       if (dalpha) {
 #pragma unroll
@@ -409,7 +409,7 @@ kf_chunk_filter_kernel(const double* __restrict__ t, const double* __restrict__ 
     {
       if (table) {   // shared-model step table for the affine mean scans (scaled.cu, smooth_shared.cu)
         constexpr int TS = D * D + 2 * D + 1;
-        double* row = table + k * TS;
+        double* row = table + ((int64_t)b * tstride + k) * TS;      // tstride = N: one table per sequence (candidates); 0: batch == 1
         double* drow = nullptr;
         if constexpr (NC > 1) { if (dtable) drow = dtable + k * (2 + (NC - 1) * TS); }
         const F iS = 1.0 / S;
@@ -1022,13 +1022,14 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
   constexpr int NC = Scalar<F>::NC;
   typedef FiltElem<D, F> FE;
   const bool smooth = o.mean != nullptr;
-  if (o.ybroadcast && (o.alpha || o.mean)) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: candidates on one sequence yield log-pdfs only");
+  if (o.ybroadcast && o.mean) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: candidates on one sequence: no smoother");
   {      // nothing per step asked for: the log-pdf (and its tangents) needs one pass over the data
     bool onepass = !smooth && !o.alpha && !o.table && !o.fstate && !o.dalpha && !o.dtable;
     if (const char* e = getenv("GPAR_KF_ONEPASS")) onepass = onepass && atoi(e) != 0;       // testing knob: 0 = three-phase path
     if (onepass) return lgssm_logpdf_onepass<D, F>(ctx, sp, batch, N, t, y, rvec, o);
   }
   const int64_t ystride = o.ybroadcast ? 0 : (o.ystride > 0 ? o.ystride : N);
+  const int64_t astride = o.ybroadcast ? N : ystride, tstride = batch > 1 ? N : 0;
   // chunk length: long chunks amortise the scan (P2), short chunks keep small problems parallel
   const int64_t total_steps = N * (int64_t)batch;
   int L = total_steps <= (1 << 19) ? 8 : (total_steps <= (1 << 21) ? 16 : 32);
@@ -1058,18 +1059,18 @@ int lgssm_run_d(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const double*
     if (smooth) {
       const Level s0 = spn.lv[0], s1 = spn.lv.size() > 1 ? spn.lv[1] : none;
       LAUNCH(ctx, (kf_chunk_filter_kernel<D, true, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, s0,
-             o.table_fwd, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr);
+             o.table_fwd, (double*)nullptr, (double*)nullptr, ystride, (double*)nullptr, astride, tstride);
       if (s0.P > nC) { dim3 gp((s0.P - nC + 127) / 128, batch); LAUNCH(ctx, smooth_pad_kernel<D>, gp, 128, 0, s0, nC, batch); }
       CHK(run_scan<SmoothElem<D>>(ctx, spn, batch));
       LAUNCH(ctx, ks_backward_kernel<D>, g3b, 128, 0, t, sp, N, L, nC, s0, s1, batch, fs, o.mean, o.var, o.table);     // (smoother: o.table = backward table)
     } else {
       LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, double>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
-             o.table, (double*)nullptr, (double*)nullptr, ystride, o.fstate);
+             o.table, (double*)nullptr, (double*)nullptr, ystride, o.fstate, astride, tstride);
     }
   } else {
     if (smooth) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: the smoother has no tangent mode");
     LAUNCH(ctx, (kf_chunk_filter_kernel<D, false, F>), g3, 128, 0, t, y, rvec, sp, N, L, nC, f0, f1, batch, o.alpha, part, fs, none,
-           o.table, o.dalpha, o.dtable, ystride, (double*)nullptr);
+           o.table, o.dalpha, o.dtable, ystride, (double*)nullptr, astride, tstride);
   }
   double* part2 = part + (size_t)batch * nC * 2 * NC;
   LAUNCH(ctx, lml_partial_kernel<NC>, dim3(nslice, batch), 256, 0, part, nC, nslice, part2);
@@ -2176,7 +2177,7 @@ int lgssm_run(gpar_ctx* ctx, int kind, const double* hl, const double* hs, const
               double* d_table, double* d_sums, double* d_table_fwd) {
   if (N < 1 || batch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: need at least one time step and one sequence");
   if (d_table_fwd && !d_mean) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: a separate forward table belongs to a smoother run");
-  if ((d_table || d_table_fwd) && batch != 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
+  if ((d_table || d_table_fwd) && batch != 1 && !(ctx->y_broadcast && !d_table_fwd)) return gpar_fail(ctx, GPAR_ERR_INVALID, "lgssm: step table needs batch == 1");
   SeqParams sp;
   CHK(upload_params(ctx, hl, hs, hn, nparam, &sp));
   if (t == ctx->t.as<double>()) sp.reg_dt = ctx->t_reg_dt;

@@ -24,6 +24,8 @@
 
 int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
 bool gpar_needs_whitened_panel(const double minmax[2]);
+bool scaled_small_applicable(const gpar_ctx* ctx);
+int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int ncand, double* vals, int* codes);
 int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2);
 
 namespace {
@@ -933,7 +935,8 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
 // `ncand` hyper-parameter candidates of the scaled objective on the SAME resident data (the simplex vertices x
 // restarts that the Nelder-Mead loop dtc.jl:58-61 evaluates one after the other).  At the reference's own sizes
 // (N = 8 496, M = 50 ... 156) one evaluation is ~30 short, latency-bound launches on an otherwise idle device, so the
-// candidates run CONCURRENTLY: up to 16 lanes — worker contexts on the same device with their own streams and scratch,
+// candidates share ONE launch sequence when the M x M tail fits shared memory (scaled_small.cu: the candidate is a grid
+// dimension of a batched filter, a whitening, a SYRK and a tail kernel); larger problems run CONCURRENTLY: up to 16 lanes — worker contexts on the same device with their own streams and scratch,
 // the resident (X, Z, t, y) borrowed from this context — each driven by a host thread through the ordinary single-
 // candidate path (bit-identical values).  Problems whose operand panel exceeds 256 MB per lane run on this context
 // alone, one candidate after the other.  codes (nullable): per candidate 0 or GPAR_ERR_NOT_POSDEF (its value is NaN);
@@ -943,6 +946,31 @@ int gpar_scaled_dtc_batch(gpar_ctx* ctx, int k_time, int k_out, const double* th
   if (!thetas || !dtc || ncand < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_batch: thetas and dtc must not be NULL, ncand >= 1");
   CHK(check_scaled(ctx, "scaled_dtc_batch"));
   CU(cudaSetDevice(ctx->device));
+  // the reference's own sizes: one fused launch sequence for all candidates (scaled_small.cu); a candidate it hands back
+  // (cov(u) too poorly conditioned for the collapsed statistic) goes through the whitened-panel path below
+  bool fused = scaled_small_applicable(ctx);
+  if (const char* e = getenv("GPAR_SCALED_SMALL")) fused = fused && atoi(e) != 0;
+  if (fused) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<int> cd(ncand, 0);
+    ctx->launches = 0;
+    CHK(scaled_small_batch(ctx, k_time, k_out, thetas, ncand, dtc, cd.data()));
+    int64_t launches = ctx->launches;
+    for (int c = 0; c < ncand; c++) {
+      if (cd[c] == -1) {
+        const int r = gpar_scaled_dtc(ctx, k_time, k_out, thetas + 5 * c, dtc + c, nullptr);
+        launches += ctx->last_launches;
+        if (r != GPAR_OK && r != GPAR_ERR_NOT_POSDEF) return r;
+        cd[c] = r;
+        if (r != GPAR_OK) dtc[c] = std::numeric_limits<double>::quiet_NaN();
+      }
+      if (codes) codes[c] = cd[c];
+      else if (cd[c] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "scaled_dtc_batch: candidate %d: a Cholesky factorisation failed", c);
+    }
+    ctx->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->last_launches = launches;
+    return GPAR_OK;
+  }
   const int Mpad = ((int)ctx->M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
   const size_t panel_bytes = (size_t)((ctx->N + GPAR_KT - 1) / GPAR_KT * GPAR_KT) * Mpad * sizeof(double);
   int max_lanes = 16;

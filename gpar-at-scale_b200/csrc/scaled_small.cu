@@ -1,0 +1,469 @@
+// scaled_small.cu — MANY hyper-parameter candidates of the scaled-GPAR objective at the reference's own problem sizes.
+//
+// The Nelder-Mead loop of the reference (src/gp/dtc.jl:58-61) evaluates compute_gpar_dtc_objective (dtc.jl:83-128)
+// hundreds of times on data of N = 8 496 points and M = 50 ... 81 pseudo-inputs; one evaluation through the large-
+// problem pipeline (scaled.cu) is ~30 short launches = 0.4 ms of latency on an otherwise idle B200.  Here `ncand`
+// candidates (simplex vertices x restarts) share ONE launch sequence, the candidate being a grid dimension:
+//   1. the LGSSM filter of the time kernel on (t, y) for all candidates at once — kalman.cu's chunked scan with one
+//      parameter set per "sequence", every sequence reading the same y — leaves per candidate the step table
+//      (Phi_k, K_k, H A_k, S_k^-1/2), alpha, sum log S_k and sum alpha_k^2                       (dtc.jl:106);
+//   2. beta[:, m] = decorrelate(cov(f, u)[:, m]) for every pseudo-input (dtc.jl:108-117), chunked along time like the
+//      whitening of scaled.cu: ss_walk_kernel<false> (zero-start chunk responses; a thread per column, so a step's table
+//      row and input point are staged once per block and read as shared-memory broadcasts), ss_chunk_product_kernel +
+//      ss_carry_kernel (start state of every chunk), ss_walk_kernel<true> (beta through a transposing tile, g = beta' alpha);
+//   3. ss_syrk_kernel: G = beta' beta, 32 x 32 tiles of the lower triangle, split along N (partial sums added in fixed
+//      order by the tail), operands staged in shared memory with register prefetch;
+//   4. ss_tail_kernel: one CTA per candidate, matrices in shared memory: cov(u) = Kuu + sigma^2 I (dtc.jl:35,119),
+//      L_u, Lambda = I + L_u^-1 G L_u^-T, L_Lambda, c = L_Lambda^-1 L_u^-1 g and the value (dtc.jl:122-125).
+// This is the collapsed form of the objective (G, g instead of A = L_u^-1 beta'), as in scaled.cu; a candidate whose
+// cov(u) is too poorly conditioned for it — (max / min diag L_u)^2 > GPAR_ROBUST_COND, the same test — is handed back to
+// the caller, which evaluates it through the whitened-panel path of gpar_scaled_dtc.
+#include "lgssm_math.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <limits>
+#include <vector>
+
+namespace {
+
+constexpr int SS_TILE = 32;                 // SYRK tile
+constexpr double LOG2PI_SS = 1.8378770664093454835606594728112;
+
+struct SmallCand { double inv_l2, out_s, noise; };      // per candidate: 1 / out_l^2, out_s = out_var^2, noise = sigma^2
+
+template <int KIND>
+__device__ __forceinline__ double ss_kernel_value(const double* __restrict__ x, const double* __restrict__ z, int DX, double inv_l2, double s) {
+  double d2 = 0.0;
+  for (int d = 0; d < DX; d++) { const double df = x[d] - z[d]; d2 = fma(df, df, d2); }
+  double dummy;
+  return s * base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
+}
+
+__device__ __forceinline__ void ss_cp8(double* smem, const double* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void ss_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NP> __device__ __forceinline__ void ss_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NP) : "memory"); }
+
+// Ordered product of the step matrices of every whitening chunk, Psi_c = Phi_{k1-1} ... Phi_{k0}: a warp per (chunk,
+// candidate), each lane a contiguous run of steps, then an ordered shuffle tree.
+template <int D>
+__global__ void __launch_bounds__(32)
+ss_chunk_product_kernel(const double* __restrict__ table, int64_t N, int Lc, int nch, double* __restrict__ psi) {
+  constexpr int TS = D * D + 2 * D + 1;
+  const int c = blockIdx.x, cd = blockIdx.y, lane = threadIdx.x;
+  const double* tab = table + (int64_t)cd * N * TS;
+  const int per = Lc / 32;
+  const int64_t k0 = (int64_t)c * Lc + (int64_t)lane * per;
+  double P[D * D];
+#pragma unroll
+  for (int i = 0; i < D * D; i++) P[i] = (i / D == i % D) ? 1.0 : 0.0;
+  for (int q = 0; q < per; q++) {
+    const int64_t k = k0 + q;
+    if (k < N) {
+      double F[D * D], R[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; i++) F[i] = __ldg(tab + k * TS + i);
+      matmul<D>(F, P, R);
+#pragma unroll
+      for (int i = 0; i < D * D; i++) P[i] = R[i];
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {       // after round d, lane l (l % 2d == 0) holds the product of lanes l .. l+2d-1 (later lanes on the left)
+    double O[D * D], R[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) O[i] = __shfl_down_sync(0xffffffffu, P[i], d);
+    matmul<D>(O, P, R);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) P[i] = R[i];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < D * D; i++) psi[((int64_t)cd * nch + c) * D * D + i] = P[i];
+  }
+}
+
+// The whitening walk of one chunk: a thread per pseudo-input (column), so that a step's table row and input point are
+// read ONCE per block (staged through shared memory in tiles of 32 steps, broadcast reads) instead of once per column.
+// FINAL = false: zero-start response of the chunk -> state[cd][c][i][m].
+// FINAL = true : from the carried start state (same array): beta = (u - HA x) / sqrt(S) written through a transposing
+//                shared-memory tile into beta[cd][m][n] (coalesced 256-byte runs), g partial sums -> gpart[cd][c][m].
+template <int KIND, int D, bool FINAL>
+__global__ void __launch_bounds__(128)
+ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int DX, int64_t N, int M, int Mp, int64_t Ns, int Lc, int nch,
+               const SmallCand* __restrict__ cand, const double* __restrict__ table, const double* __restrict__ alpha,
+               double* __restrict__ state, double* __restrict__ beta, double* __restrict__ gpart) {
+  constexpr int TS = D * D + 2 * D + 1;
+  extern __shared__ double sm[];
+  // [2][32][TS] table rows | [2][32][DX] inputs | [2][32] alpha | (FINAL) [32][Mp + 1] beta tile
+  double* stab = sm; double* sx = stab + 2 * 32 * TS; double* sal = sx + 2 * 32 * DX; double* tile = sal + 2 * 32;
+  const int m = threadIdx.x, c = blockIdx.x, cd = blockIdx.y;
+  const int64_t k0 = (int64_t)c * Lc;
+  const int ntile = Lc / 32;
+  const double* tab = table + (int64_t)cd * N * TS;
+  const double* al = alpha + (int64_t)cd * N;
+  const SmallCand cp = cand[cd];
+  const bool live = m < M;
+  double z[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) z[d] = (live && d < DX) ? Z[(int64_t)m * DX + d] : 0.0;
+  auto stage = [&](int tl, int buf) {
+    const int64_t kb = k0 + (int64_t)tl * 32;
+    const int64_t rows = N - kb < 32 ? (N - kb > 0 ? N - kb : 0) : 32;       // steps of this tile inside the sequence
+    for (int e = threadIdx.x; e < rows * TS; e += blockDim.x) ss_cp8(stab + buf * 32 * TS + e, tab + kb * TS + e);
+    for (int e = threadIdx.x; e < rows * DX; e += blockDim.x) ss_cp8(sx + buf * 32 * DX + e, X + kb * DX + e);
+    if (FINAL) for (int e = threadIdx.x; e < rows; e += blockDim.x) ss_cp8(sal + buf * 32 + e, al + kb + e);
+    ss_commit();
+  };
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) x[i] = FINAL ? state[(((int64_t)cd * nch + c) * D + i) * Mp + m] : 0.0;
+  double gacc = 0.0;
+  stage(0, 0);
+  for (int tl = 0; tl < ntile; tl++) {
+    const int buf = tl & 1;
+    if (tl + 1 < ntile) { stage(tl + 1, buf ^ 1); ss_wait<1>(); } else ss_wait<0>();
+    __syncthreads();
+    const int64_t kb = k0 + (int64_t)tl * 32;
+    const int rows = (int)(N - kb < 32 ? (N - kb > 0 ? N - kb : 0) : 32);
+    for (int sidx = 0; sidx < 32; sidx++) {
+      double bval = 0.0;
+      if (sidx < rows) {
+        const double* row = stab + (buf * 32 + sidx) * TS;
+        double u = 0.0;
+        if (live) {
+          double d2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < 8; d++) if (d < DX) { const double df = sx[(buf * 32 + sidx) * DX + d] - z[d]; d2 = fma(df, df, d2); }
+          double dummy;
+          u = cp.out_s * base_kernel_dev<KIND, false>(d2 * cp.inv_l2, dummy);
+        }
+        if (FINAL) {
+          double pred = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; j++) pred = fma(row[D * D + D + j], x[j], pred);
+          bval = (u - pred) * row[D * D + 2 * D];
+          gacc = fma(bval, sal[buf * 32 + sidx], gacc);
+        }
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) { double a = row[D * D + i] * u;
+#pragma unroll
+          for (int j = 0; j < D; j++) a = fma(row[i * D + j], x[j], a);
+          nx[i] = a; }
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = nx[i];
+      }
+      if (FINAL) tile[sidx * (Mp + 1) + m] = bval;
+    }
+    if (FINAL) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * Mp; e += blockDim.x) {
+        const int col = e >> 5, sidx = e & 31;
+        if (kb + sidx < Ns) beta[((int64_t)cd * Mp + col) * Ns + kb + sidx] = tile[sidx * (Mp + 1) + col];
+      }
+    }
+    __syncthreads();
+  }
+  if (FINAL) gpart[((int64_t)cd * nch + c) * Mp + m] = gacc;
+  else {
+#pragma unroll
+    for (int i = 0; i < D; i++) state[(((int64_t)cd * nch + c) * D + i) * Mp + m] = x[i];
+  }
+}
+
+// start state of every chunk, in place of its zero-start response: in[0] = 0, in[c+1] = Psi_c in[c] + resp[c]
+template <int D>
+__global__ void ss_carry_kernel(const double* __restrict__ psi, double* __restrict__ state, int nch, int Mp) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x, cd = blockIdx.y;
+  if (m >= Mp) return;
+  double st[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) st[i] = 0.0;
+  for (int c = 0; c < nch; c++) {
+    double r[D], nx[D];
+    const double* ps = psi + ((int64_t)cd * nch + c) * D * D;
+#pragma unroll
+    for (int i = 0; i < D; i++) { double* p = state + (((int64_t)cd * nch + c) * D + i) * Mp + m; r[i] = *p; *p = st[i]; }
+#pragma unroll
+    for (int i = 0; i < D; i++) { double a = r[i];
+#pragma unroll
+      for (int j = 0; j < D; j++) a = fma(__ldg(ps + i * D + j), st[j], a);
+      nx[i] = a; }
+#pragma unroll
+    for (int i = 0; i < D; i++) st[i] = nx[i];
+  }
+}
+
+// Gp (per candidate and split: Mp x Mp, both triangles written) = beta' beta over the split's steps.  Block (pair, split,
+// cand): 32 x 32 tile (ti >= tj), 2 x 2 entries per thread, operands through shared memory in slabs of 32 steps, the next
+// slab fetched into registers while the current one is multiplied.
+__global__ void __launch_bounds__(256)
+ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_per_split, int nsplit, double* __restrict__ Gp) {
+  __shared__ double As[SS_TILE][SS_TILE + 1], Bs[SS_TILE][SS_TILE + 1];
+  int p = blockIdx.x, ti = 0;
+  while (p > ti) { p -= ti + 1; ti++; }
+  const int tj = p, sp = blockIdx.y, cd = blockIdx.z;
+  const double* ba = beta + ((int64_t)cd * Mp + ti * SS_TILE) * Ns;
+  const double* bb = beta + ((int64_t)cd * Mp + tj * SS_TILE) * Ns;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;       // loader: row group (8 rows per pass), step
+  const int64_t nslab = Ns / SS_TILE;
+  const int64_t s0 = (int64_t)sp * slabs_per_split, s1 = s0 + slabs_per_split < nslab ? s0 + slabs_per_split : nslab;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double ra[4], rb[4];
+  if (s0 < s1) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ra[q] = ba[(int64_t)(lr + 8 * q) * Ns + s0 * SS_TILE + lc]; rb[q] = bb[(int64_t)(lr + 8 * q) * Ns + s0 * SS_TILE + lc]; }
+  }
+  for (int64_t sl = s0; sl < s1; sl++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { As[lr + 8 * q][lc] = ra[q]; Bs[lr + 8 * q][lc] = rb[q]; }
+    __syncthreads();
+    if (sl + 1 < s1) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) { ra[q] = ba[(int64_t)(lr + 8 * q) * Ns + (sl + 1) * SS_TILE + lc]; rb[q] = bb[(int64_t)(lr + 8 * q) * Ns + (sl + 1) * SS_TILE + lc]; }
+    }
+#pragma unroll 8
+    for (int k = 0; k < SS_TILE; k++) {
+      const double a0 = As[ty][k], a1 = As[ty + 16][k], b0 = Bs[tx][k], b1 = Bs[tx + 16][k];
+      acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  double* Gc = Gp + ((int64_t)cd * nsplit + sp) * Mp * Mp;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int gi = ti * SS_TILE + ty + 16 * i, gj = tj * SS_TILE + tx + 16 * j;
+      Gc[(int64_t)gi + (int64_t)gj * Mp] = acc[i][j];
+      Gc[(int64_t)gj + (int64_t)gi * Mp] = acc[i][j];
+    }
+}
+
+// In-place Cholesky (lower, column-major, leading dimension ld) of the M x M matrix A in shared memory by the whole
+// block; returns the 1-based index of the first non-positive pivot (0: success) through *info (shared).
+__device__ void ss_chol_inplace(double* A, int M, int ld, int* info) {
+  for (int j = 0; j < M; j++) {
+    __syncthreads();
+    if (*info) return;
+    const double d = A[j + j * ld];
+    if (!(d > 0.0)) { __syncthreads(); if (threadIdx.x == 0) *info = j + 1; __syncthreads(); return; }
+    const double inv = 1.0 / sqrt(d);
+    __syncthreads();
+    for (int i = j + threadIdx.x; i < M; i += blockDim.x) A[i + j * ld] *= inv;        // column j: L_jj = sqrt(d), L_ij = A_ij / L_jj
+    __syncthreads();
+    // trailing update of the lower triangle: A_ik -= L_ij L_kj for k > j, i >= k
+    const int rem = M - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int k = j + 1 + e / rem, i = j + 1 + e % rem;
+      if (i >= k) A[i + k * ld] = fma(-A[i + j * ld], A[k + j * ld], A[i + k * ld]);
+    }
+  }
+  __syncthreads();
+}
+// v <- L^-1 v for a lower-triangular L in shared memory (column-oriented substitution, one barrier per column)
+__device__ void ss_trsv_inplace(const double* L, int M, int ld, double* v) {
+  for (int j = 0; j < M; j++) {
+    __syncthreads();
+    const double cj = v[j] / L[j + j * ld];
+    __syncthreads();
+    if (threadIdx.x == 0) v[j] = cj;
+    for (int i = j + 1 + threadIdx.x; i < M; i += blockDim.x) v[i] = fma(-L[i + j * ld], cj, v[i]);
+  }
+  __syncthreads();
+}
+
+// out per candidate: [value, code]; code 0 ok, 1 / 2: Cholesky of cov(u) / Lambda failed, 3: cov(u) too poorly conditioned
+// for the collapsed statistic (the caller re-evaluates the candidate through the whitened-panel path)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, const SmallCand* __restrict__ cand,
+               const double* __restrict__ Gp, int nsplit, const double* __restrict__ gpart, int nch, const double* __restrict__ sums,
+               double cond_thr, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const int ld = M | 1;                                  // odd leading dimension: conflict-free columns and rows
+  double* Lu = sm; double* B = Lu + (size_t)ld * M; double* v = B + (size_t)ld * M;
+  __shared__ int info;
+  __shared__ double red[32];
+  const int cd = blockIdx.x;
+  const SmallCand c = cand[cd];
+  if (threadIdx.x == 0) info = 0;
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int i = e % M, j = e / M;
+    Lu[i + j * ld] = ss_kernel_value<KIND>(Z + (int64_t)i * DX, Z + (int64_t)j * DX, DX, c.inv_l2, c.out_s) + (i == j ? c.noise : 0.0);
+    double g = 0.0;
+    for (int q = 0; q < nsplit; q++) g += Gp[((int64_t)cd * nsplit + q) * Mp * Mp + i + (int64_t)j * Mp];        // fixed order
+    B[i + j * ld] = g;
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    double g = 0.0;
+    for (int c2 = 0; c2 < nch; c2++) g += gpart[((int64_t)cd * nch + c2) * Mp + i];
+    v[i] = g;
+  }
+  __syncthreads();
+  ss_chol_inplace(Lu, M, ld, &info);
+  if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 1.0; } return; }
+  {   // conditioning estimate of cov(u): (max / min of diag L_u)^2
+    double mn = 1e300, mx = 0.0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { const double d = Lu[i + i * ld]; mn = fmin(mn, d); mx = fmax(mx, d); }
+    for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mn; red[8 + (threadIdx.x >> 5)] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < (int)(blockDim.x >> 5); q++) { mn = fmin(mn, red[q]); mx = fmax(mx, red[8 + q]); }
+      const double rr = mx / mn;
+      if (rr * rr > cond_thr) info = -1;
+    }
+    __syncthreads();
+    if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 3.0; } return; }
+  }
+  // B <- L_u^-1 G L_u^-T: forward substitution down every column (a thread per column), transpose, again
+  for (int pass = 0; pass < 2; pass++) {
+    for (int col = threadIdx.x; col < M; col += blockDim.x) {
+      for (int i = 0; i < M; i++) {
+        double a = B[i + col * ld];
+        for (int k = 0; k < i; k++) a = fma(-Lu[i + k * ld], B[k + col * ld], a);
+        B[i + col * ld] = a / Lu[i + i * ld];
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M * M; e += blockDim.x) {       // in-place transpose
+      const int i = e % M, j = e / M;
+      if (i > j) { const double t1 = B[i + j * ld]; B[i + j * ld] = B[j + i * ld]; B[j + i * ld] = t1; }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) B[i + i * ld] += 1.0;
+  ss_trsv_inplace(Lu, M, ld, v);                          // L_u^-1 g
+  ss_chol_inplace(B, M, ld, &info);
+  if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 2.0; } return; }
+  ss_trsv_inplace(B, M, ld, v);                           // c = L_Lambda^-1 L_u^-1 g
+  double ld2 = 0.0, cc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { ld2 += log(B[i + i * ld]); cc = fma(v[i], v[i], cc); }
+  ld2 = block_sum(ld2, red); cc = block_sum(cc, red);
+  if (threadIdx.x == 0) {
+    const double sum_logS = sums[2 * cd], sum_a2 = sums[2 * cd + 1];
+    out[2 * cd] = -0.5 * ((double)N * LOG2PI_SS + sum_logS + 2.0 * ld2 + sum_a2 - cc);      // dtc.jl:122-125
+    out[2 * cd + 1] = 0.0;
+  }
+}
+
+struct SmallPlan { int D, DX, M, Mp, Lc, nch, nsplit, slabs_per_split, ncand; int64_t N, Ns; double cond_thr; };
+struct SmallBufs { const SmallCand* cand; const double *table, *alpha, *sums; double *beta, *Gp, *gpart, *state, *psi, *out; };
+
+template <int KIND, int D>
+int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
+  constexpr int TS = D * D + 2 * D + 1;
+  const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
+  const dim3 gwalk(p.nch, p.ncand);
+  const size_t sm0 = ((size_t)2 * 32 * TS + (size_t)2 * 32 * p.DX + 64) * sizeof(double);
+  const size_t sm1 = sm0 + (size_t)32 * (p.Mp + 1) * sizeof(double);
+  LAUNCH(ctx, ss_chunk_product_kernel<D>, gwalk, 32, 0, b.table, p.N, p.Lc, p.nch, b.psi);
+  LAUNCH(ctx, (ss_walk_kernel<KIND, D, false>), gwalk, p.Mp, sm0, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
+         b.state, b.beta, b.gpart);
+  LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 127) / 128, p.ncand), 128, 0, b.psi, b.state, p.nch, p.Mp);
+  LAUNCH(ctx, (ss_walk_kernel<KIND, D, true>), gwalk, p.Mp, sm1, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
+         b.state, b.beta, b.gpart);
+  const int T = p.Mp / SS_TILE;
+  LAUNCH(ctx, ss_syrk_kernel, dim3(T * (T + 1) / 2, p.nsplit, p.ncand), 256, 0, b.beta, p.Mp, p.Ns, p.slabs_per_split, p.nsplit, b.Gp);
+  const int ld = p.M | 1;
+  const size_t smem = ((size_t)2 * ld * p.M + p.M + 8) * sizeof(double);
+  CU(cudaFuncSetAttribute(ss_tail_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LAUNCH(ctx, ss_tail_kernel<KIND>, p.ncand, 256, smem, Z, p.DX, p.M, p.Mp, p.N, b.cand, b.Gp, p.nsplit, b.gpart, p.nch, b.sums, p.cond_thr, b.out);
+  return GPAR_OK;
+}
+template <int KIND>
+int ss_run_kind(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
+  switch (p.D) {
+    case 1: return ss_run_kd<KIND, 1>(ctx, p, b);
+    case 2: return ss_run_kd<KIND, 2>(ctx, p, b);
+    default: return ss_run_kd<KIND, 3>(ctx, p, b);
+  }
+}
+
+}  // namespace
+
+// Is the fused small-problem path applicable to the resident problem?  (M x M matrices of the tail in shared memory.)
+bool scaled_small_applicable(const gpar_ctx* ctx) {
+  const int64_t M = ctx->M, N = ctx->N;
+  const size_t smem = ((size_t)2 * (M | 1) * M + M + 8) * sizeof(double);
+  return M >= 1 && smem <= (size_t)200 * 1024 && N >= 64 && N <= ((int64_t)1 << 18) && ctx->D >= 1 && ctx->D <= 8;
+}
+
+// vals[c], codes[c] (0 ok; GPAR_ERR_NOT_POSDEF; -1: hand this candidate to the whitened-panel path) for the candidates
+// thetas (5 x ncand, raw parameters).  Everything on ctx->stream; one host synchronisation at the end.
+int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int ncand, double* vals, int* codes) {
+  const int D = k_time == GPAR_MATERN12 ? 1 : (k_time == GPAR_MATERN32 ? 2 : (k_time == GPAR_MATERN52 ? 3 : 0));
+  if (D == 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
+  if (k_out < GPAR_EQ || k_out > GPAR_MATERN52) return gpar_fail(ctx, GPAR_ERR_INVALID, "unknown output kernel code %d", k_out);
+  const int64_t N = ctx->N; const int M = (int)ctx->M, DX = ctx->D;
+  const int Mp = (M + SS_TILE - 1) / SS_TILE * SS_TILE;
+  const int64_t Ns = (N + SS_TILE - 1) / SS_TILE * SS_TILE;
+  const int TS = D * D + 2 * D + 1;
+  double cond_thr = 1e5;
+  if (const char* e = getenv("GPAR_ROBUST_COND")) cond_thr = atof(e);
+  // whitening chunks: a multiple of 32 steps, enough blocks (of Mp threads) to fill the device
+  const int want_chunks = std::max(1, (int)((int64_t)ctx->num_sms * 16 * 32 / ((int64_t)Mp * std::max(1, std::min(ncand, 64)))));
+  int Lc = (int)(((N + want_chunks - 1) / want_chunks + 31) / 32 * 32);
+  Lc = std::max(64, std::min(Lc, 2048));
+  const int nch = (int)((N + Lc - 1) / Lc);
+  const int T = Mp / SS_TILE, pairs = T * (T + 1) / 2;
+  const int64_t nslab = Ns / SS_TILE;
+  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)ctx->num_sms * 8 + (int64_t)pairs * std::min(ncand, 64) - 1) / ((int64_t)pairs * std::min(ncand, 64))));
+  nsplit = (int)std::min<int64_t>(nsplit, nslab);
+  const int slabs_per_split = (int)((nslab + nsplit - 1) / nsplit);
+  nsplit = (int)((nslab + slabs_per_split - 1) / slabs_per_split);
+  // candidates per pass: bounded scratch (table + alpha + beta + partial G + chunk states per candidate)
+  const size_t per_cand = ((size_t)N * (TS + 1) + (size_t)Mp * Ns + (size_t)nsplit * Mp * Mp + (size_t)nch * Mp * (D + 1) + (size_t)nch * D * D + 8) * sizeof(double)
+                          + sizeof(SmallCand);
+  const int group = (int)std::max<size_t>(1, std::min<size_t>(std::min(ncand, 64), ((size_t)1024 << 20) / per_cand));
+  CU(ctx->panelK.reserve(per_cand * group + 256));
+  char* base = ctx->panelK.as<char>();
+  double* table = reinterpret_cast<double*>(base);
+  double* alpha = table + (size_t)group * N * TS;
+  double* beta = alpha + (size_t)group * N;
+  double* Gp = beta + (size_t)group * Mp * Ns;
+  double* gpart = Gp + (size_t)group * nsplit * Mp * Mp;
+  double* state = gpart + (size_t)group * nch * Mp;
+  double* psi = state + (size_t)group * nch * D * Mp;
+  double* sums = psi + (size_t)group * nch * D * D;
+  double* out = sums + (size_t)2 * group;
+  SmallCand* cand = reinterpret_cast<SmallCand*>(out + (size_t)2 * group);
+  std::vector<double> hl(group), hs(group), hn(group), hout(2 * (size_t)group);
+  std::vector<SmallCand> hc(group);
+  for (int c0 = 0; c0 < ncand; c0 += group) {
+    const int nb = std::min(group, ncand - c0);
+    for (int c = 0; c < nb; c++) {
+      double pv[5];
+      for (int i = 0; i < 5; i++) pv[i] = exp(thetas[5 * (size_t)(c0 + c) + i]) + 1e-3;         // unpack_gpar (util.jl:45-55)
+      hl[c] = pv[0]; hs[c] = pv[1] * pv[1]; hn[c] = pv[4] * pv[4];
+      hc[c] = SmallCand{1.0 / (pv[2] * pv[2]), pv[3] * pv[3], pv[4] * pv[4]};
+    }
+    CU(cudaMemcpyAsync(cand, hc.data(), nb * sizeof(SmallCand), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->y_broadcast = true;
+    const int rc = lgssm_run(ctx, k_time, hl.data(), hs.data(), hn.data(), nb, nb, N, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
+                             alpha, nullptr, nullptr, nullptr, table, sums);
+    ctx->y_broadcast = false;
+    CHK(rc);
+    SmallPlan pl{D, DX, M, Mp, Lc, nch, nsplit, slabs_per_split, nb, N, Ns, cond_thr};
+    SmallBufs bf{cand, table, alpha, sums, beta, Gp, gpart, state, psi, out};
+    switch (k_out) {
+      case GPAR_EQ: CHK(ss_run_kind<GPAR_EQ>(ctx, pl, bf)); break;
+      case GPAR_MATERN12: CHK(ss_run_kind<GPAR_MATERN12>(ctx, pl, bf)); break;
+      case GPAR_MATERN32: CHK(ss_run_kind<GPAR_MATERN32>(ctx, pl, bf)); break;
+      default: CHK(ss_run_kind<GPAR_MATERN52>(ctx, pl, bf)); break;
+    }
+    CU(cudaMemcpyAsync(hout.data(), out, 2 * (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < nb; c++) {
+      const int code = (int)hout[2 * c + 1];
+      vals[c0 + c] = code == 0 ? hout[2 * c] : std::numeric_limits<double>::quiet_NaN();
+      codes[c0 + c] = code == 0 ? 0 : (code == 3 ? -1 : GPAR_ERR_NOT_POSDEF);
+    }
+  }
+  return GPAR_OK;
+}

@@ -122,8 +122,9 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
 
 /* `ncand` hyper-parameter candidates of the same objective on the SAME resident data (NEW): thetas is
  * 5 x ncand column-major — the simplex vertices x restarts that the Nelder-Mead loop dtc.jl:58-61 evaluates one after
- * the other — evaluated concurrently on up to 16 internal lanes (streams + scratch of their own) of this device; every
- * value is bit-identical to gpar_scaled_dtc.  codes (nullable, ncand): 0 or GPAR_ERR_NOT_POSDEF (value NaN); with
+ * the other.  When the M x M tail fits shared memory (M <= ~110: the reference's own sizes) all candidates share one fused
+ * launch sequence (values agree with gpar_scaled_dtc to ~1e-12 relative); otherwise they run concurrently on up to 16
+ * internal lanes (streams + scratch of their own) of this device, bit-identical to gpar_scaled_dtc.  codes (nullable, ncand): 0 or GPAR_ERR_NOT_POSDEF (value NaN); with
  * codes == NULL a failed Cholesky fails the call.  gpar_last_timing reports the wall-clock ms of the batch. */
 int gpar_scaled_dtc_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int32_t ncand, double* dtc, int32_t* codes);
 

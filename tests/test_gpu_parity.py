@@ -1031,41 +1031,55 @@ def test_lgssm_logpdf_one_pass_equals_three_phase(ctx, kind, monkeypatch):
     ctx.set_noise_vector(None)
 
 
-def test_scaled_dtc_batch_of_candidates(ctx):
-    """gpar_scaled_dtc_batch: the candidates of the Nelder-Mead loop dtc.jl:58-61 evaluated concurrently on
-    the context's lanes.  Every value is bit-identical to the single-candidate entry point (same kernels, same order) and
-    within 1e-8 of the oracle; a candidate whose Cholesky fails is flagged without failing the others; the resident data
-    can change between batches (the lanes borrow it anew); a lock-step Nelder-Mead over restarts walks the simplices of
-    separate runs."""
+def test_scaled_dtc_batch_of_candidates(ctx, monkeypatch):
+    """gpar_scaled_dtc_batch: the candidates of the Nelder-Mead loop dtc.jl:58-61 in one call.
+    Fused small-problem path (scaled_small.cu: batched filter -> whitening -> SYRK -> one-CTA tail): every value against
+    the oracle (1e-8) and against the single-candidate entry point (1e-10); a candidate with a poorly conditioned cov(u)
+    is handed to the whitened-panel path and keeps 1e-8; a failed Cholesky is flagged without failing the others.
+    Lane path (GPAR_SCALED_SMALL=0: concurrent single-candidate evaluations): bit-identical values, and a lock-step
+    Nelder-Mead over restarts walks exactly the simplices of separate runs."""
     from gpar_at_scale_b200 import neldermead
     rng = np.random.default_rng(81)
-    n, m, d, B = 2000, 50, 2, 37
+    for (n, m, d, kt, ko, B) in [(2000, 50, 2, 3, 3, 37), (8496, 81, 2, 3, 3, 5), (700, 17, 1, 2, 0, 3), (333, 33, 4, 1, 1, 9), (64, 1, 1, 3, 2, 2)]:
+        t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+        if n > 300:
+            t[n // 2] = t[n // 2 - 1]
+        ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+        ths = rng.uniform(-1.0, 0.3, (B, 5))
+        vals, codes = ctx.scaled_dtc_batch(kt, ko, ths)
+        assert vals.shape == (B,) and np.all(codes == 0)
+        for c in range(B):
+            one = ctx.scaled_dtc(kt, ko, ths[c])
+            assert abs(vals[c] - one) <= 1e-10 * abs(one), (n, m, c)
+        for c in (0, B - 1):
+            v0 = scaled_gpar_objective(ths[c], X, Z, t, y, k_out=ko, k_time=kt, decorrelate=cport.kalman_decorrelate)
+            assert abs(vals[c] - v0) <= RTOL * abs(v0)
+    # poorly conditioned cov(u) (nearly coincident pseudo-inputs, small jitter) among good candidates: handed back, still 1e-8
+    n, m = 1500, 24
+    t = np.sort(rng.uniform(0, 50, n)); X = rng.normal(size=(n, 1)); y = rng.normal(size=n)
+    Zc = np.sort(np.concatenate([np.linspace(-2, 2, 12), np.linspace(-2, 2, 12) + 1e-3]))[:, None]
+    ctx.set_inputs(X); ctx.set_pseudo(Zc); ctx.set_times(t); ctx.set_outputs(y)
+    ths = np.array([[0.0, 0.0, 0.5, 0.0, -3.0], [0.1, -0.2, 0.0, 0.1, -0.5], [0.0, 0.0, 0.5, 0.3, -3.5]])
+    vals, codes = ctx.scaled_dtc_batch(3, 0, ths)
+    assert np.all(codes == 0)
+    for c in range(3):
+        v0 = scaled_gpar_objective(ths[c], X, Zc, t, y, k_out=0, k_time=3, decorrelate=cport.kalman_decorrelate)
+        assert abs(vals[c] - v0) <= RTOL * abs(v0), c
+    # lane path: bit-identical to the single-candidate entry point; lock-step Nelder-Mead
+    monkeypatch.setenv("GPAR_SCALED_SMALL", "0")
+    n, m, d = 2000, 50, 2
     t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
     ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
-    ths = rng.uniform(-1.0, 0.3, (B, 5))
+    ths = rng.uniform(-1.0, 0.3, (21, 5))
     vals, codes = ctx.scaled_dtc_batch(3, 3, ths)
-    assert vals.shape == (B,) and np.all(codes == 0)
-    for c in range(B):
-        assert vals[c] == ctx.scaled_dtc(3, 3, ths[c]), c
-    for c in (0, 17, 36):
-        v0 = scaled_gpar_objective(ths[c], X, Z, t, y, k_out=3, k_time=3, decorrelate=cport.kalman_decorrelate)
-        assert abs(vals[c] - v0) <= RTOL * abs(v0)
-    # new resident data, other kernels, fewer candidates than lanes
-    n2 = 700; t2 = np.sort(rng.uniform(0, 20, n2)); X2 = rng.normal(size=(n2, 1)); y2 = rng.normal(size=n2)
-    ctx.set_inputs(X2); ctx.set_pseudo(np.linspace(-2, 2, 17)[:, None]); ctx.set_times(t2); ctx.set_outputs(y2)
-    v2, c2 = ctx.scaled_dtc_batch(2, 0, ths[:3])
-    assert np.all(c2 == 0) and all(v2[c] == ctx.scaled_dtc(2, 0, ths[c]) for c in range(3))
-    # an indefinite candidate among good ones: duplicated pseudo-inputs and a vanishing jitter
-    Zd = np.repeat(np.linspace(-2, 2, 9), 2)[:, None]
-    ctx.set_pseudo(Zd)
-    bad = np.array([0.0, 0.0, 0.0, 0.0, -40.0])
-    v3, c3 = ctx.scaled_dtc_batch(2, 0, np.stack([ths[0], bad, ths[1]]))
-    assert c3[0] == 0 and c3[2] == 0 and np.isfinite(v3[0]) and np.isfinite(v3[2])
-    assert (c3[1] != 0 and np.isnan(v3[1])) or np.isfinite(v3[1])     # (the 1e-3 floor of unpack_gpar may still let it factor)
-    # lock-step Nelder-Mead over restarts
-    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    assert np.all(codes == 0) and all(vals[c] == ctx.scaled_dtc(3, 3, ths[c]) for c in range(21))
     X0 = rng.random((5, 5))
     res = neldermead.optimize_batch(lambda P: -ctx.scaled_dtc_batch(3, 3, P)[0], X0, iterations=12)
     for k in range(5):
         one = neldermead.optimize(lambda th: -ctx.scaled_dtc(3, 3, th), X0[k], iterations=12)
         assert res[k].minimum == one.minimum and res[k].f_calls == one.f_calls
+    monkeypatch.delenv("GPAR_SCALED_SMALL")
+    # fused path under the same optimiser: same optimum to working precision
+    res2 = neldermead.optimize_batch(lambda P: -ctx.scaled_dtc_batch(3, 3, P)[0], X0, iterations=12)
+    for k in range(5):
+        assert abs(res2[k].minimum - res[k].minimum) <= 1e-8 * abs(res[k].minimum)

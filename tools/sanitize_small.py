@@ -31,5 +31,11 @@ for (n, m, d) in [(1, 1, 1), (37, 5, 2), (515, 131, 3), (4099, 257, 1)]:
     if d >= 2:
         ctx.exact_logpdf(0, 3, th5); ctx.exact_posterior(0, 3, th5, rng.normal(size=(7, d)))
     ctx.exact_posterior(3, 3, th3, rng.normal(size=(7, d)))
+    # round-2 entry points: gradients and batched candidates
+    ctx.set_outputs(y)
+    ctx.lgssm_logpdf_grad(3, th3); ctx.lgssm_logpdf(3, rng.uniform(-1, 0, (5, 3)))       # candidates on one sequence
+    ctx.scaled_dtc_grad(3, 3, th5); ctx.scaled_dtc_batch(3, 3, np.tile(th5, (3, 1)) + 0.01 * rng.normal(size=(3, 5)))
+    if n <= 200:
+        ctx.exact_logpdf_batch(3, 3, np.tile(th3, (4, 1)))
     print("ok", n, m, d)
 print("sanitize driver finished")
