@@ -31,6 +31,17 @@ constexpr double LOG2PI_SS = 1.8378770664093454835606594728112;
 
 struct SmallCand { double inv_l2, out_s, noise; };      // per candidate: 1 / out_l^2, out_s = out_var^2, noise = sigma^2
 
+// kappa(r), r = ||x - z|| / l, with the branch-free exponential of lgssm_math.cuh (argument <= 0): ~1 ulp from the
+// library exp of base_kernel_dev, a third fewer FP64 issue slots
+template <int KIND>
+__device__ __forceinline__ double ss_kappa_r(double r) {
+  if (KIND == GPAR_EQ) return exp_nonpos(-0.5 * r * r);
+  if (KIND == GPAR_MATERN12) return exp_nonpos(-r);
+  if (KIND == GPAR_MATERN32) { const double a = 1.7320508075688772935274463415059 * r; return (1.0 + a) * exp_nonpos(-a); }
+  const double a = 2.2360679774997896964091736687313 * r;
+  return (1.0 + a + a * a * (1.0 / 3.0)) * exp_nonpos(-a);
+}
+
 template <int KIND>
 __device__ __forceinline__ double ss_kernel_value(const double* __restrict__ x, const double* __restrict__ z, int DX, double inv_l2, double s) {
   double d2 = 0.0;
@@ -86,9 +97,10 @@ ss_chunk_product_kernel(const double* __restrict__ table, int64_t N, int Lc, int
 
 // The whitening walk of one chunk: a thread per pseudo-input (column), so that a step's table row and input point are
 // read ONCE per block (staged through shared memory in tiles of 32 steps, broadcast reads) instead of once per column.
-// FINAL = false: zero-start response of the chunk -> state[cd][c][i][m].
-// FINAL = true : from the carried start state (same array): beta = (u - HA x) / sqrt(S) written through a transposing
-//                shared-memory tile into beta[cd][m][n] (coalesced 256-byte runs), g partial sums -> gpart[cd][c][m].
+// FINAL = false: zero-start response of the chunk -> state[cd][c][i][m]; the kernel values u = cov(f, u)[n, m] are parked
+//                in beta[cd][m][n] through a transposing shared-memory tile (coalesced 256-byte runs).
+// FINAL = true : from the carried start state (same array), reading u back through the tile (no second exp / sqrt per
+//                element): beta = (u - HA x) / sqrt(S) overwrites it, g partial sums -> gpart[cd][c][m].
 template <int KIND, int D, bool FINAL>
 __global__ void __launch_bounds__(128)
 ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int DX, int64_t N, int M, int Mp, int64_t Ns, int Lc, int nch,
@@ -96,23 +108,25 @@ ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int D
                double* __restrict__ state, double* __restrict__ beta, double* __restrict__ gpart) {
   constexpr int TS = D * D + 2 * D + 1;
   extern __shared__ double sm[];
-  // [2][32][TS] table rows | [2][32][DX] inputs | [2][32] alpha | (FINAL) [32][Mp + 1] beta tile
+  // [2][32][TS] table rows | [2][32][DX] inputs | [2][32] alpha | [32][Mp + 1] transposing tile (kernel values / beta)
   double* stab = sm; double* sx = stab + 2 * 32 * TS; double* sal = sx + 2 * 32 * DX; double* tile = sal + 2 * 32;
   const int m = threadIdx.x, c = blockIdx.x, cd = blockIdx.y;
   const int64_t k0 = (int64_t)c * Lc;
   const int ntile = Lc / 32;
   const double* tab = table + (int64_t)cd * N * TS;
   const double* al = alpha + (int64_t)cd * N;
+  double* bc = beta + (int64_t)cd * Mp * Ns;
   const SmallCand cp = cand[cd];
+  const double inv_l = sqrt(cp.inv_l2);
   const bool live = m < M;
   double z[8];
 #pragma unroll
-  for (int d = 0; d < 8; d++) z[d] = (live && d < DX) ? Z[(int64_t)m * DX + d] : 0.0;
+  for (int d = 0; d < 8; d++) z[d] = (!FINAL && live && d < DX) ? Z[(int64_t)m * DX + d] : 0.0;
   auto stage = [&](int tl, int buf) {
     const int64_t kb = k0 + (int64_t)tl * 32;
     const int64_t rows = N - kb < 32 ? (N - kb > 0 ? N - kb : 0) : 32;       // steps of this tile inside the sequence
     for (int e = threadIdx.x; e < rows * TS; e += blockDim.x) ss_cp8(stab + buf * 32 * TS + e, tab + kb * TS + e);
-    for (int e = threadIdx.x; e < rows * DX; e += blockDim.x) ss_cp8(sx + buf * 32 * DX + e, X + kb * DX + e);
+    if (!FINAL) for (int e = threadIdx.x; e < rows * DX; e += blockDim.x) ss_cp8(sx + buf * 32 * DX + e, X + kb * DX + e);
     if (FINAL) for (int e = threadIdx.x; e < rows; e += blockDim.x) ss_cp8(sal + buf * 32 + e, al + kb + e);
     ss_commit();
   };
@@ -123,28 +137,41 @@ ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int D
   stage(0, 0);
   for (int tl = 0; tl < ntile; tl++) {
     const int buf = tl & 1;
+    const int64_t kb = k0 + (int64_t)tl * 32;
+    if (FINAL) {      // the kernel values of this tile, parked in the beta array by the first walk (coalesced runs -> transposed tile)
+      for (int e = threadIdx.x; e < 32 * Mp; e += blockDim.x) {
+        const int col = e >> 5, sidx = e & 31;
+        if (kb + sidx < Ns) ss_cp8(tile + sidx * (Mp + 1) + col, bc + (int64_t)col * Ns + kb + sidx);
+      }
+      ss_commit();
+    }
     if (tl + 1 < ntile) { stage(tl + 1, buf ^ 1); ss_wait<1>(); } else ss_wait<0>();
     __syncthreads();
-    const int64_t kb = k0 + (int64_t)tl * 32;
     const int rows = (int)(N - kb < 32 ? (N - kb > 0 ? N - kb : 0) : 32);
     for (int sidx = 0; sidx < 32; sidx++) {
-      double bval = 0.0;
+      double oval = 0.0;
       if (sidx < rows) {
         const double* row = stab + (buf * 32 + sidx) * TS;
         double u = 0.0;
-        if (live) {
-          double d2 = 0.0;
+        if (FINAL) u = tile[sidx * (Mp + 1) + m];
+        else if (live) {
+          double r;
+          if (DX == 1) r = fabs(sx[buf * 32 + sidx] - z[0]) * inv_l;        // one input dimension: no square root
+          else {
+            double d2 = 0.0;
 #pragma unroll
-          for (int d = 0; d < 8; d++) if (d < DX) { const double df = sx[(buf * 32 + sidx) * DX + d] - z[d]; d2 = fma(df, df, d2); }
-          double dummy;
-          u = cp.out_s * base_kernel_dev<KIND, false>(d2 * cp.inv_l2, dummy);
+            for (int d = 0; d < 8; d++) if (d < DX) { const double df = sx[(buf * 32 + sidx) * DX + d] - z[d]; d2 = fma(df, df, d2); }
+            r = sqrt(d2) * inv_l;
+          }
+          u = cp.out_s * ss_kappa_r<KIND>(r);
         }
+        oval = u;
         if (FINAL) {
           double pred = 0.0;
 #pragma unroll
           for (int j = 0; j < D; j++) pred = fma(row[D * D + D + j], x[j], pred);
-          bval = (u - pred) * row[D * D + 2 * D];
-          gacc = fma(bval, sal[buf * 32 + sidx], gacc);
+          oval = (u - pred) * row[D * D + 2 * D];
+          gacc = fma(oval, sal[buf * 32 + sidx], gacc);
         }
         double nx[D];
 #pragma unroll
@@ -155,14 +182,12 @@ ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int D
 #pragma unroll
         for (int i = 0; i < D; i++) x[i] = nx[i];
       }
-      if (FINAL) tile[sidx * (Mp + 1) + m] = bval;
+      tile[sidx * (Mp + 1) + m] = oval;
     }
-    if (FINAL) {
-      __syncthreads();
-      for (int e = threadIdx.x; e < 32 * Mp; e += blockDim.x) {
-        const int col = e >> 5, sidx = e & 31;
-        if (kb + sidx < Ns) beta[((int64_t)cd * Mp + col) * Ns + kb + sidx] = tile[sidx * (Mp + 1) + col];
-      }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * Mp; e += blockDim.x) {
+      const int col = e >> 5, sidx = e & 31;
+      if (kb + sidx < Ns) bc[(int64_t)col * Ns + kb + sidx] = tile[sidx * (Mp + 1) + col];
     }
     __syncthreads();
   }
@@ -174,95 +199,130 @@ ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int D
 }
 
 // start state of every chunk, in place of its zero-start response: in[0] = 0, in[c+1] = Psi_c in[c] + resp[c]
+// (the chain is latency bound: the operands of the next PF chunks are fetched ahead of the dependent mat-vecs)
 template <int D>
 __global__ void ss_carry_kernel(const double* __restrict__ psi, double* __restrict__ state, int nch, int Mp) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x, cd = blockIdx.y;
   if (m >= Mp) return;
+  constexpr int PF = 6;
   double st[D];
 #pragma unroll
   for (int i = 0; i < D; i++) st[i] = 0.0;
-  for (int c = 0; c < nch; c++) {
-    double r[D], nx[D];
-    const double* ps = psi + ((int64_t)cd * nch + c) * D * D;
+  for (int c0 = 0; c0 < nch; c0 += PF) {
+    double r[PF][D], ps[PF][D * D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { double* p = state + (((int64_t)cd * nch + c) * D + i) * Mp + m; r[i] = *p; *p = st[i]; }
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
 #pragma unroll
-    for (int i = 0; i < D; i++) { double a = r[i];
+        for (int i = 0; i < D; i++) r[u][i] = state[(((int64_t)cd * nch + c) * D + i) * Mp + m];
 #pragma unroll
-      for (int j = 0; j < D; j++) a = fma(__ldg(ps + i * D + j), st[j], a);
-      nx[i] = a; }
+        for (int i = 0; i < D * D; i++) ps[u][i] = __ldg(psi + ((int64_t)cd * nch + c) * D * D + i);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < D; i++) st[i] = nx[i];
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) { state[(((int64_t)cd * nch + c) * D + i) * Mp + m] = st[i]; double a = r[u][i];
+#pragma unroll
+          for (int j = 0; j < D; j++) a = fma(ps[u][i * D + j], st[j], a);
+          nx[i] = a; }
+#pragma unroll
+        for (int i = 0; i < D; i++) st[i] = nx[i];
+      }
+    }
   }
 }
 
 // Gp (per candidate and split: Mp x Mp, both triangles written) = beta' beta over the split's steps.  Block (pair, split,
-// cand): 32 x 32 tile (ti >= tj), 2 x 2 entries per thread, operands through shared memory in slabs of 32 steps, the next
-// slab fetched into registers while the current one is multiplied.
+// cand): 64 x 64 tile (ti >= tj), 4 x 4 entries per thread (8 shared-memory loads per 16 FMA), operands through shared
+// memory in slabs of 32 steps, the next slab fetched into registers while the current one is multiplied.
+constexpr int SS_ST = 64;
 __global__ void __launch_bounds__(256)
 ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_per_split, int nsplit, double* __restrict__ Gp) {
-  __shared__ double As[SS_TILE][SS_TILE + 1], Bs[SS_TILE][SS_TILE + 1];
+  __shared__ double As[SS_ST][SS_TILE + 1], Bs[SS_ST][SS_TILE + 1];
   int p = blockIdx.x, ti = 0;
   while (p > ti) { p -= ti + 1; ti++; }
   const int tj = p, sp = blockIdx.y, cd = blockIdx.z;
-  const double* ba = beta + ((int64_t)cd * Mp + ti * SS_TILE) * Ns;
-  const double* bb = beta + ((int64_t)cd * Mp + tj * SS_TILE) * Ns;
+  const double* bc = beta + (int64_t)cd * Mp * Ns;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;       // loader: row group (8 rows per pass), step
   const int64_t nslab = Ns / SS_TILE;
   const int64_t s0 = (int64_t)sp * slabs_per_split, s1 = s0 + slabs_per_split < nslab ? s0 + slabs_per_split : nslab;
-  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  double ra[4], rb[4];
-  if (s0 < s1) {
+  double acc[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { ra[q] = ba[(int64_t)(lr + 8 * q) * Ns + s0 * SS_TILE + lc]; rb[q] = bb[(int64_t)(lr + 8 * q) * Ns + s0 * SS_TILE + lc]; }
-  }
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  double ra[8], rb[8];
+  auto fetch = [&](int64_t sl) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int ra_row = ti * SS_ST + lr + 8 * q, rb_row = tj * SS_ST + lr + 8 * q;
+      ra[q] = ra_row < Mp ? bc[(int64_t)ra_row * Ns + sl * SS_TILE + lc] : 0.0;
+      rb[q] = rb_row < Mp ? bc[(int64_t)rb_row * Ns + sl * SS_TILE + lc] : 0.0;
+    }
+  };
+  if (s0 < s1) fetch(s0);
   for (int64_t sl = s0; sl < s1; sl++) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) { As[lr + 8 * q][lc] = ra[q]; Bs[lr + 8 * q][lc] = rb[q]; }
+    for (int q = 0; q < 8; q++) { As[lr + 8 * q][lc] = ra[q]; Bs[lr + 8 * q][lc] = rb[q]; }
     __syncthreads();
-    if (sl + 1 < s1) {
-#pragma unroll
-      for (int q = 0; q < 4; q++) { ra[q] = ba[(int64_t)(lr + 8 * q) * Ns + (sl + 1) * SS_TILE + lc]; rb[q] = bb[(int64_t)(lr + 8 * q) * Ns + (sl + 1) * SS_TILE + lc]; }
-    }
-#pragma unroll 8
+    if (sl + 1 < s1) fetch(sl + 1);
+#pragma unroll 4
     for (int k = 0; k < SS_TILE; k++) {
-      const double a0 = As[ty][k], a1 = As[ty + 16][k], b0 = Bs[tx][k], b1 = Bs[tx + 16][k];
-      acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
-      acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = As[ty + 16 * i][k]; b[i] = Bs[tx + 16 * i][k]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
   double* Gc = Gp + ((int64_t)cd * nsplit + sp) * Mp * Mp;
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int gi = ti * SS_TILE + ty + 16 * i, gj = tj * SS_TILE + tx + 16 * j;
-      Gc[(int64_t)gi + (int64_t)gj * Mp] = acc[i][j];
-      Gc[(int64_t)gj + (int64_t)gi * Mp] = acc[i][j];
+    for (int j = 0; j < 4; j++) {
+      const int gi = ti * SS_ST + ty + 16 * i, gj = tj * SS_ST + tx + 16 * j;
+      if (gi < Mp && gj < Mp) {
+        Gc[(int64_t)gi + (int64_t)gj * Mp] = acc[i][j];
+        Gc[(int64_t)gj + (int64_t)gi * Mp] = acc[i][j];
+      }
     }
 }
 
 // In-place Cholesky (lower, column-major, leading dimension ld) of the M x M matrix A in shared memory by the whole
-// block; returns the 1-based index of the first non-positive pivot (0: success) through *info (shared).
+// block; the 1-based index of the first non-positive pivot goes to *info (shared; 0: success).  The elimination runs in
+// L D L' form — column j stays unscaled while it updates the trailing block, A_ik -= A_ij A_kj / A_jj — so that a column
+// costs ONE barrier; the columns are scaled by 1 / sqrt(d_j) at the end.
 __device__ void ss_chol_inplace(double* A, int M, int ld, int* info) {
   for (int j = 0; j < M; j++) {
     __syncthreads();
-    if (*info) return;
     const double d = A[j + j * ld];
-    if (!(d > 0.0)) { __syncthreads(); if (threadIdx.x == 0) *info = j + 1; __syncthreads(); return; }
-    const double inv = 1.0 / sqrt(d);
-    __syncthreads();
-    for (int i = j + threadIdx.x; i < M; i += blockDim.x) A[i + j * ld] *= inv;        // column j: L_jj = sqrt(d), L_ij = A_ij / L_jj
-    __syncthreads();
-    // trailing update of the lower triangle: A_ik -= L_ij L_kj for k > j, i >= k
-    const int rem = M - j - 1;
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int k = j + 1 + e / rem, i = j + 1 + e % rem;
-      if (i >= k) A[i + k * ld] = fma(-A[i + j * ld], A[k + j * ld], A[i + k * ld]);
+    if (!(d > 0.0)) { if (threadIdx.x == 0 && *info == 0) *info = j + 1; break; }
+    const double inv = 1.0 / d;
+    for (int k = j + 1 + (threadIdx.x >> 4); k < M; k += (int)(blockDim.x >> 4)) {        // 16 lanes down a column, blockDim / 16 columns at a time
+      const double lk = A[k + j * ld] * inv;
+      for (int i = k + (threadIdx.x & 15); i < M; i += 16) A[i + k * ld] = fma(-A[i + j * ld], lk, A[i + k * ld]);
     }
   }
+  __syncthreads();
+  if (*info) return;
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int i = e % M, j = e / M;
+    if (i >= j) {
+      const double dj = A[j + j * ld];
+      if (i > j) A[e % M + j * ld] = A[i + j * ld] * rsqrt(dj);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += blockDim.x) A[j + j * ld] = sqrt(A[j + j * ld]);
   __syncthreads();
 }
 // v <- L^-1 v for a lower-triangular L in shared memory (column-oriented substitution, one barrier per column)
@@ -296,12 +356,29 @@ ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, c
     const int i = e % M, j = e / M;
     Lu[i + j * ld] = ss_kernel_value<KIND>(Z + (int64_t)i * DX, Z + (int64_t)j * DX, DX, c.inv_l2, c.out_s) + (i == j ? c.noise : 0.0);
     double g = 0.0;
-    for (int q = 0; q < nsplit; q++) g += Gp[((int64_t)cd * nsplit + q) * Mp * Mp + i + (int64_t)j * Mp];        // fixed order
+    const double* gp = Gp + (int64_t)cd * nsplit * Mp * Mp + i + (int64_t)j * Mp;
+    int q = 0;
+    for (; q + 7 < nsplit; q += 8) {        // independent loads first, then the additions in fixed order
+      double t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t8[u] = __ldg(gp + (int64_t)(q + u) * Mp * Mp);
+#pragma unroll
+      for (int u = 0; u < 8; u++) g += t8[u];
+    }
+    for (; q < nsplit; q++) g += __ldg(gp + (int64_t)q * Mp * Mp);
     B[i + j * ld] = g;
   }
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     double g = 0.0;
-    for (int c2 = 0; c2 < nch; c2++) g += gpart[((int64_t)cd * nch + c2) * Mp + i];
+    int c2 = 0;
+    for (; c2 + 7 < nch; c2 += 8) {
+      double t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t8[u] = __ldg(gpart + ((int64_t)cd * nch + c2 + u) * Mp + i);
+#pragma unroll
+      for (int u = 0; u < 8; u++) g += t8[u];
+    }
+    for (; c2 < nch; c2++) g += __ldg(gpart + ((int64_t)cd * nch + c2) * Mp + i);
     v[i] = g;
   }
   __syncthreads();
@@ -325,9 +402,14 @@ ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, c
   for (int pass = 0; pass < 2; pass++) {
     for (int col = threadIdx.x; col < M; col += blockDim.x) {
       for (int i = 0; i < M; i++) {
-        double a = B[i + col * ld];
-        for (int k = 0; k < i; k++) a = fma(-Lu[i + k * ld], B[k + col * ld], a);
-        B[i + col * ld] = a / Lu[i + i * ld];
+        double a0 = B[i + col * ld], a1 = 0.0, a2 = 0.0, a3 = 0.0;       // four partial sums: the dot product is latency bound
+        int k = 0;
+        for (; k + 3 < i; k += 4) {
+          a0 = fma(-Lu[i + k * ld], B[k + col * ld], a0); a1 = fma(-Lu[i + (k + 1) * ld], B[k + 1 + col * ld], a1);
+          a2 = fma(-Lu[i + (k + 2) * ld], B[k + 2 + col * ld], a2); a3 = fma(-Lu[i + (k + 3) * ld], B[k + 3 + col * ld], a3);
+        }
+        for (; k < i; k++) a0 = fma(-Lu[i + k * ld], B[k + col * ld], a0);
+        B[i + col * ld] = ((a0 + a1) + (a2 + a3)) / Lu[i + i * ld];
       }
     }
     __syncthreads();
@@ -360,15 +442,25 @@ int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
   constexpr int TS = D * D + 2 * D + 1;
   const double* X = ctx->X.as<double>(); const double* Z = ctx->Z.as<double>();
   const dim3 gwalk(p.nch, p.ncand);
-  const size_t sm0 = ((size_t)2 * 32 * TS + (size_t)2 * 32 * p.DX + 64) * sizeof(double);
-  const size_t sm1 = sm0 + (size_t)32 * (p.Mp + 1) * sizeof(double);
-  LAUNCH(ctx, ss_chunk_product_kernel<D>, gwalk, 32, 0, b.table, p.N, p.Lc, p.nch, b.psi);
+  const size_t sm1 = ((size_t)2 * 32 * TS + (size_t)2 * 32 * p.DX + 64 + (size_t)32 * (p.Mp + 1)) * sizeof(double);
+  const size_t sm0 = sm1;
+  {   // the chunk products only need the table: on the side stream, underneath the first walk
+    cudaStream_t main_stream = ctx->stream;
+    CU(cudaEventRecord(ctx->ev_fork, main_stream));
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->stream2;
+    const int rc = [&]() -> int { LAUNCH(ctx, ss_chunk_product_kernel<D>, gwalk, 32, 0, b.table, p.N, p.Lc, p.nch, b.psi); return GPAR_OK; }();
+    cudaEventRecord(ctx->ev_side, ctx->stream2);
+    ctx->stream = main_stream;
+    CHK(rc);
+  }
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, false>), gwalk, p.Mp, sm0, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
   LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 127) / 128, p.ncand), 128, 0, b.psi, b.state, p.nch, p.Mp);
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, true>), gwalk, p.Mp, sm1, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
-  const int T = p.Mp / SS_TILE;
+  const int T = (p.Mp + SS_ST - 1) / SS_ST;
   LAUNCH(ctx, ss_syrk_kernel, dim3(T * (T + 1) / 2, p.nsplit, p.ncand), 256, 0, b.beta, p.Mp, p.Ns, p.slabs_per_split, p.nsplit, b.Gp);
   const int ld = p.M | 1;
   const size_t smem = ((size_t)2 * ld * p.M + p.M + 8) * sizeof(double);
@@ -410,10 +502,11 @@ int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* theta
   const int want_chunks = std::max(1, (int)((int64_t)ctx->num_sms * 16 * 32 / ((int64_t)Mp * std::max(1, std::min(ncand, 64)))));
   int Lc = (int)(((N + want_chunks - 1) / want_chunks + 31) / 32 * 32);
   Lc = std::max(64, std::min(Lc, 2048));
+  if (const char* e = getenv("GPAR_SS_LC")) { int v = atoi(e); if (v >= 32 && v <= 4096 && v % 32 == 0) Lc = v; }      // tuning knob
   const int nch = (int)((N + Lc - 1) / Lc);
-  const int T = Mp / SS_TILE, pairs = T * (T + 1) / 2;
+  const int T = (Mp + 63) / 64, pairs = T * (T + 1) / 2;
   const int64_t nslab = Ns / SS_TILE;
-  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)ctx->num_sms * 8 + (int64_t)pairs * std::min(ncand, 64) - 1) / ((int64_t)pairs * std::min(ncand, 64))));
+  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)ctx->num_sms * 4 + (int64_t)pairs * std::min(ncand, 64) - 1) / ((int64_t)pairs * std::min(ncand, 64))));
   nsplit = (int)std::min<int64_t>(nsplit, nslab);
   const int slabs_per_split = (int)((nslab + nsplit - 1) / nsplit);
   nsplit = (int)((nslab + slabs_per_split - 1) / slabs_per_split);

@@ -30,8 +30,16 @@ print("exact_logpdf GPAR N=156 D=5: %.3f ms/eval (device %.3f)" % (bench(lambda:
 X = y_obs[0][:, None]; Z = np.linspace(X.min(), X.max(), 50)[:, None]
 ctx.set_times(x); ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y_obs[1])
 ths = np.tile(th5, (64, 1)) + 0.05 * rng.normal(size=(64, 5))
-for lanes in (1, 4, 8, 16, 32):
-    os.environ["GPAR_LANES"] = str(lanes)
+ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
+print("scaled_dtc_batch N=8496 M=50, 64 candidates, fused small-problem path: %.3f ms per batch = %.4f ms per candidate (device launches %d)" % (ms, ms / 64, ctx.last_timing()[1]))
+for lc in (96, 128, 192, 256, 320, 480, 960):
+    os.environ["GPAR_SS_LC"] = str(lc)
     ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
-    print("scaled_dtc_batch N=8496 M=50, 64 candidates, %2d lanes: %.3f ms per batch = %.4f ms per candidate" % (lanes, ms, ms / 64))
-os.environ.pop("GPAR_LANES")
+    print("   whitening chunk length %4d: %.3f ms per batch" % (lc, ms))
+os.environ.pop("GPAR_SS_LC")
+os.environ["GPAR_SCALED_SMALL"] = "0"
+for lanes in (1, 4, 16):
+    os.environ["GPAR_LANES"] = str(lanes)
+    ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=10)
+    print("scaled_dtc_batch N=8496 M=50, 64 candidates, lane path, %2d lanes: %.3f ms per batch = %.4f ms per candidate" % (lanes, ms, ms / 64))
+os.environ.pop("GPAR_LANES"); os.environ.pop("GPAR_SCALED_SMALL")
