@@ -11,14 +11,15 @@
 //      whitening of scaled.cu: ss_walk_kernel<false> (zero-start chunk responses; a thread per column, so a step's table
 //      row and input point are staged once per block and read as shared-memory broadcasts), ss_chunk_product_kernel +
 //      ss_carry_kernel (start state of every chunk), ss_walk_kernel<true> (beta through a transposing tile, g = beta' alpha);
-//   3. ss_syrk_kernel: G = beta' beta, 32 x 32 tiles of the lower triangle, split along N (partial sums added in fixed
-//      order by the tail), operands staged in shared memory with register prefetch;
+//   3. ss_syrk_kernel: G = beta' beta on the FP64 tensor cores (DMMA), 64 x 64 tiles of the lower triangle, split along N
+//      (partial sums added in fixed order by the tail), operands staged in shared memory with register prefetch;
 //   4. ss_tail_kernel: one CTA per candidate, matrices in shared memory: cov(u) = Kuu + sigma^2 I (dtc.jl:35,119),
 //      L_u, Lambda = I + L_u^-1 G L_u^-T, L_Lambda, c = L_Lambda^-1 L_u^-1 g and the value (dtc.jl:122-125).
 // This is the collapsed form of the objective (G, g instead of A = L_u^-1 beta'), as in scaled.cu; a candidate whose
 // cov(u) is too poorly conditioned for it — (max / min diag L_u)^2 > GPAR_ROBUST_COND, the same test — is handed back to
 // the caller, which evaluates it through the whitened-panel path of gpar_scaled_dtc.
 #include "lgssm_math.cuh"
+#include "dmma_pipe.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <limits>
@@ -238,25 +239,29 @@ __global__ void ss_carry_kernel(const double* __restrict__ psi, double* __restri
 }
 
 // Gp (per candidate and split: Mp x Mp, both triangles written) = beta' beta over the split's steps.  Block (pair, split,
-// cand): 64 x 64 tile (ti >= tj), 4 x 4 entries per thread (8 shared-memory loads per 16 FMA), operands through shared
-// memory in slabs of 32 steps, the next slab fetched into registers while the current one is multiplied.
+// cand): 64 x 64 tile (ti >= tj) on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): 8 warps, each a
+// 32 x 16 sub-tile = 4 x 2 fragments (6 shared-memory loads per 8 DMMA; rows padded to 36 doubles: a fragment load is
+// bank-conflict free per half-warp).  Operands through shared memory in slabs of 32 steps, the next slab fetched into
+// registers while the current one is multiplied.
 constexpr int SS_ST = 64;
+constexpr int SS_LD = SS_TILE + 4;
 __global__ void __launch_bounds__(256)
 ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_per_split, int nsplit, double* __restrict__ Gp) {
-  __shared__ double As[SS_ST][SS_TILE + 1], Bs[SS_ST][SS_TILE + 1];
+  __shared__ double As[SS_ST][SS_LD], Bs[SS_ST][SS_LD];
   int p = blockIdx.x, ti = 0;
   while (p > ti) { p -= ti + 1; ti++; }
   const int tj = p, sp = blockIdx.y, cd = blockIdx.z;
   const double* bc = beta + (int64_t)cd * Mp * Ns;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wy = w >> 2, wx = w & 3;
+  const int fr = lane >> 2, fc = lane & 3;                      // fragment row / k (A, B) — C: row fr, columns 2 fc + {0, 1}
   const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;       // loader: row group (8 rows per pass), step
   const int64_t nslab = Ns / SS_TILE;
   const int64_t s0 = (int64_t)sp * slabs_per_split, s1 = s0 + slabs_per_split < nslab ? s0 + slabs_per_split : nslab;
-  double acc[4][4];
+  double acc[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
   double ra[8], rb[8];
   auto fetch = [&](int64_t sl) {
 #pragma unroll
@@ -272,15 +277,17 @@ ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_pe
     for (int q = 0; q < 8; q++) { As[lr + 8 * q][lc] = ra[q]; Bs[lr + 8 * q][lc] = rb[q]; }
     __syncthreads();
     if (sl + 1 < s1) fetch(sl + 1);
-#pragma unroll 4
-    for (int k = 0; k < SS_TILE; k++) {
-      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) { a[i] = As[ty + 16 * i][k]; b[i] = Bs[tx + 16 * i][k]; }
+    for (int k4 = 0; k4 < SS_TILE / 4; k4++) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[wy * 32 + i * 8 + fr][k4 * 4 + fc];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = Bs[wx * 16 + j * 8 + fr][k4 * 4 + fc];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 2; j++) dmma::dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
   }
@@ -288,13 +295,15 @@ ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_pe
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int gi = ti * SS_ST + ty + 16 * i, gj = tj * SS_ST + tx + 16 * j;
-      if (gi < Mp && gj < Mp) {
-        Gc[(int64_t)gi + (int64_t)gj * Mp] = acc[i][j];
-        Gc[(int64_t)gj + (int64_t)gi * Mp] = acc[i][j];
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int gi = ti * SS_ST + wy * 32 + i * 8 + fr, gj = tj * SS_ST + wx * 16 + j * 8 + 2 * fc + h;
+        if (gi < Mp && gj < Mp) {
+          Gc[(int64_t)gi + (int64_t)gj * Mp] = acc[i][j][h];
+          Gc[(int64_t)gj + (int64_t)gi * Mp] = acc[i][j][h];
+        }
       }
-    }
 }
 
 // In-place Cholesky (lower, column-major, leading dimension ld) of the M x M matrix A in shared memory by the whole
