@@ -356,9 +356,12 @@ def compute_gpar_dtc_objective(f, u, time_loc, outputs, time_kernel=None, tempor
 def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_loc, outputs, out_kernel=None, time_kernel=None,
                                  i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                  optimization_time_limit=1000.0, show_optimization_trace=False, debug=False, ctx=None, rng=None,
-                                 iterations=1000, return_result=False, optimizer="neldermead"):
+                                 iterations=1000, return_result=False, optimizer="neldermead", n_restarts=1):
     """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma).  optimizer="lbfgs" replaces the
-    reference's Nelder-Mead (:58-61) by L-BFGS on gpar_scaled_dtc_grad."""
+    reference's Nelder-Mead (:58-61) by L-BFGS on gpar_scaled_dtc_grad.  n_restarts > 1 (NEW): that many Nelder-Mead
+    runs in lock-step — the first from the given / drawn initial parameters, the others from theta0 ~ U(0,1)^5 (the
+    missing-parameter rule, util.jl:128-134) — every round of candidates in ONE gpar_scaled_dtc_batch call; each run
+    performs exactly the operations of a separate Optim.optimize, the best optimum is returned."""
     out_kernel = out_kernel or Matern52(); time_kernel = time_kernel or Matern52()
     ctx = ctx or default_context()
     ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
@@ -378,6 +381,15 @@ def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_l
                 return np.inf, np.zeros(5)
             return -v, -g
         results = lbfgs.optimize(nlml_fg, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
+    elif n_restarts > 1:
+        rng_ = rng if rng is not None else np.random.default_rng()
+        X0 = np.vstack([params] + [rng_.random(5) for _ in range(n_restarts - 1)])
+
+        def nlml_batch(P):       # a failed Cholesky (PosDefException of the reference) is +Inf for that vertex only
+            vals, codes = ctx.scaled_dtc_batch(time_kernel.code, out_kernel.code, P)
+            return np.where(codes == 0, -vals, np.inf)
+        runs = neldermead.optimize_batch(nlml_batch, X0, iterations=iterations)
+        results = min(runs, key=lambda r_: r_.minimum)
     else:
         results = neldermead.optimize(nlml, params, iterations=iterations, time_limit=optimization_time_limit, show_trace=show_optimization_trace)
     opt_params = unpack_gpar(results.minimizer)
