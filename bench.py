@@ -262,6 +262,23 @@ def run_extra(ctx, gp, xp, yp, peaks):
     extra["scaled_gpar_objective_and_grad_roofline"] = {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
                                                         "frac": fl / (ms * 1e-3) / 1e12 / peaks["dmma_tflops"],
                                                         "note": "whole blocking call; DMMA work = N M (M+1) + 2 N M^2 (panel_syrk_kernel + panel_gemm_kernel, no library GEMM)"}
+    # the reference's own problem size (GPAR_scaled_examples.jl: N = 8 496, M = 50): one candidate per call vs 64 candidates
+    # (simplex vertices x restarts of dtc.jl:58-61) in one fused launch sequence (gpar_scaled_dtc_batch, scaled_small.cu)
+    ns, msm = 8496, 50
+    ts = np.arange(ns) / 30.0; xs = rng.normal(size=(ns, 1)); zs = np.linspace(xs.min(), xs.max(), msm)[:, None]
+    ctx.set_inputs(xs); ctx.set_pseudo(zs); ctx.set_times(ts); ctx.set_outputs(np.sin(xs[:, 0]) + 0.3 * rng.normal(size=ns))
+    th64 = np.tile(np.log([1.0, 1.0, 1.0, 1.0, 0.6]), (64, 1)) + 0.05 * rng.normal(size=(64, 5))
+
+    def wall_ms(fn, n=20, skip=3):
+        out = []
+        for _ in range(n):
+            t0 = time.perf_counter(); fn(); out.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(out[skip:]))
+    one = wall_ms(lambda: ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th64[0]))
+    b64 = wall_ms(lambda: ctx.scaled_dtc_batch(gp.MATERN52, gp.MATERN52, th64))
+    extra["scaled_gpar_reference_size_N8496_M50"] = {"ms_per_candidate_single_call": one, "ms_per_64_candidates_batched": b64,
+                                                     "ms_per_candidate_batched": b64 / 64, "speedup": one * 64 / b64,
+                                                     "note": "host wall-clock through the C ABI, including the result read-back"}
     return extra
 
 
