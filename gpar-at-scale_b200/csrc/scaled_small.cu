@@ -13,8 +13,9 @@
 //      ss_carry_kernel (start state of every chunk), ss_walk_kernel<true> (beta through a transposing tile, g = beta' alpha);
 //   3. ss_syrk_kernel: G = beta' beta on the FP64 tensor cores (DMMA), 64 x 64 tiles of the lower triangle, split along N
 //      (partial sums added in fixed order by the tail), operands staged in shared memory with register prefetch;
-//   4. ss_tail_kernel: one CTA per candidate, matrices in shared memory: cov(u) = Kuu + sigma^2 I (dtc.jl:35,119),
-//      L_u, Lambda = I + L_u^-1 G L_u^-T, L_Lambda, c = L_Lambda^-1 L_u^-1 g and the value (dtc.jl:122-125).
+//   4. ss_tail_kernel: one CTA per candidate, one M x M matrix in shared memory at a time: cov(u) = Kuu + sigma^2 I
+//      (dtc.jl:35,119) and W = cov(u) + G = L_u Lambda L_u' are factorised in turn — log det Lambda = log det W - log det cov(u),
+//      c'c = |L_W^-1 g|^2 — and the value follows (dtc.jl:122-125).
 // This is the collapsed form of the objective (G, g instead of A = L_u^-1 beta'), as in scaled.cu; a candidate whose
 // cov(u) is too poorly conditioned for it — (max / min diag L_u)^2 > GPAR_ROBUST_COND, the same test — is handed back to
 // the caller, which evaluates it through the whitened-panel path of gpar_scaled_dtc.
@@ -103,7 +104,7 @@ ss_chunk_product_kernel(const double* __restrict__ table, int64_t N, int Lc, int
 // FINAL = true : from the carried start state (same array), reading u back through the tile (no second exp / sqrt per
 //                element): beta = (u - HA x) / sqrt(S) overwrites it, g partial sums -> gpart[cd][c][m].
 template <int KIND, int D, bool FINAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(192)
 ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int DX, int64_t N, int M, int Mp, int64_t Ns, int Lc, int nch,
                const SmallCand* __restrict__ cand, const double* __restrict__ table, const double* __restrict__ alpha,
                double* __restrict__ state, double* __restrict__ beta, double* __restrict__ gpart) {
@@ -346,8 +347,11 @@ __device__ void ss_trsv_inplace(const double* L, int M, int ld, double* v) {
   __syncthreads();
 }
 
-// out per candidate: [value, code]; code 0 ok, 1 / 2: Cholesky of cov(u) / Lambda failed, 3: cov(u) too poorly conditioned
-// for the collapsed statistic (the caller re-evaluates the candidate through the whitened-panel path)
+// out per candidate: [value, code]; code 0 ok, 1 / 2: Cholesky of cov(u) / of cov(u) + G failed, 3: cov(u) too poorly
+// conditioned for the collapsed statistic (the caller re-evaluates the candidate through the whitened-panel path).
+// With W = cov(u) + G = L_u Lambda L_u':  log det Lambda = log det W - log det cov(u)  and  c'c = g' W^-1 g = |L_W^-1 g|^2,
+// so the value needs two Cholesky factorisations and one triangular solve — ONE M x M matrix in shared memory at a time
+// (M up to ~160: the EEG shape M = N = 156 of examples/eeg.jl:212-232 fits).
 template <int KIND>
 __global__ void __launch_bounds__(256)
 ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, const SmallCand* __restrict__ cand,
@@ -355,28 +359,38 @@ ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, c
                double cond_thr, double* __restrict__ out) {
   extern __shared__ double sm[];
   const int ld = M | 1;                                  // odd leading dimension: conflict-free columns and rows
-  double* Lu = sm; double* B = Lu + (size_t)ld * M; double* v = B + (size_t)ld * M;
+  double* S = sm; double* v = S + (size_t)ld * M;
   __shared__ int info;
   __shared__ double red[32];
   const int cd = blockIdx.x;
   const SmallCand c = cand[cd];
+  const double inv_l = sqrt(c.inv_l2);
   if (threadIdx.x == 0) info = 0;
-  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const int i = e % M, j = e / M;
-    Lu[i + j * ld] = ss_kernel_value<KIND>(Z + (int64_t)i * DX, Z + (int64_t)j * DX, DX, c.inv_l2, c.out_s) + (i == j ? c.noise : 0.0);
-    double g = 0.0;
-    const double* gp = Gp + (int64_t)cd * nsplit * Mp * Mp + i + (int64_t)j * Mp;
-    int q = 0;
-    for (; q + 7 < nsplit; q += 8) {        // independent loads first, then the additions in fixed order
-      double t8[8];
+  auto fill_cov_u = [&](bool add_G) {
+    for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+      const int i = e % M, j = e / M;
+      if (i < j) continue;                               // lower triangle only
+      double d2 = 0.0;
+      for (int d = 0; d < DX; d++) { const double df = Z[(int64_t)i * DX + d] - Z[(int64_t)j * DX + d]; d2 = fma(df, df, d2); }
+      double val = c.out_s * ss_kappa_r<KIND>(sqrt(d2) * inv_l) + (i == j ? c.noise : 0.0);
+      if (add_G) {
+        double g = 0.0;
+        const double* gp = Gp + (int64_t)cd * nsplit * Mp * Mp + i + (int64_t)j * Mp;
+        int q = 0;
+        for (; q + 7 < nsplit; q += 8) {        // independent loads first, then the additions in fixed order
+          double t8[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) t8[u] = __ldg(gp + (int64_t)(q + u) * Mp * Mp);
+          for (int u = 0; u < 8; u++) t8[u] = __ldg(gp + (int64_t)(q + u) * Mp * Mp);
 #pragma unroll
-      for (int u = 0; u < 8; u++) g += t8[u];
+          for (int u = 0; u < 8; u++) g += t8[u];
+        }
+        for (; q < nsplit; q++) g += __ldg(gp + (int64_t)q * Mp * Mp);
+        val += g;
+      }
+      S[i + j * ld] = val;
     }
-    for (; q < nsplit; q++) g += __ldg(gp + (int64_t)q * Mp * Mp);
-    B[i + j * ld] = g;
-  }
+  };
+  fill_cov_u(false);
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     double g = 0.0;
     int c2 = 0;
@@ -391,11 +405,12 @@ ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, c
     v[i] = g;
   }
   __syncthreads();
-  ss_chol_inplace(Lu, M, ld, &info);
+  ss_chol_inplace(S, M, ld, &info);
   if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 1.0; } return; }
-  {   // conditioning estimate of cov(u): (max / min of diag L_u)^2
+  double ldu = 0.0;
+  {   // log det cov(u) and its conditioning estimate: (max / min of diag L_u)^2
     double mn = 1e300, mx = 0.0;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) { const double d = Lu[i + i * ld]; mn = fmin(mn, d); mx = fmax(mx, d); }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { const double d = S[i + i * ld]; mn = fmin(mn, d); mx = fmax(mx, d); ldu += log(d); }
     for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mn; red[8 + (threadIdx.x >> 5)] = mx; }
     __syncthreads();
@@ -406,39 +421,20 @@ ss_tail_kernel(const double* __restrict__ Z, int DX, int M, int Mp, int64_t N, c
     }
     __syncthreads();
     if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 3.0; } return; }
+    ldu = block_sum(ldu, red);
   }
-  // B <- L_u^-1 G L_u^-T: forward substitution down every column (a thread per column), transpose, again
-  for (int pass = 0; pass < 2; pass++) {
-    for (int col = threadIdx.x; col < M; col += blockDim.x) {
-      for (int i = 0; i < M; i++) {
-        double a0 = B[i + col * ld], a1 = 0.0, a2 = 0.0, a3 = 0.0;       // four partial sums: the dot product is latency bound
-        int k = 0;
-        for (; k + 3 < i; k += 4) {
-          a0 = fma(-Lu[i + k * ld], B[k + col * ld], a0); a1 = fma(-Lu[i + (k + 1) * ld], B[k + 1 + col * ld], a1);
-          a2 = fma(-Lu[i + (k + 2) * ld], B[k + 2 + col * ld], a2); a3 = fma(-Lu[i + (k + 3) * ld], B[k + 3 + col * ld], a3);
-        }
-        for (; k < i; k++) a0 = fma(-Lu[i + k * ld], B[k + col * ld], a0);
-        B[i + col * ld] = ((a0 + a1) + (a2 + a3)) / Lu[i + i * ld];
-      }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < M * M; e += blockDim.x) {       // in-place transpose
-      const int i = e % M, j = e / M;
-      if (i > j) { const double t1 = B[i + j * ld]; B[i + j * ld] = B[j + i * ld]; B[j + i * ld] = t1; }
-    }
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < M; i += blockDim.x) B[i + i * ld] += 1.0;
-  ss_trsv_inplace(Lu, M, ld, v);                          // L_u^-1 g
-  ss_chol_inplace(B, M, ld, &info);
+  __syncthreads();
+  fill_cov_u(true);                                       // W = cov(u) + G
+  __syncthreads();
+  ss_chol_inplace(S, M, ld, &info);
   if (info) { if (threadIdx.x == 0) { out[2 * cd] = 0.0; out[2 * cd + 1] = 2.0; } return; }
-  ss_trsv_inplace(B, M, ld, v);                           // c = L_Lambda^-1 L_u^-1 g
-  double ld2 = 0.0, cc = 0.0;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) { ld2 += log(B[i + i * ld]); cc = fma(v[i], v[i], cc); }
-  ld2 = block_sum(ld2, red); cc = block_sum(cc, red);
+  ss_trsv_inplace(S, M, ld, v);                           // L_W^-1 g
+  double ldw = 0.0, cc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { ldw += log(S[i + i * ld]); cc = fma(v[i], v[i], cc); }
+  ldw = block_sum(ldw, red); cc = block_sum(cc, red);
   if (threadIdx.x == 0) {
     const double sum_logS = sums[2 * cd], sum_a2 = sums[2 * cd + 1];
-    out[2 * cd] = -0.5 * ((double)N * LOG2PI_SS + sum_logS + 2.0 * ld2 + sum_a2 - cc);      // dtc.jl:122-125
+    out[2 * cd] = -0.5 * ((double)N * LOG2PI_SS + sum_logS + 2.0 * (ldw - ldu) + sum_a2 - cc);      // dtc.jl:122-125
     out[2 * cd + 1] = 0.0;
   }
 }
@@ -463,6 +459,8 @@ int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
     ctx->stream = main_stream;
     CHK(rc);
   }
+  CU(cudaFuncSetAttribute((ss_walk_kernel<KIND, D, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+  CU(cudaFuncSetAttribute((ss_walk_kernel<KIND, D, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, false>), gwalk, p.Mp, sm0, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
   CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
@@ -472,7 +470,7 @@ int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
   const int T = (p.Mp + SS_ST - 1) / SS_ST;
   LAUNCH(ctx, ss_syrk_kernel, dim3(T * (T + 1) / 2, p.nsplit, p.ncand), 256, 0, b.beta, p.Mp, p.Ns, p.slabs_per_split, p.nsplit, b.Gp);
   const int ld = p.M | 1;
-  const size_t smem = ((size_t)2 * ld * p.M + p.M + 8) * sizeof(double);
+  const size_t smem = ((size_t)ld * p.M + p.M + 8) * sizeof(double);
   CU(cudaFuncSetAttribute(ss_tail_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LAUNCH(ctx, ss_tail_kernel<KIND>, p.ncand, 256, smem, Z, p.DX, p.M, p.Mp, p.N, b.cand, b.Gp, p.nsplit, b.gpart, p.nch, b.sums, p.cond_thr, b.out);
   return GPAR_OK;
@@ -491,8 +489,8 @@ int ss_run_kind(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
 // Is the fused small-problem path applicable to the resident problem?  (M x M matrices of the tail in shared memory.)
 bool scaled_small_applicable(const gpar_ctx* ctx) {
   const int64_t M = ctx->M, N = ctx->N;
-  const size_t smem = ((size_t)2 * (M | 1) * M + M + 8) * sizeof(double);
-  return M >= 1 && smem <= (size_t)200 * 1024 && N >= 64 && N <= ((int64_t)1 << 18) && ctx->D >= 1 && ctx->D <= 8;
+  const size_t smem = ((size_t)(M | 1) * M + M + 8) * sizeof(double);
+  return M >= 1 && M <= 192 && smem <= (size_t)210 * 1024 && N >= 64 && N <= ((int64_t)1 << 18) && ctx->D >= 1 && ctx->D <= 8;
 }
 
 // vals[c], codes[c] (0 ok; GPAR_ERR_NOT_POSDEF; -1: hand this candidate to the whitened-panel path) for the candidates

@@ -1040,7 +1040,8 @@ def test_scaled_dtc_batch_of_candidates(ctx, monkeypatch):
     Nelder-Mead over restarts walks exactly the simplices of separate runs."""
     from gpar_at_scale_b200 import neldermead
     rng = np.random.default_rng(81)
-    for (n, m, d, kt, ko, B) in [(2000, 50, 2, 3, 3, 37), (8496, 81, 2, 3, 3, 5), (700, 17, 1, 2, 0, 3), (333, 33, 4, 1, 1, 9), (64, 1, 1, 3, 2, 2)]:
+    for (n, m, d, kt, ko, B) in [(2000, 50, 2, 3, 3, 37), (8496, 81, 2, 3, 3, 5), (700, 17, 1, 2, 0, 3), (333, 33, 4, 1, 1, 9), (64, 1, 1, 3, 2, 2),
+                                   (156, 156, 5, 3, 3, 6), (1248, 156, 4, 3, 3, 3)]:      # (the last two: EEG shape, eeg.jl:212-232)
         t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
         if n > 300:
             t[n // 2] = t[n // 2 - 1]

@@ -32,11 +32,15 @@ ctx.set_times(x); ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y_obs[1]
 ths = np.tile(th5, (64, 1)) + 0.05 * rng.normal(size=(64, 5))
 ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
 print("scaled_dtc_batch N=8496 M=50, 64 candidates, fused small-problem path: %.3f ms per batch = %.4f ms per candidate (device launches %d)" % (ms, ms / 64, ctx.last_timing()[1]))
-for lc in (96, 128, 192, 256, 320, 480, 960):
+for lc in ():
     os.environ["GPAR_SS_LC"] = str(lc)
     ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
     print("   whitening chunk length %4d: %.3f ms per batch" % (lc, ms))
-os.environ.pop("GPAR_SS_LC")
+os.environ.pop("GPAR_SS_LC", None)
+Xe = rng.normal(size=(156, 5)); ctx.set_inputs(Xe); ctx.set_pseudo(Xe); ctx.set_times(np.arange(156) / 256.0); ctx.set_outputs(rng.normal(size=156))
+ms = bench(lambda: ctx.scaled_dtc_batch(3, 3, ths), n=20)
+print("scaled_dtc_batch EEG N=M=156 D=5, 64 candidates, fused small-problem path: %.3f ms per batch = %.4f ms per candidate" % (ms, ms / 64))
+ctx.set_times(x); ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_outputs(y_obs[1])
 os.environ["GPAR_SCALED_SMALL"] = "0"
 for lanes in (1, 4, 16):
     os.environ["GPAR_LANES"] = str(lanes)
