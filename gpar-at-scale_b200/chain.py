@@ -29,12 +29,14 @@ def make_tasks(n_outputs, n_restarts):
 
 
 def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kernel=None, out_kernel=None, verbose=False,
-              optimizer="neldermead"):
+              optimizer="neldermead", batched=None):
     """Fits all outputs.  Y: (P, N) observed outputs on the sorted time grid t.  Tasks (output,
     restart) are partitioned over the ranks; every rank returns the gathered best parameters:
     {output: (nlml, theta, restart)}, plus timing info.  optimizer: "neldermead" (the reference's,
     dtc.jl:58-61) or "lbfgs" (uses the library's analytic gradients; `iterations` then bounds the
-    L-BFGS iterations)."""
+    L-BFGS iterations).  batched (default: automatic — Nelder-Mead with several restarts at sizes the fused
+    small-problem path covers, M <= 160 and N <= 2^18): the restarts of an output run in lock-step and every round of
+    candidates is ONE gpar_scaled_dtc_batch / gpar_lgssm_logpdf call; tasks are then whole outputs."""
     time_kernel = time_kernel or api.Matern52(); out_kernel = out_kernel or api.Matern52()
     rank, world = parallel.dist_info()
     ctx = ctx or api.default_context()
@@ -80,6 +82,24 @@ def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kern
         evals[0] += res.f_calls
         return res.minimum, res.minimizer
 
+    if batched is None:
+        batched = optimizer == "neldermead" and n_restarts > 1 and M <= 160 and N <= (1 << 18)
+
+    def run_output(o):
+        """All restarts of output o in lock-step (same starting points as the separate runs) -> list of OptimResult."""
+        if o == 0:
+            ctx.set_times(t); ctx.set_outputs(Y[0]); ctx.set_noise_vector(None)
+            X0 = np.stack([np.random.default_rng([seed, 0, r]).random(3) for r in range(n_restarts)])
+            return neldermead.optimize_batch(lambda P_: -ctx.lgssm_logpdf(time_kernel.code, P_), X0, iterations=iterations)
+        X = np.ascontiguousarray(Y[:o].T)
+        ctx.set_inputs(X); ctx.set_pseudo(strided_pseudo_inputs(X, M)); ctx.set_times(t); ctx.set_outputs(Y[o])
+        X0 = np.stack([np.random.default_rng([seed, o, r]).random(5) for r in range(n_restarts)])
+
+        def fb(P_):
+            vals_, codes_ = ctx.scaled_dtc_batch(time_kernel.code, out_kernel.code, P_)
+            return np.where(codes_ == 0, -vals_, np.inf)
+        return neldermead.optimize_batch(fb, X0, iterations=iterations)
+
     t0 = time.perf_counter()
     device = None
     if world > 1:
@@ -88,7 +108,19 @@ def fit_chain(t, Y, M, n_restarts=1, iterations=200, seed=0, ctx=None, time_kern
         if dist.get_backend() == "nccl":
             device = torch.device("cuda", ctx.device)
     timing = {}
-    vals, thetas = parallel.fit_tasks(tasks, costs, run_task, 5, device, timing)
+    if batched:
+        out_costs = [0.02 if o == 0 else 1.0 + 0.03 * o for o in range(P)]
+        local = {}
+        tb = time.perf_counter()
+        for o in parallel.shard_tasks(out_costs, world, rank):
+            for r, res in enumerate(run_output(o)):
+                th = np.full(5, np.nan); th[:len(res.minimizer)] = res.minimizer
+                local[o * n_restarts + r] = (res.minimum, th)
+                evals[0] += res.f_calls
+        timing["busy_seconds"] = time.perf_counter() - tb
+        vals, thetas = parallel.gather_results(local, len(tasks), 5, device)
+    else:
+        vals, thetas = parallel.fit_tasks(tasks, costs, run_task, 5, device, timing)
     dt = time.perf_counter() - t0
     best = parallel.best_per_output(tasks, vals, thetas)
     if verbose and rank == 0:

@@ -1105,3 +1105,25 @@ def test_scaled_fit_with_batched_restarts(ctx):
     assert r8.minimum <= r1.minimum + 1e-7 * abs(r1.minimum)
     assert np.isfinite(r8.minimum) and len(p8) == 5
     assert (t2 - t1) < 4.0 * (t1 - t0), (t1 - t0, t2 - t1)          # 8 restarts in lock-step: well below 8x one fit
+
+
+def test_chain_fit_batched_restarts_matches_separate_runs(ctx):
+    """chain.fit_chain(batched=True): the restarts of every output in lock-step through the batched entry points
+    (gpar_lgssm_logpdf candidates for output 1, gpar_scaled_dtc_batch for the others) reach the optima of the separate
+    Nelder-Mead runs from the same starting points, in a fraction of the time."""
+    import time
+    from gpar_at_scale_b200 import chain
+    import toy_data as data
+    rng = np.random.default_rng(5)
+    x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=8496, true_samples=100)
+    Y = np.stack(y_obs)
+    t0 = time.perf_counter()
+    sep, info_s = chain.fit_chain(x, Y, M=50, n_restarts=6, iterations=30, seed=1, ctx=ctx, batched=False)
+    t1 = time.perf_counter()
+    bat, info_b = chain.fit_chain(x, Y, M=50, n_restarts=6, iterations=30, seed=1, ctx=ctx)          # automatic: batched
+    t2 = time.perf_counter()
+    assert set(bat) == {0, 1, 2} and info_b["tasks"] == 18
+    for o in range(3):
+        assert abs(bat[o][0] - sep[o][0]) <= 1e-6 * abs(sep[o][0]), (o, bat[o][0], sep[o][0])
+    assert info_b["objective_evals_this_rank"] == info_s["objective_evals_this_rank"]
+    assert (t2 - t1) < 0.5 * (t1 - t0), (t1 - t0, t2 - t1)
