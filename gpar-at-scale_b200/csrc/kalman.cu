@@ -939,7 +939,7 @@ struct LgssmOut {
 
 // chunk length of the one-pass log-pdf: the element pass should fill the device in whole waves of resident
 // threads (every thread walks the same number of steps, so a partly filled last wave costs a full one)
-int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads) {
+int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads, int64_t lmax) {
   const int64_t total = N * (int64_t)batch;
   if (total <= (1 << 19)) return 8;
   if (total <= (1 << 21)) return 16;
@@ -948,7 +948,7 @@ int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads) {
     const int64_t nCmax = w * resident_threads / batch;
     if (nCmax < 1) continue;
     L = (N + nCmax - 1) / nCmax;
-    if (L <= 192) break;
+    if (L <= lmax) break;
   }
   return (int)std::max<int64_t>(L, 32);
 }
@@ -962,7 +962,8 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
   int variant = NC == 1 ? 1 : 2;          // 3 resident blocks of 128 threads (no register cap) measured slightly ahead of 4 capped ones
   if (const char* e = getenv("GPAR_KF1_VARIANT")) variant = atoi(e);       // tuning knob: threads x resident blocks of the element pass
   const int tpb = variant == 3 ? 64 : 128, minb = variant == 0 ? 4 : (variant == 2 ? 1 : (variant == 3 ? 4 : (variant == 4 ? 2 : 3)));
-  int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb);
+  // tangent runs: longer chunks — the scan of their 81-double elements (255 registers, spills) costs more than the element pass
+  int L = onepass_chunk_length(N, batch, (int64_t)ctx->num_sms * tpb * minb, NC == 1 ? 192 : 640);
   if (const char* e = getenv("GPAR_KF_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) L = v; }
   const int nC = (int)((N + L - 1) / L);
   // scan plan (values): one block per sequence when it has at most 2048 chunks, else blocks of 256 chunks (2 per lane) +
