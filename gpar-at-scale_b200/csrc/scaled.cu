@@ -884,6 +884,19 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   CHK(check_scaled(ctx, "scaled_dtc"));
   CU(cudaSetDevice(ctx->device));
   CallTimer timer(ctx); gpar_drop_result(ctx);
+  // the reference's own sizes: the fused small-problem launch sequence (scaled_small.cu, 12 launches instead of ~30);
+  // it hands the candidate back (code -1) when cov(u) is too poorly conditioned for the collapsed statistic
+  if (!A_or_null && scaled_small_applicable(ctx)) {
+    bool fused = true;
+    if (const char* e = getenv("GPAR_SCALED_SMALL")) fused = atoi(e) != 0;
+    if (fused) {
+      int code = 0;
+      ctx->phase_valid = false;
+      CHK(scaled_small_batch(ctx, k_time, k_out, theta, 1, dtc, &code));
+      if (code == GPAR_ERR_NOT_POSDEF) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) or cholesky(A*A' + I) failed: the matrix is not positive definite");
+      if (code == 0) return GPAR_OK;
+    }
+  }
   // unpack_gpar (util.jl:45-55); variances squared, noise squared (dtc.jl:31-37)
   double pv[5];
   for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;
