@@ -22,11 +22,15 @@ class OptimResult:
         self.stopped_by_time = stopped_by_time
 
 
-def _simplex_steps(x0, iterations, g_tol, time_limit, show_trace):
+def _simplex_steps(x0, iterations, g_tol, time_limit, show_trace, speculative=False):
     """The algorithm as a coroutine: yields the list of points it needs evaluated next, receives their values, and
     finally returns the OptimResult.  `optimize` drives it with a scalar objective; `optimize_batch` drives several
     instances in lockstep so that one BATCHED objective call (gpar_exact_logpdf_batch, gpar_lgssm_logpdf with one
-    parameter set per candidate) serves all of them — simplex vertices x restarts evaluated concurrently."""
+    parameter set per candidate) serves all of them — simplex vertices x restarts evaluated concurrently.
+    speculative: every iteration asks for its reflection, expansion and both contraction points AT ONCE (they depend only
+    on the centroid and the worst vertex) and then takes exactly the decisions of the sequential algorithm with the values
+    it would have requested — same simplices, same `f_calls` (the count of the sequential algorithm); the extra
+    evaluations ride in the same batched call, which at small problem sizes costs no more than a single evaluation."""
     x0 = np.asarray(x0, dtype=np.float64)
     n = x0.size
     m = n + 1
@@ -52,10 +56,16 @@ def _simplex_steps(x0, iterations, g_tol, time_limit, show_trace):
         it += 1
         centroid = simplex[:-1].mean(axis=0)
         xr = centroid + alpha * (centroid - simplex[-1])
-        fr = (yield [xr])[0]; calls += 1
+        spec = None
+        if speculative:
+            spec = (yield [xr, centroid + beta * (xr - centroid), centroid + gamma * (xr - centroid), centroid - gamma * (xr - centroid)])
+            fr = spec[0]; calls += 1
+        else:
+            fr = (yield [xr])[0]; calls += 1
         if fr < fv[0]:
             xe = centroid + beta * (xr - centroid)
-            fe = (yield [xe])[0]; calls += 1
+            fe = spec[1] if speculative else (yield [xe])[0]
+            calls += 1
             if fe < fr:
                 simplex[-1], fv[-1] = xe, fe
             else:
@@ -65,11 +75,13 @@ def _simplex_steps(x0, iterations, g_tol, time_limit, show_trace):
         else:
             if fr < fv[-1]:       # outside contraction
                 xc = centroid + gamma * (xr - centroid)
-                fc = (yield [xc])[0]; calls += 1
+                fc = spec[2] if speculative else (yield [xc])[0]
+                calls += 1
                 ok = fc <= fr
             else:                 # inside contraction
                 xc = centroid - gamma * (xr - centroid)
-                fc = (yield [xc])[0]; calls += 1
+                fc = spec[3] if speculative else (yield [xc])[0]
+                calls += 1
                 ok = fc < fv[-1]
             if ok:
                 simplex[-1], fv[-1] = xc, fc
@@ -94,6 +106,19 @@ def optimize(f, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_t
     while True:
         try:
             pts = gen.send([f(p) for p in pts])
+        except StopIteration as e:
+            return e.value
+
+
+def optimize_speculative(fbatch, x0, iterations=1000, g_tol=1e-8, time_limit=float("nan"), show_trace=False):
+    """ONE Nelder-Mead run whose evaluations go through a batched objective `fbatch(points (K, n)) -> values (K,)`: the
+    initial simplex and the shrink steps as one batch each, and the four candidate points of an iteration speculatively
+    in one call (see _simplex_steps).  Same minimiser, minimum, iterations and f_calls as `optimize`."""
+    gen = _simplex_steps(x0, iterations, g_tol, time_limit, show_trace, speculative=True)
+    pts = next(gen)
+    while True:
+        try:
+            pts = gen.send(list(np.asarray(fbatch(np.array(pts, dtype=np.float64)), dtype=np.float64)))
         except StopIteration as e:
             return e.value
 

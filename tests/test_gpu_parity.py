@@ -1127,3 +1127,25 @@ def test_chain_fit_batched_restarts_matches_separate_runs(ctx):
         assert abs(bat[o][0] - sep[o][0]) <= 1e-6 * abs(sep[o][0]), (o, bat[o][0], sep[o][0])
     assert info_b["objective_evals_this_rank"] == info_s["objective_evals_this_rank"]
     assert (t2 - t1) < 0.5 * (t1 - t0), (t1 - t0, t2 - t1)
+
+
+def test_scaled_fit_speculative_nelder_mead(ctx):
+    """api.get_optim_scaled_gpar_params(speculative=True): ONE Nelder-Mead run at the reference's size whose candidate
+    points of an iteration ride in one gpar_scaled_dtc_batch call; same number of objective evaluations (as counted by
+    the sequential algorithm) and the same optimum as the plain run, in less wall-clock time."""
+    import time
+    from gpar_at_scale_b200 import api
+    import toy_data as data
+    rng = np.random.default_rng(9)
+    x, y_obs, x_true, y_true = data.generate_big_dataset(rng, data_samples=8496, true_samples=100)
+    Z = np.linspace(y_obs[0].min(), y_obs[0].max(), 50)
+    t0 = time.perf_counter()
+    p1, r1 = api.get_optim_scaled_gpar_params([y_obs[0]], [Z], x, y_obs[1], ctx=ctx, rng=np.random.default_rng(3), iterations=60, return_result=True)
+    t1 = time.perf_counter()
+    p2, r2 = api.get_optim_scaled_gpar_params([y_obs[0]], [Z], x, y_obs[1], ctx=ctx, rng=np.random.default_rng(3), iterations=60, return_result=True,
+                                              speculative=True)
+    t2 = time.perf_counter()
+    assert r2.f_calls == r1.f_calls and r2.iterations == r1.iterations
+    assert abs(r2.minimum - r1.minimum) <= 1e-8 * abs(r1.minimum)
+    print("plain %.1f ms, speculative %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+    assert (t2 - t1) < (t1 - t0)

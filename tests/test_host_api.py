@@ -96,3 +96,21 @@ def test_lbfgs_on_rosenbrock_and_failure_handling():
         return float(np.sum((v - 1.9) ** 2)), 2 * (v - 1.9)
     res = lbfgs.optimize(fg_box, np.array([-1.5, 0.0]), iterations=50)
     assert np.allclose(res.minimizer, [1.9, 1.9], atol=1e-4)
+
+
+def test_nelder_mead_speculative_walks_the_same_simplices():
+    """neldermead.optimize_speculative: the four candidate points of an iteration evaluated in one batched call, decisions
+    taken with the values the sequential algorithm would have requested — identical minimiser, minimum, iterations and
+    f_calls on Rosenbrock, a function with +inf regions, and a noisy quadratic in 5 dimensions."""
+    from gpar_at_scale_b200 import neldermead
+    fs = [lambda x: (1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2,
+          lambda x: np.inf if x[0] > 1.2 else float(np.sum((x - 0.5) ** 2) + np.sin(7 * x[1])),
+          lambda x: float(np.sum((x - np.arange(5) / 5.0) ** 2 * (1 + np.arange(5))))]
+    x0s = [np.array([-1.2, 1.0]), np.array([0.3, 0.9]), np.random.default_rng(0).random(5)]
+    for f, x0 in zip(fs, x0s):
+        calls = []
+        a = neldermead.optimize(f, x0, iterations=150)
+        b = neldermead.optimize_speculative(lambda P: (calls.append(len(P)), [f(p) for p in P])[1], x0, iterations=150)
+        assert np.array_equal(a.minimizer, b.minimizer) and a.minimum == b.minimum
+        assert a.iterations == b.iterations and a.f_calls == b.f_calls
+        assert max(calls) <= max(4, len(x0) + 1) and len(calls) <= a.iterations + 8        # one batched call per iteration (+ shrinks)
