@@ -200,42 +200,68 @@ ss_walk_kernel(const double* __restrict__ X, const double* __restrict__ Z, int D
   }
 }
 
-// start state of every chunk, in place of its zero-start response: in[0] = 0, in[c+1] = Psi_c in[c] + resp[c]
-// (the chain is latency bound: the operands of the next PF chunks are fetched ahead of the dependent mat-vecs)
+// start state of every chunk, in place of its zero-start response: in[0] = 0, in[c+1] = Psi_c in[c] + resp[c].
+// A warp per column: every lane composes the affine maps of its K consecutive chunks, the lane maps go through a
+// warp-shuffle scan, and the lane walks its chunks again from its exclusive prefix — 2K + 5 dependent steps instead of
+// nch (a single candidate at N = 8 496 has 266 chunks: the sequential chain was 30 us of a 170 us evaluation).
 template <int D>
-__global__ void ss_carry_kernel(const double* __restrict__ psi, double* __restrict__ state, int nch, int Mp) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x, cd = blockIdx.y;
+__global__ void __launch_bounds__(256)
+ss_carry_kernel(const double* __restrict__ psi, double* __restrict__ state, int nch, int Mp) {
+  const int lane = threadIdx.x & 31, m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), cd = blockIdx.y;
   if (m >= Mp) return;
-  constexpr int PF = 6;
-  double st[D];
+  const int K = (nch + 31) / 32;
+  const int c0 = lane * K, c1 = min(c0 + K, nch);
+  const double* ps = psi + (int64_t)cd * nch * D * D;
+  double* st = state + (int64_t)cd * nch * D * Mp + m;
+  double P[D * D], r[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) st[i] = 0.0;
-  for (int c0 = 0; c0 < nch; c0 += PF) {
-    double r[PF][D], ps[PF][D * D];
+  for (int i = 0; i < D * D; i++) P[i] = (i / D == i % D) ? 1.0 : 0.0;
 #pragma unroll
-    for (int u = 0; u < PF; u++) {
-      const int c = c0 + u;
-      if (c < nch) {
+  for (int i = 0; i < D; i++) r[i] = 0.0;
+  for (int c = c0; c < c1; c++) {
+    double F[D * D], R[D * D], nr[D];
 #pragma unroll
-        for (int i = 0; i < D; i++) r[u][i] = state[(((int64_t)cd * nch + c) * D + i) * Mp + m];
+    for (int i = 0; i < D * D; i++) F[i] = __ldg(ps + (int64_t)c * D * D + i);
 #pragma unroll
-        for (int i = 0; i < D * D; i++) ps[u][i] = __ldg(psi + ((int64_t)cd * nch + c) * D * D + i);
-      }
+    for (int i = 0; i < D; i++) { double a = st[((int64_t)c * D + i) * Mp];
+#pragma unroll
+      for (int j = 0; j < D; j++) a = fma(F[i * D + j], r[j], a);
+      nr[i] = a; }
+    matmul<D>(F, P, R);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) P[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) r[i] = nr[i];
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double Po[D * D], ro[D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Po[i] = __shfl_up_sync(0xffffffffu, P[i], d);
+#pragma unroll
+    for (int i = 0; i < D; i++) ro[i] = __shfl_up_sync(0xffffffffu, r[i], d);
+    if (lane >= d) {      // (earlier o this):  P <- P Po,  r <- P ro + r
+      double R[D * D], u2[D];
+      matmul<D>(P, Po, R);
+      matvec<D>(P, ro, u2);
+#pragma unroll
+      for (int i = 0; i < D * D; i++) P[i] = R[i];
+#pragma unroll
+      for (int i = 0; i < D; i++) r[i] += u2[i];
     }
+  }
+  double x[D];
 #pragma unroll
-    for (int u = 0; u < PF; u++) {
-      const int c = c0 + u;
-      if (c < nch) {
-        double nx[D];
+  for (int i = 0; i < D; i++) { const double v = __shfl_up_sync(0xffffffffu, r[i], 1); x[i] = lane == 0 ? 0.0 : v; }
+  for (int c = c0; c < c1; c++) {
+    double nx[D];
 #pragma unroll
-        for (int i = 0; i < D; i++) { state[(((int64_t)cd * nch + c) * D + i) * Mp + m] = st[i]; double a = r[u][i];
+    for (int i = 0; i < D; i++) { double* p = st + ((int64_t)c * D + i) * Mp; double a = *p; *p = x[i];
 #pragma unroll
-          for (int j = 0; j < D; j++) a = fma(ps[u][i * D + j], st[j], a);
-          nx[i] = a; }
+      for (int j = 0; j < D; j++) a = fma(__ldg(ps + (int64_t)c * D * D + i * D + j), x[j], a);
+      nx[i] = a; }
 #pragma unroll
-        for (int i = 0; i < D; i++) st[i] = nx[i];
-      }
-    }
+    for (int i = 0; i < D; i++) x[i] = nx[i];
   }
 }
 
@@ -464,7 +490,7 @@ int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, false>), gwalk, p.Mp, sm0, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
   CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-  LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 127) / 128, p.ncand), 128, 0, b.psi, b.state, p.nch, p.Mp);
+  LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 7) / 8, p.ncand), 256, 0, b.psi, b.state, p.nch, p.Mp);
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, true>), gwalk, p.Mp, sm1, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
   const int T = (p.Mp + SS_ST - 1) / SS_ST;
@@ -508,7 +534,7 @@ int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* theta
   // whitening chunks: a multiple of 32 steps, enough blocks (of Mp threads) to fill the device
   const int want_chunks = std::max(1, (int)((int64_t)ctx->num_sms * 16 * 32 / ((int64_t)Mp * std::max(1, std::min(ncand, 64)))));
   int Lc = (int)(((N + want_chunks - 1) / want_chunks + 31) / 32 * 32);
-  Lc = std::max(64, std::min(Lc, 2048));
+  Lc = std::max(32, std::min(Lc, 2048));
   if (const char* e = getenv("GPAR_SS_LC")) { int v = atoi(e); if (v >= 32 && v <= 4096 && v % 32 == 0) Lc = v; }      // tuning knob
   const int nch = (int)((N + Lc - 1) / Lc);
   const int T = (Mp + 63) / 64, pairs = T * (T + 1) / 2;
