@@ -72,45 +72,69 @@ sh_chunk_product_kernel(const double* __restrict__ table, int row, int off, int6
   }
 }
 
-// carry over chunks, one thread per sequence, in place: resp[c] (zero-start response of chunk c) -> state entering chunk c.
+// carry over the chunks, in place: resp[c] (zero-start response of chunk c) -> state entering chunk c.
 // forward: in[0] = 0, in[c+1] = Psi_c in[c] + resp[c];  reverse: in[nch-1] = 0, in[c-1] = Psi'_c in[c] + resp[c].
+// A warp per sequence: every lane composes the affine maps of its K consecutive chunks (in
+// processing order), the lane maps go through a warp-shuffle scan, and the lane walks its chunks again from its exclusive
+// prefix: 2K + 5 dependent steps instead of nch (105 chunks at 1024 x 10k: 27 us -> a few us per carry).
 template <int D, bool REVERSE>
-__global__ void __launch_bounds__(128)
-sh_carry_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Sp) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+sh_carry_warp_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Sp) {
+  const int lane = threadIdx.x & 31, s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= Sp) return;
-  constexpr int PF = 8;          // the chain is latency bound: the loads of the next PF chunks are issued ahead of the dependent mat-vecs
-  double st[D];
+  const int K = (nch + 31) / 32;
+  const int q0 = lane * K, q1 = min(q0 + K, nch);
+  double P[D * D], r[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) st[i] = 0.0;
-  for (int q0 = 0; q0 < nch; q0 += PF) {
-    double b[PF][D], ps[PF][D * D];
+  for (int i = 0; i < D * D; i++) P[i] = (i / D == i % D) ? 1.0 : 0.0;
 #pragma unroll
-    for (int u = 0; u < PF; u++) {
-      const int q = q0 + u;
-      if (q < nch) {
-        const int c = REVERSE ? nch - 1 - q : q;
+  for (int i = 0; i < D; i++) r[i] = 0.0;
+  for (int q = q0; q < q1; q++) {
+    const int c = REVERSE ? nch - 1 - q : q;
+    double F[D * D], R[D * D], nr[D];
 #pragma unroll
-        for (int i = 0; i < D; i++) b[u][i] = resp[((int64_t)c * D + i) * Sp + s];
+    for (int i = 0; i < D * D; i++) F[i] = __ldg(psi + (int64_t)c * D * D + i);
 #pragma unroll
-        for (int i = 0; i < D * D; i++) ps[u][i] = __ldg(psi + (int64_t)c * D * D + i);
-      }
+    for (int i = 0; i < D; i++) { double a = resp[((int64_t)c * D + i) * Sp + s];
+#pragma unroll
+      for (int j = 0; j < D; j++) a = fma(F[i * D + j], r[j], a);
+      nr[i] = a; }
+    matmul<D>(F, P, R);
+#pragma unroll
+    for (int i = 0; i < D * D; i++) P[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) r[i] = nr[i];
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double Po[D * D], ro[D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) Po[i] = __shfl_up_sync(0xffffffffu, P[i], d);
+#pragma unroll
+    for (int i = 0; i < D; i++) ro[i] = __shfl_up_sync(0xffffffffu, r[i], d);
+    if (lane >= d) {      // (earlier o this):  P <- P Po,  r <- P ro + r
+      double R[D * D], u2[D];
+      matmul<D>(P, Po, R);
+      matvec<D>(P, ro, u2);
+#pragma unroll
+      for (int i = 0; i < D * D; i++) P[i] = R[i];
+#pragma unroll
+      for (int i = 0; i < D; i++) r[i] += u2[i];
     }
+  }
+  double x[D];
 #pragma unroll
-    for (int u = 0; u < PF; u++) {
-      const int q = q0 + u;
-      if (q < nch) {
-        const int c = REVERSE ? nch - 1 - q : q;
-        double nx[D];
+  for (int i = 0; i < D; i++) { const double v = __shfl_up_sync(0xffffffffu, r[i], 1); x[i] = lane == 0 ? 0.0 : v; }
+  for (int q = q0; q < q1; q++) {
+    const int c = REVERSE ? nch - 1 - q : q;
+    double nx[D];
 #pragma unroll
-        for (int i = 0; i < D; i++) { resp[((int64_t)c * D + i) * Sp + s] = st[i]; double a = b[u][i];
+    for (int i = 0; i < D; i++) { double* p = resp + ((int64_t)c * D + i) * Sp + s; double a = *p; *p = x[i];
 #pragma unroll
-          for (int j = 0; j < D; j++) a = fma(ps[u][i * D + j], st[j], a);
-          nx[i] = a; }
+      for (int j = 0; j < D; j++) a = fma(__ldg(psi + (int64_t)c * D * D + i * D + j), x[j], a);
+      nx[i] = a; }
 #pragma unroll
-        for (int i = 0; i < D; i++) st[i] = nx[i];
-      }
-    }
+    for (int i = 0; i < D; i++) x[i] = nx[i];
   }
 }
 
@@ -270,11 +294,11 @@ int smooth_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
   dim3 grid(Sp / 128, nch);
   LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, (double*)nullptr, (double*)nullptr);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, false>), nch, 32, 0, table, TS, 0, N, LC, psi);
-  LAUNCH(ctx, (sh_carry_kernel<D, false>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
+  LAUNCH(ctx, (sh_carry_warp_kernel<D, false>), (Sp + 7) / 8, 256, 0, psi, state, nch, Sp);
   LAUNCH(ctx, (sh_forward_kernel<D, true>), grid, 128, 0, N, LC, table, yt, Sp, state, mst, a2part, (double*)nullptr);
   LAUNCH(ctx, (sh_backward_kernel<D, false>), grid, 128, 0, N, LC, table2, mst, Sp, state, mean_t);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, true>), nch, 32, 0, table2, TS2, D * D, N, LC, psi);
-  LAUNCH(ctx, (sh_carry_kernel<D, true>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
+  LAUNCH(ctx, (sh_carry_warp_kernel<D, true>), (Sp + 7) / 8, 256, 0, psi, state, nch, Sp);
   LAUNCH(ctx, (sh_backward_kernel<D, true>), grid, 128, 0, N, LC, table2, mst, Sp, state, mean_t);
   if (ex) { ex->var1 = v1; ex->sum_logS = lml1 + 2; ex->a2part = a2part; ex->nch = nch; }
   return GPAR_OK;
@@ -296,7 +320,7 @@ int filter_shared_d(gpar_ctx* ctx, int kind, double l, double s, double noise, i
   dim3 grid(Sp / 128, nch);
   LAUNCH(ctx, (sh_forward_kernel<D, false>), grid, 128, 0, N, LC, table, yt, Sp, state, (double*)nullptr, (double*)nullptr, (double*)nullptr);
   LAUNCH(ctx, (sh_chunk_product_kernel<D, false>), nch, 32, 0, table, TS, 0, N, LC, psi);
-  LAUNCH(ctx, (sh_carry_kernel<D, false>), (Sp + 127) / 128, 128, 0, psi, state, nch, Sp);
+  LAUNCH(ctx, (sh_carry_warp_kernel<D, false>), (Sp + 7) / 8, 256, 0, psi, state, nch, Sp);
   LAUNCH(ctx, (sh_forward_kernel<D, true>), grid, 128, 0, N, LC, table, yt, Sp, state, (double*)nullptr, a2part, alpha_t);
   ex->var1 = nullptr; ex->sum_logS = lml1 + 2; ex->a2part = a2part; ex->nch = nch;
   return GPAR_OK;
