@@ -1149,3 +1149,27 @@ def test_scaled_fit_speculative_nelder_mead(ctx):
     assert abs(r2.minimum - r1.minimum) <= 1e-8 * abs(r1.minimum)
     print("plain %.1f ms, speculative %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
     assert (t2 - t1) < (t1 - t0)
+
+
+@pytest.mark.parametrize("kt", [1, 2, 3])
+def test_scaled_objective_on_a_regular_grid_range(ctx, kt):
+    """The scaled objective with the times given as a range (gpar_set_times_range: constant transition matrix) — the
+    reference's toy data live on `range(0, step = 1/30)` (toy_data.jl:6).  Single candidate (fused small-problem
+    sequence), a batch of candidates, and the large-problem pipeline (GPAR_SCALED_SMALL=0) against the oracle."""
+    rng = np.random.default_rng(60 + kt)
+    n, m = 3000, 40
+    tt = 0.5 + np.arange(n) / 30.0
+    X = rng.normal(size=(n, 2)); Z = rng.normal(size=(m, 2)); y = np.sin(0.4 * tt) + 0.3 * rng.normal(size=n)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times_range(0.5, 1 / 30.0, n); ctx.set_outputs(y)
+    ths = rng.uniform(-1.0, 0.3, (4, 5))
+    ref = [scaled_gpar_objective(th, X, Z, tt, y, k_out=3, k_time=kt, decorrelate=cport.kalman_decorrelate) for th in ths]
+    vals, codes = ctx.scaled_dtc_batch(kt, 3, ths)
+    assert np.all(codes == 0)
+    for c in range(4):
+        assert abs(vals[c] - ref[c]) <= RTOL * abs(ref[c])
+        assert abs(ctx.scaled_dtc(kt, 3, ths[c]) - ref[c]) <= RTOL * abs(ref[c])
+    os.environ["GPAR_SCALED_SMALL"] = "0"
+    try:
+        assert abs(ctx.scaled_dtc(kt, 3, ths[0]) - ref[0]) <= RTOL * abs(ref[0])
+    finally:
+        del os.environ["GPAR_SCALED_SMALL"]
