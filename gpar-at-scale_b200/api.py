@@ -287,7 +287,7 @@ def smooth(lgssm, y, ctx=None):
 
 def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_structure=None, i_log_time_l=None, i_log_time_var=None,
                         i_log_noise_sigma=None, debug=True, ctx=None, rng=None, return_arrays=False, optimizer="neldermead",
-                        device_merge=False):
+                        device_merge=False, speculative=False):
     """temporal_gp_inference.jl:45-114 -> (opt_lgssm, output_observations).  optimizer="lbfgs" replaces the
     reference's Nelder-Mead (:82) by L-BFGS on the library's analytic gradient."""
     kernel_structure = kernel_structure or Matern52()
@@ -311,6 +311,8 @@ def get_sde_predictions(data_locations, data_outputs, output_locations, kernel_s
             v, g = ctx.lgssm_logpdf_grad(kernel_structure.code, p_)
             return -v[0], -g[0]
         results = lbfgs.optimize(nlml_fg, params)
+    elif speculative:    # the same run; the candidate points of an iteration in ONE pass over the sequence (candidates of gpar_lgssm_logpdf)
+        results = neldermead.optimize_speculative(lambda P: -ctx.lgssm_logpdf(kernel_structure.code, P), params)
     else:
         results = neldermead.optimize(nlml, params)                                            # :82
     opt_l, opt_process_var, opt_noise_sigma = unpack_gp(results.minimizer)

@@ -1173,3 +1173,15 @@ def test_scaled_objective_on_a_regular_grid_range(ctx, kt):
         assert abs(ctx.scaled_dtc(kt, 3, ths[0]) - ref[0]) <= RTOL * abs(ref[0])
     finally:
         del os.environ["GPAR_SCALED_SMALL"]
+
+
+def test_sde_fit_speculative_matches_plain(ctx):
+    """api.get_sde_predictions(speculative=True): the Nelder-Mead run of temporal_gp_inference.jl:82 with the candidate points
+    of an iteration evaluated as candidates on the one resident sequence — same predictions as the plain run."""
+    from gpar_at_scale_b200 import api
+    rng = np.random.default_rng(12)
+    n = 3000
+    t = np.sort(rng.uniform(0, 100, n)); y = np.sin(0.5 * t) + 0.2 * rng.normal(size=n); ts = np.linspace(1, 99, 200)
+    _, (m1, v1) = api.get_sde_predictions(t, y, ts, ctx=ctx, rng=np.random.default_rng(1), debug=False, return_arrays=True)
+    _, (m2, v2) = api.get_sde_predictions(t, y, ts, ctx=ctx, rng=np.random.default_rng(1), debug=False, return_arrays=True, speculative=True)
+    assert np.max(np.abs(m1 - m2)) <= 1e-6 * max(1.0, np.max(np.abs(m1))) and np.max(np.abs(v1 - v2) / v1) <= 1e-6
