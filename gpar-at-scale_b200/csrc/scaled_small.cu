@@ -334,31 +334,58 @@ ss_syrk_kernel(const double* __restrict__ beta, int Mp, int64_t Ns, int slabs_pe
 }
 
 // In-place Cholesky (lower, column-major, leading dimension ld) of the M x M matrix A in shared memory by the whole
-// block; the 1-based index of the first non-positive pivot goes to *info (shared; 0: success).  The elimination runs in
-// L D L' form — column j stays unscaled while it updates the trailing block, A_ik -= A_ij A_kj / A_jj — so that a column
-// costs ONE barrier; the columns are scaled by 1 / sqrt(d_j) at the end.
+// block; the 1-based index of the first non-positive pivot goes to *info (shared; 0: success).  Blocked by 8 columns:
+// the 8 x 8 diagonal block is factorised by one warp (warp-level barriers only), the rows below are solved against it
+// one thread per row, and the trailing block takes a rank-8 update — three block barriers per 8 columns instead of one
+// or more per column (the factorisation is a chain of M dependent pivots; everything else is latency to hide).
 __device__ void ss_chol_inplace(double* A, int M, int ld, int* info) {
-  for (int j = 0; j < M; j++) {
+  constexpr int NB = 8;
+  const int lane = threadIdx.x & 31;
+  for (int j0 = 0; j0 < M; j0 += NB) {
+    const int nb = M - j0 < NB ? M - j0 : NB;
     __syncthreads();
-    const double d = A[j + j * ld];
-    if (!(d > 0.0)) { if (threadIdx.x == 0 && *info == 0) *info = j + 1; break; }
-    const double inv = 1.0 / d;
-    for (int k = j + 1 + (threadIdx.x >> 4); k < M; k += (int)(blockDim.x >> 4)) {        // 16 lanes down a column, blockDim / 16 columns at a time
-      const double lk = A[k + j * ld] * inv;
-      for (int i = k + (threadIdx.x & 15); i < M; i += 16) A[i + k * ld] = fma(-A[i + j * ld], lk, A[i + k * ld]);
+    if (threadIdx.x < 32) {
+      for (int j = 0; j < nb; j++) {
+        const double d = A[(j0 + j) + (j0 + j) * ld];
+        if (!(d > 0.0)) { if (lane == 0 && *info == 0) *info = j0 + j + 1; break; }
+        const double inv = rsqrt(d);
+        __syncwarp();
+        if (lane > j && lane < nb) A[(j0 + lane) + (j0 + j) * ld] *= inv;
+        if (lane == j) A[(j0 + j) + (j0 + j) * ld] = d * inv;
+        __syncwarp();
+        for (int e = lane; e < NB * NB; e += 32) {
+          const int i = e % NB, k = e / NB;
+          if (k > j && i >= k && i < nb && k < nb) A[(j0 + i) + (j0 + k) * ld] = fma(-A[(j0 + i) + (j0 + j) * ld], A[(j0 + k) + (j0 + j) * ld], A[(j0 + i) + (j0 + k) * ld]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (*info) return;
+    for (int i = j0 + nb + threadIdx.x; i < M; i += blockDim.x) {        // panel: row i of L21 = A21 L11^-T
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        if (j < nb) {
+          double v = A[i + (j0 + j) * ld];
+#pragma unroll
+          for (int k = 0; k < NB; k++) if (k < j) v = fma(-A[i + (j0 + k) * ld], A[(j0 + j) + (j0 + k) * ld], v);
+          A[i + (j0 + j) * ld] = v / A[(j0 + j) + (j0 + j) * ld];
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = j0 + nb + (threadIdx.x >> 4); k < M; k += (int)(blockDim.x >> 4)) {        // trailing block: rank-nb update of the lower triangle
+      double lk[NB];
+#pragma unroll
+      for (int j = 0; j < NB; j++) lk[j] = j < nb ? A[k + (j0 + j) * ld] : 0.0;
+      for (int i = k + (threadIdx.x & 15); i < M; i += 16) {
+        double a = A[i + k * ld];
+#pragma unroll
+        for (int j = 0; j < NB; j++) if (j < nb) a = fma(-A[i + (j0 + j) * ld], lk[j], a);
+        A[i + k * ld] = a;
+      }
     }
   }
-  __syncthreads();
-  if (*info) return;
-  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const int i = e % M, j = e / M;
-    if (i >= j) {
-      const double dj = A[j + j * ld];
-      if (i > j) A[e % M + j * ld] = A[i + j * ld] * rsqrt(dj);
-    }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < M; j += blockDim.x) A[j + j * ld] = sqrt(A[j + j * ld]);
   __syncthreads();
 }
 // v <- L^-1 v for a lower-triangular L in shared memory (column-oriented substitution, one barrier per column)
