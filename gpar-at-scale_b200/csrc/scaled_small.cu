@@ -44,14 +44,6 @@ __device__ __forceinline__ double ss_kappa_r(double r) {
   return (1.0 + a + a * a * (1.0 / 3.0)) * exp_nonpos(-a);
 }
 
-template <int KIND>
-__device__ __forceinline__ double ss_kernel_value(const double* __restrict__ x, const double* __restrict__ z, int DX, double inv_l2, double s) {
-  double d2 = 0.0;
-  for (int d = 0; d < DX; d++) { const double df = x[d] - z[d]; d2 = fma(df, df, d2); }
-  double dummy;
-  return s * base_kernel_dev<KIND, false>(d2 * inv_l2, dummy);
-}
-
 __device__ __forceinline__ void ss_cp8(double* smem, const double* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
