@@ -558,8 +558,18 @@ int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* theta
   const int nch = (int)((N + Lc - 1) / Lc);
   const int T = (Mp + 63) / 64, pairs = T * (T + 1) / 2;
   const int64_t nslab = Ns / SS_TILE;
-  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)ctx->num_sms * 4 + (int64_t)pairs * std::min(ncand, 64) - 1) / ((int64_t)pairs * std::min(ncand, 64))));
-  nsplit = (int)std::min<int64_t>(nsplit, nslab);
+  // SYRK splits along N: whole waves of the 2 resident CTAs per SM (a partly filled last wave costs a full one), few
+  // enough that the tail's fixed-order sum of the partial G stays cheap
+  int nsplit = 1;
+  {
+    const int64_t resident = (int64_t)ctx->num_sms * 2, base_blocks = (int64_t)pairs * std::min(ncand, 64);
+    double best = 1e300;
+    for (int ns = 1; ns <= 32 && ns <= nslab; ns++) {
+      const int64_t waves = (base_blocks * ns + resident - 1) / resident;
+      const double cost = (double)waves / ns + 0.004 * ns;
+      if (cost < best - 1e-12) { best = cost; nsplit = ns; }
+    }
+  }
   const int slabs_per_split = (int)((nslab + nsplit - 1) / nsplit);
   nsplit = (int)((nslab + slabs_per_split - 1) / slabs_per_split);
   // candidates per pass: bounded scratch (table + alpha + beta + partial G + chunk states per candidate)
