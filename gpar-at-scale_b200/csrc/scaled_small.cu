@@ -257,6 +257,44 @@ ss_carry_kernel(const double* __restrict__ psi, double* __restrict__ state, int 
   }
 }
 
+// the same carry, one thread per column walking the chunks in order: the better choice for a few chunks (many candidates)
+template <int D>
+__global__ void ss_carry_seq_kernel(const double* __restrict__ psi, double* __restrict__ state, int nch, int Mp) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x, cd = blockIdx.y;
+  if (m >= Mp) return;
+  constexpr int PF = 6;
+  double st[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) st[i] = 0.0;
+  for (int c0 = 0; c0 < nch; c0 += PF) {
+    double r[PF][D], ps[PF][D * D];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
+#pragma unroll
+        for (int i = 0; i < D; i++) r[u][i] = state[(((int64_t)cd * nch + c) * D + i) * Mp + m];
+#pragma unroll
+        for (int i = 0; i < D * D; i++) ps[u][i] = __ldg(psi + ((int64_t)cd * nch + c) * D * D + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int c = c0 + u;
+      if (c < nch) {
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) { state[(((int64_t)cd * nch + c) * D + i) * Mp + m] = st[i]; double a = r[u][i];
+#pragma unroll
+          for (int j = 0; j < D; j++) a = fma(ps[u][i * D + j], st[j], a);
+          nx[i] = a; }
+#pragma unroll
+        for (int i = 0; i < D; i++) st[i] = nx[i];
+      }
+    }
+  }
+}
+
 // Gp (per candidate and split: Mp x Mp, both triangles written) = beta' beta over the split's steps.  Block (pair, split,
 // cand): 64 x 64 tile (ti >= tj) on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): 8 warps, each a
 // 32 x 16 sub-tile = 4 x 2 fragments (6 shared-memory loads per 8 DMMA; rows padded to 36 doubles: a fragment load is
@@ -509,7 +547,8 @@ int ss_run_kd(gpar_ctx* ctx, const SmallPlan& p, const SmallBufs& b) {
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, false>), gwalk, p.Mp, sm0, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
   CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-  LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 7) / 8, p.ncand), 256, 0, b.psi, b.state, p.nch, p.Mp);
+  if (p.nch <= 32) LAUNCH(ctx, ss_carry_seq_kernel<D>, dim3((p.Mp + 127) / 128, p.ncand), 128, 0, b.psi, b.state, p.nch, p.Mp);
+  else LAUNCH(ctx, ss_carry_kernel<D>, dim3((p.Mp + 7) / 8, p.ncand), 256, 0, b.psi, b.state, p.nch, p.Mp);
   LAUNCH(ctx, (ss_walk_kernel<KIND, D, true>), gwalk, p.Mp, sm1, X, Z, p.DX, p.N, p.M, p.Mp, p.Ns, p.Lc, p.nch, b.cand, b.table, b.alpha,
          b.state, b.beta, b.gpart);
   const int T = (p.Mp + SS_ST - 1) / SS_ST;
