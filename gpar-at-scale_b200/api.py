@@ -426,8 +426,9 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 inference_input_locations, out_kernel_structure=None, time_kernel_structure=None,
                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                 optimization_time_limit=1000.0, debug=False, ctx=None, rng=None, iterations=1000, nsamples=100,
-                                opt_params=None, sampler="device", seed=0, device_merge=True):
+                                opt_params=None, sampler="device", seed=0, device_merge=True, n_restarts=1, speculative=False):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
+    n_restarts / speculative: passed to get_optim_scaled_gpar_params (batched candidates; NEW).
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
     out_kernel_structure = out_kernel_structure or Matern52(); time_kernel_structure = time_kernel_structure or Matern52()
@@ -446,7 +447,7 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                                   i_log_time_l=i_log_time_l, i_log_time_var=i_log_time_var, i_log_out_l=i_log_out_l,
                                                   i_log_out_var=i_log_out_var, i_log_noise_sigma=i_log_noise_sigma,
                                                   optimization_time_limit=optimization_time_limit, debug=debug, ctx=ctx, rng=rng,
-                                                  iterations=iterations)
+                                                  iterations=iterations, n_restarts=n_restarts, speculative=speculative)
     opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma = opt_params
     params = np.array([opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma])
     # q(u) ~ p(u | y)  (:63-73)
