@@ -112,6 +112,8 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
                     &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->dla_ws, &ctx->dla_ws_side, &ctx->dla_ws2, &ctx->mrg, &ctx->test_pos, &ctx->shbuf, &ctx->chain};
   for (DevBuf* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+  if (ctx->sgraph.exec) cudaGraphExecDestroy(ctx->sgraph.exec);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);

@@ -70,6 +70,17 @@ struct gpar_ctx {
   DevBuf qW; int64_t qW_M = 0; int32_t qW_S = 0;     // resident W = U_u \ eps of the last gpar_sample_q_u
   DevBuf chain; int64_t chain_n = 0;                  // values passed down the GPAR chain (gpar_group_broadcast / gpar_set_inputs_column)
   void* pinned = nullptr; size_t pinned_cap = 0;
+  // pinned staging of the fused small-problem sequence (LGSSM parameters, candidates, results): fixed host addresses, so
+  // that the sequence can be replayed as a CUDA graph; param_staging (when set) is where kalman.cu packs (l, s, noise)
+  void* small_pin = nullptr; size_t small_pin_cap = 0;
+  double* param_staging = nullptr;
+  // the captured sequence of the last (shape, pointers) key and its bookkeeping (scaled_small.cu)
+  struct SmallGraph {
+    unsigned long long key[20] = {0}; bool have_key = false;      // key of `exec` / of the last plain run
+    int warm = 0;                                                // plain runs seen with this key (capture on the second)
+    bool failed = false;                                         // capture or instantiation failed for this key: stay plain
+    cudaGraphExec_t exec = nullptr;
+  } sgraph;
   // lanes: worker contexts on the same device (own streams and scratch, resident data borrowed from this context) that
   // evaluate hyper-parameter candidates concurrently (gpar_scaled_dtc_batch)
   std::vector<gpar_ctx*> lanes;

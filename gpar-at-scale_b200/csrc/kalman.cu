@@ -2162,9 +2162,13 @@ int lgssm_run_steady(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, const do
 int upload_params(gpar_ctx* ctx, const double* hl, const double* hs, const double* hn, int nparam, SeqParams* sp) {
   CU(ctx->kal_c.reserve((size_t)3 * nparam * sizeof(double)));
   double* dp = ctx->kal_c.as<double>();
-  std::vector<double> pack((size_t)3 * nparam);        // one copy instead of three (each is ~5 us of host time on the latency path)
+  // one copy instead of three (each is ~5 us of host time on the latency path); from the caller's pinned staging when it
+  // provides one (the fused small-problem sequence replays this copy inside a CUDA graph)
+  std::vector<double> pack_local;
+  double* pack = ctx->param_staging;
+  if (!pack) { pack_local.resize((size_t)3 * nparam); pack = pack_local.data(); }
   for (int i = 0; i < nparam; i++) { pack[i] = hl[i]; pack[nparam + i] = hs[i]; pack[2 * (size_t)nparam + i] = hn[i]; }
-  CU(cudaMemcpyAsync(dp, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp, pack, (size_t)3 * nparam * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   *sp = SeqParams{dp, dp + nparam, dp + 2 * nparam, nparam, -1, -1, -1, 0.0};
   return GPAR_OK;
 }
