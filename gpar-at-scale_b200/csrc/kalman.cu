@@ -937,6 +937,58 @@ struct LgssmOut {
   bool ybroadcast = false;       // every "sequence" of the batch reads the SAME y (hyper-parameter candidates on one sequence)
 };
 
+// Inclusive prefixes of a sequence's chunk elements by ONE thread walking the chunks in order.  A prefix that starts at the
+// sequence's first element is just a filtering state (A = 0, eta = 0, J = 0: the first chunk starts from the prior), so
+// applying the next element is  M = (I + P J)^-1,  m' = A M (m + P eta) + b,  P' = A M P A' + C  — half a general combine
+// and no shuffles.  With many sequences and few chunks each (tangent runs: 1024 x 18) this replaces the warp-shuffle
+// pyramid, whose 81-double Dual elements spill (same 0.2 ms at 1024 x 10k with 18 chunks per sequence, a third of the code;
+// a warp per block and a prefetched next element were measured: slower).
+template <int D, class F>
+__global__ void __launch_bounds__(64)
+kf_prefix_seq_kernel(Level l0, int batch) {
+  typedef FiltElem<D, F> E;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int64_t fstride = (int64_t)batch * l0.P, off0 = (int64_t)b * l0.P;
+  E pre; load_elem(pre, l0.base, fstride, off0);
+  for (int c = 1; c < l0.n; c++) {
+    E e; load_elem(e, l0.base, fstride, off0 + c);
+    const F* A = e.v; const F* bb = e.v + E::OB; const F* C = e.v + E::OC; const F* eta = e.v + E::OE; const F* J = e.v + E::OJ;
+    F* m = pre.v + E::OB; F* P = pre.v + E::OC;
+    F Mx[D * D], Mi[D * D], X[D * D], T[D * D], v[D], u[D];
+    symsym<D>(P, J, Mx);
+#pragma unroll
+    for (int i = 0; i < D; i++) Mx[i * D + i] += 1.0;
+    inv_general<D>(Mx, Mi);
+    matmul<D>(A, Mi, X);
+    symvec<D>(P, eta, v);
+#pragma unroll
+    for (int i = 0; i < D; i++) v[i] = v[i] + m[i];
+    matvec<D>(X, v, u);
+    matsym<D>(X, P, T);
+    F Pn[NSYM<D>];
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = i; j < D; j++) { F a = SYM(C, i, j);
+#pragma unroll
+        for (int k = 0; k < D; k++) a = fma(T[i * D + k], A[j * D + k], a);
+        SYM(Pn, i, j) = a; }
+#pragma unroll
+    for (int i = 0; i < D; i++) m[i] = u[i] + bb[i];
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) P[i] = Pn[i];
+    // the prefix as an element: (A, eta, J) stay zero
+#pragma unroll
+    for (int i = 0; i < D * D; i++) pre.v[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) pre.v[E::OE + i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NSYM<D>; i++) pre.v[E::OJ + i] = 0.0;
+    store_elem(pre, l0.base, fstride, off0 + c);
+  }
+}
+
 // chunk length of the one-pass log-pdf: the element pass should fill the device in whole waves of resident
 // threads (every thread walks the same number of steps, so a partly filled last wave costs a full one)
 int onepass_chunk_length(int64_t N, int batch, int64_t resident_threads, int64_t lmax) {
@@ -1002,8 +1054,12 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
     default: KF1_LAUNCH(128, 3, KF1_PD); break;
   }
 #undef KF1_LAUNCH
+  bool seq_prefix = false;
   if constexpr (NC > 1) {
-    if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
+    seq_prefix = nC <= 64 && batch >= 128;        // many sequences, few chunks each: one thread per sequence (kf_prefix_seq_kernel)
+    if (const char* e = getenv("GPAR_KF_SEQ_PREFIX")) seq_prefix = atoi(e) != 0 && nC <= 4096;      // testing knob
+    if (seq_prefix) { if (nC > 1) LAUNCH(ctx, (kf_prefix_seq_kernel<D, F>), (batch + 63) / 64, 64, 0, f0, batch); }
+    else if (nC > 1) CHK(run_scan<FE>(ctx, fp, batch));
   } else if (two_level) {
     LAUNCH_PDL(ctx, (scan_span_kernel<FE, 4>), dim3(n1, batch), dim3(128), 0, f0, f1, batch, span, 2);
     LAUNCH_PDL(ctx, (scan_span_kernel<FE, 8>), dim3(1, batch), dim3(256), 0, f1, none, batch, n1, std::min(8, (n1 + 255) / 256));
@@ -1014,7 +1070,8 @@ int lgssm_logpdf_onepass(gpar_ctx* ctx, SeqParams sp, int batch, int64_t N, cons
     else if (want_lanes > 64 / 2) LAUNCH_PDL(ctx, (scan_span_kernel<FE, 2>), dim3(1, batch), dim3(64), 0, f0, none, batch, span, (nC + 63) / 64);
     else LAUNCH_PDL(ctx, (scan_span_kernel<FE, 1>), dim3(1, batch), dim3(32), 0, f0, none, batch, span, (nC + 31) / 32);
   }
-  LAUNCH_PDL(ctx, (kf_chunk_lml_kernel<D, F>), dim3(nblk, batch), dim3(128), 0, f0, f1, span, nC, batch, aux, part2, tickets, N, o.lml, o.dlml, o.sums);
+  // (after the sequential prefix pass every level-0 entry is a complete prefix: no upper level)
+  LAUNCH_PDL(ctx, (kf_chunk_lml_kernel<D, F>), dim3(nblk, batch), dim3(128), 0, f0, seq_prefix ? none : f1, seq_prefix ? (nC > 0 ? nC : 1) : span, nC, batch, aux, part2, tickets, N, o.lml, o.dlml, o.sums);
   return GPAR_OK;
 }
 

@@ -23,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"onepass": os.environ.get("GPAR_KF_ONEPASS", "1"), "variant": os.environ.get("GPAR_KF1_VARIANT", "-"), "cfg3_grad_ms": round(a, 4), "cfg3_value_ms": round(v, 4), "cfg3_launches": la,
                       "1x10M_grad_ms": round(c, 4), "1x10M_launches": lc, "g0": [float(x) for x in np.ravel(ra[1])[:3]], "g10": [float(x) for x in np.ravel(rc[1])[:3]]}))
 else:
-    for op, v in (("1", "2"), ("1", "3"), ("1", "4")):
+    for op, v in (("1", None),):
         env = dict(os.environ); env["GPAR_KF_ONEPASS"] = op
         if v: env["GPAR_KF1_VARIANT"] = v
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)
