@@ -866,6 +866,26 @@ def test_abi_error_behaviour():
     assert np.all(np.isfinite(c.lgssm_logpdf(3, th3)))
     with pytest.raises(gp.GparError, match="ntheta"):
         c.exact_logpdf(3, 3, np.zeros(4))
+    # the batched entry points: missing data, kernels without a state-space form, NULL arguments, a failed Cholesky with
+    # and without the per-candidate code array
+    import ctypes
+    c2 = gp.Context(0)
+    with pytest.raises(gp.GparError, match="must be set|time|inputs"):
+        c2.scaled_dtc_batch(3, 3, np.zeros((2, 5)))
+    rng = np.random.default_rng(3)
+    c2.set_inputs(rng.normal(size=(200, 1))); c2.set_pseudo(np.repeat(np.linspace(-1, 1, 5), 2)[:, None]); c2.set_times(np.arange(200.0)); c2.set_outputs(rng.normal(size=200))
+    with pytest.raises(gp.GparError, match="state-space"):
+        c2.scaled_dtc_batch(0, 3, np.zeros((2, 5)))
+    lib = c2._lib; vals = np.zeros(2)
+    assert lib.gpar_scaled_dtc_batch(c2._h, 3, 3, None, 2, vals.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None) != 0
+    th = np.zeros((2, 5)); th[1, 4] = -60.0          # duplicated pseudo-inputs and no jitter to speak of: cov(u) singular
+    v, cd = c2.scaled_dtc_batch(3, 0, th)
+    assert cd[0] == 0 and np.isfinite(v[0])
+    if cd[1] != 0:
+        assert np.isnan(v[1])
+        rc = lib.gpar_scaled_dtc_batch(c2._h, 3, 0, th.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 2, vals.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None)
+        assert rc != 0          # without a code array a failed Cholesky fails the call
+    c2.close()
     c.close()
 
 
