@@ -114,3 +114,25 @@ def test_nelder_mead_speculative_walks_the_same_simplices():
         assert np.array_equal(a.minimizer, b.minimizer) and a.minimum == b.minimum
         assert a.iterations == b.iterations and a.f_calls == b.f_calls
         assert max(calls) <= max(4, len(x0) + 1) and len(calls) <= a.iterations + 8        # one batched call per iteration (+ shrinks)
+
+
+def test_nelder_mead_lock_step_batch_equals_separate_runs():
+    """neldermead.optimize_batch: several runs in lock-step on one batched objective — every run performs exactly the
+    operations of a separate `optimize` (same minimiser, minimum, iterations, f_calls), including runs that converge
+    early, +inf objective values and shrink steps; the batched objective sees at most (n + 1) points per run and round."""
+    from gpar_at_scale_b200 import neldermead
+    def f(x):
+        if x[0] < -2.0:
+            return np.inf
+        return float((1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2 + 0.1 * np.sin(5 * x[2]) ** 2 + x[2] ** 2)
+    rng = np.random.default_rng(4)
+    X0 = rng.uniform(-1.5, 1.5, (7, 3)); X0[3] = [1.0, 1.0, 0.0]          # (one run starts at the optimum: converges at once)
+    sizes = []
+    def fbatch(P):
+        sizes.append(len(P)); return [f(p) for p in P]
+    runs = neldermead.optimize_batch(fbatch, X0, iterations=80)
+    for k in range(7):
+        one = neldermead.optimize(f, X0[k], iterations=80)
+        assert np.array_equal(runs[k].minimizer, one.minimizer) and runs[k].minimum == one.minimum
+        assert runs[k].iterations == one.iterations and runs[k].f_calls == one.f_calls and runs[k].converged == one.converged
+    assert max(sizes) <= 7 * 4 and sizes[0] == 7 * 4
