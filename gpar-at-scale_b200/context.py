@@ -337,6 +337,29 @@ class Group:
         self._check(self._lib.gpar_group_dtc_logpdf_sharded(self._h, int(kernel), dptr(th), int(bool(vfe)), float(jitter), ctypes.byref(val), dptr(g3)))
         return (val.value, g3) if grad else val.value
 
+    def load_row_slices(self, X, Z, t, y, bounds=None):
+        """Row-shards one scaled problem over the members: every member gets the full (t, y) and Z, member i rows
+        bounds[i]:bounds[i+1] of X (default: equal slices, boundaries rounded to multiples of 1024) -> row_lo (ndev,) int64."""
+        X = np.asarray(X, dtype=np.float64); X = X[:, None] if X.ndim == 1 else X
+        n = len(self); N = X.shape[0]
+        if bounds is None:
+            bounds = [min(N, (N * i // n + 1023) // 1024 * 1024) for i in range(n)] + [N]
+        assert len(bounds) == n + 1 and bounds[0] == 0 and bounds[-1] == N
+        for i, m in enumerate(self.members):
+            m.set_times(t); m.set_outputs(y); m.set_pseudo(Z); m.set_inputs(np.ascontiguousarray(X[bounds[i]:bounds[i + 1]]))
+            m.set_noise_vector(None)
+        return np.asarray(bounds[:-1], dtype=np.int64)
+
+    def scaled_dtc_sharded(self, k_time, k_out, theta, row_lo):
+        """ONE scaled-GPAR objective over the row slices resident on the members (load_row_slices): one all-gather of the
+        slice summaries (filter carry), one all-reduce of (beta'beta, beta'alpha), tail on member 0 -> value."""
+        th = as_f64(np.asarray(theta).ravel()); lo = np.ascontiguousarray(row_lo, dtype=np.int64)
+        assert th.shape == (5,) and lo.shape == (len(self),)
+        val = ctypes.c_double()
+        self._check(self._lib.gpar_group_scaled_dtc_sharded(self._h, int(k_time), int(k_out), dptr(th),
+                                                            lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(val)))
+        return val.value
+
     def scaled_dtc(self, k_time, k_out, thetas, grad=False):
         th = as_f64(np.atleast_2d(thetas)); n = len(self)
         assert th.shape == (n, 5)

@@ -107,7 +107,7 @@ int gpar_ctx_destroy(gpar_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
-  DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->panelB, &ctx->kal_f, &ctx->partial, &ctx->segs,
+  DevBuf* bufs[] = {&ctx->X, &ctx->Z, &ctx->t, &ctx->y, &ctx->rvec, &ctx->panelK, &ctx->panelD, &ctx->panelB, &ctx->panelA, &ctx->kal_f, &ctx->partial, &ctx->segs,
                     &ctx->jobs, &ctx->gpart, &ctx->scal, &ctx->dense, &ctx->tailws, &ctx->info,
                     &ctx->kal_a, &ctx->kal_b, &ctx->kal_c, &ctx->kal_d, &ctx->kal_e, &ctx->qW, &ctx->dla_ws, &ctx->dla_ws_side, &ctx->dla_ws2, &ctx->mrg, &ctx->test_pos, &ctx->shbuf, &ctx->chain};
   for (DevBuf* b : bufs) b->release();
@@ -232,7 +232,7 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
   // value-only calls: when cov(u) is poorly conditioned, whiten the panel by L_u before the SYRK (A = L_u^-1 Kuf as the
   // reference forms it, dtc_example.jl:14-16) instead of collapsing to Kuf Kfu first — see gpar_needs_whitened_panel
-  bool whitened = false;
+  bool whitened = false, whitened_grad = false;
   {
     TailBufs tb;
     CHK(tail_layout(ctx, want_grad, vfe, &tb));
@@ -246,13 +246,23 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
       whitened = true;
     }
     if (want_grad) {
-      // poorly conditioned cov(u): the analytic gradient (collapsed statistic, explicit inverse) loses cond * eps and its
-      // Lambda may not even factor — take value and gradient from the whitened-panel value path (see gpar_fd_gradient)
-      if (const char* e = getenv("GPAR_GRAD_FD")) ill = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
-      if (ill) {
+      // poorly conditioned cov(u): the collapsed analytic gradient (explicit (cov(u) + G)^-1) loses cond * eps and its Lambda
+      // may not even factor — whiten BOTH panels by L_u (A = L_u^-1 Kuf, A_D = L_u^-1 D'), so that the SYRK yields
+      // A A' and A A_D' directly, and finish in whitened coordinates (dtc_tail_whitened).
+      // Testing knobs: GPAR_GRAD_FD=1 forces the 4-point stencil of the value path, 0 the collapsed analytic form;
+      // GPAR_GRAD_WHITENED=1 forces the whitened form.
+      bool fd = false; whitened_grad = ill;
+      if (const char* e = getenv("GPAR_GRAD_FD")) { fd = atoi(e) != 0; whitened_grad = false; }
+      if (const char* e = getenv("GPAR_GRAD_WHITENED")) { if (atoi(e) != 0) { whitened_grad = true; fd = false; } }
+      if (fd) {
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
         CHK(gpar_dtc_logpdf(ctx, kernel, theta, vfe, jitter, val, nullptr));
         return gpar_fd_gradient([&](const double* th, double* v) { return gpar_dtc_logpdf(ctx, kernel, th, vfe, jitter, v, nullptr); }, theta, 3, grad);
+      }
+      if (whitened_grad) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+        CHK(panel_left_solve(ctx, ctx->panelK.as<double>(), Npad, Mpad, M, tb.Lu));
+        CHK(panel_left_solve(ctx, ctx->panelD.as<double>(), Npad, Mpad, M, tb.Lu));
       }
     }
   }
@@ -262,6 +272,7 @@ int gpar_dtc_logpdf(gpar_ctx* ctx, int kernel, const double theta[3], int vfe, d
   double yy = 0.0;
   CU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (whitened_grad) return dtc_tail_whitened(ctx, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr);
   return dtc_tail(ctx, kernel, p, vfe, jitter, N, G, H, gh, gh + Mpad, yy, val, grad, nullptr, whitened);
 }
 

@@ -59,7 +59,7 @@ struct gpar_ctx {
   double t_reg_dt = 0.0;              // > 0: the resident times are the regular grid t0 + k dt (gpar_set_times_range)
 
   // scratch (grown on demand)
-  DevBuf panelK, panelD, panelB, kal_f, partial, segs, jobs, gpart, scal, dense, tailws, info;
+  DevBuf panelK, panelD, panelB, panelA, kal_f, partial, segs, jobs, gpart, scal, dense, tailws, info;
   DevBuf kal_a, kal_b, kal_c, kal_d, kal_e;
   // merged train+test problem (gpar_set_merged): staging, position of every test point in the sorted arrays,
   // and the device arrays of the last smoother / prediction result (for gpar_take_test)
@@ -84,6 +84,12 @@ struct gpar_ctx {
   // lanes: worker contexts on the same device (own streams and scratch, resident data borrowed from this context) that
   // evaluate hyper-parameter candidates concurrently (gpar_scaled_dtc_batch)
   std::vector<gpar_ctx*> lanes;
+  // one row slice of a scaled objective sharded over a group (scaled.cu: scaled_slice_phase1 / 2 / finish)
+  struct SliceState {
+    int D = 0, Mpad = 0, nch = 0, whg = 0, CT = 1; int64_t lo = 0, Npad = 0; bool robust = false;
+    const double *table = nullptr, *alpha = nullptr; double *sums = nullptr, *resp = nullptr, *psi = nullptr, *gp = nullptr;
+    double *summary = nullptr, *init = nullptr, *G = nullptr, *g = nullptr; size_t summary_count = 0, stats_count = 0;
+  } slice;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;
 };
@@ -286,6 +292,18 @@ int dtc_tail_prepare(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double
 int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter, int64_t N,
              const double* G, const double* H, const double* g, const double* h, double yy,
              double* val, double* grad, double* raw_out = nullptr, bool whitened_G = false);
+// The tail in whitened coordinates (ill-conditioned cov(u)): statistics of the panels whitened by L_u before the SYRK.
+// Cop = L_u^-T Lambda^-1 (dense M x M, the operand of S = A'(Lambda^-1 L_u^-1)), wt = Lambda^-1 A alpha, w = L_u^-T wt — device;
+// trQ, WQ, XQ: tr Q, <L_u^-1 L_u^-T, Q>, <L_u^-1 (l dKuu/dl) L_u^-T, Q> with Q = Lambda^-1 - I + wt wt'.
+struct WhitenedTail { const double *Cop, *wt, *w; double trQ, WQ, XQ, cc; };
+int dtc_tail_whitened(gpar_ctx* ctx, const GpParams& p, int vfe, double jitter, int64_t N,
+                      const double* Gw, const double* Hw, const double* g, const double* h, double yy,
+                      double* val, double* grad, WhitenedTail* out);
+// scaled.cu: a row slice of the scaled objective (the context holds the full (t, y) and rows [lo, lo + N) of X); group.cu
+// all-gathers ctx->slice.summary between phase 1 and 2 and all-reduces ctx->slice.G (stats_count doubles) before finish
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo);
+int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member);
+int scaled_slice_finish(gpar_ctx* ctx, double* dtc);
 // scaled.cu: conditioning decision and the panel whitening by L_u (see gpar_needs_whitened_panel)
 int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
 bool gpar_needs_whitened_panel(const double minmax[2]);

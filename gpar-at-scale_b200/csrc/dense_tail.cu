@@ -89,6 +89,43 @@ __global__ void trace_final_kernel(const double* part, int nblocks, double* out)
   out[i] = acc;
 }
 
+// ---- whitened-coordinate gradient (ill-conditioned cov(u)) ----------------------------------------
+// Q = Lambda^-1 - I + wt wt'  (= A (dF/dA)': the M x M matrix every cov(u)-derivative contracts with; eigenvalues of
+// Lambda^-1 - I lie in (-1, 0], so nothing here is larger than the data term)
+__global__ void whitened_q_kernel(const double* __restrict__ Li2, const double* __restrict__ wt, int M, double* __restrict__ Q) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)M * M) return;
+  const int a = (int)(e % M), b = (int)(e / M);
+  Q[e] = Li2[e] - (a == b ? 1.0 : 0.0) + wt[a] * wt[b];
+}
+// Element-wise sums of the whitened tail; same partial / final scheme (and slot count) as trace_kernel:
+//  [0] tr Q  [1] <W,Q>  [2] <X,Q>  [3] <Lambda^-1,Hw>  [4] wt'Hw wt  [5] wt'hA  [6] tr Hw  [7] <X,GA>  [8] <W,GA>
+// with W = L_u^-1 L_u^-T, X = L_u^-1 (l dKuu/dl) L_u^-T; Hw, hA, GA nullable.
+__global__ void __launch_bounds__(256)
+whitened_trace_kernel(int M, const double* __restrict__ Q, const double* __restrict__ W, const double* __restrict__ X,
+                      const double* __restrict__ Li2, const double* __restrict__ Hw, const double* __restrict__ GA,
+                      const double* __restrict__ wt, const double* __restrict__ hA, double* __restrict__ part) {
+  __shared__ double sh[32];
+  double acc[NTR];
+#pragma unroll
+  for (int i = 0; i < NTR; i++) acc[i] = 0.0;
+  const int64_t total = (int64_t)M * M;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e % M), b = (int)(e / M);
+    const double q = Q[e], w = W[e], x = X[e];
+    if (a == b) acc[0] += q;
+    acc[1] += w * q;  acc[2] += x * q;
+    if (Hw) { const double hh = Hw[e]; acc[3] += Li2[e] * hh; acc[4] += wt[a] * wt[b] * hh; if (a == b) acc[6] += hh; }
+    if (GA) { const double ga = GA[e]; acc[7] += x * ga; acc[8] += w * ga; }
+    if (hA && b == 0) acc[5] += wt[a] * hA[a];
+  }
+#pragma unroll
+  for (int i = 0; i < NTR; i++) {
+    double r = block_sum(acc[i], sh);
+    if (threadIdx.x == 0) part[(int64_t)blockIdx.x * NTR + i] = r;
+  }
+}
+
 }  // namespace
 
 static const double LOG2PI = 1.8378770664093454835606594728112;
@@ -233,6 +270,89 @@ int dtc_tail(gpar_ctx* ctx, int kind, const GpParams& p, int vfe, double jitter_
       ds += -0.5 * ((double)N * ip - (trB + jitter * ip * trC) / p.s);
       dn += -0.5 * (-(double)N * p.s * ip2 + trB * ip);
       if (jit_is_noise) dn += -0.5 * ip * trC;
+    }
+    grad[0] = dlogl * p.dl / p.l;
+    grad[1] = ds * p.ds_dv;
+    grad[2] = dn * p.dn;
+  }
+  return GPAR_OK;
+}
+
+// The tail in WHITENED coordinates, for cov(u) too poorly conditioned for the collapsed statistic.
+// Inputs are the statistics of the panels whitened by L_u BEFORE the SYRK: Gw = A A' sigma^2 (A = L_u^-1 Kuf / sigma as
+// the reference forms it, dtc.jl:119-120), Hw = L_u^-1 (Kuf D) L_u^-T (forward-mode callers; nullable), and the raw
+// g = Kuf y, h = D'y.  With Lambda = I + A A', a = A y / sigma, wt = Lambda^-1 a:
+//   dF/dA = -Lambda^-1 A + wt e',  e = y / sigma - A'wt;   dA = L_u^-1 dKuf / sigma - (L_u^-1 dL_u) A;
+//   L_u^-1 dL_u = Phi(L_u^-1 dcov(u) L_u^-T)  =>  cov(u)-part of dF = -1/2 <L_u^-1 dcov(u) L_u^-T, Q>,  Q = Lambda^-1 - I + wt wt'
+// — every matrix that is formed is conditioned like Lambda; L_u enters through triangular solves and V = L_u^-1 only.
+// grad (nullable): the three plain-DTC / VFE derivatives.  out (nullable): what the reverse-mode caller (scaled.cu) needs.
+int dtc_tail_whitened(gpar_ctx* ctx, const GpParams& p, int vfe, double jitter_in, int64_t N,
+                      const double* Gw, const double* Hw, const double* g, const double* h, double yy,
+                      double* val, double* grad, WhitenedTail* out) {
+  const int M = (int)ctx->M;
+  const size_t MM = (size_t)M * M;
+  const bool jit_is_noise = jitter_in < 0.0;
+  const double jitter = jit_is_noise ? p.noise : jitter_in;
+  const double ip = 1.0 / p.noise;
+  TailBufs tb;
+  CHK(tail_layout(ctx, true, vfe, &tb));
+  double *Lu = tb.Lu, *Bm = tb.Bm, *V = tb.V, *W = tb.Kinv, *Li2 = tb.R, *Q = tb.Pm, *T1 = tb.Kj, *X = tb.dKu;
+  double* GA = vfe ? tb.Cm : nullptr;
+  double *cvec = tb.cvec, *wvec = tb.wvec, *wt = tb.cvec + 2 * (size_t)M, *hA = tb.cvec + 3 * (size_t)M, *sc = tb.sc;
+  int* dinfo = tb.dinfo;
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+  CU(cudaMemcpyAsync(Bm, Gw, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ip != 1.0) CHK(dla_scal(ctx, (long long)MM, ip, Bm));
+  if (GA) CU(cudaMemcpyAsync(GA, Bm, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  LAUNCH(ctx, trace_add_identity_kernel, 1, 256, 0, Bm, M, sc + 0);
+  CHK(dla_potrf(ctx, M, Bm, M, dinfo + 1));
+  LAUNCH(ctx, logdet_kernel, 1, 256, 0, Bm, M, sc + 1);
+  CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsv(ctx, false, M, Lu, M, cvec));
+  CHK(dla_trsv(ctx, false, M, Bm, M, cvec, ip));                       // c = L_Lambda^-1 a
+  CHK(dla_dot(ctx, M, cvec, cvec, sc + 2));
+  CU(cudaMemcpyAsync(wt, cvec, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsv(ctx, true, M, Bm, M, wt));                              // wt = Lambda^-1 a
+  CU(cudaMemcpyAsync(wvec, wt, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsv(ctx, true, M, Lu, M, wvec));                            // w = L_u^-T wt
+  if (h) {
+    CU(cudaMemcpyAsync(hA, h, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CHK(dla_trsv(ctx, false, M, Lu, M, hA, ip));                       // hA = L_u^-1 h / sigma^2
+  }
+  CHK(dla_trtri(ctx, M, Bm, M, Q, M));                                                                          // L_Lambda^-1 (scratch)
+  CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, Q, M, Q, M, 0.0, Li2, M, DLA_A_UPPER | DLA_B_LOWER));            // Lambda^-1
+  LAUNCH(ctx, whitened_q_kernel, (int)((MM + 255) / 256), 256, 0, Li2, wt, M, Q);
+  CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, V, M, V, M, 0.0, W, M, DLA_A_LOWER | DLA_B_UPPER));              // W = V V'
+  CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, X, M, 0.0, T1, M, DLA_A_LOWER));                          // V (l dKuu/dl)
+  CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, T1, M, V, M, 0.0, X, M, DLA_B_UPPER));                           // X
+  const int trace_blocks = (int)std::min<size_t>((MM + 255) / 256, (size_t)ctx->num_sms * 4);
+  CU(ctx->scal.reserve((size_t)trace_blocks * NTR * sizeof(double)));
+  LAUNCH(ctx, whitened_trace_kernel, trace_blocks, 256, 0, M, Q, W, X, Li2, Hw, GA, wt, h ? hA : (const double*)nullptr, ctx->scal.as<double>());
+  LAUNCH(ctx, trace_final_kernel, 1, 32, 0, ctx->scal.as<double>(), trace_blocks, sc + 8);
+  // the operand of S = A'(Lambda^-1 L_u^-1): out_n = C in_n with C = V' Lambda^-1 (panel_gemm.cu's orientation)
+  if (out) CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, V, M, Li2, M, 0.0, T1, M, DLA_A_UPPER));
+  double hs[8 + NTR]; int hinfo[2];
+  CU(cudaMemcpyAsync(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hinfo, dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
+  const double trB = hs[0], logdetL = hs[1], cc = hs[2];
+  const double* t = hs + 8;
+  double v = -0.5 * ((double)N * LOG2PI + (double)N * log(p.noise) + logdetL + yy * ip - cc);
+  if (vfe) v += -0.5 * ((double)N * p.s * ip - trB);
+  *val = v;
+  if (out) { out->Cop = T1; out->wt = wt; out->w = wvec; out->trQ = t[0]; out->WQ = t[1]; out->XQ = t[2]; out->cc = cc; }
+  if (grad) {
+    double dlogl = -ip * t[3] + t[5] - ip * t[4] - 0.5 * t[2];
+    double ds = 0.5 * (t[0] + jitter * t[1]) / p.s;
+    double dn = 0.5 * ip * (-(double)N - t[0] + yy * ip - cc);
+    if (jit_is_noise) dn += -0.5 * t[1];
+    if (vfe) {
+      dlogl += 0.5 * (2.0 * ip * t[6] - t[7]);
+      ds += -0.5 * (double)N * ip + 0.5 * (trB + jitter * t[8]) / p.s;
+      dn += 0.5 * (double)N * p.s * ip * ip - 0.5 * trB * ip;
+      if (jit_is_noise) dn += -0.5 * t[8];
     }
     grad[0] = dlogl * p.dl / p.l;
     grad[1] = ds * p.ds_dv;

@@ -39,6 +39,7 @@ struct gpar_group {
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool loopback = false;                // testing: members share ONE device, collectives are device copies / sums (no NCCL)
   std::string err;
 };
 
@@ -71,6 +72,42 @@ int load_nccl(gpar_group* g) {
   return GPAR_OK;
 }
 
+__global__ void add_into_kernel(double* __restrict__ acc, const double* __restrict__ x, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += x[i];
+}
+// The data-path collectives.  With NCCL: one grouped call over the members' streams.  Loopback groups (all members on one
+// device — the 1-GPU test mode of the sharded entry points) do the same data movement with device copies.
+int group_allgather(gpar_group* g, const std::vector<const double*>& send, const std::vector<double*>& recv, size_t count) {
+  const int n = (int)g->ctx.size();
+  if (!g->loopback) {
+    GNC(g->GroupStart());
+    for (int i = 0; i < n; i++) GNC(g->AllGather(send[i], recv[i], count, ncclDouble, g->comm[i], g->ctx[i]->stream));
+    GNC(g->GroupEnd());
+    return GPAR_OK;
+  }
+  for (int i = 0; i < n; i++) GCU(cudaStreamSynchronize(g->ctx[i]->stream));
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) GCU(cudaMemcpyAsync(recv[i] + (size_t)j * count, send[j], count * sizeof(double), cudaMemcpyDeviceToDevice, g->ctx[i]->stream));
+  return GPAR_OK;
+}
+int group_allreduce_sum(gpar_group* g, const std::vector<double*>& buf, size_t count) {
+  const int n = (int)g->ctx.size();
+  if (!g->loopback) {
+    GNC(g->GroupStart());
+    for (int i = 0; i < n; i++) GNC(g->AllReduce(buf[i], buf[i], count, ncclDouble, ncclSum, g->comm[i], g->ctx[i]->stream));
+    GNC(g->GroupEnd());
+    return GPAR_OK;
+  }
+  for (int i = 0; i < n; i++) GCU(cudaStreamSynchronize(g->ctx[i]->stream));
+  cudaStream_t s0 = g->ctx[0]->stream;
+  for (int j = 1; j < n; j++) add_into_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s0>>>(buf[0], buf[j], count);
+  GCU(cudaGetLastError());
+  GCU(cudaStreamSynchronize(s0));
+  for (int j = 1; j < n; j++) GCU(cudaMemcpyAsync(buf[j], buf[0], count * sizeof(double), cudaMemcpyDeviceToDevice, g->ctx[j]->stream));
+  return GPAR_OK;
+}
+
 // rows: per member `width` doubles (host, member-major).  Every device ends up with the ndev x width table
 // (g->recv[i]); `table` (host, nullable) receives member 0's copy.
 int allgather_rows(gpar_group* g, const double* rows, int width, double* table) {
@@ -81,9 +118,12 @@ int allgather_rows(gpar_group* g, const double* rows, int width, double* table) 
     GCU(g->recv[i].reserve((size_t)width * n * sizeof(double)));
     GCU(cudaMemcpyAsync(g->send[i].p, rows + (size_t)i * width, (size_t)width * sizeof(double), cudaMemcpyHostToDevice, g->ctx[i]->stream));
   }
-  GNC(g->GroupStart());
-  for (int i = 0; i < n; i++) GNC(g->AllGather(g->send[i].p, g->recv[i].p, (size_t)width, ncclDouble, g->comm[i], g->ctx[i]->stream));
-  GNC(g->GroupEnd());
+  {
+    std::vector<const double*> sp(n); std::vector<double*> rp(n);
+    for (int i = 0; i < n; i++) { sp[i] = g->send[i].as<double>(); rp[i] = g->recv[i].as<double>(); }
+    const int rc = group_allgather(g, sp, rp, (size_t)width);
+    if (rc != GPAR_OK) return rc;
+  }
   for (int i = 0; i < n; i++) {
     GCU(cudaSetDevice(g->dev[i]));
     if (i == 0 && table) GCU(cudaMemcpyAsync(table, g->recv[0].p, (size_t)width * n * sizeof(double), cudaMemcpyDeviceToHost, g->ctx[0]->stream));
@@ -142,15 +182,22 @@ int gpar_group_create(const int32_t* devices, int32_t ndev, gpar_group** out) {
   if (!devices || ndev < 1) return GPAR_ERR_INVALID;
   gpar_group* g = new gpar_group();
   auto bail = [&](int code) { for (gpar_ctx* c : g->ctx) gpar_ctx_destroy(c); if (g->lib) dlclose(g->lib); delete g; return code; };
+  // GPAR_GROUP_LOOPBACK=1 (testing): several members on ONE device, collectives as device copies — the sharded entry
+  // points then run their slice logic on a 1-GPU box; otherwise one member per device
+  bool same = ndev > 1;
+  for (int i = 1; i < ndev; i++) same = same && devices[i] == devices[0];
+  if (same) { const char* e = getenv("GPAR_GROUP_LOOPBACK"); g->loopback = e && atoi(e) != 0; }
   for (int i = 0; i < ndev; i++) {
-    for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return bail(GPAR_ERR_INVALID);      // one member per device
+    for (int j = 0; j < i; j++) if (devices[j] == devices[i] && !g->loopback) return bail(GPAR_ERR_INVALID);
     gpar_ctx* c = nullptr;
     int rc = gpar_ctx_create(devices[i], &c);
     if (rc != GPAR_OK) return bail(rc);
     g->ctx.push_back(c); g->dev.push_back(devices[i]);
   }
+  g->send.resize(ndev); g->recv.resize(ndev);
+  if (g->loopback) { *out = g; return GPAR_OK; }
   if (load_nccl(g) != GPAR_OK) { fprintf(stderr, "%s\n", g->err.c_str()); return bail(GPAR_ERR_CUDA); }
-  g->comm.resize(ndev); g->send.resize(ndev); g->recv.resize(ndev);
+  g->comm.resize(ndev);
   ncclResult_t r = g->CommInitAll(g->comm.data(), ndev, g->dev.data());
   if (r != ncclSuccess) { fprintf(stderr, "gpar_group_create: ncclCommInitAll failed: %s\n", g->GetErrorString(r)); g->comm.clear(); return bail(GPAR_ERR_CUDA); }
   *out = g;
@@ -229,9 +276,8 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
   run_members(g, st, [&](int i) { return dtc_slice_stats(g->ctx[i], kernel, p, want_grad, &stats[i], &count[i]); });
   for (int i = 0; i < n; i++)
     if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
-  GNC(g->GroupStart());
-  for (int i = 0; i < n; i++) GNC(g->AllReduce(stats[i], stats[i], count[i], ncclDouble, ncclSum, g->comm[i], g->ctx[i]->stream));
-  GNC(g->GroupEnd());
+  rc = group_allreduce_sum(g, stats, count[0]);
+  if (rc != GPAR_OK) return rc;
   GCU(cudaSetDevice(g->dev[0]));
   const int M = (int)c0->M, Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
   const size_t MM = (size_t)M * M;
@@ -241,6 +287,52 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
   for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
   GCU(cudaSetDevice(g->dev[0]));
   rc = dtc_tail(c0, kernel, p, vfe, jitter, Ntot, G, H, gh, gh + Mpad, yy, val, grad, nullptr, false);
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  return GPAR_OK;
+}
+
+// ONE scaled-GPAR objective (gpar_scaled_dtc; dtc.jl:83-128) whose rows are sharded over the members: member i
+// holds the FULL (t, y) — 16 bytes per step, the 1 x N filter is cheap and every member runs it — the same pseudo-inputs, and
+// rows [row_lo[i], row_lo[i] + N_i) of the inputs X (consecutive slices, first rows multiples of 4).  The N x M work (kernel
+// panel, whitening passes, SYRK) is sliced; the filter carry of the M whitened columns crosses the slice boundaries through
+// ONE all-gather of the slice summaries (D x D transition product + D x M exit state each), and ONE all-reduce sums
+// (G, g) before member 0 runs the M x M tail: 8 (M^2 + M + n (D^2 + D M)) bytes per evaluation on NVLink.
+int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!theta || !row_lo || !val) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: theta, row_lo and val must not be NULL");
+  const int n = (int)g->ctx.size();
+  gpar_ctx* c0 = g->ctx[0];
+  int64_t expect = 0;
+  for (int i = 0; i < n; i++) {
+    gpar_ctx* c = g->ctx[i];
+    if (c->M != c0->M || c->Dz != c0->Dz || c->Nt != c0->Nt)
+      return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: member %d holds %lld pseudo-inputs (dimension %d) and %lld times, member 0 %lld (%d) and %lld",
+                        i, (long long)c->M, c->Dz, (long long)c->Nt, (long long)c0->M, c0->Dz, (long long)c0->Nt);
+    if (row_lo[i] != expect) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: member %d starts at row %lld, the slices before it end at %lld", i, (long long)row_lo[i], (long long)expect);
+    expect += c->N;
+  }
+  if (expect != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: the slices cover %lld rows, the sequence has %lld", (long long)expect, (long long)c0->Nt);
+  std::vector<int> st;
+  run_members(g, st, [&](int i) { return scaled_slice_phase1(g->ctx[i], k_time, k_out, theta, row_lo[i]); });
+  for (int i = 0; i < n; i++)
+    if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  const size_t sc = c0->slice.summary_count;
+  std::vector<const double*> sp(n); std::vector<double*> rp(n), stats(n);
+  for (int i = 0; i < n; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    GCU(g->recv[i].reserve(sc * n * sizeof(double)));
+    sp[i] = g->ctx[i]->slice.summary; rp[i] = g->recv[i].as<double>(); stats[i] = g->ctx[i]->slice.G;
+  }
+  int rc = group_allgather(g, sp, rp, sc);
+  if (rc != GPAR_OK) return rc;
+  run_members(g, st, [&](int i) { return scaled_slice_phase2(g->ctx[i], rp[i], i); });
+  for (int i = 0; i < n; i++)
+    if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  rc = group_allreduce_sum(g, stats, c0->slice.stats_count);
+  if (rc != GPAR_OK) return rc;
+  for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
+  GCU(cudaSetDevice(g->dev[0]));
+  rc = scaled_slice_finish(c0, val);
   if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
   return GPAR_OK;
 }
@@ -268,9 +360,15 @@ int gpar_group_broadcast(gpar_group* g, int32_t src, const double* host, int64_t
   if (host) GCU(cudaMemcpyAsync(sc->chain.p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, sc->stream));
   else if (merged) { const int rc = merged_gather_test(sc, sc->chain.as<double>(), nullptr); if (rc != GPAR_OK) return group_fail(g, rc, "member %d: %s", src, gpar_last_error(sc)); }
   else GCU(cudaMemcpyAsync(sc->chain.p, sc->res_a, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, sc->stream));
-  GNC(g->GroupStart());
-  for (int i = 0; i < nm; i++) GNC(g->Broadcast(g->ctx[i]->chain.p, g->ctx[i]->chain.p, (size_t)n, ncclDouble, src, g->comm[i], g->ctx[i]->stream));
-  GNC(g->GroupEnd());
+  if (g->loopback) {
+    GCU(cudaStreamSynchronize(sc->stream));
+    for (int i = 0; i < nm; i++)
+      if (i != src) GCU(cudaMemcpyAsync(g->ctx[i]->chain.p, sc->chain.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, g->ctx[i]->stream));
+  } else {
+    GNC(g->GroupStart());
+    for (int i = 0; i < nm; i++) GNC(g->Broadcast(g->ctx[i]->chain.p, g->ctx[i]->chain.p, (size_t)n, ncclDouble, src, g->comm[i], g->ctx[i]->stream));
+    GNC(g->GroupEnd());
+  }
   for (int i = 0; i < nm; i++) {
     GCU(cudaSetDevice(g->dev[i]));
     if (out && i == (src + 1) % nm) GCU(cudaMemcpyAsync(out, g->ctx[i]->chain.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g->ctx[i]->stream));   // a RECEIVER's copy

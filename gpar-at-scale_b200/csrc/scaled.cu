@@ -200,13 +200,13 @@ chunk_transition_kernel(const double* __restrict__ table, int64_t N, double* __r
 // 8 chunks are issued ahead of the dependent arithmetic.
 template <int D>
 __global__ void __launch_bounds__(32)
-carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Mpad) {
+carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int nch, int Mpad, const double* __restrict__ init) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mpad) return;
   constexpr int PF = 8;
-  double st[D];
+  double st[D];       // init (nullable, D x Mpad): the state entering the first chunk — a row slice that is not the head of the sequence
 #pragma unroll
-  for (int i = 0; i < D; i++) st[i] = 0.0;
+  for (int i = 0; i < D; i++) st[i] = init ? init[(int64_t)i * Mpad + m] : 0.0;
   for (int c0 = 0; c0 < nch; c0 += PF) {
     double b[PF][D], ps[PF][D * D];
 #pragma unroll
@@ -234,6 +234,71 @@ carry_scan_kernel(const double* __restrict__ psi, double* __restrict__ resp, int
       }
     }
   }
+}
+
+// ---- row slices of one sequence on several devices (gpar_group_scaled_dtc_sharded) ---------------
+// The whitening recurrence is affine in the state, x_{c+1} = Psi_c x_c + b_c, so a slice is summarised by the product of its
+// chunk transitions and its exit state from a ZERO entering state: summary = [Psi^(g) (D x D) | r^(g) (D x Mpad)].
+template <int D>
+__global__ void __launch_bounds__(32)
+slice_summary_kernel(const double* __restrict__ psi, const double* __restrict__ resp, int nch, int Mpad, double* __restrict__ summary) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < Mpad) {
+    double st[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) st[i] = 0.0;
+    for (int c = 0; c < nch; c++) {
+      double nx[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = resp[((int64_t)c * D + i) * Mpad + m];
+#pragma unroll
+        for (int q = 0; q < D; q++) a = fma(__ldg(psi + (int64_t)c * D * D + i * D + q), st[q], a);
+        nx[i] = a; }
+#pragma unroll
+      for (int i = 0; i < D; i++) st[i] = nx[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) summary[D * D + (int64_t)i * Mpad + m] = st[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double P[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; i++) P[i] = (i / D == i % D) ? 1.0 : 0.0;
+    for (int c = 0; c < nch; c++) {
+      double F[D * D], R[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; i++) F[i] = psi[(int64_t)c * D * D + i];
+      matmul<D>(F, P, R);
+#pragma unroll
+      for (int i = 0; i < D * D; i++) P[i] = R[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D * D; i++) summary[i] = P[i];
+  }
+}
+// State entering slice `member` from the gathered summaries of the slices before it: x <- Psi^(h) x + r^(h), h = 0 .. member-1.
+template <int D>
+__global__ void __launch_bounds__(32)
+slice_entering_kernel(const double* __restrict__ gathered, int member, int Mpad, double* __restrict__ init) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mpad) return;
+  const int64_t stride = D * D + (int64_t)D * Mpad;
+  double st[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) st[i] = 0.0;
+  for (int h = 0; h < member; h++) {
+    const double* s = gathered + h * stride;
+    double nx[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { double a = s[D * D + (int64_t)i * Mpad + m];
+#pragma unroll
+      for (int q = 0; q < D; q++) a = fma(s[i * D + q], st[q], a);
+      nx[i] = a; }
+#pragma unroll
+    for (int i = 0; i < D; i++) st[i] = nx[i];
+  }
+#pragma unroll
+  for (int i = 0; i < D; i++) init[(int64_t)i * Mpad + m] = st[i];
 }
 
 // pass 2: in-place whitening of the panel: beta = (K - HA m) / sqrt(S); m <- Phi m + K_k K; g partials.
@@ -609,14 +674,25 @@ int launch_pass1(gpar_ctx* ctx, int k_out, dim3 grid, const double* X, const dou
 }
 
 // before_syrk (nullable): called with the whitened panel right before the SYRK is enqueued (the whitening kernels are
-// already running, so a host-side wait in it costs no device time); may transform the panel in place
-typedef std::function<int(double* panel, int64_t Npad, int Mpad)> PanelHook;
+// already running, so a host-side wait in it costs no device time); may transform the panel in place, or point the SYRK at
+// a transformed copy (the gradient in whitened coordinates keeps beta and A = L_u^-1 beta' side by side)
+typedef std::function<int(double*& panel, int64_t Npad, int Mpad)> PanelHook;
 struct ScaledStats {
   double* G; double* g; double sum_logS, sum_a2; int Mpad; int64_t Npad;
   double *table, *alpha, *beta; int nch; int whg;      // whg: 4-step groups per whitening chunk of this call
+  double* syrk_panel;                                  // what the SYRK consumed: beta, or the copy a hook redirected it to
   // gradient mode only
   double *dtable, *dalpha, *panelD, *start, *psi, *evec; double dsums[4];   // dsums: d sum log S (2), d sum alpha^2 (2)
 };
+
+static int choose_whg(gpar_ctx* ctx, int T, int64_t NB4) {
+  const int col_blocks = std::max(1, T / ((T % 2 == 0) ? 2 : 1));
+  const int64_t want_chunks = (2 * (int64_t)ctx->num_sms + col_blocks - 1) / col_blocks;
+  const int64_t g = (NB4 + want_chunks - 1) / want_chunks;
+  int whg = (int)std::min<int64_t>(WH_GROUPS_MAX, std::max<int64_t>(16, (g + 15) / 16 * 16));
+  if (const char* e = getenv("GPAR_WH_GROUPS")) { int v = atoi(e); if (v >= 16 && v <= WH_GROUPS_MAX && v % 16 == 0) whg = v; }
+  return whg;
+}
 
 // Steps 1-3 of the header comment.  Leaves G (M x M) and g (M) on the device.  grad = true additionally
 // runs the filter in forward mode (tangents w.r.t. time_l and the noise of Sigma_y), keeps the
@@ -633,14 +709,7 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   // chunk length of the whitening / tangent passes: 1024 steps for large problems; shorter (a multiple of 64 steps) when
   // 1024-step chunks would leave most SMs idle — at the reference's own sizes (N = 8 496, M = 50) nine blocks each walked
   // 1024 steps sequentially (250 us per pass)
-  int whg = WH_GROUPS_MAX;
-  {
-    const int col_blocks = std::max(1, T / ((T % 2 == 0) ? 2 : 1));
-    const int64_t want_chunks = (2 * (int64_t)ctx->num_sms + col_blocks - 1) / col_blocks;
-    const int64_t g = (NB4 + want_chunks - 1) / want_chunks;
-    whg = (int)std::min<int64_t>(WH_GROUPS_MAX, std::max<int64_t>(16, (g + 15) / 16 * 16));
-    if (const char* e = getenv("GPAR_WH_GROUPS")) { int v = atoi(e); if (v >= 16 && v <= WH_GROUPS_MAX && v % 16 == 0) whg = v; }
-  }
+  const int whg = choose_whg(ctx, T, NB4);
   const int nch = (int)((NB4 + whg - 1) / whg);
   CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
   if (grad) CU(ctx->panelD.reserve((size_t)Npad * Mpad * sizeof(double)));
@@ -675,13 +744,15 @@ int scaled_stats_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, doubl
   if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD, whg)));
   else CHK((launch_pass1<D, 1>(ctx, k_out, grid, X, Z, N, M, NB4, inv_l2, out_s, table, panel, resp, Mpad, panelD, whg)));
   LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, table, N, psi, whg);
-  LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad);
+  LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad, (const double*)nullptr);
   if (CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad, whg);
   else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, table, alpha, panel, panel, resp, gp, Mpad, whg);
   CHK(launch_reduce_gh(ctx, gp, nch, Mpad, 1, g));
-  if (before_syrk) CHK((*before_syrk)(panel, Npad, Mpad));
+  double* syrk_panel = panel;
+  if (before_syrk) CHK((*before_syrk)(syrk_panel, Npad, Mpad));
   cudaEventRecord(ctx->pev[0], ctx->stream);
-  CHK(panel_syrk_run(ctx, panel, nullptr, Npad, Mpad, M, false, G, nullptr));
+  CHK(panel_syrk_run(ctx, syrk_panel, nullptr, Npad, Mpad, M, false, G, nullptr));
+  st->syrk_panel = syrk_panel;
   ctx->phase_valid = true;
   double hs[6];
   CU(cudaMemcpyAsync(hs, sums, (grad ? 6 : 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -705,16 +776,80 @@ int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double tim
   }
 }
 
-// The tangent pass of the gradient: <R, d beta_*> (3 sums) and <e, d alpha_j> (2 sums) -> out5 (host).
+// ---- one ROW SLICE of the scaled objective (gpar_group_scaled_dtc_sharded, group.cu) ---------------
+// The context holds the FULL (t, y) (set_times / set_outputs, Nt = Ny = N_full) and rows [lo, lo + ctx->N) of the inputs.
+// Phase 1: the 1 x N_full filter (cheap: every member runs it), pass 1 over the slice, the chunk transitions, the slice
+// summary.  [all-gather of the summaries]  Phase 2: entering state, carry scan, pass 2, g partials, (L_u-whitening), SYRK.
+// [all-reduce of (G, g)]  Then the ordinary M x M tail on one member.
 template <int D>
-int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec, double* out5) {
+int scaled_slice_phase1_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, int64_t lo) {
+  constexpr int TS = D * D + 2 * D + 1;
+  gpar_ctx::SliceState& sl = ctx->slice;
+  const int64_t Nfull = ctx->Nt, N = ctx->N; const int M = (int)ctx->M;
+  const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
+  const int64_t Npad = (N + GPAR_KT - 1) / GPAR_KT * GPAR_KT, NB4 = Npad / 4;
+  const int T = Mpad / GPAR_TILE;
+  const int whg = choose_whg(ctx, T, NB4);
+  const int nch = (int)((NB4 + whg - 1) / whg);
+  CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
+  CU(ctx->kal_e.reserve(((size_t)Nfull * TS + (size_t)Nfull + 16) * sizeof(double)));
+  const size_t state_doubles = (size_t)nch * D * Mpad, sum_doubles = (size_t)D * D + (size_t)D * Mpad;
+  CU(ctx->gpart.reserve((state_doubles + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad + sum_doubles + (size_t)D * Mpad) * sizeof(double)));
+  const size_t MM = (size_t)M * M;
+  CU(ctx->kal_d.reserve((MM + Mpad) * sizeof(double)));
+  double* table = ctx->kal_e.as<double>(); double* alpha = table + (size_t)Nfull * TS; double* sums = alpha + Nfull; double* lml = sums + 8;
+  double* resp = ctx->gpart.as<double>(); double* psi = resp + state_doubles; double* gp = psi + (size_t)nch * D * D;
+  double* summary = gp + (size_t)nch * Mpad + Mpad; double* init = summary + sum_doubles;
+  const int kind_time = D == 1 ? GPAR_MATERN12 : (D == 2 ? GPAR_MATERN32 : GPAR_MATERN52);
+  CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, Nfull, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
+                alpha, lml, nullptr, nullptr, table, sums));
+  const double inv_l2 = 1.0 / (out_l * out_l);
+  const int CT = (T % 2 == 0) ? 2 : 1;
+  dim3 grid(T / CT, nch);
+  const double* tableL = table + (size_t)lo * TS;
+  double* panel = ctx->panelK.as<double>();
+  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, nullptr, whg)));
+  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, nullptr, whg)));
+  LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, tableL, N, psi, whg);
+  LAUNCH(ctx, slice_summary_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad, summary);
+  sl.D = D; sl.lo = lo; sl.Mpad = Mpad; sl.Npad = Npad; sl.nch = nch; sl.whg = whg; sl.CT = CT;
+  sl.table = tableL; sl.alpha = alpha + lo; sl.sums = sums; sl.resp = resp; sl.psi = psi; sl.gp = gp; sl.summary = summary; sl.init = init;
+  sl.G = ctx->kal_d.as<double>(); sl.g = sl.G + MM; sl.summary_count = sum_doubles; sl.stats_count = MM + Mpad;
+  return GPAR_OK;
+}
+template <int D>
+int scaled_slice_phase2_d(gpar_ctx* ctx, const double* gathered, int member, const PanelHook* before_syrk) {
+  gpar_ctx::SliceState& sl = ctx->slice;
+  const int64_t N = ctx->N, NB4 = sl.Npad / 4; const int M = (int)ctx->M, Mpad = sl.Mpad, T = Mpad / GPAR_TILE;
+  LAUNCH(ctx, slice_entering_kernel<D>, (Mpad + 31) / 32, 32, 0, gathered, member, Mpad, sl.init);
+  LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, sl.psi, sl.resp, sl.nch, Mpad, (const double*)sl.init);
+  double* panel = ctx->panelK.as<double>();
+  dim3 grid(T / sl.CT, sl.nch);
+  if (sl.CT == 2) LAUNCH(ctx, (whiten_pass2_kernel<D, 2>), grid, GPAR_TILE, 0, N, NB4, sl.table, sl.alpha, panel, panel, sl.resp, sl.gp, Mpad, sl.whg);
+  else LAUNCH(ctx, (whiten_pass2_kernel<D, 1>), grid, GPAR_TILE, 0, N, NB4, sl.table, sl.alpha, panel, panel, sl.resp, sl.gp, Mpad, sl.whg);
+  CHK(launch_reduce_gh(ctx, sl.gp, sl.nch, Mpad, 1, sl.g));
+  double* syrk_panel = panel;
+  if (before_syrk) CHK((*before_syrk)(syrk_panel, sl.Npad, Mpad));
+  CHK(panel_syrk_run(ctx, syrk_panel, nullptr, sl.Npad, Mpad, M, false, sl.G, nullptr));
+  return GPAR_OK;
+}
+
+// The tangent pass of the gradient: <R, d beta_*> (3 sums) and <e, d alpha_j> (2 sums) -> out5 (host).
+// Pm: the M x M matrix C of S_n = C in_n (dense, column-major; the symmetric P = (cov(u) + G)^-1 with in = beta, or
+// L_u^-T Lambda^-1 with in = the whitened panel A — the same S, formed without cond(cov(u))-sized cancellation);
+// the residual e = alpha - res_panel res_w likewise from (beta, w) or (A, wt).
+template <int D>
+int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec, double* out5,
+                     const double* gemm_panel = nullptr, const double* res_w = nullptr) {
+  if (!gemm_panel) gemm_panel = st.beta;
+  if (!res_w) res_w = wvec;
   const int64_t N = ctx->N; const int M = (int)ctx->M;
   const int Mpad = st.Mpad, T = Mpad / GPAR_TILE, nch = st.nch;
   const int64_t NB4 = st.Npad / 4;
   const size_t state_doubles = (size_t)nch * D * Mpad;
   double* tstate = st.psi + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad;       // after gp / g partials (layout of scaled_stats_d)
   double* accpart = tstate + 3 * state_doubles;
-  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, st.beta, wvec, st.alpha, N, NB4, T, M, st.evec);
+  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, gemm_panel, res_w, st.alpha, N, NB4, T, M, st.evec);
   int CT = (T % 2 == 0) ? 2 : 1;                      // columns per thread: two halve the table reads (218 registers, 2 CTAs/SM; one: 164, 3 CTAs/SM)
   if (const char* e = getenv("GPAR_TANGENT_CT")) { if (atoi(e) == 1) CT = 1; }
   dim3 grid(T / CT, nch);
@@ -722,7 +857,7 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
                       tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
               tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
-  for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad);
+  for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad, (const double*)nullptr);
   // S = beta P slab by slab on the DMMA panel-GEMM (panel_gemm.cu): P goes once into the operand layout, every slab of S
   // comes out in the panel layout and is consumed at once by the final tangent pass, so only one slab buffer exists
   const int base_chunks = std::max(1, 131072 / (st.whg * 4));
@@ -742,7 +877,7 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   for (int c0 = 0; c0 < nch; c0 += slab_chunks) {
     const int nc = std::min(slab_chunks, nch - c0);
     const int64_t g_lo = (int64_t)c0 * st.whg, ng = std::min<int64_t>((int64_t)nc * st.whg, NB4 - g_lo);
-    CHK(panel_gemm_run(ctx, Pop, Mpad, st.beta, NB4, Ss, slab_groups, g_lo, ng, g_lo, 0, T, false));
+    CHK(panel_gemm_run(ctx, Pop, Mpad, gemm_panel, NB4, Ss, slab_groups, g_lo, ng, g_lo, 0, T, false));
     dim3 gs(T / CT, nc);
     if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, true>), gs, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
                         tstate, nch, c0, Ss, slab_groups, st.evec, wvec, accpart, Mpad, M, st.whg);
@@ -865,7 +1000,7 @@ static int factor_cov_u_side(gpar_ctx* ctx, int k_out, double out_l, double out_
 }
 // The hook of scaled_stats: wait for L_u, decide on the conditioning, whiten the panel by L_u when it is poor.
 static PanelHook make_whitening_hook(gpar_ctx* ctx, const double* Lu, const double* minmax_dev, bool* robust) {
-  return [ctx, Lu, minmax_dev, robust](double* panel, int64_t Npad, int Mpad) -> int {
+  return [ctx, Lu, minmax_dev, robust](double*& panel, int64_t Npad, int Mpad) -> int {
     double mm[2] = {1.0, 1.0};
     CU(cudaMemcpyAsync(mm, minmax_dev, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
     CU(cudaStreamSynchronize(ctx->stream2));             // the whitening kernels are already running on the main stream
@@ -874,6 +1009,88 @@ static PanelHook make_whitening_hook(gpar_ctx* ctx, const double* Lu, const doub
     if (*robust) CHK(panel_left_solve(ctx, panel, Npad, Mpad, (int)ctx->M, Lu));
     return GPAR_OK;
   };
+}
+
+// The M x M tail of the value: Lambda = I + A A' (from the collapsed statistic, B = V G V', or directly from the SYRK of the
+// L_u-whitened panel), its factor, log-determinant (sc[0]) and c'c (sc[1]) with c = L_Lambda^-1 L_u^-1 g.  Enqueued only.
+static int scaled_value_tail(gpar_ctx* ctx, const double* Lu, double* Bm, const double* V, double* Tm, double* cvec, double* sc, int* dinfo,
+                             const double* G, const double* g, bool robust) {
+  const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
+  if (!robust) {      // collapsed statistic: B = L_u^-1 (beta'beta) L_u^-T = V G V';  whitened panel: G is already A A'
+    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, G, M, 0.0, Tm, M, DLA_A_LOWER));
+    CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, Tm, M, V, M, 0.0, Bm, M, DLA_B_UPPER | DLA_LOWER_TILES));
+  } else {
+    CU(cudaMemcpyAsync(Bm, G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Bm, M);
+  CHK(dla_potrf(ctx, M, Bm, M, dinfo + 1));
+  LAUNCH(ctx, logdet2_kernel, 1, 256, 0, Bm, M, sc);
+  // c = L_Lambda^-1 (A alpha), A alpha = L_u^-1 g with g = beta'alpha (accumulated by the whitening pass, before the hook)
+  CU(cudaMemcpyAsync(cvec, g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsv(ctx, false, M, Lu, M, cvec));
+  CHK(dla_trsv(ctx, false, M, Bm, M, cvec));
+  CHK(dla_dot(ctx, M, cvec, cvec, sc + 1));
+  return GPAR_OK;
+}
+
+// ---- row-sliced evaluation: the three steps group.cu drives around its two collectives --------------------------------
+struct SliceTailBufs { double *Lu, *Bm, *V, *Tm, *cvec, *sc; int* dinfo; };
+static int slice_tail_bufs(gpar_ctx* ctx, SliceTailBufs* b) {
+  const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
+  CU(ctx->dense.reserve((4 * MM + 2 * (size_t)M + 16) * sizeof(double)));
+  b->Lu = ctx->dense.as<double>(); b->Bm = b->Lu + MM; b->V = b->Bm + MM; b->Tm = b->V + MM; b->cvec = b->Tm + MM; b->sc = b->cvec + 2 * M;
+  CU(ctx->info.reserve(4 * sizeof(int)));
+  b->dinfo = ctx->info.as<int>();
+  return GPAR_OK;
+}
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo) {
+  CU(cudaSetDevice(ctx->device));
+  gpar_drop_result(ctx);
+  if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: inputs (this member's rows) and pseudo-inputs must be set, same dimension");
+  if (ctx->Nt != ctx->Ny || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: every member holds the FULL times and outputs (%lld times, %lld outputs)", (long long)ctx->Nt, (long long)ctx->Ny);
+  if (lo < 0 || lo % 4 != 0 || lo + ctx->N > ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: rows [%lld, %lld) of %lld: the first row of a slice must be a multiple of 4", (long long)lo, (long long)(lo + ctx->N), (long long)ctx->Nt);
+  double pv[5];
+  for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;      // unpack_gpar (util.jl:45-55)
+  const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
+  SliceTailBufs b;
+  CHK(slice_tail_bufs(ctx, &b));
+  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, b.Lu, b.V, b.dinfo, b.sc + 4));
+  ctx->slice.robust = false;
+  switch (k_time) {
+    case GPAR_MATERN12: return scaled_slice_phase1_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
+    case GPAR_MATERN32: return scaled_slice_phase1_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
+    case GPAR_MATERN52: return scaled_slice_phase1_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
+    default: return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
+  }
+}
+int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member) {
+  CU(cudaSetDevice(ctx->device));
+  SliceTailBufs b;
+  CHK(slice_tail_bufs(ctx, &b));
+  // the conditioning decision is a function of L_u alone, which every member computes identically
+  PanelHook hook = make_whitening_hook(ctx, b.Lu, b.sc + 4, &ctx->slice.robust);
+  switch (ctx->slice.D) {
+    case 1: return scaled_slice_phase2_d<1>(ctx, gathered, member, &hook);
+    case 2: return scaled_slice_phase2_d<2>(ctx, gathered, member, &hook);
+    default: return scaled_slice_phase2_d<3>(ctx, gathered, member, &hook);
+  }
+}
+// on the member that holds the all-reduced (G, g)
+int scaled_slice_finish(gpar_ctx* ctx, double* dtc) {
+  CU(cudaSetDevice(ctx->device));
+  SliceTailBufs b;
+  CHK(slice_tail_bufs(ctx, &b));
+  const gpar_ctx::SliceState& sl = ctx->slice;
+  CHK(scaled_value_tail(ctx, b.Lu, b.Bm, b.V, b.Tm, b.cvec, b.sc, b.dinfo, sl.G, sl.g, sl.robust));
+  double hs[2], fs[2]; int hinfo[2];
+  CU(cudaMemcpyAsync(hs, b.sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(fs, sl.sums, sizeof(fs), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hinfo, b.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
+  *dtc = -0.5 * ((double)ctx->Nt * LOG2PI_S + fs[0] + hs[0] + fs[1] - hs[1]);      // dtc.jl:122-125
+  return GPAR_OK;
 }
 
 extern "C" {
@@ -912,20 +1129,7 @@ int gpar_scaled_dtc(gpar_ctx* ctx, int k_time, int k_out, const double theta[5],
   PanelHook hook = make_whitening_hook(ctx, Lu, sc + 4, &robust);
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, false, &hook));
-  if (!robust) {      // collapsed statistic: B = L_u^-1 (beta'beta) L_u^-T = V G V';  whitened panel: G is already A A'
-    CHK(dla_gemm(ctx, false, false, M, M, M, 1.0, V, M, st.G, M, 0.0, Tm, M, DLA_A_LOWER));
-    CHK(dla_gemm(ctx, false, true, M, M, M, 1.0, Tm, M, V, M, 0.0, Bm, M, DLA_B_UPPER | DLA_LOWER_TILES));
-  } else {
-    CU(cudaMemcpyAsync(Bm, st.G, MM * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  LAUNCH(ctx, trace_add_identity2_kernel, 1, 256, 0, Bm, M);
-  CHK(dla_potrf(ctx, M, Bm, M, dinfo + 1));
-  LAUNCH(ctx, logdet2_kernel, 1, 256, 0, Bm, M, sc);
-  // c = L_Lambda^-1 (A alpha), A alpha = L_u^-1 g with g = beta'alpha (accumulated by the whitening pass, before the hook)
-  CU(cudaMemcpyAsync(cvec, st.g, M * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CHK(dla_trsv(ctx, false, M, Lu, M, cvec));
-  CHK(dla_trsv(ctx, false, M, Bm, M, cvec));
-  CHK(dla_dot(ctx, M, cvec, cvec, sc + 1));
+  CHK(scaled_value_tail(ctx, Lu, Bm, V, Tm, cvec, sc, dinfo, st.G, st.g, robust));
   if (A_or_null) {   // A = chol(cov(u)).U' \ beta'  (dtc.jl:119), M x N column-major — small problems only
     CU(ctx->kal_b.reserve((size_t)N * M * sizeof(double)));
     double* Bt = ctx->kal_b.as<double>();
@@ -1050,6 +1254,7 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
   GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
   // fork: cov(u) = Kuu + noise I, L_u, L_u^-1, cov(u)^-1 on the side stream, underneath the filter / whitening / SYRK
   CHK(dtc_tail_prepare(ctx, k_out, p, 0, noise, true));
+  bool whitened = false;
   {
     // cov(u) too poorly conditioned for the collapsed statistic and the explicit P = (cov(u) + G)^-1 of the analytic
     // gradient (error ~ cond * eps; Lambda may not even factor): value and gradient from the whitened-panel value path
@@ -1059,12 +1264,56 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
     double mm[2] = {1.0, 1.0};
     CU(cudaMemcpyAsync(mm, tb0.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
     CU(cudaStreamSynchronize(ctx->stream2));
-    bool fd = gpar_needs_whitened_panel(mm);
-    if (const char* e = getenv("GPAR_GRAD_FD")) fd = atoi(e) != 0;      // testing knob: 1 forces, 0 forbids the fallback
+    const bool ill = gpar_needs_whitened_panel(mm);
+    bool fd = false;                                                    // testing knobs: GPAR_GRAD_FD=1 forces the stencil on the
+    if (const char* e = getenv("GPAR_GRAD_FD")) { fd = atoi(e) != 0; whitened = false; }      // value path, 0 the collapsed analytic form;
+    else whitened = ill;
+    if (const char* e = getenv("GPAR_GRAD_WHITENED")) { if (atoi(e) != 0) { whitened = true; fd = false; } }   // 1 forces the whitened form
     if (fd) {
       CHK(gpar_scaled_dtc(ctx, k_time, k_out, theta, dtc, nullptr));
       return gpar_fd_gradient([&](const double* th, double* v) { return gpar_scaled_dtc(ctx, k_time, k_out, th, v, nullptr); }, theta, 5, grad);
     }
+  }
+  if (whitened) {
+    // Gradient in whitened coordinates: A = L_u^-1 beta' next to beta (one more N x M panel), the SYRK on A,
+    // the tail conditioned like Lambda, S = A'(Lambda^-1 L_u^-1) on the whitened panel; the tangent kernels generate
+    // d beta from the un-whitened beta as before.
+    TailBufs tb;
+    CHK(tail_layout(ctx, true, 0, &tb));
+    const double* Lu = tb.Lu;
+    PanelHook hook = [ctx, Lu](double*& panel, int64_t Npad, int Mpad) -> int {
+      CU(ctx->panelA.reserve((size_t)Npad * Mpad * sizeof(double)));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+      CU(cudaMemcpyAsync(ctx->panelA.p, panel, (size_t)Npad * Mpad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      CHK(panel_left_solve(ctx, ctx->panelA.as<double>(), Npad, Mpad, (int)ctx->M, Lu));
+      panel = ctx->panelA.as<double>();
+      return GPAR_OK;
+    };
+    ScaledStats st;
+    CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, true, &hook));
+    double val = 0.0; WhitenedTail wt;
+    CHK(dtc_tail_whitened(ctx, p, 0, noise, N, st.G, nullptr, st.g, nullptr, st.sum_a2, &val, nullptr, &wt));
+    double s5[5];
+    switch (k_time) {
+      case GPAR_MATERN12: CHK(scaled_tangent_d<1>(ctx, st, wt.Cop, wt.w, s5, st.syrk_panel, wt.wt)); break;
+      case GPAR_MATERN32: CHK(scaled_tangent_d<2>(ctx, st, wt.Cop, wt.w, s5, st.syrk_panel, wt.wt)); break;
+      default: CHK(scaled_tangent_d<3>(ctx, st, wt.Cop, wt.w, s5, st.syrk_panel, wt.wt)); break;
+    }
+    timer.stop();
+    *dtc = val - 0.5 * st.sum_logS;
+    // d cov(u) = (cov(u) - noise I) d out_s / out_s + l dKuu/dl d log l + I d noise, each contracted as -1/2 <L_u^-1 . L_u^-T, Q>;
+    // <R, beta> = tr Q for the out_s scale of beta
+    const double F_os = 0.5 * (wt.trQ + noise * wt.WQ) / out_s;
+    const double F_logl = s5[2] - 0.5 * wt.XQ;
+    const double F_tl = s5[0] - s5[3] - 0.5 * st.dsums[0];
+    const double F_noise = (s5[1] - s5[4] - 0.5 * st.dsums[1]) - 0.5 * wt.WQ;
+    const double F_ts = (-0.5 * ((double)N - (st.sum_a2 - wt.cc)) - out_s * F_os - noise * F_noise) / time_s;
+    grad[0] = F_tl * ex[0];
+    grad[1] = F_ts * 2.0 * pv[1] * ex[1];
+    grad[2] = F_logl / out_l * ex[2];
+    grad[3] = F_os * 2.0 * pv[3] * ex[3];
+    grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+    return GPAR_OK;
   }
   ScaledStats st;
   CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, true));

@@ -222,6 +222,17 @@ int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* th
  * runs the M x M tail.  The only data-path collective of the library. */
 int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad);
 
+/* ONE scaled-GPAR objective (gpar_scaled_dtc; compute_gpar_dtc_objective, src/gp/dtc.jl:83-128) whose ROWS are sharded
+ * over the members: member i holds the FULL times and outputs (gpar_set_times / gpar_set_outputs, N_full each — 16 bytes
+ * per step; the 1 x N filter of dtc.jl:106 is cheap and every member runs it), the same pseudo-inputs, and rows
+ * [row_lo[i], row_lo[i] + N_i) of the inputs (gpar_set_inputs with that slice; consecutive slices covering N_full, every
+ * row_lo[i] a multiple of 4).  The N x M work — kernel panel, the M whitening passes of dtc.jl:110-117, A A' of :120 — is
+ * sliced; the filter carry of the M columns crosses the slice boundaries in ONE all-gather of slice summaries
+ * (D x D transition product + D x M exit state per member), and ONE all-reduce sums (beta'beta, beta'alpha) before member 0
+ * runs the M x M tail.  A poorly conditioned cov(u) is handled as on one device (every member whitens its panel by L_u).
+ * GPAR_GROUP_LOOPBACK=1 lets gpar_group_create put several members on ONE device (collectives become device copies). */
+int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val);
+
 /* One conditional-GP fit of the chain: inputs X (D x N ColVecs = the observed earlier outputs; D = 0: a time-only
  * state-space GP with 3 parameters, temporal_gp_inference.jl:69-82), pseudo-inputs Z (D x M), outputs y (N),
  * start point theta0 (the first 3 or 5 entries are used). */

@@ -2,6 +2,7 @@
 must reproduce the single-context entry points bit for bit; with two devices (skipped on a one-GPU box) the
 members work on different data concurrently and the NCCL-gathered tables must equal the per-context results."""
 import ctypes
+import os
 import numpy as np
 import pytest
 import oracle
@@ -175,6 +176,90 @@ def test_group_sharded_dtc_two_devices(ctx):
         g.members[1].set_pseudo(Z[:100])
         with pytest.raises(gp.GparError, match="pseudo-inputs"):
             g.dtc_logpdf_sharded(gp.MATERN52, th)
+    finally:
+        g.close()
+
+
+def _loopback_group(n):
+    import gpar_at_scale_b200 as gp
+    os.environ["GPAR_GROUP_LOOPBACK"] = "1"
+    try:
+        return gp.Group([0] * n)
+    finally:
+        del os.environ["GPAR_GROUP_LOOPBACK"]
+
+
+@pytest.mark.parametrize("nmem", [1, 2, 3, 5])
+def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
+    """gpar_group_scaled_dtc_sharded on a loopback group (several members on device 0, collectives as device copies): the
+    slice logic — filter on the full (t, y), per-slice pass 1 / transitions, slice summaries, entering states, pass 2, SYRK,
+    summed (G, g), tail — reproduces the one-device objective to 1e-11 for uneven slices (including one shorter than a
+    whitening chunk), all three time kernels and a multi-tile M; a poorly conditioned cov(u) takes the whitened-panel
+    path on every member; the sharded plain DTC goes through the same loopback collectives."""
+    import gpar_at_scale_b200 as gp
+    rng = np.random.default_rng(40 + nmem)
+    g = _loopback_group(nmem)
+    try:
+        for n, m, d, kt, ko in ((9001, 130, 2, 3, 3), (5003, 40, 1, 2, 0), (3001, 17, 3, 1, 2)):
+            t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+            th = rng.uniform(-1.0, 0.3, 5)
+            ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+            v0 = ctx.scaled_dtc(kt, ko, th)
+            cuts = sorted(int(c) * 4 for c in rng.choice(np.arange(1, n // 4), size=nmem - 1, replace=False))
+            if nmem == 3:
+                cuts[1] = cuts[0] + 8                        # a slice far shorter than a whitening chunk
+            bounds = [0] + cuts + [n]
+            lo = g.load_row_slices(X, Z, t, y, bounds)
+            v = g.scaled_dtc_sharded(kt, ko, th, lo)
+            assert abs(v - v0) <= 1e-11 * abs(v0), (nmem, n, m, bounds, v, v0)
+        # default (equal) slices and the error behaviour
+        n, m = 20000, 64
+        t = np.arange(n) / 30.0; X = rng.normal(size=(n, 2)); Z = rng.normal(size=(m, 2)); y = rng.normal(size=n)
+        th = np.array([0.2, 0.1, -0.3, 0.2, -1.0])
+        ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+        lo = g.load_row_slices(X, Z, t, y)
+        assert abs(g.scaled_dtc_sharded(3, 3, th, lo) - ctx.scaled_dtc(3, 3, th)) <= 1e-11 * abs(ctx.scaled_dtc(3, 3, th))
+        # poorly conditioned cov(u) (large output variance): the whitened-panel path on every slice
+        thi = np.array([0.2, 0.1, 1.5, 7.0, -1.0])
+        vi0 = ctx.scaled_dtc(3, 3, thi)
+        assert abs(g.scaled_dtc_sharded(3, 3, thi, lo) - vi0) <= 1e-9 * abs(vi0)
+        if nmem > 1:
+            bad = lo.copy(); bad[1] += 4
+            with pytest.raises(gp.GparError, match="starts at row"):
+                g.scaled_dtc_sharded(3, 3, th, bad)
+            g.members[1].set_pseudo(Z[:50])
+            with pytest.raises(gp.GparError, match="pseudo-inputs"):
+                g.scaled_dtc_sharded(3, 3, th, lo)
+            # plain DTC through the loopback all-reduce
+            x1 = rng.uniform(0, 10, n); z1 = np.linspace(0, 10, m); y1 = np.sin(x1) + 0.1 * rng.normal(size=n)
+            th3 = np.log([1.3, 0.9, 0.2])
+            ctx.set_inputs(x1); ctx.set_pseudo(z1); ctx.set_outputs(y1)
+            edges = np.linspace(0, n, nmem + 1).astype(int)
+            for i, mb in enumerate(g.members):
+                mb.set_inputs(x1[edges[i]:edges[i + 1]]); mb.set_pseudo(z1); mb.set_outputs(y1[edges[i]:edges[i + 1]])
+            v, gr = g.dtc_logpdf_sharded(gp.MATERN52, th3, grad=True)
+            v0, g0 = ctx.dtc_logpdf(gp.MATERN52, th3, grad=True)
+            assert abs(v - v0) <= 1e-11 * abs(v0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0))
+    finally:
+        g.close()
+
+
+@pytest.mark.skipif(device_count() < 2, reason="needs two devices (gpurun --gpus 2)")
+def test_group_scaled_dtc_row_sharded_devices(ctx):
+    """The same over NCCL on every visible device: one all-gather + one all-reduce per evaluation."""
+    import gpar_at_scale_b200 as gp
+    rng = np.random.default_rng(52)
+    nd = device_count()
+    g = gp.Group(list(range(nd)))
+    try:
+        n, m, d = 200_003, 300, 2
+        t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)) * 1.5; y = rng.normal(size=n)
+        th = np.array([0.2, 0.1, -0.3, 0.2, -1.0])
+        ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+        v0 = ctx.scaled_dtc(3, 3, th)
+        lo = g.load_row_slices(X, Z, t, y)
+        v = g.scaled_dtc_sharded(3, 3, th, lo)
+        assert abs(v - v0) <= 1e-11 * abs(v0), (v, v0)
     finally:
         g.close()
 

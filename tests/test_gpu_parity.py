@@ -510,52 +510,105 @@ def test_scaled_dtc_grad_multi_slab_and_full_size(ctx):
     print("scaled objective + gradient N=1M M=1024: %.1f ms device" % ms)
 
 
-def test_ill_conditioned_cov_u_gradient_falls_back_to_the_value_path(ctx):
-    """The analytic gradients work on the collapsed statistic and an explicit (cov(u) + G)^-1: error ~ cond eps (4e-7 at
-    cond 2e7, useless beyond 1e9).  Above the conditioning threshold the gradient entry points therefore difference the
-    whitened-panel VALUE path (4-point stencil): against torch autograd of the oracle 1e-5 relative at cond 1e9 and 1e-3 at
-    1e10, where the analytic form is off by up to O(1); value keeps 1e-8.  GPAR_GRAD_FD=0 shows what the analytic form alone would give."""
+def _env(**kw):
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+def test_ill_conditioned_cov_u_gradient_in_whitened_coordinates(ctx):
+    """The collapsed analytic gradients (statistic beta'beta, explicit (cov(u) + G)^-1) lose cond * eps (4e-7 at cond 2e7,
+    useless beyond 1e9; GPAR_GRAD_FD=0 shows them alone).  Above the conditioning threshold the gradient entry points work
+    in whitened coordinates instead (A = L_u^-1 beta' next to beta, tail conditioned like Lambda = I + A A'):
+    1e-6 against torch autograd of the oracle at cond 1e9, no finite differences; value keeps 1e-8.  At cond 1e10 (output
+    variance 1e8, |beta| ~ 1e7) the bound is 1e-5: the forward-mode tangents d beta carry rounding noise ~ eps |beta|, which
+    the contraction with R = dF/dbeta (sum |R d beta| / |sum| = 4e7 there) amplifies to ~3e-6 of the largest component; the
+    oracle's own out_s component moves by 4e-6 under a permutation of the pseudo-inputs at that conditioning."""
     import gpar_at_scale_b200 as gp
     from gpar_at_scale_b200 import chain
     import toy_data as data
-    from oracle.grad import scaled_dtc_value_and_grad
+    from oracle.grad import scaled_dtc_value_and_grad, dtc_diag_value_and_grad
     rng = np.random.default_rng(5)
     x, y_obs, _, _ = data.generate_big_dataset(rng, data_samples=3000, true_samples=4000)
     Y = np.stack(y_obs); o = 2
     X = np.ascontiguousarray(Y[:o].T); Z = chain.strided_pseudo_inputs(X, 40)
     ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(x); ctx.set_outputs(Y[o]); ctx.set_noise_vector(None)
     worst_analytic = 0.0
-    for th3, gtol in ((8.0, 1e-5), (9.2, 1e-3)):      # cond ~ 1e9 / 1e10: the stencil inherits the value's own 1e-10 / 1e-9 noise
+    for th3, gtol in ((8.0, 1e-6), (9.2, 1e-5)):        # cond ~ 1e9 / 1e10
         th = np.array([4.65, 2.31, 4.10, th3, -0.43])
         v, g = ctx.scaled_dtc_grad(3, 3, th)
+        ms, launches = ctx.last_timing()
         v0, g0 = scaled_dtc_value_and_grad(th, X, Z, x, Y[o], 3, 3)
         assert abs(v - v0) <= RTOL * abs(v0)
         assert np.max(np.abs(g - g0)) <= gtol * np.max(np.abs(g0)), (th3, g, g0)
-        os.environ["GPAR_GRAD_FD"] = "0"
-        try:
-            _, ga = ctx.scaled_dtc_grad(3, 3, th)
-            worst_analytic = max(worst_analytic, float(np.max(np.abs(ga - g0)) / np.max(np.abs(g0))))
-        except gp.PosDefException:                      # the collapsed Lambda may not even factor in this corner
-            worst_analytic = float("inf")
-        finally:
-            del os.environ["GPAR_GRAD_FD"]
-    print("analytic gradient alone: worst relative error %.1e" % worst_analytic)
-    # the stencil itself, forced on a well-conditioned problem, agrees with the analytic gradient
+        assert launches < 150                           # one pass, not 21 value evaluations
+        with _env(GPAR_GRAD_FD=0):
+            try:
+                _, ga = ctx.scaled_dtc_grad(3, 3, th)
+                worst_analytic = max(worst_analytic, float(np.max(np.abs(ga - g0)) / np.max(np.abs(g0))))
+            except gp.PosDefException:                  # the collapsed Lambda may not even factor in this corner
+                worst_analytic = float("inf")
+    print("collapsed analytic gradient alone: worst relative error %.1e" % worst_analytic)
+    # well-conditioned problem: the whitened form, the collapsed form and the stencil of the value path agree
     th = np.array([0.2, 0.1, -0.3, 0.2, -1.0])
-    _, ga = ctx.scaled_dtc_grad(3, 3, th)
-    os.environ["GPAR_GRAD_FD"] = "1"
-    try:
+    va, ga = ctx.scaled_dtc_grad(3, 3, th)
+    with _env(GPAR_GRAD_WHITENED=1):
+        vw, gw = ctx.scaled_dtc_grad(3, 3, th)
+    with _env(GPAR_GRAD_FD=1):
         _, gf = ctx.scaled_dtc_grad(3, 3, th)
-        n, m = 5000, 80
-        xs = rng.uniform(0, 10, n); zs = np.linspace(0, 10, m); ys = np.sin(xs) + 0.1 * rng.normal(size=n)
-        ctx.set_inputs(xs); ctx.set_pseudo(zs); ctx.set_outputs(ys)
-        th3 = np.log([1.0, 1.0, 0.1])
-        vf, gf3 = ctx.dtc_logpdf(3, th3, grad=True)
-    finally:
-        del os.environ["GPAR_GRAD_FD"]
+    assert abs(vw - va) <= 1e-11 * abs(va) and np.max(np.abs(gw - ga)) <= 1e-9 * np.max(np.abs(ga)), (gw, ga)
     assert np.max(np.abs(gf - ga)) <= 1e-6 * np.max(np.abs(ga))
+    # the other time / output kernels and a multi-tile M through the whitened form
+    for n, m, d, kt, ko in ((1030, 129, 2, 3, 0), (1500, 40, 4, 2, 1), (900, 17, 7, 1, 2)):
+        r2 = np.random.default_rng(3 * n + m)
+        t = np.sort(r2.uniform(0, n / 30, n)); Xr = r2.normal(size=(n, d)); Zr = r2.normal(size=(m, d)); yr = r2.normal(size=n)
+        thr = r2.uniform(-1.0, 0.3, 5)
+        ctx.set_inputs(Xr); ctx.set_pseudo(Zr); ctx.set_times(t); ctx.set_outputs(yr)
+        va, ga = ctx.scaled_dtc_grad(kt, ko, thr)
+        with _env(GPAR_GRAD_WHITENED=1):
+            vw, gw = ctx.scaled_dtc_grad(kt, ko, thr)
+        assert abs(vw - va) <= 1e-10 * abs(va) and np.max(np.abs(gw - ga)) <= 1e-7 * np.max(np.abs(ga)), (n, m, gw, ga)
+    # plain DTC / VFE, diagonal noise: (a) forced on a well-conditioned problem, jitter = noise and explicit jitter;
+    n, m = 5000, 80
+    xs = rng.uniform(0, 10, n); zs = np.linspace(0, 10, m); ys = np.sin(xs) + 0.1 * rng.normal(size=n)
+    ctx.set_inputs(xs); ctx.set_pseudo(zs); ctx.set_outputs(ys)
+    th3 = np.log([1.0, 1.0, 0.1])
+    for kind in (0, 3):
+        for vfe in (False, True):
+            for jit in (-1.0, 1e-3):
+                va, ga3 = ctx.dtc_logpdf(kind, th3, vfe=vfe, jitter=jit, grad=True)
+                with _env(GPAR_GRAD_WHITENED=1):
+                    vw, gw3 = ctx.dtc_logpdf(kind, th3, vfe=vfe, jitter=jit, grad=True)
+                v0, g0 = dtc_diag_value_and_grad(th3, xs[:, None], zs[:, None], ys, kind, vfe=vfe, jitter=jit)
+                assert abs(vw - v0) <= RTOL * abs(v0)
+                assert np.max(np.abs(gw3 - g0)) <= 1e-6 * np.max(np.abs(g0)), (kind, vfe, jit, gw3, ga3, g0)
+    with _env(GPAR_GRAD_FD=1):
+        vf, gf3 = ctx.dtc_logpdf(3, th3, grad=True)
     va, ga3 = ctx.dtc_logpdf(3, th3, grad=True)
     assert abs(vf - va) <= 1e-10 * abs(va) and np.max(np.abs(gf3 - ga3)) <= 1e-6 * np.max(np.abs(ga3))
+    # (b) ill-conditioned (EQ kernel, large variance, tiny jitter: cond ~ 7e10): taken automatically.  The VFE trace term
+    # tr(A A') differentiates to 2 tr(A A_D') - <L_u^-1 dKuu L_u^-T, A A'>, two cond-sized M x M sums that cancel: 1e-5 there
+    # (the stencil of the value path gave 1e-3 at this conditioning)
+    th3 = np.log([2.0, 30.0, 0.1])
+    for vfe, gtol in ((False, 1e-6), (True, 1e-5)):
+        v, g3 = ctx.dtc_logpdf(0, th3, vfe=vfe, jitter=1e-6, grad=True)
+        ms, launches = ctx.last_timing()
+        v0, g0 = dtc_diag_value_and_grad(th3, xs[:, None], zs[:, None], ys, 0, vfe=vfe, jitter=1e-6)
+        assert abs(v - v0) <= RTOL * abs(v0)
+        assert np.max(np.abs(g3 - g0)) <= gtol * np.max(np.abs(g0)), (vfe, g3, g0)
+        assert launches < 150
 
 
 def test_ill_conditioned_cov_u_keeps_parity(ctx):
