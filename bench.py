@@ -339,6 +339,29 @@ def run_gpar_fit(ctx, gp, world, rank, local, iterations, side_group):
                                 "f_calls": calls.tolist(), "member_of": member.tolist(), "members_used": int(len(set(member.tolist()))),
                                 "max_rel_diff_vs_torchrun_path": float(np.max(np.abs(gmin - ref) / np.abs(ref))),
                                 "identical_optima": bool(np.all(gmin == ref))}
+            # one scaled objective with its ROWS sharded over the devices (gpar_group_scaled_dtc_sharded): the last output's problem
+            # (D = P - 1 observed outputs as inputs), one all-gather of slice summaries + one all-reduce of (G, g) per evaluation,
+            # against the same evaluation on one device (this rank's context)
+            try:
+                o = P - 1
+                Xo = np.ascontiguousarray(Y[:o].T); Zo = chain.strided_pseudo_inputs(Xo, M)
+                th5 = np.log([2.0, 0.5, 1.0, 1.0, 0.1])
+                ctx.set_inputs(Xo); ctx.set_pseudo(Zo); ctx.set_times(t); ctx.set_outputs(Y[o]); ctx.set_noise_vector(None)
+                one = []
+                for _ in range(4):
+                    t1 = time.perf_counter(); v1 = ctx.scaled_dtc(gp.MATERN52, gp.MATERN52, th5); one.append(time.perf_counter() - t1)
+                lo = g.load_row_slices(Xo, Zo, t, Y[o])
+                sh = []
+                for _ in range(6):
+                    t1 = time.perf_counter(); vs = g.scaled_dtc_sharded(gp.MATERN52, gp.MATERN52, th5, lo); sh.append(time.perf_counter() - t1)
+                out["sharded_scaled_objective"] = {
+                    "path": "gpar_group_scaled_dtc_sharded, one process, %d devices, rows of ONE objective (N=%d, M=%d, D=%d) sliced" % (world, N, M, o),
+                    "ms_one_device": float(np.median(one[1:]) * 1e3), "ms_sharded": float(np.median(sh[2:]) * 1e3),
+                    "speedup": float(np.median(one[1:]) / np.median(sh[2:])), "value_one_device": repr(v1), "value_sharded": repr(vs),
+                    "rel_diff": float(abs(vs - v1) / abs(v1)), "scaling": "strong",
+                    "collective_bytes_per_evaluation": int(8 * (M * M + M + world * (9 + 3 * M)))}
+            except Exception as e:      # the fit numbers above stand on their own
+                out["sharded_scaled_objective"] = {"error": repr(e)}
             g.close()
         dist.barrier(group=side_group)       # host-side wait (gloo): no NCCL kernel spins on the GPUs the group leg uses
     return out
