@@ -358,8 +358,13 @@ def compute_gpar_dtc_objective(f, u, time_loc, outputs, time_kernel=None, tempor
 def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_loc, outputs, out_kernel=None, time_kernel=None,
                                  i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                  optimization_time_limit=1000.0, show_optimization_trace=False, debug=False, ctx=None, rng=None,
-                                 iterations=1000, return_result=False, optimizer="neldermead", n_restarts=1, speculative=False):
-    """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma).  optimizer="lbfgs" replaces the
+                                 iterations=1000, return_result=False, optimizer="neldermead", n_restarts=1, speculative=False, group=None):
+    """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma).  group (NEW; a context.Group): the ROWS of this one
+    objective are sharded over the group's devices (gpar_group_scaled_dtc_sharded) — for a single output too large for one
+    device's time or memory budget; plain Nelder-Mead only.
+    A failed Cholesky: the plain Nelder-Mead path raises PosDefException, as the reference's nlml (dtc.jl:29-48, no
+    try / catch) would; the NEW paths (lbfgs, n_restarts, speculative, the C++ group fits) read it as +Inf for that point.
+    optimizer="lbfgs" replaces the
     reference's Nelder-Mead (:58-61) by L-BFGS on gpar_scaled_dtc_grad.  n_restarts > 1 (NEW): that many Nelder-Mead
     runs in lock-step — the first from the given / drawn initial parameters, the others from theta0 ~ U(0,1)^5 (the
     missing-parameter rule, util.jl:128-134) — every round of candidates in ONE gpar_scaled_dtc_batch call; each run
@@ -367,12 +372,20 @@ def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_l
     run whose four candidate points per iteration are evaluated in one batched call (neldermead.optimize_speculative):
     the simplices, the optimum and f_calls of the plain run at ~2/3 of its wall-clock at the reference's sizes."""
     out_kernel = out_kernel or Matern52(); time_kernel = time_kernel or Matern52()
-    ctx = ctx or default_context()
-    ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
-    ctx.set_times(time_loc); ctx.set_outputs(outputs)
+    if group is not None:
+        if optimizer != "neldermead" or n_restarts > 1 or speculative:
+            raise ValueError("group=: the row-sharded objective is driven by the plain Nelder-Mead path only")
+        row_lo = group.load_row_slices(to_ColVecs(input_locations), to_ColVecs(pseudo_input_locations), time_loc, outputs)
 
-    def nlml(params):    # dtc.jl:29-48; data stays resident on the device across evaluations
-        return -ctx.scaled_dtc(time_kernel.code, out_kernel.code, params)
+        def nlml(params):
+            return -group.scaled_dtc_sharded(time_kernel.code, out_kernel.code, params, row_lo)
+    else:
+        ctx = ctx or default_context()
+        ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))
+        ctx.set_times(time_loc); ctx.set_outputs(outputs)
+
+        def nlml(params):    # dtc.jl:29-48; data stays resident on the device across evaluations
+            return -ctx.scaled_dtc(time_kernel.code, out_kernel.code, params)
 
     params = parse_initial_gpar_params(i_log_time_l, i_log_time_var, i_log_out_l, i_log_out_var, i_log_noise_sigma, rng)
     if debug:

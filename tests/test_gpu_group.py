@@ -264,6 +264,27 @@ def test_group_scaled_dtc_row_sharded_devices(ctx):
         g.close()
 
 
+def test_fit_through_the_row_sharded_objective(ctx):
+    """api.get_optim_scaled_gpar_params(group=...): Nelder-Mead on the row-sharded objective (3 loopback members) reaches the
+    optimum of the one-device fit (values differ in the last digits, so the simplices may part ways late: compare optima)."""
+    from gpar_at_scale_b200 import api
+    rng = np.random.default_rng(61)
+    n, m = 6000, 30
+    t = np.arange(n) / 30.0
+    X = np.sin(0.3 * t)[:, None] + 0.1 * rng.normal(size=(n, 1)); Z = np.linspace(X.min(), X.max(), m)[:, None]
+    y = np.cos(2.0 * X[:, 0]) + 0.3 * np.sin(0.05 * t) + 0.1 * rng.normal(size=n)
+    kw = dict(i_log_time_l=1.0, i_log_time_var=0.0, i_log_out_l=0.0, i_log_out_var=0.0, i_log_noise_sigma=-1.0, iterations=60, return_result=True)
+    p1, r1 = api.get_optim_scaled_gpar_params(X, Z, t, y, ctx=ctx, **kw)
+    g = _loopback_group(3)
+    try:
+        p3, r3 = api.get_optim_scaled_gpar_params(X, Z, t, y, group=g, **kw)
+    finally:
+        g.close()
+    assert abs(r3.minimum - r1.minimum) <= 1e-6 * abs(r1.minimum), (r1.minimum, r3.minimum)
+    with pytest.raises(ValueError):
+        api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), optimizer="lbfgs")
+
+
 def test_group_abi_error_behaviour():
     """Status codes and messages instead of crashes: duplicate devices, missing resident result, incomplete task,
     unknown optimiser, member without data."""
