@@ -42,7 +42,7 @@ __global__ void sum_final_kernel(const double* part, int n, double* out) {
 // the DMMA SYRK are enqueued on the context's stream, nothing is read back.  *stats -> [G (M*M) | H (M*M) | g (Mpad) |
 // h (Mpad) | y'y (1)], *count doubles.  Every term is a sum over data points, so slices on different devices add up
 // (gpar_group_dtc_logpdf_sharded all-reduces this buffer).
-int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count) {
+int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count, int whiten_vfe) {
   if (ctx->N < 1 || ctx->M < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: inputs (set_inputs) and pseudo-inputs (set_pseudo) must be set");
   if (ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: X has D=%d but Z has D=%d", ctx->D, ctx->Dz);
   if (ctx->Ny != ctx->N || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "dtc: outputs length %lld != N %lld", (long long)ctx->Ny, (long long)ctx->N);
@@ -67,6 +67,13 @@ int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad
   double* ypart = ctx->gpart.as<double>() + (size_t)nsplit * 2 * Mpad;
   LAUNCH(ctx, sumsq_kernel, 1024, 256, 0, ctx->y.as<double>(), N, ypart);
   LAUNCH(ctx, sum_final_kernel, 1, 256, 0, ypart, 1024, dyy);
+  if (whiten_vfe >= 0) {      // poorly conditioned cov(u): this member's dtc_tail_prepare left L_u on its side stream — whiten the
+    TailBufs tb;              // slice's panel(s) before the SYRK, so that the summed statistics are A A' (and A A_D') themselves
+    CHK(tail_layout(ctx, want_grad, whiten_vfe, &tb));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    CHK(panel_left_solve(ctx, ctx->panelK.as<double>(), Npad, Mpad, M, tb.Lu));
+    if (want_grad) CHK(panel_left_solve(ctx, ctx->panelD.as<double>(), Npad, Mpad, M, tb.Lu));
+  }
   CHK(panel_syrk_run(ctx, ctx->panelK.as<double>(), ctx->panelD.as<double>(), Npad, Mpad, M, want_grad, G, H));
   *stats = G; *count = 2 * MM + 2 * (size_t)Mpad + 1;
   return GPAR_OK;

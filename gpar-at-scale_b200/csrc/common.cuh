@@ -261,7 +261,8 @@ int merged_gather_test(gpar_ctx* ctx, double* dst_a, double* dst_b);
 // gpar_group_broadcast fails loudly instead of reading stale memory.
 static inline void gpar_drop_result(gpar_ctx* c) { c->res_a = nullptr; c->res_b = nullptr; c->res_len = 0; }
 // abi.cu: sufficient statistics of the plain DTC objective over the context's resident data slice (async on its stream)
-int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count);
+// whiten_vfe >= 0: the panels are whitened by the L_u this context's dtc_tail_prepare(vfe = whiten_vfe) computed, before the SYRK
+int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count, int whiten_vfe = -1);
 // dense_la.cu: hand-written dense linear algebra on column-major FP64 device matrices (no cuBLAS / cuSOLVER anywhere in
 // the library), enqueued on ctx->stream.  Triangular-operand flags restrict the k range of a product and mask the other
 // triangle at load time.

@@ -256,24 +256,28 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
   GCU(cudaSetDevice(g->dev[0]));
   int rc = dtc_tail_prepare(c0, kernel, p, vfe, jitter, want_grad);      // cov(u), L_u, ... on member 0's side stream
   if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  bool ill = false;
   {
-    // The sharded path sums the COLLAPSED statistic G = Kuf Kfu over the members; with a poorly conditioned cov(u) that
-    // loses cond * eps ("Conditioning") where the one-device entry point whitens the panel by L_u.  Say so
-    // instead of returning a result that depends on how the rows were sharded.
+    // The collapsed statistic G = Kuf Kfu loses cond(cov(u)) eps ("Conditioning").  When cov(u) is poorly conditioned
+    // every member factors it too and whitens ITS panels by L_u before the SYRK, exactly as the one-device entry point does,
+    // so that the result does not depend on how the rows were sharded.
     TailBufs tb;
     rc = tail_layout(c0, want_grad, vfe, &tb);
     if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
     double mm[2] = {1.0, 1.0};
     GCU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, c0->stream2));
     GCU(cudaStreamSynchronize(c0->stream2));
-    if (gpar_needs_whitened_panel(mm))
-      return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: cov(u) is too poorly conditioned for the row-sharded statistic "
-                        "((max/min diag L_u)^2 = %.3g > GPAR_ROBUST_COND); evaluate it with gpar_dtc_logpdf on one device", (mm[1] / mm[0]) * (mm[1] / mm[0]));
+    ill = gpar_needs_whitened_panel(mm);
+  }
+  std::vector<int> st;
+  if (ill) {
+    run_members(g, st, [&](int i) { return i == 0 ? GPAR_OK : dtc_tail_prepare(g->ctx[i], kernel, p, vfe, jitter, want_grad); });
+    for (int i = 0; i < n; i++)
+      if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
   }
   std::vector<double*> stats(n, nullptr);
   std::vector<size_t> count(n, 0);
-  std::vector<int> st;
-  run_members(g, st, [&](int i) { return dtc_slice_stats(g->ctx[i], kernel, p, want_grad, &stats[i], &count[i]); });
+  run_members(g, st, [&](int i) { return dtc_slice_stats(g->ctx[i], kernel, p, want_grad, &stats[i], &count[i], ill ? vfe : -1); });
   for (int i = 0; i < n; i++)
     if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
   rc = group_allreduce_sum(g, stats, count[0]);
@@ -286,7 +290,8 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
   GCU(cudaMemcpyAsync(&yy, dyy, sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
   for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
   GCU(cudaSetDevice(g->dev[0]));
-  rc = dtc_tail(c0, kernel, p, vfe, jitter, Ntot, G, H, gh, gh + Mpad, yy, val, grad, nullptr, false);
+  if (ill && want_grad) rc = dtc_tail_whitened(c0, p, vfe, jitter, Ntot, G, H, gh, gh + Mpad, yy, val, grad, nullptr);
+  else rc = dtc_tail(c0, kernel, p, vfe, jitter, Ntot, G, H, gh, gh + Mpad, yy, val, grad, nullptr, ill);
   if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
   return GPAR_OK;
 }

@@ -240,6 +240,15 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
             v, gr = g.dtc_logpdf_sharded(gp.MATERN52, th3, grad=True)
             v0, g0 = ctx.dtc_logpdf(gp.MATERN52, th3, grad=True)
             assert abs(v - v0) <= 1e-11 * abs(v0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0))
+            # poorly conditioned cov(u) (EQ kernel, variance 900, jitter 1e-6): every member whitens its panels by L_u, the
+            # whitened statistics are summed, member 0 finishes in whitened coordinates — as the one-device entry point does
+            # (cond(cov(u)) ~ 6e10 here: two float64 evaluations with different summation orders agree to ~4e-9 / ~2e-5)
+            thi3 = np.log([2.0, 30.0, 0.1])
+            for vfe in (False, True):
+                v, gr = g.dtc_logpdf_sharded(gp.EQ, thi3, vfe=vfe, jitter=1e-6, grad=True)
+                v0, g0 = ctx.dtc_logpdf(gp.EQ, thi3, vfe=vfe, jitter=1e-6, grad=True)
+                assert abs(v - v0) <= 1e-8 * abs(v0) and np.max(np.abs(gr - g0)) <= 1e-4 * np.max(np.abs(g0)), (vfe, v, v0, gr, g0)
+                assert abs(g.dtc_logpdf_sharded(gp.EQ, thi3, vfe=vfe, jitter=1e-6) - ctx.dtc_logpdf(gp.EQ, thi3, vfe=vfe, jitter=1e-6)) <= 1e-8 * abs(v0)
     finally:
         g.close()
 
