@@ -350,15 +350,16 @@ class Group:
             m.set_noise_vector(None)
         return np.asarray(bounds[:-1], dtype=np.int64)
 
-    def scaled_dtc_sharded(self, k_time, k_out, theta, row_lo):
+    def scaled_dtc_sharded(self, k_time, k_out, theta, row_lo, grad=False):
         """ONE scaled-GPAR objective over the row slices resident on the members (load_row_slices): one all-gather of the
-        slice summaries (filter carry), one all-reduce of (beta'beta, beta'alpha), tail on member 0 -> value."""
+        slice summaries (filter carry), one all-reduce of (beta'beta, beta'alpha), tail on member 0 -> value[, gradient (5,)]
+        (gradient: a second all-gather of the tangent summaries)."""
         th = as_f64(np.asarray(theta).ravel()); lo = np.ascontiguousarray(row_lo, dtype=np.int64)
         assert th.shape == (5,) and lo.shape == (len(self),)
-        val = ctypes.c_double()
+        val = ctypes.c_double(); g5 = np.zeros(5) if grad else None
         self._check(self._lib.gpar_group_scaled_dtc_sharded(self._h, int(k_time), int(k_out), dptr(th),
-                                                            lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(val)))
-        return val.value
+                                                            lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(val), dptr(g5)))
+        return (val.value, g5) if grad else val.value
 
     def scaled_dtc(self, k_time, k_out, thetas, grad=False):
         th = as_f64(np.atleast_2d(thetas)); n = len(self)

@@ -89,6 +89,11 @@ struct gpar_ctx {
     int D = 0, Mpad = 0, nch = 0, whg = 0, CT = 1; int64_t lo = 0, Npad = 0; bool robust = false;
     const double *table = nullptr, *alpha = nullptr; double *sums = nullptr, *resp = nullptr, *psi = nullptr, *gp = nullptr;
     double *summary = nullptr, *init = nullptr, *G = nullptr, *g = nullptr; size_t summary_count = 0, stats_count = 0;
+    // gradient mode (scaled_slice_grad_*): tangent tables of the slice, the tangent summaries / entering tangent states, and the
+    // host-side pieces of the final assembly
+    bool grad = false; int64_t nfull = 0; int k_out = 0;
+    const double *dtable = nullptr, *dalpha = nullptr; double *evec = nullptr, *panelD = nullptr, *summary2 = nullptr, *init2 = nullptr;
+    double pv[5] = {0}, ex[5] = {0}, val = 0.0, raw[8 + 20] = {0}, fsums[6] = {0};
   } slice;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;
@@ -302,7 +307,13 @@ int dtc_tail_whitened(gpar_ctx* ctx, const GpParams& p, int vfe, double jitter, 
                       double* val, double* grad, WhitenedTail* out);
 // scaled.cu: a row slice of the scaled objective (the context holds the full (t, y) and rows [lo, lo + N) of X); group.cu
 // all-gathers ctx->slice.summary between phase 1 and 2 and all-reduces ctx->slice.G (stats_count doubles) before finish
-int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo);
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad = false);
+// gradient mode: after the all-reduce every member runs the tail (P, w) and the zero-start tangent responses of its chunks and
+// leaves 3 tangent summaries (ctx->slice.summary2, 3 x summary_count doubles) for a second all-gather; phase 4 finishes the
+// tangent pass from the gathered summaries and returns the member's five partial sums; finish assembles on one member
+int scaled_slice_grad_phase3(gpar_ctx* ctx);
+int scaled_slice_grad_phase4(gpar_ctx* ctx, const double* gathered2, int member, double s5[5]);
+int scaled_slice_grad_finish(gpar_ctx* ctx, const double s5[5], double* dtc, double* grad);
 int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member);
 int scaled_slice_finish(gpar_ctx* ctx, double* dtc);
 // scaled.cu: conditioning decision and the panel whitening by L_u (see gpar_needs_whitened_panel)

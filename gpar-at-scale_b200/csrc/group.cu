@@ -302,10 +302,12 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
 // panel, whitening passes, SYRK) is sliced; the filter carry of the M whitened columns crosses the slice boundaries through
 // ONE all-gather of the slice summaries (D x D transition product + D x M exit state each), and ONE all-reduce sums
 // (G, g) before member 0 runs the M x M tail: 8 (M^2 + M + n (D^2 + D M)) bytes per evaluation on NVLink.
-int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val) {
+// grad (nullable): the five raw-parameter derivatives (gpar_scaled_dtc_grad) — one more all-gather (three tangent summaries).
+int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val, double* grad) {
   if (!g) return GPAR_ERR_INVALID;
   if (!theta || !row_lo || !val) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: theta, row_lo and val must not be NULL");
   const int n = (int)g->ctx.size();
+  const bool want_grad = grad != nullptr;
   gpar_ctx* c0 = g->ctx[0];
   int64_t expect = 0;
   for (int i = 0; i < n; i++) {
@@ -318,26 +320,65 @@ int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const do
   }
   if (expect != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: the slices cover %lld rows, the sequence has %lld", (long long)expect, (long long)c0->Nt);
   std::vector<int> st;
-  run_members(g, st, [&](int i) { return scaled_slice_phase1(g->ctx[i], k_time, k_out, theta, row_lo[i]); });
-  for (int i = 0; i < n; i++)
-    if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  auto members_ok = [&]() -> int {
+    for (int i = 0; i < n; i++)
+      if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+    return GPAR_OK;
+  };
+  run_members(g, st, [&](int i) { return scaled_slice_phase1(g->ctx[i], k_time, k_out, theta, row_lo[i], want_grad); });
+  int rc = members_ok();
+  if (rc != GPAR_OK) return rc;
+  if (want_grad) {
+    // the analytic gradient of the sharded path is the collapsed form (statistic beta'beta, explicit (cov(u) + G)^-1): refuse
+    // the poorly conditioned corner instead of returning cond * eps garbage — one device handles it in whitened coordinates
+    TailBufs tb;
+    GCU(cudaSetDevice(g->dev[0]));
+    rc = tail_layout(c0, true, 0, &tb);
+    if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+    double mm[2] = {1.0, 1.0};
+    GCU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, c0->stream2));
+    GCU(cudaStreamSynchronize(c0->stream2));
+    if (gpar_needs_whitened_panel(mm))
+      return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: cov(u) is too poorly conditioned for the row-sharded gradient ((max/min diag L_u)^2 = %.3g > "
+                        "GPAR_ROBUST_COND); the sharded VALUE and the one-device gradient (gpar_scaled_dtc_grad) handle it", (mm[1] / mm[0]) * (mm[1] / mm[0]));
+  }
   const size_t sc = c0->slice.summary_count;
   std::vector<const double*> sp(n); std::vector<double*> rp(n), stats(n);
   for (int i = 0; i < n; i++) {
     GCU(cudaSetDevice(g->dev[i]));
-    GCU(g->recv[i].reserve(sc * n * sizeof(double)));
+    GCU(g->recv[i].reserve((want_grad ? 3 : 1) * sc * n * sizeof(double)));
     sp[i] = g->ctx[i]->slice.summary; rp[i] = g->recv[i].as<double>(); stats[i] = g->ctx[i]->slice.G;
   }
-  int rc = group_allgather(g, sp, rp, sc);
+  rc = group_allgather(g, sp, rp, sc);
   if (rc != GPAR_OK) return rc;
   run_members(g, st, [&](int i) { return scaled_slice_phase2(g->ctx[i], rp[i], i); });
-  for (int i = 0; i < n; i++)
-    if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+  rc = members_ok();
+  if (rc != GPAR_OK) return rc;
   rc = group_allreduce_sum(g, stats, c0->slice.stats_count);
   if (rc != GPAR_OK) return rc;
   for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
-  GCU(cudaSetDevice(g->dev[0]));
-  rc = scaled_slice_finish(c0, val);
+  if (!want_grad) {
+    GCU(cudaSetDevice(g->dev[0]));
+    rc = scaled_slice_finish(c0, val);
+    if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+    return GPAR_OK;
+  }
+  // gradient: every member runs the M x M tail on the summed statistics (P, w: no broadcast needed) and the zero-start tangent
+  // responses of its chunks; a SECOND all-gather carries the three tangent summaries over the slice boundaries; the five
+  // partial sums of the members are added on the host
+  run_members(g, st, [&](int i) { return scaled_slice_grad_phase3(g->ctx[i]); });
+  rc = members_ok();
+  if (rc != GPAR_OK) return rc;
+  for (int i = 0; i < n; i++) sp[i] = g->ctx[i]->slice.summary2;
+  rc = group_allgather(g, sp, rp, 3 * sc);
+  if (rc != GPAR_OK) return rc;
+  std::vector<double> s5((size_t)n * 5, 0.0);
+  run_members(g, st, [&](int i) { return scaled_slice_grad_phase4(g->ctx[i], rp[i], i, s5.data() + (size_t)i * 5); });
+  rc = members_ok();
+  if (rc != GPAR_OK) return rc;
+  double tot[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < n; i++) for (int q = 0; q < 5; q++) tot[q] += s5[(size_t)i * 5 + q];
+  rc = scaled_slice_grad_finish(c0, tot, val, grad);
   if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
   return GPAR_OK;
 }

@@ -279,10 +279,9 @@ slice_summary_kernel(const double* __restrict__ psi, const double* __restrict__ 
 // State entering slice `member` from the gathered summaries of the slices before it: x <- Psi^(h) x + r^(h), h = 0 .. member-1.
 template <int D>
 __global__ void __launch_bounds__(32)
-slice_entering_kernel(const double* __restrict__ gathered, int member, int Mpad, double* __restrict__ init) {
+slice_entering_kernel(const double* __restrict__ gathered, int member, int Mpad, double* __restrict__ init, int64_t stride) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mpad) return;
-  const int64_t stride = D * D + (int64_t)D * Mpad;
   double st[D];
 #pragma unroll
   for (int i = 0; i < D; i++) st[i] = 0.0;
@@ -633,14 +632,14 @@ whiten_tangent_kernel(int64_t N, int64_t NB4, const double* __restrict__ table, 
 // out[q] = sum over chunks and columns of accpart[chunk][q][m] (q < 3), out[3 + j] = sum_n e_n dalpha_j[n]; fixed order
 __global__ void __launch_bounds__(1024)
 grad_sums_kernel(const double* __restrict__ accpart, int nch, int Mpad, const double* __restrict__ evec, const double* __restrict__ dalpha,
-                 int64_t N, double* __restrict__ out) {
+                 int64_t N, int64_t dstride, double* __restrict__ out) {
   __shared__ double sh[32];
   const int q = blockIdx.x;
   double a = 0.0;
   if (q < 3) {
     for (int64_t i = threadIdx.x; i < (int64_t)nch * Mpad; i += blockDim.x) a += accpart[((i / Mpad) * 3 + q) * Mpad + (i % Mpad)];
   } else {
-    const double* da = dalpha + (int64_t)(q - 3) * N;
+    const double* da = dalpha + (int64_t)(q - 3) * dstride;
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) a = fma(evec[i], da[i], a);
   }
   const double r = block_sum(a, sh);
@@ -782,8 +781,8 @@ int scaled_stats(gpar_ctx* ctx, int k_time, int k_out, double time_l, double tim
 // summary.  [all-gather of the summaries]  Phase 2: entering state, carry scan, pass 2, g partials, (L_u-whitening), SYRK.
 // [all-reduce of (G, g)]  Then the ordinary M x M tail on one member.
 template <int D>
-int scaled_slice_phase1_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, int64_t lo) {
-  constexpr int TS = D * D + 2 * D + 1;
+int scaled_slice_phase1_d(gpar_ctx* ctx, int k_out, double time_l, double time_s, double out_l, double out_s, double noise, int64_t lo, bool grad) {
+  constexpr int TS = D * D + 2 * D + 1, DTS = 2 + 2 * TS;
   gpar_ctx::SliceState& sl = ctx->slice;
   const int64_t Nfull = ctx->Nt, N = ctx->N; const int M = (int)ctx->M;
   const int Mpad = (M + GPAR_TILE - 1) / GPAR_TILE * GPAR_TILE;
@@ -792,36 +791,50 @@ int scaled_slice_phase1_d(gpar_ctx* ctx, int k_out, double time_l, double time_s
   const int whg = choose_whg(ctx, T, NB4);
   const int nch = (int)((NB4 + whg - 1) / whg);
   CU(ctx->panelK.reserve((size_t)Npad * Mpad * sizeof(double)));
-  CU(ctx->kal_e.reserve(((size_t)Nfull * TS + (size_t)Nfull + 16) * sizeof(double)));
+  if (grad) CU(ctx->panelD.reserve((size_t)Npad * Mpad * sizeof(double)));
+  CU(ctx->kal_e.reserve(((size_t)Nfull * TS + (size_t)Nfull + 16 + (grad ? (size_t)Nfull * (3 + DTS) : 0)) * sizeof(double)));
   const size_t state_doubles = (size_t)nch * D * Mpad, sum_doubles = (size_t)D * D + (size_t)D * Mpad;
-  CU(ctx->gpart.reserve((state_doubles + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad + sum_doubles + (size_t)D * Mpad) * sizeof(double)));
+  const size_t tangent_doubles = grad ? 3 * state_doubles + (size_t)nch * 3 * Mpad : 0;      // tstate | accpart, where scaled_tangent_d expects them
+  CU(ctx->gpart.reserve((state_doubles + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad + tangent_doubles
+                         + (grad ? 4 : 1) * (sum_doubles + (size_t)D * Mpad)) * sizeof(double)));
   const size_t MM = (size_t)M * M;
   CU(ctx->kal_d.reserve((MM + Mpad) * sizeof(double)));
   double* table = ctx->kal_e.as<double>(); double* alpha = table + (size_t)Nfull * TS; double* sums = alpha + Nfull; double* lml = sums + 8;
   double* resp = ctx->gpart.as<double>(); double* psi = resp + state_doubles; double* gp = psi + (size_t)nch * D * D;
-  double* summary = gp + (size_t)nch * Mpad + Mpad; double* init = summary + sum_doubles;
+  double* summary = gp + (size_t)nch * Mpad + Mpad + tangent_doubles; double* init = summary + sum_doubles;
+  double* summary2 = init + (size_t)D * Mpad; double* init2 = summary2 + 3 * sum_doubles;                  // gradient mode only
+  double* dalpha = lml + 8; double* dtable = dalpha + 2 * (size_t)Nfull; double* evec = dtable + (size_t)Nfull * DTS;
   const int kind_time = D == 1 ? GPAR_MATERN12 : (D == 2 ? GPAR_MATERN32 : GPAR_MATERN52);
-  CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, Nfull, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
-                alpha, lml, nullptr, nullptr, table, sums));
+  if (grad) {
+    const int dirs[3] = {0, -1, 1};
+    CHK(lgssm_run_tangent(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, Nfull, ctx->t.as<double>(), ctx->y.as<double>(), nullptr, dirs,
+                          alpha, nullptr, nullptr, sums, dalpha, table, dtable));
+  } else {
+    CHK(lgssm_run(ctx, kind_time, &time_l, &time_s, &noise, 1, 1, Nfull, ctx->t.as<double>(), ctx->y.as<double>(), nullptr,
+                  alpha, lml, nullptr, nullptr, table, sums));
+  }
   const double inv_l2 = 1.0 / (out_l * out_l);
   const int CT = (T % 2 == 0) ? 2 : 1;
   dim3 grid(T / CT, nch);
   const double* tableL = table + (size_t)lo * TS;
   double* panel = ctx->panelK.as<double>();
-  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, nullptr, whg)));
-  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, nullptr, whg)));
+  double* panelD = grad ? ctx->panelD.as<double>() : nullptr;
+  if (CT == 2) CHK((launch_pass1<D, 2>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, panelD, whg)));
+  else CHK((launch_pass1<D, 1>(ctx, k_out, grid, ctx->X.as<double>(), ctx->Z.as<double>(), N, M, NB4, inv_l2, out_s, tableL, panel, resp, Mpad, panelD, whg)));
   LAUNCH(ctx, chunk_transition_kernel<D>, nch, 32, 0, tableL, N, psi, whg);
   LAUNCH(ctx, slice_summary_kernel<D>, (Mpad + 31) / 32, 32, 0, psi, resp, nch, Mpad, summary);
   sl.D = D; sl.lo = lo; sl.Mpad = Mpad; sl.Npad = Npad; sl.nch = nch; sl.whg = whg; sl.CT = CT;
   sl.table = tableL; sl.alpha = alpha + lo; sl.sums = sums; sl.resp = resp; sl.psi = psi; sl.gp = gp; sl.summary = summary; sl.init = init;
   sl.G = ctx->kal_d.as<double>(); sl.g = sl.G + MM; sl.summary_count = sum_doubles; sl.stats_count = MM + Mpad;
+  sl.grad = grad; sl.dtable = dtable + (size_t)lo * DTS; sl.dalpha = dalpha + lo; sl.evec = evec; sl.panelD = panelD;
+  sl.summary2 = summary2; sl.init2 = init2; sl.nfull = Nfull;
   return GPAR_OK;
 }
 template <int D>
 int scaled_slice_phase2_d(gpar_ctx* ctx, const double* gathered, int member, const PanelHook* before_syrk) {
   gpar_ctx::SliceState& sl = ctx->slice;
   const int64_t N = ctx->N, NB4 = sl.Npad / 4; const int M = (int)ctx->M, Mpad = sl.Mpad, T = Mpad / GPAR_TILE;
-  LAUNCH(ctx, slice_entering_kernel<D>, (Mpad + 31) / 32, 32, 0, gathered, member, Mpad, sl.init);
+  LAUNCH(ctx, slice_entering_kernel<D>, (Mpad + 31) / 32, 32, 0, gathered, member, Mpad, sl.init, (int64_t)(D * D + (int64_t)D * Mpad));
   LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, sl.psi, sl.resp, sl.nch, Mpad, (const double*)sl.init);
   double* panel = ctx->panelK.as<double>();
   dim3 grid(T / sl.CT, sl.nch);
@@ -840,7 +853,11 @@ int scaled_slice_phase2_d(gpar_ctx* ctx, const double* gathered, int member, con
 // the residual e = alpha - res_panel res_w likewise from (beta, w) or (A, wt).
 template <int D>
 int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec, double* out5,
-                     const double* gemm_panel = nullptr, const double* res_w = nullptr) {
+                     const double* gemm_panel = nullptr, const double* res_w = nullptr,
+                     int stage = 0, const double* tinit = nullptr, int64_t dalpha_stride = 0) {
+  // stage 0: everything.  Row slices (scaled_slice_*): stage 1 = residual + zero-start tangent responses of the chunks,
+  // stage 2 = the rest, the three carry scans starting from tinit (3 x D x Mpad: tangent states entering the slice);
+  // dalpha_stride: distance between the two d alpha arrays (the full sequence's length; default N)
   if (!gemm_panel) gemm_panel = st.beta;
   if (!res_w) res_w = wvec;
   const int64_t N = ctx->N; const int M = (int)ctx->M;
@@ -849,15 +866,19 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
   const size_t state_doubles = (size_t)nch * D * Mpad;
   double* tstate = st.psi + (size_t)nch * D * D + (size_t)nch * Mpad + Mpad;       // after gp / g partials (layout of scaled_stats_d)
   double* accpart = tstate + 3 * state_doubles;
-  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, gemm_panel, res_w, st.alpha, N, NB4, T, M, st.evec);
   int CT = (T % 2 == 0) ? 2 : 1;                      // columns per thread: two halve the table reads (218 registers, 2 CTAs/SM; one: 164, 3 CTAs/SM)
   if (const char* e = getenv("GPAR_TANGENT_CT")) { if (atoi(e) == 1) CT = 1; }
   dim3 grid(T / CT, nch);
+  if (stage != 2) {
+  LAUNCH(ctx, residual_kernel, (int)((NB4 + 3) / 4), 128, 0, gemm_panel, res_w, st.alpha, N, NB4, T, M, st.evec);
   if (CT == 2) LAUNCH(ctx, (whiten_tangent_kernel<D, 2, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
                       tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
   else LAUNCH(ctx, (whiten_tangent_kernel<D, 1, false>), grid, GPAR_TILE, 0, N, NB4, st.table, st.dtable, st.beta, st.panelD, st.start,
               tstate, nch, 0, (const double*)nullptr, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr, Mpad, M, st.whg);
-  for (int q = 0; q < 3; q++) LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad, (const double*)nullptr);
+  }
+  if (stage == 1) return GPAR_OK;
+  for (int q = 0; q < 3; q++)
+    LAUNCH(ctx, carry_scan_kernel<D>, (Mpad + 31) / 32, 32, 0, st.psi, tstate + q * state_doubles, nch, Mpad, tinit ? tinit + (size_t)q * D * Mpad : (const double*)nullptr);
   // S = beta P slab by slab on the DMMA panel-GEMM (panel_gemm.cu): P goes once into the operand layout, every slab of S
   // comes out in the panel layout and is consumed at once by the final tangent pass, so only one slab buffer exists
   const int base_chunks = std::max(1, 131072 / (st.whg * 4));
@@ -885,7 +906,7 @@ int scaled_tangent_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, con
                 tstate, nch, c0, Ss, slab_groups, st.evec, wvec, accpart, Mpad, M, st.whg);
   }
   CU(ctx->scal.reserve(8 * sizeof(double)));
-  LAUNCH(ctx, grad_sums_kernel, 5, 1024, 0, accpart, nch, Mpad, st.evec, st.dalpha, N, ctx->scal.as<double>());
+  LAUNCH(ctx, grad_sums_kernel, 5, 1024, 0, accpart, nch, Mpad, st.evec, st.dalpha, N, dalpha_stride > 0 ? dalpha_stride : N, ctx->scal.as<double>());
   CU(cudaMemcpyAsync(out5, ctx->scal.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return GPAR_OK;
@@ -1043,28 +1064,42 @@ static int slice_tail_bufs(gpar_ctx* ctx, SliceTailBufs* b) {
   b->dinfo = ctx->info.as<int>();
   return GPAR_OK;
 }
-int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo) {
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad) {
   CU(cudaSetDevice(ctx->device));
   gpar_drop_result(ctx);
   if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: inputs (this member's rows) and pseudo-inputs must be set, same dimension");
   if (ctx->Nt != ctx->Ny || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: every member holds the FULL times and outputs (%lld times, %lld outputs)", (long long)ctx->Nt, (long long)ctx->Ny);
   if (lo < 0 || lo % 4 != 0 || lo + ctx->N > ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: rows [%lld, %lld) of %lld: the first row of a slice must be a multiple of 4", (long long)lo, (long long)(lo + ctx->N), (long long)ctx->Nt);
-  double pv[5];
-  for (int i = 0; i < 5; i++) pv[i] = exp(theta[i]) + 1e-3;      // unpack_gpar (util.jl:45-55)
+  gpar_ctx::SliceState& sl = ctx->slice;
+  for (int i = 0; i < 5; i++) { sl.ex[i] = exp(theta[i]); sl.pv[i] = sl.ex[i] + 1e-3; }      // unpack_gpar (util.jl:45-55)
+  const double* pv = sl.pv;
   const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
-  SliceTailBufs b;
-  CHK(slice_tail_bufs(ctx, &b));
-  CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, b.Lu, b.V, b.dinfo, b.sc + 4));
-  ctx->slice.robust = false;
+  sl.k_out = k_out;
+  if (grad) {      // the gradient's tail (P, w, traces) is dense_tail.cu's: its own buffer layout and side-stream job
+    GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
+    CHK(dtc_tail_prepare(ctx, k_out, p, 0, noise, true));
+  } else {
+    SliceTailBufs b;
+    CHK(slice_tail_bufs(ctx, &b));
+    CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, b.Lu, b.V, b.dinfo, b.sc + 4));
+  }
+  sl.robust = false;
   switch (k_time) {
-    case GPAR_MATERN12: return scaled_slice_phase1_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
-    case GPAR_MATERN32: return scaled_slice_phase1_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
-    case GPAR_MATERN52: return scaled_slice_phase1_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo);
+    case GPAR_MATERN12: return scaled_slice_phase1_d<1>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo, grad);
+    case GPAR_MATERN32: return scaled_slice_phase1_d<2>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo, grad);
+    case GPAR_MATERN52: return scaled_slice_phase1_d<3>(ctx, k_out, time_l, time_s, out_l, out_s, noise, lo, grad);
     default: return gpar_fail(ctx, GPAR_ERR_INVALID, "time kernel code %d has no state-space form (use Matern12/32/52)", k_time);
   }
 }
 int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member) {
   CU(cudaSetDevice(ctx->device));
+  if (ctx->slice.grad) {      // gradient mode: well-conditioned cov(u) only (checked by the caller) — no L_u-whitening of the panel
+    switch (ctx->slice.D) {
+      case 1: return scaled_slice_phase2_d<1>(ctx, gathered, member, nullptr);
+      case 2: return scaled_slice_phase2_d<2>(ctx, gathered, member, nullptr);
+      default: return scaled_slice_phase2_d<3>(ctx, gathered, member, nullptr);
+    }
+  }
   SliceTailBufs b;
   CHK(slice_tail_bufs(ctx, &b));
   // the conditioning decision is a function of L_u alone, which every member computes identically
@@ -1090,6 +1125,94 @@ int scaled_slice_finish(gpar_ctx* ctx, double* dtc) {
   if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(cov(u)) failed: leading minor %d is not positive definite", hinfo[0]);
   if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(A*A' + I) failed: leading minor %d is not positive definite", hinfo[1]);
   *dtc = -0.5 * ((double)ctx->Nt * LOG2PI_S + fs[0] + hs[0] + fs[1] - hs[1]);      // dtc.jl:122-125
+  return GPAR_OK;
+}
+
+// The five raw-parameter derivatives from the pieces (see gpar_scaled_dtc_grad): s5 = <R, d beta_{tl, noise, log l}>, <e, d alpha_{tl, noise}>
+static void assemble_scaled_grad(int64_t N, double val, const double* raw, const double dsums[4], double sum_logS, double sum_a2, const double s5[5],
+                                 const double pv[5], const double ex[5], double* dtc, double* grad) {
+  const double time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
+  *dtc = val - 0.5 * sum_logS;
+  const double* t = raw + 8;
+  const double cc = raw[2];
+  const double trTG = t[2] + t[3], trTKdK = t[4] + t[5] - t[6], trTKK = t[7] + t[8] - t[9], trTK = t[10] + t[12] - t[11], gw = t[16];
+  const double F_os = (-trTG + gw - 0.5 * (trTKK - noise * trTK)) / out_s;
+  const double F_logl = s5[2] - 0.5 * trTKdK;
+  const double F_tl = s5[0] - s5[3] - 0.5 * dsums[0];
+  const double F_noise = (s5[1] - s5[4] - 0.5 * dsums[1]) - 0.5 * trTK;
+  const double F_ts = (-0.5 * ((double)N - (sum_a2 - cc)) - out_s * F_os - noise * F_noise) / time_s;
+  grad[0] = F_tl * ex[0];
+  grad[1] = F_ts * 2.0 * pv[1] * ex[1];
+  grad[2] = F_logl / out_l * ex[2];
+  grad[3] = F_os * 2.0 * pv[3] * ex[3];
+  grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+}
+
+static_assert(GPAR_NTR == 20, "gpar_ctx::SliceState::raw is sized for 8 + 20 scalars");
+static ScaledStats slice_as_stats(gpar_ctx* ctx) {
+  const gpar_ctx::SliceState& sl = ctx->slice;
+  ScaledStats st{};
+  st.G = sl.G; st.g = sl.g; st.Mpad = sl.Mpad; st.Npad = sl.Npad; st.table = const_cast<double*>(sl.table); st.alpha = const_cast<double*>(sl.alpha);
+  st.beta = ctx->panelK.as<double>(); st.syrk_panel = st.beta; st.nch = sl.nch; st.whg = sl.whg;
+  st.dtable = const_cast<double*>(sl.dtable); st.dalpha = const_cast<double*>(sl.dalpha); st.panelD = sl.panelD; st.start = sl.resp; st.psi = sl.psi; st.evec = sl.evec;
+  st.sum_logS = sl.fsums[0]; st.sum_a2 = sl.fsums[3];
+  st.dsums[0] = sl.fsums[1]; st.dsums[1] = sl.fsums[2]; st.dsums[2] = sl.fsums[4]; st.dsums[3] = sl.fsums[5];
+  return st;
+}
+template <int D>
+static int slice_grad_phase3_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec) {
+  gpar_ctx::SliceState& sl = ctx->slice;
+  const int Mpad = sl.Mpad;
+  CHK(scaled_tangent_d<D>(ctx, st, Pm, wvec, nullptr, nullptr, nullptr, 1));
+  const size_t state_doubles = (size_t)sl.nch * D * Mpad;
+  double* tstate = sl.psi + (size_t)sl.nch * D * D + (size_t)sl.nch * Mpad + Mpad;
+  for (int q = 0; q < 3; q++)
+    LAUNCH(ctx, slice_summary_kernel<D>, (Mpad + 31) / 32, 32, 0, sl.psi, tstate + q * state_doubles, sl.nch, Mpad, sl.summary2 + q * sl.summary_count);
+  return GPAR_OK;
+}
+int scaled_slice_grad_phase3(gpar_ctx* ctx) {
+  CU(cudaSetDevice(ctx->device));
+  gpar_ctx::SliceState& sl = ctx->slice;
+  CU(cudaMemcpyAsync(sl.fsums, sl.sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));      // [sum log S, 2 tangents, sum alpha^2, 2 tangents]
+  CU(cudaStreamSynchronize(ctx->stream));
+  const double* pv = sl.pv;
+  const double out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
+  GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
+  double g3[3];
+  CHK(dtc_tail(ctx, sl.k_out, p, 0, noise, sl.nfull, sl.G, nullptr, sl.g, nullptr, sl.fsums[3], &sl.val, g3, sl.raw));
+  TailBufs tb;
+  CHK(tail_layout(ctx, true, 0, &tb));
+  const ScaledStats st = slice_as_stats(ctx);
+  switch (sl.D) {
+    case 1: return slice_grad_phase3_d<1>(ctx, st, tb.Pm, tb.wvec);
+    case 2: return slice_grad_phase3_d<2>(ctx, st, tb.Pm, tb.wvec);
+    default: return slice_grad_phase3_d<3>(ctx, st, tb.Pm, tb.wvec);
+  }
+}
+template <int D>
+static int slice_grad_phase4_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec, const double* gathered2, int member, double* s5) {
+  gpar_ctx::SliceState& sl = ctx->slice;
+  const int Mpad = sl.Mpad;
+  for (int q = 0; q < 3; q++)
+    LAUNCH(ctx, slice_entering_kernel<D>, (Mpad + 31) / 32, 32, 0, gathered2 + q * sl.summary_count, member, Mpad, sl.init2 + (size_t)q * D * Mpad,
+           (int64_t)(3 * sl.summary_count));
+  return scaled_tangent_d<D>(ctx, st, Pm, wvec, s5, nullptr, nullptr, 2, sl.init2, sl.nfull);
+}
+int scaled_slice_grad_phase4(gpar_ctx* ctx, const double* gathered2, int member, double s5[5]) {
+  CU(cudaSetDevice(ctx->device));
+  TailBufs tb;
+  CHK(tail_layout(ctx, true, 0, &tb));
+  const ScaledStats st = slice_as_stats(ctx);
+  switch (ctx->slice.D) {
+    case 1: return slice_grad_phase4_d<1>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
+    case 2: return slice_grad_phase4_d<2>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
+    default: return slice_grad_phase4_d<3>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
+  }
+}
+int scaled_slice_grad_finish(gpar_ctx* ctx, const double s5[5], double* dtc, double* grad) {
+  const gpar_ctx::SliceState& sl = ctx->slice;
+  const double dsums[4] = {sl.fsums[1], sl.fsums[2], sl.fsums[4], sl.fsums[5]};
+  assemble_scaled_grad(sl.nfull, sl.val, sl.raw, dsums, sl.fsums[0], sl.fsums[3], s5, sl.pv, sl.ex, dtc, grad);
   return GPAR_OK;
 }
 
@@ -1328,20 +1451,7 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
     default: CHK(scaled_tangent_d<3>(ctx, st, tb.Pm, tb.wvec, s5)); break;
   }
   timer.stop();
-  *dtc = val - 0.5 * st.sum_logS;
-  const double* t = raw + 8;
-  const double cc = raw[2];
-  const double trTG = t[2] + t[3], trTKdK = t[4] + t[5] - t[6], trTKK = t[7] + t[8] - t[9], trTK = t[10] + t[12] - t[11], gw = t[16];
-  const double F_os = (-trTG + gw - 0.5 * (trTKK - noise * trTK)) / out_s;
-  const double F_logl = s5[2] - 0.5 * trTKdK;
-  const double F_tl = s5[0] - s5[3] - 0.5 * st.dsums[0];
-  const double F_noise = (s5[1] - s5[4] - 0.5 * st.dsums[1]) - 0.5 * trTK;
-  const double F_ts = (-0.5 * ((double)N - (st.sum_a2 - cc)) - out_s * F_os - noise * F_noise) / time_s;
-  grad[0] = F_tl * ex[0];
-  grad[1] = F_ts * 2.0 * pv[1] * ex[1];
-  grad[2] = F_logl / out_l * ex[2];
-  grad[3] = F_os * 2.0 * pv[3] * ex[3];
-  grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+  assemble_scaled_grad(N, val, raw, st.dsums, st.sum_logS, st.sum_a2, s5, pv, ex, dtc, grad);
   return GPAR_OK;
 }
 

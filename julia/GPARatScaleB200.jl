@@ -241,11 +241,11 @@ end
 
 # ONE scaled-GPAR objective (compute_gpar_dtc_objective, dtc.jl:83-128) whose rows are sharded over the members: every member
 # holds the full (t, y) and Z and rows row_lo[i]+1 : row_lo[i]+N_i of the inputs (row_lo zero-based, multiples of 4)
-function group_scaled_dtc_sharded(g::Group, k_time, k_out, theta::Vector{Float64}, row_lo::Vector{Int64})
-    val = Ref{Float64}(0.0)
-    gcheck(g, ccall((:gpar_group_scaled_dtc_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Int64}, Ref{Float64}),
-                    g.h, kernel_code(k_time), kernel_code(k_out), theta, row_lo, val))
-    return val[]
+function group_scaled_dtc_sharded(g::Group, k_time, k_out, theta::Vector{Float64}, row_lo::Vector{Int64}; grad::Bool = false)
+    val = Ref{Float64}(0.0); gr = grad ? zeros(5) : nothing
+    gcheck(g, ccall((:gpar_group_scaled_dtc_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Int64}, Ref{Float64}, Ptr{Float64}),
+                    g.h, kernel_code(k_time), kernel_code(k_out), theta, row_lo, val, grad ? gr : C_NULL))
+    return grad ? (val[], gr) : val[]
 end
 
 # whole Nelder-Mead fits of the chain's conditional GPs; Xs[k] (D x N) / Zs[k] (D x M) are `nothing` for a time-only task

@@ -212,6 +212,10 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
             lo = g.load_row_slices(X, Z, t, y, bounds)
             v = g.scaled_dtc_sharded(kt, ko, th, lo)
             assert abs(v - v0) <= 1e-11 * abs(v0), (nmem, n, m, bounds, v, v0)
+            # value + gradient: forward-mode tangents per slice, tangent carries over the slice boundaries (second all-gather)
+            vg0, g0 = ctx.scaled_dtc_grad(kt, ko, th)
+            vg, gr = g.scaled_dtc_sharded(kt, ko, th, lo, grad=True)
+            assert abs(vg - vg0) <= 1e-11 * abs(vg0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0)), (nmem, n, m, bounds, gr, g0)
         # default (equal) slices and the error behaviour
         n, m = 20000, 64
         t = np.arange(n) / 30.0; X = rng.normal(size=(n, 2)); Z = rng.normal(size=(m, 2)); y = rng.normal(size=n)
@@ -223,6 +227,8 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
         thi = np.array([0.2, 0.1, 1.5, 7.0, -1.0])
         vi0 = ctx.scaled_dtc(3, 3, thi)
         assert abs(g.scaled_dtc_sharded(3, 3, thi, lo) - vi0) <= 1e-9 * abs(vi0)
+        with pytest.raises(gp.GparError, match="poorly conditioned"):      # the sharded gradient is the collapsed form: it refuses that corner
+            g.scaled_dtc_sharded(3, 3, thi, lo, grad=True)
         if nmem > 1:
             bad = lo.copy(); bad[1] += 4
             with pytest.raises(gp.GparError, match="starts at row"):
@@ -269,6 +275,9 @@ def test_group_scaled_dtc_row_sharded_devices(ctx):
         lo = g.load_row_slices(X, Z, t, y)
         v = g.scaled_dtc_sharded(3, 3, th, lo)
         assert abs(v - v0) <= 1e-11 * abs(v0), (v, v0)
+        vg0, g0 = ctx.scaled_dtc_grad(3, 3, th)
+        vg, gr = g.scaled_dtc_sharded(3, 3, th, lo, grad=True)
+        assert abs(vg - vg0) <= 1e-11 * abs(vg0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0)), (gr, g0)
     finally:
         g.close()
 
