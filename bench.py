@@ -360,6 +360,15 @@ def run_gpar_fit(ctx, gp, world, rank, local, iterations, side_group):
                     "speedup": float(np.median(one[1:]) / np.median(sh[2:])), "value_one_device": repr(v1), "value_sharded": repr(vs),
                     "rel_diff": float(abs(vs - v1) / abs(v1)), "scaling": "strong",
                     "collective_bytes_per_evaluation": int(8 * (M * M + M + world * (9 + 3 * M)))}
+                try:        # value + gradient, row-sharded (a second all-gather carries the tangent states over the slice boundaries)
+                    shg = []
+                    for _ in range(4):
+                        t1 = time.perf_counter(); vg, gg = g.scaled_dtc_sharded(gp.MATERN52, gp.MATERN52, th5, lo, grad=True); shg.append(time.perf_counter() - t1)
+                    out["sharded_scaled_objective"]["ms_sharded_value_and_grad"] = float(np.median(shg[1:]) * 1e3)
+                    out["sharded_scaled_objective"]["grad_sharded"] = [float(x) for x in gg]
+                    out["sharded_scaled_objective"]["value_rel_diff_grad_call"] = float(abs(vg - v1) / abs(v1))
+                except Exception as e:
+                    out["sharded_scaled_objective"]["grad_error"] = repr(e)
                 # weak scaling of the same call: 1 048 576 rows per device (8 GPUs: N = 8 388 608, M = 2048 — an operand panel of
                 # 137 GB that no single device could hold next to this bench's own buffers)
                 Nw = 1_048_576 * world

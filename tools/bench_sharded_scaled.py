@@ -43,6 +43,19 @@ for _ in range(a.steps):
 res["value"] = float(np.median(ts) * 1e3); res["value_sharded"] = repr(v)
 if not a.no_single:
     res["speedup"] = res["ms_one_device"] / res["value"]; res["rel_diff"] = abs(v - v1) / abs(v1)
-res["member_device_ms"] = [m.last_timing()[0] for m in g.members]
+ts = []
+for _ in range(a.steps):
+    t0 = time.perf_counter(); vg, gr = g.scaled_dtc_sharded(3, 3, th, lo, grad=True); ts.append(time.perf_counter() - t0)
+res["ms_sharded_value_and_grad"] = float(np.median(ts[1:]) * 1e3); res["grad_sharded"] = gr.tolist()
+if not a.no_single:
+    ctx = gp.Context(0)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); v1g, g1 = ctx.scaled_dtc_grad(3, 3, th); ts.append(time.perf_counter() - t0)
+    res["ms_one_device_value_and_grad"] = float(np.median(ts[1:]) * 1e3)
+    res["grad_rel_diff"] = float(np.max(np.abs(gr - g1)) / np.max(np.abs(g1)))
+    res["grad_speedup"] = res["ms_one_device_value_and_grad"] / res["ms_sharded_value_and_grad"]
+    ctx.close()
 print(json.dumps(res))
 g.close()
