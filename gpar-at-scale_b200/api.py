@@ -361,7 +361,7 @@ def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_l
                                  iterations=1000, return_result=False, optimizer="neldermead", n_restarts=1, speculative=False, group=None):
     """dtc.jl:11-77 -> (time_l, time_var, out_l, out_var, noise_sigma).  group (NEW; a context.Group): the ROWS of this one
     objective are sharded over the group's devices (gpar_group_scaled_dtc_sharded) — for a single output too large for one
-    device's time or memory budget; plain Nelder-Mead only.
+    device's time or memory budget; plain Nelder-Mead or optimizer="lbfgs" (sharded gradient).
     A failed Cholesky: the plain Nelder-Mead path raises PosDefException, as the reference's nlml (dtc.jl:29-48, no
     try / catch) would; the NEW paths (lbfgs, n_restarts, speculative, the C++ group fits) read it as +Inf for that point.
     optimizer="lbfgs" replaces the
@@ -373,12 +373,18 @@ def get_optim_scaled_gpar_params(input_locations, pseudo_input_locations, time_l
     the simplices, the optimum and f_calls of the plain run at ~2/3 of its wall-clock at the reference's sizes."""
     out_kernel = out_kernel or Matern52(); time_kernel = time_kernel or Matern52()
     if group is not None:
-        if optimizer != "neldermead" or n_restarts > 1 or speculative:
-            raise ValueError("group=: the row-sharded objective is driven by the plain Nelder-Mead path only")
+        if n_restarts > 1 or speculative:
+            raise ValueError("group=: the row-sharded objective is driven by plain Nelder-Mead or L-BFGS, one run")
         row_lo = group.load_row_slices(to_ColVecs(input_locations), to_ColVecs(pseudo_input_locations), time_loc, outputs)
 
         def nlml(params):
             return -group.scaled_dtc_sharded(time_kernel.code, out_kernel.code, params, row_lo)
+
+        class _Sharded:      # what the L-BFGS branch below asks of a context
+            @staticmethod
+            def scaled_dtc_grad(k_time, k_out, p_):
+                return group.scaled_dtc_sharded(k_time, k_out, p_, row_lo, grad=True)
+        ctx = _Sharded
     else:
         ctx = ctx or default_context()
         ctx.set_inputs(to_ColVecs(input_locations)); ctx.set_pseudo(to_ColVecs(pseudo_input_locations))

@@ -299,8 +299,17 @@ def test_fit_through_the_row_sharded_objective(ctx):
     finally:
         g.close()
     assert abs(r3.minimum - r1.minimum) <= 1e-6 * abs(r1.minimum), (r1.minimum, r3.minimum)
+    # L-BFGS on the sharded gradient against L-BFGS on one device
+    kw["iterations"] = 15
+    _, l1 = api.get_optim_scaled_gpar_params(X, Z, t, y, ctx=ctx, optimizer="lbfgs", **kw)
+    g = _loopback_group(2)
+    try:
+        _, l2 = api.get_optim_scaled_gpar_params(X, Z, t, y, group=g, optimizer="lbfgs", **kw)
+    finally:
+        g.close()
+    assert abs(l2.minimum - l1.minimum) <= 1e-6 * abs(l1.minimum), (l1.minimum, l2.minimum)
     with pytest.raises(ValueError):
-        api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), optimizer="lbfgs")
+        api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), n_restarts=4)
 
 
 def test_group_abi_error_behaviour():
