@@ -93,7 +93,7 @@ struct gpar_ctx {
     // host-side pieces of the final assembly
     bool grad = false; int64_t nfull = 0; int k_out = 0;
     const double *dtable = nullptr, *dalpha = nullptr; double *evec = nullptr, *panelD = nullptr, *summary2 = nullptr, *init2 = nullptr;
-    double pv[5] = {0}, ex[5] = {0}, val = 0.0, raw[8 + 20] = {0}, fsums[6] = {0};
+    double pv[5] = {0}, ex[5] = {0}, val = 0.0, raw[8 + 20] = {0}, fsums[6] = {0}, wq[4] = {0};      // wq: tr Q, <W,Q>, <X,Q>, c'c (whitened tail)
   } slice;
   // SYRK plan cache: the (tiles, k-blocks, with_h) of the plan currently resident in `segs`/`jobs`
   int plan_T = -1, plan_h = -1, plan_C = 0, plan_J = 0; int64_t plan_NBK = -1; size_t plan_nseg = 0;

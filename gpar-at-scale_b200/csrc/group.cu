@@ -302,7 +302,8 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
 // panel, whitening passes, SYRK) is sliced; the filter carry of the M whitened columns crosses the slice boundaries through
 // ONE all-gather of the slice summaries (D x D transition product + D x M exit state each), and ONE all-reduce sums
 // (G, g) before member 0 runs the M x M tail: 8 (M^2 + M + n (D^2 + D M)) bytes per evaluation on NVLink.
-// grad (nullable): the five raw-parameter derivatives (gpar_scaled_dtc_grad) — one more all-gather (three tangent summaries).
+// grad (nullable): the five raw-parameter derivatives (gpar_scaled_dtc_grad) — one more all-gather (three tangent summaries);
+// poorly conditioned cov(u): whitened coordinates on every slice, as gpar_scaled_dtc_grad does on one device.
 int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val, double* grad) {
   if (!g) return GPAR_ERR_INVALID;
   if (!theta || !row_lo || !val) return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: theta, row_lo and val must not be NULL");
@@ -328,20 +329,6 @@ int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const do
   run_members(g, st, [&](int i) { return scaled_slice_phase1(g->ctx[i], k_time, k_out, theta, row_lo[i], want_grad); });
   int rc = members_ok();
   if (rc != GPAR_OK) return rc;
-  if (want_grad) {
-    // the analytic gradient of the sharded path is the collapsed form (statistic beta'beta, explicit (cov(u) + G)^-1): refuse
-    // the poorly conditioned corner instead of returning cond * eps garbage — one device handles it in whitened coordinates
-    TailBufs tb;
-    GCU(cudaSetDevice(g->dev[0]));
-    rc = tail_layout(c0, true, 0, &tb);
-    if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
-    double mm[2] = {1.0, 1.0};
-    GCU(cudaMemcpyAsync(mm, tb.sc + 4, sizeof(mm), cudaMemcpyDeviceToHost, c0->stream2));
-    GCU(cudaStreamSynchronize(c0->stream2));
-    if (gpar_needs_whitened_panel(mm))
-      return group_fail(g, GPAR_ERR_INVALID, "scaled_dtc_sharded: cov(u) is too poorly conditioned for the row-sharded gradient ((max/min diag L_u)^2 = %.3g > "
-                        "GPAR_ROBUST_COND); the sharded VALUE and the one-device gradient (gpar_scaled_dtc_grad) handle it", (mm[1] / mm[0]) * (mm[1] / mm[0]));
-  }
   const size_t sc = c0->slice.summary_count;
   std::vector<const double*> sp(n); std::vector<double*> rp(n), stats(n);
   for (int i = 0; i < n; i++) {

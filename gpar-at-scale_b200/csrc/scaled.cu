@@ -1054,6 +1054,27 @@ static int scaled_value_tail(gpar_ctx* ctx, const double* Lu, double* Bm, const 
   return GPAR_OK;
 }
 
+// The hook of the whitened-coordinate gradient: A = L_u^-1 beta' goes into a SECOND panel (the tangent kernels still need beta),
+// and the SYRK is pointed at it.  decide != NULL: whiten only if the conditioning estimate (minmax_dev) asks for it.
+static PanelHook make_whitened_copy_hook(gpar_ctx* ctx, const double* Lu, const double* minmax_dev, bool* decide) {
+  return [ctx, Lu, minmax_dev, decide](double*& panel, int64_t Npad, int Mpad) -> int {
+    if (decide) {
+      double mm[2] = {1.0, 1.0};
+      CU(cudaMemcpyAsync(mm, minmax_dev, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream2));
+      CU(cudaStreamSynchronize(ctx->stream2));
+      *decide = gpar_needs_whitened_panel(mm);
+      if (const char* e = getenv("GPAR_GRAD_WHITENED")) { if (atoi(e) != 0) *decide = true; }
+      if (!*decide) return GPAR_OK;
+    }
+    CU(ctx->panelA.reserve((size_t)Npad * Mpad * sizeof(double)));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    CU(cudaMemcpyAsync(ctx->panelA.p, panel, (size_t)Npad * Mpad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CHK(panel_left_solve(ctx, ctx->panelA.as<double>(), Npad, Mpad, (int)ctx->M, Lu));
+    panel = ctx->panelA.as<double>();
+    return GPAR_OK;
+  };
+}
+
 // ---- row-sliced evaluation: the three steps group.cu drives around its two collectives --------------------------------
 struct SliceTailBufs { double *Lu, *Bm, *V, *Tm, *cvec, *sc; int* dinfo; };
 static int slice_tail_bufs(gpar_ctx* ctx, SliceTailBufs* b) {
@@ -1093,11 +1114,14 @@ int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta
 }
 int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member) {
   CU(cudaSetDevice(ctx->device));
-  if (ctx->slice.grad) {      // gradient mode: well-conditioned cov(u) only (checked by the caller) — no L_u-whitening of the panel
+  if (ctx->slice.grad) {      // gradient mode: a poorly conditioned cov(u) sends the SYRK to a whitened COPY of the slice's panel
+    TailBufs tb;
+    CHK(tail_layout(ctx, true, 0, &tb));
+    PanelHook hook = make_whitened_copy_hook(ctx, tb.Lu, tb.sc + 4, &ctx->slice.robust);
     switch (ctx->slice.D) {
-      case 1: return scaled_slice_phase2_d<1>(ctx, gathered, member, nullptr);
-      case 2: return scaled_slice_phase2_d<2>(ctx, gathered, member, nullptr);
-      default: return scaled_slice_phase2_d<3>(ctx, gathered, member, nullptr);
+      case 1: return scaled_slice_phase2_d<1>(ctx, gathered, member, &hook);
+      case 2: return scaled_slice_phase2_d<2>(ctx, gathered, member, &hook);
+      default: return scaled_slice_phase2_d<3>(ctx, gathered, member, &hook);
     }
   }
   SliceTailBufs b;
@@ -1148,6 +1172,24 @@ static void assemble_scaled_grad(int64_t N, double val, const double* raw, const
   grad[4] = F_noise * 2.0 * pv[4] * ex[4];
 }
 
+// The same in whitened coordinates (ill-conditioned cov(u)): d cov(u) = (cov(u) - noise I) d out_s / out_s +
+// l dKuu/dl d log l + I d noise, each contracted as -1/2 <L_u^-1 . L_u^-T, Q>; <R, beta> = tr Q for the out_s scale of beta
+static void assemble_scaled_grad_whitened(int64_t N, double val, double trQ, double WQ, double XQ, double cc, const double dsums[4], double sum_logS,
+                                          double sum_a2, const double s5[5], const double pv[5], const double ex[5], double* dtc, double* grad) {
+  const double time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
+  *dtc = val - 0.5 * sum_logS;
+  const double F_os = 0.5 * (trQ + noise * WQ) / out_s;
+  const double F_logl = s5[2] - 0.5 * XQ;
+  const double F_tl = s5[0] - s5[3] - 0.5 * dsums[0];
+  const double F_noise = (s5[1] - s5[4] - 0.5 * dsums[1]) - 0.5 * WQ;
+  const double F_ts = (-0.5 * ((double)N - (sum_a2 - cc)) - out_s * F_os - noise * F_noise) / time_s;
+  grad[0] = F_tl * ex[0];
+  grad[1] = F_ts * 2.0 * pv[1] * ex[1];
+  grad[2] = F_logl / out_l * ex[2];
+  grad[3] = F_os * 2.0 * pv[3] * ex[3];
+  grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+}
+
 static_assert(GPAR_NTR == 20, "gpar_ctx::SliceState::raw is sized for 8 + 20 scalars");
 static ScaledStats slice_as_stats(gpar_ctx* ctx) {
   const gpar_ctx::SliceState& sl = ctx->slice;
@@ -1159,11 +1201,17 @@ static ScaledStats slice_as_stats(gpar_ctx* ctx) {
   st.dsums[0] = sl.fsums[1]; st.dsums[1] = sl.fsums[2]; st.dsums[2] = sl.fsums[4]; st.dsums[3] = sl.fsums[5];
   return st;
 }
+static const double* tail_wt(gpar_ctx* ctx) {      // where dtc_tail_whitened leaves wt = Lambda^-1 A alpha (see its buffer use)
+  TailBufs tb;
+  if (tail_layout(ctx, true, 0, &tb) != GPAR_OK) return nullptr;
+  return tb.cvec + 2 * (size_t)ctx->M;
+}
 template <int D>
 static int slice_grad_phase3_d(gpar_ctx* ctx, const ScaledStats& st, const double* Pm, const double* wvec) {
   gpar_ctx::SliceState& sl = ctx->slice;
   const int Mpad = sl.Mpad;
-  CHK(scaled_tangent_d<D>(ctx, st, Pm, wvec, nullptr, nullptr, nullptr, 1));
+  const double* wtv = sl.robust ? tail_wt(ctx) : nullptr;      // residual e = alpha - A'wt on the whitened panel
+  CHK(scaled_tangent_d<D>(ctx, st, Pm, wvec, nullptr, sl.robust ? ctx->panelA.as<double>() : nullptr, wtv, 1));
   const size_t state_doubles = (size_t)sl.nch * D * Mpad;
   double* tstate = sl.psi + (size_t)sl.nch * D * D + (size_t)sl.nch * Mpad + Mpad;
   for (int q = 0; q < 3; q++)
@@ -1178,15 +1226,23 @@ int scaled_slice_grad_phase3(gpar_ctx* ctx) {
   const double* pv = sl.pv;
   const double out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
   GpParams p{}; p.l = out_l; p.var = pv[3]; p.s = out_s; p.sigma = 1.0; p.noise = 1.0; p.dl = p.ds_dv = p.dn = 1.0;
-  double g3[3];
-  CHK(dtc_tail(ctx, sl.k_out, p, 0, noise, sl.nfull, sl.G, nullptr, sl.g, nullptr, sl.fsums[3], &sl.val, g3, sl.raw));
   TailBufs tb;
   CHK(tail_layout(ctx, true, 0, &tb));
   const ScaledStats st = slice_as_stats(ctx);
+  const double* Pm = tb.Pm; const double* wvec = tb.wvec;
+  if (sl.robust) {      // whitened coordinates: (G, g) are the statistics of A = L_u^-1 beta' (G) and of beta (g)
+    WhitenedTail wt;
+    CHK(dtc_tail_whitened(ctx, p, 0, noise, sl.nfull, sl.G, nullptr, sl.g, nullptr, sl.fsums[3], &sl.val, nullptr, &wt));
+    sl.wq[0] = wt.trQ; sl.wq[1] = wt.WQ; sl.wq[2] = wt.XQ; sl.wq[3] = wt.cc;
+    Pm = wt.Cop; wvec = wt.w;
+  } else {
+    double g3[3];
+    CHK(dtc_tail(ctx, sl.k_out, p, 0, noise, sl.nfull, sl.G, nullptr, sl.g, nullptr, sl.fsums[3], &sl.val, g3, sl.raw));
+  }
   switch (sl.D) {
-    case 1: return slice_grad_phase3_d<1>(ctx, st, tb.Pm, tb.wvec);
-    case 2: return slice_grad_phase3_d<2>(ctx, st, tb.Pm, tb.wvec);
-    default: return slice_grad_phase3_d<3>(ctx, st, tb.Pm, tb.wvec);
+    case 1: return slice_grad_phase3_d<1>(ctx, st, Pm, wvec);
+    case 2: return slice_grad_phase3_d<2>(ctx, st, Pm, wvec);
+    default: return slice_grad_phase3_d<3>(ctx, st, Pm, wvec);
   }
 }
 template <int D>
@@ -1196,23 +1252,25 @@ static int slice_grad_phase4_d(gpar_ctx* ctx, const ScaledStats& st, const doubl
   for (int q = 0; q < 3; q++)
     LAUNCH(ctx, slice_entering_kernel<D>, (Mpad + 31) / 32, 32, 0, gathered2 + q * sl.summary_count, member, Mpad, sl.init2 + (size_t)q * D * Mpad,
            (int64_t)(3 * sl.summary_count));
-  return scaled_tangent_d<D>(ctx, st, Pm, wvec, s5, nullptr, nullptr, 2, sl.init2, sl.nfull);
+  return scaled_tangent_d<D>(ctx, st, Pm, wvec, s5, sl.robust ? ctx->panelA.as<double>() : nullptr, sl.robust ? tail_wt(ctx) : nullptr, 2, sl.init2, sl.nfull);
 }
 int scaled_slice_grad_phase4(gpar_ctx* ctx, const double* gathered2, int member, double s5[5]) {
   CU(cudaSetDevice(ctx->device));
   TailBufs tb;
   CHK(tail_layout(ctx, true, 0, &tb));
   const ScaledStats st = slice_as_stats(ctx);
+  const double* Pm = ctx->slice.robust ? tb.Kj : tb.Pm;      // whitened: the operand L_u^-T Lambda^-1 (dtc_tail_whitened's Cop)
   switch (ctx->slice.D) {
-    case 1: return slice_grad_phase4_d<1>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
-    case 2: return slice_grad_phase4_d<2>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
-    default: return slice_grad_phase4_d<3>(ctx, st, tb.Pm, tb.wvec, gathered2, member, s5);
+    case 1: return slice_grad_phase4_d<1>(ctx, st, Pm, tb.wvec, gathered2, member, s5);
+    case 2: return slice_grad_phase4_d<2>(ctx, st, Pm, tb.wvec, gathered2, member, s5);
+    default: return slice_grad_phase4_d<3>(ctx, st, Pm, tb.wvec, gathered2, member, s5);
   }
 }
 int scaled_slice_grad_finish(gpar_ctx* ctx, const double s5[5], double* dtc, double* grad) {
   const gpar_ctx::SliceState& sl = ctx->slice;
   const double dsums[4] = {sl.fsums[1], sl.fsums[2], sl.fsums[4], sl.fsums[5]};
-  assemble_scaled_grad(sl.nfull, sl.val, sl.raw, dsums, sl.fsums[0], sl.fsums[3], s5, sl.pv, sl.ex, dtc, grad);
+  if (sl.robust) assemble_scaled_grad_whitened(sl.nfull, sl.val, sl.wq[0], sl.wq[1], sl.wq[2], sl.wq[3], dsums, sl.fsums[0], sl.fsums[3], s5, sl.pv, sl.ex, dtc, grad);
+  else assemble_scaled_grad(sl.nfull, sl.val, sl.raw, dsums, sl.fsums[0], sl.fsums[3], s5, sl.pv, sl.ex, dtc, grad);
   return GPAR_OK;
 }
 
@@ -1404,14 +1462,7 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
     TailBufs tb;
     CHK(tail_layout(ctx, true, 0, &tb));
     const double* Lu = tb.Lu;
-    PanelHook hook = [ctx, Lu](double*& panel, int64_t Npad, int Mpad) -> int {
-      CU(ctx->panelA.reserve((size_t)Npad * Mpad * sizeof(double)));
-      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-      CU(cudaMemcpyAsync(ctx->panelA.p, panel, (size_t)Npad * Mpad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-      CHK(panel_left_solve(ctx, ctx->panelA.as<double>(), Npad, Mpad, (int)ctx->M, Lu));
-      panel = ctx->panelA.as<double>();
-      return GPAR_OK;
-    };
+    PanelHook hook = make_whitened_copy_hook(ctx, Lu, nullptr, nullptr);
     ScaledStats st;
     CHK(scaled_stats(ctx, k_time, k_out, time_l, time_s, out_l, out_s, noise, &st, true, &hook));
     double val = 0.0; WhitenedTail wt;
@@ -1423,19 +1474,7 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
       default: CHK(scaled_tangent_d<3>(ctx, st, wt.Cop, wt.w, s5, st.syrk_panel, wt.wt)); break;
     }
     timer.stop();
-    *dtc = val - 0.5 * st.sum_logS;
-    // d cov(u) = (cov(u) - noise I) d out_s / out_s + l dKuu/dl d log l + I d noise, each contracted as -1/2 <L_u^-1 . L_u^-T, Q>;
-    // <R, beta> = tr Q for the out_s scale of beta
-    const double F_os = 0.5 * (wt.trQ + noise * wt.WQ) / out_s;
-    const double F_logl = s5[2] - 0.5 * wt.XQ;
-    const double F_tl = s5[0] - s5[3] - 0.5 * st.dsums[0];
-    const double F_noise = (s5[1] - s5[4] - 0.5 * st.dsums[1]) - 0.5 * wt.WQ;
-    const double F_ts = (-0.5 * ((double)N - (st.sum_a2 - wt.cc)) - out_s * F_os - noise * F_noise) / time_s;
-    grad[0] = F_tl * ex[0];
-    grad[1] = F_ts * 2.0 * pv[1] * ex[1];
-    grad[2] = F_logl / out_l * ex[2];
-    grad[3] = F_os * 2.0 * pv[3] * ex[3];
-    grad[4] = F_noise * 2.0 * pv[4] * ex[4];
+    assemble_scaled_grad_whitened(N, val, wt.trQ, wt.WQ, wt.XQ, wt.cc, st.dsums, st.sum_logS, st.sum_a2, s5, pv, ex, dtc, grad);
     return GPAR_OK;
   }
   ScaledStats st;

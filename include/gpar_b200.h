@@ -232,7 +232,7 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
  * runs the M x M tail.  A poorly conditioned cov(u) is handled as on one device (every member whitens its panel by L_u).
  * GPAR_GROUP_LOOPBACK=1 lets gpar_group_create put several members on ONE device (collectives become device copies).
  * grad (nullable): the five derivatives of gpar_scaled_dtc_grad — forward-mode tangents per slice, a second all-gather of three
- * tangent summaries; well-conditioned cov(u) only (GPAR_ERR_INVALID otherwise: the one-device gradient handles that corner). */
+ * tangent summaries; a poorly conditioned cov(u) switches every slice to whitened coordinates (a whitened copy of its panel). */
 int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val, double* grad);
 
 /* One conditional-GP fit of the chain: inputs X (D x N ColVecs = the observed earlier outputs; D = 0: a time-only

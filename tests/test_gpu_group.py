@@ -227,8 +227,17 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
         thi = np.array([0.2, 0.1, 1.5, 7.0, -1.0])
         vi0 = ctx.scaled_dtc(3, 3, thi)
         assert abs(g.scaled_dtc_sharded(3, 3, thi, lo) - vi0) <= 1e-9 * abs(vi0)
-        with pytest.raises(gp.GparError, match="poorly conditioned"):      # the sharded gradient is the collapsed form: it refuses that corner
-            g.scaled_dtc_sharded(3, 3, thi, lo, grad=True)
+        # ... and its gradient in whitened coordinates on every slice (a whitened copy of the slice's panel), as on one device
+        vgi0, gi0 = ctx.scaled_dtc_grad(3, 3, thi)
+        vgi, gi = g.scaled_dtc_sharded(3, 3, thi, lo, grad=True)
+        assert abs(vgi - vgi0) <= 1e-9 * abs(vgi0) and np.max(np.abs(gi - gi0)) <= 1e-6 * np.max(np.abs(gi0)), (gi, gi0)
+        os.environ["GPAR_GRAD_WHITENED"] = "1"                  # forced on the well-conditioned problem: equals the collapsed form
+        try:
+            vgw, gw = g.scaled_dtc_sharded(3, 3, th, lo, grad=True)
+        finally:
+            del os.environ["GPAR_GRAD_WHITENED"]
+        vg0, g0 = ctx.scaled_dtc_grad(3, 3, th)
+        assert abs(vgw - vg0) <= 1e-10 * abs(vg0) and np.max(np.abs(gw - g0)) <= 1e-8 * np.max(np.abs(g0)), (gw, g0)
         if nmem > 1:
             bad = lo.copy(); bad[1] += 4
             with pytest.raises(gp.GparError, match="starts at row"):
