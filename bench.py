@@ -318,6 +318,31 @@ def run_gpar_fit(ctx, gp, world, rank, local, iterations, side_group):
            "best_nlml_per_output": {str(o): repr(best[o][0]) for o in sorted(best)},
            "optima_checksum": repr(float(np.sum(vals))),
            "identical_optima_note": "every task is a deterministic Nelder-Mead run on its own data: best_nlml_per_output / optima_checksum must be bit-identical for every --gpus"}
+    # ONE scaled objective (the last output's, D = P - 1) with its ROWS sharded over the ranks: one process per GPU, the two
+    # (gradient: three) exchanges through torch.distributed / NCCL (parallel.scaled_dtc_row_sharded over the gpar_scaled_slice_*
+    # C ABI) — strong scaling of a single evaluation; the one-device time of the same call is in sharded_scaled_objective below
+    if world > 1:
+        from gpar_at_scale_b200 import parallel
+        o = P - 1
+        Xo = np.ascontiguousarray(Y[:o].T); Zo = chain.strided_pseudo_inputs(Xo, M)
+        th5 = np.log([2.0, 0.5, 1.0, 1.0, 0.1])
+        bnd = parallel.row_slice_bounds(N, world)
+        ctx.set_times(t); ctx.set_outputs(Y[o]); ctx.set_pseudo(Zo); ctx.set_inputs(np.ascontiguousarray(Xo[bnd[rank]:bnd[rank + 1]])); ctx.set_noise_vector(None)
+        dev = torch.device("cuda", local)
+
+        def timed(fn, n, skip):
+            ts = []
+            for _ in range(n):
+                sync(); t1 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t1)
+            tt = torch.tensor([float(np.median(ts[skip:]))], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return r, float(tt.item()) * 1e3
+        vsh, ms_v = timed(lambda: parallel.scaled_dtc_row_sharded(ctx, gp.MATERN52, gp.MATERN52, th5, bnd[rank], device=dev), 5, 2)
+        (vgs, g5s), ms_g = timed(lambda: parallel.scaled_dtc_row_sharded(ctx, gp.MATERN52, gp.MATERN52, th5, bnd[rank], grad=True, device=dev), 4, 1)
+        out["sharded_scaled_objective_torchrun"] = {
+            "path": "parallel.scaled_dtc_row_sharded: %d ranks (one process per GPU), rows of ONE objective (N=%d, M=%d, D=%d) sliced; NCCL all-gather of slice summaries + all-reduce of (G, g) [+ all-gather of tangent summaries]" % (world, N, M, o),
+            "ms_value": ms_v, "ms_value_and_grad": ms_g, "value": repr(vsh), "grad": [float(x) for x in g5s], "scaling": "strong",
+            "timing": "max over ranks of the median wall-clock per call, barrier + device synchronisation on both sides"}
     # one process, all devices: the restart-0 task of every output through gpar_group_fit (dynamic hand-out over the
     # members, C++ Nelder-Mead twin) — must reproduce the torchrun path's optima for those tasks exactly
     if world > 1:
@@ -360,6 +385,11 @@ def run_gpar_fit(ctx, gp, world, rank, local, iterations, side_group):
                     "speedup": float(np.median(one[1:]) / np.median(sh[2:])), "value_one_device": repr(v1), "value_sharded": repr(vs),
                     "rel_diff": float(abs(vs - v1) / abs(v1)), "scaling": "strong",
                     "collective_bytes_per_evaluation": int(8 * (M * M + M + world * (9 + 3 * M)))}
+                tr = out.get("sharded_scaled_objective_torchrun")
+                if tr:
+                    tr["ms_value_one_device"] = out["sharded_scaled_objective"]["ms_one_device"]
+                    tr["speedup_value"] = tr["ms_value_one_device"] / tr["ms_value"]
+                    tr["value_rel_diff_vs_one_device"] = float(abs(float(tr["value"]) - v1) / abs(v1))
                 try:        # value + gradient, row-sharded (a second all-gather carries the tangent states over the slice boundaries)
                     shg = []
                     for _ in range(4):

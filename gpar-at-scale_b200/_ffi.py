@@ -69,6 +69,14 @@ SIGNATURES = {
                                              _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32)]),
     "gpar_group_dtc_logpdf_sharded": (ctypes.c_int, [_c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p, _c_double_p]),
     "gpar_group_scaled_dtc_sharded": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_int64), _c_double_p, _c_double_p]),
+    "gpar_scaled_slice_begin": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int32,
+                                               ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "gpar_scaled_slice_summary": (ctypes.c_int, [_c_void_p, _c_void_p]),
+    "gpar_scaled_slice_stats": (ctypes.c_int, [_c_void_p, _c_void_p, ctypes.c_int32, _c_void_p]),
+    "gpar_scaled_slice_value": (ctypes.c_int, [_c_void_p, _c_void_p, _c_double_p]),
+    "gpar_scaled_slice_tangent_summary": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "gpar_scaled_slice_grad_partial": (ctypes.c_int, [_c_void_p, _c_void_p, ctypes.c_int32, _c_double_p]),
+    "gpar_scaled_slice_grad_finish": (ctypes.c_int, [_c_void_p, _c_double_p, _c_double_p, _c_double_p]),
     "gpar_group_fit": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64, _c_void_p, ctypes.c_int32, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "gpar_group_broadcast": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p]),

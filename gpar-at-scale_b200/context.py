@@ -187,6 +187,44 @@ class Context:
         self._check(self._lib.gpar_scaled_dtc_grad(self._h, int(k_time), int(k_out), dptr(th), ctypes.byref(val), dptr(g)))
         return val.value, g
 
+    # ---- one row slice of a scaled objective, collectives owned by the caller (parallel.scaled_dtc_row_sharded) ----
+    # buffers: anything with .data_ptr() (torch CUDA tensors on this context's device) or raw device addresses
+    @staticmethod
+    def _devptr(buf):
+        return ctypes.c_void_p(buf.data_ptr() if hasattr(buf, "data_ptr") else int(buf))
+
+    def scaled_slice_begin(self, k_time, k_out, theta, row_lo, grad=False):
+        """The context holds the FULL (t, y), Z and rows [row_lo, row_lo + N) of X -> (summary_count, stats_count)."""
+        th = as_f64(np.asarray(theta).ravel())
+        sc = ctypes.c_int64(); stc = ctypes.c_int64()
+        self._check(self._lib.gpar_scaled_slice_begin(self._h, int(k_time), int(k_out), dptr(th), int(row_lo), int(bool(grad)),
+                                                      ctypes.byref(sc), ctypes.byref(stc)))
+        return sc.value, stc.value
+
+    def scaled_slice_summary(self, summary):
+        self._check(self._lib.gpar_scaled_slice_summary(self._h, self._devptr(summary)))
+
+    def scaled_slice_stats(self, gathered, member, stats):
+        self._check(self._lib.gpar_scaled_slice_stats(self._h, self._devptr(gathered), int(member), self._devptr(stats)))
+
+    def scaled_slice_value(self, stats):
+        val = ctypes.c_double()
+        self._check(self._lib.gpar_scaled_slice_value(self._h, self._devptr(stats), ctypes.byref(val)))
+        return val.value
+
+    def scaled_slice_tangent_summary(self, stats, summary2):
+        self._check(self._lib.gpar_scaled_slice_tangent_summary(self._h, self._devptr(stats), self._devptr(summary2)))
+
+    def scaled_slice_grad_partial(self, gathered2, member):
+        s5 = np.zeros(5)
+        self._check(self._lib.gpar_scaled_slice_grad_partial(self._h, self._devptr(gathered2), int(member), dptr(s5)))
+        return s5
+
+    def scaled_slice_grad_finish(self, s5_total):
+        s5 = as_f64(np.asarray(s5_total).ravel()); val = ctypes.c_double(); g = np.zeros(5)
+        self._check(self._lib.gpar_scaled_slice_grad_finish(self._h, dptr(s5), ctypes.byref(val), dptr(g)))
+        return val.value, g
+
     def compute_q_u(self, k_time, k_out, params):
         p = as_f64(np.asarray(params).ravel())
         m_e = np.zeros(self.M)

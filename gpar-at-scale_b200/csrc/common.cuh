@@ -91,7 +91,7 @@ struct gpar_ctx {
     double *summary = nullptr, *init = nullptr, *G = nullptr, *g = nullptr; size_t summary_count = 0, stats_count = 0;
     // gradient mode (scaled_slice_grad_*): tangent tables of the slice, the tangent summaries / entering tangent states, and the
     // host-side pieces of the final assembly
-    bool grad = false; int64_t nfull = 0; int k_out = 0;
+    bool grad = false, begun = false; int64_t nfull = 0; int k_out = 0;
     const double *dtable = nullptr, *dalpha = nullptr; double *evec = nullptr, *panelD = nullptr, *summary2 = nullptr, *init2 = nullptr;
     double pv[5] = {0}, ex[5] = {0}, val = 0.0, raw[8 + 20] = {0}, fsums[6] = {0}, wq[4] = {0};      // wq: tr Q, <W,Q>, <X,Q>, c'c (whitened tail)
   } slice;

@@ -1588,4 +1588,64 @@ int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5]
   return GPAR_OK;
 }
 
+// ---- row slices for hosts that run ONE PROCESS PER DEVICE and own the collectives (torch.distributed, MPI, Julia Distributed) ----
+// The same phases gpar_group_scaled_dtc_sharded drives, with the two (gradient: three) exchanged arrays copied to / from
+// DEVICE buffers of the caller: summary -> all-gather -> stats -> all-reduce (sum) -> value
+// [gradient: -> tangent summary -> all-gather -> five partial sums -> all-reduce (sum, host) -> finish].
+int gpar_scaled_slice_begin(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t row_lo, int32_t want_grad,
+                            int64_t* summary_count, int64_t* stats_count) {
+  if (!ctx) return GPAR_ERR_INVALID;
+  if (!theta || !summary_count || !stats_count) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_begin: NULL argument");
+  CHK(scaled_slice_phase1(ctx, k_time, k_out, theta, row_lo, want_grad != 0));
+  *summary_count = (int64_t)ctx->slice.summary_count; *stats_count = (int64_t)ctx->slice.stats_count;
+  ctx->slice.begun = true;
+  return GPAR_OK;
+}
+static int slice_copy(gpar_ctx* ctx, void* dst, const void* src, size_t doubles) {
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(dst, src, doubles * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPAR_OK;
+}
+#define SLICE_BEGUN(who) \
+  if (!ctx) return GPAR_ERR_INVALID; \
+  if (!ctx->slice.begun) return gpar_fail(ctx, GPAR_ERR_INVALID, who ": gpar_scaled_slice_begin has not run on this context")
+int gpar_scaled_slice_summary(gpar_ctx* ctx, double* summary_dev) {
+  SLICE_BEGUN("scaled_slice_summary");
+  if (!summary_dev) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_summary: NULL buffer");
+  return slice_copy(ctx, summary_dev, ctx->slice.summary, ctx->slice.summary_count);
+}
+int gpar_scaled_slice_stats(gpar_ctx* ctx, const double* gathered_dev, int32_t member, double* stats_dev) {
+  SLICE_BEGUN("scaled_slice_stats");
+  if (!gathered_dev || !stats_dev || member < 0) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_stats: NULL buffer or negative member index");
+  CHK(scaled_slice_phase2(ctx, gathered_dev, member));
+  return slice_copy(ctx, stats_dev, ctx->slice.G, ctx->slice.stats_count);
+}
+int gpar_scaled_slice_value(gpar_ctx* ctx, const double* stats_dev, double* val) {
+  SLICE_BEGUN("scaled_slice_value");
+  if (!stats_dev || !val) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_value: NULL argument");
+  if (ctx->slice.grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_value: the slice was begun in gradient mode (use the tangent steps)");
+  CHK(slice_copy(ctx, ctx->slice.G, stats_dev, ctx->slice.stats_count));
+  return scaled_slice_finish(ctx, val);
+}
+int gpar_scaled_slice_tangent_summary(gpar_ctx* ctx, const double* stats_dev, double* summary2_dev) {
+  SLICE_BEGUN("scaled_slice_tangent_summary");
+  if (!stats_dev || !summary2_dev) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_tangent_summary: NULL argument");
+  if (!ctx->slice.grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_tangent_summary: the slice was begun without want_grad");
+  CHK(slice_copy(ctx, ctx->slice.G, stats_dev, ctx->slice.stats_count));
+  CHK(scaled_slice_grad_phase3(ctx));
+  return slice_copy(ctx, summary2_dev, ctx->slice.summary2, 3 * ctx->slice.summary_count);
+}
+int gpar_scaled_slice_grad_partial(gpar_ctx* ctx, const double* gathered2_dev, int32_t member, double s5[5]) {
+  SLICE_BEGUN("scaled_slice_grad_partial");
+  if (!gathered2_dev || !s5 || member < 0 || !ctx->slice.grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_grad_partial: NULL argument, negative member index or value-mode slice");
+  return scaled_slice_grad_phase4(ctx, gathered2_dev, member, s5);
+}
+int gpar_scaled_slice_grad_finish(gpar_ctx* ctx, const double s5_total[5], double* val, double grad[5]) {
+  SLICE_BEGUN("scaled_slice_grad_finish");
+  if (!s5_total || !val || !grad || !ctx->slice.grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_slice_grad_finish: NULL argument or value-mode slice");
+  return scaled_slice_grad_finish(ctx, s5_total, val, grad);
+}
+#undef SLICE_BEGUN
+
 }  // extern "C"

@@ -106,3 +106,49 @@ def best_per_output(tasks, minimum, minimizer):
         if v == v and (o not in best or v < best[o][0]):
             best[o] = (float(v), np.array(th), r)
     return best
+
+
+def row_slice_bounds(n_rows, world, align=1024):
+    """Consecutive row slices of one sequence for `world` ranks: equal shares, boundaries rounded up to multiples of `align`
+    (the library needs multiples of 4) -> world + 1 boundaries."""
+    return [min(n_rows, (n_rows * i // world + align - 1) // align * align) for i in range(world)] + [n_rows]
+
+
+def scaled_dtc_row_sharded(engine, k_time, k_out, theta, row_lo, grad=False, group=None, device=None):
+    """ONE scaled-GPAR objective (compute_gpar_dtc_objective, src/gp/dtc.jl:83-128) whose rows are sharded over the RANKS of
+    a torch.distributed group — one process per GPU, NCCL for the two (gradient: three) exchanges, every rank returns the
+    result.  `engine` is this rank's Context holding the full (t, y), the pseudo-inputs and rows [row_lo, row_lo + N) of the
+    inputs (its scaled_slice_* methods wrap the C ABI of the same name).  The carry of the M whitened columns crosses the
+    slice boundaries in an all-gather of slice summaries; (beta'beta, beta'alpha) are summed by an all-reduce; the gradient
+    adds an all-gather of tangent summaries and a 5-number all-reduce.  -> value or (value, gradient (5,))."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    kw = dict(dtype=torch.float64, device=device)
+
+    def done(t):          # the library works on its own stream: a collective's result must be complete before it is handed over
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        return t
+
+    def all_gather(x):
+        out = torch.empty(world * x.numel(), **kw)
+        dist.all_gather(list(out.chunk(world)), x, group=group)
+        return done(out)
+
+    sc, stc = engine.scaled_slice_begin(k_time, k_out, theta, row_lo, grad)
+    summary = torch.empty(sc, **kw)
+    engine.scaled_slice_summary(summary)
+    gathered = all_gather(summary)
+    stats = torch.empty(stc, **kw)
+    engine.scaled_slice_stats(gathered, rank, stats)
+    dist.all_reduce(stats, group=group)
+    done(stats)
+    if not grad:
+        return engine.scaled_slice_value(stats)
+    summary2 = torch.empty(3 * sc, **kw)
+    engine.scaled_slice_tangent_summary(stats, summary2)
+    gathered2 = all_gather(summary2)
+    s5 = torch.as_tensor(engine.scaled_slice_grad_partial(gathered2, rank), dtype=torch.float64).to(device if device is not None else "cpu")
+    dist.all_reduce(s5, group=group)
+    return engine.scaled_slice_grad_finish(done(s5).cpu().numpy())

@@ -235,6 +235,27 @@ int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[
  * tangent summaries; a poorly conditioned cov(u) switches every slice to whitened coordinates (a whitened copy of its panel). */
 int gpar_group_scaled_dtc_sharded(gpar_group* g, int k_time, int k_out, const double theta[5], const int64_t* row_lo, double* val, double* grad);
 
+/* The same row-sharded evaluation for hosts that run ONE PROCESS PER DEVICE and own the collectives (torch.distributed over
+ * NCCL — gpar-at-scale_b200/parallel.py; MPI; Julia `Distributed` workers): the context holds the full (t, y), the pseudo-inputs
+ * and rows [row_lo, row_lo + N) of the inputs, exactly as a member of gpar_group_scaled_dtc_sharded.  Every pointer named *_dev
+ * is a DEVICE pointer on the context's device; every call returns after its work is complete.
+ *   begin(theta, row_lo, want_grad) -> counts;  summary(summary_dev[summary_count])
+ *   [all-gather the summaries, rank-major -> gathered_dev[world * summary_count]]
+ *   stats(gathered_dev, member = rank, stats_dev[stats_count])       [all-reduce (sum) stats_dev]
+ *   value(stats_dev, &val)                                           — any (every) rank
+ * gradient (want_grad != 0) instead of value():
+ *   tangent_summary(stats_dev, summary2_dev[3 * summary_count])      [all-gather -> gathered2_dev[world * 3 * summary_count]]
+ *   grad_partial(gathered2_dev, member, s5[5] HOST)                  [sum the five numbers over the ranks]
+ *   grad_finish(s5_total, &val, grad[5]) */
+int gpar_scaled_slice_begin(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t row_lo, int32_t want_grad,
+                            int64_t* summary_count, int64_t* stats_count);
+int gpar_scaled_slice_summary(gpar_ctx* ctx, double* summary_dev);
+int gpar_scaled_slice_stats(gpar_ctx* ctx, const double* gathered_dev, int32_t member, double* stats_dev);
+int gpar_scaled_slice_value(gpar_ctx* ctx, const double* stats_dev, double* val);
+int gpar_scaled_slice_tangent_summary(gpar_ctx* ctx, const double* stats_dev, double* summary2_dev);
+int gpar_scaled_slice_grad_partial(gpar_ctx* ctx, const double* gathered2_dev, int32_t member, double s5[5]);
+int gpar_scaled_slice_grad_finish(gpar_ctx* ctx, const double s5_total[5], double* val, double grad[5]);
+
 /* One conditional-GP fit of the chain: inputs X (D x N ColVecs = the observed earlier outputs; D = 0: a time-only
  * state-space GP with 3 parameters, temporal_gp_inference.jl:69-82), pseudo-inputs Z (D x M), outputs y (N),
  * start point theta0 (the first 3 or 5 entries are used). */
