@@ -321,6 +321,72 @@ def test_fit_through_the_row_sharded_objective(ctx):
         api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), n_restarts=4)
 
 
+def test_scaled_slice_abi_for_one_process_per_gpu_hosts(ctx):
+    """gpar_scaled_slice_* (the row-sharded objective for hosts that own their collectives): (a) three slices on three
+    contexts of device 0, the all-gather / all-reduce done by hand on torch tensors; (b) parallel.scaled_dtc_row_sharded
+    through a world_size-1 NCCL process group.  Value and gradient equal the one-device entry points."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    import gpar_at_scale_b200 as gp
+    from gpar_at_scale_b200 import parallel
+    rng = np.random.default_rng(71)
+    n, m, d = 9001, 130, 2
+    t = np.sort(rng.uniform(0, n / 30, n)); X = rng.normal(size=(n, d)); Z = rng.normal(size=(m, d)); y = rng.normal(size=n)
+    th = rng.uniform(-1.0, 0.3, 5)
+    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(t); ctx.set_outputs(y); ctx.set_noise_vector(None)
+    v0 = ctx.scaled_dtc(3, 3, th); vg0, g0 = ctx.scaled_dtc_grad(3, 3, th)
+    dev = torch.device("cuda", 0)
+    kw = dict(dtype=torch.float64, device=dev)
+    b = [0, 2048, 2060, n]
+    engines = [gp.Context(0) for _ in range(3)]
+    try:
+        for i, e in enumerate(engines):
+            e.set_times(t); e.set_outputs(y); e.set_pseudo(Z); e.set_inputs(np.ascontiguousarray(X[b[i]:b[i + 1]]))
+        for grad in (False, True):
+            counts = [e.scaled_slice_begin(3, 3, th, b[i], grad) for i, e in enumerate(engines)]
+            sc, stc = counts[0]
+            assert all(c == (sc, stc) for c in counts)
+            summaries = [torch.empty(sc, **kw) for _ in engines]
+            for e, sm in zip(engines, summaries):
+                e.scaled_slice_summary(sm)
+            gathered = torch.cat(summaries)
+            stats = [torch.empty(stc, **kw) for _ in engines]
+            for i, (e, st) in enumerate(zip(engines, stats)):
+                e.scaled_slice_stats(gathered, i, st)
+            total = torch.stack(stats).sum(0)
+            if not grad:
+                for e in engines:                                   # every rank can finish
+                    assert abs(e.scaled_slice_value(total) - v0) <= 1e-11 * abs(v0)
+                continue
+            s2 = [torch.empty(3 * sc, **kw) for _ in engines]
+            for e, x in zip(engines, s2):
+                e.scaled_slice_tangent_summary(total, x)
+            g2 = torch.cat(s2)
+            s5 = sum(e.scaled_slice_grad_partial(g2, i) for i, e in enumerate(engines))
+            vg, gr = engines[0].scaled_slice_grad_finish(s5)
+            assert abs(vg - vg0) <= 1e-11 * abs(vg0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0)), (gr, g0)
+        with pytest.raises(gp.GparError):                            # a value-mode call on a gradient-mode slice
+            engines[0].scaled_slice_value(total)
+        with pytest.raises(gp.GparError):                            # begin has not run on this context
+            gp.Context(0).scaled_slice_summary(summaries[0])
+    finally:
+        for e in engines:
+            e.close()
+    # (b) the torch.distributed driver, one rank
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        assert parallel.row_slice_bounds(n, 1) == [0, n]
+        v = parallel.scaled_dtc_row_sharded(ctx, 3, 3, th, 0, device=dev)
+        vg, gr = parallel.scaled_dtc_row_sharded(ctx, 3, 3, th, 0, grad=True, device=dev)
+        assert abs(v - v0) <= 1e-11 * abs(v0) and abs(vg - vg0) <= 1e-11 * abs(vg0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0))
+    finally:
+        dist.destroy_process_group()
+
+
 def test_group_abi_error_behaviour():
     """Status codes and messages instead of crashes: duplicate devices, missing resident result, incomplete task,
     unknown optimiser, member without data."""
