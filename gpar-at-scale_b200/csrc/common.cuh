@@ -105,7 +105,7 @@ int gpar_fail(gpar_ctx* c, int code, const char* fmt, ...);
 // before the device->host copies of the results so that gpar_last_timing reports device work only.
 struct CallTimer {
   gpar_ctx* c; bool stopped = false;
-  explicit CallTimer(gpar_ctx* ctx) : c(ctx) { c->launches = 0; cudaEventRecord(c->ev0, c->stream); }
+  explicit CallTimer(gpar_ctx* ctx) : c(ctx) { c->launches = 0; c->slice.begun = false; cudaEventRecord(c->ev0, c->stream); }      // any other compute call ends a row-slice evaluation (shared scratch)
   void stop() { if (!stopped) { cudaEventRecord(c->ev1, c->stream); stopped = true; } }
   ~CallTimer() {
     stop();
@@ -264,7 +264,7 @@ int lgssm_filter_shared_seqmajor(gpar_ctx* ctx, int kind, double l, double s, do
 int merged_gather_test(gpar_ctx* ctx, double* dst_a, double* dst_b);
 // Entry points that overwrite the buffers the resident result lives in call this first, so that a later gpar_take_test /
 // gpar_group_broadcast fails loudly instead of reading stale memory.
-static inline void gpar_drop_result(gpar_ctx* c) { c->res_a = nullptr; c->res_b = nullptr; c->res_len = 0; }
+static inline void gpar_drop_result(gpar_ctx* c) { c->res_a = nullptr; c->res_b = nullptr; c->res_len = 0; c->slice.begun = false; }      // (a running row-slice evaluation points into the same scratch)
 // abi.cu: sufficient statistics of the plain DTC objective over the context's resident data slice (async on its stream)
 // whiten_vfe >= 0: the panels are whitened by the L_u this context's dtc_tail_prepare(vfe = whiten_vfe) computed, before the SYRK
 int dtc_slice_stats(gpar_ctx* ctx, int kernel, const GpParams& p, bool want_grad, double** stats, size_t* count, int whiten_vfe = -1);

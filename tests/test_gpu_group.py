@@ -370,6 +370,10 @@ def test_scaled_slice_abi_for_one_process_per_gpu_hosts(ctx):
             engines[0].scaled_slice_value(total)
         with pytest.raises(gp.GparError):                            # begin has not run on this context
             gp.Context(0).scaled_slice_summary(summaries[0])
+        engines[1].scaled_slice_begin(3, 3, th, b[1], False)
+        engines[1].lgssm_logpdf(gp.MATERN52, np.zeros(3))            # any other compute call ends the slice evaluation (shared scratch)
+        with pytest.raises(gp.GparError):
+            engines[1].scaled_slice_summary(summaries[1])
     finally:
         for e in engines:
             e.close()
