@@ -399,6 +399,16 @@ class Group:
                                                             lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(val), dptr(g5)))
         return (val.value, g5) if grad else val.value
 
+    def fit_sharded(self, k_time, k_out, row_lo, theta0, iterations=200, optimizer="neldermead"):
+        """One whole fit on the row-sharded objective (slices resident: load_row_slices), optimiser in the library (C++ twins of
+        neldermead.py / lbfgs.py) -> (minimum of the negated objective, minimizer (5,), f_calls)."""
+        lo = np.ascontiguousarray(row_lo, dtype=np.int64); th0 = as_f64(np.asarray(theta0).ravel())
+        assert th0.shape == (5,) and lo.shape == (len(self),)
+        fmin = ctypes.c_double(); xmin = np.zeros(5); calls = ctypes.c_int32()
+        self._check(self._lib.gpar_group_fit_sharded(self._h, int(k_time), int(k_out), lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), dptr(th0),
+                                                     {"neldermead": 0, "lbfgs": 1}[optimizer], int(iterations), ctypes.byref(fmin), dptr(xmin), ctypes.byref(calls)))
+        return fmin.value, xmin, calls.value
+
     def scaled_dtc(self, k_time, k_out, thetas, grad=False):
         th = as_f64(np.atleast_2d(thetas)); n = len(self)
         assert th.shape == (n, 5)

@@ -488,6 +488,42 @@ int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_tas
   return GPAR_OK;
 }
 
+// ONE fit with every device working on every evaluation: the rows of the objective are sharded over the members
+// (gpar_group_scaled_dtc_sharded on the slices already resident: full (t, y), Z and the member's rows of X — e.g. loaded once by
+// the caller) and the host optimiser of gpar_group_fit — Nelder-Mead (dtc.jl:58-61) or L-BFGS on the sharded gradient — drives
+// it.  For a single output too large for one device's memory or time budget.  minimizer[5], minimum (of the NEGATED objective).
+int gpar_group_fit_sharded(gpar_group* g, int k_time, int k_out, const int64_t* row_lo, const double theta0[5], int32_t optimizer, int32_t iterations,
+                           double* minimum, double* minimizer, int32_t* f_calls) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!row_lo || !theta0 || !minimum || !minimizer) return group_fail(g, GPAR_ERR_INVALID, "group_fit_sharded: row_lo, theta0, minimum and minimizer must be given");
+  if (optimizer != GPAR_OPT_NELDER_MEAD && optimizer != GPAR_OPT_LBFGS) return group_fail(g, GPAR_ERR_INVALID, "group_fit_sharded: unknown optimizer %d", optimizer);
+  int hard = GPAR_OK;
+  const double inf = std::numeric_limits<double>::infinity();
+  auto f = [&](const double* th) -> double {
+    double v = 0.0;
+    const int r = gpar_group_scaled_dtc_sharded(g, k_time, k_out, th, row_lo, &v, nullptr);
+    if (r == GPAR_ERR_NOT_POSDEF) return inf;
+    if (r != GPAR_OK) { if (hard == GPAR_OK) hard = r; return inf; }
+    return -v;
+  };
+  auto fgr = [&](const double* th, double* gr) -> double {
+    double v = 0.0;
+    const int r = gpar_group_scaled_dtc_sharded(g, k_time, k_out, th, row_lo, &v, gr);
+    if (r != GPAR_OK) { if (r != GPAR_ERR_NOT_POSDEF && hard == GPAR_OK) hard = r; for (int j = 0; j < 5; j++) gr[j] = 0.0; return inf; }
+    for (int j = 0; j < 5; j++) gr[j] = -gr[j];
+    return -v;
+  };
+  double xb[5], fb = std::numeric_limits<double>::quiet_NaN(); int calls = 0;
+  for (int j = 0; j < 5; j++) xb[j] = fb;
+  if (optimizer == GPAR_OPT_LBFGS) lbfgs(fgr, theta0, 5, iterations, 1e-6, 1e-10, xb, &fb, &calls);
+  else nelder_mead(f, theta0, 5, iterations, 1e-8, xb, &fb, &calls);
+  if (hard != GPAR_OK) return hard;          // g->err holds the message of the failing evaluation (or a later one of the same kind)
+  *minimum = fb;
+  for (int j = 0; j < 5; j++) minimizer[j] = xb[j];
+  if (f_calls) *f_calls = calls;
+  return GPAR_OK;
+}
+
 // Column d of the resident inputs X (N records of D doubles) <- col (host), or, with col == NULL, the context's
 // chain buffer (filled by gpar_group_broadcast): the predicted means of an earlier output become an input feature
 // of the later ones without a host round trip (GPAR_scaled_examples.jl:172).

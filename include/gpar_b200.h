@@ -272,6 +272,13 @@ enum gpar_optimizer { GPAR_OPT_NELDER_MEAD = 0, GPAR_OPT_LBFGS = 1 };   /* L-BFG
 int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
                    int32_t optimizer, int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
 
+/* ONE fit with every device working on every evaluation: the optimiser of gpar_group_fit on the ROW-SHARDED scaled objective
+ * (gpar_group_scaled_dtc_sharded; the slices — full (t, y), Z, the member's rows of X — are already resident).  For a single output
+ * too large for one device; replaces the loop src/gp/dtc.jl:58-61 for that output.  minimum (of the NEGATED objective), minimizer[5],
+ * f_calls (nullable). */
+int gpar_group_fit_sharded(gpar_group* g, int k_time, int k_out, const int64_t* row_lo, const double theta0[5], int32_t optimizer, int32_t iterations,
+                           double* minimum, double* minimizer, int32_t* f_calls);
+
 /* n doubles from member src into EVERY member's chain buffer (ncclBroadcast over NVLink): `host` if given, else the
  * resident result of its last gpar_lgssm_smooth / gpar_scaled_predict — for a merged train+test problem
  * (gpar_set_merged) the posterior means AT THE N* TEST LOCATIONS IN TEST ORDER (what gpar_take_test returns first;

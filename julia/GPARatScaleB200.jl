@@ -248,6 +248,14 @@ function group_scaled_dtc_sharded(g::Group, k_time, k_out, theta::Vector{Float64
     return grad ? (val[], gr) : val[]
 end
 
+# one whole fit (dtc.jl:58-61) on the row-sharded objective: every device works on every evaluation
+function group_fit_sharded(g::Group, k_time, k_out, row_lo::Vector{Int64}, theta0::Vector{Float64}; iterations::Integer = 200, optimizer::Symbol = :neldermead)
+    fmin = Ref{Float64}(0.0); xmin = zeros(5); calls = Ref{Int32}(0)
+    gcheck(g, ccall((:gpar_group_fit_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Int32, Int32, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
+                    g.h, kernel_code(k_time), kernel_code(k_out), row_lo, theta0, optimizer == :lbfgs ? 1 : 0, iterations, fmin, xmin, calls))
+    return fmin[], xmin, Int(calls[])
+end
+
 # whole Nelder-Mead fits of the chain's conditional GPs; Xs[k] (D x N) / Zs[k] (D x M) are `nothing` for a time-only task
 function group_fit(g::Group, t::Vector{Float64}, Xs, Zs, ys::Vector{Vector{Float64}}, theta0s::Vector{Vector{Float64}}, k_time, k_out; iterations::Integer = 200, optimizer::Symbol = :neldermead)
     nt = length(ys)

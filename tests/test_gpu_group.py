@@ -317,6 +317,25 @@ def test_fit_through_the_row_sharded_objective(ctx):
     finally:
         g.close()
     assert abs(l2.minimum - l1.minimum) <= 1e-6 * abs(l1.minimum), (l1.minimum, l2.minimum)
+    # the same fits with the optimiser inside the library (gpar_group_fit_sharded): the C++ Nelder-Mead / L-BFGS are operation-for-
+    # operation twins of the Python ones and the objective is the same call, so minima and evaluation counts are identical
+    from gpar_at_scale_b200 import neldermead, lbfgs
+    g = _loopback_group(2)
+    try:
+        lo = g.load_row_slices(X, Z, t, y)
+        th0 = np.array([1.0, 0.0, 0.0, 0.0, -1.0])
+        fmin, xmin, calls = g.fit_sharded(3, 3, lo, th0, iterations=25)
+        rp = neldermead.optimize(lambda p_: -g.scaled_dtc_sharded(3, 3, p_, lo), th0, iterations=25)
+        assert fmin == rp.minimum and np.array_equal(xmin, rp.minimizer) and calls == rp.f_calls
+        fl, xl, cl = g.fit_sharded(3, 3, lo, th0, iterations=6, optimizer="lbfgs")
+
+        def fg(p_):
+            v, gr = g.scaled_dtc_sharded(3, 3, p_, lo, grad=True)
+            return -v, -gr
+        rl = lbfgs.optimize(fg, th0, iterations=6)
+        assert abs(fl - rl.minimum) <= 1e-12 * abs(rl.minimum) and np.allclose(xl, rl.minimizer, rtol=0, atol=1e-10)
+    finally:
+        g.close()
     with pytest.raises(ValueError):
         api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), n_restarts=4)
 
