@@ -445,8 +445,11 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 inference_input_locations, out_kernel_structure=None, time_kernel_structure=None,
                                 i_log_time_l=None, i_log_time_var=None, i_log_out_l=None, i_log_out_var=None, i_log_noise_sigma=None,
                                 optimization_time_limit=1000.0, debug=False, ctx=None, rng=None, iterations=1000, nsamples=100,
-                                opt_params=None, sampler="device", seed=0, device_merge=True, n_restarts=1, speculative=False):
+                                opt_params=None, sampler="device", seed=0, device_merge=True, n_restarts=1, speculative=False, group=None):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
+    group (NEW; a context.Group): the two N x M stages — the fit and compute_q_u — run with their rows sharded over the group's
+    devices (gpar_group_scaled_dtc_sharded / gpar_group_compute_q_u_sharded); the draws from q(u) (host, from `rng`) and the
+    prediction itself need no N x M array and stay on `ctx`.
     n_restarts / speculative: passed to get_optim_scaled_gpar_params (batched candidates; NEW).
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
@@ -466,12 +469,20 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                                   i_log_time_l=i_log_time_l, i_log_time_var=i_log_time_var, i_log_out_l=i_log_out_l,
                                                   i_log_out_var=i_log_out_var, i_log_noise_sigma=i_log_noise_sigma,
                                                   optimization_time_limit=optimization_time_limit, debug=debug, ctx=ctx, rng=rng,
-                                                  iterations=iterations, n_restarts=n_restarts, speculative=speculative)
+                                                  iterations=iterations, n_restarts=n_restarts, speculative=speculative, group=group)
     opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma = opt_params
     params = np.array([opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma])
     # q(u) ~ p(u | y)  (:63-73)
-    ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(time_loc); ctx.set_outputs(outputs); ctx.set_noise_vector(None)
-    if sampler == "device":
+    if group is not None:
+        row_lo = group.load_row_slices(X, Z, time_loc, outputs)
+        m_e, Dinv, U_u = group.compute_q_u_sharded(time_kernel_structure.code, out_kernel_structure.code, params, row_lo)
+        sampler = "host"
+        ctx.set_pseudo(Z)
+    else:
+        ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(time_loc); ctx.set_outputs(outputs); ctx.set_noise_vector(None)
+    if group is not None:
+        pass                                       # (m_e, inv(D), U_u) came from the sharded evaluation
+    elif sampler == "device":
         ctx.sample_q_u(time_kernel_structure.code, out_kernel_structure.code, params, seed, nsamples)
     else:
         m_e, Dinv, U_u = ctx.compute_q_u(time_kernel_structure.code, out_kernel_structure.code, params)

@@ -399,6 +399,15 @@ class Group:
                                                             lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(val), dptr(g5)))
         return (val.value, g5) if grad else val.value
 
+    def compute_q_u_sharded(self, k_time, k_out, params, row_lo):
+        """compute_q_u on the row slices resident on the members -> (m_e (M,), inv(D) (M, M), U_u (M, M)) as Context.compute_q_u."""
+        p = as_f64(np.asarray(params).ravel()); lo = np.ascontiguousarray(row_lo, dtype=np.int64)
+        M = self.members[0].M
+        m_e = np.zeros(M); Dinv = np.zeros((M, M), order="F"); U_u = np.zeros((M, M), order="F")
+        self._check(self._lib.gpar_group_compute_q_u_sharded(self._h, int(k_time), int(k_out), dptr(p), lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                             dptr(m_e), dptr(Dinv), dptr(U_u)))
+        return m_e, Dinv, U_u
+
     def fit_sharded(self, k_time, k_out, row_lo, theta0, iterations=200, optimizer="neldermead"):
         """One whole fit on the row-sharded objective (slices resident: load_row_slices), optimiser in the library (C++ twins of
         neldermead.py / lbfgs.py) -> (minimum of the negated objective, minimizer (5,), f_calls)."""

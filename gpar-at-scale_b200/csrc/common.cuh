@@ -91,7 +91,7 @@ struct gpar_ctx {
     double *summary = nullptr, *init = nullptr, *G = nullptr, *g = nullptr; size_t summary_count = 0, stats_count = 0;
     // gradient mode (scaled_slice_grad_*): tangent tables of the slice, the tangent summaries / entering tangent states, and the
     // host-side pieces of the final assembly
-    bool grad = false, begun = false; int64_t nfull = 0; int k_out = 0;
+    bool grad = false, begun = false, qu = false; int64_t nfull = 0; int k_out = 0;
     const double *dtable = nullptr, *dalpha = nullptr; double *evec = nullptr, *panelD = nullptr, *summary2 = nullptr, *init2 = nullptr;
     double pv[5] = {0}, ex[5] = {0}, val = 0.0, raw[8 + 20] = {0}, fsums[6] = {0}, wq[4] = {0};      // wq: tr Q, <W,Q>, <X,Q>, c'c (whitened tail)
   } slice;
@@ -307,7 +307,8 @@ int dtc_tail_whitened(gpar_ctx* ctx, const GpParams& p, int vfe, double jitter, 
                       double* val, double* grad, WhitenedTail* out);
 // scaled.cu: a row slice of the scaled objective (the context holds the full (t, y) and rows [lo, lo + N) of X); group.cu
 // all-gathers ctx->slice.summary between phase 1 and 2 and all-reduces ctx->slice.G (stats_count doubles) before finish
-int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad = false);
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad = false, bool qu = false);   // qu: theta = the positive parameters of compute_q_u, bare Cuu
+int scaled_slice_qu_finish(gpar_ctx* ctx, double* m_e, double* Dinv, double* U_u);
 // gradient mode: after the all-reduce every member runs the tail (P, w) and the zero-start tangent responses of its chunks and
 // leaves 3 tangent summaries (ctx->slice.summary2, 3 x summary_count doubles) for a second all-gather; phase 4 finishes the
 // tangent pass from the gathered summaries and returns the member's five partial sums; finish assembles on one member

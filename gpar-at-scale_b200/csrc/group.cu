@@ -488,6 +488,53 @@ int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_tas
   return GPAR_OK;
 }
 
+// compute_q_u (gpar_scaled_inference.jl:141-196) with the rows sharded like gpar_group_scaled_dtc_sharded: the same two collectives,
+// bare Cuu (usually poorly conditioned: every member then whitens its panel by L_u), the M x M tail on member 0.
+// m_e[M], Dinv[M x M], U_u[M x M] column-major, as gpar_compute_q_u.  With it a single output whose N x M panel exceeds one device
+// can be fitted (gpar_group_fit_sharded) AND predicted: the draws from q(u) and gpar_scaled_predict need no N x M array.
+int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, double* m_e, double* Dinv, double* U_u) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!params || !row_lo || !m_e || !Dinv || !U_u) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: NULL argument");
+  const int n = (int)g->ctx.size();
+  gpar_ctx* c0 = g->ctx[0];
+  int64_t expect = 0;
+  for (int i = 0; i < n; i++) {
+    gpar_ctx* c = g->ctx[i];
+    if (c->M != c0->M || c->Dz != c0->Dz || c->Nt != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: member %d holds other pseudo-inputs or times than member 0", i);
+    if (row_lo[i] != expect) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: member %d starts at row %lld, the slices before it end at %lld", i, (long long)row_lo[i], (long long)expect);
+    expect += c->N;
+  }
+  if (expect != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: the slices cover %lld rows, the sequence has %lld", (long long)expect, (long long)c0->Nt);
+  std::vector<int> st;
+  auto members_ok = [&]() -> int {
+    for (int i = 0; i < n; i++)
+      if (st[i] != GPAR_OK) return group_fail(g, st[i], "member %d (device %d): %s", i, g->dev[i], gpar_last_error(g->ctx[i]));
+    return GPAR_OK;
+  };
+  run_members(g, st, [&](int i) { return scaled_slice_phase1(g->ctx[i], k_time, k_out, params, row_lo[i], false, true); });
+  int rc = members_ok();
+  if (rc != GPAR_OK) return rc;
+  const size_t sc = c0->slice.summary_count;
+  std::vector<const double*> sp(n); std::vector<double*> rp(n), stats(n);
+  for (int i = 0; i < n; i++) {
+    GCU(cudaSetDevice(g->dev[i]));
+    GCU(g->recv[i].reserve(sc * n * sizeof(double)));
+    sp[i] = g->ctx[i]->slice.summary; rp[i] = g->recv[i].as<double>(); stats[i] = g->ctx[i]->slice.G;
+  }
+  rc = group_allgather(g, sp, rp, sc);
+  if (rc != GPAR_OK) return rc;
+  run_members(g, st, [&](int i) { return scaled_slice_phase2(g->ctx[i], rp[i], i); });
+  rc = members_ok();
+  if (rc != GPAR_OK) return rc;
+  rc = group_allreduce_sum(g, stats, c0->slice.stats_count);
+  if (rc != GPAR_OK) return rc;
+  for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
+  GCU(cudaSetDevice(g->dev[0]));
+  rc = scaled_slice_qu_finish(c0, m_e, Dinv, U_u);
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  return GPAR_OK;
+}
+
 // ONE fit with every device working on every evaluation: the rows of the objective are sharded over the members
 // (gpar_group_scaled_dtc_sharded on the slices already resident: full (t, y), Z and the member's rows of X — e.g. loaded once by
 // the caller) and the host optimiser of gpar_group_fit — Nelder-Mead (dtc.jl:58-61) or L-BFGS on the sharded gradient — drives

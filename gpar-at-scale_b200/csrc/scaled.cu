@@ -1076,23 +1076,29 @@ static PanelHook make_whitened_copy_hook(gpar_ctx* ctx, const double* Lu, const 
 }
 
 // ---- row-sliced evaluation: the three steps group.cu drives around its two collectives --------------------------------
-struct SliceTailBufs { double *Lu, *Bm, *V, *Tm, *cvec, *sc; int* dinfo; };
-static int slice_tail_bufs(gpar_ctx* ctx, SliceTailBufs* b) {
+struct SliceTailBufs { double *Lu, *Bm, *Uu, *V, *Tm, *cvec, *sc; int* dinfo; };
+static int slice_tail_bufs(gpar_ctx* ctx, SliceTailBufs* b, bool qu = false) {
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
-  CU(ctx->dense.reserve((4 * MM + 2 * (size_t)M + 16) * sizeof(double)));
-  b->Lu = ctx->dense.as<double>(); b->Bm = b->Lu + MM; b->V = b->Bm + MM; b->Tm = b->V + MM; b->cvec = b->Tm + MM; b->sc = b->cvec + 2 * M;
+  CU(ctx->dense.reserve(((qu ? 5 : 4) * MM + 2 * (size_t)M + 16) * sizeof(double)));
+  b->Lu = ctx->dense.as<double>(); b->Bm = b->Lu + MM;
+  if (qu) { b->Uu = b->Bm + MM; b->V = b->Uu + MM; }      // q(u) mode: room for U_u = L_u' (the layout of q_u_factors)
+  else { b->Uu = nullptr; b->V = b->Bm + MM; }
+  b->Tm = b->V + MM; b->cvec = b->Tm + MM; b->sc = b->cvec + 2 * M;
   CU(ctx->info.reserve(4 * sizeof(int)));
   b->dinfo = ctx->info.as<int>();
   return GPAR_OK;
 }
-int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad) {
+int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad, bool qu) {
   CU(cudaSetDevice(ctx->device));
   gpar_drop_result(ctx);
   if (ctx->N < 1 || ctx->M < 1 || ctx->D != ctx->Dz) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: inputs (this member's rows) and pseudo-inputs must be set, same dimension");
   if (ctx->Nt != ctx->Ny || ctx->ybatch < 1) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: every member holds the FULL times and outputs (%lld times, %lld outputs)", (long long)ctx->Nt, (long long)ctx->Ny);
   if (lo < 0 || lo % 4 != 0 || lo + ctx->N > ctx->Nt) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled_dtc_sharded: rows [%lld, %lld) of %lld: the first row of a slice must be a multiple of 4", (long long)lo, (long long)(lo + ctx->N), (long long)ctx->Nt);
   gpar_ctx::SliceState& sl = ctx->slice;
+  if (qu && grad) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled slice: q(u) mode has no gradient");
   for (int i = 0; i < 5; i++) { sl.ex[i] = exp(theta[i]); sl.pv[i] = sl.ex[i] + 1e-3; }      // unpack_gpar (util.jl:45-55)
+  if (qu) for (int i = 0; i < 5; i++) sl.pv[i] = theta[i];      // compute_q_u takes the positive parameters themselves (gpar_scaled_inference.jl:141-150)
+  sl.qu = qu;
   const double* pv = sl.pv;
   const double time_l = pv[0], time_s = pv[1] * pv[1], out_l = pv[2], out_s = pv[3] * pv[3], noise = pv[4] * pv[4];
   sl.k_out = k_out;
@@ -1101,8 +1107,10 @@ int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta
     CHK(dtc_tail_prepare(ctx, k_out, p, 0, noise, true));
   } else {
     SliceTailBufs b;
-    CHK(slice_tail_bufs(ctx, &b));
-    CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, noise, b.Lu, b.V, b.dinfo, b.sc + 4));
+    CHK(slice_tail_bufs(ctx, &b, qu));
+    CU(cudaMemsetAsync(b.dinfo, 0, 4 * sizeof(int), ctx->stream));
+    // q(u): bare Cuu, no jitter (gpar_scaled_inference.jl:157-159); objective: cov(u) = Kuu + noise I (dtc.jl:35,119)
+    CHK(factor_cov_u_side(ctx, k_out, out_l, out_s, qu ? 0.0 : noise, b.Lu, b.V, b.dinfo, b.sc + 4));
   }
   sl.robust = false;
   switch (k_time) {
@@ -1125,7 +1133,7 @@ int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member) {
     }
   }
   SliceTailBufs b;
-  CHK(slice_tail_bufs(ctx, &b));
+  CHK(slice_tail_bufs(ctx, &b, ctx->slice.qu));
   // the conditioning decision is a function of L_u alone, which every member computes identically
   PanelHook hook = make_whitening_hook(ctx, b.Lu, b.sc + 4, &ctx->slice.robust);
   switch (ctx->slice.D) {
@@ -1137,6 +1145,7 @@ int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member) {
 // on the member that holds the all-reduced (G, g)
 int scaled_slice_finish(gpar_ctx* ctx, double* dtc) {
   CU(cudaSetDevice(ctx->device));
+  if (ctx->slice.qu) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled slice: begun in q(u) mode");
   SliceTailBufs b;
   CHK(slice_tail_bufs(ctx, &b));
   const gpar_ctx::SliceState& sl = ctx->slice;
@@ -1497,6 +1506,39 @@ int gpar_scaled_dtc_grad(gpar_ctx* ctx, int k_time, int k_out, const double thet
 // Shared front half of compute_q_u and the sampler: L_u = chol(Cuu) (bare, gpar_scaled_inference.jl:157-159),
 // L_D = chol(B_ef B_ef' + I) (:187), m_e = L_D^-T L_D^-1 L_u^-1 g (:189) — all left on the device.
 struct QuFactors { double *Lu, *LD, *Uu, *me, *tmp; int* dinfo; };
+// U_u = L_u' (:159 `cholesky(Cuu).U`), inv(D) = L_D^-T L_D^-1 (:192), copies to the host, factorisation checks
+static int q_u_finish(gpar_ctx* ctx, const QuFactors& q, double* m_e, double* Dinv, double* U_u) {
+  const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
+  LAUNCH(ctx, lower_to_upper_kernel, (int)((MM + 255) / 256), 256, 0, q.Lu, M, q.Uu);
+  // triangular inverse, then one product (the full symmetric matrix comes out)
+  CHK(dla_trtri(ctx, M, q.LD, M, q.tmp, M));
+  CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, q.tmp, M, q.tmp, M, 0.0, q.LD, M, DLA_A_UPPER | DLA_B_LOWER));
+  int hinfo[3];
+  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(m_e, q.me, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(Dinv, q.LD, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(U_u, q.Uu, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0 || hinfo[2] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
+  return GPAR_OK;
+}
+}  // extern "C"
+// q(u) from the all-reduced statistics of a row-sliced evaluation (scaled_slice_phase1(qu = true) / phase2 on every member)
+int scaled_slice_qu_finish(gpar_ctx* ctx, double* m_e, double* Dinv, double* U_u) {
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->slice.qu) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled slice: not begun in q(u) mode");
+  SliceTailBufs b;
+  CHK(slice_tail_bufs(ctx, &b, true));
+  const gpar_ctx::SliceState& sl = ctx->slice;
+  const int M = (int)ctx->M;
+  // D = B_ef B_ef' + I, L_D, L_D^-1 L_u^-1 g (the objective's tail, jitter-free) ... and the second solve of :189
+  CHK(scaled_value_tail(ctx, b.Lu, b.Bm, b.V, b.Tm, b.cvec, b.sc, b.dinfo, sl.G, sl.g, sl.robust));
+  CHK(dla_trsv(ctx, true, M, b.Bm, M, b.cvec));
+  QuFactors q; q.Lu = b.Lu; q.LD = b.Bm; q.Uu = b.Uu; q.me = b.cvec; q.tmp = b.Tm; q.dinfo = b.dinfo;
+  return q_u_finish(ctx, q, m_e, Dinv, U_u);
+}
+extern "C" {
 static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params[5], QuFactors* q) {
   const double time_l = params[0], time_s = params[1] * params[1], out_l = params[2], out_s = params[3] * params[3], noise = params[4] * params[4];
   const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
@@ -1538,21 +1580,8 @@ int gpar_compute_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5
   CallTimer timer(ctx); gpar_drop_result(ctx);
   QuFactors q;
   CHK(q_u_factors(ctx, k_time, k_out, params, &q));
-  const int M = (int)ctx->M; const size_t MM = (size_t)M * M;
-  LAUNCH(ctx, lower_to_upper_kernel, (int)((MM + 255) / 256), 256, 0, q.Lu, M, q.Uu);
-  // inv(D) = L_D^-T L_D^-1 (:192): triangular inverse, then one product (the full symmetric matrix comes out)
-  CHK(dla_trtri(ctx, M, q.LD, M, q.tmp, M));
-  CHK(dla_gemm(ctx, true, false, M, M, M, 1.0, q.tmp, M, q.tmp, M, 0.0, q.LD, M, DLA_A_UPPER | DLA_B_LOWER));
-  timer.stop();
-  int hinfo[3];
-  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(m_e, q.me, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(Dinv, q.LD, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(U_u, q.Uu, MM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
-  if (hinfo[1] != 0 || hinfo[2] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
-  return GPAR_OK;
+  timer.stop();       // (the device work of q_u_finish is short; its copies are not timed)
+  return q_u_finish(ctx, q, m_e, Dinv, U_u);
 }
 
 // S seeded draws eps_j ~ q_u = MvNormal(m_e, inv(D)) and the weights the prediction needs,

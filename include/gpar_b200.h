@@ -272,6 +272,13 @@ enum gpar_optimizer { GPAR_OPT_NELDER_MEAD = 0, GPAR_OPT_LBFGS = 1 };   /* L-BFG
 int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_task* tasks, int32_t ntasks, int k_time, int k_out,
                    int32_t optimizer, int32_t iterations, double* minimum, double* minimizer, int32_t* f_calls, int32_t* member_of);
 
+/* compute_q_u (src/gp/gpar_scaled_inference.jl:141-196; gpar_compute_q_u) with the rows sharded over the members exactly like
+ * gpar_group_scaled_dtc_sharded (same resident slices, same two collectives; bare Cuu — every member whitens its panel by L_u when
+ * it is poorly conditioned).  m_e[M], Dinv[M x M], U_u[M x M] column-major.  A single output whose N x M panel exceeds one device can
+ * then be fitted (gpar_group_fit_sharded) and predicted: sampling q(u) and gpar_scaled_predict need no N x M array. */
+int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo,
+                                   double* m_e, double* Dinv, double* U_u);
+
 /* ONE fit with every device working on every evaluation: the optimiser of gpar_group_fit on the ROW-SHARDED scaled objective
  * (gpar_group_scaled_dtc_sharded; the slices — full (t, y), Z, the member's rows of X — are already resident).  For a single output
  * too large for one device; replaces the loop src/gp/dtc.jl:58-61 for that output.  minimum (of the NEGATED objective), minimizer[5],

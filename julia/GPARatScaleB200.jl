@@ -248,6 +248,14 @@ function group_scaled_dtc_sharded(g::Group, k_time, k_out, theta::Vector{Float64
     return grad ? (val[], gr) : val[]
 end
 
+# compute_q_u (gpar_scaled_inference.jl:141-196) on the row slices resident on the members -> (m_e, inv(D), U_u)
+function group_compute_q_u_sharded(g::Group, k_time, k_out, params::Vector{Float64}, row_lo::Vector{Int64}, M::Integer)
+    m_e = zeros(M); Dinv = zeros(M, M); U_u = zeros(M, M)
+    gcheck(g, ccall((:gpar_group_compute_q_u_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    g.h, kernel_code(k_time), kernel_code(k_out), params, row_lo, m_e, Dinv, U_u))
+    return m_e, Dinv, U_u
+end
+
 # one whole fit (dtc.jl:58-61) on the row-sharded objective: every device works on every evaluation
 function group_fit_sharded(g::Group, k_time, k_out, row_lo::Vector{Int64}, theta0::Vector{Float64}; iterations::Integer = 200, optimizer::Symbol = :neldermead)
     fmin = Ref{Float64}(0.0); xmin = zeros(5); calls = Ref{Int32}(0)

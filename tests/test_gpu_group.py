@@ -238,6 +238,16 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
             del os.environ["GPAR_GRAD_WHITENED"]
         vg0, g0 = ctx.scaled_dtc_grad(3, 3, th)
         assert abs(vgw - vg0) <= 1e-10 * abs(vg0) and np.max(np.abs(gw - g0)) <= 1e-8 * np.max(np.abs(g0)), (gw, g0)
+        # q(u) on the same slices (bare Cuu: the whitened-panel path on every member) against the one-device compute_q_u
+        params = np.array([0.9, 1.2, 1.4, 0.8, 0.12])
+        m0, D0, U0 = ctx.compute_q_u(3, 3, params)
+        m1, D1, U1 = g.compute_q_u_sharded(3, 3, params, lo)
+        # (two float64 evaluations with different summation orders: the whitened panel A = U_u' \ beta' carries ~ eps cond(U_u),
+        # which inv(D) = (I + A A')^-1 amplifies by cond(D))
+        eps = np.finfo(float).eps
+        tolq = max(1e-8, 100 * eps * np.linalg.cond(U0) ** 2); told = max(tolq, 100 * eps * np.linalg.cond(U0) * np.linalg.cond(D0))
+        rel = lambda a, b_: np.max(np.abs(a - b_)) / np.max(np.abs(b_))
+        assert rel(U1, U0) <= 1e-12 and rel(m1, m0) <= tolq and rel(D1, D0) <= told, (rel(m1, m0), rel(D1, D0), tolq, told)
         if nmem > 1:
             bad = lo.copy(); bad[1] += 4
             with pytest.raises(gp.GparError, match="starts at row"):
@@ -338,6 +348,17 @@ def test_fit_through_the_row_sharded_objective(ctx):
         g.close()
     with pytest.raises(ValueError):
         api.get_optim_scaled_gpar_params(X, Z, t, y, group=object(), n_restarts=4)
+    # prediction with the two N x M stages (fit skipped here, q(u)) on the sharded path: the same host draws (same rng seed) through
+    # the one-device q(u) and through the sharded q(u) give the same predictive means / stds
+    ts = t[:500] + 0.5 / 30.0; Xs = np.sin(0.3 * ts)[:, None]
+    kwp = dict(opt_params=p1, nsamples=20, sampler="host", ctx=ctx)
+    mean1, std1 = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, rng=np.random.default_rng(3), **kwp)
+    g = _loopback_group(3)
+    try:
+        mean3, std3 = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, rng=np.random.default_rng(3), group=g, **kwp)
+    finally:
+        g.close()
+    assert np.max(np.abs(mean3 - mean1)) <= 1e-6 * np.max(np.abs(mean1)) and np.max(np.abs(std3 - std1)) <= 1e-6 * np.max(std1)
 
 
 def test_scaled_slice_abi_for_one_process_per_gpu_hosts(ctx):
