@@ -297,6 +297,18 @@ def test_group_scaled_dtc_row_sharded_devices(ctx):
         vg0, g0 = ctx.scaled_dtc_grad(3, 3, th)
         vg, gr = g.scaled_dtc_sharded(3, 3, th, lo, grad=True)
         assert abs(vg - vg0) <= 1e-11 * abs(vg0) and np.max(np.abs(gr - g0)) <= 1e-9 * np.max(np.abs(g0)), (gr, g0)
+        # q(u) and a short fit over NCCL
+        params = np.array([0.9, 1.2, 1.4, 0.8, 0.12])
+        m0, D0, U0 = ctx.compute_q_u(3, 3, params)
+        m1, D1, U1 = g.compute_q_u_sharded(3, 3, params, lo)
+        eps = np.finfo(float).eps
+        tolq = max(1e-8, 100 * eps * np.linalg.cond(U0) ** 2); told = max(tolq, 100 * eps * np.linalg.cond(U0) * np.linalg.cond(D0))
+        rel = lambda a, b_: np.max(np.abs(a - b_)) / np.max(np.abs(b_))
+        assert rel(U1, U0) <= 1e-12 and rel(m1, m0) <= tolq and rel(D1, D0) <= told
+        from gpar_at_scale_b200 import neldermead
+        fmin, xmin, calls = g.fit_sharded(3, 3, lo, th, iterations=5)
+        rp = neldermead.optimize(lambda p_: -g.scaled_dtc_sharded(3, 3, p_, lo), th, iterations=5)
+        assert fmin == rp.minimum and np.array_equal(xmin, rp.minimizer) and calls == rp.f_calls
     finally:
         g.close()
 
