@@ -80,6 +80,8 @@ SIGNATURES = {
     "gpar_group_fit": (ctypes.c_int, [_c_void_p, _c_double_p, ctypes.c_int64, _c_void_p, ctypes.c_int32, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int32, ctypes.c_int32, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "gpar_group_compute_q_u_sharded": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_int64), _c_double_p, _c_double_p, _c_double_p]),
+    "gpar_group_sample_q_u_sharded": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint64, ctypes.c_int32,
+                                                     _c_double_p, _c_double_p]),
     "gpar_group_fit_sharded": (ctypes.c_int, [_c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), _c_double_p, ctypes.c_int32, ctypes.c_int32,
                                               _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int32)]),
     "gpar_group_broadcast": (ctypes.c_int, [_c_void_p, ctypes.c_int32, _c_double_p, ctypes.c_int64, _c_double_p]),

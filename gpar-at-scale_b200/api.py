@@ -448,8 +448,8 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
                                 opt_params=None, sampler="device", seed=0, device_merge=True, n_restarts=1, speculative=False, group=None):
     """gpar_scaled_inference.jl:20-136 -> (inferred_outputs, inferred_stds) at the inference locations.
     group (NEW; a context.Group): the two N x M stages — the fit and compute_q_u — run with their rows sharded over the group's
-    devices (gpar_group_scaled_dtc_sharded / gpar_group_compute_q_u_sharded); the draws from q(u) (host, from `rng`) and the
-    prediction itself need no N x M array and stay on `ctx`.
+    devices (gpar_group_scaled_dtc_sharded / gpar_group_sample_q_u_sharded or _compute_q_u_sharded); the prediction itself needs
+    no N x M array and stays on `ctx`.
     n_restarts / speculative: passed to get_optim_scaled_gpar_params (batched candidates; NEW).
     `opt_params` (positive 5-tuple) skips the optimisation (used by the chain driver, which fits all
     outputs in parallel first); `rng` seeds the q_u draws the reference takes from Julia's global RNG."""
@@ -473,10 +473,13 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma = opt_params
     params = np.array([opt_time_l, opt_time_var, opt_out_l, opt_out_var, opt_noise_sigma])
     # q(u) ~ p(u | y)  (:63-73)
+    W_group = None
     if group is not None:
         row_lo = group.load_row_slices(X, Z, time_loc, outputs)
-        m_e, Dinv, U_u = group.compute_q_u_sharded(time_kernel_structure.code, out_kernel_structure.code, params, row_lo)
-        sampler = "host"
+        if sampler == "device":       # seeded Philox draws on the member that holds the summed statistics: no host numerics
+            W_group, _ = group.sample_q_u_sharded(time_kernel_structure.code, out_kernel_structure.code, params, row_lo, seed, nsamples)
+        else:
+            m_e, Dinv, U_u = group.compute_q_u_sharded(time_kernel_structure.code, out_kernel_structure.code, params, row_lo)
         ctx.set_pseudo(Z)
     else:
         ctx.set_inputs(X); ctx.set_pseudo(Z); ctx.set_times(time_loc); ctx.set_outputs(outputs); ctx.set_noise_vector(None)
@@ -493,7 +496,7 @@ def get_gpar_scaled_predictions(input_locations, pseudo_input_locations, time_lo
     input_loc_star = np.concatenate([X, Xs], axis=0)[sorting_perm]
     outputs_star = np.concatenate([outputs, np.zeros(len(inference_time_loc))])[sorting_perm]
     noise_vector_star = np.concatenate([np.full(ntr, opt_noise_sigma ** 2), np.full(len(inference_time_loc), 1e10)])[sorting_perm]   # :100-103
-    W = None
+    W = W_group
     if sampler != "device":
         # draws eps_j ~ MvNormal(m_e, inv(D)) (:94) and the weights U_u \ eps_j (:96) — tiny M x S host work
         Lc = np.linalg.cholesky(0.5 * (Dinv + Dinv.T))

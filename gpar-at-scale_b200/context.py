@@ -408,6 +408,15 @@ class Group:
                                                              dptr(m_e), dptr(Dinv), dptr(U_u)))
         return m_e, Dinv, U_u
 
+    def sample_q_u_sharded(self, k_time, k_out, params, row_lo, seed, nsamples):
+        """Seeded device draws from the q(u) of the row-sharded evaluation -> (W = U_u \\ eps, eps), each (M, S)."""
+        p = as_f64(np.asarray(params).ravel()); lo = np.ascontiguousarray(row_lo, dtype=np.int64)
+        M = self.members[0].M
+        W = np.zeros((M, nsamples), order="F"); E = np.zeros((M, nsamples), order="F")
+        self._check(self._lib.gpar_group_sample_q_u_sharded(self._h, int(k_time), int(k_out), dptr(p), lo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                            int(seed), int(nsamples), dptr(W), dptr(E)))
+        return W, E
+
     def fit_sharded(self, k_time, k_out, row_lo, theta0, iterations=200, optimizer="neldermead"):
         """One whole fit on the row-sharded objective (slices resident: load_row_slices), optimiser in the library (C++ twins of
         neldermead.py / lbfgs.py) -> (minimum of the negated objective, minimizer (5,), f_calls)."""

@@ -309,6 +309,7 @@ int dtc_tail_whitened(gpar_ctx* ctx, const GpParams& p, int vfe, double jitter, 
 // all-gathers ctx->slice.summary between phase 1 and 2 and all-reduces ctx->slice.G (stats_count doubles) before finish
 int scaled_slice_phase1(gpar_ctx* ctx, int k_time, int k_out, const double theta[5], int64_t lo, bool grad = false, bool qu = false);   // qu: theta = the positive parameters of compute_q_u, bare Cuu
 int scaled_slice_qu_finish(gpar_ctx* ctx, double* m_e, double* Dinv, double* U_u);
+int scaled_slice_qu_sample(gpar_ctx* ctx, uint64_t seed, int32_t S, double* W_out, double* eps_out);
 // gradient mode: after the all-reduce every member runs the tail (P, w) and the zero-start tangent responses of its chunks and
 // leaves 3 tangent summaries (ctx->slice.summary2, 3 x summary_count doubles) for a second all-gather; phase 4 finishes the
 // tangent pass from the gathered summaries and returns the member's five partial sums; finish assembles on one member

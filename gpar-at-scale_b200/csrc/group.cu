@@ -492,19 +492,17 @@ int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_tas
 // bare Cuu (usually poorly conditioned: every member then whitens its panel by L_u), the M x M tail on member 0.
 // m_e[M], Dinv[M x M], U_u[M x M] column-major, as gpar_compute_q_u.  With it a single output whose N x M panel exceeds one device
 // can be fitted (gpar_group_fit_sharded) AND predicted: the draws from q(u) and gpar_scaled_predict need no N x M array.
-int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, double* m_e, double* Dinv, double* U_u) {
-  if (!g) return GPAR_ERR_INVALID;
-  if (!params || !row_lo || !m_e || !Dinv || !U_u) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: NULL argument");
+static int group_qu_stats(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, const char* who) {
   const int n = (int)g->ctx.size();
   gpar_ctx* c0 = g->ctx[0];
   int64_t expect = 0;
   for (int i = 0; i < n; i++) {
     gpar_ctx* c = g->ctx[i];
-    if (c->M != c0->M || c->Dz != c0->Dz || c->Nt != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: member %d holds other pseudo-inputs or times than member 0", i);
-    if (row_lo[i] != expect) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: member %d starts at row %lld, the slices before it end at %lld", i, (long long)row_lo[i], (long long)expect);
+    if (c->M != c0->M || c->Dz != c0->Dz || c->Nt != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "%s: member %d holds other pseudo-inputs or times than member 0", who, i);
+    if (row_lo[i] != expect) return group_fail(g, GPAR_ERR_INVALID, "%s: member %d starts at row %lld, the slices before it end at %lld", who, i, (long long)row_lo[i], (long long)expect);
     expect += c->N;
   }
-  if (expect != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: the slices cover %lld rows, the sequence has %lld", (long long)expect, (long long)c0->Nt);
+  if (expect != c0->Nt) return group_fail(g, GPAR_ERR_INVALID, "%s: the slices cover %lld rows, the sequence has %lld", who, (long long)expect, (long long)c0->Nt);
   std::vector<int> st;
   auto members_ok = [&]() -> int {
     for (int i = 0; i < n; i++)
@@ -530,8 +528,27 @@ int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const d
   if (rc != GPAR_OK) return rc;
   for (int i = 0; i < n; i++) { GCU(cudaSetDevice(g->dev[i])); GCU(cudaStreamSynchronize(g->ctx[i]->stream)); }
   GCU(cudaSetDevice(g->dev[0]));
-  rc = scaled_slice_qu_finish(c0, m_e, Dinv, U_u);
-  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(c0));
+  return GPAR_OK;
+}
+int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, double* m_e, double* Dinv, double* U_u) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!params || !row_lo || !m_e || !Dinv || !U_u) return group_fail(g, GPAR_ERR_INVALID, "compute_q_u_sharded: NULL argument");
+  int rc = group_qu_stats(g, k_time, k_out, params, row_lo, "compute_q_u_sharded");
+  if (rc != GPAR_OK) return rc;
+  rc = scaled_slice_qu_finish(g->ctx[0], m_e, Dinv, U_u);
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(g->ctx[0]));
+  return GPAR_OK;
+}
+// S seeded draws from that q(u) on member 0's device (gpar_sample_q_u's Philox sampler) -> W = U_u \ eps (M x S, host; also resident on
+// member 0 for a gpar_scaled_predict(W = NULL) there), eps_out (nullable).  No host numerics between the sharded statistics and W.
+int gpar_group_sample_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, uint64_t seed, int32_t S,
+                                  double* W_out, double* eps_out) {
+  if (!g) return GPAR_ERR_INVALID;
+  if (!params || !row_lo || S < 1) return group_fail(g, GPAR_ERR_INVALID, "sample_q_u_sharded: params and row_lo must be given, S >= 1");
+  int rc = group_qu_stats(g, k_time, k_out, params, row_lo, "sample_q_u_sharded");
+  if (rc != GPAR_OK) return rc;
+  rc = scaled_slice_qu_sample(g->ctx[0], seed, S, W_out, eps_out);
+  if (rc != GPAR_OK) return group_fail(g, rc, "member 0: %s", gpar_last_error(g->ctx[0]));
   return GPAR_OK;
 }
 

@@ -1523,6 +1523,27 @@ static int q_u_finish(gpar_ctx* ctx, const QuFactors& q, double* m_e, double* Di
   if (hinfo[1] != 0 || hinfo[2] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
   return GPAR_OK;
 }
+// z ~ N(0, I) (Philox), eps = m_e + L_D^-T z, W = L_u^-T eps from the factors on the device; W stays resident (ctx->qW)
+static int q_u_sample(gpar_ctx* ctx, const QuFactors& q, uint64_t seed, int32_t S, double* W_out, double* eps_out) {
+  const int M = (int)ctx->M; const int64_t total = (int64_t)M * S;
+  CU(ctx->qW.reserve((size_t)2 * total * sizeof(double)));
+  double* W = ctx->qW.as<double>(); double* E = W + total;
+  LAUNCH(ctx, philox_normal_kernel, (int)(((total + 1) / 2 + 255) / 256), 256, 0, E, total, seed);
+  CHK(dla_trsm_left(ctx, true, M, S, q.LD, M, E, M));
+  LAUNCH(ctx, add_column_vector_kernel, (int)((total + 255) / 256), 256, 0, E, q.me, M, total);
+  CU(cudaMemcpyAsync(W, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CHK(dla_trsm_left(ctx, true, M, S, q.Lu, M, W, M));
+  int hinfo[2];
+  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  if (W_out) CU(cudaMemcpyAsync(W_out, W, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (eps_out) CU(cudaMemcpyAsync(eps_out, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->qW_M = 0; ctx->qW_S = 0;
+  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
+  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
+  ctx->qW_M = M; ctx->qW_S = S;
+  return GPAR_OK;
+}
 }  // extern "C"
 // q(u) from the all-reduced statistics of a row-sliced evaluation (scaled_slice_phase1(qu = true) / phase2 on every member)
 int scaled_slice_qu_finish(gpar_ctx* ctx, double* m_e, double* Dinv, double* U_u) {
@@ -1537,6 +1558,19 @@ int scaled_slice_qu_finish(gpar_ctx* ctx, double* m_e, double* Dinv, double* U_u
   CHK(dla_trsv(ctx, true, M, b.Bm, M, b.cvec));
   QuFactors q; q.Lu = b.Lu; q.LD = b.Bm; q.Uu = b.Uu; q.me = b.cvec; q.tmp = b.Tm; q.dinfo = b.dinfo;
   return q_u_finish(ctx, q, m_e, Dinv, U_u);
+}
+// ... or S seeded draws W = U_u \ eps_j from it (gpar_sample_q_u's sampler on the member that holds the summed statistics)
+int scaled_slice_qu_sample(gpar_ctx* ctx, uint64_t seed, int32_t S, double* W_out, double* eps_out) {
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->slice.qu) return gpar_fail(ctx, GPAR_ERR_INVALID, "scaled slice: not begun in q(u) mode");
+  SliceTailBufs b;
+  CHK(slice_tail_bufs(ctx, &b, true));
+  const gpar_ctx::SliceState& sl = ctx->slice;
+  const int M = (int)ctx->M;
+  CHK(scaled_value_tail(ctx, b.Lu, b.Bm, b.V, b.Tm, b.cvec, b.sc, b.dinfo, sl.G, sl.g, sl.robust));
+  CHK(dla_trsv(ctx, true, M, b.Bm, M, b.cvec));
+  QuFactors q; q.Lu = b.Lu; q.LD = b.Bm; q.Uu = b.Uu; q.me = b.cvec; q.tmp = b.Tm; q.dinfo = b.dinfo;
+  return q_u_sample(ctx, q, seed, S, W_out, eps_out);
 }
 extern "C" {
 static int q_u_factors(gpar_ctx* ctx, int k_time, int k_out, const double params[5], QuFactors* q) {
@@ -1596,25 +1630,8 @@ int gpar_sample_q_u(gpar_ctx* ctx, int k_time, int k_out, const double params[5]
   CallTimer timer(ctx); gpar_drop_result(ctx);
   QuFactors q;
   CHK(q_u_factors(ctx, k_time, k_out, params, &q));
-  const int M = (int)ctx->M; const int64_t total = (int64_t)M * S;
-  CU(ctx->qW.reserve((size_t)2 * total * sizeof(double)));
-  double* W = ctx->qW.as<double>(); double* E = W + total;
-  LAUNCH(ctx, philox_normal_kernel, (int)(((total + 1) / 2 + 255) / 256), 256, 0, E, total, seed);
-  CHK(dla_trsm_left(ctx, true, M, S, q.LD, M, E, M));
-  LAUNCH(ctx, add_column_vector_kernel, (int)((total + 255) / 256), 256, 0, E, q.me, M, total);
-  CU(cudaMemcpyAsync(W, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  CHK(dla_trsm_left(ctx, true, M, S, q.Lu, M, W, M));
   timer.stop();
-  int hinfo[2];
-  CU(cudaMemcpyAsync(hinfo, q.dinfo, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
-  if (W_out) CU(cudaMemcpyAsync(W_out, W, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (eps_out) CU(cudaMemcpyAsync(eps_out, E, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  ctx->qW_M = 0; ctx->qW_S = 0;
-  if (hinfo[0] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(Cuu) failed: leading minor %d is not positive definite", hinfo[0]);
-  if (hinfo[1] != 0) return gpar_fail(ctx, GPAR_ERR_NOT_POSDEF, "cholesky(D) failed: leading minor %d is not positive definite", hinfo[1]);
-  ctx->qW_M = M; ctx->qW_S = S;
-  return GPAR_OK;
+  return q_u_sample(ctx, q, seed, S, W_out, eps_out);
 }
 
 // ---- row slices for hosts that run ONE PROCESS PER DEVICE and own the collectives (torch.distributed, MPI, Julia Distributed) ----

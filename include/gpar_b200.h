@@ -278,6 +278,10 @@ int gpar_group_fit(gpar_group* g, const double* t, int64_t N, const gpar_fit_tas
  * then be fitted (gpar_group_fit_sharded) and predicted: sampling q(u) and gpar_scaled_predict need no N x M array. */
 int gpar_group_compute_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo,
                                    double* m_e, double* Dinv, double* U_u);
+/* ... and S seeded draws from that q(u) (gpar_sample_q_u's device sampler on member 0): W = U_u \ eps_j (M x S column-major, host
+ * copy; nullable) for gpar_scaled_predict, eps_out (nullable). */
+int gpar_group_sample_q_u_sharded(gpar_group* g, int k_time, int k_out, const double params[5], const int64_t* row_lo, uint64_t seed, int32_t S,
+                                  double* W_out, double* eps_out);
 
 /* ONE fit with every device working on every evaluation: the optimiser of gpar_group_fit on the ROW-SHARDED scaled objective
  * (gpar_group_scaled_dtc_sharded; the slices — full (t, y), Z, the member's rows of X — are already resident).  For a single output

@@ -256,6 +256,14 @@ function group_compute_q_u_sharded(g::Group, k_time, k_out, params::Vector{Float
     return m_e, Dinv, U_u
 end
 
+# S seeded draws W = U_u \\ eps_j from the q(u) of the row-sharded evaluation (device sampler on member 0)
+function group_sample_q_u_sharded(g::Group, k_time, k_out, params::Vector{Float64}, row_lo::Vector{Int64}, M::Integer, seed::Integer, S::Integer)
+    W = zeros(M, S); E = zeros(M, S)
+    gcheck(g, ccall((:gpar_group_sample_q_u_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Int64}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}),
+                    g.h, kernel_code(k_time), kernel_code(k_out), params, row_lo, seed, S, W, E))
+    return W, E
+end
+
 # one whole fit (dtc.jl:58-61) on the row-sharded objective: every device works on every evaluation
 function group_fit_sharded(g::Group, k_time, k_out, row_lo::Vector{Int64}, theta0::Vector{Float64}; iterations::Integer = 200, optimizer::Symbol = :neldermead)
     fmin = Ref{Float64}(0.0); xmin = zeros(5); calls = Ref{Int32}(0)

@@ -248,6 +248,10 @@ def test_group_scaled_dtc_row_sharded_loopback(ctx, nmem):
         tolq = max(1e-8, 100 * eps * np.linalg.cond(U0) ** 2); told = max(tolq, 100 * eps * np.linalg.cond(U0) * np.linalg.cond(D0))
         rel = lambda a, b_: np.max(np.abs(a - b_)) / np.max(np.abs(b_))
         assert rel(U1, U0) <= 1e-12 and rel(m1, m0) <= tolq and rel(D1, D0) <= told, (rel(m1, m0), rel(D1, D0), tolq, told)
+        # the seeded device sampler on the sharded statistics: the draws of gpar_sample_q_u with the same seed
+        W0, E0 = ctx.sample_q_u(3, 3, params, 11, 7, return_host=True)
+        W1, E1 = g.sample_q_u_sharded(3, 3, params, lo, 11, 7)
+        assert rel(E1, E0) <= 10 * told and rel(W1, W0) <= 10 * told * np.linalg.cond(U0), (rel(E1, E0), rel(W1, W0))
         if nmem > 1:
             bad = lo.copy(); bad[1] += 4
             with pytest.raises(gp.GparError, match="starts at row"):
@@ -365,12 +369,16 @@ def test_fit_through_the_row_sharded_objective(ctx):
     ts = t[:500] + 0.5 / 30.0; Xs = np.sin(0.3 * ts)[:, None]
     kwp = dict(opt_params=p1, nsamples=20, sampler="host", ctx=ctx)
     mean1, std1 = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, rng=np.random.default_rng(3), **kwp)
+    kwd = dict(opt_params=p1, nsamples=20, sampler="device", seed=5, ctx=ctx)
+    mean1d, std1d = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, **kwd)
     g = _loopback_group(3)
     try:
         mean3, std3 = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, rng=np.random.default_rng(3), group=g, **kwp)
+        mean3d, std3d = api.get_gpar_scaled_predictions(X, Z, t, y, ts, Xs, group=g, **kwd)      # seeded device draws on member 0
     finally:
         g.close()
     assert np.max(np.abs(mean3 - mean1)) <= 1e-6 * np.max(np.abs(mean1)) and np.max(np.abs(std3 - std1)) <= 1e-6 * np.max(std1)
+    assert np.max(np.abs(mean3d - mean1d)) <= 1e-6 * np.max(np.abs(mean1d)) and np.max(np.abs(std3d - std1d)) <= 1e-6 * np.max(std1d)
 
 
 def test_scaled_slice_abi_for_one_process_per_gpu_hosts(ctx):
