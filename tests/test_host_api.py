@@ -136,3 +136,39 @@ def test_nelder_mead_lock_step_batch_equals_separate_runs():
         assert np.array_equal(runs[k].minimizer, one.minimizer) and runs[k].minimum == one.minimum
         assert runs[k].iterations == one.iterations and runs[k].f_calls == one.f_calls and runs[k].converged == one.converged
     assert max(sizes) <= 7 * 4 and sizes[0] == 7 * 4
+
+
+def test_row_sharded_fit_on_a_stand_in_group():
+    """api.get_optim_scaled_gpar_params(group=...) is host logic over two Group methods (load_row_slices, scaled_dtc_sharded):
+    with a stand-in group whose 'objective' is a quadratic, Nelder-Mead and L-BFGS reach its optimum, the slices are loaded
+    once, and the options that need the batched single-device entry points are refused before anything is touched."""
+    class FakeGroup:
+        def __init__(self):
+            self.loaded = 0; self.evals = 0
+        def load_row_slices(self, X, Z, t, y):
+            self.loaded += 1; self.shapes = (X.shape, Z.shape, len(t), len(y))
+            return np.array([0, 1024], dtype=np.int64)
+        def scaled_dtc_sharded(self, k_time, k_out, theta, row_lo, grad=False):
+            self.evals += 1
+            assert k_time == gp.MATERN52 and k_out == gp.MATERN52 and list(row_lo) == [0, 1024]
+            d = np.asarray(theta) - np.array([0.5, -0.2, 0.1, 0.3, -1.0])
+            v = -float(d @ d)                                   # the library maximises the objective: nlml = -v
+            return (v, -2.0 * d) if grad else v
+    n = 2000
+    X = np.zeros((n, 2)); Z = np.zeros((7, 2)); t = np.arange(n, dtype=float); y = np.zeros(n)
+    g = FakeGroup()
+    p, r = api.get_optim_scaled_gpar_params(X, Z, t, y, group=g, iterations=400, return_result=True,
+                                            i_log_time_l=0.0, i_log_time_var=0.0, i_log_out_l=0.0, i_log_out_var=0.0, i_log_noise_sigma=0.0)
+    assert g.loaded == 1 and g.shapes == ((n, 2), (7, 2), n, n) and g.evals == r.f_calls
+    assert np.allclose(r.minimizer, [0.5, -0.2, 0.1, 0.3, -1.0], atol=1e-4) and p == pytest.approx(api.unpack_gpar(r.minimizer))
+    g2 = FakeGroup()
+    _, r2 = api.get_optim_scaled_gpar_params(X, Z, t, y, group=g2, optimizer="lbfgs", iterations=50, return_result=True,
+                                             i_log_time_l=0.0, i_log_time_var=0.0, i_log_out_l=0.0, i_log_out_var=0.0, i_log_noise_sigma=0.0)
+    assert np.allclose(r2.minimizer, [0.5, -0.2, 0.1, 0.3, -1.0], atol=1e-6)
+    for bad in (dict(n_restarts=4), dict(speculative=True)):
+        g3 = FakeGroup()
+        with pytest.raises(ValueError):
+            api.get_optim_scaled_gpar_params(X, Z, t, y, group=g3, **bad)
+        assert g3.loaded == 0
+    assert parallel.row_slice_bounds(10_000, 4) == [0, 3072, 5120, 8192, 10_000]
+    assert parallel.row_slice_bounds(100, 3, align=4) == [0, 36, 68, 100]
