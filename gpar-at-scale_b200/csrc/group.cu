@@ -11,7 +11,9 @@
 //     dynamically, longest first,
 //   * all-gathers the SCALARS (status, value, gradient / minimum, minimiser) with NCCL so that every device holds
 //     the table, and broadcasts posterior means down the GPAR chain (GPAR_scaled_examples.jl:172) with ncclBroadcast
-//     over NVLink.  No collective touches the data path.
+//     over NVLink.  No collective touches the data path of these task-sharded calls;
+//   * evaluates ONE objective whose rows are sharded over the members (gpar_group_*_sharded): per-slice statistics, one or two
+//     small all-gathers (filter carries) and one all-reduce of the M x M statistics per evaluation.
 // NCCL is bound at run time (dlopen of libnccl.so.2: the library has no link-time dependency on it).
 #include "common.cuh"
 #include "optim_host.h"
@@ -237,7 +239,7 @@ int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* th
 // ONE plain DTC / VFE objective whose data are sharded over the members by rows (SURVEY 8e "intra-output N-sharding"):
 // every member evaluates the sufficient statistics G = Kuf Kfu, H, g, h, y'y of ITS slice (same pseudo-inputs on every
 // member; slices may differ in length), ONE ncclAllReduce sums the M x M + ... buffer over NVLink, member 0 runs the tail.
-// The only data-path collective of the library: 8 (2 M^2 + 2 M + 1) bytes per evaluation (16.8 MB at M = 1024).
+// 8 (2 M^2 + 2 M + 1) bytes per evaluation (16.8 MB at M = 1024); the row-sharded entry points are the only ones with a data-path collective.
 int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad) {
   if (!g) return GPAR_ERR_INVALID;
   if (!theta || !val) return group_fail(g, GPAR_ERR_INVALID, "dtc_logpdf_sharded: theta and val must not be NULL");

@@ -198,7 +198,8 @@ int gpar_exact_posterior(gpar_ctx* ctx, int k_time, int k_out, const double* the
  * The shards are the reference's own: per-output conditional GPs (examples/GPAR_scaled_examples.jl:132-175 fits
  * output i on the OBSERVED outputs < i, so the fits are independent) and hyper-parameter restarts (util.jl:128-134).
  * A group owns one context per device; load each member's data with the gpar_set_* calls on gpar_group_ctx(g, i).
- * No collective touches the data path: NCCL (bound at run time from libnccl.so.2) all-gathers the scalars —
+ * No collective touches the data path of these task-sharded calls (the *_sharded entry points below shard the ROWS of one
+ * objective instead and exchange slice summaries / M x M statistics): NCCL (bound at run time from libnccl.so.2) all-gathers the scalars —
  * (status, value, gradient) or (minimum, minimiser) — so that every device holds the table, and broadcasts posterior
  * means down the GPAR chain (GPAR_scaled_examples.jl:172).  Group calls are blocking and not thread-safe. */
 typedef struct gpar_group gpar_group;
@@ -219,7 +220,7 @@ int gpar_group_scaled_dtc(gpar_group* g, int k_time, int k_out, const double* th
 /* ONE plain DTC / VFE objective (gpar_dtc_logpdf) whose data rows are sharded over the members — SURVEY 8e's optional
  * intra-output N-sharding: load slice i of (X, y) and the SAME pseudo-inputs on member i; each member evaluates the
  * sufficient statistics of its slice, one ncclAllReduce (8 (2 M^2 + 2 M + 1) bytes) sums them over NVLink, member 0
- * runs the M x M tail.  The only data-path collective of the library. */
+ * runs the M x M tail.  (The row-sharded entry points are the only ones with a data-path collective.) */
 int gpar_group_dtc_logpdf_sharded(gpar_group* g, int kernel, const double theta[3], int vfe, double jitter, double* val, double* grad);
 
 /* ONE scaled-GPAR objective (gpar_scaled_dtc; compute_gpar_dtc_objective, src/gp/dtc.jl:83-128) whose ROWS are sharded
