@@ -250,9 +250,9 @@ int launch_panel_residual(gpar_ctx* ctx, const double* panel, const double* w, c
 // panel_gemm.cu: out[n, m'] = sum_m C[m', m] in[n, m] on DMMA (C pre-arranged by launch_dense_to_operand / launch_tri_operand)
 int launch_dense_to_operand(gpar_ctx* ctx, const double* Q, int M, int Mpad, double* Aop);
 int panel_gemm_run(gpar_ctx* ctx, const double* Aop, int Mpad, const double* in, int64_t in_groups, double* out, int64_t out_groups,
-                   int64_t g_lo, int64_t ng, int64_t out_g0, int mt_lo, int n_mt, bool triangular);
+                   int64_t g_lo, int64_t ng, int64_t out_g0, int mt_lo, int n_mt, bool triangular, const double* in_diag = nullptr);
 int launch_tri_operand(gpar_ctx* ctx, const double* L, int M, int Mpad, double* Yd, double* Aop);
-int panel_tri_solve_run(gpar_ctx* ctx, const double* Aop, int Mpad, double* panel, int64_t groups, int64_t g_lo, int64_t ng);
+int panel_tri_solve_run(gpar_ctx* ctx, const double* Aop, int Mpad, double* panel, int64_t groups, int64_t g_lo, int64_t ng, const double* src = nullptr);
 // smooth_shared.cu: smoothed means of Sp (multiple of 128) TIME-MAJOR sequences yt[n][Sp] that share one model
 int lgssm_smooth_shared(gpar_ctx* ctx, int kind, double l, double s, double noise, int64_t N, const double* t, const double* y1,
                         const double* rvec, const double* yt, int Sp, double* mean_t);
@@ -319,7 +319,7 @@ int scaled_slice_grad_finish(gpar_ctx* ctx, const double s5[5], double* dtc, dou
 int scaled_slice_phase2(gpar_ctx* ctx, const double* gathered, int member);
 int scaled_slice_finish(gpar_ctx* ctx, double* dtc);
 // scaled.cu: conditioning decision and the panel whitening by L_u (see gpar_needs_whitened_panel)
-int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
+int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu, const double* src = nullptr);   // src: out of place
 bool gpar_needs_whitened_panel(const double minmax[2]);
 // Gradient of a value entry point by the 4-point central stencil (h = 1e-2 in the raw log-space parameters; env
 // GPAR_FD_STEP): the fallback of the analytic-gradient entry points when cov(u) is too poorly conditioned for the

@@ -41,6 +41,8 @@ constexpr size_t SMEM_BYTES = (size_t)2 * STAGES * STAGE_BYTES + 2 * STAGES * 8 
 struct GemmArgs {
   const double* Aop;          // the small matrix in operand layout, tile stride a_stride doubles
   const double* in;           // input panel, m-tile stride in_stride doubles
+  const double* in_diag;      // triangular solves out of place (nullable): the DIAGONAL tile row (j == m') is read from this panel
+                              // (the un-solved right-hand side), the tile rows j < m' from `in` (= out: already solved)
   double* out;                // output panel, m'-tile stride out_stride doubles
   int64_t a_stride, in_stride, out_stride;
   int64_t g_lo, ng;           // 4-step groups [g_lo, g_lo + ng) of the input panel
@@ -74,8 +76,9 @@ panel_gemm_kernel(const GemmArgs a) {
       const int gvalid = (int)((a.g_lo + a.ng - g0 < TILE_GROUPS) ? a.g_lo + a.ng - g0 : TILE_GROUPS);
       const int kb1 = a.triangular ? (mt + 1) * (GPAR_TILE / GPAR_KT) : a.kb_full;
       const double* arow = a.Aop + (int64_t)mt * a.a_stride;
-      const double* brow = a.in + ((g0 + lane) * GPAR_TILE) * 4;
+      const int64_t boffs = ((g0 + lane) * GPAR_TILE) * 4;
       for (int kb = 0; kb < kb1; kb++) {
+        const double* brow = ((a.in_diag && (kb >> 2) == mt) ? a.in_diag : a.in) + boffs;
         mbar_wait(&empty[stage], phase ^ 1u);
         if (lane == 0) {
           mbar_expect_tx(&full[stage], (uint32_t)(STAGE_BYTES + gvalid * PIECE_DOUBLES * 8));
@@ -218,10 +221,10 @@ int launch_dense_to_operand(gpar_ctx* ctx, const double* Q, int M, int Mpad, dou
 // out groups [g_lo - out_g0, ...) <- in groups [g_lo, g_lo + ng) times the operand matrix, m'-tiles [mt_lo, mt_lo + n_mt).
 // in_groups / out_groups: 4-step groups per m-tile of the two panels (their tile strides are groups * 512 doubles).
 int panel_gemm_run(gpar_ctx* ctx, const double* Aop, int Mpad, const double* in, int64_t in_groups, double* out, int64_t out_groups,
-                   int64_t g_lo, int64_t ng, int64_t out_g0, int mt_lo, int n_mt, bool triangular) {
+                   int64_t g_lo, int64_t ng, int64_t out_g0, int mt_lo, int n_mt, bool triangular, const double* in_diag) {
   if (ng <= 0 || n_mt <= 0) return GPAR_OK;
   GemmArgs a;
-  a.Aop = Aop; a.in = in; a.out = out;
+  a.Aop = Aop; a.in = in; a.out = out; a.in_diag = in_diag;
   a.a_stride = (int64_t)(Mpad / 4) * GPAR_TILE * 4; a.in_stride = in_groups * GPAR_TILE * 4; a.out_stride = out_groups * GPAR_TILE * 4;
   a.g_lo = g_lo; a.ng = ng; a.out_g0 = out_g0; a.mt_lo = mt_lo; a.n_mt = n_mt; a.kb_full = Mpad / GPAR_KT; a.triangular = triangular ? 1 : 0;
   const int64_t ntiles = ((ng + TILE_GROUPS - 1) / TILE_GROUPS) * n_mt;
@@ -245,8 +248,9 @@ int launch_tri_operand(gpar_ctx* ctx, const double* L, int M, int Mpad, double* 
 
 // panel rows [4 g_lo, 4 (g_lo + ng)) <- (L^-1 row')' in place: one launch per tile row, each contracting over the
 // already solved tile rows above it.
-int panel_tri_solve_run(gpar_ctx* ctx, const double* Aop, int Mpad, double* panel, int64_t groups, int64_t g_lo, int64_t ng) {
+// src (nullable): solve OUT OF PLACE — the right-hand sides are read from `src` (same shape), the solution goes to `panel`.
+int panel_tri_solve_run(gpar_ctx* ctx, const double* Aop, int Mpad, double* panel, int64_t groups, int64_t g_lo, int64_t ng, const double* src) {
   const int T = Mpad / GPAR_TILE;
-  for (int i = 0; i < T; i++) CHK(panel_gemm_run(ctx, Aop, Mpad, panel, groups, panel, groups, g_lo, ng, 0, i, 1, true));
+  for (int i = 0; i < T; i++) CHK(panel_gemm_run(ctx, Aop, Mpad, panel, groups, panel, groups, g_lo, ng, 0, i, 1, true, src));
   return GPAR_OK;
 }

@@ -22,7 +22,6 @@
 #include <chrono>
 #include <limits>
 
-int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu);
 bool gpar_needs_whitened_panel(const double minmax[2]);
 bool scaled_small_applicable(const gpar_ctx* ctx);
 int scaled_small_batch(gpar_ctx* ctx, int k_time, int k_out, const double* thetas, int ncand, double* vals, int* codes);
@@ -984,12 +983,12 @@ int launch_diag_minmax(gpar_ctx* ctx, const double* L, int M, double* out2) {
 }
 // panel (operand layout, N x M) <- panel L_u^-T  i.e. every row beta_n' becomes (L_u^-1 beta_n)': the blocked triangular
 // solve of panel_gemm.cu (inverted 128 x 128 diagonal blocks, DMMA products over the tile rows above), in place
-int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu) {
+int panel_left_solve(gpar_ctx* ctx, double* panel, int64_t Npad, int Mpad, int M, const double* Lu, const double* src) {
   const int T = Mpad / GPAR_TILE; const int64_t NB4 = Npad / 4;
   CU(ctx->panelB.reserve(((size_t)Mpad * Mpad + (size_t)T * GPAR_TILE * GPAR_TILE) * sizeof(double)));
   double* Aop = ctx->panelB.as<double>(); double* Yd = Aop + (size_t)Mpad * Mpad;
   CHK(launch_tri_operand(ctx, Lu, M, Mpad, Yd, Aop));
-  return panel_tri_solve_run(ctx, Aop, Mpad, panel, NB4, 0, NB4);
+  return panel_tri_solve_run(ctx, Aop, Mpad, panel, NB4, 0, NB4, src);
 }
 
 // helpers shared with zgrad.cu
@@ -1068,8 +1067,7 @@ static PanelHook make_whitened_copy_hook(gpar_ctx* ctx, const double* Lu, const 
     }
     CU(ctx->panelA.reserve((size_t)Npad * Mpad * sizeof(double)));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-    CU(cudaMemcpyAsync(ctx->panelA.p, panel, (size_t)Npad * Mpad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CHK(panel_left_solve(ctx, ctx->panelA.as<double>(), Npad, Mpad, (int)ctx->M, Lu));
+    CHK(panel_left_solve(ctx, ctx->panelA.as<double>(), Npad, Mpad, (int)ctx->M, Lu, panel));      // out of place: beta stays, no copy
     panel = ctx->panelA.as<double>();
     return GPAR_OK;
   };
